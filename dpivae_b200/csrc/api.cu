@@ -1,0 +1,528 @@
+// C ABI of libdpivae_b200.so (include/dpivae_b200.h): handle management, shared-memory /
+// workspace planning and the launch sequences of the hot path.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/dpivae_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace dpv {
+int configure_dec_kernel();
+int configure_enc_kernels();
+}  // namespace dpv
+
+using namespace dpv;
+
+static thread_local std::string g_err;
+static int fail(const std::string& m) {
+  g_err = m;
+  return 1;
+}
+#define CUDA_OK(expr)                                                                         \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) return fail(std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+struct dpivae_model {
+  dpivae_model_desc_t d;
+  int sm_count = 0;
+  DecParams dec;
+  EncParams enc;
+  int n_enc_units = 0;     // encoder units come first in enc.u, prior units after
+  int H_tot = 0, O_tot = 0;
+  float* d_frozen = nullptr;
+  unsigned char* d_owner = nullptr;
+  unsigned char* d_group = nullptr;
+  float* d_clip = nullptr;
+  float *params = nullptr, *grads = nullptr, *m = nullptr, *v = nullptr;
+  int n_groups = 0;
+  float lr[16], wd[16];
+  int last_launches = 0;
+  long long part_stride = 0;
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int check_mlp2(const dpivae_mlp2_t& m, int in_dim, int hid, int out_dim, long long n_params, const char* name) {
+  if (m.in_dim != in_dim || m.hid != hid || m.out_dim != out_dim)
+    return fail(std::string("unit ") + name + ": unexpected dims");
+  const long long ends[4] = {m.w0 + (long long)in_dim * hid, m.b0 + hid, m.w1 + (long long)hid * out_dim, m.b1 + out_dim};
+  const long long begs[4] = {m.w0, m.b0, m.w1, m.b1};
+  for (int i = 0; i < 4; ++i)
+    if (begs[i] < 0 || ends[i] > n_params) return fail(std::string("unit ") + name + ": offsets out of range");
+  return 0;
+}
+
+static void fill_mlp2s(Mlp2S& s, const dpivae_mlp2_t& m, int& o) {
+  s.K0 = m.in_dim; s.H = m.hid; s.O = m.out_dim;
+  s.ldw0 = m.hid + 4;
+  s.ldw1 = pad4(m.out_dim) + 4;
+  s.s_w0t = o; o += pad4(m.in_dim) * s.ldw0;
+  s.s_b0 = o; o += m.hid;
+  s.s_w1t = o; o += m.hid * s.ldw1;
+  s.s_b1 = o; o += pad4(m.out_dim);
+  s.g_w0 = m.w0; s.g_b0 = m.b0; s.g_w1 = m.w1; s.g_b1 = m.b1;
+}
+
+static int build_plan(dpivae_model* h) {
+  const dpivae_model_desc_t& d = h->d;
+  DecParams& P = h->dec;
+  memset(&P, 0, sizeof(P));
+  const int Z = d.nz_x + d.nz_c + d.nz_y;
+  if (d.nz_x < 1 || d.nz_x > DPIVAE_MAX_ZX || d.nz_c < 1 || d.nz_c > DPIVAE_MAX_ZCY || d.nz_y < 1 ||
+      d.nz_y > DPIVAE_MAX_ZCY || Z > DPIVAE_MAX_Z)
+    return fail("latent dimensions out of the supported range");
+  if (d.nd_x < 4 || d.nd_x > DPIVAE_MAX_NDX || d.nd_c < 1 || d.nd_c > DPIVAE_MAX_NDCY || d.nd_y < 1 ||
+      d.nd_y > DPIVAE_MAX_NDCY || d.nd_p < 0 || d.nd_p > d.nd_c)
+    return fail("data dimensions out of the supported range");
+  if (d.model_type != DPIVAE_MODEL_P && d.model_type != DPIVAE_MODEL_S) return fail("Invalid model_type");
+  P.model_type = d.model_type;
+  P.nz_x = d.nz_x; P.nz_c = d.nz_c; P.nz_y = d.nz_y; P.Z = Z;
+  P.nd_x = d.nd_x; P.nd_c = d.nd_c; P.nd_y = d.nd_y; P.nd_p = d.nd_p;
+  for (int i = 0; i < 4; ++i) P.idx_c_phys[i] = d.idx_c_phys[i];
+  for (int i = 0; i < d.nd_p; ++i)
+    if (d.idx_c_phys[i] < 0 || d.idx_c_phys[i] >= d.nd_c) return fail("idx_c_phys out of range");
+  if (d.model_type == DPIVAE_MODEL_P) {
+    P.n_blk = 3;
+    P.blk_start[0] = 0; P.blk_size[0] = d.nz_x;
+    P.blk_start[1] = d.nz_x; P.blk_size[1] = d.nz_c;
+    P.blk_start[2] = d.nz_x + d.nz_c; P.blk_size[2] = d.nz_y;
+  } else {
+    P.n_blk = 1;
+    P.blk_start[0] = 0; P.blk_size[0] = Z;
+  }
+  int nL = 0, hrow = 0;
+  for (int b = 0; b < P.n_blk; ++b) {
+    const int nzb = P.blk_size[b];
+    P.blk_loff[b] = nL;
+    for (int i = 0; i < nzb; ++i)
+      for (int j = 0; j <= i; ++j) {
+        P.L_blk[nL] = (unsigned char)b; P.L_i[nL] = (unsigned char)i; P.L_j[nL] = (unsigned char)j;
+        ++nL;
+      }
+    P.henc[b] = hrow;
+    hrow += 2 * nzb + nzb * nzb;
+  }
+  P.nL = nL;
+  P.hpri[0] = hrow; hrow += 2 * d.nz_c;
+  P.hpri[1] = hrow; hrow += 2 * d.nz_y;
+  P.O_tot = hrow;
+  h->O_tot = hrow;
+  for (int i = 0; i < DPIVAE_MAX_ZX; ++i) {
+    P.lb[i] = d.lb[i]; P.ub[i] = d.ub[i];
+    P.prior_kind[i] = d.prior_kind[i]; P.prior_a[i] = d.prior_a[i]; P.prior_b[i] = d.prior_b[i];
+  }
+  P.lambda_g0 = d.lambda_g0; P.has_lambda_x = d.has_lambda_x; P.lambda_x = d.lambda_x;
+  P.phys_kind = d.phys_kind;
+  for (int i = 0; i < DPIVAE_MAX_NDX; ++i) P.grid[i] = d.phys_grid[i];
+  P.g_lsx = d.log_sigma_x;
+  if (d.log_sigma_x < 0 || d.log_sigma_x >= d.n_params) return fail("log_sigma_x offset out of range");
+
+  // ---- validate units ----
+  const int nzd = d.nz_c + d.nz_y, nzin = d.nz_x + d.nd_p;
+  if (check_mlp2(d.fx, nzd, 128, d.nd_x, d.n_params, "decoder_x")) return 1;
+  if (check_mlp2(d.dec_c, d.nz_c, 64, 2 * d.nd_c, d.n_params, "decoder_c")) return 1;
+  if (check_mlp2(d.dec_y, d.nz_y, 64, 2 * d.nd_y, d.n_params, "decoder_y")) return 1;
+  if (check_mlp2(d.prior[0], d.nd_c, 64, 2 * d.nz_c, d.n_params, "prior_net_c")) return 1;
+  if (check_mlp2(d.prior[1], d.nd_y, 64, 2 * d.nz_y, d.n_params, "prior_net_y")) return 1;
+  if (d.model_type == DPIVAE_MODEL_P) {
+    const int nzs[3] = {d.nz_x, d.nz_c, d.nz_y};
+    for (int e = 0; e < 3; ++e)
+      if (check_mlp2(d.enc[e], d.nd_x, 64, 2 * nzs[e] + nzs[e] * nzs[e], d.n_params, "encoder")) return 1;
+  } else {
+    if (check_mlp2(d.enc[0], d.nd_x, 128, 2 * Z + Z * Z, d.n_params, "encoder")) return 1;
+  }
+
+  // ---- shared-memory plan of the decoder kernel ----
+  int o = 0;
+  fill_mlp2s(P.fx, d.fx, o);
+  fill_mlp2s(P.dc, d.dec_c, o);
+  fill_mlp2s(P.dy, d.dec_y, o);
+  int act_rows = 0;
+  const int act_start_marker = -1;
+  (void)act_start_marker;
+  if (d.phys_kind == DPIVAE_PHYS_MLP) {
+    if (d.phys_n_layers < 1 || d.phys_n_layers > 5) return fail("physics MLP: 1..5 linear layers supported");
+    if (d.phys_dims[0] != nzin || d.phys_dims[d.phys_n_layers] != d.nd_x) return fail("physics MLP: in/out dims mismatch");
+    P.phys_n_layers = d.phys_n_layers;
+    long long gw = 0;
+    for (int l = 0; l < d.phys_n_layers; ++l) {
+      PhysLayerS& L = P.pl[l];
+      L.K = d.phys_dims[l]; L.N = d.phys_dims[l + 1];
+      if (L.K < 1 || L.N < 1 || L.K > 128 || L.N > 128) return fail("physics MLP: layer width out of range");
+      L.ldw = pad4(L.N) + 4;
+      L.s_wt = o; o += pad4(L.K) * L.ldw;
+      L.s_b = o; o += pad4(L.N);
+      L.g_w = gw; gw += (long long)L.K * L.N;
+      L.g_b = gw; gw += L.N;
+    }
+  } else if (d.phys_kind == DPIVAE_PHYS_MASS_SPRING) {
+    if (d.nz_x != 1 || d.nd_p != 0) return fail("mass_spring physics expects nz_x = 1, nd_p = 0");
+  } else if (d.phys_kind == DPIVAE_PHYS_BEAM) {
+    if (d.nz_x != 2 || d.nd_p != 0) return fail("beam physics expects nz_x = 2, nd_p = 0");
+  } else {
+    return fail("unknown physics decoder kind");
+  }
+  const int act_start = o;
+  if (d.phys_kind == DPIVAE_PHYS_MLP)
+    for (int l = 0; l + 1 < d.phys_n_layers; ++l) {
+      P.s_A[l] = o; o += pad4(d.phys_dims[l + 1]) * LDP; act_rows += pad4(d.phys_dims[l + 1]);
+    }
+  P.s_XHP = o; o += pad4(d.nd_x) * LDP; act_rows += pad4(d.nd_x);
+  P.s_HD = o; o += 128 * LDP; act_rows += 128;
+  P.s_XHD = o; o += pad4(d.nd_x) * LDP; act_rows += pad4(d.nd_x);
+  P.s_FEAT = act_start;
+  P.rp_loc = 0; P.rp_L = Z; P.rp_pmu = Z + nL; P.rp_psig = P.rp_pmu + nzd; P.n_rowpar = P.rp_psig + nzd;
+  P.f_loc = 0; P.f_L = Z; P.f_pmu = Z + nL; P.f_psig = P.f_pmu + nzd; P.n_feat = P.f_psig + nzd;
+  if (P.n_feat > act_rows) return fail("internal: gradient feature rows exceed the activation region");
+  auto rows = [&](int r) { int s = o; o += r * LDP; return s; };
+  P.s_EPS = rows(pad4(Z));
+  P.s_EPSC = rows(pad4(d.nz_c));
+  P.s_U = rows(pad4(d.nz_x));
+  P.s_ZXIN = rows(pad4(nzin));
+  P.s_S0 = rows(pad4(nzin));
+  P.s_ZD = rows(pad4(nzd) + 4);
+  P.s_OC = rows(pad4(2 * d.nd_c));
+  P.s_OY = rows(pad4(2 * d.nd_y));
+  P.s_DZD = rows(pad4(nzd));
+  P.s_DZC = rows(pad4(d.nz_c));
+  P.s_DZY = rows(pad4(d.nz_y));
+  P.s_DZX = rows(pad4(nzin));
+  P.s_SC = rows(16);
+  P.s_ROWPAR = o; o += P.n_rowpar * RBMAX;
+  P.s_ROWRAW = o; o += (d.nd_c + d.nd_y) * RBMAX;
+  P.s_ROWACC = o; o += (P.n_feat + 5) * RBMAX;
+  P.s_total = o;
+  P.s_zero_end = o;
+  if ((size_t)o * sizeof(float) > 232448) {
+    char buf[128];
+    snprintf(buf, sizeof buf, "decoder kernel shared-memory plan needs %zu bytes (> 232448)", (size_t)o * 4);
+    return fail(buf);
+  }
+  P.n_params = d.n_params;
+
+  // ---- encoder-side units ----
+  EncParams& E = h->enc;
+  memset(&E, 0, sizeof(E));
+  int nu = 0, hid_row = 0;
+  const int n_enc = d.model_type == DPIVAE_MODEL_P ? 3 : 1;
+  for (int e = 0; e < n_enc; ++e) {
+    EncUnit& U = E.u[nu++];
+    U.K0 = d.enc[e].in_dim; U.H = d.enc[e].hid; U.O = d.enc[e].out_dim; U.src = 0;
+    U.hid_row = hid_row; hid_row += U.H;
+    U.out_row = P.henc[e];
+    U.g_w0 = d.enc[e].w0; U.g_b0 = d.enc[e].b0; U.g_w1 = d.enc[e].w1; U.g_b1 = d.enc[e].b1;
+  }
+  h->n_enc_units = nu;
+  for (int k = 0; k < 2; ++k) {
+    EncUnit& U = E.u[nu++];
+    U.K0 = d.prior[k].in_dim; U.H = d.prior[k].hid; U.O = d.prior[k].out_dim; U.src = 1 + k;
+    U.hid_row = hid_row; hid_row += U.H;
+    U.out_row = P.hpri[k];
+    U.g_w0 = d.prior[k].w0; U.g_b0 = d.prior[k].b0; U.g_w1 = d.prior[k].w1; U.g_b1 = d.prior[k].b1;
+  }
+  E.n_units = nu;
+  h->H_tot = hid_row;
+  E.nd_x = d.nd_x; E.nd_c = d.nd_c; E.nd_y = d.nd_y;
+  for (int i = 0; i < d.nd_x; ++i) { E.mean_x[i] = d.mean_x[i]; E.std_x[i] = d.std_x[i]; E.istd_x[i] = 1.0f / d.std_x[i]; }
+  for (int i = 0; i < d.nd_c; ++i) { E.mean_c[i] = d.mean_c[i]; E.std_c[i] = d.std_c[i]; E.istd_c[i] = 1.0f / d.std_c[i]; }
+  for (int i = 0; i < d.nd_y; ++i) { E.mean_y[i] = d.mean_y[i]; E.std_y[i] = d.std_y[i]; E.istd_y[i] = 1.0f / d.std_y[i]; }
+  E.n_params = d.n_params;
+  if (enc_smem_bytes(E, true) > 232448) return fail("encoder kernel shared-memory plan exceeds 227 KB");
+  h->part_stride = (long long)align_up((size_t)d.n_params + NSCAL, 64);
+  return 0;
+}
+
+extern "C" {
+
+int dpivae_abi_version(void) { return 1; }
+const char* dpivae_last_error(void) { return g_err.c_str(); }
+
+int dpivae_create(const dpivae_model_desc_t* desc, dpivae_handle_t* out) {
+  if (!desc || !out) return fail("null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail("no CUDA device: libdpivae_b200 has no CPU fallback");
+  int dev = 0;
+  CUDA_OK(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major < 10) return fail("libdpivae_b200 is built for sm_100a (B200) only");
+  dpivae_model* h = new dpivae_model();
+  h->d = *desc;
+  h->sm_count = prop.multiProcessorCount;
+  if (build_plan(h)) { delete h; return 1; }
+  if (configure_dec_kernel() || configure_enc_kernels()) { delete h; return fail("cudaFuncSetAttribute(max dynamic smem) failed"); }
+  // owner map: which kernel's partials hold each parameter's gradient
+  std::vector<unsigned char> owner((size_t)desc->n_params, 0);
+  for (int u = 0; u < h->enc.n_units; ++u) {
+    const EncUnit& U = h->enc.u[u];
+    for (long long e = 0; e < (long long)U.K0 * U.H; ++e) owner[U.g_w0 + e] = 1;
+    for (long long e = 0; e < U.H; ++e) owner[U.g_b0 + e] = 1;
+    for (long long e = 0; e < (long long)U.H * U.O; ++e) owner[U.g_w1 + e] = 1;
+    for (long long e = 0; e < U.O; ++e) owner[U.g_b1 + e] = 1;
+  }
+  CUDA_OK(cudaMalloc(&h->d_owner, owner.size()));
+  CUDA_OK(cudaMemcpy(h->d_owner, owner.data(), owner.size(), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMalloc(&h->d_group, owner.size()));
+  CUDA_OK(cudaMemset(h->d_group, 0, owner.size()));
+  CUDA_OK(cudaMalloc(&h->d_clip, sizeof(float)));
+  h->n_groups = 1;
+  h->lr[0] = 1e-3f; h->wd[0] = 0.0f;
+  *out = h;
+  return 0;
+}
+
+int dpivae_destroy(dpivae_handle_t h) {
+  if (!h) return 0;
+  cudaFree(h->d_frozen); cudaFree(h->d_owner); cudaFree(h->d_group); cudaFree(h->d_clip);
+  delete h;
+  return 0;
+}
+
+int dpivae_set_physics_mlp(dpivae_handle_t h, const float* w, const float* b, const float* in_mean, const float* in_std) {
+  if (!h || !w || !b || !in_mean || !in_std) return fail("null argument");
+  if (h->d.phys_kind != DPIVAE_PHYS_MLP) return fail("model has no MLP physics decoder");
+  std::vector<float> flat;
+  long long wo = 0, bo = 0;
+  for (int l = 0; l < h->d.phys_n_layers; ++l) {
+    const int K = h->d.phys_dims[l], N = h->d.phys_dims[l + 1];
+    flat.insert(flat.end(), w + wo, w + wo + (long long)K * N);
+    flat.insert(flat.end(), b + bo, b + bo + N);
+    wo += (long long)K * N; bo += N;
+  }
+  if (h->d_frozen) cudaFree(h->d_frozen);
+  CUDA_OK(cudaMalloc(&h->d_frozen, flat.size() * sizeof(float)));
+  CUDA_OK(cudaMemcpy(h->d_frozen, flat.data(), flat.size() * sizeof(float), cudaMemcpyHostToDevice));
+  for (int i = 0; i < h->d.phys_dims[0] && i < 8; ++i) {
+    h->dec.phys_in_mean[i] = in_mean[i];
+    h->dec.phys_in_std[i] = in_std[i];
+  }
+  return 0;
+}
+
+int dpivae_bind(dpivae_handle_t h, float* params, float* grads, float* exp_avg, float* exp_avg_sq) {
+  if (!h || !params) return fail("null argument");
+  h->params = params; h->grads = grads; h->m = exp_avg; h->v = exp_avg_sq;
+  return 0;
+}
+
+int dpivae_set_groups(dpivae_handle_t h, int32_t n_groups, const int64_t* begin, const int64_t* end, const float* lr,
+                      const float* weight_decay) {
+  if (!h || n_groups < 1 || n_groups > 16) return fail("1..16 parameter groups supported");
+  std::vector<unsigned char> grp((size_t)h->d.n_params, 255);
+  for (int g = 0; g < n_groups; ++g) {
+    if (begin[g] < 0 || end[g] > h->d.n_params || begin[g] > end[g]) return fail("group range out of bounds");
+    for (int64_t i = begin[g]; i < end[g]; ++i) grp[i] = (unsigned char)g;
+    h->lr[g] = lr[g];
+    h->wd[g] = weight_decay[g];
+  }
+  for (size_t i = 0; i < grp.size(); ++i)
+    if (grp[i] == 255) return fail("parameter groups do not cover the flat buffer");
+  h->n_groups = n_groups;
+  CUDA_OK(cudaMemcpy(h->d_group, grp.data(), grp.size(), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+struct WsLayout {
+  size_t hid, headpre, gpre, rowloss, part, scal, total;
+  int grid_enc, grid_dec, RB, n_chunks;
+  long long n_rowblocks;
+};
+
+static WsLayout ws_layout(dpivae_handle_t h, int64_t B, int32_t n_mc) {
+  WsLayout L;
+  size_t o = 0;
+  auto take = [&](size_t floats) { size_t s = o; o = align_up(o + floats * sizeof(float), 256); return s; };
+  L.hid = take((size_t)h->H_tot * B);
+  L.headpre = take((size_t)h->O_tot * B);
+  L.gpre = take((size_t)h->O_tot * B);
+  L.rowloss = take((size_t)6 * B);
+  const long long ntiles = (B + TILE - 1) / TILE;
+  L.grid_enc = (int)(ntiles < h->sm_count ? ntiles : h->sm_count);
+  int RB = TILE / (n_mc < 1 ? 1 : n_mc);
+  RB = RB < 1 ? 1 : (RB > RBMAX ? RBMAX : RB);
+  L.RB = RB;
+  L.n_chunks = (int)(((long long)RB * n_mc + TILE - 1) / TILE);
+  L.n_rowblocks = (B + RB - 1) / RB;
+  L.grid_dec = (int)(L.n_rowblocks < h->sm_count ? L.n_rowblocks : h->sm_count);
+  if (L.grid_enc < 1) L.grid_enc = 1;
+  if (L.grid_dec < 1) L.grid_dec = 1;
+  L.part = take((size_t)(2 * h->sm_count) * h->part_stride);
+  L.scal = take(16);
+  L.total = o;
+  return L;
+}
+
+size_t dpivae_workspace_bytes(dpivae_handle_t h, int64_t B, int32_t n_mc) {
+  if (!h || B < 1 || n_mc < 1) return 0;
+  return ws_layout(h, B, n_mc).total;
+}
+
+static int run_loss(dpivae_handle_t h, const dpivae_batch_t* bt, const dpivae_rng_t* rng, const dpivae_loss_weights_t* w,
+                    int with_grad, int latent_only, int x_std, const dpivae_outputs_t* out, void* ws, size_t ws_bytes,
+                    cudaStream_t st) {
+  if (!h || !bt || !rng) return fail("null argument");
+  if (!h->params) return fail("dpivae_bind has not been called");
+  if (bt->B < 1 || bt->n_mc < 1 || bt->B_global < bt->B) return fail("bad batch sizes");
+  if (!bt->x || (!latent_only && !bt->c)) return fail("x / c must be given");
+  if (with_grad && (!bt->y || !h->grads)) return fail("training needs y and a bound gradient buffer");
+  if (h->d.phys_kind == DPIVAE_PHYS_MLP && !h->d_frozen && !latent_only) return fail("dpivae_set_physics_mlp has not been called");
+  const WsLayout L = ws_layout(h, bt->B, bt->n_mc);
+  if (!ws || ws_bytes < L.total) return fail("workspace too small");
+  if (rng->mode == 0) {
+    const int need = h->d.model_type == DPIVAE_MODEL_P ? 3 : 1;
+    for (int k = 0; k < need; ++k)
+      if (!rng->eps[k]) return fail("rng mode 0 needs injected eps buffers");
+    if (bt->cond && !rng->eps[3]) return fail("cond=True needs eps[3]");
+  }
+  char* base = (char*)ws;
+  float* hid = (float*)(base + L.hid);
+  float* headpre = (float*)(base + L.headpre);
+  float* gpre = (float*)(base + L.gpre);
+  float* part = (float*)(base + L.part);
+  float* scal = (float*)(base + L.scal);
+  int launches = 0;
+
+  EncParams E = h->enc;
+  E.params = h->params;
+  E.x = bt->x; E.c = bt->c; E.y = bt->y; E.idx = (const long long*)bt->idx;
+  E.B = bt->B;
+  E.hid = hid; E.headpre = headpre; E.gpre = gpre;
+  E.with_hid = with_grad;
+  E.x_is_standardised = x_std;
+  E.part = part + (long long)L.grid_dec * h->part_stride;
+  E.part_stride = h->part_stride;
+  if (latent_only) E.n_units = h->n_enc_units;  // prior nets not needed for encode
+  const size_t enc_smem = enc_smem_bytes(h->enc, true);
+  launch_enc_fwd(E, L.grid_enc, enc_smem, st);
+  ++launches;
+
+  DecParams D = h->dec;
+  D.params = h->params; D.frozen = h->d_frozen;
+  D.x = bt->x; D.c = bt->c; D.y = bt->y; D.idx = (const long long*)bt->idx;
+  D.B = bt->B; D.Bg = bt->B_global; D.row_off = bt->row_offset;
+  D.n_mc = bt->n_mc; D.cond = bt->cond; D.with_grad = with_grad;
+  D.RB = L.RB; D.n_chunks = L.n_chunks; D.n_rowblocks = L.n_rowblocks;
+  D.latent_only = latent_only;
+  D.rng.mode = rng->mode; D.rng.seed = rng->seed;
+  for (int k = 0; k < 4; ++k) { D.rng.eps[k] = rng->eps[k]; D.rng.offset[k] = rng->offset[k]; D.rng.grid_threads[k] = rng->grid_threads[k] ? rng->grid_threads[k] : 256; }
+  if (w) { D.beta_x = w->beta_x; D.alpha_x = w->alpha_x; D.alpha_c = w->alpha_c; D.alpha_y = w->alpha_y; }
+  else { D.beta_x = D.alpha_x = D.alpha_c = D.alpha_y = 1.0f; }
+  D.headpre = headpre; D.gpre = gpre;
+  D.part = part; D.part_stride = h->part_stride;
+  memset(&D.out, 0, sizeof(D.out));
+  if (out) {
+    D.out.row_loss = out->row_loss;
+    D.out.xh_p = out->xh_p; D.out.xh_d = out->xh_d; D.out.ch = out->ch; D.out.lsc = out->log_sigma_c;
+    D.out.yh = out->yh; D.out.lsy = out->log_sigma_y; D.out.zx = out->zx; D.out.zc = out->zc; D.out.zy = out->zy;
+    D.out.dens = out->dens_z;
+  }
+  launch_dec(D, L.grid_dec, st);
+  ++launches;
+
+  if (with_grad) {
+    launch_enc_bwd(E, L.grid_enc, enc_smem, st);
+    ++launches;
+  }
+  if (!latent_only) {
+    ReduceParams R;
+    R.part = part; R.part_stride = h->part_stride;
+    R.n_cta_dec = L.grid_dec; R.n_cta_enc = L.grid_enc;
+    R.n_params = h->d.n_params;
+    R.owner = h->d_owner;
+    R.grads = with_grad ? h->grads : nullptr;
+    R.scalars = (out && out->scalars) ? out->scalars : scal;
+    R.inv_B = 1.0f / (float)bt->B_global;
+    R.inv_BD = 1.0f / ((float)bt->B_global * (float)(h->d.nd_x + h->d.nd_c + h->d.nd_y));
+    launch_reduce(R, st);
+    ++launches;
+  }
+  h->last_launches = launches;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int dpivae_loss(dpivae_handle_t h, const dpivae_batch_t* batch, const dpivae_rng_t* rng, const dpivae_loss_weights_t* w,
+                int32_t with_grad, const dpivae_outputs_t* out, void* workspace, size_t workspace_bytes, void* stream) {
+  return run_loss(h, batch, rng, w, with_grad, 0, 0, out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int dpivae_adam_step(dpivae_handle_t h, int64_t step, float max_grad_norm, void* stream) {
+  if (!h || !h->params || !h->grads || !h->m || !h->v) return fail("Adam needs bound params / grads / exp_avg / exp_avg_sq");
+  if (step < 1) return fail("step is 1-based");
+  cudaStream_t st = (cudaStream_t)stream;
+  int launches = 0;
+  AdamParams A;
+  memset(&A, 0, sizeof(A));
+  A.params = h->params; A.grads = h->grads; A.m = h->m; A.v = h->v; A.group = h->d_group;
+  const double b1 = 0.9, b2 = 0.999;
+  const double bc1 = 1.0 - pow(b1, (double)step), bc2 = 1.0 - pow(b2, (double)step);
+  for (int g = 0; g < h->n_groups; ++g) { A.step_size[g] = (float)((double)h->lr[g] / bc1); A.wd[g] = h->wd[g]; }
+  A.bc2_sqrt = (float)sqrt(bc2);
+  A.beta1 = 0.9f; A.beta2 = 0.999f; A.eps = 1e-8f;
+  A.n_params = h->d.n_params;
+  A.clip_coef = nullptr;
+  if (max_grad_norm > 0.0f) {
+    launch_gradnorm(h->grads, h->d.n_params, max_grad_norm, h->d_clip, st);
+    A.clip_coef = h->d_clip;
+    ++launches;
+  }
+  launch_adam(A, st);
+  ++launches;
+  h->last_launches = launches;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int dpivae_train_step(dpivae_handle_t h, const dpivae_batch_t* batch, const dpivae_rng_t* rng, const dpivae_loss_weights_t* w,
+                      int64_t step, float max_grad_norm, const dpivae_outputs_t* out, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  if (run_loss(h, batch, rng, w, 1, 0, 0, out, workspace, workspace_bytes, (cudaStream_t)stream)) return 1;
+  const int l0 = h->last_launches;
+  if (dpivae_adam_step(h, step, max_grad_norm, stream)) return 1;
+  h->last_launches += l0;
+  return 0;
+}
+
+int dpivae_encode(dpivae_handle_t h, const dpivae_batch_t* batch, const dpivae_rng_t* rng, int32_t x_is_standardised,
+                  float* zx, float* zc, float* zy, float* dens_z, void* workspace, size_t workspace_bytes, void* stream) {
+  dpivae_outputs_t o;
+  memset(&o, 0, sizeof(o));
+  o.zx = zx; o.zc = zc; o.zy = zy; o.dens_z = dens_z;
+  return run_loss(h, batch, rng, nullptr, 0, 1, x_is_standardised, &o, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+uint64_t dpivae_philox_plan(dpivae_handle_t h, int64_t B_global, int32_t n_mc, int32_t cond, uint64_t offset_in,
+                            int32_t sm_count, int32_t max_threads_per_sm, dpivae_rng_t* rng) {
+  if (!h || !rng) return offset_in;
+  int nz[4] = {0, 0, 0, 0};
+  int nt = 0;
+  if (h->d.model_type == DPIVAE_MODEL_P) { nz[0] = h->d.nz_x; nz[1] = h->d.nz_c; nz[2] = h->d.nz_y; nt = 3; }
+  else { nz[0] = h->d.nz_x + h->d.nz_c + h->d.nz_y; nt = 1; }
+  uint64_t cur = offset_in;
+  const uint64_t blocks_per_sm = (uint64_t)max_threads_per_sm / 256;
+  auto plan_one = [&](int slot, int width) {
+    const uint64_t numel = (uint64_t)n_mc * (uint64_t)B_global * (uint64_t)width;
+    uint64_t grid = (numel + 255) / 256;
+    const uint64_t cap = (uint64_t)sm_count * blocks_per_sm;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    rng->offset[slot] = cur;
+    rng->grid_threads[slot] = (uint32_t)(256 * grid);
+    cur += ((numel - 1) / (256 * grid * 4) + 1) * 4;
+  };
+  for (int k = 0; k < nt; ++k) plan_one(k, nz[k]);
+  if (cond) plan_one(3, h->d.nz_c);
+  return cur;
+}
+
+int dpivae_last_launch_count(dpivae_handle_t h) { return h ? h->last_launches : 0; }
+
+}  // extern "C"

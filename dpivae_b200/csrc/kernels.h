@@ -1,0 +1,151 @@
+// Internal kernel-parameter structs shared by api.cu and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dpv {
+
+constexpr int MAXZ = 16;
+constexpr int MAXL = MAXZ * (MAXZ + 1) / 2;  // packed lower-triangular entries incl. diagonal
+constexpr int RBMAX = 16;                    // rows per row block in the decoder kernel
+constexpr int NSCAL = 8;                     // per-CTA scalar partials appended to the grad partials
+
+// One-hidden-layer MLP staged in shared memory (weights transposed: Wt[k][n], n contiguous).
+struct Mlp2S {
+  int K0, H, O;            // true dims
+  int ldw0, ldw1;          // leading dims of w0t / w1t
+  int s_w0t, s_b0, s_w1t, s_b1;  // smem offsets (floats)
+  long long g_w0, g_b0, g_w1, g_b1;  // offsets in the flat param / grad buffers
+};
+
+struct PhysLayerS {
+  int K, N, ldw, s_wt, s_b;
+  long long g_w, g_b;      // offsets in the frozen-weights device buffer
+};
+
+struct RngP {
+  int mode;                // 0 injected buffers, 1 philox (torch.cuda normal_ stream)
+  const float* eps[4];
+  unsigned long long seed;
+  unsigned long long offset[4];
+  unsigned int grid_threads[4];
+};
+
+struct OutP {
+  float* row_loss;
+  float *xh_p, *xh_d, *ch, *lsc, *yh, *lsy, *zx, *zc, *zy, *dens;
+};
+
+// ---- decoder-side fused kernel -------------------------------------------------------------
+struct DecParams {
+  // model
+  int model_type, nz_x, nz_c, nz_y, Z, nd_x, nd_c, nd_y, nd_p;
+  int idx_c_phys[4];
+  int n_blk, blk_start[3], blk_size[3], blk_loff[3];  // latent blocks (P: x,c,y ; S: one)
+  int nL;                                              // packed L entries (all blocks)
+  unsigned char L_blk[MAXL], L_i[MAXL], L_j[MAXL];
+  float lb[4], ub[4];
+  int prior_kind[4];
+  float prior_a[4], prior_b[4];
+  float lambda_g0;
+  int has_lambda_x;
+  float lambda_x;
+  int phys_kind, phys_n_layers;
+  PhysLayerS pl[6];
+  float phys_in_mean[8], phys_in_std[8];
+  float grid[64];
+  Mlp2S fx, dc, dy;
+  long long g_lsx;              // offset of log_sigma_x in the flat buffers
+  int henc[3], hpri[2], O_tot;  // feature rows in headpre / gpre
+  // smem plan (float offsets); rows have leading dimension LDP
+  int s_zero_end;               // everything below is zero-filled once
+  int s_A[4];                   // physics MLP hidden activations (layer outputs 0..n-2)
+  int s_XHP, s_HD, s_XHD;
+  int s_EPS, s_EPSC, s_U, s_ZXIN, s_S0, s_ZD, s_OC, s_OY, s_DZD, s_DZC, s_DZY, s_DZX;
+  int s_SC;                     // scalar rows: KLP, RXP, RCP, RYP, REGP, WP, LSXP + 4 partial rows
+  int s_ROWPAR, s_ROWRAW, s_ROWACC, s_FEAT;
+  int rp_loc, rp_L, rp_pmu, rp_psig, n_rowpar;
+  int f_loc, f_L, f_pmu, f_psig, n_feat;  // per-pair gradient feature rows
+  int s_total;
+  // runtime
+  const float* params;
+  const float* frozen;
+  const float *x, *c, *y;
+  const long long* idx;
+  long long B, Bg, row_off;
+  int n_mc, cond, with_grad, RB, n_chunks, latent_only;
+  long long n_rowblocks;
+  RngP rng;
+  float beta_x, alpha_x, alpha_c, alpha_y;
+  const float* headpre;   // [O_tot][B]
+  float* gpre;            // [O_tot][B]
+  float* part;            // per-CTA partial grads + scalars
+  long long part_stride;
+  long long n_params;
+  OutP out;
+};
+
+// ---- encoder-side kernels (forward and backward over "MLP2 units") ------------------------------
+struct EncUnit {
+  int K0, H, O;
+  int src;                 // 0 = x, 1 = c, 2 = y
+  int hid_row, out_row;    // first feature row in hid / headpre buffers
+  long long g_w0, g_b0, g_w1, g_b1;
+};
+
+struct EncParams {
+  int n_units;
+  EncUnit u[5];
+  int nd_x, nd_c, nd_y;
+  int x_is_standardised;
+  float mean_x[64], istd_x[64], mean_c[4], istd_c[4], mean_y[4], istd_y[4];
+  float std_x[64], std_c[4], std_y[4];
+  const float* params;
+  const float *x, *c, *y;
+  const long long* idx;
+  long long B;
+  float* hid;       // [H_tot][B]
+  float* headpre;   // [O_tot][B]
+  const float* gpre;
+  float* part;
+  long long part_stride;
+  long long n_params;
+  int with_hid;     // forward: also store hidden activations (needed by the backward)
+};
+
+// ---- reduce + Adam ------------------------------------------------------------------------------
+struct ReduceParams {
+  const float* part;
+  long long part_stride;
+  int n_cta_dec, n_cta_enc;     // number of CTA partials written by each kernel
+  long long n_params;
+  const unsigned char* owner;   // per param: 0 = decoder kernel wrote it, 1 = encoder kernel
+  float* grads;
+  float* scalars;               // 8 floats
+  float inv_B, inv_BD;
+};
+
+struct AdamParams {
+  float* params;
+  const float* grads;
+  float *m, *v;
+  const unsigned char* group;   // per param group id
+  float step_size[16];          // lr / (1 - beta1^t)
+  float wd[16];
+  float bc2_sqrt;
+  float beta1, beta2, eps;
+  long long n_params;
+  const float* clip_coef;       // device scalar or nullptr
+};
+
+size_t dec_smem_bytes(const DecParams& p);
+void launch_dec(const DecParams& p, int grid, cudaStream_t s);
+void launch_enc_fwd(const EncParams& p, int grid, size_t smem, cudaStream_t s);
+void launch_enc_bwd(const EncParams& p, int grid, size_t smem, cudaStream_t s);
+size_t enc_smem_bytes(const EncParams& p, bool bwd);
+void launch_reduce(const ReduceParams& p, cudaStream_t s);
+void launch_gradnorm(const float* grads, long long n, float max_norm, float* clip_coef, cudaStream_t s);
+void launch_adam(const AdamParams& p, cudaStream_t s);
+int configure_kernels();
+
+}  // namespace dpv

@@ -1,0 +1,82 @@
+// Deterministic cross-CTA gradient reduction, loss-scalar finalisation, clip_grad_norm_ and the
+// fused multi-group Adam update over the flat parameter buffer (dpivae.py:335-373,419-436;
+// torch.optim.Adam: lerp first moment, L2 weight decay, bias-corrected step, eps 1e-8).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace dpv {
+
+// grads[i] = sum over the owning kernel's CTAs (fixed order) of part[cta][i]; block 0 also folds
+// the 6 per-CTA loss sums into the 8 normalised scalars (dpivae.py:419-426).
+__global__ void __launch_bounds__(256) reduce_kernel(const ReduceParams P) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (P.grads != nullptr && i < P.n_params) {
+    const bool enc = P.owner[i] != 0;
+    const float* base = P.part + (enc ? (long long)P.n_cta_dec * P.part_stride : 0ll) + i;
+    const int ncta = enc ? P.n_cta_enc : P.n_cta_dec;
+    float s = 0.0f;
+    for (int c = 0; c < ncta; ++c) s += base[(long long)c * P.part_stride];
+    P.grads[i] = s;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < 6 && P.scalars != nullptr) {
+    const int k = threadIdx.x;
+    float s = 0.0f;
+    for (int c = 0; c < P.n_cta_dec; ++c) s += P.part[(long long)c * P.part_stride + P.n_params + k];
+    // order: ELBO, KLx, KLc(0), KLy(0), Rx, Rc, Ry, reg
+    if (k == 0) P.scalars[0] = s * P.inv_BD;
+    else if (k == 1) { P.scalars[1] = s * P.inv_B; P.scalars[2] = 0.0f; P.scalars[3] = 0.0f; }
+    else P.scalars[k + 2] = s * P.inv_B;
+  }
+}
+
+// clip_coef = min(1, max_norm / (||g||_2 + 1e-6))   (torch.nn.utils.clip_grad_norm_)
+__global__ void __launch_bounds__(1024) gradnorm_kernel(const float* __restrict__ g, long long n, float max_norm,
+                                                        float* __restrict__ clip_coef) {
+  __shared__ float red[1024];
+  float s = 0.0f;
+  for (long long i = threadIdx.x; i < n; i += 1024) s = fmaf(g[i], g[i], s);
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = 512; w > 0; w >>= 1) {
+    if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float c = max_norm / (sqrtf(red[0]) + 1e-6f);
+    *clip_coef = c < 1.0f ? c : 1.0f;
+  }
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(const AdamParams P) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.n_params) return;
+  const int gid = P.group[i];
+  float g = P.grads[i];
+  if (P.clip_coef != nullptr) {
+    g *= *P.clip_coef;
+    const_cast<float*>(P.grads)[i] = g;
+  }
+  const float p = P.params[i];
+  const float wd = P.wd[gid];
+  if (wd != 0.0f) g = fmaf(wd, p, g);
+  float m = P.m[i], v = P.v[i];
+  m = fmaf(1.0f - P.beta1, g - m, m);              // exp_avg.lerp_(grad, 1 - beta1)
+  v = fmaf(1.0f - P.beta2, g * g, v * P.beta2);    // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+  const float denom = sqrtf(v) / P.bc2_sqrt + P.eps;
+  P.params[i] = p - P.step_size[gid] * (m / denom);
+  P.m[i] = m;
+  P.v[i] = v;
+}
+
+void launch_reduce(const ReduceParams& p, cudaStream_t s) {
+  const long long n = p.grads ? p.n_params : 1;
+  reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p);
+}
+void launch_gradnorm(const float* grads, long long n, float max_norm, float* clip_coef, cudaStream_t s) {
+  gradnorm_kernel<<<1, 1024, 0, s>>>(grads, n, max_norm, clip_coef);
+}
+void launch_adam(const AdamParams& p, cudaStream_t s) {
+  adam_kernel<<<(unsigned)((p.n_params + 255) / 256), 256, 0, s>>>(p);
+}
+
+}  // namespace dpv

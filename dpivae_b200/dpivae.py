@@ -1,0 +1,203 @@
+"""Drop-in mirror of the reference's orchestration API for the training-step path:
+`setup_model`, `train_model`, `evaluate_model`, `disentanglement_metric` (dpivae.py:89-703).
+
+Same signatures, `args` flags, error behaviour and logger surface as the reference; the step
+itself (gather -> forward -> ELBO -> backward -> Adam) is one `dpivae_train_step` call into
+libdpivae_b200.so per iteration.
+"""
+import numpy as np
+import torch
+
+from .modules import Decoder, FactorizedNN, FullCovarianceNN, GaussianEncoder, GradRevAdditive
+from .utils import (Annealing, ChainTransform, ChainTransformMasked, EarlyStopping, LayerGradRev, Logistic,
+                    MarginalDistribution, ScalarLogger, ShiftScale, StandardScaler, device)
+from .vae import DPIVAE
+
+_NAMES8 = ["ELBO", "KLx", "KLc", "KLy", "Rx", "Rc", "Ry", "reg"]
+
+
+def setup_model(args, definition, data_train):
+    """dpivae.py:89-283.  Module creation order follows the reference so that `--use_seed`
+    reproduces its nn.Linear initialisation tensor for tensor."""
+    if args.use_seed == True:  # noqa: E712
+        torch.manual_seed(args.seed)
+    print(args)
+    nz_c, nz_y = args.nz_c, args.nz_y
+    nz_x, nd_x = definition["nz_x"], definition["nd_x"]
+    nd_c, nd_y, nd_p = definition["nd_c"], definition["nd_y"], definition["nd_p"]
+    part_model = definition["part_model"]
+    dict_prior_x = definition["dict_prior_x"]
+    prior_zx = MarginalDistribution([item["dist"](**item["args"]) for item in dict_prior_x.values()])
+    z_c = [item for item in definition["dict_gt"].values() if item["type"] == "c"]
+    idx_c_phys = [idx for idx, item in enumerate(z_c) if item["phys"] == True]  # noqa: E712
+    if nz_x != len(dict_prior_x):
+        raise ValueError("Prior distribution dimension mismatch with ground truth")
+
+    x_train, c_train, y_train = data_train[0], data_train[1], data_train[2]
+    assert x_train.shape[0] == args.n_train
+    assert args.n_batch <= args.n_train
+    input_transform_x = StandardScaler().fit(x_train)
+    input_transform_c = StandardScaler().fit(c_train)
+    input_transform_y = StandardScaler().fit(y_train)
+
+    if args.full_cov_prior == True:  # noqa: E712
+        prior_net_c = GaussianEncoder(FullCovarianceNN(nz_c, nd_c, [64]))
+        prior_net_y = GaussianEncoder(FullCovarianceNN(nz_y, nd_y, [64]))
+    elif args.full_cov_prior == False:  # noqa: E712
+        prior_net_c = GaussianEncoder(FactorizedNN(nz_c, nd_c, [64]))
+        prior_net_y = GaussianEncoder(FactorizedNN(nz_y, nd_y, [64]))
+    else:
+        raise ValueError(f"Unknown full_cov_prior argument: {args.full_cov_prior}")
+
+    layer_gradrev_x = LayerGradRev(None, alpha=args.lambda_g0)
+    decoder_x = GradRevAdditive(part_model, nz_x + nd_p, nz_c + nz_y, nd_x, hidden=128, grad_reverse=layer_gradrev_x)
+    decoder_c = Decoder(nz_c, nd_c, [64])
+    decoder_y = Decoder(nz_y, nd_y, [64])
+
+    transform_lb = torch.tensor([item["lb"] for item in dict_prior_x.values()])
+    transform_ub = torch.tensor([item["ub"] for item in dict_prior_x.values()])
+    logistic_transform = Logistic(k=1.0)
+    shift_scale = ShiftScale(transform_lb, transform_ub)
+
+    if args.model_type == "P":
+        output_transform_zx = ChainTransform(logistic_transform, shift_scale)
+        for which in (args.encoder_x, args.encoder_c, args.encoder_y):
+            if which != "NN":
+                raise ValueError(f"Unknown encoder x choice: {args.encoder_x}")
+        encoder = GaussianEncoder(FullCovarianceNN(nz_x, nd_x, [64]), output_transform=output_transform_zx)
+        encoder_c = GaussianEncoder(FullCovarianceNN(nz_c, nd_x, [64]))
+        encoder_y = GaussianEncoder(FullCovarianceNN(nz_y, nd_x, [64]))
+    elif args.model_type == "S":
+        z_idx_x = [idx for idx, val in enumerate(definition["dict_gt"].values()) if val["type"] == "x"]
+        output_transform_zx = ChainTransformMasked(z_idx_x, logistic_transform, shift_scale)
+        if args.encoder_x != "NN":
+            raise ValueError(f"Unknown encoder choice: {args.encoder_x}")
+        encoder = GaussianEncoder(FullCovarianceNN(nz_x + nz_c + nz_y, nd_x, [128]), output_transform=output_transform_zx)
+        encoder_c = None
+        encoder_y = None
+    else:
+        raise ValueError(f"Unknown model type {args.model_type}")
+
+    return DPIVAE(prior_zx, prior_net_c, prior_net_y, encoder, decoder_x, decoder_c, decoder_y, nz_x, nz_c, nz_y,
+                  nd_x, nd_c, nd_y, idx_c_phys, model_type=args.model_type, encoder_c=encoder_c, encoder_y=encoder_y,
+                  lambda_x=args.lambda_x, transform_x=input_transform_x, transform_c=input_transform_c,
+                  transform_y=input_transform_y)
+
+
+def param_groups(args):
+    """(flat range, lr, weight_decay) per Adam group, dpivae.py:335-363."""
+    g = []
+    if args.model_type == "P":
+        g += [("encoder", args.lr_ex, args.wd_e), ("encoder_c", args.lr_ec, args.wd_e), ("encoder_y", args.lr_ey, args.wd_e)]
+    elif args.model_type == "S":
+        g += [("encoder", args.lr_e, args.wd_e)]
+    else:
+        raise ValueError(f"Unknown model type {args.model_type}")
+    g += [("prior_net_c", args.lr_p, args.wd_p), ("prior_net_y", args.lr_p, args.wd_p),
+          ("decoder_x", args.lr_dx, args.wd_dx), ("decoder_c", args.lr_dc, args.wd_dc),
+          ("decoder_y", args.lr_dy, args.wd_dy), ("log_sigma_x", args.lr_sigma, args.wd_sigma)]
+    return g
+
+
+def _annealers(args):
+    def mk(key):
+        return Annealing(getattr(args, f"{key}_annealing"), args.n_iter, n_cycles=getattr(args, f"{key}_n_cycles"),
+                         R=getattr(args, f"{key}_R"), mu=getattr(args, f"{key}_mu"), cov=getattr(args, f"{key}_cov"))
+
+    return mk("lambda"), mk("beta_x"), mk("beta_c"), mk("beta_y")
+
+
+def train_model(args, vae, definition, data_train, data_val, path_metrics=None, path_figures=None, progress=False):
+    """dpivae.py:285-524.  Returns (vae, logger); logger.experiment.scalars[name] -> [(iter, float)]."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
+    eng = vae.engine(dev)
+    x_train, c_train, y_train = (t.to(eng.dev, torch.float32).contiguous() for t in data_train[:3])
+    x_val, c_val, y_val = (t.to(eng.dev, torch.float32).contiguous() for t in data_val[:3])
+    eng.set_groups(param_groups(args))
+    try:
+        for param in vae.decoder_x.model.parameters():
+            param.requires_grad = False
+    except Exception:
+        print("No parameters found for partial model")
+    logger = ScalarLogger(exp_name="", log_dir=path_metrics)
+    lambda_annealer, beta_x_annealer, beta_c_annealer, beta_y_annealer = _annealers(args)
+    early_stopping = EarlyStopping(patience=args.patience, min_delta=args.min_delta)
+    max_norm = float(args.max_grad_norm) if args.clip_gradients == True else 0.0  # noqa: E712
+    ones = torch.ones(args.n_train)
+    it_range = range(args.n_iter)
+    if progress:
+        from tqdm import trange
+
+        it_range = trange(args.n_iter)
+    for it in it_range:
+        lambda_x_i = lambda_annealer.forward(it) * args.lambda_g0
+        vae.decoder_x.grad_reverse.alpha_ = lambda_x_i  # logged only; the GRL uses _alpha
+        beta_x_i = args.beta_x0 * beta_x_annealer.forward(it)
+        beta_c_i = args.beta_c0 * beta_c_annealer.forward(it)
+        beta_y_i = args.beta_y0 * beta_y_annealer.forward(it)
+        # minibatch draw on the CPU generator (dpivae.py:403); the row gather is fused into the kernels
+        sample_idx = torch.multinomial(ones, args.n_batch, replacement=False)
+        eng.step_count += 1
+        w = (float(beta_x_i), float(args.alpha_x), float(args.alpha_c), float(args.alpha_y))
+        _, scal = eng.loss(x_train, c_train, y_train, args.n_mc_train, w, True, idx=sample_idx,
+                           adam_step=eng.step_count, max_grad_norm=max_norm)
+        for k, nme in enumerate(_NAMES8):
+            logger.log_scalar(nme, scal[k], it)
+        logger.log_scalar("lambda_x", lambda_x_i, it)
+        logger.log_scalar("beta_x", beta_x_i, it)
+        logger.log_scalar("beta_c", beta_c_i, it)
+        logger.log_scalar("beta_y", beta_y_i, it)
+        logger.log_scalar("sigma_x", eng.params[eng.ranges["log_sigma_x"][0]].exp(), it)
+        if it % args.val_freq == 0:
+            _, sv = eng.loss(x_val, c_val, y_val, args.n_mc_val, w, False)
+            for k, nme in enumerate(_NAMES8):
+                logger.log_scalar(nme + "_val", sv[k], it)
+            if early_stopping.early_stop(float(sv[0])):
+                break
+    return vae, logger
+
+
+def regression_metrics(y_true, y_pred):
+    """utils/metrics.py:11-32 (sklearn R2 / MSE / MAE) on host arrays."""
+    from sklearn import metrics
+
+    y_true = y_true.detach().cpu().numpy() if torch.is_tensor(y_true) else np.asarray(y_true)
+    return {"r2": metrics.r2_score(y_true, y_pred), "mse": metrics.mean_squared_error(y_true, y_pred),
+            "mae": metrics.mean_absolute_error(y_true, y_pred)}
+
+
+def evaluate_model(args, definition, model, data_test, cond=False):
+    """dpivae.py:527-559."""
+    x_test, c_test, y_test = data_test[0], data_test[1], data_test[2]
+    model.eval()
+    with torch.no_grad():
+        out = model.sample(x_test, c_test, cond=cond, n=args.n_mc_test)
+    y_pred = out[4].mean(dim=0).detach().cpu().numpy()
+    return {args.name: regression_metrics(y_test, y_pred)}, {args.name: y_pred}
+
+
+def disentanglement_metric(args, model, definition, data_train, data_test, regressor="linear", cond=False, use_mean=False):
+    """dpivae.py:618-703: regress every generative factor on each latent group, report test R2."""
+    from sklearn.linear_model import LinearRegression
+    from sklearn.neural_network import MLPRegressor
+
+    gen_factors = list(definition["dict_gt"].keys())
+    model.eval()
+    n = args.n_mc_test if use_mean == True else 1  # noqa: E712
+    lat = {}
+    for tag, data in (("train", data_train), ("test", data_test)):
+        out = model.sample(data[0], data[1], cond=cond, n=n)
+        lat[tag] = [out[k].mean(dim=0).detach().cpu() for k in (5, 6, 7)]
+    z_train = data_train[3].squeeze(0).detach().cpu()
+    z_test = data_test[3].squeeze(0).detach().cpu()
+    score_test = []
+    for i, factor_i in enumerate(gen_factors):
+        for tag, ztr, zte in zip(("zx", "zc", "zy"), lat["train"], lat["test"]):
+            if regressor == "linear":
+                reg = LinearRegression().fit(ztr, z_train[:, i])
+            elif regressor == "mlp":
+                reg = MLPRegressor(hidden_layer_sizes=(128, 128), max_iter=20000).fit(ztr, z_train[:, i])
+            else:
+                raise ValueError(f"Unknown regressor type {regressor}")
+            score_test.append([tag, factor_i, reg.score(zte, z_test[:, i])])
+    return score_test

@@ -1,0 +1,462 @@
+"""`DPIVAE`: drop-in mirror of the reference's `models/vae.py` class whose arithmetic runs in the
+hand-written sm_100a kernels of libdpivae_b200.so (no eager PyTorch path, no CPU fallback).
+
+Same constructor, attributes, method signatures and tuple orders as the reference
+(models/vae.py:9-255); parameters keep their `state_dict` names but are views into one flat
+device buffer, with gradients / Adam moments in parallel flat buffers (the fused optimizer and the
+single NCCL allreduce of the data-parallel path operate on those).
+"""
+import ctypes as C
+from contextlib import contextmanager
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib
+from .modules import FactorizedNN, FullCovarianceNN
+from .utils import ChainTransform, ChainTransformMasked, Logistic, ShiftScale
+
+_L8 = ("loss", "KLx", "KLc", "KLy", "Rx", "Rc", "Ry", "reg")
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(None)
+
+
+class _Engine:
+    """Owns the C handle, the flat buffers and the workspace of one DPIVAE on one CUDA device."""
+
+    def __init__(self, vae, dev):
+        self.lib = _lib.load()
+        self.dev = torch.device(dev)
+        if self.dev.type != "cuda":
+            raise RuntimeError("DPIVAE runs on CUDA only (sm_100a kernels; there is no CPU fallback)")
+        self.vae = vae
+        self.handle = C.c_void_p(None)
+        self.workspace = None
+        self.step_count = 0
+        self._build(vae)
+
+    # -- flat layout --------------------------------------------------------------------------------
+    def _build(self, vae):
+        units = []  # (name, [(param, ...)] ) in flat order
+
+        def enc_unit(mod):  # GaussianEncoder(FullCovarianceNN | FactorizedNN)
+            net = mod.net
+            l0 = net.net.encoder_linear_0
+            heads = [net.f_mean, net.f_sigma] + ([net.f_cov] if isinstance(net, FullCovarianceNN) else [])
+            return dict(in_dim=l0.in_features, hid=l0.out_features, out_dim=sum(h.out_features for h in heads),
+                        w0=[l0.weight], b0=[l0.bias], w1=[h.weight for h in heads], b1=[h.bias for h in heads])
+
+        def dec_unit(l0, l1):
+            return dict(in_dim=l0.in_features, hid=l0.out_features, out_dim=l1.out_features,
+                        w0=[l0.weight], b0=[l0.bias], w1=[l1.weight], b1=[l1.bias])
+
+        if isinstance(vae.prior_net_c.net, FullCovarianceNN) or isinstance(vae.prior_net_y.net, FullCovarianceNN):
+            raise ValueError("full_cov_prior=True is not supported by the fused kernels (diagonal prior nets only)")
+        enc_mods = [vae.encoder] + ([vae.encoder_c, vae.encoder_y] if vae.model_type == "P" else [])
+        groups = []  # (name, unit dict)
+        for name, m in zip(["encoder", "encoder_c", "encoder_y"], enc_mods):
+            groups.append((name, enc_unit(m)))
+        groups.append(("prior_net_c", enc_unit(vae.prior_net_c)))
+        groups.append(("prior_net_y", enc_unit(vae.prior_net_y)))
+        groups.append(("decoder_x", dec_unit(vae.decoder_x.fx0, vae.decoder_x.fx1)))
+        groups.append(("decoder_c", dec_unit(vae.decoder_c.net[0], vae.decoder_c.net[2])))
+        groups.append(("decoder_y", dec_unit(vae.decoder_y.net[0], vae.decoder_y.net[2])))
+
+        slots, ranges, off = [], {}, 0
+        for name, u in groups:
+            beg = off
+            for key in ("w0", "b0", "w1", "b1"):
+                u[key + "_off"] = off
+                for p in u[key]:
+                    slots.append((p, off))
+                    off += p.numel()
+            ranges[name] = (beg, off)
+        slots.append((vae.log_sigma_x, off))
+        ranges["log_sigma_x"] = (off, off + 1)
+        lsx_off = off
+        off += 1
+        self.n_params = off
+        self.ranges = ranges
+        self.slots = slots
+
+        dev = self.dev
+        self.params = torch.empty(off, dtype=torch.float32, device=dev)
+        self.grads = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(off, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for p, o in slots:
+                self.params[o:o + p.numel()].copy_(p.detach().reshape(-1).to(dev, torch.float32))
+                p.data = self.params[o:o + p.numel()].view(p.shape)
+                p.grad = None
+
+        # -- descriptor ------------------------------------------------------------------------------
+        d = _lib.ModelDesc()
+        d.model_type = _lib.MODEL_P if vae.model_type == "P" else _lib.MODEL_S
+        d.nz_x, d.nz_c, d.nz_y = vae.nz_x, vae.nz_c, vae.nz_y
+        d.nd_x, d.nd_c, d.nd_y = vae.nd_x, vae.nd_c, vae.nd_y
+        d.nd_p = len(vae.idx_c_phys)
+        for i, v in enumerate(vae.idx_c_phys):
+            d.idx_c_phys[i] = int(v)
+
+        def fill(dst, u):
+            dst.in_dim, dst.hid, dst.out_dim = u["in_dim"], u["hid"], u["out_dim"]
+            dst.w0, dst.b0, dst.w1, dst.b1 = u["w0_off"], u["b0_off"], u["w1_off"], u["b1_off"]
+
+        gd = dict(groups)
+        fill(d.enc[0], gd["encoder"])
+        if vae.model_type == "P":
+            fill(d.enc[1], gd["encoder_c"])
+            fill(d.enc[2], gd["encoder_y"])
+        fill(d.prior[0], gd["prior_net_c"])
+        fill(d.prior[1], gd["prior_net_y"])
+        fill(d.fx, gd["decoder_x"])
+        fill(d.dec_c, gd["decoder_c"])
+        fill(d.dec_y, gd["decoder_y"])
+        d.log_sigma_x = lsx_off
+        d.n_params = off
+
+        def put(dst, t, n):
+            v = t.detach().reshape(-1).cpu().float().tolist()
+            if len(v) != n:
+                raise ValueError("scaler statistics do not match the data dimension")
+            for i, val in enumerate(v):
+                dst[i] = val
+
+        for nm, tr, n in (("x", vae.transform_x, vae.nd_x), ("c", vae.transform_c, vae.nd_c), ("y", vae.transform_y, vae.nd_y)):
+            if tr is None:
+                put(getattr(d, "mean_" + nm), torch.zeros(n), n)
+                put(getattr(d, "std_" + nm), torch.ones(n), n)
+            else:
+                put(getattr(d, "mean_" + nm), tr.mean_, n)
+                put(getattr(d, "std_" + nm), tr.scale_, n)
+
+        # bijector Logistic(k=1) -> ShiftScale(lb, ub) on the physics latents (dpivae.py:184-187,237-238)
+        ot = vae.encoder.output_transform
+        if not isinstance(ot, (ChainTransform, ChainTransformMasked)) or len(ot.lst_transforms) != 2 \
+                or not isinstance(ot.lst_transforms[0], Logistic) or not isinstance(ot.lst_transforms[1], ShiftScale) \
+                or float(ot.lst_transforms[0].k) != 1.0:
+            raise ValueError("encoder output transform must be Logistic(k=1) -> ShiftScale(lb, ub)")
+        if isinstance(ot, ChainTransformMasked) and list(ot.mask) != list(range(vae.nz_x)):
+            raise ValueError("S-model bijector mask must be the leading nz_x latent columns")
+        lb = ot.lst_transforms[1].lb.detach().cpu().float().tolist()
+        ub = ot.lst_transforms[1].ub.detach().cpu().float().tolist()
+        for i in range(vae.nz_x):
+            d.lb[i], d.ub[i] = lb[i], ub[i]
+        for i, dist_i in enumerate(vae.prior_x.distributions):
+            if isinstance(dist_i, torch.distributions.Uniform):
+                d.prior_kind[i], d.prior_a[i], d.prior_b[i] = _lib.PRIOR_UNIFORM, float(dist_i.low), float(dist_i.high)
+            elif isinstance(dist_i, torch.distributions.Normal):
+                d.prior_kind[i], d.prior_a[i], d.prior_b[i] = _lib.PRIOR_NORMAL, float(dist_i.loc), float(dist_i.scale)
+            else:
+                raise ValueError(f"unsupported prior over zx: {type(dist_i).__name__}")
+        gr = vae.decoder_x.grad_reverse
+        d.lambda_g0 = float(gr._alpha) if gr is not None else -1.0  # no GRL == plain gradient (x +1)
+        d.has_lambda_x = 0 if vae.lambda_x is None else 1
+        d.lambda_x = 0.0 if vae.lambda_x is None else float(vae.lambda_x)
+
+        model = vae.decoder_x.model
+        kind = getattr(model, "physics_kind", None)
+        frozen = None
+        if kind == "mlp":
+            lin = model.linear_layers()
+            d.phys_kind, d.phys_n_layers = _lib.PHYS_MLP, len(lin)
+            d.phys_dims[0] = lin[0].in_features
+            for i, l in enumerate(lin):
+                d.phys_dims[i + 1] = l.out_features
+            frozen = (
+                np.concatenate([l.weight.detach().cpu().float().numpy().reshape(-1) for l in lin]),
+                np.concatenate([l.bias.detach().cpu().float().numpy().reshape(-1) for l in lin]),
+                model.input_transform.mean_.detach().cpu().float().numpy().reshape(-1).copy(),
+                model.input_transform.scale_.detach().cpu().float().numpy().reshape(-1).copy(),
+            )
+        elif kind in ("mass_spring", "beam"):
+            d.phys_kind = _lib.PHYS_MASS_SPRING if kind == "mass_spring" else _lib.PHYS_BEAM
+            grid = model.t.detach().cpu().float().tolist()
+            if len(grid) != vae.nd_x:
+                raise ValueError("physics grid length must equal nd_x")
+            for i, v in enumerate(grid):
+                d.phys_grid[i] = v
+        else:
+            raise ValueError("part_model must carry physics_kind in {'mlp', 'mass_spring', 'beam'}: arbitrary Python "
+                             "callables cannot run inside the fused decoder kernel")
+        self.desc = d
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.dpivae_create(C.byref(d), C.byref(self.handle)))
+            if frozen is not None:
+                arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in frozen]
+                _lib.check(self.lib.dpivae_set_physics_mlp(self.handle, *[a.ctypes.data_as(C.c_void_p) for a in arrs]))
+            _lib.check(self.lib.dpivae_bind(self.handle, _ptr(self.params), _ptr(self.grads), _ptr(self.exp_avg),
+                                            _ptr(self.exp_avg_sq)))
+        props = torch.cuda.get_device_properties(dev)
+        self.sm_count = props.multi_processor_count
+        self.max_threads_per_sm = props.max_threads_per_multi_processor
+        self.launches = 0
+
+    def close(self):
+        if self.handle:
+            self.lib.dpivae_destroy(self.handle)
+            self.handle = C.c_void_p(None)
+
+    # -- optimizer groups ----------------------------------------------------------------------------
+    def set_groups(self, groups):
+        """groups: list of (range name, lr, weight_decay) covering every range (dpivae.py:335-363)."""
+        n = len(groups)
+        beg = (C.c_int64 * n)(*[self.ranges[g[0]][0] for g in groups])
+        end = (C.c_int64 * n)(*[self.ranges[g[0]][1] for g in groups])
+        lr = (C.c_float * n)(*[float(g[1]) for g in groups])
+        wd = (C.c_float * n)(*[float(g[2]) for g in groups])
+        _lib.check(self.lib.dpivae_set_groups(self.handle, n, beg, end, lr, wd))
+
+    # -- calls -----------------------------------------------------------------------------------------
+    def _workspace(self, B, n):
+        need = self.lib.dpivae_workspace_bytes(self.handle, B, n)
+        if self.workspace is None or self.workspace.numel() < need:
+            self.workspace = torch.empty(need, dtype=torch.uint8, device=self.dev)
+        return self.workspace
+
+    def _rng(self, B_global, n, cond, eps):
+        r = _lib.Rng()
+        if eps is not None:
+            r.mode = 0
+            eps = list(eps) if isinstance(eps, (tuple, list)) else [eps]
+            self._keep = [e.to(self.dev, torch.float32).contiguous() for e in eps]
+            for k, e in enumerate(self._keep):
+                r.eps[k] = e.data_ptr()
+            return r
+        r.mode = 1
+        gen = torch.cuda.default_generators[self.dev.index if self.dev.index is not None else torch.cuda.current_device()]
+        r.seed = gen.initial_seed()
+        new_off = self.lib.dpivae_philox_plan(self.handle, B_global, n, int(bool(cond)), gen.get_offset(), self.sm_count,
+                                              self.max_threads_per_sm, C.byref(r))
+        gen.set_offset(new_off)
+        return r
+
+    def _batch(self, x, c, y, n, cond=False, idx=None, B_global=None, row_offset=0):
+        def prep(t):
+            return None if t is None else t.to(self.dev, torch.float32).contiguous()
+
+        x, c, y = prep(x), prep(c), prep(y)
+        if idx is not None:
+            idx = idx.to(self.dev, torch.int64).contiguous()
+        B = int(idx.shape[0]) if idx is not None else int(x.shape[0])
+        b = _lib.Batch()
+        b.x, b.c, b.y, b.idx = _ptr(x), _ptr(c), _ptr(y), _ptr(idx)
+        b.B, b.B_global, b.row_offset = B, int(B_global if B_global is not None else B), int(row_offset)
+        b.n_mc, b.cond = int(n), int(bool(cond))
+        return b, (x, c, y, idx), B
+
+    def loss(self, x, c, y, n, weights, with_grad, outputs=None, eps=None, idx=None, B_global=None, row_offset=0,
+             adam_step=None, max_grad_norm=0.0):
+        """One dpivae_loss / dpivae_train_step call.  Returns (row_loss (6,B), scalars (8,))."""
+        with torch.cuda.device(self.dev):
+            b, keep, B = self._batch(x, c, y, n, False, idx, B_global, row_offset)
+            rng = self._rng(b.B_global, n, False, eps)
+            w = _lib.LossWeights(*[float(v) for v in weights])
+            out = _lib.Outputs()
+            row_loss = torch.empty((6, B), dtype=torch.float32, device=self.dev)
+            scalars = torch.empty(8, dtype=torch.float32, device=self.dev)
+            out.row_loss, out.scalars = row_loss.data_ptr(), scalars.data_ptr()
+            for k, t in (outputs or {}).items():
+                setattr(out, k, t.data_ptr())
+            ws = self._workspace(B, n)
+            stream = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+            if adam_step is not None:
+                _lib.check(self.lib.dpivae_train_step(self.handle, C.byref(b), C.byref(rng), C.byref(w), int(adam_step),
+                                                      float(max_grad_norm), C.byref(out), _ptr(ws), ws.numel(), stream))
+            else:
+                _lib.check(self.lib.dpivae_loss(self.handle, C.byref(b), C.byref(rng), C.byref(w), int(with_grad),
+                                                C.byref(out), _ptr(ws), ws.numel(), stream))
+            self.launches += self.lib.dpivae_last_launch_count(self.handle)
+            del keep
+            return row_loss, scalars
+
+    def forward(self, x, c, n, cond, eps=None):
+        with torch.cuda.device(self.dev):
+            b, keep, B = self._batch(x, c, None, n, cond)
+            rng = self._rng(B, n, cond, eps)
+            v = self.vae
+            shp = {"xh_p": v.nd_x, "xh_d": v.nd_x, "ch": v.nd_c, "log_sigma_c": v.nd_c, "yh": v.nd_y, "log_sigma_y": v.nd_y,
+                   "zx": v.nz_x, "zc": v.nz_c, "zy": v.nz_y}
+            outs = {k: torch.empty((n, B, d), dtype=torch.float32, device=self.dev) for k, d in shp.items()}
+            outs["dens_z"] = torch.empty((n, B), dtype=torch.float32, device=self.dev)
+            out = _lib.Outputs()
+            for k, t in outs.items():
+                setattr(out, k, t.data_ptr())
+            ws = self._workspace(B, n)
+            stream = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+            _lib.check(self.lib.dpivae_loss(self.handle, C.byref(b), C.byref(rng), None, 0, C.byref(out), _ptr(ws),
+                                            ws.numel(), stream))
+            self.launches += self.lib.dpivae_last_launch_count(self.handle)
+            del keep
+            return outs
+
+    def encode(self, x, n, standardised, eps=None):
+        with torch.cuda.device(self.dev):
+            b, keep, B = self._batch(x, None, None, n)
+            rng = self._rng(B, n, False, eps)
+            v = self.vae
+            zx = torch.empty((n, B, v.nz_x), dtype=torch.float32, device=self.dev)
+            zc = torch.empty((n, B, v.nz_c), dtype=torch.float32, device=self.dev)
+            zy = torch.empty((n, B, v.nz_y), dtype=torch.float32, device=self.dev)
+            dens = torch.empty((n, B), dtype=torch.float32, device=self.dev)
+            ws = self._workspace(B, n)
+            stream = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+            _lib.check(self.lib.dpivae_encode(self.handle, C.byref(b), C.byref(rng), int(bool(standardised)), _ptr(zx),
+                                              _ptr(zc), _ptr(zy), _ptr(dens), _ptr(ws), ws.numel(), stream))
+            self.launches += self.lib.dpivae_last_launch_count(self.handle)
+            del keep
+            return zx, zc, zy, dens
+
+    def adam_step(self, step, max_grad_norm=0.0):
+        with torch.cuda.device(self.dev):
+            stream = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+            _lib.check(self.lib.dpivae_adam_step(self.handle, int(step), float(max_grad_norm), stream))
+            self.launches += self.lib.dpivae_last_launch_count(self.handle)
+
+
+class _LossFn(torch.autograd.Function):
+    """Keeps `vae.loss(...)[0].sum().backward()` (the reference loop, dpivae.py:407-429) working:
+    the fused kernel already produced d(sum_b loss_b / (B*D)) / d(params); a uniform upstream
+    gradient rescales it, anything else cannot be expressed by the fused backward and raises."""
+
+    @staticmethod
+    def forward(ctx, engine, row_loss, scale, *params):
+        ctx.engine, ctx.scale = engine, scale
+        ctx.flat = engine.grads.clone()
+        return tuple(row_loss[i] for i in range(6))
+
+    @staticmethod
+    def backward(ctx, g_loss, *g_rest):
+        for g in g_rest:
+            if g is not None and bool((g != 0).any()):
+                raise RuntimeError("only the total loss (first element of DPIVAE.loss) is differentiable in the fused path")
+        if g_loss is None:
+            return (None, None, None) + tuple(None for _ in ctx.engine.slots)
+        g0 = g_loss.reshape(-1)[0]
+        if not bool(torch.all(g_loss == g0)):
+            raise RuntimeError("the fused backward supports a uniform upstream gradient (loss.sum() / const) only")
+        flat = ctx.flat * (g0 * ctx.scale)
+        outs = [flat[o:o + p.numel()].view(p.shape) for p, o in ctx.engine.slots]
+        return (None, None, None) + tuple(outs)
+
+
+class DPIVAE(nn.Module):
+    """models/vae.py:9-255."""
+
+    def __init__(self, prior_x, prior_net_c, prior_net_y, encoder, decoder_x, decoder_c, decoder_y, nz_x, nz_c, nz_y,
+                 nd_x, nd_c, nd_y, idx_c_phys, model_type=None, encoder_c=None, encoder_y=None, lambda_x=None,
+                 transform_x=None, transform_c=None, transform_y=None, jitter=1e-6):
+        super().__init__()
+        self.prior_x = prior_x
+        self.prior_net_c = prior_net_c
+        self.prior_net_y = prior_net_y
+        self.encoder = encoder
+        self.model_type = model_type
+        self.encoder_c = encoder_c
+        self.encoder_y = encoder_y
+        self.decoder_x = decoder_x
+        self.decoder_c = decoder_c
+        self.decoder_y = decoder_y
+        self.nz_x, self.nz_c, self.nz_y = nz_x, nz_c, nz_y
+        self.nd_x, self.nd_c, self.nd_y = nd_x, nd_c, nd_y
+        self.idx_c_phys = idx_c_phys
+        self.lambda_x = lambda_x
+        self.transform_x, self.transform_c, self.transform_y = transform_x, transform_c, transform_y
+        self.jitter = jitter
+        if (self.model_type != "P") and (self.model_type != "S"):
+            raise ValueError(f"Invalid model_type {self.model_type}")
+        if self.model_type == "S" and ((self.encoder_c is not None) or (self.encoder_y is not None)):
+            raise ValueError("encoder_c and encoder_y must NOT be defined for model type S")
+        if self.model_type == "P" and ((self.encoder_c is None) or (self.encoder_y is None)):
+            raise ValueError("encoder_c and encoder_y must be defined for model type P")
+        self.log_sigma_x = nn.Parameter(torch.tensor(0.0), requires_grad=True)
+        self._engine = None
+        self._eps = None
+
+    # -- engine plumbing ---------------------------------------------------------------------------
+    def engine(self, dev=None):
+        if self._engine is None:
+            if dev is None:
+                dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
+            if dev is None:
+                raise RuntimeError("DPIVAE needs a CUDA device: the step runs in sm_100a kernels, there is no CPU path")
+            self._engine = _Engine(self, dev)
+        return self._engine
+
+    def _apply(self, fn, *a, **k):
+        # .to()/.cuda() would replace the flat-buffer views; re-flatten lazily afterwards
+        if self._engine is not None:
+            self._engine.close()
+            self._engine = None
+        return super()._apply(fn, *a, **k)
+
+    def compile(self, *a, **k):  # the reference's vae.compile() is inert
+        return self
+
+    @contextmanager
+    def inject_noise(self, eps):
+        """Use the given reparameterisation noise instead of the in-kernel Philox stream.
+        P: (eps_x, eps_c, eps_y[, eps_cond]) each (n, B, nz_k); S: tensor (n, B, Z)."""
+        self._eps = eps
+        try:
+            yield self
+        finally:
+            self._eps = None
+
+    # -- reference API -----------------------------------------------------------------------------------
+    def transform_inputs(self, x=None, c=None, y=None):
+        out = []
+        for v, tr in ((x, self.transform_x), (c, self.transform_c), (y, self.transform_y)):
+            if v is None:
+                out.append(torch.nan)
+            else:
+                out.append(tr.forward(v)[0] if tr is not None else v)
+        return tuple(out)
+
+    def encode(self, x, n=1):
+        """models/vae.py:125-151 -- `x` is the already standardised input."""
+        return self.engine().encode(x, n, True, self._eps)
+
+    def forward(self, x, c, cond=False, n=1):
+        o = self.engine().forward(x, c, n, cond, self._eps)
+        return (o["xh_p"], o["xh_d"], o["ch"], o["log_sigma_c"], o["yh"], o["log_sigma_y"], o["zx"], o["zc"], o["zy"],
+                o["dens_z"])
+
+    def loss(self, x, c, y, n=1, beta_x=1.0, beta_c=1.0, beta_y=1.0, alpha_x=1.0, alpha_c=1.0, alpha_y=1.0):
+        """models/vae.py:177-231 -> (loss (B,), KL_x (B,), 0, 0, R_x, R_c, R_y, reg)."""
+        eng = self.engine()
+        with_grad = torch.is_grad_enabled() and any(p.requires_grad for p, _ in eng.slots)
+        w = (float(beta_x), float(alpha_x), float(alpha_c), float(alpha_y))
+        row_loss, _ = eng.loss(x, c, y, n, w, with_grad, eps=self._eps)
+        zero = torch.tensor(0.0)
+        if with_grad:
+            B = row_loss.shape[1]
+            scale = float(B * (self.nd_x + self.nd_c + self.nd_y))
+            rl = _LossFn.apply(eng, row_loss, scale, *[p for p, _ in eng.slots])
+        else:
+            rl = tuple(row_loss[i] for i in range(6))
+        return rl[0], rl[1], zero, zero.clone(), rl[2], rl[3], rl[4], rl[5]
+
+    def sample(self, x, c, cond=False, n=1):
+        """models/vae.py:233-255: forward + three Gaussian noise draws (taken from torch's CUDA
+        generator right after the in-kernel Philox draws, i.e. at the reference's stream positions)."""
+        xh_p, xh_d, ch, lsc, yh, lsy, zx, zc, zy, dens_z = self.forward(x, c, cond=cond, n=n)
+        with torch.no_grad():
+            sx = self.log_sigma_x.detach().exp()
+            x_sample = torch.normal(xh_p + xh_d, sx.expand_as(xh_p))
+            c_sample = torch.normal(ch, lsc.exp())
+            y_sample = torch.normal(yh, lsy.exp())
+        return x_sample, xh_p, xh_d, c_sample, y_sample, zx, zc, zy, dens_z
+
+    def decode(self, zx, zc, zy):
+        raise NotImplementedError("DPIVAE.decode on user-supplied latents is not part of the fused training-step path")
+
+    def prior_net(self, c, y=None):
+        raise NotImplementedError("DPIVAE.prior_net is evaluated inside the fused kernels; use loss()/sample()")
+
+    def sample_prior(self, c, y, n=1):
+        raise NotImplementedError("DPIVAE.sample_prior is outside the fused training-step path")

@@ -1,0 +1,173 @@
+/*
+ * dpivae_b200.h -- C ABI of the B200-native DPI-VAE training-step library (libdpivae_b200.so).
+ *
+ * The reference (JanKoune/DPI-VAE) has NO native/FFI interface: its boundary for this path is the
+ * Python surface `models/vae.py` (DPIVAE.loss/forward/encode/sample) + `dpivae.py`
+ * (setup_model/train_model/evaluate_model).  Each entry point below states which reference
+ * lines it replaces; the Python mirror in dpivae_b200/ binds them with ctypes.
+ *
+ * Conventions: plain C, no torch types.  All tensor pointers are DEVICE pointers (fp32, row-major,
+ * contiguous) unless the name ends in `_host`.  Work is enqueued on the caller's `stream`
+ * (a cudaStream_t passed as void*).  No entry point allocates device memory per call: scratch is
+ * a caller-provided workspace sized by dpivae_workspace_bytes().  Return value 0 = ok; non-zero =
+ * error, message in dpivae_last_error().  No exception crosses the ABI.
+ */
+#ifndef DPIVAE_B200_H
+#define DPIVAE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPIVAE_MAX_ZX 4      /* physics latents            */
+#define DPIVAE_MAX_ZCY 8     /* nz_c, nz_y each            */
+#define DPIVAE_MAX_Z 16      /* nz_x + nz_c + nz_y         */
+#define DPIVAE_MAX_NDX 64    /* response vector length     */
+#define DPIVAE_MAX_NDCY 4    /* nd_c, nd_y each            */
+#define DPIVAE_MAX_PHYS_LAYERS 6
+
+/* One hidden-layer ReLU MLP: in -> hid -> out.  Weights live in the flat parameter buffer in
+ * torch nn.Linear layout: w0 (hid,in), b0 (hid), w1 (out,hid), b1 (out); offsets in floats.
+ * For encoders / prior nets `w1` is the concatenation [f_mean ; f_sigma ; f_cov] (models/encoders.py:20-22). */
+typedef struct {
+  int32_t in_dim, hid, out_dim, _pad;
+  int64_t w0, b0, w1, b1;
+} dpivae_mlp2_t;
+
+enum { DPIVAE_MODEL_P = 0, DPIVAE_MODEL_S = 1 };
+enum { DPIVAE_PHYS_MLP = 0, DPIVAE_PHYS_MASS_SPRING = 1, DPIVAE_PHYS_BEAM = 2 };
+enum { DPIVAE_PRIOR_UNIFORM = 0, DPIVAE_PRIOR_NORMAL = 1 };
+
+/* Everything `setup_model` (dpivae.py:89-283) fixes for a model instance. */
+typedef struct {
+  int32_t model_type;                 /* DPIVAE_MODEL_P: encoder, encoder_c, encoder_y ; _S: one encoder */
+  int32_t nz_x, nz_c, nz_y, nd_x, nd_c, nd_y, nd_p;
+  int32_t idx_c_phys[DPIVAE_MAX_NDCY]; /* columns of raw c appended to zx (models/vae.py:171) */
+  dpivae_mlp2_t enc[3];               /* P: x,c,y (nz_k latents each) ; S: enc[0] over Z = nz_x+nz_c+nz_y */
+  dpivae_mlp2_t prior[2];             /* FactorizedNN prior nets p(zc|c), p(zy|y) (models/encoders.py:96-128) */
+  dpivae_mlp2_t fx, dec_c, dec_y;     /* GradRevAdditive.fx0/fx1, Decoder c / y (models/decoders.py) */
+  int64_t log_sigma_x;                /* offset of the scalar parameter (models/vae.py:70) */
+  int64_t n_params;                   /* length of the flat trainable buffer */
+  float mean_x[DPIVAE_MAX_NDX], std_x[DPIVAE_MAX_NDX];   /* StandardScaler stats (utils/transforms.py:64-68) */
+  float mean_c[DPIVAE_MAX_NDCY], std_c[DPIVAE_MAX_NDCY];
+  float mean_y[DPIVAE_MAX_NDCY], std_y[DPIVAE_MAX_NDCY];
+  float lb[DPIVAE_MAX_ZX], ub[DPIVAE_MAX_ZX];            /* Logistic -> ShiftScale bounds (dpivae.py:184-187) */
+  int32_t prior_kind[DPIVAE_MAX_ZX];                     /* prior over zx (utils/priors.py:19-23) */
+  float prior_a[DPIVAE_MAX_ZX], prior_b[DPIVAE_MAX_ZX];  /* uniform: low, high ; normal: loc, scale */
+  float lambda_g0;                    /* constant GRL scale (utils/transforms.py:207-219,235) */
+  int32_t has_lambda_x;               /* optional regulariser on xh_d (models/vae.py:217-219) */
+  float lambda_x;
+  int32_t phys_kind;
+  int32_t phys_n_layers;              /* MLP surrogate: number of Linear layers (Tanh between) */
+  int32_t phys_dims[DPIVAE_MAX_PHYS_LAYERS + 1];
+  float phys_grid[DPIVAE_MAX_NDX];    /* mass_spring: t ; beam: x = linspace(0, 1, nd_x) */
+} dpivae_model_desc_t;
+
+typedef struct dpivae_model* dpivae_handle_t;
+
+/* One minibatch (dpivae.py:403-404).  x/c/y may be the whole resident dataset with `idx` selecting
+ * rows (the reference's multinomial gather, fused), or already-gathered rows with idx == NULL. */
+typedef struct {
+  const float* x;        /* (rows, nd_x) */
+  const float* c;        /* (rows, nd_c) */
+  const float* y;        /* (rows, nd_y) ; may be NULL for forward/sample/encode */
+  const int64_t* idx;    /* (B) row indices into x/c/y, or NULL */
+  int64_t B;             /* rows this call processes (this rank's shard) */
+  int64_t B_global;      /* rows of the global minibatch: loss normaliser + noise indexing */
+  int64_t row_offset;    /* global index of this shard's first row */
+  int32_t n_mc;          /* Monte-Carlo samples per row */
+  int32_t cond;          /* forward(cond=True): zc drawn from the prior net (models/vae.py:165-167) */
+} dpivae_batch_t;
+
+/* Reparameterisation noise.  mode 0: injected buffers eps[k] of shape (n_mc, B_global, nz_k)
+ * (P: k = x,c,y ; S: eps[0] of width Z ; eps[3] = the cond draw).  mode 1: in-kernel Philox4x32-10
+ * reproducing torch.cuda's normal_() stream: tensor k starts at philox offset `offset[k]`, and the
+ * element -> (subsequence, counter, lane) map uses `grid_threads[k]` = 256 * grid of the torch
+ * launch (ATen/native/cuda/DistributionTemplates.h); dpivae_philox_plan() fills both. */
+typedef struct {
+  int32_t mode;
+  int32_t _pad;
+  const float* eps[4];
+  uint64_t seed;
+  uint64_t offset[4];
+  uint32_t grid_threads[4];
+} dpivae_rng_t;
+
+typedef struct {
+  float beta_x, alpha_x, alpha_c, alpha_y;  /* models/vae.py:177-231; beta_c/beta_y are unused there */
+} dpivae_loss_weights_t;
+
+/* Optional outputs; any pointer may be NULL. */
+typedef struct {
+  float* row_loss;   /* (6, B): loss, KL_x, R_x, R_c, R_y, reg per datapoint (models/vae.py:222-231) */
+  float* scalars;    /* (8): ELBO/(B_global*(nd_x+nd_c+nd_y)), KL_x, 0, 0, R_x, R_c, R_y, reg (each /B_global) -- dpivae.py:419-426 */
+  float* xh_p; float* xh_d;            /* (n, B, nd_x) */
+  float* ch; float* log_sigma_c;       /* (n, B, nd_c) */
+  float* yh; float* log_sigma_y;       /* (n, B, nd_y) */
+  float* zx; float* zc; float* zy;     /* (n, B, nz_*) */
+  float* dens_z;                       /* (n, B) */
+} dpivae_outputs_t;
+
+/* ---- lifecycle ------------------------------------------------------------------------------ */
+int dpivae_create(const dpivae_model_desc_t* desc, dpivae_handle_t* out);
+int dpivae_destroy(dpivae_handle_t h);
+const char* dpivae_last_error(void);
+int dpivae_abi_version(void);
+
+/* Frozen physics surrogate (cases/bridge/__init__.py:163-174, models/nn.py:67-80): host arrays in
+ * nn.Linear layout, concatenated layer by layer; input scaler mean/std of length phys_dims[0]. */
+int dpivae_set_physics_mlp(dpivae_handle_t h, const float* weights_host, const float* biases_host,
+                           const float* in_mean_host, const float* in_std_host);
+
+/* Flat parameter / gradient / Adam-state buffers (n_params floats each; grads/m/v may be NULL for
+ * inference-only use).  Replaces the per-tensor nn.Parameter storage of the reference. */
+int dpivae_bind(dpivae_handle_t h, float* params, float* grads, float* exp_avg, float* exp_avg_sq);
+
+/* Adam parameter groups (dpivae.py:335-363): group g covers flat range [begin[g], end[g]). */
+int dpivae_set_groups(dpivae_handle_t h, int32_t n_groups, const int64_t* begin, const int64_t* end,
+                      const float* lr, const float* weight_decay);
+
+/* ---- the hot path --------------------------------------------------------------------------- */
+size_t dpivae_workspace_bytes(dpivae_handle_t h, int64_t B, int32_t n_mc);
+
+/* DPIVAE.loss (models/vae.py:177-231) [+ forward outputs].  with_grad != 0 additionally runs the
+ * fused backward of ELBO/(B_global*(nd_x+nd_c+nd_y)) (dpivae.py:419,429) and leaves THIS SHARD's
+ * gradient sum in the bound grads buffer and the 8 scalars (shard sums, already normalised by the
+ * global batch) in out->scalars -- ready for one allreduce(sum) across shards. */
+int dpivae_loss(dpivae_handle_t h, const dpivae_batch_t* batch, const dpivae_rng_t* rng,
+                const dpivae_loss_weights_t* w, int32_t with_grad, const dpivae_outputs_t* out,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/* torch.optim.Adam.step (dpivae.py:373,436) over the flat buffers, per-group lr / L2 weight decay,
+ * betas (0.9, 0.999), eps 1e-8.  `step` is 1-based.  max_grad_norm > 0 applies clip_grad_norm_
+ * (dpivae.py:432-433) first. */
+int dpivae_adam_step(dpivae_handle_t h, int64_t step, float max_grad_norm, void* stream);
+
+/* dpivae.py:390-436 minus the minibatch draw: loss(with_grad) + Adam in one call (single shard). */
+int dpivae_train_step(dpivae_handle_t h, const dpivae_batch_t* batch, const dpivae_rng_t* rng,
+                      const dpivae_loss_weights_t* w, int64_t step, float max_grad_norm,
+                      const dpivae_outputs_t* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* transform_inputs -> encode (models/vae.py:161-162, 125-151): zx (n,B,nz_x), zc, zy, dens_z (n,B).
+ * x_is_standardised != 0 mirrors DPIVAE.encode(x_t, n), which receives already-scaled inputs. */
+int dpivae_encode(dpivae_handle_t h, const dpivae_batch_t* batch, const dpivae_rng_t* rng,
+                  int32_t x_is_standardised, float* zx, float* zc, float* zy, float* dens_z,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* Philox bookkeeping for rng mode 1: given the torch CUDA generator's current offset and the SM
+ * count / max threads per SM of the device, fill rng->offset / grid_threads for the draws of one
+ * forward (P: 3 tensors, S: 1, +1 if cond) and return the generator offset after them. */
+uint64_t dpivae_philox_plan(dpivae_handle_t h, int64_t B_global, int32_t n_mc, int32_t cond,
+                            uint64_t offset_in, int32_t sm_count, int32_t max_threads_per_sm,
+                            dpivae_rng_t* rng);
+
+/* Number of kernels launched by the last dpivae_loss / train_step / encode call on this handle. */
+int dpivae_last_launch_count(dpivae_handle_t h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPIVAE_B200_H */
