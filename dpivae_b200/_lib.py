@@ -66,6 +66,7 @@ EXPORTS = [
     "dpivae_create", "dpivae_destroy", "dpivae_last_error", "dpivae_abi_version", "dpivae_set_physics_mlp",
     "dpivae_bind", "dpivae_set_groups", "dpivae_workspace_bytes", "dpivae_loss", "dpivae_adam_step",
     "dpivae_train_step", "dpivae_encode", "dpivae_philox_plan", "dpivae_last_launch_count",
+    "dpivae_set_timing", "dpivae_last_kernel_ms", "dpivae_ffma_peak_tflops",
 ]
 
 _lib = None
@@ -101,6 +102,9 @@ def load():
     lib.dpivae_philox_plan.argtypes = [vp, i64, i32, i32, u64, i32, i32, C.POINTER(Rng)]
     lib.dpivae_philox_plan.restype = u64
     lib.dpivae_last_launch_count.argtypes = [vp]
+    lib.dpivae_set_timing.argtypes = [vp, i32]
+    lib.dpivae_last_kernel_ms.argtypes = [vp, C.POINTER(f32)]
+    lib.dpivae_ffma_peak_tflops.argtypes = [C.POINTER(f32), vp]
     for name in EXPORTS:
         getattr(lib, name)  # fail loudly on a stale library
     _lib = lib

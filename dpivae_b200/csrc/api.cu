@@ -45,6 +45,17 @@ struct dpivae_model {
   float lr[16], wd[16];
   int last_launches = 0;
   long long part_stride = 0;
+  int timing = 0;
+  cudaEvent_t ev[10] = {};   // start/stop pairs: enc_fwd, dec, enc_bwd, reduce, adam
+  int ev_used[5] = {0, 0, 0, 0, 0};
+};
+
+struct KTimer {
+  dpivae_model* h; int k; cudaStream_t st;
+  KTimer(dpivae_model* h_, int k_, cudaStream_t st_) : h(h_), k(k_), st(st_) {
+    if (h->timing) { cudaEventRecord(h->ev[2 * k], st); h->ev_used[k] = 1; }
+  }
+  ~KTimer() { if (h->timing) cudaEventRecord(h->ev[2 * k + 1], st); }
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -282,6 +293,7 @@ int dpivae_create(const dpivae_model_desc_t* desc, dpivae_handle_t* out) {
 int dpivae_destroy(dpivae_handle_t h) {
   if (!h) return 0;
   cudaFree(h->d_frozen); cudaFree(h->d_owner); cudaFree(h->d_group); cudaFree(h->d_clip);
+  for (int i = 0; i < 10; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   delete h;
   return 0;
 }
@@ -401,7 +413,8 @@ static int run_loss(dpivae_handle_t h, const dpivae_batch_t* bt, const dpivae_rn
   E.part_stride = h->part_stride;
   if (latent_only) E.n_units = h->n_enc_units;  // prior nets not needed for encode
   const size_t enc_smem = enc_smem_bytes(h->enc, true);
-  launch_enc_fwd(E, L.grid_enc, enc_smem, st);
+  for (int k = 0; k < 4; ++k) h->ev_used[k] = 0;
+  { KTimer t(h, 0, st); launch_enc_fwd(E, L.grid_enc, enc_smem, st); }
   ++launches;
 
   DecParams D = h->dec;
@@ -424,11 +437,11 @@ static int run_loss(dpivae_handle_t h, const dpivae_batch_t* bt, const dpivae_rn
     D.out.yh = out->yh; D.out.lsy = out->log_sigma_y; D.out.zx = out->zx; D.out.zc = out->zc; D.out.zy = out->zy;
     D.out.dens = out->dens_z;
   }
-  launch_dec(D, L.grid_dec, st);
+  { KTimer t(h, 1, st); launch_dec(D, L.grid_dec, st); }
   ++launches;
 
   if (with_grad) {
-    launch_enc_bwd(E, L.grid_enc, enc_smem, st);
+    { KTimer t(h, 2, st); launch_enc_bwd(E, L.grid_enc, enc_smem, st); }
     ++launches;
   }
   if (!latent_only) {
@@ -441,7 +454,7 @@ static int run_loss(dpivae_handle_t h, const dpivae_batch_t* bt, const dpivae_rn
     R.scalars = (out && out->scalars) ? out->scalars : scal;
     R.inv_B = 1.0f / (float)bt->B_global;
     R.inv_BD = 1.0f / ((float)bt->B_global * (float)(h->d.nd_x + h->d.nd_c + h->d.nd_y));
-    launch_reduce(R, st);
+    { KTimer t(h, 3, st); launch_reduce(R, st); }
     ++launches;
   }
   h->last_launches = launches;
@@ -474,7 +487,8 @@ int dpivae_adam_step(dpivae_handle_t h, int64_t step, float max_grad_norm, void*
     A.clip_coef = h->d_clip;
     ++launches;
   }
-  launch_adam(A, st);
+  h->ev_used[4] = 0;
+  { KTimer t(h, 4, st); launch_adam(A, st); }
   ++launches;
   h->last_launches = launches;
   CUDA_OK(cudaGetLastError());
@@ -524,5 +538,32 @@ uint64_t dpivae_philox_plan(dpivae_handle_t h, int64_t B_global, int32_t n_mc, i
 }
 
 int dpivae_last_launch_count(dpivae_handle_t h) { return h ? h->last_launches : 0; }
+
+int dpivae_set_timing(dpivae_handle_t h, int32_t enable) {
+  if (!h) return fail("null handle");
+  if (enable && !h->ev[0])
+    for (int i = 0; i < 10; ++i) CUDA_OK(cudaEventCreate(&h->ev[i]));
+  h->timing = enable ? 1 : 0;
+  return 0;
+}
+
+int dpivae_last_kernel_ms(dpivae_handle_t h, float* out5) {
+  if (!h || !out5) return fail("null argument");
+  for (int k = 0; k < 5; ++k) {
+    out5[k] = 0.0f;
+    if (h->ev[0] && h->ev_used[k]) {
+      CUDA_OK(cudaEventSynchronize(h->ev[2 * k + 1]));
+      CUDA_OK(cudaEventElapsedTime(&out5[k], h->ev[2 * k], h->ev[2 * k + 1]));
+    }
+  }
+  return 0;
+}
+
+int dpivae_ffma_peak_tflops(float* tflops_out, void* stream) {
+  if (!tflops_out) return fail("null argument");
+  *tflops_out = ffma_peak_tflops((cudaStream_t)stream);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
 
 }  // extern "C"

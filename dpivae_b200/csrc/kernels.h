@@ -147,5 +147,6 @@ void launch_reduce(const ReduceParams& p, cudaStream_t s);
 void launch_gradnorm(const float* grads, long long n, float max_norm, float* clip_coef, cudaStream_t s);
 void launch_adam(const AdamParams& p, cudaStream_t s);
 int configure_kernels();
+float ffma_peak_tflops(cudaStream_t s);
 
 }  // namespace dpv

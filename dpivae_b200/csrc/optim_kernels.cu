@@ -68,6 +68,51 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamParams P) {
   P.v[i] = v;
 }
 
+// FP32 FFMA peak micro-benchmark: 16 independent accumulator chains per thread.
+__global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, float a, float b, int iters) {
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = (float)(threadIdx.x + i);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[i] = fmaf(acc[i], a, b);
+  }
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += acc[i];
+  if (s == 12345.678f) out[0] = s;  // never true; keeps the chains alive
+}
+
+float ffma_peak_tflops(cudaStream_t st) {
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  float* d = nullptr;
+  cudaMalloc(&d, 4);
+  const int iters = 4096, blocks = sms * 8;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 0.0f;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0, st);
+    ffma_peak_kernel<<<blocks, 256, 0, st>>>(d, 0.999f, 0.001f, iters);
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flop = 2.0 * 16 * 8 * (double)iters * 256.0 * blocks;
+    const float tf = (float)(flop / (ms * 1e-3) / 1e12);
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  return best;
+}
+
 void launch_reduce(const ReduceParams& p, cudaStream_t s) {
   const long long n = p.grads ? p.n_params : 1;
   reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p);

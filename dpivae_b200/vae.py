@@ -84,7 +84,10 @@ class _Engine:
 
         dev = self.dev
         self.params = torch.empty(off, dtype=torch.float32, device=dev)
-        self.grads = torch.zeros(off, dtype=torch.float32, device=dev)
+        # gradients and the 8 loss scalars share one buffer: ONE allreduce covers both (data parallel)
+        self.gradbuf = torch.zeros(off + 8, dtype=torch.float32, device=dev)
+        self.grads = self.gradbuf[:off]
+        self.scalars = self.gradbuf[off:]
         self.exp_avg = torch.zeros(off, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(off, dtype=torch.float32, device=dev)
         with torch.no_grad():
@@ -258,7 +261,7 @@ class _Engine:
             w = _lib.LossWeights(*[float(v) for v in weights])
             out = _lib.Outputs()
             row_loss = torch.empty((6, B), dtype=torch.float32, device=self.dev)
-            scalars = torch.empty(8, dtype=torch.float32, device=self.dev)
+            scalars = self.scalars if with_grad or adam_step is not None else torch.empty(8, dtype=torch.float32, device=self.dev)
             out.row_loss, out.scalars = row_loss.data_ptr(), scalars.data_ptr()
             for k, t in (outputs or {}).items():
                 setattr(out, k, t.data_ptr())
@@ -272,7 +275,7 @@ class _Engine:
                                                 C.byref(out), _ptr(ws), ws.numel(), stream))
             self.launches += self.lib.dpivae_last_launch_count(self.handle)
             del keep
-            return row_loss, scalars
+            return row_loss, (scalars.clone() if scalars is self.scalars else scalars)
 
     def forward(self, x, c, n, cond, eps=None):
         with torch.cuda.device(self.dev):
@@ -310,6 +313,20 @@ class _Engine:
             self.launches += self.lib.dpivae_last_launch_count(self.handle)
             del keep
             return zx, zc, zy, dens
+
+    def set_timing(self, enable):
+        _lib.check(self.lib.dpivae_set_timing(self.handle, int(bool(enable))))
+
+    def last_kernel_ms(self):
+        out = (C.c_float * 5)()
+        _lib.check(self.lib.dpivae_last_kernel_ms(self.handle, out))
+        return dict(zip(("enc_fwd", "dec_fused", "enc_bwd", "reduce", "adam"), [float(v) for v in out]))
+
+    def ffma_peak_tflops(self):
+        v = C.c_float(0.0)
+        with torch.cuda.device(self.dev):
+            _lib.check(self.lib.dpivae_ffma_peak_tflops(C.byref(v), C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)))
+        return float(v.value)
 
     def adam_step(self, step, max_grad_norm=0.0):
         with torch.cuda.device(self.dev):

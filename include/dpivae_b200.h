@@ -164,6 +164,16 @@ uint64_t dpivae_philox_plan(dpivae_handle_t h, int64_t B_global, int32_t n_mc, i
                             uint64_t offset_in, int32_t sm_count, int32_t max_threads_per_sm,
                             dpivae_rng_t* rng);
 
+/* Measurement hooks (bench.py): with timing enabled every hot-path call brackets each of its kernels
+ * with CUDA events on the caller's stream; dpivae_last_kernel_ms synchronises those events and returns
+ * the durations [enc_fwd, dec_fused, enc_bwd, reduce, adam] of the last call in milliseconds. */
+int dpivae_set_timing(dpivae_handle_t h, int32_t enable);
+int dpivae_last_kernel_ms(dpivae_handle_t h, float* out5);
+
+/* FP32 FFMA peak of the current device (micro-benchmark, 2 FLOP per FFMA), in TFLOP/s: the roofline
+ * denominator for the fp32-parity mode, which MEASURED_PEAKS.json does not carry. */
+int dpivae_ffma_peak_tflops(float* tflops_out, void* stream);
+
 /* Number of kernels launched by the last dpivae_loss / train_step / encode call on this handle. */
 int dpivae_last_launch_count(dpivae_handle_t h);
 
