@@ -66,7 +66,7 @@ EXPORTS = [
     "dpivae_create", "dpivae_destroy", "dpivae_last_error", "dpivae_abi_version", "dpivae_set_physics_mlp",
     "dpivae_bind", "dpivae_set_groups", "dpivae_workspace_bytes", "dpivae_loss", "dpivae_adam_step",
     "dpivae_train_step", "dpivae_encode", "dpivae_philox_plan", "dpivae_last_launch_count",
-    "dpivae_set_timing", "dpivae_last_kernel_ms", "dpivae_ffma_peak_tflops",
+    "dpivae_set_timing", "dpivae_last_kernel_ms", "dpivae_ffma_peak_tflops", "dpivae_set_phase_buffer",
 ]
 
 _lib = None
@@ -103,6 +103,7 @@ def load():
     lib.dpivae_philox_plan.restype = u64
     lib.dpivae_last_launch_count.argtypes = [vp]
     lib.dpivae_set_timing.argtypes = [vp, i32]
+    lib.dpivae_set_phase_buffer.argtypes = [vp, vp]
     lib.dpivae_last_kernel_ms.argtypes = [vp, C.POINTER(f32)]
     lib.dpivae_ffma_peak_tflops.argtypes = [C.POINTER(f32), vp]
     for name in EXPORTS:

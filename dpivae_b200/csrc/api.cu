@@ -40,6 +40,7 @@ struct dpivae_model {
   unsigned char* d_owner = nullptr;
   unsigned char* d_group = nullptr;
   float* d_clip = nullptr;
+  long long* d_phase = nullptr;
   float *params = nullptr, *grads = nullptr, *m = nullptr, *v = nullptr;
   int n_groups = 0;
   float lr[16], wd[16];
@@ -208,7 +209,10 @@ static int build_plan(dpivae_model* h) {
   P.s_SC = rows(16);
   P.s_ROWPAR = o; o += P.n_rowpar * RBMAX;
   P.s_ROWRAW = o; o += (d.nd_c + d.nd_y) * RBMAX;
-  P.s_ROWACC = o; o += (P.n_feat + 5) * RBMAX;
+  P.s_ROWACC = o; o += pad4(P.n_feat + 5);          // multi-chunk blocks only (one row per block)
+  P.s_ROWX = o; o += d.nd_x * RBMAX;
+  P.s_PH = o; o += 32;                              // 16 x int64 phase counters
+  if (P.n_feat * LDP + (P.n_feat + 5) * RBMAX > act_rows * LDP) return fail("internal: row accumulators exceed the activation region");
   P.s_total = o;
   P.s_zero_end = o;
   if ((size_t)o * sizeof(float) > 232448) {
@@ -430,6 +434,7 @@ static int run_loss(dpivae_handle_t h, const dpivae_batch_t* bt, const dpivae_rn
   else { D.beta_x = D.alpha_x = D.alpha_c = D.alpha_y = 1.0f; }
   D.headpre = headpre; D.gpre = gpre;
   D.part = part; D.part_stride = h->part_stride;
+  D.phase = h->d_phase;
   memset(&D.out, 0, sizeof(D.out));
   if (out) {
     D.out.row_loss = out->row_loss;
@@ -538,6 +543,12 @@ uint64_t dpivae_philox_plan(dpivae_handle_t h, int64_t B_global, int32_t n_mc, i
 }
 
 int dpivae_last_launch_count(dpivae_handle_t h) { return h ? h->last_launches : 0; }
+
+int dpivae_set_phase_buffer(dpivae_handle_t h, void* dev_counters16) {
+  if (!h) return fail("null handle");
+  h->d_phase = (long long*)dev_counters16;
+  return 0;
+}
 
 int dpivae_set_timing(dpivae_handle_t h, int32_t enable) {
   if (!h) return fail("null handle");

@@ -6,6 +6,10 @@
 // LDP = 4 (mod 32) makes 8 consecutive rows start in 8 different 16-byte bank groups, so the
 // LDS.128 along the unit axis (forward / dgrad) AND the LDS.128 along the reduction axis from
 // 8 different rows (wgrad, dgrad weight operand) are both conflict-free.
+//
+// Every GEMM flavour comes in three register-tile shapes; the dispatcher picks the largest tile
+// that still gives all 256 threads a tile, so the skinny layers (K or N of 2..8) do not leave
+// most of the CTA idle at the next barrier.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -27,6 +31,26 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf
 __device__ __forceinline__ float softplusf_(float x) { return x > 20.0f ? x : log1pf(expf(x)); }
 __device__ __forceinline__ float clampf_(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 
+// contiguous vector load / store of V floats (V = 1, 2, 4) from shared memory
+template <int V>
+__device__ __forceinline__ void ldv(const float* p, float* out) {
+  if (V == 4) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+  } else if (V == 2) {
+    const float2 v = *reinterpret_cast<const float2*>(p);
+    out[0] = v.x; out[1] = v.y;
+  } else {
+    out[0] = *p;
+  }
+}
+template <int V>
+__device__ __forceinline__ void stv(float* p, const float* in) {
+  if (V == 4) *reinterpret_cast<float4*>(p) = make_float4(in[0], in[1], in[2], in[3]);
+  else if (V == 2) *reinterpret_cast<float2*>(p) = make_float2(in[0], in[1]);
+  else *p = in[0];
+}
+
 // ------------------------------------------------------------------------------------------
 // Weight staging: global nn.Linear layout w[N][K] -> shared Wt[Kp][ldw] (n contiguous), bias[Np].
 // The destination must have been zero-filled (pad rows/cols stay zero).
@@ -34,163 +58,189 @@ __device__ __forceinline__ float clampf_(float x, float lo, float hi) { return f
 __device__ inline void stage_linear(const float* __restrict__ w, const float* __restrict__ b, int K, int N,
                                     float* __restrict__ Wt, int ldw, float* __restrict__ bias) {
   for (int e = threadIdx.x; e < K * N; e += NT) {
-    int n = e / K, k = e - n * K;
+    const int n = e / K, k = e - n * K;
     Wt[k * ldw + n] = w[e];
   }
   for (int e = threadIdx.x; e < N; e += NT) bias[e] = b[e];
 }
 
 // ------------------------------------------------------------------------------------------
-// O[n][u] = act(bias[n] + sum_k Wt[k][n] * A[k][u]),  u in [0,64), n in [0,Np)
-// 4x4 register tiles: thread -> (4 units) x (4 outputs); 16 FFMA per 2 LDS.128.
+// O[n][u] = act(bias[n] + sum_k Wt[k][n] * A[k][u]),  u in [0,64), n in [0,Np), Np % 4 == 0
 // ------------------------------------------------------------------------------------------
-template <int ACT>
-__device__ __forceinline__ void gemm_fwd(const float* __restrict__ Wt, int ldw, const float* __restrict__ bias,
-                                         const float* __restrict__ A, float* __restrict__ O, int K, int Np) {
-  const int ntiles = 16 * (Np >> 2);
+template <int ACT, int TM, int TN>
+__device__ __forceinline__ void gemm_fwd_t(const float* __restrict__ Wt, int ldw, const float* __restrict__ bias,
+                                           const float* __restrict__ A, float* __restrict__ O, int K, int Np) {
+  constexpr int MT = TILE / TM;
+  const int ntiles = MT * (Np / TN);
   for (int t = threadIdx.x; t < ntiles; t += NT) {
-    const int tm = t & 15, tn = t >> 4;
-    float acc[4][4];
+    const int tm = t % MT, tn = t / MT;
+    float acc[TN][TM];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float bj = bias[4 * tn + j];
+    for (int j = 0; j < TN; ++j) {
+      const float bj = bias[TN * tn + j];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) acc[j][i] = bj;
+      for (int i = 0; i < TM; ++i) acc[j][i] = bj;
     }
-    const float* a = A + 4 * tm;
-    const float* w = Wt + 4 * tn;
+    const float* a = A + TM * tm;
+    const float* w = Wt + TN * tn;
 #pragma unroll 4
     for (int k = 0; k < K; ++k) {
-      const float4 av = *reinterpret_cast<const float4*>(a + k * LDP);
-      const float4 wv = *reinterpret_cast<const float4*>(w + k * ldw);
-      const float am[4] = {av.x, av.y, av.z, av.w};
-      const float wn[4] = {wv.x, wv.y, wv.z, wv.w};
+      float am[TM], wn[TN];
+      ldv<TM>(a + k * LDP, am);
+      ldv<TN>(w + k * ldw, wn);
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
+      for (int j = 0; j < TN; ++j)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) acc[j][i] = fmaf(wn[j], am[i], acc[j][i]);
+        for (int i = 0; i < TM; ++i) acc[j][i] = fmaf(wn[j], am[i], acc[j][i]);
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float4 o;
-      float* op = reinterpret_cast<float*>(&o);
+    for (int j = 0; j < TN; ++j) {
+      float o[TM];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < TM; ++i) {
         float v = acc[j][i];
         if (ACT == ACT_RELU) v = fmaxf(v, 0.0f);
         if (ACT == ACT_TANH) v = tanhf(v);
-        op[i] = v;
+        o[i] = v;
       }
-      *reinterpret_cast<float4*>(O + (4 * tn + j) * LDP + 4 * tm) = o;
+      stv<TM>(O + (TN * tn + j) * LDP + TM * tm, o);
     }
   }
 }
 
+template <int ACT>
+__device__ __forceinline__ void gemm_fwd(const float* __restrict__ Wt, int ldw, const float* __restrict__ bias,
+                                         const float* __restrict__ A, float* __restrict__ O, int K, int Np) {
+  if (Np >= 64) gemm_fwd_t<ACT, 4, 4>(Wt, ldw, bias, A, O, K, Np);
+  else if (Np >= 32) gemm_fwd_t<ACT, 2, 4>(Wt, ldw, bias, A, O, K, Np);
+  else if (Np >= 16) gemm_fwd_t<ACT, 1, 4>(Wt, ldw, bias, A, O, K, Np);
+  else gemm_fwd_t<ACT, 1, 1>(Wt, ldw, bias, A, O, K, Np);
+}
+
 // ------------------------------------------------------------------------------------------
-// Out[k][u] = (sum_n Wt[k][n] * G[n][u]) * act'(Aact[k][u]),  k in [0,Kp), Kp % 4 == 0
-// Thread tile: rows {tk + i*KT} (interleaved -> conflict-free weight loads) x 4 units.
+// Out[k][u] = (sum_n Wt[k][n] * G[n][u]) * act'(Aact[k][u]),  k in [0,Kp), Kp % 4 == 0, Np % 4 == 0
+// Thread tile: rows {tk + i*KT} (interleaved -> conflict-free weight loads) x TM units.
 // In place (Out == Aact) is safe: a thread reads exactly the elements it overwrites.
 // ------------------------------------------------------------------------------------------
+template <int ACT, int TK, int TM>
+__device__ __forceinline__ void gemm_dgrad_t(const float* __restrict__ Wt, int ldw, const float* __restrict__ G,
+                                             const float* Aact, float* Out, int Kp, int Np) {
+  constexpr int MT = TILE / TM;
+  const int KT = Kp / TK;
+  const int ntiles = MT * KT;
+  for (int t = threadIdx.x; t < ntiles; t += NT) {
+    const int tm = t % MT, tk = t / MT;
+    float acc[TK][TM];
+#pragma unroll
+    for (int i = 0; i < TK; ++i)
+#pragma unroll
+      for (int m = 0; m < TM; ++m) acc[i][m] = 0.0f;
+    const float* g = G + TM * tm;
+#pragma unroll 2
+    for (int n = 0; n < Np; n += 4) {
+      float gv[4][TM];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ldv<TM>(g + (n + j) * LDP, gv[j]);
+#pragma unroll
+      for (int i = 0; i < TK; ++i) {
+        float wj[4];
+        ldv<4>(Wt + (tk + i * KT) * ldw + n, wj);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int m = 0; m < TM; ++m) acc[i][m] = fmaf(wj[j], gv[j][m], acc[i][m]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < TK; ++i) {
+      const int row = (tk + i * KT) * LDP + TM * tm;
+      float o[TM];
+#pragma unroll
+      for (int m = 0; m < TM; ++m) o[m] = acc[i][m];
+      if (ACT != ACT_NONE) {
+        float a[TM];
+        ldv<TM>(Aact + row, a);
+#pragma unroll
+        for (int m = 0; m < TM; ++m) {
+          if (ACT == ACT_RELU) o[m] = a[m] > 0.0f ? o[m] : 0.0f;
+          else o[m] *= (1.0f - a[m] * a[m]);
+        }
+      }
+      stv<TM>(Out + row, o);
+    }
+  }
+}
+
 template <int ACT>
 __device__ __forceinline__ void gemm_dgrad(const float* __restrict__ Wt, int ldw, const float* __restrict__ G,
                                            const float* Aact, float* Out, int Kp, int Np) {
-  const int KT = Kp >> 2;
-  const int ntiles = 16 * KT;
-  for (int t = threadIdx.x; t < ntiles; t += NT) {
-    const int tm = t & 15, tk = t >> 4;
-    float acc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int m = 0; m < 4; ++m) acc[i][m] = 0.0f;
-    const float* g = G + 4 * tm;
-    for (int n = 0; n < Np; n += 4) {
-      float4 gv[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) gv[j] = *reinterpret_cast<const float4*>(g + (n + j) * LDP);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 wv = *reinterpret_cast<const float4*>(Wt + (tk + i * KT) * ldw + n);
-        const float wj[4] = {wv.x, wv.y, wv.z, wv.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          acc[i][0] = fmaf(wj[j], gv[j].x, acc[i][0]);
-          acc[i][1] = fmaf(wj[j], gv[j].y, acc[i][1]);
-          acc[i][2] = fmaf(wj[j], gv[j].z, acc[i][2]);
-          acc[i][3] = fmaf(wj[j], gv[j].w, acc[i][3]);
-        }
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int row = (tk + i * KT) * LDP + 4 * tm;
-      float4 o = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-      if (ACT != ACT_NONE) {
-        const float4 a = *reinterpret_cast<const float4*>(Aact + row);
-        if (ACT == ACT_RELU) {
-          o.x = a.x > 0.0f ? o.x : 0.0f; o.y = a.y > 0.0f ? o.y : 0.0f;
-          o.z = a.z > 0.0f ? o.z : 0.0f; o.w = a.w > 0.0f ? o.w : 0.0f;
-        } else {
-          o.x *= (1.0f - a.x * a.x); o.y *= (1.0f - a.y * a.y);
-          o.z *= (1.0f - a.z * a.z); o.w *= (1.0f - a.w * a.w);
-        }
-      }
-      *reinterpret_cast<float4*>(Out + row) = o;
-    }
-  }
+  if (Kp >= 64) gemm_dgrad_t<ACT, 4, 4>(Wt, ldw, G, Aact, Out, Kp, Np);
+  else if (Kp >= 32) gemm_dgrad_t<ACT, 2, 4>(Wt, ldw, G, Aact, Out, Kp, Np);
+  else if (Kp >= 16) gemm_dgrad_t<ACT, 1, 4>(Wt, ldw, G, Aact, Out, Kp, Np);
+  else gemm_dgrad_t<ACT, 1, 1>(Wt, ldw, G, Aact, Out, Kp, Np);
 }
 
 // ------------------------------------------------------------------------------------------
 // dW[n][k] += sum_u A[k][u] * G[n][u] ; db[n] += sum_u G[n][u]     (u over the 64 units)
-// dW/db: this CTA's private accumulators in global memory, nn.Linear layout dW[n*K + k].
+// dW/db: this CTA's private accumulators in global memory (L2-resident), nn.Linear layout
+// dW[n*K + k].  Each accumulator has exactly one writer thread, so the fire-and-forget
+// RED.ADD keeps the sum order deterministic while not stalling on the L2 round trip.
 // Thread tile: k rows {tk + i*KT} x n rows {tn + j*NTn}, LDS.128 along u for both operands.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void gemm_wgrad(const float* __restrict__ A, const float* __restrict__ G,
-                                           float* __restrict__ dW, float* __restrict__ db, int K, int N) {
-  const int KT = pad4(K) >> 2, NTn = pad4(N) >> 2;
+template <int TK, int TN>
+__device__ __forceinline__ void gemm_wgrad_t(const float* __restrict__ A, const float* __restrict__ G,
+                                             float* __restrict__ dW, float* __restrict__ db, int K, int N) {
+  const int KT = pad4(K) / TK, NTn = pad4(N) / TN;
   const int ntiles = KT * NTn;
   for (int t = threadIdx.x; t < ntiles; t += NT) {
     const int tk = t % KT, tn = t / KT;
-    float acc[4][4];
-    float bs[4] = {0.f, 0.f, 0.f, 0.f};
+    float acc[TK][TN];
+    float bs[TN];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < TN; ++j) bs[j] = 0.0f;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+    for (int i = 0; i < TK; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc[i][j] = 0.0f;
 #pragma unroll 2
     for (int u = 0; u < TILE; u += 4) {
-      float4 av[4], gv[4];
+      float av[TK][4], gv[TN][4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) av[i] = *reinterpret_cast<const float4*>(A + (tk + i * KT) * LDP + u);
+      for (int i = 0; i < TK; ++i) ldv<4>(A + (tk + i * KT) * LDP + u, av[i]);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) gv[j] = *reinterpret_cast<const float4*>(G + (tn + j * NTn) * LDP + u);
+      for (int j = 0; j < TN; ++j) ldv<4>(G + (tn + j * NTn) * LDP + u, gv[j]);
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < TK; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          acc[i][j] = fmaf(av[i].x, gv[j].x, acc[i][j]);
-          acc[i][j] = fmaf(av[i].y, gv[j].y, acc[i][j]);
-          acc[i][j] = fmaf(av[i].z, gv[j].z, acc[i][j]);
-          acc[i][j] = fmaf(av[i].w, gv[j].w, acc[i][j]);
-        }
+        for (int j = 0; j < TN; ++j)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[i][j] = fmaf(av[i][q], gv[j][q], acc[i][j]);
       if (tk == 0) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) bs[j] += (gv[j].x + gv[j].y) + (gv[j].z + gv[j].w);
+        for (int j = 0; j < TN; ++j) bs[j] += (gv[j][0] + gv[j][1]) + (gv[j][2] + gv[j][3]);
       }
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < TN; ++j) {
       const int n = tn + j * NTn;
       if (n < N) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < TK; ++i) {
           const int k = tk + i * KT;
-          if (k < K) dW[n * K + k] += acc[i][j];
+          if (k < K) atomicAdd(&dW[n * K + k], acc[i][j]);
         }
-        if (tk == 0) db[n] += bs[j];
+        if (tk == 0) atomicAdd(&db[n], bs[j]);
       }
     }
   }
+}
+
+__device__ __forceinline__ void gemm_wgrad(const float* __restrict__ A, const float* __restrict__ G,
+                                           float* __restrict__ dW, float* __restrict__ db, int K, int N) {
+  const int kn = pad4(K) * pad4(N);
+  if (kn >= 4096) gemm_wgrad_t<4, 4>(A, G, dW, db, K, N);
+  else if (kn >= 1024) gemm_wgrad_t<2, 2>(A, G, dW, db, K, N);
+  else gemm_wgrad_t<1, 1>(A, G, dW, db, K, N);
 }
 
 }  // namespace dpv

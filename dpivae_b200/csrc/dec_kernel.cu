@@ -23,6 +23,18 @@ namespace dpv {
 // scalar rows (one value per pair) inside the SC region
 enum { SC_KL = 0, SC_RX, SC_RC, SC_RY, SC_REG, SC_W, SC_LSX, SC_P0, SC_Q0 = SC_P0 + 4, SC_ROWS = SC_Q0 + 4 };
 
+// optional per-phase cycle accounting (thread 0, clock64 after each barrier); see tools/phase_profile.py
+enum { PH_SETUP = 0, PH_ROWPAR, PH_EPS, PH_LATENT_FWD, PH_AUX_FWD, PH_AUX_LOSS, PH_AUX_BWD, PH_PHYS_FWD, PH_DATA_FWD,
+       PH_XLOSS, PH_DATA_BWD, PH_PHYS_BWD, PH_LATENT_BWD, PH_ROWRED, PH_ROWOUT, PH_COUNT };
+#define PHASE(k)                                          \
+  do {                                                    \
+    if (P.phase != nullptr && tid == 0) {                 \
+      const long long _t = clock64();                     \
+      PHS[k] += _t - t_last;                              \
+      t_last = _t;                                        \
+    }                                                     \
+  } while (0)
+
 __device__ __forceinline__ float philox_normal(unsigned long long seed, unsigned long long offset, unsigned int T,
                                                unsigned long long li) {
   // torch.cuda normal_(): thread `sub` of a grid of T threads draws 4 normals per curand_normal4
@@ -125,8 +137,15 @@ __global__ void __launch_bounds__(NT, 1) dec_kernel(const __grid_constant__ DecP
   float* SC = sm + P.s_SC;
   float* ROWPAR = sm + P.s_ROWPAR;  // [n_rowpar][RBMAX]
   float* ROWRAW = sm + P.s_ROWRAW;  // [nd_c + nd_y][RBMAX]
-  float* ROWACC = sm + P.s_ROWACC;  // [n_feat + 5][RBMAX]
+  float* ROWX = sm + P.s_ROWX;      // [nd_x][RBMAX] raw x rows of the block
   float* FEAT = sm + P.s_FEAT;      // aliases the activation region (dead by the time it is written)
+  // per-row accumulators [n_feat + 5][racc_ld]: single-chunk blocks keep them right behind FEAT in the
+  // (dead) activation region, multi-chunk blocks (RB == 1) in a small dedicated region
+  const bool multi_chunk = P.n_chunks > 1;
+  const int racc_ld = multi_chunk ? 1 : RBMAX;
+  float* ROWACC = multi_chunk ? sm + P.s_ROWACC : FEAT + P.n_feat * LDP;
+  long long* PHS = reinterpret_cast<long long*>(sm + P.s_PH);
+  long long t_last = (P.phase != nullptr && tid == 0) ? clock64() : 0;
 
   const float lsx = P.params[P.g_lsx];
   const float sx = expf(lsx);
@@ -135,7 +154,8 @@ __global__ void __launch_bounds__(NT, 1) dec_kernel(const __grid_constant__ DecP
   const int n_acc = P.n_feat + 5;
 
   float tot[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // thread 0: running sums of the per-row outputs
-  float lsx_grad = 0.0f;                           // thread 0
+  const bool n_pow2 = (n & (n - 1)) == 0 && n <= 32;
+  PHASE(PH_SETUP);
 
   for (long long rb = blockIdx.x; rb < P.n_rowblocks; rb += gridDim.x) {
     const long long row0 = rb * P.RB;
@@ -188,8 +208,16 @@ __global__ void __launch_bounds__(NT, 1) dec_kernel(const __grid_constant__ DecP
       else if (P.y != nullptr) v = P.y[drow * P.nd_y + (j - P.nd_c)];
       ROWRAW[j * RBMAX + r] = v;
     }
-    for (int e = tid; e < n_acc * RBMAX; e += NT) ROWACC[e] = 0.0f;
+    for (int e = tid; e < RBMAX * P.nd_x; e += NT) {
+      const int r = e / P.nd_x, d = e - r * P.nd_x;
+      const long long lrow = row0 + min(r, nrows - 1);
+      const long long drow = P.idx ? P.idx[lrow] : lrow;
+      ROWX[d * RBMAX + r] = P.x[drow * P.nd_x + d];
+    }
+    if (multi_chunk)
+      for (int e = tid; e < n_acc; e += NT) ROWACC[e] = 0.0f;
     __syncthreads();
+    PHASE(PH_ROWPAR);
 
     for (int chunk = 0; chunk < P.n_chunks; ++chunk) {
       const long long q0 = (long long)chunk * TILE;
@@ -224,6 +252,7 @@ __global__ void __launch_bounds__(NT, 1) dec_kernel(const __grid_constant__ DecP
         }
       }
       __syncthreads();
+      PHASE(PH_EPS);
 
       // ---- P2: z = loc + L eps, bijector, log q, log prior (one thread per pair) ---------------
       if (tid < TILE) {
@@ -306,6 +335,7 @@ __global__ void __launch_bounds__(NT, 1) dec_kernel(const __grid_constant__ DecP
         }
       }
       __syncthreads();
+      PHASE(PH_LATENT_FWD);
       if (P.latent_only) continue;  // dpivae_encode: transform_inputs -> encode only
 
       // ---- auxiliary decoders c, y: forward, log-likelihood, backward ----------------------------
@@ -320,6 +350,7 @@ __global__ void __launch_bounds__(NT, 1) dec_kernel(const __grid_constant__ DecP
       store_pairs(P.out.yh, OY, P.nd_y, q0, npairs, row0, n, B);
       store_pairs(P.out.lsy, OY + P.nd_y * LDP, P.nd_y, q0, npairs, row0, n, B);
       if (P.out.ch || P.out.lsc || P.out.yh || P.out.lsy) __syncthreads();
+      PHASE(PH_AUX_FWD);
       if (tid < 2 * TILE) {
         const int which = tid >> 6, p = tid & (TILE - 1);
         const long long q = q0 + p;
@@ -344,6 +375,7 @@ __global__ void __launch_bounds__(NT, 1) dec_kernel(const __grid_constant__ DecP
         SC[(which ? SC_RY : SC_RC) * LDP + p] = valid ? R : 0.0f;
       }
       __syncthreads();
+      PHASE(PH_AUX_LOSS);
       if (P.with_grad) {
         gemm_wgrad(HC, OC, part + P.dc.g_w1, part + P.dc.g_b1, 64, 2 * P.nd_c);
         gemm_wgrad(HY, OY, part + P.dy.g_w1, part + P.dy.g_b1, 64, 2 * P.nd_y);
@@ -357,6 +389,7 @@ __global__ void __launch_bounds__(NT, 1) dec_kernel(const __grid_constant__ DecP
         gemm_dgrad<ACT_NONE>(sm + P.dy.s_w0t, P.dy.ldw0, HY, nullptr, DZY, pad4(P.nz_y), 64);
         __syncthreads();
       }
+      PHASE(PH_AUX_BWD);
 
       // ---- physics decoder forward -----------------------------------------------------------------
       if (P.phys_kind == 0) {
@@ -399,6 +432,8 @@ __global__ void __launch_bounds__(NT, 1) dec_kernel(const __grid_constant__ DecP
           XHP[d * LDP + p] = -1000.0f * w;
         }
       }
+      __syncthreads();
+      PHASE(PH_PHYS_FWD);
       // ---- data-driven decoder forward (behind the GRL: identity) ------------------------------------
       gemm_fwd<ACT_RELU>(sm + P.fx.s_w0t, P.fx.ldw0, sm + P.fx.s_b0, ZD, HD, nzd, 128);
       __syncthreads();
@@ -407,6 +442,7 @@ __global__ void __launch_bounds__(NT, 1) dec_kernel(const __grid_constant__ DecP
       store_pairs(P.out.xh_p, XHP, P.nd_x, q0, npairs, row0, n, B);
       store_pairs(P.out.xh_d, XHD, P.nd_x, q0, npairs, row0, n, B);
       if (P.out.xh_p || P.out.xh_d) __syncthreads();
+      PHASE(PH_DATA_FWD);
 
       // ---- Gaussian log-likelihood of x (raw) and its gradient ---------------------------------------
       {
@@ -414,9 +450,7 @@ __global__ void __launch_bounds__(NT, 1) dec_kernel(const __grid_constant__ DecP
         const long long q = q0 + p;
         const bool valid = q < npairs;
         const int r = (int)((valid ? q : npairs - 1) / n);
-        const long long lrow = row0 + r;
-        const long long drow = P.idx ? P.idx[lrow] : lrow;
-        const float* xrow = P.x + drow * P.nd_x;
+        const float* xrow = ROWX + r;
         const float w = SC[SC_W * LDP + p];
         const float gx = -(P.alpha_x * w) / var_x;
         const float inv_l2 = P.has_lambda_x ? 1.0f / (P.lambda_x * P.lambda_x) : 0.0f;
@@ -424,7 +458,7 @@ __global__ void __launch_bounds__(NT, 1) dec_kernel(const __grid_constant__ DecP
         float ssq = 0.0f, sreg = 0.0f;
         for (int d = prt; d < P.nd_x; d += 4) {
           const float xp = XHP[d * LDP + p], xd = XHD[d * LDP + p];
-          const float res = xrow[d] - (xp + xd);
+          const float res = xrow[d * RBMAX] - (xp + xd);
           ssq = fmaf(res, res, ssq);
           if (P.has_lambda_x) sreg += -(xd * xd) * 0.5f * inv_l2 - log_l - LOG_SQRT_2PI;
           if (P.with_grad) {
@@ -444,16 +478,18 @@ __global__ void __launch_bounds__(NT, 1) dec_kernel(const __grid_constant__ DecP
         const float Q = ((SC[(SC_Q0 + 0) * LDP + p] + SC[(SC_Q0 + 1) * LDP + p]) + SC[(SC_Q0 + 2) * LDP + p]) + SC[(SC_Q0 + 3) * LDP + p];
         SC[SC_RX * LDP + p] = valid ? (-S / (2.0f * var_x) - (float)P.nd_x * (lsx + LOG_SQRT_2PI)) : 0.0f;
         SC[SC_REG * LDP + p] = valid ? Q : 0.0f;
-        SC[SC_LSX * LDP + p] = -(P.alpha_x * SC[SC_W * LDP + p]) * (S / var_x - (float)P.nd_x);
+        if (P.with_grad) {
+          // d loss / d log_sigma_x: fixed-shape warp tree, one accumulator per warp (SC_LSX row, slots 0/1)
+          float lv = -(P.alpha_x * SC[SC_W * LDP + p]) * (S / var_x - (float)P.nd_x);
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) lv += __shfl_xor_sync(0xffffffffu, lv, off);
+          if ((tid & 31) == 0) SC[SC_LSX * LDP + (tid >> 5)] += lv;
+        }
       }
       __syncthreads();
+      PHASE(PH_XLOSS);
 
       if (P.with_grad) {
-        if (tid == 0) {
-          float s = 0.0f;
-          for (int p = 0; p < TILE; ++p) s += SC[SC_LSX * LDP + p];
-          lsx_grad += s;
-        }
         // ---- data-driven decoder backward ----------------------------------------------------------
         gemm_wgrad(HD, XHD, part + P.fx.g_w1, part + P.fx.g_b1, 128, P.nd_x);
         __syncthreads();
@@ -462,6 +498,7 @@ __global__ void __launch_bounds__(NT, 1) dec_kernel(const __grid_constant__ DecP
         gemm_wgrad(ZD, HD, part + P.fx.g_w0, part + P.fx.g_b0, nzd, 128);
         gemm_dgrad<ACT_NONE>(sm + P.fx.s_w0t, P.fx.ldw0, HD, nullptr, DZD, pad4(nzd), 128);
         __syncthreads();
+        PHASE(PH_DATA_BWD);
 
         // ---- physics decoder backward (input gradient only; surrogate weights are frozen) -----------
         if (P.phys_kind == 0) {
@@ -519,13 +556,14 @@ __global__ void __launch_bounds__(NT, 1) dec_kernel(const __grid_constant__ DecP
         }
         __syncthreads();
 
+        PHASE(PH_PHYS_BWD);
         // ---- latent backward: per-pair gradients w.r.t. loc / L / prior parameters --------------------
-        if (tid < TILE) {
-          const int p = tid;
+        {
+          const int p = tid & (TILE - 1), prt = tid >> 6;
           const long long q = q0 + p;
           const int r = (int)((q < npairs ? q : npairs - 1) / n);
           const float bw = P.beta_x * SC[SC_W * LDP + p];
-          for (int k = 0; k < nzd; ++k) {
+          for (int k = prt; k < nzd; k += 4) {
             float g = -P.lambda_g0 * DZD[k * LDP + p] + (k < P.nz_c ? DZC[k * LDP + p] : DZY[(k - P.nz_c) * LDP + p]);
             const float sg = ROWPAR[(P.rp_psig + k) * RBMAX + r];
             const float t = (ZD[k * LDP + p] - ROWPAR[(P.rp_pmu + k) * RBMAX + r]) / sg;
@@ -534,40 +572,60 @@ __global__ void __launch_bounds__(NT, 1) dec_kernel(const __grid_constant__ DecP
             FEAT[(P.f_psig + k) * LDP + p] = -bw * (t * t - 1.0f) / sg;
             FEAT[(P.f_loc + P.nz_x + k) * LDP + p] = g;
           }
-          for (int i = 0; i < P.nz_x; ++i) {
+          for (int i = prt; i < P.nz_x; i += 4) {
             float g = DZX[i * LDP + p];
             if (P.prior_kind[i] == 1) g += bw * (ZXIN[i * LDP + p] - P.prior_a[i]) / (P.prior_b[i] * P.prior_b[i]);
             const float u = U[i * LDP + p];
             FEAT[(P.f_loc + i) * LDP + p] = g * (P.ub[i] - P.lb[i]) * u * (1.0f - u) + bw * (2.0f * u - 1.0f);
           }
-          for (int li = 0; li < P.nL; ++li) {
-            const int b = P.L_blk[li], i = P.L_i[li], j = P.L_j[li], s = P.blk_start[b];
-            float v = FEAT[(P.f_loc + s + i) * LDP + p] * EPS[(s + j) * LDP + p];
-            if (i == j) v -= bw / ROWPAR[(P.rp_L + li) * RBMAX + r];
-            FEAT[(P.f_L + li) * LDP + p] = v;
-          }
         }
         __syncthreads();
+        for (int e = tid; e < TILE * P.nL; e += NT) {
+          const int p = e & (TILE - 1), li = e >> 6;
+          const long long q = q0 + p;
+          const int r = (int)((q < npairs ? q : npairs - 1) / n);
+          const int b = P.L_blk[li], i = P.L_i[li], j = P.L_j[li], s = P.blk_start[b];
+          float v = FEAT[(P.f_loc + s + i) * LDP + p] * EPS[(s + j) * LDP + p];
+          if (i == j) v -= P.beta_x * SC[SC_W * LDP + p] / ROWPAR[(P.rp_L + li) * RBMAX + r];
+          FEAT[(P.f_L + li) * LDP + p] = v;
+        }
+        __syncthreads();
+        PHASE(PH_LATENT_BWD);
       }
 
       // ---- reduce the chunk's pairs over the MC axis into per-row accumulators -----------------------
       {
         const int f0 = P.with_grad ? 0 : P.n_feat;
-        for (int e = tid + f0 * RBMAX; e < n_acc * RBMAX; e += NT) {
-          const int f = e / RBMAX, r = e - f * RBMAX;
-          if (r < nrows) {
-            const long long qa = max((long long)r * n, q0);
-            const long long qb = min(min((long long)(r + 1) * n, q0 + TILE), npairs);
-            if (qb > qa) {
-              const float* src = f < P.n_feat ? FEAT + f * LDP : SC + (f - P.n_feat) * LDP;
-              float s = 0.0f;
-              for (long long q = qa; q < qb; ++q) s += src[q - q0];
-              ROWACC[e] += s;
+        if (n_pow2 && !multi_chunk) {
+          // n | 32: segmented warp-shuffle tree over the n consecutive pairs of each row
+          const int lane = tid & 31, warp = tid >> 5;
+          for (int it = warp + 2 * f0; it < 2 * n_acc; it += NT / 32) {
+            const int f = it >> 1, p = (it & 1) * 32 + lane;
+            const float* src = f < P.n_feat ? FEAT + f * LDP : SC + (f - P.n_feat) * LDP;
+            float v = src[p];
+            for (int off = n >> 1; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+            const int r = p / n;
+            if ((lane & (n - 1)) == 0 && r < nrows) ROWACC[f * racc_ld + r] = v;
+          }
+        } else {
+          for (int e = tid + f0 * RBMAX; e < n_acc * RBMAX; e += NT) {
+            const int f = e / RBMAX, r = e - f * RBMAX;
+            if (r < nrows) {
+              const long long qa = max((long long)r * n, q0);
+              const long long qb = min(min((long long)(r + 1) * n, q0 + TILE), npairs);
+              if (qb > qa) {
+                const float* src = f < P.n_feat ? FEAT + f * LDP : SC + (f - P.n_feat) * LDP;
+                float s = 0.0f;
+                for (long long q = qa; q < qb; ++q) s += src[q - q0];
+                if (multi_chunk) ROWACC[f * racc_ld + r] += s;
+                else ROWACC[f * racc_ld + r] = s;
+              }
             }
           }
         }
       }
       __syncthreads();
+      PHASE(PH_ROWRED);
     }  // chunks
     if (P.latent_only) continue;
 
@@ -575,21 +633,21 @@ __global__ void __launch_bounds__(NT, 1) dec_kernel(const __grid_constant__ DecP
     if (tid < nrows) {
       const int r = tid;
       const float inv_n = 1.0f / (float)n;
-      const float kl = ROWACC[(P.n_feat + SC_KL) * RBMAX + r] * inv_n;
-      const float rx = ROWACC[(P.n_feat + SC_RX) * RBMAX + r] * inv_n;
-      const float rc = ROWACC[(P.n_feat + SC_RC) * RBMAX + r] * inv_n;
-      const float ry = ROWACC[(P.n_feat + SC_RY) * RBMAX + r] * inv_n;
-      const float rg = ROWACC[(P.n_feat + SC_REG) * RBMAX + r] * inv_n;
+      const float kl = ROWACC[(P.n_feat + SC_KL) * racc_ld + r] * inv_n;
+      const float rx = ROWACC[(P.n_feat + SC_RX) * racc_ld + r] * inv_n;
+      const float rc = ROWACC[(P.n_feat + SC_RC) * racc_ld + r] * inv_n;
+      const float ry = ROWACC[(P.n_feat + SC_RY) * racc_ld + r] * inv_n;
+      const float rg = ROWACC[(P.n_feat + SC_REG) * racc_ld + r] * inv_n;
       const float loss = P.beta_x * kl - P.alpha_x * rx - P.alpha_c * rc - P.alpha_y * ry - rg;
       if (P.out.row_loss) {
         float* o = P.out.row_loss + row0 + r;
         o[0] = loss; o[B] = kl; o[2 * B] = rx; o[3 * B] = rc; o[4 * B] = ry; o[5 * B] = rg;
       }
-      ROWACC[(P.n_feat + SC_KL) * RBMAX + r] = kl;
-      ROWACC[(P.n_feat + SC_RX) * RBMAX + r] = rx;
-      ROWACC[(P.n_feat + SC_RC) * RBMAX + r] = rc;
-      ROWACC[(P.n_feat + SC_RY) * RBMAX + r] = ry;
-      ROWACC[(P.n_feat + SC_REG) * RBMAX + r] = rg;
+      ROWACC[(P.n_feat + SC_KL) * racc_ld + r] = kl;
+      ROWACC[(P.n_feat + SC_RX) * racc_ld + r] = rx;
+      ROWACC[(P.n_feat + SC_RC) * racc_ld + r] = rc;
+      ROWACC[(P.n_feat + SC_RY) * racc_ld + r] = ry;
+      ROWACC[(P.n_feat + SC_REG) * racc_ld + r] = rg;
       SC[SC_P0 * LDP + r] = loss;
     }
     if (P.with_grad) {
@@ -601,7 +659,7 @@ __global__ void __launch_bounds__(NT, 1) dec_kernel(const __grid_constant__ DecP
           const int b = block_of(P, i), il = i - P.blk_start[b], nzb = P.blk_size[b];
           const long long om = (long long)(P.henc[b] + il) * B + lrow;
           const float pm = P.headpre[om];
-          P.gpre[om] = (pm >= -50.0f && pm <= 50.0f) ? ROWACC[(P.f_loc + i) * RBMAX + r] : 0.0f;
+          P.gpre[om] = (pm >= -50.0f && pm <= 50.0f) ? ROWACC[(P.f_loc + i) * racc_ld + r] : 0.0f;
           // f_cov entries of latent row il: strict lower triangle gets the L gradient, the rest zero
           for (int j = 0; j < nzb; ++j) {
             const long long oc = (long long)(P.henc[b] + 2 * nzb + il * nzb + j) * B + lrow;
@@ -609,14 +667,14 @@ __global__ void __launch_bounds__(NT, 1) dec_kernel(const __grid_constant__ DecP
             if (j < il) {
               const float pc = P.headpre[oc];
               const int li = P.blk_loff[b] + il * (il + 1) / 2 + j;
-              g = (pc >= -20.0f && pc <= 20.0f) ? ROWACC[(P.f_L + li) * RBMAX + r] : 0.0f;
+              g = (pc >= -20.0f && pc <= 20.0f) ? ROWACC[(P.f_L + li) * racc_ld + r] : 0.0f;
             }
             P.gpre[oc] = g;
           }
           const long long os = (long long)(P.henc[b] + nzb + il) * B + lrow;
           const float ps = P.headpre[os];
           const int ld = P.blk_loff[b] + il * (il + 1) / 2 + il;
-          P.gpre[os] = (ps >= -7.0f && ps <= 3.0f) ? ROWACC[(P.f_L + ld) * RBMAX + r] * expf(ps) : 0.0f;
+          P.gpre[os] = (ps >= -7.0f && ps <= 3.0f) ? ROWACC[(P.f_L + ld) * racc_ld + r] * expf(ps) : 0.0f;
         }
       }
       for (int e = tid; e < RBMAX * nzd; e += NT) {
@@ -628,8 +686,8 @@ __global__ void __launch_bounds__(NT, 1) dec_kernel(const __grid_constant__ DecP
           const long long om = (long long)(P.hpri[which] + kk) * B + lrow;
           const long long os = (long long)(P.hpri[which] + nzk + kk) * B + lrow;
           const float pm = P.headpre[om], ps = P.headpre[os];
-          P.gpre[om] = (pm >= -50.0f && pm <= 50.0f) ? ROWACC[(P.f_pmu + k) * RBMAX + r] : 0.0f;
-          P.gpre[os] = (ps >= -7.0f && ps <= 3.0f) ? ROWACC[(P.f_psig + k) * RBMAX + r] * expf(ps) : 0.0f;
+          P.gpre[om] = (pm >= -50.0f && pm <= 50.0f) ? ROWACC[(P.f_pmu + k) * racc_ld + r] : 0.0f;
+          P.gpre[os] = (ps >= -7.0f && ps <= 3.0f) ? ROWACC[(P.f_psig + k) * racc_ld + r] * expf(ps) : 0.0f;
         }
       }
     }
@@ -637,19 +695,22 @@ __global__ void __launch_bounds__(NT, 1) dec_kernel(const __grid_constant__ DecP
     if (tid == 0) {
       for (int r = 0; r < nrows; ++r) {
         tot[0] += SC[SC_P0 * LDP + r];
-        tot[1] += ROWACC[(P.n_feat + SC_KL) * RBMAX + r];
-        tot[2] += ROWACC[(P.n_feat + SC_RX) * RBMAX + r];
-        tot[3] += ROWACC[(P.n_feat + SC_RC) * RBMAX + r];
-        tot[4] += ROWACC[(P.n_feat + SC_RY) * RBMAX + r];
-        tot[5] += ROWACC[(P.n_feat + SC_REG) * RBMAX + r];
+        tot[1] += ROWACC[(P.n_feat + SC_KL) * racc_ld + r];
+        tot[2] += ROWACC[(P.n_feat + SC_RX) * racc_ld + r];
+        tot[3] += ROWACC[(P.n_feat + SC_RC) * racc_ld + r];
+        tot[4] += ROWACC[(P.n_feat + SC_RY) * racc_ld + r];
+        tot[5] += ROWACC[(P.n_feat + SC_REG) * racc_ld + r];
       }
     }
     __syncthreads();
+    PHASE(PH_ROWOUT);
   }  // row blocks
 
   if (tid == 0) {
     for (int k = 0; k < 6; ++k) part[P.n_params + k] = tot[k];
-    if (P.with_grad) part[P.g_lsx] = lsx_grad;
+    if (P.with_grad) part[P.g_lsx] = SC[SC_LSX * LDP] + SC[SC_LSX * LDP + 1];
+    if (P.phase != nullptr)
+      for (int k = 0; k < PH_COUNT; ++k) atomicAdd(reinterpret_cast<unsigned long long*>(P.phase) + k, (unsigned long long)PHS[k]);
   }
 }
 

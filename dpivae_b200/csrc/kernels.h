@@ -63,7 +63,7 @@ struct DecParams {
   int s_XHP, s_HD, s_XHD;
   int s_EPS, s_EPSC, s_U, s_ZXIN, s_S0, s_ZD, s_OC, s_OY, s_DZD, s_DZC, s_DZY, s_DZX;
   int s_SC;                     // scalar rows: KLP, RXP, RCP, RYP, REGP, WP, LSXP + 4 partial rows
-  int s_ROWPAR, s_ROWRAW, s_ROWACC, s_FEAT;
+  int s_ROWPAR, s_ROWRAW, s_ROWACC, s_FEAT, s_ROWX, s_PH;
   int rp_loc, rp_L, rp_pmu, rp_psig, n_rowpar;
   int f_loc, f_L, f_pmu, f_psig, n_feat;  // per-pair gradient feature rows
   int s_total;
@@ -83,6 +83,7 @@ struct DecParams {
   long long part_stride;
   long long n_params;
   OutP out;
+  long long* phase;        // optional [PH_COUNT] cycle counters (profiling), else nullptr
 };
 
 // ---- encoder-side kernels (forward and backward over "MLP2 units") ------------------------------
