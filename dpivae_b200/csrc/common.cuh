@@ -192,8 +192,20 @@ __device__ __forceinline__ void gemm_wgrad_t(const float* __restrict__ A, const 
                                              float* __restrict__ dW, float* __restrict__ db, int K, int N) {
   const int KT = pad4(K) / TK, NTn = pad4(N) / TN;
   const int ntiles = KT * NTn;
+  // lane -> tile map: a warp covers an 8 (k) x 4 (n) block of tiles when the shape allows, so each
+  // LDS.128 touches <= 8 distinct rows (2 shared-memory wavefronts instead of 4 for 32 distinct rows)
+  const bool blocked = (KT % 8 == 0) && (NTn % 4 == 0);
+  const int nbk = KT >> 3;
   for (int t = threadIdx.x; t < ntiles; t += NT) {
-    const int tk = t % KT, tn = t / KT;
+    int tk, tn;
+    if (blocked) {
+      const int bid = t >> 5, l = t & 31;
+      tk = (bid % nbk) * 8 + (l & 7);
+      tn = (bid / nbk) * 4 + (l >> 3);
+    } else {
+      tk = t % KT;
+      tn = t / KT;
+    }
     float acc[TK][TN];
     float bs[TN];
 #pragma unroll

@@ -1,0 +1,131 @@
+"""Host-side mirror of the reference API: flags, schedules, early stopping, logger, model setup."""
+import numpy as np
+import pytest
+import torch
+
+import golden_util as gu
+from helpers import PRESET, build_from_golden, make_args
+
+
+def test_parser_defaults_match_reference():
+    from dpivae_b200 import make_parser
+
+    a, _ = make_parser().parse_known_args([])
+    expect = dict(n_iter=20000, n_train=1024, n_val=512, n_test=512, n_batch=64, n_mc_train=16, n_mc_val=64,
+                  n_mc_test=512, val_freq=10, lambda_g0=1 / 256, lr=1e-3, lr_sigma=5e-3, patience=200, min_delta=0.001,
+                  use_seed=False, seed=123, full_cov_prior=False, clip_gradients=False, lambda_x=None,
+                  beta_y_n_cycles=4, beta_y_mu=0.2, lambda_annealing=None, alpha_x=1.0, wd_e=0.0, max_grad_norm=1.0)
+    for k, v in expect.items():
+        assert getattr(a, k) == v, k
+
+
+def test_annealing_schedules():
+    from dpivae_b200 import Annealing
+
+    assert float(Annealing(None, 100).forward(3)) == 1.0
+    cyc = Annealing("cyclical", 100, n_cycles=5, R=0.5)
+    assert float(cyc.forward(0)) == 0.0 and abs(float(cyc.forward(5)) - 0.5) < 1e-12 and float(cyc.forward(15)) == 1.0
+    sig = Annealing("sigmoid", 1000, mu=0.15, cov=0.15)
+    assert abs(float(sig.forward(150)) - 0.5) < 1e-6 and float(sig.forward(0)) < 1e-6
+    with pytest.raises(ValueError):
+        Annealing("bogus", 10).forward(0)
+
+
+def test_early_stopping_semantics():
+    from dpivae_b200 import EarlyStopping
+
+    es = EarlyStopping(patience=2, min_delta=0.1)
+    assert not es.early_stop(1.0)
+    assert not es.early_stop(0.95)   # not an improvement by min_delta, not worse than best -> no count
+    assert not es.early_stop(1.2)    # worse: counter 1
+    assert es.early_stop(1.3)        # counter 2 -> stop
+    es2 = EarlyStopping(patience=2, min_delta=0.1)
+    es2.early_stop(1.0); es2.early_stop(1.2); es2.early_stop(0.5)
+    assert es2.counter == 0
+
+
+def test_scalar_logger_surface():
+    from dpivae_b200 import ScalarLogger, get_logger_training_curve
+
+    lg = ScalarLogger()
+    lg.log_scalar("ELBO", torch.tensor(1.5), 0)
+    lg.log_scalar("ELBO", 2.5, 1)
+    assert lg.experiment.scalars["ELBO"] == [(0, 1.5), (1, 2.5)]
+    assert get_logger_training_curve(lg, "ELBO") == ([0, 1], [1.5, 2.5])
+
+
+@pytest.mark.parametrize("case,mtype", gu.CONFIGS)
+def test_setup_model_reproduces_reference_init_and_keys(case, mtype):
+    """--use_seed 123: nn.Linear creation order mirrors dpivae.py:156-250 -> tensor-for-tensor the reference's
+    initial weights; state_dict names and fitted scaler statistics match too."""
+    import importlib
+
+    import dpivae_b200 as dpv
+
+    g, spec, sd = gu.load(case, mtype)
+    case_mod = importlib.import_module(f"dpivae_b200.cases.{case}")
+    x, c, y = (torch.from_numpy(g[k].copy()) for k in "xcy")
+    args = make_args(case_mod, PRESET[(case, mtype)], use_seed=True, seed=123, n_train=x.shape[0], n_batch=x.shape[0])
+    vae = dpv.setup_model(args, case_mod.definition, (x, c, y))
+    mine = vae.state_dict()
+    trainable = [k for k in mine if not k.startswith("decoder_x.model.")]
+    assert sorted(trainable) == sorted(spec["trainable"])
+    for k in spec["trainable"]:
+        assert torch.equal(mine[k], sd[k]), k
+    for nm, tr in (("x", vae.transform_x), ("c", vae.transform_c), ("y", vae.transform_y)):
+        assert np.allclose(tr.mean_.numpy().reshape(-1), g[f"spec.mean_{nm}"], rtol=1e-6, atol=0)
+        assert np.allclose(tr.scale_.numpy().reshape(-1), g[f"spec.std_{nm}"], rtol=1e-6, atol=0)
+    assert list(vae.idx_c_phys) == spec["idx_c_phys"]
+    assert sum(p.numel() for p in vae.parameters() if p.requires_grad) == \
+        {"bridge": {"P": 28113, "S": 35793}, "damped_oscillator": {"P": 27400, "S": 32696},
+         "simple_beam": {"P": 14085, "S": 16605}}[case][mtype]
+
+
+def test_setup_model_errors():
+    import dpivae_b200 as dpv
+    from dpivae_b200.cases import simple_beam as case
+
+    x = torch.randn(8, 32); c = torch.randn(8, 1); y = torch.randn(8, 1)
+    args = make_args(case, "dpivae", n_train=8, n_batch=8)
+    args.model_type = "Q"
+    with pytest.raises(ValueError):
+        dpv.setup_model(args, case.definition, (x, c, y))
+    args = make_args(case, "dpivae", n_train=9, n_batch=8)
+    with pytest.raises(AssertionError):
+        dpv.setup_model(args, case.definition, (x, c, y))
+    args = make_args(case, "vae", n_train=8, n_batch=8, encoder_c="CNN")
+    with pytest.raises(ValueError):
+        dpv.setup_model(args, case.definition, (x, c, y))
+    bad = dict(case.definition)
+    bad["nz_x"] = 3
+    with pytest.raises(ValueError):
+        dpv.setup_model(make_args(case, "vae", n_train=8, n_batch=8), bad, (x, c, y))
+
+
+def test_param_groups_follow_reference():
+    import dpivae_b200 as dpv
+    from dpivae_b200.cases import bridge
+
+    a = make_args(bridge, "DPIVAE-A", lr_ex=2e-3, wd_e=0.1)
+    g = dpv.param_groups(a)
+    assert [n for n, _, _ in g] == ["encoder", "encoder_c", "encoder_y", "prior_net_c", "prior_net_y", "decoder_x",
+                                    "decoder_c", "decoder_y", "log_sigma_x"]
+    assert g[0][1] == 2e-3 and g[0][2] == 0.1 and g[-1][1] == 5e-3
+    b = make_args(bridge, "DPIVAE-B")
+    assert [n for n, _, _ in dpv.param_groups(b)][0:2] == ["encoder", "prior_net_c"]
+
+
+def test_case_physics_models_match_assets():
+    """part_model / full_model torch forwards (data generation, plotting) agree with the oracle physics."""
+    from oracle import dpivae_oracle as orc
+    from dpivae_b200.cases import bridge, damped_oscillator, simple_beam
+
+    torch.manual_seed(0)
+    for case, name, zin in ((bridge, "bridge", 3), (damped_oscillator, "damped_oscillator", 1), (simple_beam, "simple_beam", 2)):
+        z = torch.rand(5, zin) * 0.4 + torch.tensor({"bridge": [10.0, 10.0, -0.2], "damped_oscillator": [1.2],
+                                                     "simple_beam": [3.0, 0.3]}[name])
+        phys = orc.cast_spec({"physics": gu.physics_spec(name), **{k: [0.0] for k in
+                              ["mean_x", "std_x", "mean_c", "std_c", "mean_y", "std_y", "lb", "ub"]}}, torch.float32)["physics"]
+        ref = orc.PHYSICS[phys["kind"]](phys, z)
+        out = case.definition["part_model"](z)
+        assert torch.allclose(out, ref, rtol=1e-6, atol=1e-6), name
