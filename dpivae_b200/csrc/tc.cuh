@@ -1,0 +1,203 @@
+// tcgen05 / TMEM / mbarrier primitives (inline PTX, sm_100a) used by the tensor-core decoder kernel.
+//
+// Operand storage ("X8" layout, 16-bit elements): a matrix with R rows and C columns (C % 8 == 0) is
+// kept in shared memory as uint4 X8[C/8][R], X8[c/8][r] = the 8 halves X[r][c .. c+7].  With NO
+// swizzle this single array is a valid tcgen05 canonical layout in BOTH orientations:
+//   K-major  operand (MN index = r, K index = c): core matrix = 8 rows x 16 B contiguous (128 B),
+//            SBO (next 8 rows) = 128 B, LBO (next 16 B of K) = R * 16 B.
+//   MN-major operand (MN index = c, K index = r): core matrix = 8 K-rows x 16 B (8 MN elements),
+//            SBO (next 8 MN elements) = R * 16 B, LBO (next 8 K rows) = 128 B.
+// So forward (activations x weights^T), dgrad (gradients x weights) and wgrad (activations^T x
+// gradients) all read the same buffers; only the descriptor orientation changes.  (32-bit tf32
+// operands cannot do this: MN-major tf32 exists only in the SWIZZLE_128B_BASE32B layout -- measured,
+// tools/microbench/tc_layout_probe.cu -- which no K-major layout matches.)
+//
+// FP32 accuracy on the fp16 tensor pipe: every fp32 operand x is split x = hi + lo with
+// hi = fp16(x), lo = fp16(x - hi) (22 significant bits) and each GEMM is issued as the three
+// products hi*hi + lo*hi + hi*lo into the same fp32 TMEM accumulator.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dpv {
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- shared-memory matrix descriptor (no swizzle, descriptor version 1) ----------------------
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= 1ull << 46;
+  return d;
+}
+// X8 buffer with R rows, used K-major starting at column chunk `chunk0` (8 columns per chunk)
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t base, int R, int chunk0) {
+  return make_desc(base + (uint32_t)(chunk0 * R) * 16u, (uint32_t)R * 16u, 128u);
+}
+// X8 buffer with R rows, used MN-major: MN starts at column chunk `chunk0`, K starts at row `row0`
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t base, int R, int chunk0, int row0) {
+  return make_desc(base + (uint32_t)(chunk0 * R + row0) * 16u, 128u, (uint32_t)R * 16u);
+}
+
+// instruction descriptor: kind::f16 with fp16 operands, fp32 accumulate, M x N tile, operand majors (0 = K, 1 = MN)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// D[tmem] (+)= A[smem] * B[smem]; one K = 16 step (32 bytes of fp16 along K)
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// generic-proxy shared-memory writes -> visible to the async proxy (tensor core operand reads)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+
+// ---- TMEM ------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {  // one full warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  // the allocating warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// 32 lanes x 32 consecutive columns: thread t of the warp gets row (lane quadrant base + t)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  tmem_wait_ld();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  tmem_wait_ld();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
+  uint32_t r[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(v[i]);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+  tmem_wait_st();
+}
+
+// ---- fp32 -> (hi, lo) fp16 split of 8 consecutive values, packed as two uint4 ------------------
+__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half2 hh = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    const float2 hf = __half22float2(hh);
+    const __half2 ll = __floats2half2_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// A split operand: hi plane at `base`, lo plane at `base + lo_off` (bytes), both X8 with R rows.
+struct Op {
+  uint32_t base, lo_off;
+  int R;
+};
+
+// GEMM issue helpers (ONE thread); k extents in elements, multiples of 16.  `terms` = 3 issues
+// hi*hi + lo*hi + hi*lo (fp32-accurate), `terms` = 1 only hi*hi (plain fp16 inputs).
+//   fwd   : D[128 rows of A][N]   (+)= sum_k A[r][k] * W[n][k]      A K-major, W K-major (N rows)
+__device__ __forceinline__ void issue_fwd(uint32_t d_tmem, Op a, Op w, int N, int K, uint32_t accumulate, int terms) {
+  const uint32_t idesc = make_idesc(128, N, 0, 0);
+  for (int t = 0; t < terms; ++t) {
+    const uint32_t ab = a.base + (t == 1 ? a.lo_off : 0u), wb = w.base + (t == 2 ? w.lo_off : 0u);
+    for (int k = 0; k < K; k += 16) {
+      mma_f16(d_tmem, desc_kmajor(ab, a.R, k >> 3), desc_kmajor(wb, w.R, k >> 3), idesc, accumulate);
+      accumulate = 1;
+    }
+  }
+}
+//   dgrad : D[128 rows of G][Kin] (+)= sum_n G[r][n] * W[n][kin]    G K-major, W (Nout rows) MN-major over kin
+__device__ __forceinline__ void issue_dgrad(uint32_t d_tmem, Op g, Op w, int Nout, int Kin, uint32_t accumulate, int terms) {
+  const uint32_t idesc = make_idesc(128, Kin, 0, 1);
+  for (int t = 0; t < terms; ++t) {
+    const uint32_t gb = g.base + (t == 1 ? g.lo_off : 0u), wb = w.base + (t == 2 ? w.lo_off : 0u);
+    for (int n = 0; n < Nout; n += 16) {
+      mma_f16(d_tmem, desc_kmajor(gb, g.R, n >> 3), desc_mnmajor(wb, w.R, 0, n), idesc, accumulate);
+      accumulate = 1;
+    }
+  }
+}
+//   wgrad : D[128 cols of H][N cols of G] (+)= sum_r H[r][m] * G[r][n]   both MN-major, r over R rows
+__device__ __forceinline__ void issue_wgrad(uint32_t d_tmem, Op h, Op g, int N, uint32_t accumulate, int terms) {
+  const uint32_t idesc = make_idesc(128, N, 1, 1);
+  for (int t = 0; t < terms; ++t) {
+    const uint32_t hb = h.base + (t == 1 ? h.lo_off : 0u), gb = g.base + (t == 2 ? g.lo_off : 0u);
+    for (int r = 0; r < h.R; r += 16) {
+      mma_f16(d_tmem, desc_mnmajor(hb, h.R, 0, r), desc_mnmajor(gb, g.R, 0, r), idesc, accumulate);
+      accumulate = 1;
+    }
+  }
+}
+
+}  // namespace tc
+}  // namespace dpv
