@@ -171,6 +171,8 @@ def main():
     ap.add_argument("--workload", default="bridge_p", choices=list(WORKLOADS))
     ap.add_argument("--rows", type=int, default=0, help="override rows per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--math", default="fp32", choices=["fp32", "tc_fp16x3", "tc_fp16"],
+                    help="decoder GEMM arithmetic (include/dpivae_b200.h DPIVAE_MATH_*)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     wl = dict(WORKLOADS[a.workload])
@@ -213,6 +215,7 @@ def main():
     x, c, y = synth(case_mod, rows, 1000 + rank, dev)  # this rank's shard, resident in HBM
     dp = DataParallelStep(vae, dpv.param_groups(args))
     eng = dp.eng
+    eng.set_math_mode(a.math)
     w = (1.0, 1.0, 1.0, 1.0)
     torch.manual_seed(99)  # same Philox seed/offset on every rank; noise indexed by global row
 
@@ -318,7 +321,7 @@ def main():
                          "hbm_gbs_achieved": wl["bytes_row"] * rows / (ms_step * 1e-3) / 1e9,
                          "kernel_ms": kshare},
             "clocks": clk.summary(),
-            "elbo": loss_now,
+            "elbo": loss_now, "math": a.math, "tensor_cores": eng.used_tensor_cores(),
         }
         if not a.no_cpu_baseline and n_gpus == 1:
             val, sec, threads, crow = cpu_oracle_throughput(wl, 3, 1)

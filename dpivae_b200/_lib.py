@@ -67,7 +67,9 @@ EXPORTS = [
     "dpivae_bind", "dpivae_set_groups", "dpivae_workspace_bytes", "dpivae_loss", "dpivae_adam_step",
     "dpivae_train_step", "dpivae_encode", "dpivae_philox_plan", "dpivae_last_launch_count",
     "dpivae_set_timing", "dpivae_last_kernel_ms", "dpivae_ffma_peak_tflops", "dpivae_set_phase_buffer",
+    "dpivae_set_math_mode", "dpivae_last_used_tensor_cores",
 ]
+MATH_FP32, MATH_TC_FP16X3, MATH_TC_FP16 = 0, 1, 2
 
 _lib = None
 
@@ -106,6 +108,8 @@ def load():
     lib.dpivae_set_phase_buffer.argtypes = [vp, vp]
     lib.dpivae_last_kernel_ms.argtypes = [vp, C.POINTER(f32)]
     lib.dpivae_ffma_peak_tflops.argtypes = [C.POINTER(f32), vp]
+    lib.dpivae_set_math_mode.argtypes = [vp, i32]
+    lib.dpivae_last_used_tensor_cores.argtypes = [vp]
     for name in EXPORTS:
         getattr(lib, name)  # fail loudly on a stale library
     _lib = lib

@@ -16,6 +16,7 @@ int configure_dec_kernel();
 int configure_enc_kernels();
 }  // namespace dpv
 
+
 using namespace dpv;
 
 static thread_local std::string g_err;
@@ -46,6 +47,10 @@ struct dpivae_model {
   float lr[16], wd[16];
   int last_launches = 0;
   long long part_stride = 0;
+  int math_mode = 0;        // DPIVAE_MATH_*
+  TcParams tc;              // tensor-core decoder plan
+  int tc_ok = 0;            // model shape supported by dec_tc_kernel
+  int last_dec_tc = 0;      // the last hot-path call ran the tensor-core decoder kernel
   int timing = 0;
   cudaEvent_t ev[10] = {};   // start/stop pairs: enc_fwd, dec, enc_bwd, reduce, adam
   int ev_used[5] = {0, 0, 0, 0, 0};
@@ -251,6 +256,48 @@ static int build_plan(dpivae_model* h) {
   E.n_params = d.n_params;
   if (enc_smem_bytes(E, true) > 232448) return fail("encoder kernel shared-memory plan exceeds 227 KB");
   h->part_stride = (long long)align_up((size_t)d.n_params + NSCAL, 64);
+
+  // ---- shared-memory plan of the tensor-core decoder kernel (byte offsets) ----
+  TcParams& T = h->tc;
+  memset(&T, 0, sizeof(T));
+  h->tc_ok = 0;
+  {
+    const bool mlp = d.phys_kind == DPIVAE_PHYS_MLP;
+    const int need = nzd + 1 + (mlp ? nzin : 0);
+    bool ok = need <= 16 && (d.nd_x == 32 || d.nd_x == 64) && !d.has_lambda_x && 2 * d.nd_c <= 8 && 2 * d.nd_y <= 8;
+    if (mlp) ok = ok && d.phys_n_layers == 4 && d.phys_dims[1] == 64 && d.phys_dims[2] == 32 && d.phys_dims[3] == 64;
+    if (ok) {
+      const int KZ = 16, d1 = mlp ? 64 : 0, d2 = mlp ? 32 : 0, d3 = mlp ? 64 : 0;
+      T.KZ = KZ; T.c_ones = nzd; T.c_s0 = nzd + 1;
+      int b = 0;
+      auto plane2 = [&](int chunks, int rows, int& off, int& lo) {   // hi + lo planes
+        const int bytes = chunks * rows * 16;
+        off = b; lo = bytes; b += 2 * bytes;
+      };
+      plane2(KZ / 8, 128, T.w_fx0, T.l_fx0);
+      plane2(KZ / 8, 128, T.w_ax0, T.l_ax0);
+      plane2(16, 16, T.w_ax1, T.l_ax1);
+      plane2(16, d.nd_x, T.w_fx1, T.l_fx1);
+      if (mlp) {
+        plane2(KZ / 8, d1, T.w_p[0], T.l_p[0]);
+        plane2(d1 / 8, d2, T.w_p[1], T.l_p[1]);
+        plane2(d2 / 8, d3, T.w_p[2], T.l_p[2]);
+        plane2(d3 / 8, d.nd_x, T.w_p[3], T.l_p[3]);
+      }
+      plane2(16, 128, T.a_big, T.l_big);
+      plane2(8, 128, T.a_g, T.l_g);
+      plane2(KZ / 8, 128, T.a_lat, T.l_lat);
+      auto f32 = [&](int floats) { int off = b; b += ((floats + 3) & ~3) * 4; return off; };
+      T.f_inv = f32(16); T.f_bias_x = f32(64); T.f_bias_p1 = f32(32); T.f_bias_p2 = f32(64); T.f_bias_a1 = f32(16);
+      T.f_eps = f32(Z * 128); T.f_u = f32(4 * 128); T.f_zxin = f32((nzin > 4 ? nzin : 4) * 128); T.f_zd = f32(nzd * 128);
+      T.f_dza = f32(nzd * 128); T.f_dzx = f32(4 * 128); T.f_sc = f32(8 * 128);
+      T.f_rowpar = f32(P.n_rowpar * RBMAX); T.f_rowraw = f32((d.nd_c + d.nd_y) * RBMAX); T.f_red = f32(256);
+      T.o_bar = b; b += 16;
+      T.total = (b + 127) & ~127;
+      const int feat_bytes = (P.n_feat * 128 + (P.n_feat + 5) * RBMAX) * 4;
+      if (T.total <= 232448 && feat_bytes <= 2 * T.l_big && 256 * 33 * 4 <= 2 * T.l_big) h->tc_ok = 1;
+    }
+  }
   return 0;
 }
 
@@ -273,7 +320,7 @@ int dpivae_create(const dpivae_model_desc_t* desc, dpivae_handle_t* out) {
   h->d = *desc;
   h->sm_count = prop.multiProcessorCount;
   if (build_plan(h)) { delete h; return 1; }
-  if (configure_dec_kernel() || configure_enc_kernels()) { delete h; return fail("cudaFuncSetAttribute(max dynamic smem) failed"); }
+  if (configure_dec_kernel() || configure_enc_kernels() || configure_dec_tc_kernel()) { delete h; return fail("cudaFuncSetAttribute(max dynamic smem) failed"); }
   // owner map: which kernel's partials hold each parameter's gradient
   std::vector<unsigned char> owner((size_t)desc->n_params, 0);
   for (int u = 0; u < h->enc.n_units; ++u) {
@@ -350,6 +397,8 @@ struct WsLayout {
   size_t hid, headpre, gpre, rowloss, part, scal, total;
   int grid_enc, grid_dec, RB, n_chunks;
   long long n_rowblocks;
+  int tc_RB, tc_grid;           // tensor-core decoder kernel: rows per 128-pair tile, CTAs
+  long long tc_rowblocks;
 };
 
 static WsLayout ws_layout(dpivae_handle_t h, int64_t B, int32_t n_mc) {
@@ -370,6 +419,11 @@ static WsLayout ws_layout(dpivae_handle_t h, int64_t B, int32_t n_mc) {
   L.grid_dec = (int)(L.n_rowblocks < h->sm_count ? L.n_rowblocks : h->sm_count);
   if (L.grid_enc < 1) L.grid_enc = 1;
   if (L.grid_dec < 1) L.grid_dec = 1;
+  L.tc_RB = 128 / (n_mc < 1 ? 1 : (n_mc > 128 ? 128 : n_mc));
+  if (L.tc_RB < 1) L.tc_RB = 1;
+  L.tc_rowblocks = (B + L.tc_RB - 1) / L.tc_RB;
+  L.tc_grid = (int)(L.tc_rowblocks < h->sm_count ? L.tc_rowblocks : h->sm_count);
+  if (L.tc_grid < 1) L.tc_grid = 1;
   L.part = take((size_t)(2 * h->sm_count) * h->part_stride);
   L.scal = take(16);
   L.total = o;
@@ -406,6 +460,12 @@ static int run_loss(dpivae_handle_t h, const dpivae_batch_t* bt, const dpivae_rn
   float* scal = (float*)(base + L.scal);
   int launches = 0;
 
+  const bool extra_out = out && (out->xh_p || out->xh_d || out->ch || out->log_sigma_c || out->yh || out->log_sigma_y);
+  const bool use_tc = h->math_mode != DPIVAE_MATH_FP32 && h->tc_ok && !latent_only && !bt->cond && !extra_out &&
+                      bt->n_mc >= 8 && bt->n_mc <= 128;
+  h->last_dec_tc = use_tc ? 1 : 0;
+  const int grid_dec = use_tc ? L.tc_grid : L.grid_dec;
+
   EncParams E = h->enc;
   E.params = h->params;
   E.x = bt->x; E.c = bt->c; E.y = bt->y; E.idx = (const long long*)bt->idx;
@@ -413,7 +473,7 @@ static int run_loss(dpivae_handle_t h, const dpivae_batch_t* bt, const dpivae_rn
   E.hid = hid; E.headpre = headpre; E.gpre = gpre;
   E.with_hid = with_grad;
   E.x_is_standardised = x_std;
-  E.part = part + (long long)L.grid_dec * h->part_stride;
+  E.part = part + (long long)grid_dec * h->part_stride;
   E.part_stride = h->part_stride;
   if (latent_only) E.n_units = h->n_enc_units;  // prior nets not needed for encode
   const size_t enc_smem = enc_smem_bytes(h->enc, true);
@@ -442,7 +502,17 @@ static int run_loss(dpivae_handle_t h, const dpivae_batch_t* bt, const dpivae_rn
     D.out.yh = out->yh; D.out.lsy = out->log_sigma_y; D.out.zx = out->zx; D.out.zc = out->zc; D.out.zy = out->zy;
     D.out.dens = out->dens_z;
   }
-  { KTimer t(h, 1, st); launch_dec(D, L.grid_dec, st); }
+  if (use_tc) {
+    TcParams T = h->tc;
+    D.RB = L.tc_RB; D.n_chunks = 1; D.n_rowblocks = L.tc_rowblocks;
+    T.d = D;
+    T.terms = h->math_mode == DPIVAE_MATH_TC_FP16X3 ? 3 : 1;
+    KTimer t(h, 1, st);
+    launch_dec_tc(T, grid_dec, st);
+  } else {
+    KTimer t(h, 1, st);
+    launch_dec(D, grid_dec, st);
+  }
   ++launches;
 
   if (with_grad) {
@@ -452,7 +522,7 @@ static int run_loss(dpivae_handle_t h, const dpivae_batch_t* bt, const dpivae_rn
   if (!latent_only) {
     ReduceParams R;
     R.part = part; R.part_stride = h->part_stride;
-    R.n_cta_dec = L.grid_dec; R.n_cta_enc = L.grid_enc;
+    R.n_cta_dec = grid_dec; R.n_cta_enc = L.grid_enc;
     R.n_params = h->d.n_params;
     R.owner = h->d_owner;
     R.grads = with_grad ? h->grads : nullptr;
@@ -543,6 +613,16 @@ uint64_t dpivae_philox_plan(dpivae_handle_t h, int64_t B_global, int32_t n_mc, i
 }
 
 int dpivae_last_launch_count(dpivae_handle_t h) { return h ? h->last_launches : 0; }
+
+int dpivae_set_math_mode(dpivae_handle_t h, int32_t mode) {
+  if (!h) return fail("null handle");
+  if (mode != DPIVAE_MATH_FP32 && mode != DPIVAE_MATH_TC_FP16X3 && mode != DPIVAE_MATH_TC_FP16)
+    return fail("unknown math mode");
+  h->math_mode = mode;
+  return 0;
+}
+
+int dpivae_last_used_tensor_cores(dpivae_handle_t h) { return h ? h->last_dec_tc : 0; }
 
 int dpivae_set_phase_buffer(dpivae_handle_t h, void* dev_counters16) {
   if (!h) return fail("null handle");

@@ -1,0 +1,1014 @@
+// Tensor-core (tcgen05 / TMEM) variant of the decoder-side fused kernel of the DPI-VAE step (sm_100a).
+//
+// Same contract as dec_kernel.cu (models/vae.py:160-231, models/decoders.py, models/nn.py:67-80,
+// dpivae.py:419-429), but every GEMM of the decoders -- forward, dgrad and wgrad -- runs on the 5th-gen
+// tensor cores:
+//   * one persistent CTA per SM walks tiles of 128 (row, MC-sample) pairs = the M dimension of
+//     tcgen05.mma.cta_group::1.kind::f16 (M = 128), accumulators in TMEM, operands in shared memory in
+//     the dual-orientation X8 layout of tc.cuh (the same buffer is read K-major by forward / dgrad and
+//     MN-major by wgrad);
+//   * fp32 accuracy: operands are split x = hi + lo into two fp16 planes (power-of-two pre-scaling keeps
+//     them in the fp16 normal range) and each GEMM issues hi*hi + lo*hi + hi*lo into one fp32
+//     accumulator (terms = 3); terms = 1 is the plain fp16-input mode;
+//   * weight gradients of the trainable decoders accumulate in TMEM across ALL tiles of the CTA and are
+//     read back once at the end of the kernel (no per-tile reduction traffic); bias gradients ride on a
+//     constant-one input column (first layers) or on per-thread running sums (output layers);
+//   * the 256 threads are the epilogue: thread (quadrant q, lane, half hh) owns pair p = 32 q + lane and
+//     one half of the accumulator columns, applies bias / ReLU / tanh / likelihood gradients and writes
+//     the next operand straight back to shared memory.
+// The auxiliary decoders c and y run as ONE block-diagonal MLP (zc|zy -> 64|64 -> c-head|y-head).
+#include <cuda_fp16.h>
+#include <curand_kernel.h>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "tc.cuh"
+
+namespace dpv {
+
+namespace {
+
+constexpr int TP = 128;    // pairs per tile
+constexpr int TNT = 256;   // threads per CTA
+// TMEM column map (fp32 columns, 128 lanes)
+enum { C_W1 = 0, C_W0 = 64, C_AW1 = 80, C_AW0 = 96, C_H = 112, C_X = 240, C_S = 304, C_A0 = 336, C_A1 = 400, C_A2 = 432, C_ALLOC = 512 };
+// power-of-two operand scales (exponents)
+constexpr int E_LAT = 4, E_H = 6, E_T = 8;
+// scalar rows (one value per pair)
+enum { S_KL = 0, S_RX, S_RC, S_RY, S_REG, S_W, S_Q0, S_Q1, S_ROWS };
+// inverse-scale table
+enum { I_AX0 = 0, I_AX1, I_AX1D, I_AX0D, I_FX0, I_P0, I_P1, I_P2, I_X, I_XD, I_FX0D, I_P2D, I_P1D, I_P0D, I_COUNT };
+
+__device__ __forceinline__ float philox_normal_tc(unsigned long long seed, unsigned long long offset, unsigned int T,
+                                                  unsigned long long li) {
+  const unsigned long long sub = li % T;
+  const unsigned long long q4 = li / T;
+  const unsigned long long it = q4 >> 2;
+  const int comp = (int)(q4 & 3ull);
+  curandStatePhilox4_32_10_t st;
+  curand_init(seed, sub, offset + 4ull * it, &st);
+  const float4 r = curand_normal4(&st);
+  return comp == 0 ? r.x : (comp == 1 ? r.y : (comp == 2 ? r.z : r.w));
+}
+
+__device__ __forceinline__ int block_of_tc(const DecParams& P, int i) {
+  int b = 0;
+  while (b + 1 < P.n_blk && i >= P.blk_start[b + 1]) ++b;
+  return b;
+}
+
+// write 8 consecutive columns (chunk) of row `row` of an X8 operand: hi plane + lo plane
+__device__ __forceinline__ void put8(unsigned char* plane, uint32_t lo_off, int R, int chunk, int row, const float* v) {
+  uint4 hi, lo;
+  tc::split8(v, hi, lo);
+  unsigned char* dst = plane + ((size_t)chunk * R + row) * 16;
+  *reinterpret_cast<uint4*>(dst) = hi;
+  *reinterpret_cast<uint4*>(dst + lo_off) = lo;
+}
+
+template <int W>
+__device__ __forceinline__ void tld(uint32_t taddr, float* v) {
+  if (W == 32) tc::tmem_ld32(taddr, v);
+  else tc::tmem_ld16(taddr, v);
+}
+
+__device__ __forceinline__ tc::Op mkop(unsigned char* sm, int off, uint32_t lo_off, int R, int col0 = 0) {
+  tc::Op o;
+  o.base = tc::smem_u32(sm + off) + (uint32_t)((col0 >> 3) * R) * 16u;
+  o.lo_off = lo_off;
+  o.R = R;
+  return o;
+}
+
+template <class F>
+__device__ __forceinline__ void mma_stage(uint64_t* bar, uint32_t& phase, F issue) {
+  tc::fence_async_smem();
+  tc::fence_before_sync();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    tc::fence_after_sync();
+    issue();
+    tc::commit(bar);
+  }
+  tc::mbar_wait(bar, phase);
+  phase ^= 1u;
+  __syncwarp();
+  tc::fence_after_sync();
+}
+
+// block-wide max of |v| over a strided getter; result broadcast (uses red[8])
+template <class G>
+__device__ float block_absmax(int count, G get, float* red) {
+  float m = 0.0f;
+  for (int e = threadIdx.x; e < count; e += TNT) m = fmaxf(m, fabsf(get(e)));
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  float r = red[0];
+#pragma unroll
+  for (int w = 1; w < TNT / 32; ++w) r = fmaxf(r, red[w]);
+  return r;
+}
+// exponent k with max * 2^k in [256, 512)
+__device__ __forceinline__ int scale_exp(float mx) {
+  if (!(mx > 0.0f) || !isfinite(mx)) return 0;
+  int e;
+  frexpf(mx, &e);  // mx = m * 2^e, m in [0.5, 1)
+  return 9 - e;
+}
+
+// stage a (N x KP) operand whose element (n, k) is get(n, k), scaled by 2^kexp, into an X8 hi/lo plane pair
+template <class G>
+__device__ void stage_weight(unsigned char* plane, uint32_t lo_off, int N, int KP, int kexp, G get) {
+  const float s = exp2f((float)kexp);
+  const int nch = KP >> 3;
+  for (int e = threadIdx.x; e < nch * N; e += TNT) {
+    const int ch = e / N, n = e - ch * N;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = get(n, 8 * ch + i) * s;
+    put8(plane, lo_off, N, ch, n, v);
+  }
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ TcParams T) {
+  const DecParams& P = T.d;
+  extern __shared__ __align__(1024) unsigned char smb[];
+  float* smf = reinterpret_cast<float*>(smb);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int q = warp & 3, hh = warp >> 2;
+  const int p = 32 * q + lane;  // pair (TMEM lane) owned in the epilogues
+  const int n = P.n_mc;
+  const int nzd = P.nz_c + P.nz_y;
+  const int nzin = P.nz_x + P.nd_p;
+  const int ndx = P.nd_x, nxh = ndx >> 1;  // columns of the x head per thread
+  const long long B = P.B;
+  const int terms = T.terms;
+  const bool mlp = P.phys_kind == 0;
+  const int d1 = mlp ? P.pl[0].N : 0, d2 = mlp ? P.pl[1].N : 0, d3 = mlp ? P.pl[2].N : 0;
+  float* part = P.part + (long long)blockIdx.x * P.part_stride;
+
+  float* INV = smf + (T.f_inv >> 2);
+  float* BX = smf + (T.f_bias_x >> 2);    // fx1 bias (+ last physics-layer bias)
+  float* BP1 = smf + (T.f_bias_p1 >> 2);
+  float* BP2 = smf + (T.f_bias_p2 >> 2);
+  float* BA1 = smf + (T.f_bias_a1 >> 2);  // aux head biases, c at 0.., y at 8..
+  float* EPS = smf + (T.f_eps >> 2);
+  float* U = smf + (T.f_u >> 2);
+  float* ZXIN = smf + (T.f_zxin >> 2);
+  float* ZD = smf + (T.f_zd >> 2);
+  float* DZA = smf + (T.f_dza >> 2);
+  float* DZX = smf + (T.f_dzx >> 2);
+  float* SC = smf + (T.f_sc >> 2);
+  float* ROWPAR = smf + (T.f_rowpar >> 2);
+  float* ROWRAW = smf + (T.f_rowraw >> 2);
+  float* RED = smf + (T.f_red >> 2);
+  float* FEAT = smf + (T.a_big >> 2);  // aliases the BIG operand buffer (dead by then)
+  float* ROWACC = FEAT + P.n_feat * TP;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smb + T.o_bar);
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(smb + T.o_bar + 8);
+
+  // ---- one-time: zero smem, barrier, TMEM, weights -------------------------------------------------
+  for (int e = tid; e < (T.total >> 2); e += TNT) smf[e] = 0.0f;
+  __syncthreads();
+  if (tid == 0) {
+    tc::mbar_init(bar, 1);
+    tc::mbar_fence_init();
+  }
+  __syncwarp();
+  if (warp == 0) tc::tmem_alloc(tptr, C_ALLOC);
+
+  const float* prm = P.params;
+  const int c1 = T.c_ones, cs0 = T.c_s0;
+  // element getters of the padded first-layer matrices (bias in the constant-one column)
+  auto g_fx0 = [&](int nn, int k) -> float {
+    if (k < nzd) return prm[P.fx.g_w0 + (long long)nn * nzd + k];
+    return k == c1 ? prm[P.fx.g_b0 + nn] : 0.0f;
+  };
+  auto g_ax0 = [&](int nn, int k) -> float {
+    if (nn < 64) {
+      if (k < P.nz_c) return prm[P.dc.g_w0 + (long long)nn * P.nz_c + k];
+      return k == c1 ? prm[P.dc.g_b0 + nn] : 0.0f;
+    }
+    if (k >= P.nz_c && k < nzd) return prm[P.dy.g_w0 + (long long)(nn - 64) * P.nz_y + (k - P.nz_c)];
+    return k == c1 ? prm[P.dy.g_b0 + nn - 64] : 0.0f;
+  };
+  auto g_ax1 = [&](int nn, int k) -> float {
+    if (nn < 2 * P.nd_c) return k < 64 ? prm[P.dc.g_w1 + (long long)nn * 64 + k] : 0.0f;
+    if (nn >= 8 && nn < 8 + 2 * P.nd_y) return k >= 64 ? prm[P.dy.g_w1 + (long long)(nn - 8) * 64 + (k - 64)] : 0.0f;
+    return 0.0f;
+  };
+  auto g_fx1 = [&](int nn, int k) -> float { return prm[P.fx.g_w1 + (long long)nn * 128 + k]; };
+  auto g_p0 = [&](int nn, int k) -> float {
+    if (k >= cs0 && k < cs0 + nzin) return P.frozen[P.pl[0].g_w + (long long)nn * nzin + (k - cs0)];
+    return k == c1 ? P.frozen[P.pl[0].g_b + nn] : 0.0f;
+  };
+  auto g_p1 = [&](int nn, int k) -> float { return P.frozen[P.pl[1].g_w + (long long)nn * d1 + k]; };
+  auto g_p2 = [&](int nn, int k) -> float { return P.frozen[P.pl[2].g_w + (long long)nn * d2 + k]; };
+  auto g_p3 = [&](int nn, int k) -> float { return P.frozen[P.pl[3].g_w + (long long)nn * d3 + k]; };
+
+  const int KZ = T.KZ;
+  const int k_fx0 = scale_exp(block_absmax(128 * KZ, [&](int e) { return g_fx0(e / KZ, e % KZ); }, RED));
+  const int k_ax0 = scale_exp(block_absmax(128 * KZ, [&](int e) { return g_ax0(e / KZ, e % KZ); }, RED));
+  const int k_ax1 = scale_exp(block_absmax(16 * 128, [&](int e) { return g_ax1(e >> 7, e & 127); }, RED));
+  int k_x = scale_exp(block_absmax(ndx * 128, [&](int e) { return g_fx1(e >> 7, e & 127); }, RED));
+  int k_p0 = 0, k_p1 = 0, k_p2 = 0;
+  if (mlp) {
+    k_p0 = scale_exp(block_absmax(d1 * KZ, [&](int e) { return g_p0(e / KZ, e % KZ); }, RED));
+    k_p1 = scale_exp(block_absmax(d2 * d1, [&](int e) { return g_p1(e / d1, e % d1); }, RED));
+    k_p2 = scale_exp(block_absmax(d3 * d2, [&](int e) { return g_p2(e / d2, e % d2); }, RED));
+    const int k_p3 = scale_exp(block_absmax(ndx * d3, [&](int e) { return g_p3(e / d3, e % d3); }, RED));
+    k_x = min(k_x, k_p3);  // fx1 and the last physics layer accumulate into the same TMEM columns
+  }
+  stage_weight(smb + T.w_fx0, T.l_fx0, 128, KZ, k_fx0, g_fx0);
+  stage_weight(smb + T.w_ax0, T.l_ax0, 128, KZ, k_ax0, g_ax0);
+  stage_weight(smb + T.w_ax1, T.l_ax1, 16, 128, k_ax1, g_ax1);
+  stage_weight(smb + T.w_fx1, T.l_fx1, ndx, 128, k_x, g_fx1);
+  if (mlp) {
+    stage_weight(smb + T.w_p[0], T.l_p[0], d1, KZ, k_p0, g_p0);
+    stage_weight(smb + T.w_p[1], T.l_p[1], d2, d1, k_p1, g_p1);
+    stage_weight(smb + T.w_p[2], T.l_p[2], d3, d2, k_p2, g_p2);
+    stage_weight(smb + T.w_p[3], T.l_p[3], ndx, d3, k_x, g_p3);
+  }
+  for (int e = tid; e < ndx; e += TNT) BX[e] = prm[P.fx.g_b1 + e] + (mlp ? P.frozen[P.pl[3].g_b + e] : 0.0f);
+  if (mlp) {
+    for (int e = tid; e < d2; e += TNT) BP1[e] = P.frozen[P.pl[1].g_b + e];
+    for (int e = tid; e < d3; e += TNT) BP2[e] = P.frozen[P.pl[2].g_b + e];
+  }
+  if (tid < 2 * P.nd_c) BA1[tid] = prm[P.dc.g_b1 + tid];
+  if (tid >= 32 && tid < 32 + 2 * P.nd_y) BA1[8 + tid - 32] = prm[P.dy.g_b1 + tid - 32];
+
+  const float lsx = prm[P.g_lsx];
+  const float sx = expf(lsx);
+  const float var_x = sx * sx;
+  // gradient scale of the x residual: sg = 2^round(log2(64 / sigma_x)), kept inside the fp16 range
+  int e_g = (int)rintf(6.0f - lsx * 1.4426950408889634f);
+  e_g = max(-8, min(e_g, 24));
+  const float sg = exp2f((float)e_g);
+  if (tid == 0) {
+    INV[I_AX0] = exp2f(-(float)(k_ax0 + E_LAT));
+    INV[I_AX1] = exp2f(-(float)(k_ax1 + E_H));
+    INV[I_AX1D] = exp2f(-(float)k_ax1);
+    INV[I_AX0D] = exp2f(-(float)k_ax0);
+    INV[I_FX0] = exp2f(-(float)(k_fx0 + E_LAT));
+    INV[I_P0] = exp2f(-(float)(k_p0 + E_LAT));
+    INV[I_P1] = exp2f(-(float)(k_p1 + E_T));
+    INV[I_P2] = exp2f(-(float)(k_p2 + E_T));
+    INV[I_X] = exp2f(-(float)(k_x + E_H));
+    INV[I_XD] = exp2f(-(float)k_x);
+    INV[I_FX0D] = exp2f(-(float)k_fx0);
+    INV[I_P2D] = exp2f(-(float)k_p2);
+    INV[I_P1D] = exp2f(-(float)k_p1);
+    INV[I_P0D] = exp2f(-(float)k_p0);
+  }
+  if (P.with_grad && tid == 0) part[P.g_lsx] = 0.0f;
+  for (int e = tid; e < NSCAL; e += TNT) part[P.n_params + e] = 0.0f;
+  tc::fence_async_smem();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tb = *tptr;
+  const uint32_t trow = tb + ((uint32_t)(32 * q) << 16);
+  uint32_t phase = 0;
+
+  const float wpair = 1.0f / ((float)P.Bg * (float)(P.nd_x + P.nd_c + P.nd_y) * (float)n);
+  const float cx = -(P.alpha_x * wpair) / var_x / sg;  // true dL/dxh = cx * g~
+  const float awc = P.alpha_c * wpair, awy = P.alpha_y * wpair;
+  const int n_acc = P.n_feat + 5;
+  const bool n_pow2 = (n & (n - 1)) == 0 && n <= 32;
+  const float s_lat = exp2f((float)E_LAT), s_h = exp2f((float)E_H), s_t = exp2f((float)E_T);
+
+  // operands
+  const tc::Op oLAT = mkop(smb, T.a_lat, T.l_lat, TP);
+  const tc::Op oBIG = mkop(smb, T.a_big, T.l_big, TP);
+  const tc::Op oG = mkop(smb, T.a_g, T.l_g, TP);
+  const tc::Op oWFX0 = mkop(smb, T.w_fx0, T.l_fx0, 128), oWAX0 = mkop(smb, T.w_ax0, T.l_ax0, 128);
+  const tc::Op oWAX1 = mkop(smb, T.w_ax1, T.l_ax1, 16), oWFX1 = mkop(smb, T.w_fx1, T.l_fx1, ndx);
+  const tc::Op oWP0 = mkop(smb, T.w_p[0], T.l_p[0], d1 ? d1 : 16), oWP1 = mkop(smb, T.w_p[1], T.l_p[1], d2 ? d2 : 16);
+  const tc::Op oWP2 = mkop(smb, T.w_p[2], T.l_p[2], d3 ? d3 : 16), oWP3 = mkop(smb, T.w_p[3], T.l_p[3], ndx);
+  unsigned char* pBIG = smb + T.a_big;
+  unsigned char* pG = smb + T.a_g;
+  unsigned char* pLAT = smb + T.a_lat;
+
+  // per-thread running sums over all tiles (fixed thread <-> column assignment: deterministic)
+  float dbx[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) dbx[i] = 0.0f;
+  float dba[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) dba[i] = 0.0f;
+  float dlsx = 0.0f;
+  float tot[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  uint32_t wacc = 0;  // 0 on the first tile (weight-gradient accumulators start from zero)
+
+  for (long long rb = blockIdx.x; rb < P.n_rowblocks; rb += gridDim.x) {
+    const long long row0 = rb * P.RB;
+    const int nrows = (int)min((long long)P.RB, B - row0);
+    const int npairs = nrows * n;
+
+    // ---- per-row parameters of q(z|x) and of the conditional priors -------------------------------
+    for (int e = tid; e < RBMAX * P.Z; e += TNT) {
+      const int i = e / RBMAX, r = e - i * RBMAX;
+      const long long lrow = row0 + min(r, nrows - 1);
+      const int b = block_of_tc(P, i), il = i - P.blk_start[b];
+      const float pm = P.headpre[(long long)(P.henc[b] + il) * B + lrow];
+      ROWPAR[(P.rp_loc + i) * RBMAX + r] = clampf_(pm, -50.0f, 50.0f);
+    }
+    for (int e = tid; e < RBMAX * P.nL; e += TNT) {
+      const int li = e / RBMAX, r = e - li * RBMAX;
+      const long long lrow = row0 + min(r, nrows - 1);
+      const int b = P.L_blk[li], i = P.L_i[li], j = P.L_j[li], nzb = P.blk_size[b];
+      float v;
+      if (i == j) {
+        const float ps = P.headpre[(long long)(P.henc[b] + nzb + i) * B + lrow];
+        v = expf(clampf_(ps, -7.0f, 3.0f)) + 1e-8f;
+      } else {
+        const float pc = P.headpre[(long long)(P.henc[b] + 2 * nzb + i * nzb + j) * B + lrow];
+        v = clampf_(pc, -20.0f, 20.0f);
+      }
+      ROWPAR[(P.rp_L + li) * RBMAX + r] = v;
+    }
+    for (int e = tid; e < RBMAX * nzd; e += TNT) {
+      const int k = e / RBMAX, r = e - k * RBMAX;
+      const long long lrow = row0 + min(r, nrows - 1);
+      const int which = k < P.nz_c ? 0 : 1;
+      const int kk = which ? k - P.nz_c : k, nzk = which ? P.nz_y : P.nz_c;
+      float mu = 0.0f, sgm = 1.0f;
+      if (which == 0 || P.y != nullptr) {
+        const float pm = P.headpre[(long long)(P.hpri[which] + kk) * B + lrow];
+        const float ps = P.headpre[(long long)(P.hpri[which] + nzk + kk) * B + lrow];
+        mu = clampf_(pm, -50.0f, 50.0f);
+        sgm = expf(clampf_(ps, -7.0f, 3.0f)) + 1e-8f;
+      }
+      ROWPAR[(P.rp_pmu + k) * RBMAX + r] = mu;
+      ROWPAR[(P.rp_psig + k) * RBMAX + r] = sgm;
+    }
+    for (int e = tid; e < RBMAX * (P.nd_c + P.nd_y); e += TNT) {
+      const int j = e / RBMAX, r = e - j * RBMAX;
+      const long long lrow = row0 + min(r, nrows - 1);
+      const long long drow = P.idx ? P.idx[lrow] : lrow;
+      float v = 0.0f;
+      if (j < P.nd_c) v = P.c[drow * P.nd_c + j];
+      else if (P.y != nullptr) v = P.y[drow * P.nd_y + (j - P.nd_c)];
+      ROWRAW[j * RBMAX + r] = v;
+    }
+    // ---- reparameterisation noise ----------------------------------------------------------------------
+    for (int e = tid; e < TP * P.Z; e += TNT) {
+      const int pp = e & (TP - 1), i = e >> 7;
+      float v = 0.0f;
+      if (pp < npairs) {
+        const int r = pp / n, m = pp - r * n;
+        const unsigned long long grow = (unsigned long long)(P.row_off + row0 + r);
+        const int b = block_of_tc(P, i), il = i - P.blk_start[b], nzb = P.blk_size[b];
+        const unsigned long long li = ((unsigned long long)m * (unsigned long long)P.Bg + grow) * nzb + il;
+        v = P.rng.mode == 0 ? P.rng.eps[b][li] : philox_normal_tc(P.rng.seed, P.rng.offset[b], P.rng.grid_threads[b], li);
+      }
+      EPS[i * TP + pp] = v;
+    }
+    __syncthreads();
+
+    // ---- latents: z = loc + L eps, bijector, log q, log priors (one thread per pair) -------------------
+    if (tid < TP) {
+      const int pp = tid;
+      const bool valid = pp < npairs;
+      const int qq = valid ? pp : npairs - 1;
+      const int r = qq / n, m = qq - r * n;
+      float dens = 0.0f, ld1 = 0.0f, ld2 = 0.0f, lpx = 0.0f;
+      for (int b = 0; b < P.n_blk; ++b) {
+        const int s = P.blk_start[b], nzb = P.blk_size[b];
+        float ss = 0.0f, hld = 0.0f;
+        for (int i = 0; i < nzb; ++i) {
+          float acc = ROWPAR[(P.rp_loc + s + i) * RBMAX + r];
+          const int base = P.rp_L + P.blk_loff[b] + i * (i + 1) / 2;
+          for (int j = 0; j <= i; ++j) acc = fmaf(ROWPAR[(base + j) * RBMAX + r], EPS[(s + j) * TP + pp], acc);
+          const float e = EPS[(s + i) * TP + pp];
+          ss = fmaf(e, e, ss);
+          hld += logf(ROWPAR[(base + i) * RBMAX + r]);
+          const int gi = s + i;
+          if (gi < P.nz_x) {
+            const float u = sigmoidf_(acc);
+            const float a = P.ub[gi] - P.lb[gi];
+            const float zx = fmaf(u, a, P.lb[gi]);
+            ld1 += acc - 2.0f * softplusf_(acc);
+            ld2 += logf(fabsf(a));
+            U[gi * TP + pp] = u;
+            ZXIN[gi * TP + pp] = zx;
+            if (P.prior_kind[gi] == 0) {
+              const bool inside = (zx >= P.prior_a[gi]) && (zx < P.prior_b[gi]);
+              lpx += (inside ? 0.0f : -INFINITY) - logf(P.prior_b[gi] - P.prior_a[gi]);
+            } else {
+              const float d = zx - P.prior_a[gi];
+              lpx += -(d * d) / (2.0f * P.prior_b[gi] * P.prior_b[gi]) - logf(P.prior_b[gi]) - LOG_SQRT_2PI;
+            }
+          } else {
+            ZD[(gi - P.nz_x) * TP + pp] = acc;
+          }
+        }
+        const float lq = -0.5f * ((float)nzb * LOG_2PI + ss) - hld;
+        if (b == 0) dens = lq - (ld1 + ld2);
+        else dens += lq;
+      }
+      for (int j = 0; j < P.nd_p; ++j) ZXIN[(P.nz_x + j) * TP + pp] = ROWRAW[P.idx_c_phys[j] * RBMAX + r];
+      float lpc, lpy;
+      {
+        float mh = 0.0f, hl = 0.0f;
+        for (int k = 0; k < P.nz_c; ++k) {
+          const float sgm = ROWPAR[(P.rp_psig + k) * RBMAX + r];
+          const float t = (ZD[k * TP + pp] - ROWPAR[(P.rp_pmu + k) * RBMAX + r]) / sgm;
+          mh = fmaf(t, t, mh);
+          hl += logf(sgm);
+        }
+        lpc = -0.5f * ((float)P.nz_c * LOG_2PI + mh) - hl;
+        mh = 0.0f; hl = 0.0f;
+        for (int k = P.nz_c; k < nzd; ++k) {
+          const float sgm = ROWPAR[(P.rp_psig + k) * RBMAX + r];
+          const float t = (ZD[k * TP + pp] - ROWPAR[(P.rp_pmu + k) * RBMAX + r]) / sgm;
+          mh = fmaf(t, t, mh);
+          hl += logf(sgm);
+        }
+        lpy = -0.5f * ((float)P.nz_y * LOG_2PI + mh) - hl;
+      }
+      const float klp = dens - ((lpx + lpc) + lpy);
+      SC[S_KL * TP + pp] = valid ? klp : 0.0f;
+      SC[S_W * TP + pp] = valid ? wpair : 0.0f;
+      if (valid) {
+        const long long o = (long long)m * B + row0 + r;
+        if (P.out.dens) P.out.dens[o] = dens;
+        if (P.out.zx) for (int k = 0; k < P.nz_x; ++k) P.out.zx[o * P.nz_x + k] = ZXIN[k * TP + pp];
+        if (P.out.zc) for (int k = 0; k < P.nz_c; ++k) P.out.zc[o * P.nz_c + k] = ZD[k * TP + pp];
+        if (P.out.zy) for (int k = 0; k < P.nz_y; ++k) P.out.zy[o * P.nz_y + k] = ZD[(P.nz_c + k) * TP + pp];
+      }
+      // latent operand row: [zd | 1 | standardised physics input | 0], scaled by 2^E_LAT
+      for (int ch = 0; ch < (KZ >> 3); ++ch) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int k = 8 * ch + i;
+          float x = 0.0f;
+          if (k < nzd) x = valid ? ZD[k * TP + pp] : 0.0f;
+          else if (k == c1) x = 1.0f;
+          else if (mlp && k >= cs0 && k < cs0 + nzin)
+            x = valid ? (ZXIN[(k - cs0) * TP + pp] - P.phys_in_mean[k - cs0]) / P.phys_in_std[k - cs0] : 0.0f;
+          v[i] = x * s_lat;
+        }
+        put8(pLAT, T.l_lat, TP, ch, pp, v);
+      }
+    }
+    if (P.latent_only) {
+      __syncthreads();
+      continue;
+    }
+
+    const bool pvalid = p < npairs;
+    const int prow = (pvalid ? p : npairs - 1) / n;
+    uint32_t mA[2] = {0u, 0u}, mH[2] = {0u, 0u};
+
+    // ================= auxiliary decoders (block-diagonal) ==============================================
+    mma_stage(bar, phase, [&] { tc::issue_fwd(tb + C_H, oLAT, oWAX0, 128, KZ, 0, terms); });
+    {
+      const float inv = INV[I_AX0];
+#pragma unroll
+      for (int blk = 0; blk < 2; ++blk) {
+        float v[32];
+        tc::tmem_ld32(trow + C_H + 64 * hh + 32 * blk, v);
+        uint32_t mk = 0u;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float a = v[i] * inv;
+          mk |= (a > 0.0f ? 1u : 0u) << i;
+          v[i] = fmaxf(a, 0.0f) * s_h;
+        }
+        mA[blk] = mk;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) put8(pBIG, T.l_big, TP, (64 * hh + 32 * blk) / 8 + c, p, v + 8 * c);
+      }
+    }
+    mma_stage(bar, phase, [&] { tc::issue_fwd(tb + C_S, oBIG, oWAX1, 16, 128, 0, terms); });
+    {
+      float v[16];
+      tc::tmem_ld16(trow + C_S, v);
+      const float inv = INV[I_AX1];
+      const int nd = hh ? P.nd_y : P.nd_c;
+      float g8[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g8[i] = 0.0f;
+      float R = 0.0f;
+      if (hh == 0 || P.y != nullptr) {
+        for (int j = 0; j < nd; ++j) {
+          const float mean = v[8 * hh + j] * inv + BA1[8 * hh + j];
+          const float ls = v[8 * hh + nd + j] * inv + BA1[8 * hh + nd + j];
+          const float val = ROWRAW[((hh ? P.nd_c : 0) + j) * RBMAX + prow];
+          const float es = expf(ls), var = es * es, d = val - mean;
+          R += -(d * d) / (2.0f * var) - ls - LOG_SQRT_2PI;
+          if (pvalid) {
+            g8[j] = fminf(fmaxf(-d / var, -60000.0f), 60000.0f);
+            g8[nd + j] = fminf(fmaxf(-(d * d / var - 1.0f), -60000.0f), 60000.0f);
+          }
+        }
+      }
+      SC[(hh ? S_RY : S_RC) * TP + p] = pvalid ? R : 0.0f;
+      if (P.with_grad) {
+        put8(pG, T.l_g, TP, hh, p, g8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dba[i] += g8[i];
+      }
+    }
+    if (P.with_grad) {
+      mma_stage(bar, phase, [&] {
+        tc::issue_wgrad(tb + C_AW1, oBIG, oG, 16, wacc, terms);
+        tc::issue_dgrad(tb + C_H, oG, oWAX1, 16, 128, 0, terms);
+      });
+      {
+        const float inv = INV[I_AX1D];
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk) {
+          float v[32];
+          tc::tmem_ld32(trow + C_H + 64 * hh + 32 * blk, v);
+          const uint32_t mk = mA[blk];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = ((mk >> i) & 1u) ? v[i] * inv : 0.0f;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) put8(pBIG, T.l_big, TP, (64 * hh + 32 * blk) / 8 + c, p, v + 8 * c);
+        }
+      }
+      mma_stage(bar, phase, [&] {
+        tc::issue_wgrad(tb + C_AW0, oBIG, oLAT, KZ, wacc, terms);
+        tc::issue_dgrad(tb + C_S + 16, oBIG, oWAX0, 128, KZ, 0, terms);
+      });
+      if (hh == 0) {
+        float v[16];
+        tc::tmem_ld16(trow + C_S + 16, v);
+        const float inv = INV[I_AX0D];
+        for (int k = 0; k < nzd; ++k) DZA[k * TP + p] = v[k] * inv;
+      }
+    }
+
+    // ================= physics surrogate forward + data-driven decoder ====================================
+    mma_stage(bar, phase, [&] {
+      tc::issue_fwd(tb + C_H, oLAT, oWFX0, 128, KZ, 0, terms);
+      if (mlp) tc::issue_fwd(tb + C_A0, oLAT, oWP0, d1, KZ, 0, terms);
+    });
+    if (mlp) {
+      // layer 0 -> tanh (bias folded into the constant-one column)
+      {
+        const float inv = INV[I_P0];
+        if (d1 == 64) {
+          float v[32];
+          tc::tmem_ld32(trow + C_A0 + 32 * hh, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = tanhf(v[i] * inv);
+          tc::tmem_st32(trow + C_A0 + 32 * hh, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] *= s_t;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) put8(pBIG, T.l_big, TP, 4 * hh + c, p, v + 8 * c);
+        }
+      }
+      mma_stage(bar, phase, [&] { tc::issue_fwd(tb + C_A1, mkop(smb, T.a_big, T.l_big, TP, 0), oWP1, d2, d1, 0, terms); });
+      {
+        const float inv = INV[I_P1];
+        float v[32];
+        tc::tmem_ld16(trow + C_A1 + 16 * hh, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = tanhf(v[i] * inv + BP1[16 * hh + i]);
+        tc::tmem_st16(trow + C_A1 + 16 * hh, v);  // tanh outputs saved for the backward
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] *= s_t;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) put8(pBIG, T.l_big, TP, 8 + 2 * hh + c, p, v + 8 * c);
+      }
+      mma_stage(bar, phase, [&] { tc::issue_fwd(tb + C_A2, mkop(smb, T.a_big, T.l_big, TP, 64), oWP2, d3, d2, 0, terms); });
+      {
+        const float inv = INV[I_P2];
+        float v[32];
+        tc::tmem_ld32(trow + C_A2 + 32 * hh, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = tanhf(v[i] * inv + BP2[32 * hh + i]);
+        tc::tmem_st32(trow + C_A2 + 32 * hh, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] *= s_h;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) put8(pBIG, T.l_big, TP, 4 * hh + c, p, v + 8 * c);
+      }
+      mma_stage(bar, phase, [&] { tc::issue_fwd(tb + C_X, mkop(smb, T.a_big, T.l_big, TP, 0), oWP3, ndx, d3, 0, terms); });
+    }
+    // hidden layer of the data-driven decoder: ReLU (bias folded), mask kept in registers
+    {
+      const float inv = INV[I_FX0];
+#pragma unroll
+      for (int blk = 0; blk < 2; ++blk) {
+        float v[32];
+        tc::tmem_ld32(trow + C_H + 64 * hh + 32 * blk, v);
+        uint32_t mk = 0u;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float a = v[i] * inv;
+          mk |= (a > 0.0f ? 1u : 0u) << i;
+          v[i] = fmaxf(a, 0.0f) * s_h;
+        }
+        mH[blk] = mk;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) put8(pBIG, T.l_big, TP, (64 * hh + 32 * blk) / 8 + c, p, v + 8 * c);
+      }
+    }
+    mma_stage(bar, phase, [&] { tc::issue_fwd(tb + C_X, oBIG, oWFX1, ndx, 128, mlp ? 1u : 0u, terms); });
+
+    // ---- x head: xh = xh_p + xh_d, Gaussian log-likelihood of raw x, residual gradient -----------------
+    {
+      const float inv = INV[I_X];
+      const long long lrow = row0 + prow;
+      const long long drow = P.idx ? P.idx[lrow] : lrow;
+      const float* xr = P.x + drow * ndx + nxh * hh;
+      float ssq = 0.0f;
+      float v[32];
+      if (nxh == 32) tc::tmem_ld32(trow + C_X + 32 * hh, v);
+      else tc::tmem_ld16(trow + C_X + 16 * hh, v);
+      const float gsc = pvalid ? sg : 0.0f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if (i < nxh) {
+          float xh = v[i] * inv + BX[nxh * hh + i];
+          if (!mlp) {
+            // closed-form physics (cases/damped_oscillator/mass_spring.py:8-28, cases/simple_beam/simple_beam_model.py:4-30)
+            const int d = nxh * hh + i;
+            if (P.phys_kind == 1) {
+              const float om = sqrtf(1.0f / ZXIN[p]);
+              const float bb = 0.0f / om;
+              const float ph = om * P.grid[d];
+              xh += bb * sinf(ph) + 1.0f * cosf(ph);
+            } else {
+              const float E = ZXIN[p] * 1e6f, a = ZXIN[TP + p], b = 1.0f - a, xg = P.grid[d];
+              const float den1 = 6.0f * E * 2e-6f * 1.0f, den2 = 6.0f * E * 2e-6f;
+              float w = 1.0f * b * xg * (1.0f - b * b - xg * xg) / den1;
+              if (xg > a) {
+                const float t = xg - a;
+                w += 1.0f * (t * t * t) / den2;
+              }
+              xh += -1000.0f * w;
+            }
+          }
+          const float res = __ldg(xr + i) - xh;
+          ssq = fmaf(res, res, ssq);
+          v[i] = fminf(fmaxf(gsc * res, -60000.0f), 60000.0f);
+          dbx[i] += v[i];
+        }
+      }
+      if (P.with_grad) {
+        for (int c = 0; c < (nxh >> 3); ++c) put8(pG, T.l_g, TP, (nxh * hh) / 8 + c, p, v + 8 * c);
+      }
+      SC[(S_Q0 + hh) * TP + p] = ssq;
+    }
+    __syncthreads();
+    if (tid < TP) {
+      const bool valid = tid < npairs;
+      const float S = SC[S_Q0 * TP + tid] + SC[S_Q1 * TP + tid];
+      SC[S_RX * TP + tid] = valid ? (-S / (2.0f * var_x) - (float)ndx * (lsx + LOG_SQRT_2PI)) : 0.0f;
+      SC[S_REG * TP + tid] = 0.0f;
+      if (P.with_grad && valid) dlsx += -(P.alpha_x * wpair) * (S / var_x - (float)ndx);
+    }
+
+    if (P.with_grad) {
+      // ================= backward ============================================================================
+      mma_stage(bar, phase, [&] {
+        tc::issue_wgrad(tb + C_W1, oBIG, oG, ndx, wacc, terms);
+        tc::issue_dgrad(tb + C_H, oG, oWFX1, ndx, 128, 0, terms);
+        if (mlp) tc::issue_dgrad(tb + C_X, oG, oWP3, ndx, d3, 0, terms);
+      });
+      {
+        const float inv = INV[I_XD];
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk) {
+          float v[32];
+          tc::tmem_ld32(trow + C_H + 64 * hh + 32 * blk, v);
+          const uint32_t mk = mH[blk];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = ((mk >> i) & 1u) ? v[i] * inv : 0.0f;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) put8(pBIG, T.l_big, TP, (64 * hh + 32 * blk) / 8 + c, p, v + 8 * c);
+        }
+        if (mlp) {
+          float g[32], a[32];
+          tc::tmem_ld32(trow + C_X + 32 * hh, g);
+          tc::tmem_ld32(trow + C_A2 + 32 * hh, a);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) g[i] = g[i] * inv * (1.0f - a[i] * a[i]);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) put8(pG, T.l_g, TP, 4 * hh + c, p, g + 8 * c);
+        }
+      }
+      mma_stage(bar, phase, [&] {
+        tc::issue_wgrad(tb + C_W0, oBIG, oLAT, KZ, wacc, terms);
+        tc::issue_dgrad(tb + C_S, oBIG, oWFX0, 128, KZ, 0, terms);
+        if (mlp) tc::issue_dgrad(tb + C_X, mkop(smb, T.a_g, T.l_g, TP, 0), oWP2, d3, d2, 0, terms);
+      });
+      {
+        float v[16];
+        tc::tmem_ld16(trow + C_S, v);
+        if (hh == 0) {
+          // total dL/d(zc|zy): reversed + scaled gradient of the data-driven decoder (utils/transforms.py:207-219)
+          // plus the auxiliary decoders' gradient
+          const float inv = -P.lambda_g0 * cx * INV[I_FX0D];
+          for (int k = 0; k < nzd; ++k) DZA[k * TP + p] = fmaf(v[k], inv, (k < P.nz_c ? awc : awy) * DZA[k * TP + p]);
+        }
+        if (mlp) {
+          float g[16], a[16];
+          tc::tmem_ld16(trow + C_X + 16 * hh, g);
+          tc::tmem_ld16(trow + C_A1 + 16 * hh, a);
+          const float inv = INV[I_P2D];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) g[i] = g[i] * inv * (1.0f - a[i] * a[i]);
+#pragma unroll
+          for (int c = 0; c < 2; ++c) put8(pG, T.l_g, TP, 2 * hh + c, p, g + 8 * c);
+        }
+      }
+      if (mlp) {
+        mma_stage(bar, phase, [&] { tc::issue_dgrad(tb + C_X, mkop(smb, T.a_g, T.l_g, TP, 0), oWP1, d2, d1, 0, terms); });
+        {
+          float g[32], a[32];
+          tc::tmem_ld32(trow + C_X + 32 * hh, g);
+          tc::tmem_ld32(trow + C_A0 + 32 * hh, a);
+          const float inv = INV[I_P1D];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) g[i] = g[i] * inv * (1.0f - a[i] * a[i]);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) put8(pG, T.l_g, TP, 4 * hh + c, p, g + 8 * c);
+        }
+        mma_stage(bar, phase, [&] { tc::issue_dgrad(tb + C_S, mkop(smb, T.a_g, T.l_g, TP, 0), oWP0, d1, KZ, 0, terms); });
+        {
+          float v[16];
+          tc::tmem_ld16(trow + C_S, v);
+          if (hh == 0) {
+            const float inv = INV[I_P0D] * cx;
+            for (int k = 0; k < P.nz_x; ++k) DZX[k * TP + p] = v[cs0 + k] * inv / P.phys_in_std[k];
+          }
+        }
+      } else {
+        // closed-form physics backward: d xh_p / d zx contracted with g~ (this thread's half of the x columns)
+        float s0 = 0.0f, s1 = 0.0f;
+        {
+          const unsigned char* gh = pG;
+          for (int i = 0; i < nxh; ++i) {
+            const int d = nxh * hh + i;
+            const __half* hrow = reinterpret_cast<const __half*>(gh + ((size_t)(d >> 3) * TP + p) * 16) + (d & 7);
+            const __half* lrow = reinterpret_cast<const __half*>(gh + T.l_g + ((size_t)(d >> 3) * TP + p) * 16) + (d & 7);
+            const float g = __half2float(*hrow) + __half2float(*lrow);
+            if (P.phys_kind == 1) {
+              const float mass = ZXIN[p];
+              const float om = sqrtf(1.0f / mass);
+              const float dom = -om / (2.0f * mass);
+              const float t = P.grid[d];
+              s0 = fmaf(g, -sinf(om * t) * t * dom, s0);
+            } else {
+              const float z0 = ZXIN[p], E = z0 * 1e6f, a = ZXIN[TP + p], b = 1.0f - a;
+              const float den = 6.0f * E * 2e-6f;
+              const float xg = P.grid[d];
+              float w = b * xg * (1.0f - b * b - xg * xg) / den;
+              float dwa = -(xg * (1.0f - b * b - xg * xg) - 2.0f * b * b * xg) / den;
+              if (xg > a) {
+                const float t = xg - a;
+                w += (t * t * t) / den;
+                dwa += -3.0f * t * t / den;
+              }
+              s0 = fmaf(g, 1000.0f * w / z0, s0);
+              s1 = fmaf(g, -1000.0f * dwa, s1);
+            }
+          }
+        }
+        __syncthreads();
+        SC[(S_Q0 + hh) * TP + p] = s0;
+        float* Q2 = RED;  // second component, [2][TP]
+        Q2[hh * TP + p] = s1;
+        __syncthreads();
+        if (tid < TP) {
+          DZX[tid] = (SC[S_Q0 * TP + tid] + SC[S_Q1 * TP + tid]) * cx;
+          if (P.nz_x > 1) DZX[TP + tid] = (Q2[tid] + Q2[TP + tid]) * cx;
+        }
+      }
+      __syncthreads();
+
+      // ---- latent backward: per-pair gradients w.r.t. loc / L / prior parameters ---------------------------
+      {
+        const int pp = tid & (TP - 1), prt = tid >> 7;
+        const int r = (pp < npairs ? pp : npairs - 1) / n;
+        const float bw = P.beta_x * SC[S_W * TP + pp];
+        const float wv = pp < npairs ? 1.0f : 0.0f;
+        for (int k = prt; k < nzd; k += 2) {
+          float g = wv * DZA[k * TP + pp];
+          const float sgm = ROWPAR[(P.rp_psig + k) * RBMAX + r];
+          const float t = (ZD[k * TP + pp] - ROWPAR[(P.rp_pmu + k) * RBMAX + r]) / sgm;
+          g += bw * t / sgm;
+          FEAT[(P.f_pmu + k) * TP + pp] = -bw * t / sgm;
+          FEAT[(P.f_psig + k) * TP + pp] = -bw * (t * t - 1.0f) / sgm;
+          FEAT[(P.f_loc + P.nz_x + k) * TP + pp] = g;
+        }
+        for (int i = prt; i < P.nz_x; i += 2) {
+          float g = wv * DZX[i * TP + pp];
+          if (P.prior_kind[i] == 1) g += bw * (ZXIN[i * TP + pp] - P.prior_a[i]) / (P.prior_b[i] * P.prior_b[i]);
+          const float u = U[i * TP + pp];
+          FEAT[(P.f_loc + i) * TP + pp] = g * (P.ub[i] - P.lb[i]) * u * (1.0f - u) + bw * (2.0f * u - 1.0f);
+        }
+      }
+      __syncthreads();
+      for (int e = tid; e < TP * P.nL; e += TNT) {
+        const int pp = e & (TP - 1), li = e >> 7;
+        const int r = (pp < npairs ? pp : npairs - 1) / n;
+        const int b = P.L_blk[li], i = P.L_i[li], j = P.L_j[li], s = P.blk_start[b];
+        float v = FEAT[(P.f_loc + s + i) * TP + pp] * EPS[(s + j) * TP + pp];
+        if (i == j) v -= P.beta_x * SC[S_W * TP + pp] / ROWPAR[(P.rp_L + li) * RBMAX + r];
+        FEAT[(P.f_L + li) * TP + pp] = v;
+      }
+    }
+    __syncthreads();
+
+    // ---- reduce the pairs over the MC axis into per-row accumulators ------------------------------------------
+    {
+      const int f0 = P.with_grad ? 0 : P.n_feat;
+      if (n_pow2) {
+        for (int it = warp + 4 * f0; it < 4 * n_acc; it += TNT / 32) {
+          const int f = it >> 2, pp = (it & 3) * 32 + lane;
+          const float* src = f < P.n_feat ? FEAT + f * TP : SC + (f - P.n_feat) * TP;
+          float v = src[pp];
+          for (int off = n >> 1; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+          const int r = pp / n;
+          if ((lane & (n - 1)) == 0 && r < nrows) ROWACC[f * RBMAX + r] = v;
+        }
+      } else {
+        for (int e = tid + f0 * RBMAX; e < n_acc * RBMAX; e += TNT) {
+          const int f = e / RBMAX, r = e - f * RBMAX;
+          if (r < nrows) {
+            const float* src = f < P.n_feat ? FEAT + f * TP : SC + (f - P.n_feat) * TP;
+            float s = 0.0f;
+            for (int m = 0; m < n; ++m) s += src[r * n + m];
+            ROWACC[f * RBMAX + r] = s;
+          }
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- per-row outputs -----------------------------------------------------------------------------------
+    if (tid < nrows) {
+      const int r = tid;
+      const float inv_n = 1.0f / (float)n;
+      const float kl = ROWACC[(P.n_feat + S_KL) * RBMAX + r] * inv_n;
+      const float rx = ROWACC[(P.n_feat + S_RX) * RBMAX + r] * inv_n;
+      const float rc = ROWACC[(P.n_feat + S_RC) * RBMAX + r] * inv_n;
+      const float ry = ROWACC[(P.n_feat + S_RY) * RBMAX + r] * inv_n;
+      const float rg = ROWACC[(P.n_feat + S_REG) * RBMAX + r] * inv_n;
+      const float loss = P.beta_x * kl - P.alpha_x * rx - P.alpha_c * rc - P.alpha_y * ry - rg;
+      if (P.out.row_loss) {
+        float* o = P.out.row_loss + row0 + r;
+        o[0] = loss; o[B] = kl; o[2 * B] = rx; o[3 * B] = rc; o[4 * B] = ry; o[5 * B] = rg;
+      }
+      ROWACC[(P.n_feat + S_KL) * RBMAX + r] = kl;
+      ROWACC[(P.n_feat + S_RX) * RBMAX + r] = rx;
+      ROWACC[(P.n_feat + S_RC) * RBMAX + r] = rc;
+      ROWACC[(P.n_feat + S_RY) * RBMAX + r] = ry;
+      ROWACC[(P.n_feat + S_REG) * RBMAX + r] = rg;
+      SC[S_Q0 * TP + r] = loss;
+    }
+    if (P.with_grad) {
+      for (int e = tid; e < RBMAX * P.Z; e += TNT) {
+        const int i = e / RBMAX, r = e - i * RBMAX;
+        if (r < nrows) {
+          const long long lrow = row0 + r;
+          const int b = block_of_tc(P, i), il = i - P.blk_start[b], nzb = P.blk_size[b];
+          const long long om = (long long)(P.henc[b] + il) * B + lrow;
+          const float pm = P.headpre[om];
+          P.gpre[om] = (pm >= -50.0f && pm <= 50.0f) ? ROWACC[(P.f_loc + i) * RBMAX + r] : 0.0f;
+          for (int j = 0; j < nzb; ++j) {
+            const long long oc = (long long)(P.henc[b] + 2 * nzb + il * nzb + j) * B + lrow;
+            float g = 0.0f;
+            if (j < il) {
+              const float pc = P.headpre[oc];
+              const int li = P.blk_loff[b] + il * (il + 1) / 2 + j;
+              g = (pc >= -20.0f && pc <= 20.0f) ? ROWACC[(P.f_L + li) * RBMAX + r] : 0.0f;
+            }
+            P.gpre[oc] = g;
+          }
+          const long long os = (long long)(P.henc[b] + nzb + il) * B + lrow;
+          const float ps = P.headpre[os];
+          const int ld = P.blk_loff[b] + il * (il + 1) / 2 + il;
+          P.gpre[os] = (ps >= -7.0f && ps <= 3.0f) ? ROWACC[(P.f_L + ld) * RBMAX + r] * expf(ps) : 0.0f;
+        }
+      }
+      for (int e = tid; e < RBMAX * nzd; e += TNT) {
+        const int k = e / RBMAX, r = e - k * RBMAX;
+        if (r < nrows) {
+          const long long lrow = row0 + r;
+          const int which = k < P.nz_c ? 0 : 1;
+          const int kk = which ? k - P.nz_c : k, nzk = which ? P.nz_y : P.nz_c;
+          const long long om = (long long)(P.hpri[which] + kk) * B + lrow;
+          const long long os = (long long)(P.hpri[which] + nzk + kk) * B + lrow;
+          const float pm = P.headpre[om], ps = P.headpre[os];
+          P.gpre[om] = (pm >= -50.0f && pm <= 50.0f) ? ROWACC[(P.f_pmu + k) * RBMAX + r] : 0.0f;
+          P.gpre[os] = (ps >= -7.0f && ps <= 3.0f) ? ROWACC[(P.f_psig + k) * RBMAX + r] * expf(ps) : 0.0f;
+        }
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      for (int r = 0; r < nrows; ++r) {
+        tot[0] += SC[S_Q0 * TP + r];
+        tot[1] += ROWACC[(P.n_feat + S_KL) * RBMAX + r];
+        tot[2] += ROWACC[(P.n_feat + S_RX) * RBMAX + r];
+        tot[3] += ROWACC[(P.n_feat + S_RC) * RBMAX + r];
+        tot[4] += ROWACC[(P.n_feat + S_RY) * RBMAX + r];
+        tot[5] += ROWACC[(P.n_feat + S_REG) * RBMAX + r];
+      }
+    }
+    // FEAT / ROWACC alias the BIG operand buffer: clear what the next tile's MMAs could read as padding
+    __syncthreads();
+    wacc = 1u;
+  }  // tiles
+
+  // ---- end of kernel: loss sums, weight gradients out of TMEM, bias / log_sigma_x sums ---------------------
+  if (tid == 0)
+    for (int k = 0; k < 6; ++k) part[P.n_params + k] = tot[k];
+  if (P.with_grad && !P.latent_only) {
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const int k = p;  // TMEM lane = hidden unit of the 128-wide layers
+    // fx1: dW[n][k] (nd_x x 128)
+    {
+      const float sc = exp2f(-(float)E_H) * cx;
+      float v[32];
+      if (nxh == 32) tc::tmem_ld32(trow + C_W1 + 32 * hh, v);
+      else tc::tmem_ld16(trow + C_W1 + 16 * hh, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < nxh) part[P.fx.g_w1 + (long long)(nxh * hh + i) * 128 + k] = v[i] * sc;
+    }
+    {
+      float v0[16], va1[16], va0[16];
+      tc::tmem_ld16(trow + C_W0, v0);
+      tc::tmem_ld16(trow + C_AW1, va1);
+      tc::tmem_ld16(trow + C_AW0, va0);
+      if (hh == 0) {
+        // fx0: dW[k][j] (128 x nzd), bias from the constant-one column; gradient reversal: the decoder's own
+        // weights see the un-reversed gradient (utils/transforms.py:207-219 reverses only d/dz)
+        const float sc = exp2f(-(float)E_LAT) * cx;
+        for (int j = 0; j < nzd; ++j) part[P.fx.g_w0 + (long long)k * nzd + j] = v0[j] * sc;
+        part[P.fx.g_b0 + k] = v0[c1] * sc;
+      } else {
+        const bool cside = k < 64;
+        const Mlp2S& M = cside ? P.dc : P.dy;
+        const int kk = cside ? k : k - 64;
+        const float aw = cside ? awc : awy;
+        const int nzk = cside ? P.nz_c : P.nz_y, j0 = cside ? 0 : P.nz_c;
+        const int nd2 = 2 * (cside ? P.nd_c : P.nd_y), n0 = cside ? 0 : 8;
+        const float s1 = exp2f(-(float)E_H) * aw, s0 = exp2f(-(float)E_LAT) * aw;
+        for (int nn = 0; nn < nd2; ++nn) part[M.g_w1 + (long long)nn * 64 + kk] = va1[n0 + nn] * s1;
+        for (int j = 0; j < nzk; ++j) part[M.g_w0 + (long long)kk * nzk + j] = va0[j0 + j] * s0;
+        part[M.g_b0 + kk] = va0[c1] * s0;
+      }
+    }
+    // per-thread running sums -> fixed-order tree over the 128 pair slots of each column
+    __syncthreads();
+    float* R0 = FEAT;  // [TNT][32]
+#pragma unroll
+    for (int i = 0; i < 32; ++i) R0[tid * 32 + i] = dbx[i];
+    __syncthreads();
+    if (tid < ndx) {
+      const int h2 = tid / nxh, i = tid - h2 * nxh;
+      float s = 0.0f;
+      for (int j = 0; j < TP; ++j) s += R0[(h2 * TP + j) * 32 + i];
+      part[P.fx.g_b1 + tid] = s * cx;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) R0[tid * 8 + i] = dba[i];
+    R0[TNT * 8 + tid] = dlsx;
+    __syncthreads();
+    if (tid < 16) {
+      const int h2 = tid >> 3, i = tid & 7;
+      const int nd2 = 2 * (h2 ? P.nd_y : P.nd_c);
+      if (i < nd2) {
+        float s = 0.0f;
+        for (int j = 0; j < TP; ++j) s += R0[(h2 * TP + j) * 8 + i];
+        part[(h2 ? P.dy.g_b1 : P.dc.g_b1) + i] = s * (h2 ? awy : awc);
+      }
+    }
+    if (tid == 32) {
+      float s = 0.0f;
+      for (int j = 0; j < TP; ++j) s += R0[TNT * 8 + j];
+      part[P.g_lsx] = s;
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tb, C_ALLOC);
+}
+
+void launch_dec_tc(const TcParams& p, int grid, cudaStream_t s) { dec_tc_kernel<<<grid, TNT, p.total, s>>>(p); }
+
+int configure_dec_tc_kernel() {
+  return (int)cudaFuncSetAttribute(dec_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+}
+
+}  // namespace dpv

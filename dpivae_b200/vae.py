@@ -314,6 +314,16 @@ class _Engine:
             del keep
             return zx, zc, zy, dens
 
+    def set_math_mode(self, mode):
+        """'fp32' (FFMA, default) | 'tc_fp16x3' (tcgen05, fp16 hi/lo split, fp32-accurate) | 'tc_fp16' (tcgen05, plain
+        fp16 operands) -- include/dpivae_b200.h DPIVAE_MATH_*."""
+        code = {"fp32": _lib.MATH_FP32, "tc_fp16x3": _lib.MATH_TC_FP16X3, "tc_fp16": _lib.MATH_TC_FP16}[mode]
+        _lib.check(self.lib.dpivae_set_math_mode(self.handle, code))
+        self.math_mode = mode
+
+    def used_tensor_cores(self):
+        return bool(self.lib.dpivae_last_used_tensor_cores(self.handle))
+
     def set_timing(self, enable):
         _lib.check(self.lib.dpivae_set_timing(self.handle, int(bool(enable))))
 

@@ -177,6 +177,20 @@ int dpivae_last_kernel_ms(dpivae_handle_t h, float* out5);
  * denominator for the fp32-parity mode, which MEASURED_PEAKS.json does not carry. */
 int dpivae_ffma_peak_tflops(float* tflops_out, void* stream);
 
+/* Arithmetic of the decoder-side GEMMs (MLP stacks of models/decoders.py, models/nn.py).
+ *   DPIVAE_MATH_FP32     : fp32 FFMA on the CUDA cores (default; bit-reproducible, 1e-5 parity).
+ *   DPIVAE_MATH_TC_FP16X3: tcgen05 tensor cores, every fp32 operand split into two fp16 planes and each
+ *                          GEMM issued as hi*hi + lo*hi + hi*lo into an fp32 TMEM accumulator
+ *                          (fp32-level accuracy; parity tolerance stated in tests/test_gpu_tc.py).
+ *   DPIVAE_MATH_TC_FP16  : tcgen05 with plain fp16 operands, fp32 accumulate (reduced precision, separately
+ *                          stated tolerance).
+ * Shapes / options the tensor-core kernel does not cover (n_mc outside [8,128], cond, lambda_x, per-sample
+ * decoder outputs, encode-only) run on the fp32 kernel whatever the mode; dpivae_last_used_tensor_cores()
+ * says which kernel the last call used. */
+enum { DPIVAE_MATH_FP32 = 0, DPIVAE_MATH_TC_FP16X3 = 1, DPIVAE_MATH_TC_FP16 = 2 };
+int dpivae_set_math_mode(dpivae_handle_t h, int32_t mode);
+int dpivae_last_used_tensor_cores(dpivae_handle_t h);
+
 /* Number of kernels launched by the last dpivae_loss / train_step / encode call on this handle. */
 int dpivae_last_launch_count(dpivae_handle_t h);
 

@@ -1,0 +1,93 @@
+"""GPU parity of the tensor-core (tcgen05) decoder kernel, through the C ABI.
+
+Two modes (include/dpivae_b200.h DPIVAE_MATH_*), each against the fp64 oracle on the golden inputs,
+weights and injected noise:
+  tc_fp16x3  fp16 hi/lo operand split, three MMAs per GEMM, fp32 TMEM accumulators.  Stated tolerance:
+             1e-5 relative on the per-row loss and the 8 scalars, 2e-5 per-tensor relative L2 on gradients
+             (the same bars the fp32 kernel is held to against the reference's fp32 golden outputs).
+  tc_fp16    plain fp16 operands.  Stated tolerance: 2e-3 on loss / scalars, 2e-2 on gradients (1e-1 on the
+             f_cov tensors, whose gradient is the round-off-dominated residue of an analytically-zero term).
+"""
+import pytest
+import torch
+
+import golden_util as gu
+from helpers import build_from_golden
+
+pytestmark = pytest.mark.gpu
+TOL = {"tc_fp16x3": (1e-5, 2e-5), "tc_fp16": (2e-3, 2e-2)}
+
+
+def _dev_eps(g, spec):
+    eps = gu.eps_of(g, spec)
+    return tuple(e.cuda() for e in eps) if isinstance(eps, tuple) else eps.cuda()
+
+
+def _tile(t, reps):
+    return torch.cat([t] * reps, dim=0)
+
+
+def _oracle(g, spec, sd, x, c, y, eps, reps, n_rep):
+    from oracle import dpivae_oracle as orc
+
+    spec64 = orc.cast_spec(spec, torch.float64)
+    sd64 = {k: v.double() for k, v in sd.items()}
+    if isinstance(eps, tuple):
+        eps64 = tuple(torch.cat([torch.cat([e.double().cpu()] * reps, dim=1)] * n_rep, dim=0) for e in eps)
+    else:
+        eps64 = torch.cat([torch.cat([eps.double().cpu()] * reps, dim=1)] * n_rep, dim=0)
+    return orc.loss_and_grads(sd64, spec64, _tile(x, reps).double(), _tile(c, reps).double(), _tile(y, reps).double(), eps64), eps64
+
+
+@pytest.mark.parametrize("mode", ["tc_fp16x3", "tc_fp16"])
+@pytest.mark.parametrize("case,mtype", gu.CONFIGS)
+def test_tc_loss_and_gradients_vs_fp64_oracle(case, mtype, mode):
+    g, spec, sd, args, case_mod, vae, (x, c, y) = build_from_golden(case, mtype)
+    n0 = g["eps0"].shape[0]
+    # the tensor-core kernel needs 8 <= n_mc <= 128: repeat the golden MC draws along the MC axis, and the
+    # rows so that several 128-pair tiles (and a ragged last tile) are exercised
+    n_rep = max(1, -(-8 // n0))
+    n = n0 * n_rep
+    reps = 3
+    eps = gu.eps_of(g, spec)
+    (scal, l8, fw, grads), eps64 = _oracle(g, spec, sd, x, c, y, eps, reps, n_rep)
+    eng = vae.engine()
+    eng.set_math_mode(mode)
+    dev_eps = tuple(e.float().cuda() for e in eps64) if isinstance(eps64, tuple) else eps64.float().cuda()
+    row_loss, s = eng.loss(_tile(x, reps), _tile(c, reps), _tile(y, reps), n, (1.0, 1.0, 1.0, 1.0), True, eps=dev_eps)
+    assert eng.used_tensor_cores(), "tensor-core kernel was not selected"
+    tol_l, tol_g = TOL[mode]
+    assert gu.rel_l2(row_loss[0].cpu(), l8[0]) < tol_l
+    for k in range(8):
+        assert abs(float(s[k]) - float(scal[k])) < tol_l * max(1.0, abs(float(scal[k]))), (k, float(s[k]), float(scal[k]))
+    bad = {}
+    for p, o in eng.slots:
+        name = [k for k, q in vae.named_parameters() if q is p][0]
+        err = gu.rel_l2(eng.grads[o:o + p.numel()].cpu(), grads[name])
+        if err > (1e-1 if mode == "tc_fp16" and ".f_cov." in name else tol_g):
+            bad[name] = err
+    assert not bad, bad
+
+
+def test_tc_matches_fp32_kernel_with_philox_noise():
+    """Same in-kernel Philox stream in both kernels: per-row losses of the tensor-core path track the fp32
+    kernel on a multi-tile batch with a ragged tail."""
+    g, spec, sd, args, case_mod, vae, (x, c, y) = build_from_golden("bridge", "P")
+    eng = vae.engine()
+    reps = 37  # 37 * 24 rows = 888 rows x 16 MC = 111 tiles, last one ragged
+    X, C_, Y = _tile(x, reps), _tile(c, reps), _tile(y, reps)
+    torch.manual_seed(5)
+    rl32, s32 = eng.loss(X, C_, Y, 16, (1.0, 1.0, 1.0, 1.0), True)
+    g32 = eng.grads.clone()
+    assert not eng.used_tensor_cores()
+    eng.set_math_mode("tc_fp16x3")
+    torch.manual_seed(5)
+    rl, s = eng.loss(X, C_, Y, 16, (1.0, 1.0, 1.0, 1.0), True)
+    assert eng.used_tensor_cores()
+    assert gu.rel_l2(rl.cpu(), rl32.cpu()) < 1e-5
+    assert gu.rel_l2(s.cpu(), s32.cpu()) < 1e-5
+    assert gu.rel_l2(eng.grads.cpu(), g32.cpu()) < 2e-5
+    # deterministic: same call, same bits
+    torch.manual_seed(5)
+    rl2, _ = eng.loss(X, C_, Y, 16, (1.0, 1.0, 1.0, 1.0), True)
+    assert torch.equal(rl, rl2)
