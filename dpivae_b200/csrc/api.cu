@@ -264,7 +264,7 @@ static int build_plan(dpivae_model* h) {
   {
     const bool mlp = d.phys_kind == DPIVAE_PHYS_MLP;
     const int need = nzd + 1 + (mlp ? nzin : 0);
-    bool ok = need <= 16 && (d.nd_x == 32 || d.nd_x == 64) && !d.has_lambda_x && 2 * d.nd_c <= 8 && 2 * d.nd_y <= 8;
+    bool ok = need <= 16 && dec_tc_has_variant(d.phys_kind, d.nd_x) && !d.has_lambda_x && 2 * d.nd_c <= 8 && 2 * d.nd_y <= 8;
     if (mlp) ok = ok && d.phys_n_layers == 4 && d.phys_dims[1] == 64 && d.phys_dims[2] == 32 && d.phys_dims[3] == 64;
     if (ok) {
       const int KZ = 16, d1 = mlp ? 64 : 0, d2 = mlp ? 32 : 0, d3 = mlp ? 64 : 0;

@@ -39,6 +39,18 @@ enum { S_KL = 0, S_RX, S_RC, S_RY, S_REG, S_W, S_Q0, S_Q1, S_ROWS };
 // inverse-scale table
 enum { I_AX0 = 0, I_AX1, I_AX1D, I_AX0D, I_FX0, I_P0, I_P1, I_P2, I_X, I_XD, I_FX0D, I_P2D, I_P1D, I_P0D, I_COUNT };
 
+// optional per-phase cycle accounting (thread 0, clock64); see tools/phase_profile.py
+enum { TPH_SETUP = 0, TPH_ROWPAR_EPS, TPH_LATENT, TPH_AUX, TPH_PHYS_FWD, TPH_FX_FWD, TPH_XHEAD, TPH_BWD_FX, TPH_BWD_PHYS, TPH_LATENT_BWD,
+       TPH_ROWRED, TPH_ROWOUT, TPH_FLUSH, TPH_COUNT };
+#define TPHASE(k)                                  \
+  do {                                             \
+    if (PROF && tid == 0) {                        \
+      const long long _t = clock64();              \
+      phs[k] += _t - t_last;                       \
+      t_last = _t;                                 \
+    }                                              \
+  } while (0)
+
 __device__ __forceinline__ float philox_normal_tc(unsigned long long seed, unsigned long long offset, unsigned int T,
                                                   unsigned long long li) {
   const unsigned long long sub = li % T;
@@ -64,6 +76,13 @@ __device__ __forceinline__ void put8(unsigned char* plane, uint32_t lo_off, int 
   unsigned char* dst = plane + ((size_t)chunk * R + row) * 16;
   *reinterpret_cast<uint4*>(dst) = hi;
   *reinterpret_cast<uint4*>(dst + lo_off) = lo;
+}
+
+// tanh(x) = 1 - 2 / (1 + 2^(2 x log2 e)): ex2.approx + rcp.approx, absolute error < 4e-7 (checked against
+// tanhf over [-12, 12] in tests/test_gpu_tc.py); saturates cleanly for large |x|
+__device__ __forceinline__ float tanh_fast(float x) {
+  const float e = exp2f(x * 2.8853900817779268f);
+  return 1.0f - __fdividef(2.0f, 1.0f + e);
 }
 
 template <int W>
@@ -135,6 +154,9 @@ __device__ void stage_weight(unsigned char* plane, uint32_t lo_off, int N, int K
 
 }  // namespace
 
+// PHYS: physics decoder kind (0 MLP surrogate, 1 mass_spring, 2 beam); NDX: response length -- compile-time so
+// that the epilogues are straight-line code (a taken branch in this ~200 KB kernel costs an I-cache miss)
+template <bool PROF, int PHYS, int NDX>
 __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ TcParams T) {
   const DecParams& P = T.d;
   extern __shared__ __align__(1024) unsigned char smb[];
@@ -145,10 +167,10 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
   const int n = P.n_mc;
   const int nzd = P.nz_c + P.nz_y;
   const int nzin = P.nz_x + P.nd_p;
-  const int ndx = P.nd_x, nxh = ndx >> 1;  // columns of the x head per thread
+  constexpr int ndx = NDX, nxh = NDX >> 1;  // columns of the x head per thread
   const long long B = P.B;
   const int terms = T.terms;
-  const bool mlp = P.phys_kind == 0;
+  constexpr bool mlp = PHYS == 0;
   const int d1 = mlp ? P.pl[0].N : 0, d2 = mlp ? P.pl[1].N : 0, d3 = mlp ? P.pl[2].N : 0;
   float* part = P.part + (long long)blockIdx.x * P.part_stride;
 
@@ -197,10 +219,19 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
     if (k >= P.nz_c && k < nzd) return prm[P.dy.g_w0 + (long long)(nn - 64) * P.nz_y + (k - P.nz_c)];
     return k == c1 ? prm[P.dy.g_b0 + nn - 64] : 0.0f;
   };
+  // aux head columns: side s (0 = c, 1 = y) owns columns 8 s .. 8 s + 7: mean_j at 8 s + j, log_sigma_j at 8 s + 4 + j
+  auto head_row = [&](int col, int& side) -> int {  // decoder output index of an aux head column, or -1
+    side = col >> 3;
+    const int nd = side ? P.nd_y : P.nd_c, j = col & 3;
+    if (j >= nd) return -1;
+    return (col & 4) ? nd + j : j;
+  };
   auto g_ax1 = [&](int nn, int k) -> float {
-    if (nn < 2 * P.nd_c) return k < 64 ? prm[P.dc.g_w1 + (long long)nn * 64 + k] : 0.0f;
-    if (nn >= 8 && nn < 8 + 2 * P.nd_y) return k >= 64 ? prm[P.dy.g_w1 + (long long)(nn - 8) * 64 + (k - 64)] : 0.0f;
-    return 0.0f;
+    int side;
+    const int o = head_row(nn, side);
+    if (o < 0) return 0.0f;
+    if (side == 0) return k < 64 ? prm[P.dc.g_w1 + (long long)o * 64 + k] : 0.0f;
+    return k >= 64 ? prm[P.dy.g_w1 + (long long)o * 64 + (k - 64)] : 0.0f;
   };
   auto g_fx1 = [&](int nn, int k) -> float { return prm[P.fx.g_w1 + (long long)nn * 128 + k]; };
   auto g_p0 = [&](int nn, int k) -> float {
@@ -239,8 +270,11 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
     for (int e = tid; e < d2; e += TNT) BP1[e] = P.frozen[P.pl[1].g_b + e];
     for (int e = tid; e < d3; e += TNT) BP2[e] = P.frozen[P.pl[2].g_b + e];
   }
-  if (tid < 2 * P.nd_c) BA1[tid] = prm[P.dc.g_b1 + tid];
-  if (tid >= 32 && tid < 32 + 2 * P.nd_y) BA1[8 + tid - 32] = prm[P.dy.g_b1 + tid - 32];
+  if (tid < 16) {
+    int side;
+    const int o = head_row(tid, side);
+    BA1[tid] = o < 0 ? 0.0f : prm[(side ? P.dy.g_b1 : P.dc.g_b1) + o];
+  }
 
   const float lsx = prm[P.g_lsx];
   const float sx = expf(lsx);
@@ -304,6 +338,11 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
   float dlsx = 0.0f;
   float tot[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   uint32_t wacc = 0;  // 0 on the first tile (weight-gradient accumulators start from zero)
+  long long phs[PROF ? TPH_COUNT : 1];
+#pragma unroll
+  for (int i = 0; i < (PROF ? TPH_COUNT : 1); ++i) phs[i] = 0;
+  long long t_last = (PROF && tid == 0) ? clock64() : 0;
+  TPHASE(TPH_SETUP);
 
   for (long long rb = blockIdx.x; rb < P.n_rowblocks; rb += gridDim.x) {
     const long long row0 = rb * P.RB;
@@ -370,6 +409,7 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
       EPS[i * TP + pp] = v;
     }
     __syncthreads();
+    TPHASE(TPH_ROWPAR_EPS);
 
     // ---- latents: z = loc + L eps, bijector, log q, log priors (one thread per pair) -------------------
     if (tid < TP) {
@@ -463,6 +503,8 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
       continue;
     }
 
+    __syncthreads();
+    TPHASE(TPH_LATENT);
     const bool pvalid = p < npairs;
     const int prow = (pvalid ? p : npairs - 1) / n;
     uint32_t mA[2] = {0u, 0u}, mH[2] = {0u, 0u};
@@ -489,8 +531,8 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
     }
     mma_stage(bar, phase, [&] { tc::issue_fwd(tb + C_S, oBIG, oWAX1, 16, 128, 0, terms); });
     {
-      float v[16];
-      tc::tmem_ld16(trow + C_S, v);
+      float v[8];
+      tc::tmem_ld8(trow + C_S + 8 * hh, v);
       const float inv = INV[I_AX1];
       const int nd = hh ? P.nd_y : P.nd_c;
       float g8[8];
@@ -498,15 +540,18 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
       for (int i = 0; i < 8; ++i) g8[i] = 0.0f;
       float R = 0.0f;
       if (hh == 0 || P.y != nullptr) {
-        for (int j = 0; j < nd; ++j) {
-          const float mean = v[8 * hh + j] * inv + BA1[8 * hh + j];
-          const float ls = v[8 * hh + nd + j] * inv + BA1[8 * hh + nd + j];
-          const float val = ROWRAW[((hh ? P.nd_c : 0) + j) * RBMAX + prow];
-          const float es = expf(ls), var = es * es, d = val - mean;
-          R += -(d * d) / (2.0f * var) - ls - LOG_SQRT_2PI;
-          if (pvalid) {
-            g8[j] = fminf(fmaxf(-d / var, -60000.0f), 60000.0f);
-            g8[nd + j] = fminf(fmaxf(-(d * d / var - 1.0f), -60000.0f), 60000.0f);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (j < nd) {
+            const float mean = v[j] * inv + BA1[8 * hh + j];
+            const float ls = v[4 + j] * inv + BA1[8 * hh + 4 + j];
+            const float val = ROWRAW[((hh ? P.nd_c : 0) + j) * RBMAX + prow];
+            const float es = expf(ls), var = es * es, d = val - mean;
+            R += -(d * d) / (2.0f * var) - ls - LOG_SQRT_2PI;
+            if (pvalid) {
+              g8[j] = fminf(fmaxf(-d / var, -60000.0f), 60000.0f);
+              g8[4 + j] = fminf(fmaxf(-(d * d / var - 1.0f), -60000.0f), 60000.0f);
+            }
           }
         }
       }
@@ -543,10 +588,13 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
         float v[16];
         tc::tmem_ld16(trow + C_S + 16, v);
         const float inv = INV[I_AX0D];
-        for (int k = 0; k < nzd; ++k) DZA[k * TP + p] = v[k] * inv;
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+          if (k < nzd) DZA[k * TP + p] = v[k] * inv;
       }
     }
 
+    TPHASE(TPH_AUX);
     // ================= physics surrogate forward + data-driven decoder ====================================
     mma_stage(bar, phase, [&] {
       tc::issue_fwd(tb + C_H, oLAT, oWFX0, 128, KZ, 0, terms);
@@ -560,7 +608,7 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
           float v[32];
           tc::tmem_ld32(trow + C_A0 + 32 * hh, v);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = tanhf(v[i] * inv);
+          for (int i = 0; i < 32; ++i) v[i] = tanh_fast(v[i] * inv);
           tc::tmem_st32(trow + C_A0 + 32 * hh, v);
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] *= s_t;
@@ -574,7 +622,7 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
         float v[32];
         tc::tmem_ld16(trow + C_A1 + 16 * hh, v);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = tanhf(v[i] * inv + BP1[16 * hh + i]);
+        for (int i = 0; i < 16; ++i) v[i] = tanh_fast(v[i] * inv + BP1[16 * hh + i]);
         tc::tmem_st16(trow + C_A1 + 16 * hh, v);  // tanh outputs saved for the backward
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] *= s_t;
@@ -587,7 +635,7 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
         float v[32];
         tc::tmem_ld32(trow + C_A2 + 32 * hh, v);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = tanhf(v[i] * inv + BP2[32 * hh + i]);
+        for (int i = 0; i < 32; ++i) v[i] = tanh_fast(v[i] * inv + BP2[32 * hh + i]);
         tc::tmem_st32(trow + C_A2 + 32 * hh, v);
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] *= s_h;
@@ -596,6 +644,7 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
       }
       mma_stage(bar, phase, [&] { tc::issue_fwd(tb + C_X, mkop(smb, T.a_big, T.l_big, TP, 0), oWP3, ndx, d3, 0, terms); });
     }
+    TPHASE(TPH_PHYS_FWD);
     // hidden layer of the data-driven decoder: ReLU (bias folded), mask kept in registers
     {
       const float inv = INV[I_FX0];
@@ -617,6 +666,7 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
     }
     mma_stage(bar, phase, [&] { tc::issue_fwd(tb + C_X, oBIG, oWFX1, ndx, 128, mlp ? 1u : 0u, terms); });
 
+    TPHASE(TPH_FX_FWD);
     // ---- x head: xh = xh_p + xh_d, Gaussian log-likelihood of raw x, residual gradient -----------------
     {
       const float inv = INV[I_X];
@@ -624,6 +674,14 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
       const long long drow = P.idx ? P.idx[lrow] : lrow;
       const float* xr = P.x + drow * ndx + nxh * hh;
       float ssq = 0.0f;
+      float xv[32];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        if (4 * c < nxh) {
+          const float4 t4 = __ldg(reinterpret_cast<const float4*>(xr) + c);
+          xv[4 * c] = t4.x; xv[4 * c + 1] = t4.y; xv[4 * c + 2] = t4.z; xv[4 * c + 3] = t4.w;
+        }
+      }
       float v[32];
       if (nxh == 32) tc::tmem_ld32(trow + C_X + 32 * hh, v);
       else tc::tmem_ld16(trow + C_X + 16 * hh, v);
@@ -635,7 +693,7 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
           if (!mlp) {
             // closed-form physics (cases/damped_oscillator/mass_spring.py:8-28, cases/simple_beam/simple_beam_model.py:4-30)
             const int d = nxh * hh + i;
-            if (P.phys_kind == 1) {
+            if (PHYS == 1) {
               const float om = sqrtf(1.0f / ZXIN[p]);
               const float bb = 0.0f / om;
               const float ph = om * P.grid[d];
@@ -651,14 +709,16 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
               xh += -1000.0f * w;
             }
           }
-          const float res = __ldg(xr + i) - xh;
+          const float res = xv[i] - xh;
           ssq = fmaf(res, res, ssq);
           v[i] = fminf(fmaxf(gsc * res, -60000.0f), 60000.0f);
           dbx[i] += v[i];
         }
       }
       if (P.with_grad) {
-        for (int c = 0; c < (nxh >> 3); ++c) put8(pG, T.l_g, TP, (nxh * hh) / 8 + c, p, v + 8 * c);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c < (nxh >> 3)) put8(pG, T.l_g, TP, (nxh * hh) / 8 + c, p, v + 8 * c);
       }
       SC[(S_Q0 + hh) * TP + p] = ssq;
     }
@@ -671,6 +731,7 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
       if (P.with_grad && valid) dlsx += -(P.alpha_x * wpair) * (S / var_x - (float)ndx);
     }
 
+    TPHASE(TPH_XHEAD);
     if (P.with_grad) {
       // ================= backward ============================================================================
       mma_stage(bar, phase, [&] {
@@ -712,7 +773,9 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
           // total dL/d(zc|zy): reversed + scaled gradient of the data-driven decoder (utils/transforms.py:207-219)
           // plus the auxiliary decoders' gradient
           const float inv = -P.lambda_g0 * cx * INV[I_FX0D];
-          for (int k = 0; k < nzd; ++k) DZA[k * TP + p] = fmaf(v[k], inv, (k < P.nz_c ? awc : awy) * DZA[k * TP + p]);
+#pragma unroll
+          for (int k = 0; k < 16; ++k)
+            if (k < nzd) DZA[k * TP + p] = fmaf(v[k], inv, (k < P.nz_c ? awc : awy) * DZA[k * TP + p]);
         }
         if (mlp) {
           float g[16], a[16];
@@ -725,6 +788,7 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
           for (int c = 0; c < 2; ++c) put8(pG, T.l_g, TP, 2 * hh + c, p, g + 8 * c);
         }
       }
+      TPHASE(TPH_BWD_FX);
       if (mlp) {
         mma_stage(bar, phase, [&] { tc::issue_dgrad(tb + C_X, mkop(smb, T.a_g, T.l_g, TP, 0), oWP1, d2, d1, 0, terms); });
         {
@@ -743,7 +807,11 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
           tc::tmem_ld16(trow + C_S, v);
           if (hh == 0) {
             const float inv = INV[I_P0D] * cx;
-            for (int k = 0; k < P.nz_x; ++k) DZX[k * TP + p] = v[cs0 + k] * inv / P.phys_in_std[k];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+              const int k = c - cs0;
+              if (k >= 0 && k < P.nz_x) DZX[k * TP + p] = v[c] * inv / P.phys_in_std[k];
+            }
           }
         }
       } else {
@@ -756,7 +824,7 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
             const __half* hrow = reinterpret_cast<const __half*>(gh + ((size_t)(d >> 3) * TP + p) * 16) + (d & 7);
             const __half* lrow = reinterpret_cast<const __half*>(gh + T.l_g + ((size_t)(d >> 3) * TP + p) * 16) + (d & 7);
             const float g = __half2float(*hrow) + __half2float(*lrow);
-            if (P.phys_kind == 1) {
+            if (PHYS == 1) {
               const float mass = ZXIN[p];
               const float om = sqrtf(1.0f / mass);
               const float dom = -om / (2.0f * mass);
@@ -790,6 +858,7 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
       }
       __syncthreads();
 
+      TPHASE(TPH_BWD_PHYS);
       // ---- latent backward: per-pair gradients w.r.t. loc / L / prior parameters ---------------------------
       {
         const int pp = tid & (TP - 1), prt = tid >> 7;
@@ -824,17 +893,22 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
     }
     __syncthreads();
 
+    TPHASE(TPH_LATENT_BWD);
     // ---- reduce the pairs over the MC axis into per-row accumulators ------------------------------------------
     {
       const int f0 = P.with_grad ? 0 : P.n_feat;
-      if (n_pow2) {
-        for (int it = warp + 4 * f0; it < 4 * n_acc; it += TNT / 32) {
-          const int f = it >> 2, pp = (it & 3) * 32 + lane;
-          const float* src = f < P.n_feat ? FEAT + f * TP : SC + (f - P.n_feat) * TP;
-          float v = src[pp];
-          for (int off = n >> 1; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-          const int r = pp / n;
-          if ((lane & (n - 1)) == 0 && r < nrows) ROWACC[f * RBMAX + r] = v;
+      if ((n & 3) == 0) {
+        for (int e = tid + f0 * RBMAX; e < n_acc * RBMAX; e += TNT) {
+          const int f = e / RBMAX, r = e - f * RBMAX;
+          if (r < nrows) {
+            const float4* src = reinterpret_cast<const float4*>((f < P.n_feat ? FEAT + f * TP : SC + (f - P.n_feat) * TP) + r * n);
+            float s = 0.0f;
+            for (int m = 0; m < (n >> 2); ++m) {
+              const float4 t = src[m];
+              s += (t.x + t.y) + (t.z + t.w);
+            }
+            ROWACC[f * RBMAX + r] = s;
+          }
         }
       } else {
         for (int e = tid + f0 * RBMAX; e < n_acc * RBMAX; e += TNT) {
@@ -850,6 +924,7 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
     }
     __syncthreads();
 
+    TPHASE(TPH_ROWRED);
     // ---- per-row outputs -----------------------------------------------------------------------------------
     if (tid < nrows) {
       const int r = tid;
@@ -924,6 +999,7 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
     // FEAT / ROWACC alias the BIG operand buffer: clear what the next tile's MMAs could read as padding
     __syncthreads();
     wacc = 1u;
+    TPHASE(TPH_ROWOUT);
   }  // tiles
 
   // ---- end of kernel: loss sums, weight gradients out of TMEM, bias / log_sigma_x sums ---------------------
@@ -953,19 +1029,27 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
         // fx0: dW[k][j] (128 x nzd), bias from the constant-one column; gradient reversal: the decoder's own
         // weights see the un-reversed gradient (utils/transforms.py:207-219 reverses only d/dz)
         const float sc = exp2f(-(float)E_LAT) * cx;
-        for (int j = 0; j < nzd; ++j) part[P.fx.g_w0 + (long long)k * nzd + j] = v0[j] * sc;
-        part[P.fx.g_b0 + k] = v0[c1] * sc;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (j < nzd) part[P.fx.g_w0 + (long long)k * nzd + j] = v0[j] * sc;
+          if (j == c1) part[P.fx.g_b0 + k] = v0[j] * sc;
+        }
       } else {
         const bool cside = k < 64;
         const Mlp2S& M = cside ? P.dc : P.dy;
         const int kk = cside ? k : k - 64;
         const float aw = cside ? awc : awy;
         const int nzk = cside ? P.nz_c : P.nz_y, j0 = cside ? 0 : P.nz_c;
-        const int nd2 = 2 * (cside ? P.nd_c : P.nd_y), n0 = cside ? 0 : 8;
         const float s1 = exp2f(-(float)E_H) * aw, s0 = exp2f(-(float)E_LAT) * aw;
-        for (int nn = 0; nn < nd2; ++nn) part[M.g_w1 + (long long)nn * 64 + kk] = va1[n0 + nn] * s1;
-        for (int j = 0; j < nzk; ++j) part[M.g_w0 + (long long)kk * nzk + j] = va0[j0 + j] * s0;
-        part[M.g_b0 + kk] = va0[c1] * s0;
+#pragma unroll
+        for (int col = 0; col < 16; ++col) {
+          int side;
+          const int o = head_row(col, side);
+          if (o >= 0 && side == (cside ? 0 : 1)) part[M.g_w1 + (long long)o * 64 + kk] = va1[col] * s1;
+          const int j = col - j0;
+          if (j >= 0 && j < nzk) part[M.g_w0 + (long long)kk * nzk + j] = va0[col] * s0;
+          if (col == c1) part[M.g_b0 + kk] = va0[col] * s0;
+        }
       }
     }
     // per-thread running sums -> fixed-order tree over the 128 pair slots of each column
@@ -986,12 +1070,12 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
     R0[TNT * 8 + tid] = dlsx;
     __syncthreads();
     if (tid < 16) {
-      const int h2 = tid >> 3, i = tid & 7;
-      const int nd2 = 2 * (h2 ? P.nd_y : P.nd_c);
-      if (i < nd2) {
+      int h2;
+      const int o = head_row(tid, h2);
+      if (o >= 0) {
         float s = 0.0f;
-        for (int j = 0; j < TP; ++j) s += R0[(h2 * TP + j) * 8 + i];
-        part[(h2 ? P.dy.g_b1 : P.dc.g_b1) + i] = s * (h2 ? awy : awc);
+        for (int j = 0; j < TP; ++j) s += R0[(h2 * TP + j) * 8 + (tid & 7)];
+        part[(h2 ? P.dy.g_b1 : P.dc.g_b1) + o] = s * (h2 ? awy : awc);
       }
     }
     if (tid == 32) {
@@ -1000,15 +1084,41 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
       part[P.g_lsx] = s;
     }
   }
+  TPHASE(TPH_FLUSH);
+  if (PROF && tid == 0)
+#pragma unroll
+    for (int k = 0; k < (PROF ? TPH_COUNT : 1); ++k) atomicAdd(reinterpret_cast<unsigned long long*>(P.phase) + k, (unsigned long long)phs[k]);
   tc::fence_before_sync();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(tb, C_ALLOC);
 }
 
-void launch_dec_tc(const TcParams& p, int grid, cudaStream_t s) { dec_tc_kernel<<<grid, TNT, p.total, s>>>(p); }
+template <bool PROF, int PHYS, int NDX>
+static void launch_one(const TcParams& p, int grid, cudaStream_t s) {
+  dec_tc_kernel<PROF, PHYS, NDX><<<grid, TNT, p.total, s>>>(p);
+}
+
+// supported (physics kind, nd_x) pairs: (MLP, 64) bridge, (mass_spring, 64) damped_oscillator, (beam, 32) simple_beam,
+// plus the other nd_x of each closed form
+void launch_dec_tc(const TcParams& p, int grid, cudaStream_t s) {
+  const int ph = p.d.phys_kind, nx = p.d.nd_x;
+  if (ph == 0 && nx == 64) {
+    if (p.d.phase != nullptr) launch_one<true, 0, 64>(p, grid, s);
+    else launch_one<false, 0, 64>(p, grid, s);
+  } else if (ph == 1 && nx == 64) launch_one<false, 1, 64>(p, grid, s);
+  else if (ph == 2 && nx == 32) launch_one<false, 2, 32>(p, grid, s);
+}
+
+bool dec_tc_has_variant(int phys_kind, int nd_x) {
+  return (phys_kind == 0 && nd_x == 64) || (phys_kind == 1 && nd_x == 64) || (phys_kind == 2 && nd_x == 32);
+}
 
 int configure_dec_tc_kernel() {
-  return (int)cudaFuncSetAttribute(dec_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  int e = (int)cudaFuncSetAttribute(dec_tc_kernel<true, 0, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  if (!e) e = (int)cudaFuncSetAttribute(dec_tc_kernel<false, 0, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  if (!e) e = (int)cudaFuncSetAttribute(dec_tc_kernel<false, 1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  if (!e) e = (int)cudaFuncSetAttribute(dec_tc_kernel<false, 2, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  return e;
 }
 
 }  // namespace dpv

@@ -101,6 +101,7 @@ struct TcParams {
 };
 void launch_dec_tc(const TcParams& p, int grid, cudaStream_t s);
 int configure_dec_tc_kernel();
+bool dec_tc_has_variant(int phys_kind, int nd_x);
 
 // ---- encoder-side kernels (forward and backward over "MLP2 units") ------------------------------
 struct EncUnit {

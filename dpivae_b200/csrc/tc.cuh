@@ -126,6 +126,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+  tmem_wait_ld();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
   uint32_t r[32];
 #pragma unroll
@@ -177,37 +187,61 @@ struct Op {
 };
 
 // GEMM issue helpers (ONE thread); k extents in elements, multiples of 16.  `terms` = 3 issues
-// hi*hi + lo*hi + hi*lo (fp32-accurate), `terms` = 1 only hi*hi (plain fp16 inputs).
+// hi*hi + lo*hi + hi*lo (fp32-accurate), `terms` = 1 only hi*hi (plain fp16 inputs).  Descriptors are kept
+// as (lo, hi) 32-bit words: stepping along K only adds a constant to the 14-bit start-address field.
+__device__ __forceinline__ uint64_t pack64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+constexpr uint32_t DESC_VERSION_HI = 1u << 14;  // descriptor bit 46
+
 //   fwd   : D[128 rows of A][N]   (+)= sum_k A[r][k] * W[n][k]      A K-major, W K-major (N rows)
-__device__ __forceinline__ void issue_fwd(uint32_t d_tmem, Op a, Op w, int N, int K, uint32_t accumulate, int terms) {
+__device__ __noinline__ void issue_fwd(uint32_t d_tmem, Op a, Op w, int N, int K, uint32_t accumulate, int terms) {
   const uint32_t idesc = make_idesc(128, N, 0, 0);
+  const uint32_t ahi = 8u | DESC_VERSION_HI, whi = 8u | DESC_VERSION_HI;       // SBO = 128 B
+  const uint32_t astep = 2u * (uint32_t)a.R, wstep = 2u * (uint32_t)w.R;       // two 16-byte K chunks per MMA
+  const int ks = K >> 4;
   for (int t = 0; t < terms; ++t) {
-    const uint32_t ab = a.base + (t == 1 ? a.lo_off : 0u), wb = w.base + (t == 2 ? w.lo_off : 0u);
-    for (int k = 0; k < K; k += 16) {
-      mma_f16(d_tmem, desc_kmajor(ab, a.R, k >> 3), desc_kmajor(wb, w.R, k >> 3), idesc, accumulate);
+    uint32_t alo = (((a.base + (t == 1 ? a.lo_off : 0u)) >> 4) & 0x3FFFu) | ((uint32_t)a.R << 16);  // LBO = R * 16 B
+    uint32_t wlo = (((w.base + (t == 2 ? w.lo_off : 0u)) >> 4) & 0x3FFFu) | ((uint32_t)w.R << 16);
+#pragma unroll 4
+    for (int k = 0; k < ks; ++k) {
+      mma_f16(d_tmem, pack64(alo, ahi), pack64(wlo, whi), idesc, accumulate);
       accumulate = 1;
+      alo += astep;
+      wlo += wstep;
     }
   }
 }
 //   dgrad : D[128 rows of G][Kin] (+)= sum_n G[r][n] * W[n][kin]    G K-major, W (Nout rows) MN-major over kin
-__device__ __forceinline__ void issue_dgrad(uint32_t d_tmem, Op g, Op w, int Nout, int Kin, uint32_t accumulate, int terms) {
+__device__ __noinline__ void issue_dgrad(uint32_t d_tmem, Op g, Op w, int Nout, int Kin, uint32_t accumulate, int terms) {
   const uint32_t idesc = make_idesc(128, Kin, 0, 1);
+  const uint32_t ghi = 8u | DESC_VERSION_HI, whi = (uint32_t)w.R | DESC_VERSION_HI;  // MN-major: SBO = R * 16 B
+  const uint32_t gstep = 2u * (uint32_t)g.R, wstep = 16u;                            // 16 K rows = 256 B
+  const int ks = Nout >> 4;
   for (int t = 0; t < terms; ++t) {
-    const uint32_t gb = g.base + (t == 1 ? g.lo_off : 0u), wb = w.base + (t == 2 ? w.lo_off : 0u);
-    for (int n = 0; n < Nout; n += 16) {
-      mma_f16(d_tmem, desc_kmajor(gb, g.R, n >> 3), desc_mnmajor(wb, w.R, 0, n), idesc, accumulate);
+    uint32_t glo = (((g.base + (t == 1 ? g.lo_off : 0u)) >> 4) & 0x3FFFu) | ((uint32_t)g.R << 16);
+    uint32_t wlo = (((w.base + (t == 2 ? w.lo_off : 0u)) >> 4) & 0x3FFFu) | (8u << 16);   // LBO = 128 B
+#pragma unroll 4
+    for (int k = 0; k < ks; ++k) {
+      mma_f16(d_tmem, pack64(glo, ghi), pack64(wlo, whi), idesc, accumulate);
       accumulate = 1;
+      glo += gstep;
+      wlo += wstep;
     }
   }
 }
 //   wgrad : D[128 cols of H][N cols of G] (+)= sum_r H[r][m] * G[r][n]   both MN-major, r over R rows
-__device__ __forceinline__ void issue_wgrad(uint32_t d_tmem, Op h, Op g, int N, uint32_t accumulate, int terms) {
+__device__ __noinline__ void issue_wgrad(uint32_t d_tmem, Op h, Op g, int N, uint32_t accumulate, int terms) {
   const uint32_t idesc = make_idesc(128, N, 1, 1);
+  const uint32_t hhi = (uint32_t)h.R | DESC_VERSION_HI, ghi = (uint32_t)g.R | DESC_VERSION_HI;
+  const int ks = h.R >> 4;
   for (int t = 0; t < terms; ++t) {
-    const uint32_t hb = h.base + (t == 1 ? h.lo_off : 0u), gb = g.base + (t == 2 ? g.lo_off : 0u);
-    for (int r = 0; r < h.R; r += 16) {
-      mma_f16(d_tmem, desc_mnmajor(hb, h.R, 0, r), desc_mnmajor(gb, g.R, 0, r), idesc, accumulate);
+    uint32_t hlo = (((h.base + (t == 1 ? h.lo_off : 0u)) >> 4) & 0x3FFFu) | (8u << 16);
+    uint32_t glo = (((g.base + (t == 2 ? g.lo_off : 0u)) >> 4) & 0x3FFFu) | (8u << 16);
+#pragma unroll 4
+    for (int k = 0; k < ks; ++k) {
+      mma_f16(d_tmem, pack64(hlo, hhi), pack64(glo, ghi), idesc, accumulate);
       accumulate = 1;
+      hlo += 16u;
+      glo += 16u;
     }
   }
 }

@@ -17,6 +17,8 @@ import bench  # noqa: E402
 import dpivae_b200 as dpv  # noqa: E402
 from dpivae_b200 import _lib  # noqa: E402
 
+TC_NAMES = ["setup", "rowpar_eps", "latent", "aux", "phys_fwd", "fx_fwd", "x_head", "bwd_fx", "bwd_phys", "latent_bwd",
+            "row_reduce", "row_out", "flush"]
 NAMES = ["setup", "rowpar", "eps", "latent_fwd", "aux_fwd", "aux_loss", "aux_bwd", "phys_fwd", "data_fwd", "x_loss",
          "data_bwd", "phys_bwd", "latent_bwd", "row_reduce", "row_out"]
 
@@ -24,6 +26,7 @@ NAMES = ["setup", "rowpar", "eps", "latent_fwd", "aux_fwd", "aux_loss", "aux_bwd
 def main():
     wl = dict(bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "bridge_p"])
     rows = int(sys.argv[2]) if len(sys.argv) > 2 else 32768
+    math = sys.argv[3] if len(sys.argv) > 3 else "fp32"
     case_mod = importlib.import_module(f"dpivae_b200.cases.{wl['case']}")
     dev = torch.device("cuda", 0)
     xs, cs, ys = bench.synth(case_mod, 4096, 7, dev)
@@ -33,6 +36,7 @@ def main():
     x, c, y = bench.synth(case_mod, rows, 5, dev)
     eng = vae.engine()
     eng.set_groups(dpv.param_groups(args))
+    eng.set_math_mode(math)
     w = (1.0, 1.0, 1.0, 1.0)
     for i in range(3):
         eng.loss(x, c, y, wl["n_mc"], w, True, adam_step=i + 1)
@@ -43,9 +47,10 @@ def main():
     _lib.check(eng.lib.dpivae_set_phase_buffer(eng.handle, C.c_void_p(None)))
     v = buf.cpu().tolist()
     tot = sum(v)
-    nchunks = rows * wl["n_mc"] / 64
-    print(f"workload {wl['case']} {wl['preset']} rows {rows}: {tot / nchunks:.0f} cycles per 64-pair chunk")
-    for nme, c_ in zip(NAMES, v):
+    tile = 64 if math == "fp32" else 128
+    nchunks = rows * wl["n_mc"] / tile
+    print(f"workload {wl['case']} {wl['preset']} rows {rows} math {math}: {tot / nchunks:.0f} cycles per {tile}-pair tile")
+    for nme, c_ in zip(NAMES if math == "fp32" else TC_NAMES, v):
         print(f"  {nme:12s} {100.0 * c_ / tot:5.1f}%  {c_ / nchunks:9.0f} cyc/chunk")
 
 
