@@ -264,7 +264,8 @@ static int build_plan(dpivae_model* h) {
   {
     const bool mlp = d.phys_kind == DPIVAE_PHYS_MLP;
     const int need = nzd + 1 + (mlp ? nzin : 0);
-    bool ok = need <= 16 && dec_tc_has_variant(d.phys_kind, d.nd_x) && !d.has_lambda_x && 2 * d.nd_c <= 8 && 2 * d.nd_y <= 8;
+    bool ok = need <= 16 && dec_tc_has_variant(d.phys_kind, d.nd_x) && !d.has_lambda_x && d.nd_c <= 2 && d.nd_y <= 2 &&
+              d.nz_c <= 4 && d.nz_y <= 4;
     if (mlp) ok = ok && d.phys_n_layers == 4 && d.phys_dims[1] == 64 && d.phys_dims[2] == 32 && d.phys_dims[3] == 64;
     if (ok) {
       const int KZ = 16, d1 = mlp ? 64 : 0, d2 = mlp ? 32 : 0, d3 = mlp ? 64 : 0;
@@ -275,8 +276,6 @@ static int build_plan(dpivae_model* h) {
         off = b; lo = bytes; b += 2 * bytes;
       };
       plane2(KZ / 8, 128, T.w_fx0, T.l_fx0);
-      plane2(KZ / 8, 128, T.w_ax0, T.l_ax0);
-      plane2(16, 16, T.w_ax1, T.l_ax1);
       plane2(16, d.nd_x, T.w_fx1, T.l_fx1);
       if (mlp) {
         plane2(KZ / 8, d1, T.w_p[0], T.l_p[0]);
@@ -287,12 +286,15 @@ static int build_plan(dpivae_model* h) {
       plane2(16, 128, T.a_big, T.l_big);
       plane2(8, 128, T.a_g, T.l_g);
       plane2(KZ / 8, 128, T.a_lat, T.l_lat);
+      plane2(2, 128, T.a_oa, T.l_oa);      // aux head gradients: 8 columns used, columns 8..15 stay zero (N = 16)
       auto f32 = [&](int floats) { int off = b; b += ((floats + 3) & ~3) * 4; return off; };
-      T.f_inv = f32(16); T.f_bias_x = f32(64); T.f_bias_p1 = f32(32); T.f_bias_p2 = f32(64); T.f_bias_a1 = f32(16);
-      T.f_eps = f32(Z * 128); T.f_u = f32(4 * 128); T.f_zxin = f32((nzin > 4 ? nzin : 4) * 128); T.f_zd = f32(nzd * 128);
-      T.f_dza = f32(nzd * 128); T.f_dzx = f32(4 * 128); T.f_sc = f32(8 * 128);
-      T.f_rowpar = f32(P.n_rowpar * RBMAX); T.f_rowraw = f32((d.nd_c + d.nd_y) * RBMAX); T.f_red = f32(256);
-      T.o_bar = b; b += 16;
+      T.f_inv = f32(16); T.f_bias_x = f32(64); T.f_bias_p1 = f32(32); T.f_bias_p2 = f32(64);
+      T.f_aw0 = f32(2 * 64 * 4); T.f_ab0 = f32(2 * 64); T.f_aw1 = f32(2 * 64 * 4); T.f_ab1 = f32(8);
+      T.f_eps = f32(Z * 128); T.f_u = f32(d.nz_x * 128); T.f_zxin = f32(nzin * 128); T.f_zd = f32(nzd * 128);
+      T.f_dza = f32(nzd * 128); T.f_dzx = f32(d.nz_x * 128); T.f_sc = f32(8 * 128);
+      T.f_rowpar = f32(P.n_rowpar * RBMAX); T.f_rowraw = f32((d.nd_c + d.nd_y) * RBMAX); T.f_rowlog = f32(5 * RBMAX);
+      T.f_red = f32(256);
+      T.o_bar = b; b += 32;
       T.total = (b + 127) & ~127;
       const int feat_bytes = (P.n_feat * 128 + (P.n_feat + 5) * RBMAX) * 4;
       if (T.total <= 232448 && feat_bytes <= 2 * T.l_big && 256 * 33 * 4 <= 2 * T.l_big) h->tc_ok = 1;

@@ -35,13 +35,13 @@ enum { C_W1 = 0, C_W0 = 64, C_AW1 = 80, C_AW0 = 96, C_H = 112, C_X = 240, C_S = 
 // power-of-two operand scales (exponents)
 constexpr int E_LAT = 4, E_H = 6, E_T = 8;
 // scalar rows (one value per pair)
-enum { S_KL = 0, S_RX, S_RC, S_RY, S_REG, S_W, S_Q0, S_Q1, S_ROWS };
+enum { S_KL = 0, S_RX, S_RC, S_RY, S_KL2, S_W, S_Q0, S_Q1, S_ROWS };
 // inverse-scale table
-enum { I_AX0 = 0, I_AX1, I_AX1D, I_AX0D, I_FX0, I_P0, I_P1, I_P2, I_X, I_XD, I_FX0D, I_P2D, I_P1D, I_P0D, I_COUNT };
+enum { I_FX0 = 0, I_P0, I_P1, I_P2, I_X, I_XD, I_FX0D, I_P2D, I_P1D, I_P0D, I_COUNT };
 
 // optional per-phase cycle accounting (thread 0, clock64); see tools/phase_profile.py
-enum { TPH_SETUP = 0, TPH_ROWPAR_EPS, TPH_LATENT, TPH_AUX, TPH_PHYS_FWD, TPH_FX_FWD, TPH_XHEAD, TPH_BWD_FX, TPH_BWD_PHYS, TPH_LATENT_BWD,
-       TPH_ROWRED, TPH_ROWOUT, TPH_FLUSH, TPH_COUNT };
+enum { TPH_SETUP = 0, TPH_ROWPAR_EPS, TPH_LATENT, TPH_AUX1, TPH_A0, TPH_AUX2, TPH_A1, TPH_HD, TPH_A2, TPH_XHEAD, TPH_BWD1, TPH_BWD2,
+       TPH_BWD3, TPH_BWD4, TPH_LATENT_BWD, TPH_ROWRED, TPH_ROWOUT, TPH_FLUSH, TPH_COUNT };
 #define TPHASE(k)                                  \
   do {                                             \
     if (PROF && tid == 0) {                        \
@@ -99,8 +99,9 @@ __device__ __forceinline__ tc::Op mkop(unsigned char* sm, int off, uint32_t lo_o
   return o;
 }
 
+// one MMA batch: make the operands written so far visible, let thread 0 issue + commit to `bar`; no wait
 template <class F>
-__device__ __forceinline__ void mma_stage(uint64_t* bar, uint32_t& phase, F issue) {
+__device__ __forceinline__ void stage_issue(uint64_t* bar, F issue) {
   tc::fence_async_smem();
   tc::fence_before_sync();
   __syncthreads();
@@ -109,10 +110,23 @@ __device__ __forceinline__ void mma_stage(uint64_t* bar, uint32_t& phase, F issu
     issue();
     tc::commit(bar);
   }
+  __syncwarp();
+}
+__device__ __forceinline__ void stage_wait(uint64_t* bar, uint32_t& phase) {
   tc::mbar_wait(bar, phase);
   phase ^= 1u;
   __syncwarp();
   tc::fence_after_sync();
+}
+
+// write 4 consecutive columns (half a chunk) of an X8 operand row
+__device__ __forceinline__ void put4(unsigned char* plane, uint32_t lo_off, int R, int chunk, int row, int half, const float* v) {
+  const __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+  const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+  const __half2 l0 = __floats2half2_rn(v[0] - f0.x, v[1] - f0.y), l1 = __floats2half2_rn(v[2] - f1.x, v[3] - f1.y);
+  unsigned char* dst = plane + ((size_t)chunk * R + row) * 16 + 8 * half;
+  *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+  *reinterpret_cast<uint2*>(dst + lo_off) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
 }
 
 // block-wide max of |v| over a strided getter; result broadcast (uses red[8])
@@ -155,7 +169,7 @@ __device__ void stage_weight(unsigned char* plane, uint32_t lo_off, int N, int K
 }  // namespace
 
 // PHYS: physics decoder kind (0 MLP surrogate, 1 mass_spring, 2 beam); NDX: response length -- compile-time so
-// that the epilogues are straight-line code (a taken branch in this ~200 KB kernel costs an I-cache miss)
+// that the epilogues are straight-line code (a taken branch in this large kernel costs an I-cache miss)
 template <bool PROF, int PHYS, int NDX>
 __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ TcParams T) {
   const DecParams& P = T.d;
@@ -163,7 +177,7 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
   float* smf = reinterpret_cast<float*>(smb);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int q = warp & 3, hh = warp >> 2;
-  const int p = 32 * q + lane;  // pair (TMEM lane) owned in the epilogues
+  const int p = 32 * q + lane;  // pair (TMEM lane) owned in the epilogues; hh = column half / aux side (0 = c, 1 = y)
   const int n = P.n_mc;
   const int nzd = P.nz_c + P.nz_y;
   const int nzin = P.nz_x + P.nd_p;
@@ -178,7 +192,10 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
   float* BX = smf + (T.f_bias_x >> 2);    // fx1 bias (+ last physics-layer bias)
   float* BP1 = smf + (T.f_bias_p1 >> 2);
   float* BP2 = smf + (T.f_bias_p2 >> 2);
-  float* BA1 = smf + (T.f_bias_a1 >> 2);  // aux head biases, c at 0.., y at 8..
+  float* AW0 = smf + (T.f_aw0 >> 2);      // aux first layers  [side][64][4]
+  float* AB0 = smf + (T.f_ab0 >> 2);      //                   [side][64]
+  float* AW1 = smf + (T.f_aw1 >> 2);      // aux heads, transposed [side][64][4]: mean_0, mean_1, ls_0, ls_1 per hidden unit
+  float* AB1 = smf + (T.f_ab1 >> 2);      //                   [side][4]
   float* EPS = smf + (T.f_eps >> 2);
   float* U = smf + (T.f_u >> 2);
   float* ZXIN = smf + (T.f_zxin >> 2);
@@ -188,17 +205,20 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
   float* SC = smf + (T.f_sc >> 2);
   float* ROWPAR = smf + (T.f_rowpar >> 2);
   float* ROWRAW = smf + (T.f_rowraw >> 2);
+  float* ROWLOG = smf + (T.f_rowlog >> 2);  // [n_blk + 2][RBMAX]: sum log diag L per block, sum log sigma of each prior
   float* RED = smf + (T.f_red >> 2);
   float* FEAT = smf + (T.a_big >> 2);  // aliases the BIG operand buffer (dead by then)
   float* ROWACC = FEAT + P.n_feat * TP;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smb + T.o_bar);
-  uint32_t* tptr = reinterpret_cast<uint32_t*>(smb + T.o_bar + 8);
+  uint64_t* bar0 = reinterpret_cast<uint64_t*>(smb + T.o_bar);
+  uint64_t* bar1 = bar0 + 1;
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(smb + T.o_bar + 16);
 
-  // ---- one-time: zero smem, barrier, TMEM, weights -------------------------------------------------
+  // ---- one-time: zero smem, barriers, TMEM, weights -------------------------------------------------
   for (int e = tid; e < (T.total >> 2); e += TNT) smf[e] = 0.0f;
   __syncthreads();
   if (tid == 0) {
-    tc::mbar_init(bar, 1);
+    tc::mbar_init(bar0, 1);
+    tc::mbar_init(bar1, 1);
     tc::mbar_fence_init();
   }
   __syncwarp();
@@ -211,28 +231,6 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
     if (k < nzd) return prm[P.fx.g_w0 + (long long)nn * nzd + k];
     return k == c1 ? prm[P.fx.g_b0 + nn] : 0.0f;
   };
-  auto g_ax0 = [&](int nn, int k) -> float {
-    if (nn < 64) {
-      if (k < P.nz_c) return prm[P.dc.g_w0 + (long long)nn * P.nz_c + k];
-      return k == c1 ? prm[P.dc.g_b0 + nn] : 0.0f;
-    }
-    if (k >= P.nz_c && k < nzd) return prm[P.dy.g_w0 + (long long)(nn - 64) * P.nz_y + (k - P.nz_c)];
-    return k == c1 ? prm[P.dy.g_b0 + nn - 64] : 0.0f;
-  };
-  // aux head columns: side s (0 = c, 1 = y) owns columns 8 s .. 8 s + 7: mean_j at 8 s + j, log_sigma_j at 8 s + 4 + j
-  auto head_row = [&](int col, int& side) -> int {  // decoder output index of an aux head column, or -1
-    side = col >> 3;
-    const int nd = side ? P.nd_y : P.nd_c, j = col & 3;
-    if (j >= nd) return -1;
-    return (col & 4) ? nd + j : j;
-  };
-  auto g_ax1 = [&](int nn, int k) -> float {
-    int side;
-    const int o = head_row(nn, side);
-    if (o < 0) return 0.0f;
-    if (side == 0) return k < 64 ? prm[P.dc.g_w1 + (long long)o * 64 + k] : 0.0f;
-    return k >= 64 ? prm[P.dy.g_w1 + (long long)o * 64 + (k - 64)] : 0.0f;
-  };
   auto g_fx1 = [&](int nn, int k) -> float { return prm[P.fx.g_w1 + (long long)nn * 128 + k]; };
   auto g_p0 = [&](int nn, int k) -> float {
     if (k >= cs0 && k < cs0 + nzin) return P.frozen[P.pl[0].g_w + (long long)nn * nzin + (k - cs0)];
@@ -244,8 +242,6 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
 
   const int KZ = T.KZ;
   const int k_fx0 = scale_exp(block_absmax(128 * KZ, [&](int e) { return g_fx0(e / KZ, e % KZ); }, RED));
-  const int k_ax0 = scale_exp(block_absmax(128 * KZ, [&](int e) { return g_ax0(e / KZ, e % KZ); }, RED));
-  const int k_ax1 = scale_exp(block_absmax(16 * 128, [&](int e) { return g_ax1(e >> 7, e & 127); }, RED));
   int k_x = scale_exp(block_absmax(ndx * 128, [&](int e) { return g_fx1(e >> 7, e & 127); }, RED));
   int k_p0 = 0, k_p1 = 0, k_p2 = 0;
   if (mlp) {
@@ -256,8 +252,6 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
     k_x = min(k_x, k_p3);  // fx1 and the last physics layer accumulate into the same TMEM columns
   }
   stage_weight(smb + T.w_fx0, T.l_fx0, 128, KZ, k_fx0, g_fx0);
-  stage_weight(smb + T.w_ax0, T.l_ax0, 128, KZ, k_ax0, g_ax0);
-  stage_weight(smb + T.w_ax1, T.l_ax1, 16, 128, k_ax1, g_ax1);
   stage_weight(smb + T.w_fx1, T.l_fx1, ndx, 128, k_x, g_fx1);
   if (mlp) {
     stage_weight(smb + T.w_p[0], T.l_p[0], d1, KZ, k_p0, g_p0);
@@ -270,10 +264,16 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
     for (int e = tid; e < d2; e += TNT) BP1[e] = P.frozen[P.pl[1].g_b + e];
     for (int e = tid; e < d3; e += TNT) BP2[e] = P.frozen[P.pl[2].g_b + e];
   }
-  if (tid < 16) {
-    int side;
-    const int o = head_row(tid, side);
-    BA1[tid] = o < 0 ? 0.0f : prm[(side ? P.dy.g_b1 : P.dc.g_b1) + o];
+  // auxiliary decoders (fp32, CUDA cores): side 0 = decoder_c, side 1 = decoder_y
+  for (int e = tid; e < 2 * 64 * 4; e += TNT) {
+    const int side = e >> 8, k = (e >> 2) & 63, j = e & 3;
+    const Mlp2S& M = side ? P.dy : P.dc;
+    const int nzs = side ? P.nz_y : P.nz_c, nd = side ? P.nd_y : P.nd_c;
+    AW0[e] = j < nzs ? prm[M.g_w0 + (long long)k * nzs + j] : 0.0f;
+    const int o = (j & 1) < nd ? ((j >> 1) * nd + (j & 1)) : -1;  // head column j: mean_(j&1) (j < 2) or log_sigma_(j&1)
+    AW1[e] = o >= 0 ? prm[M.g_w1 + (long long)o * 64 + k] : 0.0f;
+    if (j == 0) AB0[side * 64 + k] = prm[M.g_b0 + k];
+    if (k == 0) AB1[side * 4 + j] = o >= 0 ? prm[M.g_b1 + o] : 0.0f;
   }
 
   const float lsx = prm[P.g_lsx];
@@ -284,10 +284,6 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
   e_g = max(-8, min(e_g, 24));
   const float sg = exp2f((float)e_g);
   if (tid == 0) {
-    INV[I_AX0] = exp2f(-(float)(k_ax0 + E_LAT));
-    INV[I_AX1] = exp2f(-(float)(k_ax1 + E_H));
-    INV[I_AX1D] = exp2f(-(float)k_ax1);
-    INV[I_AX0D] = exp2f(-(float)k_ax0);
     INV[I_FX0] = exp2f(-(float)(k_fx0 + E_LAT));
     INV[I_P0] = exp2f(-(float)(k_p0 + E_LAT));
     INV[I_P1] = exp2f(-(float)(k_p1 + E_T));
@@ -307,34 +303,39 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
   tc::fence_after_sync();
   const uint32_t tb = *tptr;
   const uint32_t trow = tb + ((uint32_t)(32 * q) << 16);
-  uint32_t phase = 0;
+  uint32_t ph0 = 0, ph1 = 0;
 
   const float wpair = 1.0f / ((float)P.Bg * (float)(P.nd_x + P.nd_c + P.nd_y) * (float)n);
   const float cx = -(P.alpha_x * wpair) / var_x / sg;  // true dL/dxh = cx * g~
   const float awc = P.alpha_c * wpair, awy = P.alpha_y * wpair;
   const int n_acc = P.n_feat + 5;
-  const bool n_pow2 = (n & (n - 1)) == 0 && n <= 32;
   const float s_lat = exp2f((float)E_LAT), s_h = exp2f((float)E_H), s_t = exp2f((float)E_T);
+  const int RB = P.RB;
 
   // operands
   const tc::Op oLAT = mkop(smb, T.a_lat, T.l_lat, TP);
   const tc::Op oBIG = mkop(smb, T.a_big, T.l_big, TP);
   const tc::Op oG = mkop(smb, T.a_g, T.l_g, TP);
-  const tc::Op oWFX0 = mkop(smb, T.w_fx0, T.l_fx0, 128), oWAX0 = mkop(smb, T.w_ax0, T.l_ax0, 128);
-  const tc::Op oWAX1 = mkop(smb, T.w_ax1, T.l_ax1, 16), oWFX1 = mkop(smb, T.w_fx1, T.l_fx1, ndx);
+  const tc::Op oOA = mkop(smb, T.a_oa, T.l_oa, TP);
+  const tc::Op oWFX0 = mkop(smb, T.w_fx0, T.l_fx0, 128), oWFX1 = mkop(smb, T.w_fx1, T.l_fx1, ndx);
   const tc::Op oWP0 = mkop(smb, T.w_p[0], T.l_p[0], d1 ? d1 : 16), oWP1 = mkop(smb, T.w_p[1], T.l_p[1], d2 ? d2 : 16);
   const tc::Op oWP2 = mkop(smb, T.w_p[2], T.l_p[2], d3 ? d3 : 16), oWP3 = mkop(smb, T.w_p[3], T.l_p[3], ndx);
   unsigned char* pBIG = smb + T.a_big;
   unsigned char* pG = smb + T.a_g;
   unsigned char* pLAT = smb + T.a_lat;
+  unsigned char* pOA = smb + T.a_oa;
+
+  // aux side of this thread
+  const int a_nz = hh ? P.nz_y : P.nz_c, a_j0 = hh ? P.nz_c : 0, a_nd = hh ? P.nd_y : P.nd_c;
+  const float4* aW0 = reinterpret_cast<const float4*>(AW0) + hh * 64;
+  const float4* aW1 = reinterpret_cast<const float4*>(AW1) + hh * 64;
+  const float* aB0 = AB0 + hh * 64;
 
   // per-thread running sums over all tiles (fixed thread <-> column assignment: deterministic)
   float dbx[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) dbx[i] = 0.0f;
-  float dba[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) dba[i] = 0.0f;
+  float dba[4] = {0.f, 0.f, 0.f, 0.f};
   float dlsx = 0.0f;
   float tot[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   uint32_t wacc = 0;  // 0 on the first tile (weight-gradient accumulators start from zero)
@@ -345,20 +346,20 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
   TPHASE(TPH_SETUP);
 
   for (long long rb = blockIdx.x; rb < P.n_rowblocks; rb += gridDim.x) {
-    const long long row0 = rb * P.RB;
-    const int nrows = (int)min((long long)P.RB, B - row0);
+    const long long row0 = rb * RB;
+    const int nrows = (int)min((long long)RB, B - row0);
     const int npairs = nrows * n;
 
     // ---- per-row parameters of q(z|x) and of the conditional priors -------------------------------
-    for (int e = tid; e < RBMAX * P.Z; e += TNT) {
-      const int i = e / RBMAX, r = e - i * RBMAX;
+    for (int e = tid; e < RB * P.Z; e += TNT) {
+      const int i = e / RB, r = e - i * RB;
       const long long lrow = row0 + min(r, nrows - 1);
       const int b = block_of_tc(P, i), il = i - P.blk_start[b];
       const float pm = P.headpre[(long long)(P.henc[b] + il) * B + lrow];
       ROWPAR[(P.rp_loc + i) * RBMAX + r] = clampf_(pm, -50.0f, 50.0f);
     }
-    for (int e = tid; e < RBMAX * P.nL; e += TNT) {
-      const int li = e / RBMAX, r = e - li * RBMAX;
+    for (int e = tid; e < RB * P.nL; e += TNT) {
+      const int li = e / RB, r = e - li * RB;
       const long long lrow = row0 + min(r, nrows - 1);
       const int b = P.L_blk[li], i = P.L_i[li], j = P.L_j[li], nzb = P.blk_size[b];
       float v;
@@ -371,8 +372,8 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
       }
       ROWPAR[(P.rp_L + li) * RBMAX + r] = v;
     }
-    for (int e = tid; e < RBMAX * nzd; e += TNT) {
-      const int k = e / RBMAX, r = e - k * RBMAX;
+    for (int e = tid; e < RB * nzd; e += TNT) {
+      const int k = e / RB, r = e - k * RB;
       const long long lrow = row0 + min(r, nrows - 1);
       const int which = k < P.nz_c ? 0 : 1;
       const int kk = which ? k - P.nz_c : k, nzk = which ? P.nz_y : P.nz_c;
@@ -386,8 +387,8 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
       ROWPAR[(P.rp_pmu + k) * RBMAX + r] = mu;
       ROWPAR[(P.rp_psig + k) * RBMAX + r] = sgm;
     }
-    for (int e = tid; e < RBMAX * (P.nd_c + P.nd_y); e += TNT) {
-      const int j = e / RBMAX, r = e - j * RBMAX;
+    for (int e = tid; e < RB * (P.nd_c + P.nd_y); e += TNT) {
+      const int j = e / RB, r = e - j * RB;
       const long long lrow = row0 + min(r, nrows - 1);
       const long long drow = P.idx ? P.idx[lrow] : lrow;
       float v = 0.0f;
@@ -409,25 +410,38 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
       EPS[i * TP + pp] = v;
     }
     __syncthreads();
+    // per-row log-determinant terms (once per row instead of once per pair)
+    for (int e = tid; e < RB * (P.n_blk + 2); e += TNT) {
+      const int t = e / RB, r = e - t * RB;
+      float s = 0.0f;
+      if (t < P.n_blk) {
+        for (int i = 0; i < P.blk_size[t]; ++i) s += logf(ROWPAR[(P.rp_L + P.blk_loff[t] + i * (i + 1) / 2 + i) * RBMAX + r]);
+      } else {
+        const int k0 = t == P.n_blk ? 0 : P.nz_c, k1 = t == P.n_blk ? P.nz_c : nzd;
+        for (int k = k0; k < k1; ++k) s += logf(ROWPAR[(P.rp_psig + k) * RBMAX + r]);
+      }
+      ROWLOG[t * RBMAX + r] = s;
+    }
+    __syncthreads();
     TPHASE(TPH_ROWPAR_EPS);
 
-    // ---- latents: z = loc + L eps, bijector, log q, log priors (one thread per pair) -------------------
-    if (tid < TP) {
-      const int pp = tid;
-      const bool valid = pp < npairs;
-      const int qq = valid ? pp : npairs - 1;
-      const int r = qq / n, m = qq - r * n;
-      float dens = 0.0f, ld1 = 0.0f, ld2 = 0.0f, lpx = 0.0f;
-      for (int b = 0; b < P.n_blk; ++b) {
+    // ---- latents: z = loc + L eps, bijector, log q, log priors.  Both threads of a pair work: thread hh takes the
+    //      latent blocks b with (b & 1) == hh of the P model (x and y | c); the single block of the S model is hh = 0's
+    const bool pvalid = p < npairs;
+    const int prow = (pvalid ? p : npairs - 1) / n;
+    const int pm_ = (pvalid ? p : npairs - 1) - prow * n;
+    float lq_part = 0.0f;   // this thread's share of log q (minus bijector log-det) - log p(zx)
+    {
+      float ld1 = 0.0f, ld2 = 0.0f, lpx = 0.0f;
+      for (int b = hh; b < P.n_blk; b += 2) {
         const int s = P.blk_start[b], nzb = P.blk_size[b];
-        float ss = 0.0f, hld = 0.0f;
+        float ss = 0.0f;
         for (int i = 0; i < nzb; ++i) {
-          float acc = ROWPAR[(P.rp_loc + s + i) * RBMAX + r];
+          float acc = ROWPAR[(P.rp_loc + s + i) * RBMAX + prow];
           const int base = P.rp_L + P.blk_loff[b] + i * (i + 1) / 2;
-          for (int j = 0; j <= i; ++j) acc = fmaf(ROWPAR[(base + j) * RBMAX + r], EPS[(s + j) * TP + pp], acc);
-          const float e = EPS[(s + i) * TP + pp];
+          for (int j = 0; j <= i; ++j) acc = fmaf(ROWPAR[(base + j) * RBMAX + prow], EPS[(s + j) * TP + p], acc);
+          const float e = EPS[(s + i) * TP + p];
           ss = fmaf(e, e, ss);
-          hld += logf(ROWPAR[(base + i) * RBMAX + r]);
           const int gi = s + i;
           if (gi < P.nz_x) {
             const float u = sigmoidf_(acc);
@@ -435,8 +449,8 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
             const float zx = fmaf(u, a, P.lb[gi]);
             ld1 += acc - 2.0f * softplusf_(acc);
             ld2 += logf(fabsf(a));
-            U[gi * TP + pp] = u;
-            ZXIN[gi * TP + pp] = zx;
+            U[gi * TP + p] = u;
+            ZXIN[gi * TP + p] = zx;
             if (P.prior_kind[gi] == 0) {
               const bool inside = (zx >= P.prior_a[gi]) && (zx < P.prior_b[gi]);
               lpx += (inside ? 0.0f : -INFINITY) - logf(P.prior_b[gi] - P.prior_a[gi]);
@@ -445,228 +459,234 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
               lpx += -(d * d) / (2.0f * P.prior_b[gi] * P.prior_b[gi]) - logf(P.prior_b[gi]) - LOG_SQRT_2PI;
             }
           } else {
-            ZD[(gi - P.nz_x) * TP + pp] = acc;
+            ZD[(gi - P.nz_x) * TP + p] = acc;
           }
         }
-        const float lq = -0.5f * ((float)nzb * LOG_2PI + ss) - hld;
-        if (b == 0) dens = lq - (ld1 + ld2);
-        else dens += lq;
+        lq_part += -0.5f * ((float)nzb * LOG_2PI + ss) - ROWLOG[b * RBMAX + prow];
       }
-      for (int j = 0; j < P.nd_p; ++j) ZXIN[(P.nz_x + j) * TP + pp] = ROWRAW[P.idx_c_phys[j] * RBMAX + r];
-      float lpc, lpy;
-      {
-        float mh = 0.0f, hl = 0.0f;
-        for (int k = 0; k < P.nz_c; ++k) {
-          const float sgm = ROWPAR[(P.rp_psig + k) * RBMAX + r];
-          const float t = (ZD[k * TP + pp] - ROWPAR[(P.rp_pmu + k) * RBMAX + r]) / sgm;
-          mh = fmaf(t, t, mh);
-          hl += logf(sgm);
+      if (hh == 0) {
+        for (int j = 0; j < P.nd_p; ++j) ZXIN[(P.nz_x + j) * TP + p] = ROWRAW[P.idx_c_phys[j] * RBMAX + prow];
+      }
+      SC[(S_Q0 + hh) * TP + p] = lq_part - (ld1 + ld2);  // dens share (log q minus bijector log-det)
+      lq_part = lq_part - (ld1 + ld2) - lpx;
+    }
+    __syncthreads();
+    {
+      // conditional prior of side hh: p(zc|c) (hh = 0) or p(zy|y) (hh = 1), diagonal Gaussian
+      float mh = 0.0f;
+      for (int k = a_j0; k < a_j0 + a_nz; ++k) {
+        const float t = (ZD[k * TP + p] - ROWPAR[(P.rp_pmu + k) * RBMAX + prow]) / ROWPAR[(P.rp_psig + k) * RBMAX + prow];
+        mh = fmaf(t, t, mh);
+      }
+      const float lp = -0.5f * ((float)a_nz * LOG_2PI + mh) - ROWLOG[(P.n_blk + hh) * RBMAX + prow];
+      SC[(hh ? S_KL2 : S_KL) * TP + p] = pvalid ? lq_part - lp : 0.0f;
+      if (hh == 0) {
+        SC[S_W * TP + p] = pvalid ? wpair : 0.0f;
+        if (pvalid && (P.out.dens || P.out.zx || P.out.zc || P.out.zy)) {
+          const long long o = (long long)pm_ * B + row0 + prow;
+          if (P.out.dens) P.out.dens[o] = SC[S_Q0 * TP + p] + SC[S_Q1 * TP + p];
+          if (P.out.zx) for (int k = 0; k < P.nz_x; ++k) P.out.zx[o * P.nz_x + k] = ZXIN[k * TP + p];
+          if (P.out.zc) for (int k = 0; k < P.nz_c; ++k) P.out.zc[o * P.nz_c + k] = ZD[k * TP + p];
+          if (P.out.zy) for (int k = 0; k < P.nz_y; ++k) P.out.zy[o * P.nz_y + k] = ZD[(P.nz_c + k) * TP + p];
         }
-        lpc = -0.5f * ((float)P.nz_c * LOG_2PI + mh) - hl;
-        mh = 0.0f; hl = 0.0f;
-        for (int k = P.nz_c; k < nzd; ++k) {
-          const float sgm = ROWPAR[(P.rp_psig + k) * RBMAX + r];
-          const float t = (ZD[k * TP + pp] - ROWPAR[(P.rp_pmu + k) * RBMAX + r]) / sgm;
-          mh = fmaf(t, t, mh);
-          hl += logf(sgm);
-        }
-        lpy = -0.5f * ((float)P.nz_y * LOG_2PI + mh) - hl;
       }
-      const float klp = dens - ((lpx + lpc) + lpy);
-      SC[S_KL * TP + pp] = valid ? klp : 0.0f;
-      SC[S_W * TP + pp] = valid ? wpair : 0.0f;
-      if (valid) {
-        const long long o = (long long)m * B + row0 + r;
-        if (P.out.dens) P.out.dens[o] = dens;
-        if (P.out.zx) for (int k = 0; k < P.nz_x; ++k) P.out.zx[o * P.nz_x + k] = ZXIN[k * TP + pp];
-        if (P.out.zc) for (int k = 0; k < P.nz_c; ++k) P.out.zc[o * P.nz_c + k] = ZD[k * TP + pp];
-        if (P.out.zy) for (int k = 0; k < P.nz_y; ++k) P.out.zy[o * P.nz_y + k] = ZD[(P.nz_c + k) * TP + pp];
-      }
-      // latent operand row: [zd | 1 | standardised physics input | 0], scaled by 2^E_LAT
-      for (int ch = 0; ch < (KZ >> 3); ++ch) {
-        float v[8];
+      // latent operand row, chunk hh: [zd | 1 | standardised physics input | 0], scaled by 2^E_LAT
+      float v[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int k = 8 * ch + i;
-          float x = 0.0f;
-          if (k < nzd) x = valid ? ZD[k * TP + pp] : 0.0f;
-          else if (k == c1) x = 1.0f;
-          else if (mlp && k >= cs0 && k < cs0 + nzin)
-            x = valid ? (ZXIN[(k - cs0) * TP + pp] - P.phys_in_mean[k - cs0]) / P.phys_in_std[k - cs0] : 0.0f;
-          v[i] = x * s_lat;
-        }
-        put8(pLAT, T.l_lat, TP, ch, pp, v);
+      for (int i = 0; i < 8; ++i) {
+        const int k = 8 * hh + i;
+        float x = 0.0f;
+        if (k < nzd) x = pvalid ? ZD[k * TP + p] : 0.0f;
+        else if (k == c1) x = 1.0f;
+        else if (mlp && k >= cs0 && k < cs0 + nzin)
+          x = pvalid ? (ZXIN[(k - cs0) * TP + p] - P.phys_in_mean[k - cs0]) / P.phys_in_std[k - cs0] : 0.0f;
+        v[i] = x * s_lat;
       }
+      put8(pLAT, T.l_lat, TP, hh, p, v);
     }
     if (P.latent_only) {
       __syncthreads();
       continue;
     }
-
-    __syncthreads();
+    // ---- first layers of the data-driven decoder and of the physics surrogate: issued now, consumed later ----
+    stage_issue(bar0, [&] {
+      tc::issue_fwd(tb + C_H, oLAT, oWFX0, 128, KZ, 0, terms);
+      if (mlp) tc::issue_fwd(tb + C_A0, oLAT, oWP0, d1, KZ, 0, terms);
+    });
     TPHASE(TPH_LATENT);
-    const bool pvalid = p < npairs;
-    const int prow = (pvalid ? p : npairs - 1) / n;
-    uint32_t mA[2] = {0u, 0u}, mH[2] = {0u, 0u};
 
-    // ================= auxiliary decoders (block-diagonal) ==============================================
-    mma_stage(bar, phase, [&] { tc::issue_fwd(tb + C_H, oLAT, oWAX0, 128, KZ, 0, terms); });
+    // ================= auxiliary decoder of side hh, forward, on the CUDA cores (fp32) =======================
+    // Block-diagonal ownership: thread (p, hh) owns all 64 hidden units and the head of decoder hh for pair p, so
+    // forward and dgrad need no cross-thread traffic; only the two weight gradients (sums over pairs) go to the
+    // tensor cores, as fire-and-forget MMAs on the operand copies written here.
+    float z4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) z4[j] = (j < a_nz && pvalid) ? ZD[(a_j0 + j) * TP + p] : 0.0f;
+    unsigned long long mkA = 0ull;
+    float g4[4] = {0.f, 0.f, 0.f, 0.f};
     {
-      const float inv = INV[I_AX0];
+      float o0 = AB1[hh * 4 + 0], o1 = AB1[hh * 4 + 1], o2 = AB1[hh * 4 + 2], o3 = AB1[hh * 4 + 3];
+#pragma unroll 2
+      for (int c = 0; c < 8; ++c) {
+        float hv[8];
+        uint32_t m8 = 0u;
 #pragma unroll
-      for (int blk = 0; blk < 2; ++blk) {
-        float v[32];
-        tc::tmem_ld32(trow + C_H + 64 * hh + 32 * blk, v);
-        uint32_t mk = 0u;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float a = v[i] * inv;
-          mk |= (a > 0.0f ? 1u : 0u) << i;
-          v[i] = fmaxf(a, 0.0f) * s_h;
+        for (int i = 0; i < 8; ++i) {
+          const int k = 8 * c + i;
+          const float4 w = aW0[k];
+          const float pre = fmaf(z4[3], w.w, fmaf(z4[2], w.z, fmaf(z4[1], w.y, fmaf(z4[0], w.x, aB0[k]))));
+          const float h = fmaxf(pre, 0.0f);
+          m8 |= (pre > 0.0f ? 1u : 0u) << i;
+          const float4 t = aW1[k];
+          o0 = fmaf(h, t.x, o0); o1 = fmaf(h, t.y, o1); o2 = fmaf(h, t.z, o2); o3 = fmaf(h, t.w, o3);
+          hv[i] = h * s_h;
         }
-        mA[blk] = mk;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) put8(pBIG, T.l_big, TP, (64 * hh + 32 * blk) / 8 + c, p, v + 8 * c);
+        mkA |= (unsigned long long)m8 << (8 * c);
+        if (P.with_grad) put8(pBIG, T.l_big, TP, 8 * hh + c, p, hv);
       }
-    }
-    mma_stage(bar, phase, [&] { tc::issue_fwd(tb + C_S, oBIG, oWAX1, 16, 128, 0, terms); });
-    {
-      float v[8];
-      tc::tmem_ld8(trow + C_S + 8 * hh, v);
-      const float inv = INV[I_AX1];
-      const int nd = hh ? P.nd_y : P.nd_c;
-      float g8[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) g8[i] = 0.0f;
+      // Gaussian log-likelihood of the raw covariate / label and its gradient w.r.t. (mean, log sigma)
       float R = 0.0f;
       if (hh == 0 || P.y != nullptr) {
+        const float om[2] = {o0, o1}, ol[2] = {o2, o3};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (j < nd) {
-            const float mean = v[j] * inv + BA1[8 * hh + j];
-            const float ls = v[4 + j] * inv + BA1[8 * hh + 4 + j];
+        for (int j = 0; j < 2; ++j) {
+          if (j < a_nd) {
             const float val = ROWRAW[((hh ? P.nd_c : 0) + j) * RBMAX + prow];
-            const float es = expf(ls), var = es * es, d = val - mean;
-            R += -(d * d) / (2.0f * var) - ls - LOG_SQRT_2PI;
+            const float es = expf(ol[j]), var = es * es, d = val - om[j];
+            R += -(d * d) / (2.0f * var) - ol[j] - LOG_SQRT_2PI;
             if (pvalid) {
-              g8[j] = fminf(fmaxf(-d / var, -60000.0f), 60000.0f);
-              g8[4 + j] = fminf(fmaxf(-(d * d / var - 1.0f), -60000.0f), 60000.0f);
+              g4[j] = fminf(fmaxf(-d / var, -60000.0f), 60000.0f);
+              g4[2 + j] = fminf(fmaxf(-(d * d / var - 1.0f), -60000.0f), 60000.0f);
             }
           }
         }
       }
       SC[(hh ? S_RY : S_RC) * TP + p] = pvalid ? R : 0.0f;
       if (P.with_grad) {
-        put8(pG, T.l_g, TP, hh, p, g8);
+        put4(pOA, T.l_oa, TP, 0, p, hh, g4);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) dba[i] += g8[i];
+        for (int i = 0; i < 4; ++i) dba[i] += g4[i];
       }
     }
-    if (P.with_grad) {
-      mma_stage(bar, phase, [&] {
-        tc::issue_wgrad(tb + C_AW1, oBIG, oG, 16, wacc, terms);
-        tc::issue_dgrad(tb + C_H, oG, oWAX1, 16, 128, 0, terms);
-      });
-      {
-        const float inv = INV[I_AX1D];
-#pragma unroll
-        for (int blk = 0; blk < 2; ++blk) {
-          float v[32];
-          tc::tmem_ld32(trow + C_H + 64 * hh + 32 * blk, v);
-          const uint32_t mk = mA[blk];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = ((mk >> i) & 1u) ? v[i] * inv : 0.0f;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) put8(pBIG, T.l_big, TP, (64 * hh + 32 * blk) / 8 + c, p, v + 8 * c);
-        }
-      }
-      mma_stage(bar, phase, [&] {
-        tc::issue_wgrad(tb + C_AW0, oBIG, oLAT, KZ, wacc, terms);
-        tc::issue_dgrad(tb + C_S + 16, oBIG, oWAX0, 128, KZ, 0, terms);
-      });
-      if (hh == 0) {
-        float v[16];
-        tc::tmem_ld16(trow + C_S + 16, v);
-        const float inv = INV[I_AX0D];
-#pragma unroll
-        for (int k = 0; k < 16; ++k)
-          if (k < nzd) DZA[k * TP + p] = v[k] * inv;
-      }
-    }
+    if (P.with_grad) stage_issue(bar1, [&] { tc::issue_wgrad(tb + C_AW1, oBIG, oOA, 16, wacc, terms); });
+    TPHASE(TPH_AUX1);
 
-    TPHASE(TPH_AUX);
-    // ================= physics surrogate forward + data-driven decoder ====================================
-    mma_stage(bar, phase, [&] {
-      tc::issue_fwd(tb + C_H, oLAT, oWFX0, 128, KZ, 0, terms);
-      if (mlp) tc::issue_fwd(tb + C_A0, oLAT, oWP0, d1, KZ, 0, terms);
-    });
+    // ================= physics layer 0 -> tanh (bias folded into the constant-one column) =====================
+    stage_wait(bar0, ph0);
     if (mlp) {
-      // layer 0 -> tanh (bias folded into the constant-one column)
-      {
-        const float inv = INV[I_P0];
-        if (d1 == 64) {
-          float v[32];
-          tc::tmem_ld32(trow + C_A0 + 32 * hh, v);
+      const float inv = INV[I_P0];
+#pragma unroll 2
+      for (int c = 0; c < 4; ++c) {
+        float v[8];
+        tc::tmem_ld8(trow + C_A0 + 32 * hh + 8 * c, v);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = tanh_fast(v[i] * inv);
-          tc::tmem_st32(trow + C_A0 + 32 * hh, v);
+        for (int i = 0; i < 8; ++i) v[i] = tanh_fast(v[i] * inv);
+        tc::tmem_st8(trow + C_A0 + 32 * hh + 8 * c, v);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] *= s_t;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) put8(pBIG, T.l_big, TP, 4 * hh + c, p, v + 8 * c);
-        }
+        for (int i = 0; i < 8; ++i) v[i] *= s_t;
+        put8(pG, T.l_g, TP, 4 * hh + c, p, v);
       }
-      mma_stage(bar, phase, [&] { tc::issue_fwd(tb + C_A1, mkop(smb, T.a_big, T.l_big, TP, 0), oWP1, d2, d1, 0, terms); });
+      stage_issue(bar0, [&] { tc::issue_fwd(tb + C_A1, oG, oWP1, d2, d1, 0, terms); });
+    }
+    TPHASE(TPH_A0);
+
+    // ================= auxiliary decoder backward (dgrad on the CUDA cores) =====================================
+    if (P.with_grad) {
+      stage_wait(bar1, ph1);  // wgrad aux1 done: BIG may be overwritten
+      float gz0 = 0.f, gz1 = 0.f, gz2 = 0.f, gz3 = 0.f;
+#pragma unroll 2
+      for (int c = 0; c < 8; ++c) {
+        float hv[8];
+        const uint32_t m8 = (uint32_t)(mkA >> (8 * c)) & 0xFFu;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int k = 8 * c + i;
+          const float4 t = aW1[k];
+          float gh = fmaf(g4[3], t.w, fmaf(g4[2], t.z, fmaf(g4[1], t.y, g4[0] * t.x)));
+          gh = ((m8 >> i) & 1u) ? gh : 0.0f;
+          const float4 w = aW0[k];
+          gz0 = fmaf(gh, w.x, gz0); gz1 = fmaf(gh, w.y, gz1); gz2 = fmaf(gh, w.z, gz2); gz3 = fmaf(gh, w.w, gz3);
+          hv[i] = gh;
+        }
+        put8(pBIG, T.l_big, TP, 8 * hh + c, p, hv);
+      }
+      const float gz[4] = {gz0, gz1, gz2, gz3};
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < a_nz) DZA[(a_j0 + j) * TP + p] = gz[j];
+      stage_issue(bar1, [&] { tc::issue_wgrad(tb + C_AW0, oBIG, oLAT, KZ, wacc, terms); });
+    }
+    TPHASE(TPH_AUX2);
+
+    if (mlp) {
+      // ================= physics layer 1 -> tanh ===================================================================
+      stage_wait(bar0, ph0);
       {
         const float inv = INV[I_P1];
-        float v[32];
-        tc::tmem_ld16(trow + C_A1 + 16 * hh, v);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = tanh_fast(v[i] * inv + BP1[16 * hh + i]);
-        tc::tmem_st16(trow + C_A1 + 16 * hh, v);  // tanh outputs saved for the backward
+        for (int c = 0; c < 2; ++c) {
+          float v[8];
+          tc::tmem_ld8(trow + C_A1 + 16 * hh + 8 * c, v);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] *= s_t;
+          for (int i = 0; i < 8; ++i) v[i] = tanh_fast(v[i] * inv + BP1[16 * hh + 8 * c + i]);
+          tc::tmem_st8(trow + C_A1 + 16 * hh + 8 * c, v);
 #pragma unroll
-        for (int c = 0; c < 2; ++c) put8(pBIG, T.l_big, TP, 8 + 2 * hh + c, p, v + 8 * c);
+          for (int i = 0; i < 8; ++i) v[i] *= s_t;
+          put8(pG, T.l_g, TP, 2 * hh + c, p, v);
+        }
       }
-      mma_stage(bar, phase, [&] { tc::issue_fwd(tb + C_A2, mkop(smb, T.a_big, T.l_big, TP, 64), oWP2, d3, d2, 0, terms); });
-      {
-        const float inv = INV[I_P2];
-        float v[32];
-        tc::tmem_ld32(trow + C_A2 + 32 * hh, v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = tanh_fast(v[i] * inv + BP2[32 * hh + i]);
-        tc::tmem_st32(trow + C_A2 + 32 * hh, v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] *= s_h;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) put8(pBIG, T.l_big, TP, 4 * hh + c, p, v + 8 * c);
-      }
-      mma_stage(bar, phase, [&] { tc::issue_fwd(tb + C_X, mkop(smb, T.a_big, T.l_big, TP, 0), oWP3, ndx, d3, 0, terms); });
+      stage_issue(bar0, [&] { tc::issue_fwd(tb + C_A2, oG, oWP2, d3, d2, 0, terms); });
     }
-    TPHASE(TPH_PHYS_FWD);
-    // hidden layer of the data-driven decoder: ReLU (bias folded), mask kept in registers
+    TPHASE(TPH_A1);
+
+    // ================= hidden layer of the data-driven decoder: ReLU (bias folded), mask in registers ============
+    if (P.with_grad) stage_wait(bar1, ph1);  // wgrad aux0 done: BIG may be overwritten
+    unsigned long long mkH = 0ull;
     {
       const float inv = INV[I_FX0];
+#pragma unroll 2
+      for (int c = 0; c < 8; ++c) {
+        float v[8];
+        tc::tmem_ld8(trow + C_H + 64 * hh + 8 * c, v);
+        uint32_t m8 = 0u;
 #pragma unroll
-      for (int blk = 0; blk < 2; ++blk) {
-        float v[32];
-        tc::tmem_ld32(trow + C_H + 64 * hh + 32 * blk, v);
-        uint32_t mk = 0u;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
+        for (int i = 0; i < 8; ++i) {
           const float a = v[i] * inv;
-          mk |= (a > 0.0f ? 1u : 0u) << i;
+          m8 |= (a > 0.0f ? 1u : 0u) << i;
           v[i] = fmaxf(a, 0.0f) * s_h;
         }
-        mH[blk] = mk;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) put8(pBIG, T.l_big, TP, (64 * hh + 32 * blk) / 8 + c, p, v + 8 * c);
+        mkH |= (unsigned long long)m8 << (8 * c);
+        put8(pBIG, T.l_big, TP, 8 * hh + c, p, v);
       }
     }
-    mma_stage(bar, phase, [&] { tc::issue_fwd(tb + C_X, oBIG, oWFX1, ndx, 128, mlp ? 1u : 0u, terms); });
+    TPHASE(TPH_HD);
 
-    TPHASE(TPH_FX_FWD);
+    if (mlp) {
+      // ================= physics layer 2 -> tanh ===================================================================
+      stage_wait(bar0, ph0);
+      {
+        const float inv = INV[I_P2];
+#pragma unroll 2
+        for (int c = 0; c < 4; ++c) {
+          float v[8];
+          tc::tmem_ld8(trow + C_A2 + 32 * hh + 8 * c, v);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = tanh_fast(v[i] * inv + BP2[32 * hh + 8 * c + i]);
+          tc::tmem_st8(trow + C_A2 + 32 * hh + 8 * c, v);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] *= s_h;
+          put8(pG, T.l_g, TP, 4 * hh + c, p, v);
+        }
+      }
+    }
+    // x head = data-driven decoder output (+ last physics layer) into the same accumulator
+    stage_issue(bar0, [&] {
+      tc::issue_fwd(tb + C_X, oBIG, oWFX1, ndx, 128, 0, terms);
+      if (mlp) tc::issue_fwd(tb + C_X, oG, oWP3, ndx, d3, 1, terms);
+    });
+    TPHASE(TPH_A2);
+    stage_wait(bar0, ph0);
+
     // ---- x head: xh = xh_p + xh_d, Gaussian log-likelihood of raw x, residual gradient -----------------
     {
       const float inv = INV[I_X];
@@ -674,144 +694,149 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
       const long long drow = P.idx ? P.idx[lrow] : lrow;
       const float* xr = P.x + drow * ndx + nxh * hh;
       float ssq = 0.0f;
-      float xv[32];
+      float xv[nxh];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        if (4 * c < nxh) {
-          const float4 t4 = __ldg(reinterpret_cast<const float4*>(xr) + c);
-          xv[4 * c] = t4.x; xv[4 * c + 1] = t4.y; xv[4 * c + 2] = t4.z; xv[4 * c + 3] = t4.w;
-        }
+      for (int c = 0; c < nxh / 4; ++c) {
+        const float4 t4 = __ldg(reinterpret_cast<const float4*>(xr) + c);
+        xv[4 * c] = t4.x; xv[4 * c + 1] = t4.y; xv[4 * c + 2] = t4.z; xv[4 * c + 3] = t4.w;
       }
-      float v[32];
-      if (nxh == 32) tc::tmem_ld32(trow + C_X + 32 * hh, v);
-      else tc::tmem_ld16(trow + C_X + 16 * hh, v);
+      float v[nxh];
+      tld<nxh>(trow + C_X + nxh * hh, v);
       const float gsc = pvalid ? sg : 0.0f;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        if (i < nxh) {
-          float xh = v[i] * inv + BX[nxh * hh + i];
-          if (!mlp) {
-            // closed-form physics (cases/damped_oscillator/mass_spring.py:8-28, cases/simple_beam/simple_beam_model.py:4-30)
-            const int d = nxh * hh + i;
-            if (PHYS == 1) {
-              const float om = sqrtf(1.0f / ZXIN[p]);
-              const float bb = 0.0f / om;
-              const float ph = om * P.grid[d];
-              xh += bb * sinf(ph) + 1.0f * cosf(ph);
-            } else {
-              const float E = ZXIN[p] * 1e6f, a = ZXIN[TP + p], b = 1.0f - a, xg = P.grid[d];
-              const float den1 = 6.0f * E * 2e-6f * 1.0f, den2 = 6.0f * E * 2e-6f;
-              float w = 1.0f * b * xg * (1.0f - b * b - xg * xg) / den1;
-              if (xg > a) {
-                const float t = xg - a;
-                w += 1.0f * (t * t * t) / den2;
-              }
-              xh += -1000.0f * w;
+      for (int i = 0; i < nxh; ++i) {
+        float xh = v[i] * inv + BX[nxh * hh + i];
+        if (PHYS != 0) {
+          // closed-form physics (cases/damped_oscillator/mass_spring.py:8-28, cases/simple_beam/simple_beam_model.py:4-30)
+          const int d = nxh * hh + i;
+          if (PHYS == 1) {
+            const float om = sqrtf(1.0f / ZXIN[p]);
+            const float bb = 0.0f / om;
+            const float ph = om * P.grid[d];
+            xh += bb * sinf(ph) + 1.0f * cosf(ph);
+          } else {
+            const float E = ZXIN[p] * 1e6f, a = ZXIN[TP + p], b = 1.0f - a, xg = P.grid[d];
+            const float den1 = 6.0f * E * 2e-6f * 1.0f, den2 = 6.0f * E * 2e-6f;
+            float w = 1.0f * b * xg * (1.0f - b * b - xg * xg) / den1;
+            if (xg > a) {
+              const float t = xg - a;
+              w += 1.0f * (t * t * t) / den2;
             }
+            xh += -1000.0f * w;
           }
-          const float res = xv[i] - xh;
-          ssq = fmaf(res, res, ssq);
-          v[i] = fminf(fmaxf(gsc * res, -60000.0f), 60000.0f);
-          dbx[i] += v[i];
         }
+        const float res = xv[i] - xh;
+        ssq = fmaf(res, res, ssq);
+        v[i] = fminf(fmaxf(gsc * res, -60000.0f), 60000.0f);
+        dbx[i] += v[i];
       }
       if (P.with_grad) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-          if (c < (nxh >> 3)) put8(pG, T.l_g, TP, (nxh * hh) / 8 + c, p, v + 8 * c);
+        for (int c = 0; c < nxh / 8; ++c) put8(pG, T.l_g, TP, (nxh * hh) / 8 + c, p, v + 8 * c);
       }
       SC[(S_Q0 + hh) * TP + p] = ssq;
     }
-    __syncthreads();
-    if (tid < TP) {
-      const bool valid = tid < npairs;
-      const float S = SC[S_Q0 * TP + tid] + SC[S_Q1 * TP + tid];
-      SC[S_RX * TP + tid] = valid ? (-S / (2.0f * var_x) - (float)ndx * (lsx + LOG_SQRT_2PI)) : 0.0f;
-      SC[S_REG * TP + tid] = 0.0f;
-      if (P.with_grad && valid) dlsx += -(P.alpha_x * wpair) * (S / var_x - (float)ndx);
-    }
-
-    TPHASE(TPH_XHEAD);
     if (P.with_grad) {
       // ================= backward ============================================================================
-      mma_stage(bar, phase, [&] {
+      stage_issue(bar0, [&] {
         tc::issue_wgrad(tb + C_W1, oBIG, oG, ndx, wacc, terms);
         tc::issue_dgrad(tb + C_H, oG, oWFX1, ndx, 128, 0, terms);
         if (mlp) tc::issue_dgrad(tb + C_X, oG, oWP3, ndx, d3, 0, terms);
       });
+    } else {
+      __syncthreads();
+    }
+    if (tid < TP) {
+      const bool valid = tid < npairs;
+      const float S = SC[S_Q0 * TP + tid] + SC[S_Q1 * TP + tid];
+      SC[S_RX * TP + tid] = valid ? (-S / (2.0f * var_x) - (float)ndx * (lsx + LOG_SQRT_2PI)) : 0.0f;
+      if (P.with_grad && valid) dlsx += -(P.alpha_x * wpair) * (S / var_x - (float)ndx);
+    }
+    TPHASE(TPH_XHEAD);
+
+    if (P.with_grad) {
+      stage_wait(bar0, ph0);
+      if (mlp) {
+        // d tanh of physics layer 2 (operand for the next dgrad), then let that dgrad run under the ReLU-mask epilogue
+        const float inv = INV[I_XD];
+#pragma unroll 2
+        for (int c = 0; c < 4; ++c) {
+          float g[8], a[8];
+          tc::tmem_ld8(trow + C_X + 32 * hh + 8 * c, g);
+          tc::tmem_ld8(trow + C_A2 + 32 * hh + 8 * c, a);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) g[i] = g[i] * inv * (1.0f - a[i] * a[i]);
+          put8(pG, T.l_g, TP, 4 * hh + c, p, g);
+        }
+        stage_issue(bar1, [&] { tc::issue_dgrad(tb + C_X, oG, oWP2, d3, d2, 0, terms); });
+      }
       {
         const float inv = INV[I_XD];
+#pragma unroll 2
+        for (int c = 0; c < 8; ++c) {
+          float v[8];
+          tc::tmem_ld8(trow + C_H + 64 * hh + 8 * c, v);
+          const uint32_t m8 = (uint32_t)(mkH >> (8 * c)) & 0xFFu;
 #pragma unroll
-        for (int blk = 0; blk < 2; ++blk) {
-          float v[32];
-          tc::tmem_ld32(trow + C_H + 64 * hh + 32 * blk, v);
-          const uint32_t mk = mH[blk];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = ((mk >> i) & 1u) ? v[i] * inv : 0.0f;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) put8(pBIG, T.l_big, TP, (64 * hh + 32 * blk) / 8 + c, p, v + 8 * c);
-        }
-        if (mlp) {
-          float g[32], a[32];
-          tc::tmem_ld32(trow + C_X + 32 * hh, g);
-          tc::tmem_ld32(trow + C_A2 + 32 * hh, a);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) g[i] = g[i] * inv * (1.0f - a[i] * a[i]);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) put8(pG, T.l_g, TP, 4 * hh + c, p, g + 8 * c);
+          for (int i = 0; i < 8; ++i) v[i] = ((m8 >> i) & 1u) ? v[i] * inv : 0.0f;
+          put8(pBIG, T.l_big, TP, 8 * hh + c, p, v);
         }
       }
-      mma_stage(bar, phase, [&] {
+      TPHASE(TPH_BWD1);
+      if (mlp) {
+        stage_wait(bar1, ph1);
+        const float inv = INV[I_P2D];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          float g[8], a[8];
+          tc::tmem_ld8(trow + C_X + 16 * hh + 8 * c, g);
+          tc::tmem_ld8(trow + C_A1 + 16 * hh + 8 * c, a);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) g[i] = g[i] * inv * (1.0f - a[i] * a[i]);
+          put8(pG, T.l_g, TP, 2 * hh + c, p, g);
+        }
+      }
+      stage_issue(bar0, [&] {
+        if (mlp) tc::issue_dgrad(tb + C_X, oG, oWP1, d2, d1, 0, terms);
         tc::issue_wgrad(tb + C_W0, oBIG, oLAT, KZ, wacc, terms);
         tc::issue_dgrad(tb + C_S, oBIG, oWFX0, 128, KZ, 0, terms);
-        if (mlp) tc::issue_dgrad(tb + C_X, mkop(smb, T.a_g, T.l_g, TP, 0), oWP2, d3, d2, 0, terms);
       });
-      {
+      TPHASE(TPH_BWD2);
+      stage_wait(bar0, ph0);
+      if (mlp) {
+        const float inv = INV[I_P1D];
+#pragma unroll 2
+        for (int c = 0; c < 4; ++c) {
+          float g[8], a[8];
+          tc::tmem_ld8(trow + C_X + 32 * hh + 8 * c, g);
+          tc::tmem_ld8(trow + C_A0 + 32 * hh + 8 * c, a);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) g[i] = g[i] * inv * (1.0f - a[i] * a[i]);
+          put8(pG, T.l_g, TP, 4 * hh + c, p, g);
+        }
+        stage_issue(bar1, [&] { tc::issue_dgrad(tb + C_S + 16, oG, oWP0, d1, KZ, 0, terms); });
+      }
+      if (hh == 0) {
+        // total dL/d(zc|zy): reversed + scaled gradient of the data-driven decoder (utils/transforms.py:207-219)
+        // plus the auxiliary decoders' gradient
         float v[16];
         tc::tmem_ld16(trow + C_S, v);
-        if (hh == 0) {
-          // total dL/d(zc|zy): reversed + scaled gradient of the data-driven decoder (utils/transforms.py:207-219)
-          // plus the auxiliary decoders' gradient
-          const float inv = -P.lambda_g0 * cx * INV[I_FX0D];
+        const float inv = -P.lambda_g0 * cx * INV[I_FX0D];
 #pragma unroll
-          for (int k = 0; k < 16; ++k)
-            if (k < nzd) DZA[k * TP + p] = fmaf(v[k], inv, (k < P.nz_c ? awc : awy) * DZA[k * TP + p]);
-        }
-        if (mlp) {
-          float g[16], a[16];
-          tc::tmem_ld16(trow + C_X + 16 * hh, g);
-          tc::tmem_ld16(trow + C_A1 + 16 * hh, a);
-          const float inv = INV[I_P2D];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) g[i] = g[i] * inv * (1.0f - a[i] * a[i]);
-#pragma unroll
-          for (int c = 0; c < 2; ++c) put8(pG, T.l_g, TP, 2 * hh + c, p, g + 8 * c);
-        }
+        for (int k = 0; k < 16; ++k)
+          if (k < nzd) DZA[k * TP + p] = fmaf(v[k], inv, (k < P.nz_c ? awc : awy) * DZA[k * TP + p]);
       }
-      TPHASE(TPH_BWD_FX);
+      TPHASE(TPH_BWD3);
       if (mlp) {
-        mma_stage(bar, phase, [&] { tc::issue_dgrad(tb + C_X, mkop(smb, T.a_g, T.l_g, TP, 0), oWP1, d2, d1, 0, terms); });
-        {
-          float g[32], a[32];
-          tc::tmem_ld32(trow + C_X + 32 * hh, g);
-          tc::tmem_ld32(trow + C_A0 + 32 * hh, a);
-          const float inv = INV[I_P1D];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) g[i] = g[i] * inv * (1.0f - a[i] * a[i]);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) put8(pG, T.l_g, TP, 4 * hh + c, p, g + 8 * c);
-        }
-        mma_stage(bar, phase, [&] { tc::issue_dgrad(tb + C_S, mkop(smb, T.a_g, T.l_g, TP, 0), oWP0, d1, KZ, 0, terms); });
-        {
+        stage_wait(bar1, ph1);
+        if (hh == 0) {
           float v[16];
-          tc::tmem_ld16(trow + C_S, v);
-          if (hh == 0) {
-            const float inv = INV[I_P0D] * cx;
+          tc::tmem_ld16(trow + C_S + 16, v);
+          const float inv = INV[I_P0D] * cx;
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
-              const int k = c - cs0;
-              if (k >= 0 && k < P.nz_x) DZX[k * TP + p] = v[c] * inv / P.phys_in_std[k];
-            }
+          for (int c = 0; c < 16; ++c) {
+            const int k = c - cs0;
+            if (k >= 0 && k < P.nz_x) DZX[k * TP + p] = v[c] * inv / P.phys_in_std[k];
           }
         }
       } else {
@@ -819,6 +844,7 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
         float s0 = 0.0f, s1 = 0.0f;
         {
           const unsigned char* gh = pG;
+#pragma unroll 4
           for (int i = 0; i < nxh; ++i) {
             const int d = nxh * hh + i;
             const __half* hrow = reinterpret_cast<const __half*>(gh + ((size_t)(d >> 3) * TP + p) * 16) + (d & 7);
@@ -857,8 +883,8 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
         }
       }
       __syncthreads();
+      TPHASE(TPH_BWD4);
 
-      TPHASE(TPH_BWD_PHYS);
       // ---- latent backward: per-pair gradients w.r.t. loc / L / prior parameters ---------------------------
       {
         const int pp = tid & (TP - 1), prt = tid >> 7;
@@ -892,8 +918,8 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
       }
     }
     __syncthreads();
-
     TPHASE(TPH_LATENT_BWD);
+
     // ---- reduce the pairs over the MC axis into per-row accumulators ------------------------------------------
     {
       const int f0 = P.with_grad ? 0 : P.n_feat;
@@ -923,32 +949,30 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
       }
     }
     __syncthreads();
-
     TPHASE(TPH_ROWRED);
+
     // ---- per-row outputs -----------------------------------------------------------------------------------
     if (tid < nrows) {
       const int r = tid;
       const float inv_n = 1.0f / (float)n;
-      const float kl = ROWACC[(P.n_feat + S_KL) * RBMAX + r] * inv_n;
+      const float kl = (ROWACC[(P.n_feat + S_KL) * RBMAX + r] + ROWACC[(P.n_feat + S_KL2) * RBMAX + r]) * inv_n;
       const float rx = ROWACC[(P.n_feat + S_RX) * RBMAX + r] * inv_n;
       const float rc = ROWACC[(P.n_feat + S_RC) * RBMAX + r] * inv_n;
       const float ry = ROWACC[(P.n_feat + S_RY) * RBMAX + r] * inv_n;
-      const float rg = ROWACC[(P.n_feat + S_REG) * RBMAX + r] * inv_n;
-      const float loss = P.beta_x * kl - P.alpha_x * rx - P.alpha_c * rc - P.alpha_y * ry - rg;
+      const float loss = P.beta_x * kl - P.alpha_x * rx - P.alpha_c * rc - P.alpha_y * ry;
       if (P.out.row_loss) {
         float* o = P.out.row_loss + row0 + r;
-        o[0] = loss; o[B] = kl; o[2 * B] = rx; o[3 * B] = rc; o[4 * B] = ry; o[5 * B] = rg;
+        o[0] = loss; o[B] = kl; o[2 * B] = rx; o[3 * B] = rc; o[4 * B] = ry; o[5 * B] = 0.0f;
       }
       ROWACC[(P.n_feat + S_KL) * RBMAX + r] = kl;
       ROWACC[(P.n_feat + S_RX) * RBMAX + r] = rx;
       ROWACC[(P.n_feat + S_RC) * RBMAX + r] = rc;
       ROWACC[(P.n_feat + S_RY) * RBMAX + r] = ry;
-      ROWACC[(P.n_feat + S_REG) * RBMAX + r] = rg;
       SC[S_Q0 * TP + r] = loss;
     }
     if (P.with_grad) {
-      for (int e = tid; e < RBMAX * P.Z; e += TNT) {
-        const int i = e / RBMAX, r = e - i * RBMAX;
+      for (int e = tid; e < RB * P.Z; e += TNT) {
+        const int i = e / RB, r = e - i * RB;
         if (r < nrows) {
           const long long lrow = row0 + r;
           const int b = block_of_tc(P, i), il = i - P.blk_start[b], nzb = P.blk_size[b];
@@ -971,8 +995,8 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
           P.gpre[os] = (ps >= -7.0f && ps <= 3.0f) ? ROWACC[(P.f_L + ld) * RBMAX + r] * expf(ps) : 0.0f;
         }
       }
-      for (int e = tid; e < RBMAX * nzd; e += TNT) {
-        const int k = e / RBMAX, r = e - k * RBMAX;
+      for (int e = tid; e < RB * nzd; e += TNT) {
+        const int k = e / RB, r = e - k * RB;
         if (r < nrows) {
           const long long lrow = row0 + r;
           const int which = k < P.nz_c ? 0 : 1;
@@ -993,10 +1017,8 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
         tot[2] += ROWACC[(P.n_feat + S_RX) * RBMAX + r];
         tot[3] += ROWACC[(P.n_feat + S_RC) * RBMAX + r];
         tot[4] += ROWACC[(P.n_feat + S_RY) * RBMAX + r];
-        tot[5] += ROWACC[(P.n_feat + S_REG) * RBMAX + r];
       }
     }
-    // FEAT / ROWACC alias the BIG operand buffer: clear what the next tile's MMAs could read as padding
     __syncthreads();
     wacc = 1u;
     TPHASE(TPH_ROWOUT);
@@ -1013,12 +1035,10 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
     // fx1: dW[n][k] (nd_x x 128)
     {
       const float sc = exp2f(-(float)E_H) * cx;
-      float v[32];
-      if (nxh == 32) tc::tmem_ld32(trow + C_W1 + 32 * hh, v);
-      else tc::tmem_ld16(trow + C_W1 + 16 * hh, v);
+      float v[nxh];
+      tld<nxh>(trow + C_W1 + nxh * hh, v);
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (i < nxh) part[P.fx.g_w1 + (long long)(nxh * hh + i) * 128 + k] = v[i] * sc;
+      for (int i = 0; i < nxh; ++i) part[P.fx.g_w1 + (long long)(nxh * hh + i) * 128 + k] = v[i] * sc;
     }
     {
       float v0[16], va1[16], va0[16];
@@ -1026,8 +1046,8 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
       tc::tmem_ld16(trow + C_AW1, va1);
       tc::tmem_ld16(trow + C_AW0, va0);
       if (hh == 0) {
-        // fx0: dW[k][j] (128 x nzd), bias from the constant-one column; gradient reversal: the decoder's own
-        // weights see the un-reversed gradient (utils/transforms.py:207-219 reverses only d/dz)
+        // fx0: dW[k][j] (128 x nzd), bias from the constant-one column; the decoder's own weights see the
+        // un-reversed gradient (utils/transforms.py:207-219 reverses only d/dz)
         const float sc = exp2f(-(float)E_LAT) * cx;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -1035,24 +1055,23 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
           if (j == c1) part[P.fx.g_b0 + k] = v0[j] * sc;
         }
       } else {
-        const bool cside = k < 64;
-        const Mlp2S& M = cside ? P.dc : P.dy;
-        const int kk = cside ? k : k - 64;
-        const float aw = cside ? awc : awy;
-        const int nzk = cside ? P.nz_c : P.nz_y, j0 = cside ? 0 : P.nz_c;
+        // aux decoders: hidden unit k of side (k >> 6); heads in columns 4 side + {mean_0, mean_1, ls_0, ls_1}
+        const int side = k >> 6, kk = k & 63;
+        const Mlp2S& M = side ? P.dy : P.dc;
+        const float aw = side ? awy : awc;
+        const int nzk = side ? P.nz_y : P.nz_c, j0 = side ? P.nz_c : 0, nd = side ? P.nd_y : P.nd_c;
         const float s1 = exp2f(-(float)E_H) * aw, s0 = exp2f(-(float)E_LAT) * aw;
 #pragma unroll
         for (int col = 0; col < 16; ++col) {
-          int side;
-          const int o = head_row(col, side);
-          if (o >= 0 && side == (cside ? 0 : 1)) part[M.g_w1 + (long long)o * 64 + kk] = va1[col] * s1;
+          const int jj = col & 3;
+          if ((col >> 2) == side && (jj & 1) < nd) part[M.g_w1 + (long long)((jj >> 1) * nd + (jj & 1)) * 64 + kk] = va1[col] * s1;
           const int j = col - j0;
           if (j >= 0 && j < nzk) part[M.g_w0 + (long long)kk * nzk + j] = va0[col] * s0;
           if (col == c1) part[M.g_b0 + kk] = va0[col] * s0;
         }
       }
     }
-    // per-thread running sums -> fixed-order tree over the 128 pair slots of each column
+    // per-thread running sums -> fixed-order sums over the 128 pair slots of each column
     __syncthreads();
     float* R0 = FEAT;  // [TNT][32]
 #pragma unroll
@@ -1066,21 +1085,21 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
     }
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < 8; ++i) R0[tid * 8 + i] = dba[i];
-    R0[TNT * 8 + tid] = dlsx;
+    for (int i = 0; i < 4; ++i) R0[tid * 4 + i] = dba[i];
+    R0[TNT * 4 + tid] = dlsx;
     __syncthreads();
-    if (tid < 16) {
-      int h2;
-      const int o = head_row(tid, h2);
-      if (o >= 0) {
+    if (tid < 8) {
+      const int side = tid >> 2, jj = tid & 3;
+      const int nd = side ? P.nd_y : P.nd_c;
+      if ((jj & 1) < nd) {
         float s = 0.0f;
-        for (int j = 0; j < TP; ++j) s += R0[(h2 * TP + j) * 8 + (tid & 7)];
-        part[(h2 ? P.dy.g_b1 : P.dc.g_b1) + o] = s * (h2 ? awy : awc);
+        for (int j = 0; j < TP; ++j) s += R0[(side * TP + j) * 4 + jj];
+        part[(side ? P.dy.g_b1 : P.dc.g_b1) + (jj >> 1) * nd + (jj & 1)] = s * (side ? awy : awc);
       }
     }
     if (tid == 32) {
       float s = 0.0f;
-      for (int j = 0; j < TP; ++j) s += R0[TNT * 8 + j];
+      for (int j = 0; j < TP; ++j) s += R0[TNT * 4 + j];
       part[P.g_lsx] = s;
     }
   }

@@ -91,11 +91,11 @@ struct TcParams {
   DecParams d;
   int terms;                 // 3 = fp16 hi/lo split (fp32-accurate), 1 = plain fp16 inputs
   int KZ, c_ones, c_s0;      // latent operand: columns, constant-one column, first physics-input column
-  int w_fx0, w_fx1, w_ax0, w_ax1, w_p[4];   // weight operands (hi plane), lo plane at + l_*
-  int l_fx0, l_fx1, l_ax0, l_ax1, l_p[4];
-  int a_big, a_g, a_lat, l_big, l_g, l_lat; // activation / gradient operands
-  int f_inv, f_bias_x, f_bias_p1, f_bias_p2, f_bias_a1;
-  int f_eps, f_u, f_zxin, f_zd, f_dza, f_dzx, f_sc, f_rowpar, f_rowraw, f_red;
+  int w_fx0, w_fx1, w_p[4];  // weight operands (hi plane), lo plane at + l_*
+  int l_fx0, l_fx1, l_p[4];
+  int a_big, a_g, a_lat, a_oa, l_big, l_g, l_lat, l_oa;   // activation / gradient operands
+  int f_inv, f_bias_x, f_bias_p1, f_bias_p2, f_aw0, f_ab0, f_aw1, f_ab1;
+  int f_eps, f_u, f_zxin, f_zd, f_dza, f_dzx, f_sc, f_rowpar, f_rowraw, f_rowlog, f_red;
   int o_bar;
   int total;
 };

@@ -152,6 +152,13 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
   tmem_wait_st();
 }
 
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+               "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+               "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+               : "memory");
+  tmem_wait_st();
+}
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
   uint32_t r[16];
 #pragma unroll

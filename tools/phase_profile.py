@@ -17,8 +17,8 @@ import bench  # noqa: E402
 import dpivae_b200 as dpv  # noqa: E402
 from dpivae_b200 import _lib  # noqa: E402
 
-TC_NAMES = ["setup", "rowpar_eps", "latent", "aux", "phys_fwd", "fx_fwd", "x_head", "bwd_fx", "bwd_phys", "latent_bwd",
-            "row_reduce", "row_out", "flush"]
+TC_NAMES = ["setup", "rowpar_eps", "latent", "aux_fwd", "phys_l0", "aux_bwd", "phys_l1", "fx_hidden", "phys_l2+x_mma", "x_head",
+            "bwd1", "bwd2", "bwd3", "bwd4", "latent_bwd", "row_reduce", "row_out", "flush"]
 NAMES = ["setup", "rowpar", "eps", "latent_fwd", "aux_fwd", "aux_loss", "aux_bwd", "phys_fwd", "data_fwd", "x_loss",
          "data_bwd", "phys_bwd", "latent_bwd", "row_reduce", "row_out"]
 
@@ -40,7 +40,7 @@ def main():
     w = (1.0, 1.0, 1.0, 1.0)
     for i in range(3):
         eng.loss(x, c, y, wl["n_mc"], w, True, adam_step=i + 1)
-    buf = torch.zeros(16, dtype=torch.int64, device=dev)
+    buf = torch.zeros(32, dtype=torch.int64, device=dev)
     _lib.check(eng.lib.dpivae_set_phase_buffer(eng.handle, C.c_void_p(buf.data_ptr())))
     eng.loss(x, c, y, wl["n_mc"], w, True, adam_step=4)
     torch.cuda.synchronize()
