@@ -30,6 +30,12 @@ WORKLOADS = {
     "beam_s": dict(case="simple_beam", preset="dpivae", rows=65536, n_mc=16, cpu_rows=16384,
                    flop_step=548_352, flop_dec=2 * 16 * ((4 * 128 + 128 * 32) * 3 + (2 * 64 + 128) * 2 * 3), bytes_row=160),
 }
+MATH_DOC = {
+    "tc_fp16x3": "decoder GEMMs on tcgen05: fp32 operands split into fp16 hi+lo planes, 3 MMAs per GEMM, fp32 TMEM accumulators "
+                 "(parity 1e-5 vs the fp64 oracle, tests/test_gpu_tc.py); encoders / ELBO / Adam fp32 FFMA",
+    "fp32": "all GEMMs fp32 FFMA on the CUDA cores",
+    "tc_fp16": "decoder GEMMs on tcgen05 with plain fp16 operands, fp32 accumulate (tolerance 2e-3 loss / 2e-2 gradients)",
+}
 METRIC = "ELBO train samples/s (fwd+bwd+Adam)"
 UNIT = "datapoints/s"
 
@@ -171,8 +177,11 @@ def main():
     ap.add_argument("--workload", default="bridge_p", choices=list(WORKLOADS))
     ap.add_argument("--rows", type=int, default=0, help="override rows per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--math", default="fp32", choices=["fp32", "tc_fp16x3", "tc_fp16"],
-                    help="decoder GEMM arithmetic (include/dpivae_b200.h DPIVAE_MATH_*)")
+    ap.add_argument("--math", default="tc_fp16x3", choices=["fp32", "tc_fp16x3", "tc_fp16"],
+                    help="decoder GEMM arithmetic (include/dpivae_b200.h DPIVAE_MATH_*): tc_fp16x3 = tcgen05 with the fp16 hi/lo "
+                         "operand split (fp32-accurate, same 1e-5 parity bar as the FFMA kernel), fp32 = CUDA-core FFMA, "
+                         "tc_fp16 = tcgen05 with plain fp16 operands (reduced precision, reported separately)")
+    ap.add_argument("--no-other-modes", action="store_true", help="skip the short runs of the other math modes")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     wl = dict(WORKLOADS[a.workload])
@@ -261,18 +270,18 @@ def main():
     l0 = eng.launches
     with ClockSampler(local_rank) as clk:
         ms_total = timed(step_resident, a.steps, step_no)
-    launches = eng.launches - l0
-    step_no += a.steps
-    ms_step = ms_total / a.steps
-    value = B_global / (ms_step * 1e-3)
+        launches = eng.launches - l0
+        step_no += a.steps
+        ms_step = ms_total / a.steps
+        value = B_global / (ms_step * 1e-3)
 
-    # end-to-end arm: host buffers in, loss scalars out, every step
-    for i in range(2):
-        step_e2e(step_no)
-        step_no += 1
-    ms_e2e = timed(step_e2e, a.steps, step_no) / a.steps
-    step_no += a.steps
-    e2e_val = B_global / (ms_e2e * 1e-3)
+        # end-to-end arm: host buffers in, loss scalars out, every step
+        for i in range(2):
+            step_e2e(step_no)
+            step_no += 1
+        ms_e2e = timed(step_e2e, a.steps, step_no) / a.steps
+        step_no += a.steps
+        e2e_val = B_global / (ms_e2e * 1e-3)
 
     # per-kernel durations of the dominant kernel, CUDA events on the launching stream
     eng.set_timing(True)
@@ -285,6 +294,23 @@ def main():
     dec_ms = statistics.mean(k["dec_fused"] for k in kms)
     kshare = {k: statistics.mean(v[k] for v in kms) for k in kms[0]}
     loss_now = float(eng.scalars[0])
+    used_tc = eng.used_tensor_cores()
+
+    # the other arithmetic modes of the same step, short runs (reported beside the headline, never as it)
+    modes = {}
+    if not a.no_other_modes:
+        for m in ("fp32", "tc_fp16x3", "tc_fp16"):
+            if m == a.math:
+                continue
+            eng.set_math_mode(m)
+            for i in range(3):
+                step_resident(step_no)
+                step_no += 1
+            k = max(3, min(a.steps, 10))
+            ms_m = timed(step_resident, k, step_no) / k
+            step_no += k
+            modes[m] = {"value": B_global / (ms_m * 1e-3), "ms_per_step": ms_m, "tensor_cores": eng.used_tensor_cores()}
+        eng.set_math_mode(a.math)
 
     if rank == 0:
         peaks = {}
@@ -298,14 +324,14 @@ def main():
         achieved = wl["flop_dec"] * rows / (dec_ms * 1e-3) / 1e12
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "dec_traffic.json"))).get(a.workload)
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "dec_traffic.json"))).get(f"{a.workload}:{a.math}", {}).get("total")
         except Exception:
             pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": a.workload, "case": wl["case"], "preset": wl["preset"], "rows_per_gpu": rows,
+            "config": {"workload": a.workload, "math": MATH_DOC[a.math], "case": wl["case"], "preset": wl["preset"], "rows_per_gpu": rows,
                        "global_batch": B_global, "n_mc": n, "parallelism": f"dp{n_gpus}",
                        "minibatch_order": "identity (loss is a row sum; the reference's CPU multinomial draw is hoisted)",
                        "l2": "per-step working set (inputs + activations workspace) ~0.3 GB > 126 MB L2, no flush",
@@ -313,7 +339,9 @@ def main():
             "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(rows * (vae.nd_x + vae.nd_c + vae.nd_y) * 4), "d2h_bytes_per_step": 32},
             "gpu_launches": launches,
-            "roofline": {"bound": "tensor", "kernel": "dec_kernel (fused decoders fwd+bwd, fp32 FFMA)",
+            "roofline": {"bound": "tensor",
+                         "kernel": ("dec_tc_kernel (fused decoders fwd+bwd, tcgen05 kind::f16, TMEM accumulators)" if used_tc
+                                    else "dec_kernel (fused decoders fwd+bwd, fp32 FFMA)"),
                          "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
                          "peak_source": peak_src, "traffic": traffic,
                          "algorithmic_flop_per_launch": wl["flop_dec"] * rows, "launch_ms": dec_ms,
@@ -321,7 +349,7 @@ def main():
                          "hbm_gbs_achieved": wl["bytes_row"] * rows / (ms_step * 1e-3) / 1e9,
                          "kernel_ms": kshare},
             "clocks": clk.summary(),
-            "elbo": loss_now, "math": a.math, "tensor_cores": eng.used_tensor_cores(),
+            "elbo": loss_now, "math": a.math, "tensor_cores": used_tc, "other_modes": modes,
         }
         if not a.no_cpu_baseline and n_gpus == 1:
             val, sec, threads, crow = cpu_oracle_throughput(wl, 3, 1)

@@ -114,6 +114,9 @@ def train_model(args, vae, definition, data_train, data_val, path_metrics=None, 
     x_train, c_train, y_train = (t.to(eng.dev, torch.float32).contiguous() for t in data_train[:3])
     x_val, c_val, y_val = (t.to(eng.dev, torch.float32).contiguous() for t in data_val[:3])
     eng.set_groups(param_groups(args))
+    # decoder GEMM arithmetic (not a reference flag): fp32-accurate tensor-core split by default, `args.math_mode`
+    # = "fp32" selects the CUDA-core FFMA kernels, "tc_fp16" the reduced-precision tensor-core mode
+    eng.set_math_mode(getattr(args, "math_mode", "tc_fp16x3"))
     try:
         for param in vae.decoder_x.model.parameters():
             param.requires_grad = False
