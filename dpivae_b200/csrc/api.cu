@@ -52,8 +52,8 @@ struct dpivae_model {
   int tc_ok = 0;            // model shape supported by dec_tc_kernel
   int last_dec_tc = 0;      // the last hot-path call ran the tensor-core decoder kernel
   int timing = 0;
-  cudaEvent_t ev[10] = {};   // start/stop pairs: enc_fwd, dec, enc_bwd, reduce, adam
-  int ev_used[5] = {0, 0, 0, 0, 0};
+  cudaEvent_t ev[14] = {};   // start/stop pairs: enc_fwd, dec, enc_bwd, reduce, adam, lat_fwd, lat_bwd
+  int ev_used[7] = {0, 0, 0, 0, 0, 0, 0};
 };
 
 struct KTimer {
@@ -285,19 +285,16 @@ static int build_plan(dpivae_model* h) {
       }
       plane2(16, 128, T.a_big, T.l_big);
       plane2(8, 128, T.a_g, T.l_g);
-      plane2(KZ / 8, 128, T.a_lat, T.l_lat);
       plane2(2, 128, T.a_oa, T.l_oa);      // aux head gradients: 8 columns used, columns 8..15 stay zero (N = 16)
+      T.rec_buf = 8192 + (d.nd_c + d.nd_y) * 512;   // tile record: latent operand hi/lo planes + raw c|y per pair
+      T.a_rec = b; b += 2 * T.rec_buf;
       auto f32 = [&](int floats) { int off = b; b += ((floats + 3) & ~3) * 4; return off; };
       T.f_inv = f32(16); T.f_bias_x = f32(64); T.f_bias_p1 = f32(32); T.f_bias_p2 = f32(64);
       T.f_aw0 = f32(2 * 64 * 4); T.f_ab0 = f32(2 * 64); T.f_aw1 = f32(2 * 64 * 4); T.f_ab1 = f32(8);
-      T.f_eps = f32(Z * 128); T.f_u = f32(d.nz_x * 128); T.f_zxin = f32(nzin * 128); T.f_zd = f32(nzd * 128);
-      T.f_dza = f32(nzd * 128); T.f_dzx = f32(d.nz_x * 128); T.f_sc = f32(8 * 128);
-      T.f_rowpar = f32(P.n_rowpar * RBMAX); T.f_rowraw = f32((d.nd_c + d.nd_y) * RBMAX); T.f_rowlog = f32(5 * RBMAX);
-      T.f_red = f32(256);
-      T.o_bar = b; b += 32;
+      T.f_dza = f32(nzd * 128); T.f_sc = f32(8 * 128); T.f_red = f32(256);
+      T.o_bar = b; b += 64;
       T.total = (b + 127) & ~127;
-      const int feat_bytes = (P.n_feat * 128 + (P.n_feat + 5) * RBMAX) * 4;
-      if (T.total <= 232448 && feat_bytes <= 2 * T.l_big && 256 * 33 * 4 <= 2 * T.l_big) h->tc_ok = 1;
+      if (T.total <= 232448 && 256 * 33 * 4 <= 2 * T.l_big && lat_smem_bytes(P, true) <= 160 * 1024) h->tc_ok = 1;
     }
   }
   return 0;
@@ -322,7 +319,7 @@ int dpivae_create(const dpivae_model_desc_t* desc, dpivae_handle_t* out) {
   h->d = *desc;
   h->sm_count = prop.multiProcessorCount;
   if (build_plan(h)) { delete h; return 1; }
-  if (configure_dec_kernel() || configure_enc_kernels() || configure_dec_tc_kernel()) { delete h; return fail("cudaFuncSetAttribute(max dynamic smem) failed"); }
+  if (configure_dec_kernel() || configure_enc_kernels() || configure_dec_tc_kernel() || configure_lat_kernels()) { delete h; return fail("cudaFuncSetAttribute(max dynamic smem) failed"); }
   // owner map: which kernel's partials hold each parameter's gradient
   std::vector<unsigned char> owner((size_t)desc->n_params, 0);
   for (int u = 0; u < h->enc.n_units; ++u) {
@@ -346,7 +343,7 @@ int dpivae_create(const dpivae_model_desc_t* desc, dpivae_handle_t* out) {
 int dpivae_destroy(dpivae_handle_t h) {
   if (!h) return 0;
   cudaFree(h->d_frozen); cudaFree(h->d_owner); cudaFree(h->d_group); cudaFree(h->d_clip);
-  for (int i = 0; i < 10; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  for (int i = 0; i < 14; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   delete h;
   return 0;
 }
@@ -396,7 +393,7 @@ int dpivae_set_groups(dpivae_handle_t h, int32_t n_groups, const int64_t* begin,
 }
 
 struct WsLayout {
-  size_t hid, headpre, gpre, rowloss, part, scal, total;
+  size_t hid, headpre, gpre, rowloss, part, scal, rec, dzrec, epsbuf, rowkl, total;
   int grid_enc, grid_dec, RB, n_chunks;
   long long n_rowblocks;
   int tc_RB, tc_grid;           // tensor-core decoder kernel: rows per 128-pair tile, CTAs
@@ -411,6 +408,11 @@ static WsLayout ws_layout(dpivae_handle_t h, int64_t B, int32_t n_mc) {
   L.headpre = take((size_t)h->O_tot * B);
   L.gpre = take((size_t)h->O_tot * B);
   L.rowloss = take((size_t)6 * B);
+  L.tc_RB = 128 / (n_mc < 1 ? 1 : (n_mc > 128 ? 128 : n_mc));
+  if (L.tc_RB < 1) L.tc_RB = 1;
+  L.tc_rowblocks = (B + L.tc_RB - 1) / L.tc_RB;
+  L.tc_grid = (int)(L.tc_rowblocks < h->sm_count ? L.tc_rowblocks : h->sm_count);
+  if (L.tc_grid < 1) L.tc_grid = 1;
   const long long ntiles = (B + TILE - 1) / TILE;
   L.grid_enc = (int)(ntiles < h->sm_count ? ntiles : h->sm_count);
   int RB = TILE / (n_mc < 1 ? 1 : n_mc);
@@ -421,13 +423,18 @@ static WsLayout ws_layout(dpivae_handle_t h, int64_t B, int32_t n_mc) {
   L.grid_dec = (int)(L.n_rowblocks < h->sm_count ? L.n_rowblocks : h->sm_count);
   if (L.grid_enc < 1) L.grid_enc = 1;
   if (L.grid_dec < 1) L.grid_dec = 1;
-  L.tc_RB = 128 / (n_mc < 1 ? 1 : (n_mc > 128 ? 128 : n_mc));
-  if (L.tc_RB < 1) L.tc_RB = 1;
-  L.tc_rowblocks = (B + L.tc_RB - 1) / L.tc_RB;
-  L.tc_grid = (int)(L.tc_rowblocks < h->sm_count ? L.tc_rowblocks : h->sm_count);
-  if (L.tc_grid < 1) L.tc_grid = 1;
+
   L.part = take((size_t)(2 * h->sm_count) * h->part_stride);
   L.scal = take(16);
+  L.rec = L.dzrec = L.epsbuf = L.rowkl = 0;
+  if (h->tc_ok && n_mc >= 8 && n_mc <= 128) {
+    const size_t nt = (size_t)L.tc_rowblocks;
+    const int Z = h->d.nz_x + h->d.nz_c + h->d.nz_y;
+    L.rec = take(nt * (size_t)h->tc.rec_buf / 4);
+    L.dzrec = take(nt * (size_t)Z * 128);
+    L.epsbuf = take(nt * (size_t)Z * 128);
+    L.rowkl = take((size_t)B);
+  }
   L.total = o;
   return L;
 }
@@ -480,6 +487,7 @@ static int run_loss(dpivae_handle_t h, const dpivae_batch_t* bt, const dpivae_rn
   if (latent_only) E.n_units = h->n_enc_units;  // prior nets not needed for encode
   const size_t enc_smem = enc_smem_bytes(h->enc, true);
   for (int k = 0; k < 4; ++k) h->ev_used[k] = 0;
+  h->ev_used[5] = h->ev_used[6] = 0;
   { KTimer t(h, 0, st); launch_enc_fwd(E, L.grid_enc, enc_smem, st); }
   ++launches;
 
@@ -507,10 +515,17 @@ static int run_loss(dpivae_handle_t h, const dpivae_batch_t* bt, const dpivae_rn
   if (use_tc) {
     TcParams T = h->tc;
     D.RB = L.tc_RB; D.n_chunks = 1; D.n_rowblocks = L.tc_rowblocks;
+    D.rec = (unsigned char*)(base + L.rec); D.rec_stride = h->tc.rec_buf;
+    D.dzrec = (float*)(base + L.dzrec); D.epsbuf = (float*)(base + L.epsbuf); D.rowkl = (float*)(base + L.rowkl);
+    { KTimer t(h, 5, st); launch_lat_fwd(D, L.tc_rowblocks, st); }
+    ++launches;
     T.d = D;
     T.terms = h->math_mode == DPIVAE_MATH_TC_FP16X3 ? 3 : 1;
-    KTimer t(h, 1, st);
-    launch_dec_tc(T, grid_dec, st);
+    { KTimer t(h, 1, st); launch_dec_tc(T, grid_dec, st); }
+    if (with_grad) {
+      { KTimer t(h, 6, st); launch_lat_bwd(D, L.tc_rowblocks, st); }
+      ++launches;
+    }
   } else {
     KTimer t(h, 1, st);
     launch_dec(D, grid_dec, st);
@@ -635,14 +650,14 @@ int dpivae_set_phase_buffer(dpivae_handle_t h, void* dev_counters16) {
 int dpivae_set_timing(dpivae_handle_t h, int32_t enable) {
   if (!h) return fail("null handle");
   if (enable && !h->ev[0])
-    for (int i = 0; i < 10; ++i) CUDA_OK(cudaEventCreate(&h->ev[i]));
+    for (int i = 0; i < 14; ++i) CUDA_OK(cudaEventCreate(&h->ev[i]));
   h->timing = enable ? 1 : 0;
   return 0;
 }
 
 int dpivae_last_kernel_ms(dpivae_handle_t h, float* out5) {
   if (!h || !out5) return fail("null argument");
-  for (int k = 0; k < 5; ++k) {
+  for (int k = 0; k < 7; ++k) {
     out5[k] = 0.0f;
     if (h->ev[0] && h->ev_used[k]) {
       CUDA_OK(cudaEventSynchronize(h->ev[2 * k + 1]));

@@ -85,13 +85,21 @@ __device__ __forceinline__ float tanh_fast(float x) {
   return 1.0f - __fdividef(2.0f, 1.0f + e);
 }
 
+// element (row p, column k) of the latent operand record: hi + lo fp16 planes, undoing the 2^4 operand scale
+__device__ __forceinline__ float lat_elem(const unsigned char* rec, int k, int p) {
+  const size_t off = ((size_t)(k >> 3) * TP + p) * 16 + (size_t)(k & 7) * 2;
+  const float h = __half2float(*reinterpret_cast<const __half*>(rec + off));
+  const float l = __half2float(*reinterpret_cast<const __half*>(rec + 4096 + off));
+  return (h + l) * 0.0625f;
+}
+
 template <int W>
 __device__ __forceinline__ void tld(uint32_t taddr, float* v) {
   if (W == 32) tc::tmem_ld32(taddr, v);
   else tc::tmem_ld16(taddr, v);
 }
 
-__device__ __forceinline__ tc::Op mkop(unsigned char* sm, int off, uint32_t lo_off, int R, int col0 = 0) {
+__device__ __forceinline__ tc::Op mkop(const unsigned char* sm, int off, uint32_t lo_off, int R, int col0 = 0) {
   tc::Op o;
   o.base = tc::smem_u32(sm + off) + (uint32_t)((col0 >> 3) * R) * 16u;
   o.lo_off = lo_off;
@@ -196,19 +204,12 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
   float* AB0 = smf + (T.f_ab0 >> 2);      //                   [side][64]
   float* AW1 = smf + (T.f_aw1 >> 2);      // aux heads, transposed [side][64][4]: mean_0, mean_1, ls_0, ls_1 per hidden unit
   float* AB1 = smf + (T.f_ab1 >> 2);      //                   [side][4]
-  float* EPS = smf + (T.f_eps >> 2);
-  float* U = smf + (T.f_u >> 2);
-  float* ZXIN = smf + (T.f_zxin >> 2);
-  float* ZD = smf + (T.f_zd >> 2);
   float* DZA = smf + (T.f_dza >> 2);
-  float* DZX = smf + (T.f_dzx >> 2);
   float* SC = smf + (T.f_sc >> 2);
-  float* ROWPAR = smf + (T.f_rowpar >> 2);
-  float* ROWRAW = smf + (T.f_rowraw >> 2);
-  float* ROWLOG = smf + (T.f_rowlog >> 2);  // [n_blk + 2][RBMAX]: sum log diag L per block, sum log sigma of each prior
   float* RED = smf + (T.f_red >> 2);
-  float* FEAT = smf + (T.a_big >> 2);  // aliases the BIG operand buffer (dead by then)
-  float* ROWACC = FEAT + P.n_feat * TP;
+  float* R0 = smf + (T.a_big >> 2);      // end-of-kernel reduction scratch, aliases the BIG operand buffer
+  unsigned char* RECB = smb + T.a_rec;   // two tile-record buffers (bulk-copied from the latent kernel's output)
+  uint64_t* rbar = reinterpret_cast<uint64_t*>(smb + T.o_bar + 32);  // [2] record-arrival barriers
   uint64_t* bar0 = reinterpret_cast<uint64_t*>(smb + T.o_bar);
   uint64_t* bar1 = bar0 + 1;
   uint32_t* tptr = reinterpret_cast<uint32_t*>(smb + T.o_bar + 16);
@@ -219,6 +220,8 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
   if (tid == 0) {
     tc::mbar_init(bar0, 1);
     tc::mbar_init(bar1, 1);
+    tc::mbar_init(rbar, 1);
+    tc::mbar_init(rbar + 1, 1);
     tc::mbar_fence_init();
   }
   __syncwarp();
@@ -240,11 +243,15 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
   auto g_p2 = [&](int nn, int k) -> float { return P.frozen[P.pl[2].g_w + (long long)nn * d2 + k]; };
   auto g_p3 = [&](int nn, int k) -> float { return P.frozen[P.pl[3].g_w + (long long)nn * d3 + k]; };
 
+  auto bias_p3 = [&](int e) -> float {
+    if constexpr (mlp) return P.frozen[P.pl[3].g_b + e];
+    else return 0.0f;
+  };
   const int KZ = T.KZ;
   const int k_fx0 = scale_exp(block_absmax(128 * KZ, [&](int e) { return g_fx0(e / KZ, e % KZ); }, RED));
   int k_x = scale_exp(block_absmax(ndx * 128, [&](int e) { return g_fx1(e >> 7, e & 127); }, RED));
   int k_p0 = 0, k_p1 = 0, k_p2 = 0;
-  if (mlp) {
+  if constexpr (mlp) {
     k_p0 = scale_exp(block_absmax(d1 * KZ, [&](int e) { return g_p0(e / KZ, e % KZ); }, RED));
     k_p1 = scale_exp(block_absmax(d2 * d1, [&](int e) { return g_p1(e / d1, e % d1); }, RED));
     k_p2 = scale_exp(block_absmax(d3 * d2, [&](int e) { return g_p2(e / d2, e % d2); }, RED));
@@ -253,14 +260,14 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
   }
   stage_weight(smb + T.w_fx0, T.l_fx0, 128, KZ, k_fx0, g_fx0);
   stage_weight(smb + T.w_fx1, T.l_fx1, ndx, 128, k_x, g_fx1);
-  if (mlp) {
+  if constexpr (mlp) {
     stage_weight(smb + T.w_p[0], T.l_p[0], d1, KZ, k_p0, g_p0);
     stage_weight(smb + T.w_p[1], T.l_p[1], d2, d1, k_p1, g_p1);
     stage_weight(smb + T.w_p[2], T.l_p[2], d3, d2, k_p2, g_p2);
     stage_weight(smb + T.w_p[3], T.l_p[3], ndx, d3, k_x, g_p3);
   }
-  for (int e = tid; e < ndx; e += TNT) BX[e] = prm[P.fx.g_b1 + e] + (mlp ? P.frozen[P.pl[3].g_b + e] : 0.0f);
-  if (mlp) {
+  for (int e = tid; e < ndx; e += TNT) BX[e] = prm[P.fx.g_b1 + e] + bias_p3(e);
+  if constexpr (mlp) {
     for (int e = tid; e < d2; e += TNT) BP1[e] = P.frozen[P.pl[1].g_b + e];
     for (int e = tid; e < d3; e += TNT) BP2[e] = P.frozen[P.pl[2].g_b + e];
   }
@@ -308,12 +315,10 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
   const float wpair = 1.0f / ((float)P.Bg * (float)(P.nd_x + P.nd_c + P.nd_y) * (float)n);
   const float cx = -(P.alpha_x * wpair) / var_x / sg;  // true dL/dxh = cx * g~
   const float awc = P.alpha_c * wpair, awy = P.alpha_y * wpair;
-  const int n_acc = P.n_feat + 5;
   const float s_lat = exp2f((float)E_LAT), s_h = exp2f((float)E_H), s_t = exp2f((float)E_T);
   const int RB = P.RB;
 
   // operands
-  const tc::Op oLAT = mkop(smb, T.a_lat, T.l_lat, TP);
   const tc::Op oBIG = mkop(smb, T.a_big, T.l_big, TP);
   const tc::Op oG = mkop(smb, T.a_g, T.l_g, TP);
   const tc::Op oOA = mkop(smb, T.a_oa, T.l_oa, TP);
@@ -322,7 +327,6 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
   const tc::Op oWP2 = mkop(smb, T.w_p[2], T.l_p[2], d3 ? d3 : 16), oWP3 = mkop(smb, T.w_p[3], T.l_p[3], ndx);
   unsigned char* pBIG = smb + T.a_big;
   unsigned char* pG = smb + T.a_g;
-  unsigned char* pLAT = smb + T.a_lat;
   unsigned char* pOA = smb + T.a_oa;
 
   // aux side of this thread
@@ -345,173 +349,35 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
   long long t_last = (PROF && tid == 0) ? clock64() : 0;
   TPHASE(TPH_SETUP);
 
-  for (long long rb = blockIdx.x; rb < P.n_rowblocks; rb += gridDim.x) {
+  const uint32_t rec_bytes = (uint32_t)P.rec_stride;
+  if (tid == 0 && (long long)blockIdx.x < P.n_rowblocks) {
+    tc::mbar_expect_tx(rbar, rec_bytes);
+    tc::bulk_g2s(RECB, P.rec + (long long)blockIdx.x * P.rec_stride, rec_bytes, rbar);
+  }
+  int it = 0;
+  for (long long rb = blockIdx.x; rb < P.n_rowblocks; rb += gridDim.x, ++it) {
     const long long row0 = rb * RB;
     const int nrows = (int)min((long long)RB, B - row0);
     const int npairs = nrows * n;
-
-    // ---- per-row parameters of q(z|x) and of the conditional priors -------------------------------
-    for (int e = tid; e < RB * P.Z; e += TNT) {
-      const int i = e / RB, r = e - i * RB;
-      const long long lrow = row0 + min(r, nrows - 1);
-      const int b = block_of_tc(P, i), il = i - P.blk_start[b];
-      const float pm = P.headpre[(long long)(P.henc[b] + il) * B + lrow];
-      ROWPAR[(P.rp_loc + i) * RBMAX + r] = clampf_(pm, -50.0f, 50.0f);
+    const int buf = it & 1;
+    unsigned char* rec = RECB + (size_t)buf * T.rec_buf;
+    // prefetch the next tile's record into the other buffer (its previous tile is fully consumed: every MMA that read
+    // it was waited for and all threads passed the end-of-tile barrier)
+    if (tid == 0 && rb + gridDim.x < P.n_rowblocks) {
+      tc::fence_async_smem();
+      tc::mbar_expect_tx(rbar + (buf ^ 1), rec_bytes);
+      tc::bulk_g2s(RECB + (size_t)(buf ^ 1) * T.rec_buf, P.rec + (rb + gridDim.x) * P.rec_stride, rec_bytes, rbar + (buf ^ 1));
     }
-    for (int e = tid; e < RB * P.nL; e += TNT) {
-      const int li = e / RB, r = e - li * RB;
-      const long long lrow = row0 + min(r, nrows - 1);
-      const int b = P.L_blk[li], i = P.L_i[li], j = P.L_j[li], nzb = P.blk_size[b];
-      float v;
-      if (i == j) {
-        const float ps = P.headpre[(long long)(P.henc[b] + nzb + i) * B + lrow];
-        v = expf(clampf_(ps, -7.0f, 3.0f)) + 1e-8f;
-      } else {
-        const float pc = P.headpre[(long long)(P.henc[b] + 2 * nzb + i * nzb + j) * B + lrow];
-        v = clampf_(pc, -20.0f, 20.0f);
-      }
-      ROWPAR[(P.rp_L + li) * RBMAX + r] = v;
-    }
-    for (int e = tid; e < RB * nzd; e += TNT) {
-      const int k = e / RB, r = e - k * RB;
-      const long long lrow = row0 + min(r, nrows - 1);
-      const int which = k < P.nz_c ? 0 : 1;
-      const int kk = which ? k - P.nz_c : k, nzk = which ? P.nz_y : P.nz_c;
-      float mu = 0.0f, sgm = 1.0f;
-      if (which == 0 || P.y != nullptr) {
-        const float pm = P.headpre[(long long)(P.hpri[which] + kk) * B + lrow];
-        const float ps = P.headpre[(long long)(P.hpri[which] + nzk + kk) * B + lrow];
-        mu = clampf_(pm, -50.0f, 50.0f);
-        sgm = expf(clampf_(ps, -7.0f, 3.0f)) + 1e-8f;
-      }
-      ROWPAR[(P.rp_pmu + k) * RBMAX + r] = mu;
-      ROWPAR[(P.rp_psig + k) * RBMAX + r] = sgm;
-    }
-    for (int e = tid; e < RB * (P.nd_c + P.nd_y); e += TNT) {
-      const int j = e / RB, r = e - j * RB;
-      const long long lrow = row0 + min(r, nrows - 1);
-      const long long drow = P.idx ? P.idx[lrow] : lrow;
-      float v = 0.0f;
-      if (j < P.nd_c) v = P.c[drow * P.nd_c + j];
-      else if (P.y != nullptr) v = P.y[drow * P.nd_y + (j - P.nd_c)];
-      ROWRAW[j * RBMAX + r] = v;
-    }
-    // ---- reparameterisation noise ----------------------------------------------------------------------
-    for (int e = tid; e < TP * P.Z; e += TNT) {
-      const int pp = e & (TP - 1), i = e >> 7;
-      float v = 0.0f;
-      if (pp < npairs) {
-        const int r = pp / n, m = pp - r * n;
-        const unsigned long long grow = (unsigned long long)(P.row_off + row0 + r);
-        const int b = block_of_tc(P, i), il = i - P.blk_start[b], nzb = P.blk_size[b];
-        const unsigned long long li = ((unsigned long long)m * (unsigned long long)P.Bg + grow) * nzb + il;
-        v = P.rng.mode == 0 ? P.rng.eps[b][li] : philox_normal_tc(P.rng.seed, P.rng.offset[b], P.rng.grid_threads[b], li);
-      }
-      EPS[i * TP + pp] = v;
-    }
-    __syncthreads();
-    // per-row log-determinant terms (once per row instead of once per pair)
-    for (int e = tid; e < RB * (P.n_blk + 2); e += TNT) {
-      const int t = e / RB, r = e - t * RB;
-      float s = 0.0f;
-      if (t < P.n_blk) {
-        for (int i = 0; i < P.blk_size[t]; ++i) s += logf(ROWPAR[(P.rp_L + P.blk_loff[t] + i * (i + 1) / 2 + i) * RBMAX + r]);
-      } else {
-        const int k0 = t == P.n_blk ? 0 : P.nz_c, k1 = t == P.n_blk ? P.nz_c : nzd;
-        for (int k = k0; k < k1; ++k) s += logf(ROWPAR[(P.rp_psig + k) * RBMAX + r]);
-      }
-      ROWLOG[t * RBMAX + r] = s;
-    }
-    __syncthreads();
-    TPHASE(TPH_ROWPAR_EPS);
-
-    // ---- latents: z = loc + L eps, bijector, log q, log priors.  Both threads of a pair work: thread hh takes the
-    //      latent blocks b with (b & 1) == hh of the P model (x and y | c); the single block of the S model is hh = 0's
+    tc::mbar_wait(rbar + buf, (uint32_t)(it >> 1) & 1u);
+    __syncwarp();
+    const tc::Op oLAT = mkop(rec, 0, 4096u, TP);   // latent operand [zd | 1 | physics input] as written by lat_fwd_kernel
+    const float* RAW = reinterpret_cast<const float*>(rec + 8192);
     const bool pvalid = p < npairs;
     const int prow = (pvalid ? p : npairs - 1) / n;
-    const int pm_ = (pvalid ? p : npairs - 1) - prow * n;
-    float lq_part = 0.0f;   // this thread's share of log q (minus bijector log-det) - log p(zx)
-    {
-      float ld1 = 0.0f, ld2 = 0.0f, lpx = 0.0f;
-      for (int b = hh; b < P.n_blk; b += 2) {
-        const int s = P.blk_start[b], nzb = P.blk_size[b];
-        float ss = 0.0f;
-        for (int i = 0; i < nzb; ++i) {
-          float acc = ROWPAR[(P.rp_loc + s + i) * RBMAX + prow];
-          const int base = P.rp_L + P.blk_loff[b] + i * (i + 1) / 2;
-          for (int j = 0; j <= i; ++j) acc = fmaf(ROWPAR[(base + j) * RBMAX + prow], EPS[(s + j) * TP + p], acc);
-          const float e = EPS[(s + i) * TP + p];
-          ss = fmaf(e, e, ss);
-          const int gi = s + i;
-          if (gi < P.nz_x) {
-            const float u = sigmoidf_(acc);
-            const float a = P.ub[gi] - P.lb[gi];
-            const float zx = fmaf(u, a, P.lb[gi]);
-            ld1 += acc - 2.0f * softplusf_(acc);
-            ld2 += logf(fabsf(a));
-            U[gi * TP + p] = u;
-            ZXIN[gi * TP + p] = zx;
-            if (P.prior_kind[gi] == 0) {
-              const bool inside = (zx >= P.prior_a[gi]) && (zx < P.prior_b[gi]);
-              lpx += (inside ? 0.0f : -INFINITY) - logf(P.prior_b[gi] - P.prior_a[gi]);
-            } else {
-              const float d = zx - P.prior_a[gi];
-              lpx += -(d * d) / (2.0f * P.prior_b[gi] * P.prior_b[gi]) - logf(P.prior_b[gi]) - LOG_SQRT_2PI;
-            }
-          } else {
-            ZD[(gi - P.nz_x) * TP + p] = acc;
-          }
-        }
-        lq_part += -0.5f * ((float)nzb * LOG_2PI + ss) - ROWLOG[b * RBMAX + prow];
-      }
-      if (hh == 0) {
-        for (int j = 0; j < P.nd_p; ++j) ZXIN[(P.nz_x + j) * TP + p] = ROWRAW[P.idx_c_phys[j] * RBMAX + prow];
-      }
-      SC[(S_Q0 + hh) * TP + p] = lq_part - (ld1 + ld2);  // dens share (log q minus bijector log-det)
-      lq_part = lq_part - (ld1 + ld2) - lpx;
-    }
-    __syncthreads();
-    {
-      // conditional prior of side hh: p(zc|c) (hh = 0) or p(zy|y) (hh = 1), diagonal Gaussian
-      float mh = 0.0f;
-      for (int k = a_j0; k < a_j0 + a_nz; ++k) {
-        const float t = (ZD[k * TP + p] - ROWPAR[(P.rp_pmu + k) * RBMAX + prow]) / ROWPAR[(P.rp_psig + k) * RBMAX + prow];
-        mh = fmaf(t, t, mh);
-      }
-      const float lp = -0.5f * ((float)a_nz * LOG_2PI + mh) - ROWLOG[(P.n_blk + hh) * RBMAX + prow];
-      SC[(hh ? S_KL2 : S_KL) * TP + p] = pvalid ? lq_part - lp : 0.0f;
-      if (hh == 0) {
-        SC[S_W * TP + p] = pvalid ? wpair : 0.0f;
-        if (pvalid && (P.out.dens || P.out.zx || P.out.zc || P.out.zy)) {
-          const long long o = (long long)pm_ * B + row0 + prow;
-          if (P.out.dens) P.out.dens[o] = SC[S_Q0 * TP + p] + SC[S_Q1 * TP + p];
-          if (P.out.zx) for (int k = 0; k < P.nz_x; ++k) P.out.zx[o * P.nz_x + k] = ZXIN[k * TP + p];
-          if (P.out.zc) for (int k = 0; k < P.nz_c; ++k) P.out.zc[o * P.nz_c + k] = ZD[k * TP + p];
-          if (P.out.zy) for (int k = 0; k < P.nz_y; ++k) P.out.zy[o * P.nz_y + k] = ZD[(P.nz_c + k) * TP + p];
-        }
-      }
-      // latent operand row, chunk hh: [zd | 1 | standardised physics input | 0], scaled by 2^E_LAT
-      float v[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int k = 8 * hh + i;
-        float x = 0.0f;
-        if (k < nzd) x = pvalid ? ZD[k * TP + p] : 0.0f;
-        else if (k == c1) x = 1.0f;
-        else if (mlp && k >= cs0 && k < cs0 + nzin)
-          x = pvalid ? (ZXIN[(k - cs0) * TP + p] - P.phys_in_mean[k - cs0]) / P.phys_in_std[k - cs0] : 0.0f;
-        v[i] = x * s_lat;
-      }
-      put8(pLAT, T.l_lat, TP, hh, p, v);
-    }
-    if (P.latent_only) {
-      __syncthreads();
-      continue;
-    }
     // ---- first layers of the data-driven decoder and of the physics surrogate: issued now, consumed later ----
     stage_issue(bar0, [&] {
       tc::issue_fwd(tb + C_H, oLAT, oWFX0, 128, KZ, 0, terms);
-      if (mlp) tc::issue_fwd(tb + C_A0, oLAT, oWP0, d1, KZ, 0, terms);
+      if constexpr (mlp) tc::issue_fwd(tb + C_A0, oLAT, oWP0, d1, KZ, 0, terms);
     });
     TPHASE(TPH_LATENT);
 
@@ -521,7 +387,7 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
     // tensor cores, as fire-and-forget MMAs on the operand copies written here.
     float z4[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) z4[j] = (j < a_nz && pvalid) ? ZD[(a_j0 + j) * TP + p] : 0.0f;
+    for (int j = 0; j < 4; ++j) z4[j] = (j < a_nz && pvalid) ? lat_elem(rec, a_j0 + j, p) : 0.0f;
     unsigned long long mkA = 0ull;
     float g4[4] = {0.f, 0.f, 0.f, 0.f};
     {
@@ -551,7 +417,7 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           if (j < a_nd) {
-            const float val = ROWRAW[((hh ? P.nd_c : 0) + j) * RBMAX + prow];
+            const float val = RAW[((hh ? P.nd_c : 0) + j) * TP + p];
             const float es = expf(ol[j]), var = es * es, d = val - om[j];
             R += -(d * d) / (2.0f * var) - ol[j] - LOG_SQRT_2PI;
             if (pvalid) {
@@ -573,7 +439,7 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
 
     // ================= physics layer 0 -> tanh (bias folded into the constant-one column) =====================
     stage_wait(bar0, ph0);
-    if (mlp) {
+    if constexpr (mlp) {
       const float inv = INV[I_P0];
 #pragma unroll 2
       for (int c = 0; c < 4; ++c) {
@@ -618,7 +484,7 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
     }
     TPHASE(TPH_AUX2);
 
-    if (mlp) {
+    if constexpr (mlp) {
       // ================= physics layer 1 -> tanh ===================================================================
       stage_wait(bar0, ph0);
       {
@@ -661,7 +527,7 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
     }
     TPHASE(TPH_HD);
 
-    if (mlp) {
+    if constexpr (mlp) {
       // ================= physics layer 2 -> tanh ===================================================================
       stage_wait(bar0, ph0);
       {
@@ -682,7 +548,7 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
     // x head = data-driven decoder output (+ last physics layer) into the same accumulator
     stage_issue(bar0, [&] {
       tc::issue_fwd(tb + C_X, oBIG, oWFX1, ndx, 128, 0, terms);
-      if (mlp) tc::issue_fwd(tb + C_X, oG, oWP3, ndx, d3, 1, terms);
+      if constexpr (mlp) tc::issue_fwd(tb + C_X, oG, oWP3, ndx, d3, 1, terms);
     });
     TPHASE(TPH_A2);
     stage_wait(bar0, ph0);
@@ -703,19 +569,20 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
       float v[nxh];
       tld<nxh>(trow + C_X + nxh * hh, v);
       const float gsc = pvalid ? sg : 0.0f;
+      const float zx0 = PHYS != 0 ? lat_elem(rec, cs0, p) : 0.0f, zx1 = PHYS == 2 ? lat_elem(rec, cs0 + 1, p) : 0.0f;
 #pragma unroll
       for (int i = 0; i < nxh; ++i) {
         float xh = v[i] * inv + BX[nxh * hh + i];
-        if (PHYS != 0) {
+        if constexpr (PHYS != 0) {
           // closed-form physics (cases/damped_oscillator/mass_spring.py:8-28, cases/simple_beam/simple_beam_model.py:4-30)
           const int d = nxh * hh + i;
-          if (PHYS == 1) {
-            const float om = sqrtf(1.0f / ZXIN[p]);
+          if constexpr (PHYS == 1) {
+            const float om = sqrtf(1.0f / zx0);
             const float bb = 0.0f / om;
             const float ph = om * P.grid[d];
             xh += bb * sinf(ph) + 1.0f * cosf(ph);
           } else {
-            const float E = ZXIN[p] * 1e6f, a = ZXIN[TP + p], b = 1.0f - a, xg = P.grid[d];
+            const float E = zx0 * 1e6f, a = zx1, b = 1.0f - a, xg = P.grid[d];
             const float den1 = 6.0f * E * 2e-6f * 1.0f, den2 = 6.0f * E * 2e-6f;
             float w = 1.0f * b * xg * (1.0f - b * b - xg * xg) / den1;
             if (xg > a) {
@@ -741,7 +608,7 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
       stage_issue(bar0, [&] {
         tc::issue_wgrad(tb + C_W1, oBIG, oG, ndx, wacc, terms);
         tc::issue_dgrad(tb + C_H, oG, oWFX1, ndx, 128, 0, terms);
-        if (mlp) tc::issue_dgrad(tb + C_X, oG, oWP3, ndx, d3, 0, terms);
+        if constexpr (mlp) tc::issue_dgrad(tb + C_X, oG, oWP3, ndx, d3, 0, terms);
       });
     } else {
       __syncthreads();
@@ -756,7 +623,7 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
 
     if (P.with_grad) {
       stage_wait(bar0, ph0);
-      if (mlp) {
+      if constexpr (mlp) {
         // d tanh of physics layer 2 (operand for the next dgrad), then let that dgrad run under the ReLU-mask epilogue
         const float inv = INV[I_XD];
 #pragma unroll 2
@@ -783,7 +650,7 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
         }
       }
       TPHASE(TPH_BWD1);
-      if (mlp) {
+      if constexpr (mlp) {
         stage_wait(bar1, ph1);
         const float inv = INV[I_P2D];
 #pragma unroll
@@ -797,13 +664,13 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
         }
       }
       stage_issue(bar0, [&] {
-        if (mlp) tc::issue_dgrad(tb + C_X, oG, oWP1, d2, d1, 0, terms);
+        if constexpr (mlp) tc::issue_dgrad(tb + C_X, oG, oWP1, d2, d1, 0, terms);
         tc::issue_wgrad(tb + C_W0, oBIG, oLAT, KZ, wacc, terms);
         tc::issue_dgrad(tb + C_S, oBIG, oWFX0, 128, KZ, 0, terms);
       });
       TPHASE(TPH_BWD2);
       stage_wait(bar0, ph0);
-      if (mlp) {
+      if constexpr (mlp) {
         const float inv = INV[I_P1D];
 #pragma unroll 2
         for (int c = 0; c < 4; ++c) {
@@ -822,12 +689,13 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
         float v[16];
         tc::tmem_ld16(trow + C_S, v);
         const float inv = -P.lambda_g0 * cx * INV[I_FX0D];
+        float* dz = P.dzrec + (long long)rb * (nzd + P.nz_x) * TP;
 #pragma unroll
         for (int k = 0; k < 16; ++k)
-          if (k < nzd) DZA[k * TP + p] = fmaf(v[k], inv, (k < P.nz_c ? awc : awy) * DZA[k * TP + p]);
+          if (k < nzd) dz[k * TP + p] = fmaf(v[k], inv, (k < P.nz_c ? awc : awy) * DZA[k * TP + p]);
       }
       TPHASE(TPH_BWD3);
-      if (mlp) {
+      if constexpr (mlp) {
         stage_wait(bar1, ph1);
         if (hh == 0) {
           float v[16];
@@ -836,7 +704,7 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
 #pragma unroll
           for (int c = 0; c < 16; ++c) {
             const int k = c - cs0;
-            if (k >= 0 && k < P.nz_x) DZX[k * TP + p] = v[c] * inv / P.phys_in_std[k];
+            if (k >= 0 && k < P.nz_x) P.dzrec[((long long)rb * (nzd + P.nz_x) + nzd + k) * TP + p] = v[c] * inv / P.phys_in_std[k];
           }
         }
       } else {
@@ -850,14 +718,14 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
             const __half* hrow = reinterpret_cast<const __half*>(gh + ((size_t)(d >> 3) * TP + p) * 16) + (d & 7);
             const __half* lrow = reinterpret_cast<const __half*>(gh + T.l_g + ((size_t)(d >> 3) * TP + p) * 16) + (d & 7);
             const float g = __half2float(*hrow) + __half2float(*lrow);
-            if (PHYS == 1) {
-              const float mass = ZXIN[p];
+            if constexpr (PHYS == 1) {
+              const float mass = lat_elem(rec, cs0, p);
               const float om = sqrtf(1.0f / mass);
               const float dom = -om / (2.0f * mass);
               const float t = P.grid[d];
               s0 = fmaf(g, -sinf(om * t) * t * dom, s0);
             } else {
-              const float z0 = ZXIN[p], E = z0 * 1e6f, a = ZXIN[TP + p], b = 1.0f - a;
+              const float z0 = lat_elem(rec, cs0, p), E = z0 * 1e6f, a = lat_elem(rec, cs0 + 1, p), b = 1.0f - a;
               const float den = 6.0f * E * 2e-6f;
               const float xg = P.grid[d];
               float w = b * xg * (1.0f - b * b - xg * xg) / den;
@@ -878,145 +746,45 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
         Q2[hh * TP + p] = s1;
         __syncthreads();
         if (tid < TP) {
-          DZX[tid] = (SC[S_Q0 * TP + tid] + SC[S_Q1 * TP + tid]) * cx;
-          if (P.nz_x > 1) DZX[TP + tid] = (Q2[tid] + Q2[TP + tid]) * cx;
+          float* dzx = P.dzrec + ((long long)rb * (nzd + P.nz_x) + nzd) * TP;
+          dzx[tid] = (SC[S_Q0 * TP + tid] + SC[S_Q1 * TP + tid]) * cx;
+          if (P.nz_x > 1) dzx[TP + tid] = (Q2[tid] + Q2[TP + tid]) * cx;
         }
       }
       __syncthreads();
       TPHASE(TPH_BWD4);
 
-      // ---- latent backward: per-pair gradients w.r.t. loc / L / prior parameters ---------------------------
-      {
-        const int pp = tid & (TP - 1), prt = tid >> 7;
-        const int r = (pp < npairs ? pp : npairs - 1) / n;
-        const float bw = P.beta_x * SC[S_W * TP + pp];
-        const float wv = pp < npairs ? 1.0f : 0.0f;
-        for (int k = prt; k < nzd; k += 2) {
-          float g = wv * DZA[k * TP + pp];
-          const float sgm = ROWPAR[(P.rp_psig + k) * RBMAX + r];
-          const float t = (ZD[k * TP + pp] - ROWPAR[(P.rp_pmu + k) * RBMAX + r]) / sgm;
-          g += bw * t / sgm;
-          FEAT[(P.f_pmu + k) * TP + pp] = -bw * t / sgm;
-          FEAT[(P.f_psig + k) * TP + pp] = -bw * (t * t - 1.0f) / sgm;
-          FEAT[(P.f_loc + P.nz_x + k) * TP + pp] = g;
-        }
-        for (int i = prt; i < P.nz_x; i += 2) {
-          float g = wv * DZX[i * TP + pp];
-          if (P.prior_kind[i] == 1) g += bw * (ZXIN[i * TP + pp] - P.prior_a[i]) / (P.prior_b[i] * P.prior_b[i]);
-          const float u = U[i * TP + pp];
-          FEAT[(P.f_loc + i) * TP + pp] = g * (P.ub[i] - P.lb[i]) * u * (1.0f - u) + bw * (2.0f * u - 1.0f);
-        }
-      }
-      __syncthreads();
-      for (int e = tid; e < TP * P.nL; e += TNT) {
-        const int pp = e & (TP - 1), li = e >> 7;
-        const int r = (pp < npairs ? pp : npairs - 1) / n;
-        const int b = P.L_blk[li], i = P.L_i[li], j = P.L_j[li], s = P.blk_start[b];
-        float v = FEAT[(P.f_loc + s + i) * TP + pp] * EPS[(s + j) * TP + pp];
-        if (i == j) v -= P.beta_x * SC[S_W * TP + pp] / ROWPAR[(P.rp_L + li) * RBMAX + r];
-        FEAT[(P.f_L + li) * TP + pp] = v;
-      }
     }
     __syncthreads();
     TPHASE(TPH_LATENT_BWD);
-
-    // ---- reduce the pairs over the MC axis into per-row accumulators ------------------------------------------
-    {
-      const int f0 = P.with_grad ? 0 : P.n_feat;
-      if ((n & 3) == 0) {
-        for (int e = tid + f0 * RBMAX; e < n_acc * RBMAX; e += TNT) {
-          const int f = e / RBMAX, r = e - f * RBMAX;
-          if (r < nrows) {
-            const float4* src = reinterpret_cast<const float4*>((f < P.n_feat ? FEAT + f * TP : SC + (f - P.n_feat) * TP) + r * n);
-            float s = 0.0f;
-            for (int m = 0; m < (n >> 2); ++m) {
-              const float4 t = src[m];
-              s += (t.x + t.y) + (t.z + t.w);
-            }
-            ROWACC[f * RBMAX + r] = s;
-          }
-        }
-      } else {
-        for (int e = tid + f0 * RBMAX; e < n_acc * RBMAX; e += TNT) {
-          const int f = e / RBMAX, r = e - f * RBMAX;
-          if (r < nrows) {
-            const float* src = f < P.n_feat ? FEAT + f * TP : SC + (f - P.n_feat) * TP;
-            float s = 0.0f;
-            for (int m = 0; m < n; ++m) s += src[r * n + m];
-            ROWACC[f * RBMAX + r] = s;
-          }
-        }
-      }
-    }
-    __syncthreads();
-    TPHASE(TPH_ROWRED);
-
-    // ---- per-row outputs -----------------------------------------------------------------------------------
+    // ---- per-row outputs: MC means of the three reconstruction terms + the KL of lat_fwd_kernel ---------------------
     if (tid < nrows) {
       const int r = tid;
+      float rx = 0.0f, rc = 0.0f, ry = 0.0f;
+      for (int m = 0; m < n; ++m) {
+        rx += SC[S_RX * TP + r * n + m];
+        rc += SC[S_RC * TP + r * n + m];
+        ry += SC[S_RY * TP + r * n + m];
+      }
       const float inv_n = 1.0f / (float)n;
-      const float kl = (ROWACC[(P.n_feat + S_KL) * RBMAX + r] + ROWACC[(P.n_feat + S_KL2) * RBMAX + r]) * inv_n;
-      const float rx = ROWACC[(P.n_feat + S_RX) * RBMAX + r] * inv_n;
-      const float rc = ROWACC[(P.n_feat + S_RC) * RBMAX + r] * inv_n;
-      const float ry = ROWACC[(P.n_feat + S_RY) * RBMAX + r] * inv_n;
+      rx *= inv_n; rc *= inv_n; ry *= inv_n;
+      const float kl = P.rowkl[row0 + r];
       const float loss = P.beta_x * kl - P.alpha_x * rx - P.alpha_c * rc - P.alpha_y * ry;
       if (P.out.row_loss) {
         float* o = P.out.row_loss + row0 + r;
         o[0] = loss; o[B] = kl; o[2 * B] = rx; o[3 * B] = rc; o[4 * B] = ry; o[5 * B] = 0.0f;
       }
-      ROWACC[(P.n_feat + S_KL) * RBMAX + r] = kl;
-      ROWACC[(P.n_feat + S_RX) * RBMAX + r] = rx;
-      ROWACC[(P.n_feat + S_RC) * RBMAX + r] = rc;
-      ROWACC[(P.n_feat + S_RY) * RBMAX + r] = ry;
-      SC[S_Q0 * TP + r] = loss;
-    }
-    if (P.with_grad) {
-      for (int e = tid; e < RB * P.Z; e += TNT) {
-        const int i = e / RB, r = e - i * RB;
-        if (r < nrows) {
-          const long long lrow = row0 + r;
-          const int b = block_of_tc(P, i), il = i - P.blk_start[b], nzb = P.blk_size[b];
-          const long long om = (long long)(P.henc[b] + il) * B + lrow;
-          const float pm = P.headpre[om];
-          P.gpre[om] = (pm >= -50.0f && pm <= 50.0f) ? ROWACC[(P.f_loc + i) * RBMAX + r] : 0.0f;
-          for (int j = 0; j < nzb; ++j) {
-            const long long oc = (long long)(P.henc[b] + 2 * nzb + il * nzb + j) * B + lrow;
-            float g = 0.0f;
-            if (j < il) {
-              const float pc = P.headpre[oc];
-              const int li = P.blk_loff[b] + il * (il + 1) / 2 + j;
-              g = (pc >= -20.0f && pc <= 20.0f) ? ROWACC[(P.f_L + li) * RBMAX + r] : 0.0f;
-            }
-            P.gpre[oc] = g;
-          }
-          const long long os = (long long)(P.henc[b] + nzb + il) * B + lrow;
-          const float ps = P.headpre[os];
-          const int ld = P.blk_loff[b] + il * (il + 1) / 2 + il;
-          P.gpre[os] = (ps >= -7.0f && ps <= 3.0f) ? ROWACC[(P.f_L + ld) * RBMAX + r] * expf(ps) : 0.0f;
-        }
-      }
-      for (int e = tid; e < RB * nzd; e += TNT) {
-        const int k = e / RB, r = e - k * RB;
-        if (r < nrows) {
-          const long long lrow = row0 + r;
-          const int which = k < P.nz_c ? 0 : 1;
-          const int kk = which ? k - P.nz_c : k, nzk = which ? P.nz_y : P.nz_c;
-          const long long om = (long long)(P.hpri[which] + kk) * B + lrow;
-          const long long os = (long long)(P.hpri[which] + nzk + kk) * B + lrow;
-          const float pm = P.headpre[om], ps = P.headpre[os];
-          P.gpre[om] = (pm >= -50.0f && pm <= 50.0f) ? ROWACC[(P.f_pmu + k) * RBMAX + r] : 0.0f;
-          P.gpre[os] = (ps >= -7.0f && ps <= 3.0f) ? ROWACC[(P.f_psig + k) * RBMAX + r] * expf(ps) : 0.0f;
-        }
-      }
+      SC[S_Q0 * TP + r] = loss; SC[S_Q1 * TP + r] = kl;
+      SC[S_KL * TP + r] = rx; SC[S_KL2 * TP + r] = rc; SC[S_W * TP + r] = ry;
     }
     __syncthreads();
     if (tid == 0) {
       for (int r = 0; r < nrows; ++r) {
         tot[0] += SC[S_Q0 * TP + r];
-        tot[1] += ROWACC[(P.n_feat + S_KL) * RBMAX + r];
-        tot[2] += ROWACC[(P.n_feat + S_RX) * RBMAX + r];
-        tot[3] += ROWACC[(P.n_feat + S_RC) * RBMAX + r];
-        tot[4] += ROWACC[(P.n_feat + S_RY) * RBMAX + r];
+        tot[1] += SC[S_Q1 * TP + r];
+        tot[2] += SC[S_KL * TP + r];
+        tot[3] += SC[S_KL2 * TP + r];
+        tot[4] += SC[S_W * TP + r];
       }
     }
     __syncthreads();
@@ -1073,7 +841,6 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
     }
     // per-thread running sums -> fixed-order sums over the 128 pair slots of each column
     __syncthreads();
-    float* R0 = FEAT;  // [TNT][32]
 #pragma unroll
     for (int i = 0; i < 32; ++i) R0[tid * 32 + i] = dbx[i];
     __syncthreads();

@@ -84,6 +84,12 @@ struct DecParams {
   long long n_params;
   OutP out;
   long long* phase;        // optional [PH_COUNT] cycle counters (profiling), else nullptr
+  // tensor-core path: per-tile records exchanged between lat_fwd_kernel / dec_tc_kernel / lat_bwd_kernel
+  unsigned char* rec;      // [tiles][rec_stride]: latent operand hi/lo planes (8 KB) + raw c|y per pair
+  long long rec_stride;
+  float* dzrec;            // [tiles][nz_c + nz_y + nz_x][128]: dL/dz per pair
+  float* epsbuf;           // [tiles][Z][128]: reparameterisation noise
+  float* rowkl;            // [B]: per-row KL (MC mean)
 };
 
 // ---- tensor-core decoder kernel (dec_tc_kernel.cu): DecParams + its own shared-memory plan (BYTE offsets) ----
@@ -93,14 +99,19 @@ struct TcParams {
   int KZ, c_ones, c_s0;      // latent operand: columns, constant-one column, first physics-input column
   int w_fx0, w_fx1, w_p[4];  // weight operands (hi plane), lo plane at + l_*
   int l_fx0, l_fx1, l_p[4];
-  int a_big, a_g, a_lat, a_oa, l_big, l_g, l_lat, l_oa;   // activation / gradient operands
+  int a_big, a_g, a_oa, l_big, l_g, l_oa;   // activation / gradient operands
+  int a_rec, rec_buf;        // two tile-record buffers of rec_buf bytes each
   int f_inv, f_bias_x, f_bias_p1, f_bias_p2, f_aw0, f_ab0, f_aw1, f_ab1;
-  int f_eps, f_u, f_zxin, f_zd, f_dza, f_dzx, f_sc, f_rowpar, f_rowraw, f_rowlog, f_red;
+  int f_dza, f_sc, f_red;
   int o_bar;
   int total;
 };
 void launch_dec_tc(const TcParams& p, int grid, cudaStream_t s);
 int configure_dec_tc_kernel();
+size_t lat_smem_bytes(const DecParams& p, bool bwd);
+void launch_lat_fwd(const DecParams& p, long long n_tiles, cudaStream_t s);
+void launch_lat_bwd(const DecParams& p, long long n_tiles, cudaStream_t s);
+int configure_lat_kernels();
 bool dec_tc_has_variant(int phys_kind, int nd_x);
 
 // ---- encoder-side kernels (forward and backward over "MLP2 units") ------------------------------

@@ -1,0 +1,409 @@
+// Per-pair latent kernels of the tensor-core path (sm_100a): everything between the encoder heads and the
+// decoders that is scalar work per (row, MC-sample) pair, kept OUT of the tensor-core decoder kernel so that it
+// runs at full occupancy instead of on the 8 latency-bound epilogue warps:
+//
+//   lat_fwd_kernel : head post-processing (clamp / exp / tril, models/encoders.py:35-43), reparameterised sample
+//                    z = loc + L eps (models/encoders.py:73-93), logistic + shift/scale bijector and its log-det
+//                    (utils/transforms.py:97-150), log q, log p(zx) (utils/priors.py:19-23), log p(zc|c), log p(zy|y)
+//                    (models/vae.py:200-207) -> per-row KL; writes, per 128-pair tile, the decoder kernel's input
+//                    RECORD: the latent operand [zd | 1 | physics input] already split into fp16 hi/lo planes in the
+//                    X8 layout of tc.cuh (the decoder kernel bulk-copies it straight into its operand buffer) plus
+//                    the raw c / y values per pair, and the noise (reused by the backward).
+//   lat_bwd_kernel : from the decoder kernel's per-pair dL/dz record: gradients w.r.t. loc / L / prior-net heads,
+//                    reduced over the MC axis, chain rule through clamp / exp -> gpre (input of enc_bwd_kernel).
+//
+// One CTA (256 threads) per tile of 128 pairs = RB rows x n_mc samples, same tiling as dec_tc_kernel.
+#include <cuda_fp16.h>
+#include <curand_kernel.h>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "tc.cuh"
+
+namespace dpv {
+
+namespace {
+
+constexpr int TP = 128;
+constexpr int LNT = 256;
+
+__device__ __forceinline__ float philox_normal_l(unsigned long long seed, unsigned long long offset, unsigned int T,
+                                                 unsigned long long li) {
+  // torch.cuda normal_() element -> (subsequence, call, lane) map, see dec_kernel.cu
+  const unsigned long long sub = li % T;
+  const unsigned long long q4 = li / T;
+  const unsigned long long it = q4 >> 2;
+  const int comp = (int)(q4 & 3ull);
+  curandStatePhilox4_32_10_t st;
+  curand_init(seed, sub, offset + 4ull * it, &st);
+  const float4 r = curand_normal4(&st);
+  return comp == 0 ? r.x : (comp == 1 ? r.y : (comp == 2 ? r.z : r.w));
+}
+
+__device__ __forceinline__ int block_of_l(const DecParams& P, int i) {
+  int b = 0;
+  while (b + 1 < P.n_blk && i >= P.blk_start[b + 1]) ++b;
+  return b;
+}
+
+// shared-memory carve-up (floats), identical for both kernels
+struct LatSmem {
+  float *ROWPAR, *ROWRAW, *ROWLOG, *EPS, *U, *ZXIN, *ZD, *DZ, *SC, *FEAT, *ROWACC;
+};
+__host__ __device__ inline int lat_smem_floats(const DecParams& P, bool bwd) {
+  const int nzd = P.nz_c + P.nz_y, nzin = P.nz_x + P.nd_p;
+  int f = P.n_rowpar * RBMAX + (P.nd_c + P.nd_y) * RBMAX + 5 * RBMAX + P.Z * TP + P.nz_x * TP + nzin * TP + nzd * TP +
+          (nzd + P.nz_x) * TP + 4 * TP;
+  if (bwd) f += P.n_feat * TP + P.n_feat * RBMAX;
+  return f;
+}
+__device__ inline LatSmem lat_carve(float* sm, const DecParams& P, bool bwd) {
+  const int nzd = P.nz_c + P.nz_y, nzin = P.nz_x + P.nd_p;
+  LatSmem S;
+  S.ROWPAR = sm; sm += P.n_rowpar * RBMAX;
+  S.ROWRAW = sm; sm += (P.nd_c + P.nd_y) * RBMAX;
+  S.ROWLOG = sm; sm += 5 * RBMAX;
+  S.EPS = sm; sm += P.Z * TP;
+  S.U = sm; sm += P.nz_x * TP;
+  S.ZXIN = sm; sm += nzin * TP;
+  S.ZD = sm; sm += nzd * TP;
+  S.DZ = sm; sm += (nzd + P.nz_x) * TP;
+  S.SC = sm; sm += 4 * TP;
+  S.FEAT = sm; sm += bwd ? P.n_feat * TP : 0;
+  S.ROWACC = sm;
+  return S;
+}
+
+// per-row parameters of q(z|x) and of the conditional priors, raw c / y
+__device__ void load_row_params(const DecParams& P, const LatSmem& S, long long row0, int nrows) {
+  const int tid = threadIdx.x, RB = P.RB, nzd = P.nz_c + P.nz_y;
+  const long long B = P.B;
+  for (int e = tid; e < RB * P.Z; e += LNT) {
+    const int i = e / RB, r = e - i * RB;
+    const long long lrow = row0 + min(r, nrows - 1);
+    const int b = block_of_l(P, i), il = i - P.blk_start[b];
+    const float pm = P.headpre[(long long)(P.henc[b] + il) * B + lrow];
+    S.ROWPAR[(P.rp_loc + i) * RBMAX + r] = clampf_(pm, -50.0f, 50.0f);
+  }
+  for (int e = tid; e < RB * P.nL; e += LNT) {
+    const int li = e / RB, r = e - li * RB;
+    const long long lrow = row0 + min(r, nrows - 1);
+    const int b = P.L_blk[li], i = P.L_i[li], j = P.L_j[li], nzb = P.blk_size[b];
+    float v;
+    if (i == j) {
+      const float ps = P.headpre[(long long)(P.henc[b] + nzb + i) * B + lrow];
+      v = expf(clampf_(ps, -7.0f, 3.0f)) + 1e-8f;
+    } else {
+      const float pc = P.headpre[(long long)(P.henc[b] + 2 * nzb + i * nzb + j) * B + lrow];
+      v = clampf_(pc, -20.0f, 20.0f);
+    }
+    S.ROWPAR[(P.rp_L + li) * RBMAX + r] = v;
+  }
+  for (int e = tid; e < RB * nzd; e += LNT) {
+    const int k = e / RB, r = e - k * RB;
+    const long long lrow = row0 + min(r, nrows - 1);
+    const int which = k < P.nz_c ? 0 : 1;
+    const int kk = which ? k - P.nz_c : k, nzk = which ? P.nz_y : P.nz_c;
+    float mu = 0.0f, sgm = 1.0f;
+    if (which == 0 || P.y != nullptr) {
+      const float pm = P.headpre[(long long)(P.hpri[which] + kk) * B + lrow];
+      const float ps = P.headpre[(long long)(P.hpri[which] + nzk + kk) * B + lrow];
+      mu = clampf_(pm, -50.0f, 50.0f);
+      sgm = expf(clampf_(ps, -7.0f, 3.0f)) + 1e-8f;
+    }
+    S.ROWPAR[(P.rp_pmu + k) * RBMAX + r] = mu;
+    S.ROWPAR[(P.rp_psig + k) * RBMAX + r] = sgm;
+  }
+  for (int e = tid; e < RB * (P.nd_c + P.nd_y); e += LNT) {
+    const int j = e / RB, r = e - j * RB;
+    const long long lrow = row0 + min(r, nrows - 1);
+    const long long drow = P.idx ? P.idx[lrow] : lrow;
+    float v = 0.0f;
+    if (j < P.nd_c) v = P.c[drow * P.nd_c + j];
+    else if (P.y != nullptr) v = P.y[drow * P.nd_y + (j - P.nd_c)];
+    S.ROWRAW[j * RBMAX + r] = v;
+  }
+}
+
+// z = loc + L eps for the latent blocks b with (b & 1) == hh; returns this thread's share of
+// log q - bijector log-det - log p(zx)
+__device__ __forceinline__ float sample_blocks(const DecParams& P, const LatSmem& S, int hh, int p, int prow, bool with_logs,
+                                               float& dens_share) {
+  float lq_part = 0.0f, ld1 = 0.0f, ld2 = 0.0f, lpx = 0.0f;
+  for (int b = hh; b < P.n_blk; b += 2) {
+    const int s = P.blk_start[b], nzb = P.blk_size[b];
+    float ss = 0.0f;
+    for (int i = 0; i < nzb; ++i) {
+      float acc = S.ROWPAR[(P.rp_loc + s + i) * RBMAX + prow];
+      const int base = P.rp_L + P.blk_loff[b] + i * (i + 1) / 2;
+      for (int j = 0; j <= i; ++j) acc = fmaf(S.ROWPAR[(base + j) * RBMAX + prow], S.EPS[(s + j) * TP + p], acc);
+      const float e = S.EPS[(s + i) * TP + p];
+      ss = fmaf(e, e, ss);
+      const int gi = s + i;
+      if (gi < P.nz_x) {
+        const float u = sigmoidf_(acc);
+        const float a = P.ub[gi] - P.lb[gi];
+        const float zx = fmaf(u, a, P.lb[gi]);
+        S.U[gi * TP + p] = u;
+        S.ZXIN[gi * TP + p] = zx;
+        if (with_logs) {
+          ld1 += acc - 2.0f * softplusf_(acc);
+          ld2 += logf(fabsf(a));
+          if (P.prior_kind[gi] == 0) {
+            const bool inside = (zx >= P.prior_a[gi]) && (zx < P.prior_b[gi]);
+            lpx += (inside ? 0.0f : -INFINITY) - logf(P.prior_b[gi] - P.prior_a[gi]);
+          } else {
+            const float d = zx - P.prior_a[gi];
+            lpx += -(d * d) / (2.0f * P.prior_b[gi] * P.prior_b[gi]) - logf(P.prior_b[gi]) - LOG_SQRT_2PI;
+          }
+        }
+      } else {
+        S.ZD[(gi - P.nz_x) * TP + p] = acc;
+      }
+    }
+    if (with_logs) lq_part += -0.5f * ((float)nzb * LOG_2PI + ss) - S.ROWLOG[b * RBMAX + prow];
+  }
+  dens_share = lq_part - (ld1 + ld2);
+  return dens_share - lpx;
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(LNT) lat_fwd_kernel(const __grid_constant__ DecParams P) {
+  extern __shared__ __align__(16) float lsm[];
+  const LatSmem S = lat_carve(lsm, P, false);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, hh = warp >> 2, p = 32 * q + lane;
+  const int n = P.n_mc, RB = P.RB, nzd = P.nz_c + P.nz_y, nzin = P.nz_x + P.nd_p;
+  const long long B = P.B;
+  const bool mlp = P.phys_kind == 0;
+  const int c1 = nzd, cs0 = nzd + 1;
+  const long long rb = blockIdx.x;
+  const long long row0 = rb * RB;
+  const int nrows = (int)min((long long)RB, B - row0);
+  const int npairs = nrows * n;
+
+  load_row_params(P, S, row0, nrows);
+  // reparameterisation noise (kept for the backward)
+  float* epsg = P.epsbuf + (long long)rb * P.Z * TP;
+  for (int e = tid; e < TP * P.Z; e += LNT) {
+    const int pp = e & (TP - 1), i = e >> 7;
+    float v = 0.0f;
+    if (pp < npairs) {
+      const int r = pp / n, m = pp - r * n;
+      const unsigned long long grow = (unsigned long long)(P.row_off + row0 + r);
+      const int b = block_of_l(P, i), il = i - P.blk_start[b], nzb = P.blk_size[b];
+      const unsigned long long li = ((unsigned long long)m * (unsigned long long)P.Bg + grow) * nzb + il;
+      v = P.rng.mode == 0 ? P.rng.eps[b][li] : philox_normal_l(P.rng.seed, P.rng.offset[b], P.rng.grid_threads[b], li);
+    }
+    S.EPS[e] = v;
+    epsg[e] = v;
+  }
+  __syncthreads();
+  for (int e = tid; e < RB * (P.n_blk + 2); e += LNT) {
+    const int t = e / RB, r = e - t * RB;
+    float s = 0.0f;
+    if (t < P.n_blk) {
+      for (int i = 0; i < P.blk_size[t]; ++i) s += logf(S.ROWPAR[(P.rp_L + P.blk_loff[t] + i * (i + 1) / 2 + i) * RBMAX + r]);
+    } else {
+      const int k0 = t == P.n_blk ? 0 : P.nz_c, k1 = t == P.n_blk ? P.nz_c : nzd;
+      for (int k = k0; k < k1; ++k) s += logf(S.ROWPAR[(P.rp_psig + k) * RBMAX + r]);
+    }
+    S.ROWLOG[t * RBMAX + r] = s;
+  }
+  __syncthreads();
+
+  const bool pvalid = p < npairs;
+  const int prow = (pvalid ? p : npairs - 1) / n;
+  const int pm_ = (pvalid ? p : npairs - 1) - prow * n;
+  float dens_share;
+  const float lq_part = sample_blocks(P, S, hh, p, prow, true, dens_share);
+  if (hh == 0)
+    for (int j = 0; j < P.nd_p; ++j) S.ZXIN[(P.nz_x + j) * TP + p] = S.ROWRAW[P.idx_c_phys[j] * RBMAX + prow];
+  S.SC[(2 + hh) * TP + p] = dens_share;
+  __syncthreads();
+  {
+    // conditional prior of side hh: p(zc|c) (hh = 0) or p(zy|y) (hh = 1), diagonal Gaussian
+    const int a_nz = hh ? P.nz_y : P.nz_c, a_j0 = hh ? P.nz_c : 0;
+    float mh = 0.0f;
+    for (int k = a_j0; k < a_j0 + a_nz; ++k) {
+      const float t = (S.ZD[k * TP + p] - S.ROWPAR[(P.rp_pmu + k) * RBMAX + prow]) / S.ROWPAR[(P.rp_psig + k) * RBMAX + prow];
+      mh = fmaf(t, t, mh);
+    }
+    const float lp = -0.5f * ((float)a_nz * LOG_2PI + mh) - S.ROWLOG[(P.n_blk + hh) * RBMAX + prow];
+    S.SC[hh * TP + p] = pvalid ? lq_part - lp : 0.0f;
+    if (hh == 0 && pvalid && (P.out.dens || P.out.zx || P.out.zc || P.out.zy)) {
+      const long long o = (long long)pm_ * B + row0 + prow;
+      if (P.out.dens) P.out.dens[o] = S.SC[2 * TP + p] + S.SC[3 * TP + p];
+      if (P.out.zx) for (int k = 0; k < P.nz_x; ++k) P.out.zx[o * P.nz_x + k] = S.ZXIN[k * TP + p];
+      if (P.out.zc) for (int k = 0; k < P.nz_c; ++k) P.out.zc[o * P.nz_c + k] = S.ZD[k * TP + p];
+      if (P.out.zy) for (int k = 0; k < P.nz_y; ++k) P.out.zy[o * P.nz_y + k] = S.ZD[(P.nz_c + k) * TP + p];
+    }
+    // decoder-kernel input record: latent operand row, chunk hh: [zd | 1 | physics input | 0] * 2^4, fp16 hi / lo
+    // planes (physics input: standardised for the MLP surrogate, raw zx for the closed forms)
+    unsigned char* rec = P.rec + (long long)rb * P.rec_stride;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = 8 * hh + i;
+      float x = 0.0f;
+      if (k < nzd) x = pvalid ? S.ZD[k * TP + p] : 0.0f;
+      else if (k == c1) x = 1.0f;
+      else if (k >= cs0 && k < cs0 + nzin) {
+        const float z = S.ZXIN[(k - cs0) * TP + p];
+        x = mlp ? (z - P.phys_in_mean[k - cs0]) / P.phys_in_std[k - cs0] : z;
+        if (!pvalid && mlp) x = 0.0f;
+      }
+      v[i] = x * 16.0f;
+    }
+    uint4 hi, lo;
+    tc::split8(v, hi, lo);
+    *reinterpret_cast<uint4*>(rec + (hh * TP + p) * 16) = hi;
+    *reinterpret_cast<uint4*>(rec + 4096 + (hh * TP + p) * 16) = lo;
+    // raw covariates / labels per pair (rows of 128 floats)
+    float* raw = reinterpret_cast<float*>(rec + 8192);
+    if (hh == 0) {
+      for (int j = 0; j < P.nd_c; ++j) raw[j * TP + p] = S.ROWRAW[j * RBMAX + prow];
+    } else {
+      for (int j = 0; j < P.nd_y; ++j) raw[(P.nd_c + j) * TP + p] = S.ROWRAW[(P.nd_c + j) * RBMAX + prow];
+    }
+  }
+  __syncthreads();
+  // per-row KL = mean over the MC axis (models/vae.py:207)
+  if (tid < nrows) {
+    float s = 0.0f;
+    for (int m = 0; m < n; ++m) s += S.SC[tid * n + m] + S.SC[TP + tid * n + m];
+    P.rowkl[row0 + tid] = s / (float)n;
+  }
+}
+
+__global__ void __launch_bounds__(LNT) lat_bwd_kernel(const __grid_constant__ DecParams P) {
+  extern __shared__ __align__(16) float lsm[];
+  const LatSmem S = lat_carve(lsm, P, true);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, hh = warp >> 2, p = 32 * q + lane;
+  const int n = P.n_mc, RB = P.RB, nzd = P.nz_c + P.nz_y;
+  const long long B = P.B;
+  const long long rb = blockIdx.x;
+  const long long row0 = rb * RB;
+  const int nrows = (int)min((long long)RB, B - row0);
+  const int npairs = nrows * n;
+  const float wpair = 1.0f / ((float)P.Bg * (float)(P.nd_x + P.nd_c + P.nd_y) * (float)n);
+
+  load_row_params(P, S, row0, nrows);
+  const float* epsg = P.epsbuf + (long long)rb * P.Z * TP;
+  for (int e = tid; e < TP * P.Z; e += LNT) S.EPS[e] = epsg[e];
+  const float* dzg = P.dzrec + (long long)rb * (nzd + P.nz_x) * TP;
+  for (int e = tid; e < (nzd + P.nz_x) * TP; e += LNT) S.DZ[e] = dzg[e];
+  __syncthreads();
+  const bool pvalid = p < npairs;
+  const int prow = (pvalid ? p : npairs - 1) / n;
+  float dens_share;
+  sample_blocks(P, S, hh, p, prow, false, dens_share);
+  __syncthreads();
+
+  // per-pair gradients w.r.t. loc / L / prior parameters
+  {
+    const int pp = tid & (TP - 1), prt = tid >> 7;
+    const int r = (pp < npairs ? pp : npairs - 1) / n;
+    const float bw = pp < npairs ? P.beta_x * wpair : 0.0f;
+    const float wv = pp < npairs ? 1.0f : 0.0f;
+    for (int k = prt; k < nzd; k += 2) {
+      float g = wv * S.DZ[k * TP + pp];
+      const float sgm = S.ROWPAR[(P.rp_psig + k) * RBMAX + r];
+      const float t = (S.ZD[k * TP + pp] - S.ROWPAR[(P.rp_pmu + k) * RBMAX + r]) / sgm;
+      g += bw * t / sgm;
+      S.FEAT[(P.f_pmu + k) * TP + pp] = -bw * t / sgm;
+      S.FEAT[(P.f_psig + k) * TP + pp] = -bw * (t * t - 1.0f) / sgm;
+      S.FEAT[(P.f_loc + P.nz_x + k) * TP + pp] = g;
+    }
+    for (int i = prt; i < P.nz_x; i += 2) {
+      float g = wv * S.DZ[(nzd + i) * TP + pp];
+      if (P.prior_kind[i] == 1) g += bw * (S.ZXIN[i * TP + pp] - P.prior_a[i]) / (P.prior_b[i] * P.prior_b[i]);
+      const float u = S.U[i * TP + pp];
+      S.FEAT[(P.f_loc + i) * TP + pp] = g * (P.ub[i] - P.lb[i]) * u * (1.0f - u) + bw * (2.0f * u - 1.0f);
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < TP * P.nL; e += LNT) {
+    const int pp = e & (TP - 1), li = e >> 7;
+    const int r = (pp < npairs ? pp : npairs - 1) / n;
+    const int b = P.L_blk[li], i = P.L_i[li], j = P.L_j[li], s = P.blk_start[b];
+    float v = S.FEAT[(P.f_loc + s + i) * TP + pp] * S.EPS[(s + j) * TP + pp];
+    if (i == j) v -= (pp < npairs ? P.beta_x * wpair : 0.0f) / S.ROWPAR[(P.rp_L + li) * RBMAX + r];
+    S.FEAT[(P.f_L + li) * TP + pp] = v;
+  }
+  __syncthreads();
+  // reduce over the MC axis (n consecutive pairs per row, fixed order)
+  for (int e = tid; e < P.n_feat * RBMAX; e += LNT) {
+    const int f = e / RBMAX, r = e - f * RBMAX;
+    if (r < nrows) {
+      const float* src = S.FEAT + f * TP + r * n;
+      float s = 0.0f;
+      if ((n & 3) == 0) {
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+        for (int m = 0; m < (n >> 2); ++m) {
+          const float4 t = s4[m];
+          s += (t.x + t.y) + (t.z + t.w);
+        }
+      } else {
+        for (int m = 0; m < n; ++m) s += src[m];
+      }
+      S.ROWACC[f * RBMAX + r] = s;
+    }
+  }
+  __syncthreads();
+  // gradients w.r.t. the head pre-activations (clamp / exp chain rule, models/encoders.py:35-43)
+  for (int e = tid; e < RB * P.Z; e += LNT) {
+    const int i = e / RB, r = e - i * RB;
+    if (r < nrows) {
+      const long long lrow = row0 + r;
+      const int b = block_of_l(P, i), il = i - P.blk_start[b], nzb = P.blk_size[b];
+      const long long om = (long long)(P.henc[b] + il) * B + lrow;
+      const float pm = P.headpre[om];
+      P.gpre[om] = (pm >= -50.0f && pm <= 50.0f) ? S.ROWACC[(P.f_loc + i) * RBMAX + r] : 0.0f;
+      for (int j = 0; j < nzb; ++j) {
+        const long long oc = (long long)(P.henc[b] + 2 * nzb + il * nzb + j) * B + lrow;
+        float g = 0.0f;
+        if (j < il) {
+          const float pc = P.headpre[oc];
+          const int li = P.blk_loff[b] + il * (il + 1) / 2 + j;
+          g = (pc >= -20.0f && pc <= 20.0f) ? S.ROWACC[(P.f_L + li) * RBMAX + r] : 0.0f;
+        }
+        P.gpre[oc] = g;
+      }
+      const long long os = (long long)(P.henc[b] + nzb + il) * B + lrow;
+      const float ps = P.headpre[os];
+      const int ld = P.blk_loff[b] + il * (il + 1) / 2 + il;
+      P.gpre[os] = (ps >= -7.0f && ps <= 3.0f) ? S.ROWACC[(P.f_L + ld) * RBMAX + r] * expf(ps) : 0.0f;
+    }
+  }
+  for (int e = tid; e < RB * nzd; e += LNT) {
+    const int k = e / RB, r = e - k * RB;
+    if (r < nrows) {
+      const long long lrow = row0 + r;
+      const int which = k < P.nz_c ? 0 : 1;
+      const int kk = which ? k - P.nz_c : k, nzk = which ? P.nz_y : P.nz_c;
+      const long long om = (long long)(P.hpri[which] + kk) * B + lrow;
+      const long long os = (long long)(P.hpri[which] + nzk + kk) * B + lrow;
+      const float pm = P.headpre[om], ps = P.headpre[os];
+      P.gpre[om] = (pm >= -50.0f && pm <= 50.0f) ? S.ROWACC[(P.f_pmu + k) * RBMAX + r] : 0.0f;
+      P.gpre[os] = (ps >= -7.0f && ps <= 3.0f) ? S.ROWACC[(P.f_psig + k) * RBMAX + r] * expf(ps) : 0.0f;
+    }
+  }
+}
+
+size_t lat_smem_bytes(const DecParams& p, bool bwd) { return (size_t)lat_smem_floats(p, bwd) * sizeof(float); }
+void launch_lat_fwd(const DecParams& p, long long n_tiles, cudaStream_t s) {
+  lat_fwd_kernel<<<(unsigned)n_tiles, LNT, lat_smem_bytes(p, false), s>>>(p);
+}
+void launch_lat_bwd(const DecParams& p, long long n_tiles, cudaStream_t s) {
+  lat_bwd_kernel<<<(unsigned)n_tiles, LNT, lat_smem_bytes(p, true), s>>>(p);
+}
+int configure_lat_kernels() {
+  int e = (int)cudaFuncSetAttribute(lat_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  if (!e) e = (int)cudaFuncSetAttribute(lat_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  return e;
+}
+
+}  // namespace dpv

@@ -85,6 +85,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+// transaction-count arrive + 1-D bulk async copy global -> shared (TMA engine, completes on `bar`)
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // ---- TMEM ------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {  // one full warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
@@ -200,7 +210,7 @@ __device__ __forceinline__ uint64_t pack64(uint32_t lo, uint32_t hi) { return ((
 constexpr uint32_t DESC_VERSION_HI = 1u << 14;  // descriptor bit 46
 
 //   fwd   : D[128 rows of A][N]   (+)= sum_k A[r][k] * W[n][k]      A K-major, W K-major (N rows)
-__device__ __noinline__ void issue_fwd(uint32_t d_tmem, Op a, Op w, int N, int K, uint32_t accumulate, int terms) {
+static __device__ __noinline__ void issue_fwd(uint32_t d_tmem, Op a, Op w, int N, int K, uint32_t accumulate, int terms) {
   const uint32_t idesc = make_idesc(128, N, 0, 0);
   const uint32_t ahi = 8u | DESC_VERSION_HI, whi = 8u | DESC_VERSION_HI;       // SBO = 128 B
   const uint32_t astep = 2u * (uint32_t)a.R, wstep = 2u * (uint32_t)w.R;       // two 16-byte K chunks per MMA
@@ -218,7 +228,7 @@ __device__ __noinline__ void issue_fwd(uint32_t d_tmem, Op a, Op w, int N, int K
   }
 }
 //   dgrad : D[128 rows of G][Kin] (+)= sum_n G[r][n] * W[n][kin]    G K-major, W (Nout rows) MN-major over kin
-__device__ __noinline__ void issue_dgrad(uint32_t d_tmem, Op g, Op w, int Nout, int Kin, uint32_t accumulate, int terms) {
+static __device__ __noinline__ void issue_dgrad(uint32_t d_tmem, Op g, Op w, int Nout, int Kin, uint32_t accumulate, int terms) {
   const uint32_t idesc = make_idesc(128, Kin, 0, 1);
   const uint32_t ghi = 8u | DESC_VERSION_HI, whi = (uint32_t)w.R | DESC_VERSION_HI;  // MN-major: SBO = R * 16 B
   const uint32_t gstep = 2u * (uint32_t)g.R, wstep = 16u;                            // 16 K rows = 256 B
@@ -236,7 +246,7 @@ __device__ __noinline__ void issue_dgrad(uint32_t d_tmem, Op g, Op w, int Nout, 
   }
 }
 //   wgrad : D[128 cols of H][N cols of G] (+)= sum_r H[r][m] * G[r][n]   both MN-major, r over R rows
-__device__ __noinline__ void issue_wgrad(uint32_t d_tmem, Op h, Op g, int N, uint32_t accumulate, int terms) {
+static __device__ __noinline__ void issue_wgrad(uint32_t d_tmem, Op h, Op g, int N, uint32_t accumulate, int terms) {
   const uint32_t idesc = make_idesc(128, N, 1, 1);
   const uint32_t hhi = (uint32_t)h.R | DESC_VERSION_HI, ghi = (uint32_t)g.R | DESC_VERSION_HI;
   const int ks = h.R >> 4;

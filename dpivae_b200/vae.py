@@ -328,9 +328,9 @@ class _Engine:
         _lib.check(self.lib.dpivae_set_timing(self.handle, int(bool(enable))))
 
     def last_kernel_ms(self):
-        out = (C.c_float * 5)()
+        out = (C.c_float * 7)()
         _lib.check(self.lib.dpivae_last_kernel_ms(self.handle, out))
-        return dict(zip(("enc_fwd", "dec_fused", "enc_bwd", "reduce", "adam"), [float(v) for v in out]))
+        return dict(zip(("enc_fwd", "dec_fused", "enc_bwd", "reduce", "adam", "lat_fwd", "lat_bwd"), [float(v) for v in out]))
 
     def ffma_peak_tflops(self):
         v = C.c_float(0.0)

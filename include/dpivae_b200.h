@@ -166,12 +166,13 @@ uint64_t dpivae_philox_plan(dpivae_handle_t h, int64_t B_global, int32_t n_mc, i
 
 /* Measurement hooks (bench.py): with timing enabled every hot-path call brackets each of its kernels
  * with CUDA events on the caller's stream; dpivae_last_kernel_ms synchronises those events and returns
- * the durations [enc_fwd, dec_fused, enc_bwd, reduce, adam] of the last call in milliseconds. */
+ * the durations [enc_fwd, dec_fused, enc_bwd, reduce, adam, lat_fwd, lat_bwd] (7 floats) of the last call in
+ * milliseconds (lat_*: the per-pair latent kernels of the tensor-core path, 0 in fp32 mode). */
 int dpivae_set_timing(dpivae_handle_t h, int32_t enable);
 /* Profiling: device buffer of 16 uint64 cycle counters accumulated per phase of the fused decoder kernel
  * (thread 0 of every CTA, clock64 after each barrier); NULL switches it off. */
 int dpivae_set_phase_buffer(dpivae_handle_t h, void* dev_counters16);
-int dpivae_last_kernel_ms(dpivae_handle_t h, float* out5);
+int dpivae_last_kernel_ms(dpivae_handle_t h, float* out7);
 
 /* FP32 FFMA peak of the current device (micro-benchmark, 2 FLOP per FFMA), in TFLOP/s: the roofline
  * denominator for the fp32-parity mode, which MEASURED_PEAKS.json does not carry. */
