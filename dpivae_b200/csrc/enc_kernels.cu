@@ -64,7 +64,7 @@ __device__ __forceinline__ void load_input_tile(const EncParams& P, const EncUni
   }
 }
 
-__global__ void __launch_bounds__(NT, 1) enc_fwd_kernel(const __grid_constant__ EncParams P) {
+__global__ void __launch_bounds__(NT, 2) enc_fwd_kernel(const __grid_constant__ EncParams P) {
   extern __shared__ __align__(16) float sm[];
   int K0m, Hm, Om;
   enc_max_dims(P, K0m, Hm, Om);
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(NT, 1) enc_fwd_kernel(const __grid_constant__ 
   }
 }
 
-__global__ void __launch_bounds__(NT, 1) enc_bwd_kernel(const __grid_constant__ EncParams P) {
+__global__ void __launch_bounds__(NT, 2) enc_bwd_kernel(const __grid_constant__ EncParams P) {
   extern __shared__ __align__(16) float sm[];
   int K0m, Hm, Om;
   enc_max_dims(P, K0m, Hm, Om);
