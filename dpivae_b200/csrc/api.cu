@@ -414,7 +414,9 @@ static WsLayout ws_layout(dpivae_handle_t h, int64_t B, int32_t n_mc) {
   L.tc_grid = (int)(L.tc_rowblocks < h->sm_count ? L.tc_rowblocks : h->sm_count);
   if (L.tc_grid < 1) L.tc_grid = 1;
   const long long ntiles = (B + TILE - 1) / TILE;
-  L.grid_enc = (int)(ntiles < h->sm_count ? ntiles : h->sm_count);
+  // encoder kernels: two resident CTAs per SM when their shared-memory plan allows it (latency hiding)
+  const int enc_per_sm = enc_smem_bytes(h->enc, true) <= 110 * 1024 ? 2 : 1;
+  L.grid_enc = (int)(ntiles < (long long)enc_per_sm * h->sm_count ? ntiles : (long long)enc_per_sm * h->sm_count);
   int RB = TILE / (n_mc < 1 ? 1 : n_mc);
   RB = RB < 1 ? 1 : (RB > RBMAX ? RBMAX : RB);
   L.RB = RB;
@@ -424,7 +426,7 @@ static WsLayout ws_layout(dpivae_handle_t h, int64_t B, int32_t n_mc) {
   if (L.grid_enc < 1) L.grid_enc = 1;
   if (L.grid_dec < 1) L.grid_dec = 1;
 
-  L.part = take((size_t)(2 * h->sm_count) * h->part_stride);
+  L.part = take((size_t)(3 * h->sm_count) * h->part_stride);
   L.scal = take(16);
   L.rec = L.dzrec = L.epsbuf = L.rowkl = 0;
   if (h->tc_ok && n_mc >= 8 && n_mc <= 128) {
