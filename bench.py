@@ -8,6 +8,11 @@ Workloads (BASELINE.json configs):
             At N GPUs the global minibatch is N x 131,072 (N=8 -> config 3's 1,048,576 rows), rows
             sharded, ONE NCCL allreduce of [grads | scalars] per step -> "scaling": "weak".
   beam_s    simple_beam dpivae (S) preset, 65,536 rows x 16 MC (config 2).
+  bridge_encode   bridge encode-only inference (transform_inputs -> encode, n = 1), 524,288 rows per GPU (config 5:
+            4,194,304 rows over 8 GPUs), communication-free replicas; HBM-bound, 300 B per row.
+  ensemble  independent small trainings (damped_oscillator dpivae, seeds x lambda_g0 of 1_disentanglement_metric.py,
+            reference-default shape n_train 1024 / n_batch 64 / n_mc 16), 8 members per GPU on 8 CUDA streams, no
+            communication (config 4); value = members x 64 datapoints per round / time.
 One JSON line on stdout (rank 0).  `--impl reference` times the reference algorithm on the host CPU
 (the oracle port, all host threads) on a bounded sample of the same workload.
 """
@@ -36,6 +41,8 @@ MATH_DOC = {
     "fp32": "all GEMMs fp32 FFMA on the CUDA cores",
     "tc_fp16": "decoder GEMMs on tcgen05 with plain fp16 operands, fp32 accumulate (tolerance 2e-3 loss / 2e-2 gradients)",
 }
+WORKLOADS["bridge_encode"] = dict(case="bridge", preset="DPIVAE-A", rows=524288, n_mc=1, bytes_row=300, flop_row=31_744)
+WORKLOADS["ensemble"] = dict(case="damped_oscillator", preset="dpivae", rows=64, n_mc=16, members=8)
 METRIC = "ELBO train samples/s (fwd+bwd+Adam)"
 UNIT = "datapoints/s"
 
@@ -168,6 +175,178 @@ def run_reference(a, wl):
     print(json.dumps(line), flush=True)
 
 
+def _dist_setup():
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the host baseline")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=dev)
+    return world, rank, local_rank, dev
+
+
+def _timed_region(fn, steps, world, dev):
+    """barrier + synchronize, CUDA events around `steps` calls, max over ranks (ms total)."""
+    import torch
+    import torch.distributed as dist
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(i)
+    e1.record()
+    sync_all()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms)
+
+
+def run_encode(a, wl):
+    """Config 5: encode-only inference, rows sharded as independent replicas (no collective)."""
+    import contextlib, importlib, io
+
+    import torch
+    import torch.distributed as dist
+
+    import dpivae_b200 as dpv
+
+    world, rank, local_rank, dev = _dist_setup()
+    case_mod = importlib.import_module(f"dpivae_b200.cases.{wl['case']}")
+    rows = wl["rows"]
+    xs, cs, ys = synth(case_mod, 4096, 7, dev)
+    args = make_args(case_mod, wl["preset"], use_seed=True, seed=123, n_train=4096, n_batch=4096)
+    with contextlib.redirect_stdout(io.StringIO()):
+        vae = dpv.setup_model(args, case_mod.definition, (xs, cs, ys))
+    x, _, _ = synth(case_mod, rows, 2000 + rank, dev)
+    eng = vae.engine()
+    torch.manual_seed(5)
+    xh = x.cpu().pin_memory()
+    xd = torch.empty_like(x)
+    out_host = [torch.empty((1, rows, k), dtype=torch.float32).pin_memory() for k in (vae.nz_x, vae.nz_c, vae.nz_y)]
+
+    def step_resident(i):
+        eng.encode(x, 1, False)
+
+    def step_e2e(i):
+        xd.copy_(xh, non_blocking=True)
+        zx, zc, zy, dens = eng.encode(xd, 1, False)
+        for h, t in zip(out_host, (zx, zc, zy)):
+            h.copy_(t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for i in range(a.warmup):
+        step_resident(i)
+    l0 = eng.launches
+    with ClockSampler(local_rank) as clk:
+        ms = _timed_region(step_resident, a.steps, world, dev) / a.steps
+        launches = eng.launches - l0
+        step_e2e(0)
+        ms_e2e = _timed_region(step_e2e, a.steps, world, dev) / a.steps
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm = peaks.get("hbm_gbs", 6650.0)
+        achieved = wl["bytes_row"] * rows / (ms * 1e-3) / 1e9
+        line = {"metric": "encode-only datapoints/s (transform_inputs -> encode, n=1)", "value": rows * world / (ms * 1e-3),
+                "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": a.workload, "case": wl["case"], "preset": wl["preset"], "rows_per_gpu": rows, "n_mc": 1,
+                           "parallelism": f"replicas x{world} (no collective)", "l2": "inputs 134 MB per GPU > 126 MB L2, no flush"},
+                "e2e": {"value": rows * world / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                        "h2d_bytes_per_step": int(rows * vae.nd_x * 4), "d2h_bytes_per_step": int(rows * 10 * 4)},
+                "gpu_launches": launches,
+                "roofline": {"bound": "hbm", "kernel": "enc_fwd_kernel + dec_kernel(latent_only)", "achieved": achieved, "peak": hbm,
+                             "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+                             "peak_source": "measured copy bandwidth (MEASURED_PEAKS.json)" if peaks else "fallback 6.65 TB/s"},
+                "clocks": clk.summary()}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_ensemble(a, wl):
+    """Config 4: independent small trainings, several members per GPU on separate CUDA streams, no communication."""
+    import contextlib, importlib, io
+
+    import torch
+    import torch.distributed as dist
+
+    import dpivae_b200 as dpv
+
+    world, rank, local_rank, dev = _dist_setup()
+    case_mod = importlib.import_module(f"dpivae_b200.cases.{wl['case']}")
+    M, n, nb = wl["members"], wl["n_mc"], wl["rows"]
+    lambdas = [1e4, 1e3, 1e2, 1e1, 1e0, 0.0, -1e0, -1e1, -1e2, -1e3, -1e4]  # 1_disentanglement_metric.py:56 (/1e4)
+    members = []
+    for m in range(M):
+        gm = rank * M + m
+        x, c, y = synth(case_mod, 1024, 100 + gm, dev)
+        args = make_args(case_mod, wl["preset"], use_seed=True, seed=gm, n_train=1024, n_batch=nb,
+                         lambda_g0=lambdas[gm % len(lambdas)] / 1e4)
+        with contextlib.redirect_stdout(io.StringIO()):
+            vae = dpv.setup_model(args, case_mod.definition, (x, c, y))
+        eng = vae.engine()
+        eng.set_groups(dpv.param_groups(args))
+        eng.set_math_mode(a.math)
+        gcpu = torch.Generator().manual_seed(gm)
+        pool = torch.stack([torch.multinomial(torch.ones(1024), nb, False, generator=gcpu) for _ in range(64)]).to(dev)
+        members.append(dict(eng=eng, x=x, c=c, y=y, pool=pool, stream=torch.cuda.Stream(dev), step=0))
+    w = (1.0, 1.0, 1.0, 1.0)
+
+    def round_(i):
+        for mb in members:
+            with torch.cuda.stream(mb["stream"]):
+                mb["step"] += 1
+                mb["eng"].loss(mb["x"], mb["c"], mb["y"], n, w, True, idx=mb["pool"][mb["step"] % 64], adam_step=mb["step"])
+
+    def round_synced(i):
+        cur = torch.cuda.current_stream()
+        for mb in members:
+            mb["stream"].wait_stream(cur)
+        round_(i)
+        for mb in members:
+            cur.wait_stream(mb["stream"])
+
+    for i in range(a.warmup):
+        round_synced(i)
+    l0 = sum(mb["eng"].launches for mb in members)
+    with ClockSampler(local_rank) as clk:
+        ms = _timed_region(round_synced, a.steps, world, dev) / a.steps
+    launches = sum(mb["eng"].launches for mb in members) - l0
+    if rank == 0:
+        line = {"metric": "ensemble train samples/s (independent small models, fwd+bwd+Adam)", "value": M * nb * world / (ms * 1e-3),
+                "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": a.workload, "case": wl["case"], "preset": wl["preset"], "members_per_gpu": M, "n_batch": nb,
+                           "n_mc": n, "n_train": 1024, "math": a.math, "parallelism": f"{M * world} independent members, no collective"},
+                "gpu_launches": launches, "clocks": clk.summary(),
+                "elbo": [float(mb["eng"].scalars[0]) for mb in members]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -187,8 +366,14 @@ def main():
     wl = dict(WORKLOADS[a.workload])
     if a.rows:
         wl["rows"] = a.rows
+    if a.workload in ("bridge_encode", "ensemble") and a.impl == "reference":
+        raise SystemExit("--impl reference covers the training-step workloads (bridge_p, beam_s)")
     if a.impl == "reference":
         return run_reference(a, wl)
+    if a.workload == "bridge_encode":
+        return run_encode(a, wl)
+    if a.workload == "ensemble":
+        return run_ensemble(a, wl)
 
     import importlib
 

@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(NT, 1) dec_kernel(const __grid_constant__ DecP
       const long long lrow = row0 + min(r, nrows - 1);
       const long long drow = P.idx ? P.idx[lrow] : lrow;
       float v = 0.0f;
-      if (j < P.nd_c) v = P.c[drow * P.nd_c + j];
+      if (j < P.nd_c) v = P.c != nullptr ? P.c[drow * P.nd_c + j] : 0.0f;   // encode-only calls pass neither c nor y
       else if (P.y != nullptr) v = P.y[drow * P.nd_y + (j - P.nd_c)];
       ROWRAW[j * RBMAX + r] = v;
     }

@@ -141,3 +141,32 @@ def test_shard_invariance_and_determinism():
     assert torch.equal(torch.cat([rl_a, rl_b], dim=1), rl)
     assert gu.rel_l2((g_a + g_b).cpu(), g_full.cpu()) < 1e-6
     assert gu.rel_l2((s_a + s_b).cpu(), s.cpu()) < 1e-6
+
+
+@pytest.mark.parametrize("case,mtype", gu.CONFIGS)
+def test_encode_only(case, mtype):
+    """transform_inputs -> encode (models/vae.py:161-162, 125-151; dpivae_encode): latents and density of the
+    encode-only inference path against the reference's forward outputs on the same noise."""
+    g, spec, sd, args, case_mod, vae, (x, c, y) = build_from_golden(case, mtype)
+    n = g["eps0"].shape[0]
+    x_t = vae.transform_inputs(x.cuda())[0]
+    with vae.inject_noise(_dev_eps(g, spec)):
+        zx, zc, zy, dens = vae.encode(x_t, n=n)
+    for name, t in (("zx", zx), ("zc", zc), ("zy", zy), ("dens_z", dens)):
+        err = gu.rel_l2(t.cpu(), g[f"fw.{name}"])
+        assert err < TOL, (name, err)
+
+
+def test_sample_and_evaluate_model():
+    """DPIVAE.sample 9-tuple (models/vae.py:233-255) and evaluate_model (dpivae.py:527-559) on the fused path."""
+    import dpivae_b200 as dpv
+
+    g, spec, sd, args, case_mod, vae, (x, c, y) = build_from_golden("bridge", "P")
+    out = vae.sample(x.cuda(), c.cuda(), cond=False, n=3)
+    assert len(out) == 9
+    B = x.shape[0]
+    assert out[0].shape == (3, B, vae.nd_x) and out[4].shape == (3, B, vae.nd_y) and out[8].shape == (3, B)
+    assert all(torch.isfinite(t).all() for t in out)
+    args.n_mc_test = 8
+    metrics, pred = dpv.evaluate_model(args, case_mod.definition, vae, (x.cuda(), c.cuda(), y))
+    assert set(metrics[args.name]) == {"r2", "mse", "mae"} and pred[args.name].shape == (B, vae.nd_y)

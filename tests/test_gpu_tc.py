@@ -121,3 +121,30 @@ def test_tc_adam_trajectory(case, mtype):
         if p.requires_grad:
             err = gu.rel_l2(p.detach().cpu(), g[f"traj.final.{k}"])
             assert err < 1e-4, (k, err)
+
+
+def test_tc_training_tracks_fp32_kernel():
+    """Ten fused train steps (in-kernel Philox noise, n_mc = 16, several tiles) in tc_fp16x3 mode end at the same
+    parameters as the fp32 FFMA kernels: 1e-5 on the logged ELBO of every step, 1e-4 relative L2 on every tensor."""
+    from dpivae_b200 import param_groups
+
+    finals, elbos = {}, {}
+    for mode in ("fp32", "tc_fp16x3"):
+        g, spec, sd, args, case_mod, vae, (x, c, y) = build_from_golden("bridge", "P")
+        eng = vae.engine()
+        eng.set_groups(param_groups(args))
+        eng.set_math_mode(mode)
+        X, C_, Y = _tile(x, 11).cuda(), _tile(c, 11).cuda(), _tile(y, 11).cuda()
+        torch.manual_seed(77)
+        e = []
+        for it in range(10):
+            _, scal = eng.loss(X, C_, Y, 16, (1.0, 1.0, 1.0, 1.0), True, adam_step=it + 1)
+            e.append(float(scal[0]))
+        assert eng.used_tensor_cores() == (mode != "fp32")
+        finals[mode] = {k: p.detach().clone() for k, p in vae.named_parameters() if p.requires_grad}
+        elbos[mode] = e
+    for a, b in zip(elbos["fp32"], elbos["tc_fp16x3"]):
+        assert abs(a - b) < 1e-5 * max(1.0, abs(a)), (a, b)
+    for k in finals["fp32"]:
+        err = gu.rel_l2(finals["tc_fp16x3"][k].cpu(), finals["fp32"][k].cpu())
+        assert err < 1e-4, (k, err)
