@@ -235,6 +235,7 @@ def run_encode(a, wl):
         vae = dpv.setup_model(args, case_mod.definition, (xs, cs, ys))
     x, _, _ = synth(case_mod, rows, 2000 + rank, dev)
     eng = vae.engine()
+    eng.set_math_mode(a.math)
     torch.manual_seed(5)
     xh = x.cpu().pin_memory()
     xd = torch.empty_like(x)

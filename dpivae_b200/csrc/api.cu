@@ -47,6 +47,8 @@ struct dpivae_model {
   float lr[16], wd[16];
   int last_launches = 0;
   long long part_stride = 0;
+  EncTcParams enc_tc;       // tensor-core encoder plan
+  int enc_tc_ok = 0;
   int math_mode = 0;        // DPIVAE_MATH_*
   TcParams tc;              // tensor-core decoder plan
   int tc_ok = 0;            // model shape supported by dec_tc_kernel
@@ -257,6 +259,44 @@ static int build_plan(dpivae_model* h) {
   if (enc_smem_bytes(E, true) > 232448) return fail("encoder kernel shared-memory plan exceeds 227 KB");
   h->part_stride = (long long)align_up((size_t)d.n_params + NSCAL, 64);
 
+  // ---- tensor-core encoder plan ----
+  {
+    EncTcParams& Q = h->enc_tc;
+    memset(&Q, 0, sizeof(Q));
+    h->enc_tc_ok = 0;
+    const int nu = h->n_enc_units;
+    Q.n_units = nu; Q.K0 = d.nd_x; Q.KX = d.nd_x + 16; Q.terms = 3;
+    int hoff = 0, ooff = 0;
+    bool ok = (d.nd_x == 32 || d.nd_x == 64);
+    for (int u = 0; u < nu; ++u) {
+      const EncUnit& U = E.u[u];
+      Q.H[u] = U.H; Q.O[u] = U.O; Q.h_off[u] = hoff; Q.o_off[u] = ooff; Q.out_row[u] = U.out_row;
+      Q.g_w0[u] = U.g_w0; Q.g_b0[u] = U.g_b0; Q.g_w1[u] = U.g_w1; Q.g_b1[u] = U.g_b1;
+      hoff += U.H; ooff += U.O;
+      ok = ok && U.K0 == d.nd_x && (U.H % 16 == 0);
+    }
+    Q.h_off[nu] = hoff;
+    Q.Hc = hoff; Q.Oc = (ooff + 15) & ~15;
+    ok = ok && Q.Hc % 16 == 0 && Q.Hc <= 256 && Q.Oc <= 256 && 2 * Q.Hc + Q.Oc <= 512;
+    for (int i = 0; i < d.nd_x; ++i) { Q.mean_x[i] = d.mean_x[i]; Q.std_x[i] = d.std_x[i]; }
+    int b = 0;
+    auto plane2 = [&](int chunks, int rows, int& off, int& lo) {
+      const int bytes = chunks * rows * 16;
+      off = b; lo = bytes; b += 2 * bytes;
+    };
+    plane2(Q.KX / 8, Q.Hc, Q.w_0, Q.l_0);
+    plane2(Q.Hc / 8, Q.Oc, Q.w_1, Q.l_1);
+    plane2(Q.KX / 8, 128, Q.a_x, Q.l_x);
+    Q.f_b1 = b; b += Q.Oc * 4;
+    Q.f_orow = b; b += Q.Oc * 4;
+    Q.f_red = b; b += 256;
+    Q.o_bar = b; b += 16;
+    Q.total = (b + 127) & ~127;
+    Q.hid_lo = (Q.Hc / 8) * 128 * 16;
+    Q.hid_stride = 2 * (long long)Q.hid_lo;
+    if (ok && Q.total <= 232448) h->enc_tc_ok = 1;
+  }
+
   // ---- shared-memory plan of the tensor-core decoder kernel (byte offsets) ----
   TcParams& T = h->tc;
   memset(&T, 0, sizeof(T));
@@ -319,7 +359,8 @@ int dpivae_create(const dpivae_model_desc_t* desc, dpivae_handle_t* out) {
   h->d = *desc;
   h->sm_count = prop.multiProcessorCount;
   if (build_plan(h)) { delete h; return 1; }
-  if (configure_dec_kernel() || configure_enc_kernels() || configure_dec_tc_kernel() || configure_lat_kernels()) { delete h; return fail("cudaFuncSetAttribute(max dynamic smem) failed"); }
+  if (configure_dec_kernel() || configure_enc_kernels() || configure_dec_tc_kernel() || configure_lat_kernels() ||
+      configure_enc_tc_kernels()) { delete h; return fail("cudaFuncSetAttribute(max dynamic smem) failed"); }
   // owner map: which kernel's partials hold each parameter's gradient
   std::vector<unsigned char> owner((size_t)desc->n_params, 0);
   for (int u = 0; u < h->enc.n_units; ++u) {
@@ -490,8 +531,31 @@ static int run_loss(dpivae_handle_t h, const dpivae_batch_t* bt, const dpivae_rn
   const size_t enc_smem = enc_smem_bytes(h->enc, true);
   for (int k = 0; k < 4; ++k) h->ev_used[k] = 0;
   h->ev_used[5] = h->ev_used[6] = 0;
-  { KTimer t(h, 0, st); launch_enc_fwd(E, L.grid_enc, enc_smem, st); }
-  ++launches;
+  // encoder forward: tensor-core kernel for the encoder units (+ the FFMA kernel for the two prior nets) in the
+  // tensor-core math modes when no backward follows; the FFMA kernel for everything otherwise
+  const bool enc_tc = h->math_mode != DPIVAE_MATH_FP32 && h->enc_tc_ok && !with_grad;
+  {
+    KTimer t(h, 0, st);
+    if (enc_tc) {
+      EncTcParams Q = h->enc_tc;
+      Q.params = h->params; Q.x = bt->x; Q.idx = (const long long*)bt->idx; Q.B = bt->B;
+      Q.headpre = headpre; Q.hidrec = nullptr; Q.x_is_standardised = x_std;
+      Q.terms = h->math_mode == DPIVAE_MATH_TC_FP16X3 ? 3 : 1;
+      const long long nt = (bt->B + 127) / 128;
+      launch_enc_tc_fwd(Q, (int)(nt < h->sm_count ? nt : h->sm_count), st);
+      ++launches;
+      if (!latent_only) {
+        EncParams E2 = E;
+        E2.n_units = E.n_units - h->n_enc_units;
+        for (int u = 0; u < E2.n_units; ++u) E2.u[u] = E.u[h->n_enc_units + u];
+        launch_enc_fwd(E2, L.grid_enc, enc_smem, st);
+        ++launches;
+      }
+    } else {
+      launch_enc_fwd(E, L.grid_enc, enc_smem, st);
+      ++launches;
+    }
+  }
 
   DecParams D = h->dec;
   D.params = h->params; D.frozen = h->d_frozen;
@@ -514,7 +578,11 @@ static int run_loss(dpivae_handle_t h, const dpivae_batch_t* bt, const dpivae_rn
     D.out.yh = out->yh; D.out.lsy = out->log_sigma_y; D.out.zx = out->zx; D.out.zc = out->zc; D.out.zy = out->zy;
     D.out.dens = out->dens_z;
   }
-  if (use_tc) {
+  if (latent_only) {
+    // encode-only: per-pair streaming kernel (no decoders, no priors)
+    KTimer t(h, 1, st);
+    launch_lat_encode(D, st);
+  } else if (use_tc) {
     TcParams T = h->tc;
     D.RB = L.tc_RB; D.n_chunks = 1; D.n_rowblocks = L.tc_rowblocks;
     D.rec = (unsigned char*)(base + L.rec); D.rec_stride = h->tc.rec_buf;

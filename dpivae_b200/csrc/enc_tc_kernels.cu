@@ -1,0 +1,271 @@
+// Encoder MLPs on the tensor cores (sm_100a, tcgen05 / TMEM): the FullCovarianceNN encoders of
+// models/encoders.py:7-44 -- hidden layer ReLU(W0 x_t + b0) and the concatenated heads [f_mean ; f_sigma ; f_cov] --
+// for all encoder units at once (P: three 64-wide units side by side, S: one 128-wide unit), 128 minibatch rows per
+// tile = the M dimension of tcgen05.mma.  Same fp16 hi/lo operand split as the decoder kernel (tc.cuh), so the
+// results carry fp32 accuracy.
+//
+//   enc_tc_fwd_kernel: x tile -> standardise (utils/transforms.py:70-73) -> X8 operand (+ constant-one column that
+//       carries b0) -> MMA (N = all hidden units) -> ReLU epilogue writes the hidden activations as PACKED fp16
+//       hi/lo planes straight back to tensor memory, from where the head MMA reads its A operand (no shared-memory
+//       round trip), and -- for training -- to global memory in the X8 layout the backward kernel bulk-copies ->
+//       head MMA (block-diagonal W1) -> head pre-activations `headpre` [O_tot][B].
+//   enc_tc_bwd_kernel: gpre tile + hidden record + x tile -> wgrad of the heads, dgrad through the heads with the
+//       ReLU mask, wgrad of the first layers; weight gradients accumulate in TMEM across all tiles of the CTA.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "tc.cuh"
+
+namespace dpv {
+
+namespace {
+
+constexpr int TP = 128;
+constexpr int ENT = 256;
+constexpr int E_X = 4;   // operand scale exponents: standardised inputs
+constexpr int E_HID = 6;  // hidden activations
+
+__device__ __forceinline__ void put8e(unsigned char* plane, uint32_t lo_off, int R, int chunk, int row, const float* v) {
+  uint4 hi, lo;
+  tc::split8(v, hi, lo);
+  unsigned char* dst = plane + ((size_t)chunk * R + row) * 16;
+  *reinterpret_cast<uint4*>(dst) = hi;
+  *reinterpret_cast<uint4*>(dst + lo_off) = lo;
+}
+
+template <class G>
+__device__ float block_absmax_e(int count, G get, float* red) {
+  float m = 0.0f;
+  for (int e = threadIdx.x; e < count; e += ENT) m = fmaxf(m, fabsf(get(e)));
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  float r = red[0];
+#pragma unroll
+  for (int w = 1; w < ENT / 32; ++w) r = fmaxf(r, red[w]);
+  return r;
+}
+__device__ __forceinline__ int scale_exp_e(float mx) {
+  if (!(mx > 0.0f) || !isfinite(mx)) return 0;
+  int e;
+  frexpf(mx, &e);
+  return 9 - e;
+}
+template <class G>
+__device__ void stage_weight_e(unsigned char* plane, uint32_t lo_off, int N, int KP, int kexp, G get) {
+  const float s = exp2f((float)kexp);
+  const int nch = KP >> 3;
+  for (int e = threadIdx.x; e < nch * N; e += ENT) {
+    const int ch = e / N, n = e - ch * N;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = get(n, 8 * ch + i) * s;
+    put8e(plane, lo_off, N, ch, n, v);
+  }
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(ENT, 1) enc_tc_fwd_kernel(const __grid_constant__ EncTcParams P) {
+  extern __shared__ __align__(1024) unsigned char smb[];
+  float* smf = reinterpret_cast<float*>(smb);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int q = warp & 3, hh = warp >> 2;
+  const int p = 32 * q + lane;
+  const int K0 = P.K0, KX = P.KX, Hc = P.Hc, Oc = P.Oc;
+  const long long B = P.B;
+  float* B1 = smf + (P.f_b1 >> 2);
+  float* RED = smf + (P.f_red >> 2);
+  int* OROW = reinterpret_cast<int*>(smb + P.f_orow);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smb + P.o_bar);
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(smb + P.o_bar + 8);
+
+  for (int e = tid; e < (P.total >> 2); e += ENT) smf[e] = 0.0f;
+  __syncthreads();
+  if (tid == 0) {
+    tc::mbar_init(bar, 1);
+    tc::mbar_fence_init();
+  }
+  __syncwarp();
+  if (warp == 0) tc::tmem_alloc(tptr, 512);
+
+  const float* prm = P.params;
+  // hidden unit n of the concatenated first layers: unit u(n), local index; column K0 of the operand carries the bias
+  auto unit_of_h = [&](int n, int& local) -> int {
+    int u = 0;
+    while (u + 1 < P.n_units && n >= P.h_off[u + 1]) ++u;
+    local = n - P.h_off[u];
+    return u;
+  };
+  auto g_w0 = [&](int n, int k) -> float {
+    int l;
+    const int u = unit_of_h(n, l);
+    if (k < K0) return prm[P.g_w0[u] + (long long)l * K0 + k];
+    return k == K0 ? prm[P.g_b0[u] + l] : 0.0f;
+  };
+  // head row o of the concatenated (block-diagonal) heads
+  auto unit_of_o = [&](int o, int& local) -> int {
+    for (int u = 0; u < P.n_units; ++u)
+      if (o >= P.o_off[u] && o < P.o_off[u] + P.O[u]) {
+        local = o - P.o_off[u];
+        return u;
+      }
+    local = 0;
+    return -1;
+  };
+  auto g_w1 = [&](int o, int k) -> float {
+    int l, lk;
+    const int u = unit_of_o(o, l);
+    if (u < 0) return 0.0f;
+    const int uk = unit_of_h(k, lk);
+    return uk == u ? prm[P.g_w1[u] + (long long)l * P.H[u] + lk] : 0.0f;
+  };
+  const int k_w0 = scale_exp_e(block_absmax_e(Hc * KX, [&](int e) { return g_w0(e / KX, e % KX); }, RED));
+  const int k_w1 = scale_exp_e(block_absmax_e(Oc * Hc, [&](int e) { return g_w1(e / Hc, e % Hc); }, RED));
+  stage_weight_e(smb + P.w_0, P.l_0, Hc, KX, k_w0, g_w0);
+  stage_weight_e(smb + P.w_1, P.l_1, Oc, Hc, k_w1, g_w1);
+  for (int o = tid; o < Oc; o += ENT) {
+    int l;
+    const int u = unit_of_o(o, l);
+    B1[o] = u >= 0 ? prm[P.g_b1[u] + l] : 0.0f;
+    OROW[o] = u >= 0 ? P.out_row[u] + l : -1;
+  }
+  tc::fence_async_smem();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tb = *tptr;
+  const uint32_t trow = tb + ((uint32_t)(32 * q) << 16);
+  const uint32_t C_H = 0, C_A = (uint32_t)Hc, C_O = (uint32_t)(2 * Hc);   // accumulator, packed hidden operand, heads
+  uint32_t phase = 0;
+  const float inv0 = exp2f(-(float)(k_w0 + E_X)), inv1 = exp2f(-(float)(k_w1 + E_HID));
+  const float s_x = exp2f((float)E_X), s_h = exp2f((float)E_HID);
+  unsigned char* pX = smb + P.a_x;
+  tc::Op oX, oW0, oW1;
+  oX.base = tc::smem_u32(pX); oX.lo_off = P.l_x; oX.R = TP;
+  oW0.base = tc::smem_u32(smb + P.w_0); oW0.lo_off = P.l_0; oW0.R = Hc;
+  oW1.base = tc::smem_u32(smb + P.w_1); oW1.lo_off = P.l_1; oW1.R = Oc;
+  const int hcols = Hc >> 1, ocols = Oc >> 1;   // columns per thread (multiples of 8)
+  const long long ntiles = (B + TP - 1) / TP;
+
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long row0 = tile * TP;
+    const long long lrow = row0 + p;
+    const bool valid = lrow < B;
+    // ---- x tile: standardise, scale, split -> X8 operand (thread = row x half of the columns) ----
+    {
+      const long long drow = valid ? (P.idx ? P.idx[lrow] : lrow) : 0;
+      const float* xr = P.x + drow * K0 + hh * (K0 >> 1);
+      const int nch = K0 >> 4;  // chunks of 8 columns per thread
+      for (int c = 0; c < nch; ++c) {
+        float v[8];
+        const int k0 = hh * (K0 >> 1) + 8 * c;
+        if (valid) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(xr + 8 * c)), b = __ldg(reinterpret_cast<const float4*>(xr + 8 * c) + 1);
+          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float t = P.x_is_standardised ? v[i] : (v[i] - P.mean_x[k0 + i]) / P.std_x[k0 + i];
+            v[i] = t * s_x;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = 0.0f;
+        }
+        put8e(pX, P.l_x, TP, k0 >> 3, p, v);
+      }
+      if (hh == 0) {  // constant-one column (bias of the first layers) + zero padding up to KX
+        float v[8] = {s_x, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        put8e(pX, P.l_x, TP, K0 >> 3, p, v);
+      } else {
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        put8e(pX, P.l_x, TP, (K0 >> 3) + 1, p, v);
+      }
+    }
+    // ---- hidden layers of all units: one MMA series, N = Hc ----
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      tc::fence_after_sync();
+      tc::issue_fwd(tb + C_H, oX, oW0, Hc, KX, 0, 3);
+      tc::commit(bar);
+    }
+    __syncwarp();
+    tc::mbar_wait(bar, phase);
+    phase ^= 1u;
+    __syncwarp();
+    tc::fence_after_sync();
+    // ---- ReLU epilogue: packed fp16 hi / lo planes -> tensor memory (A operand of the heads) [+ global record] ----
+    {
+      unsigned char* hrec = P.hidrec ? P.hidrec + (long long)tile * P.hid_stride : nullptr;
+      for (int c = 0; c < (hcols >> 3); ++c) {
+        const int k0 = hh * hcols + 8 * c;
+        float v[8];
+        tc::tmem_ld8(trow + C_H + k0, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i] * inv0, 0.0f) * s_h;
+        uint4 hi, lo;
+        tc::split8(v, hi, lo);
+        float ph[4] = {__uint_as_float(hi.x), __uint_as_float(hi.y), __uint_as_float(hi.z), __uint_as_float(hi.w)};
+        float pl[4] = {__uint_as_float(lo.x), __uint_as_float(lo.y), __uint_as_float(lo.z), __uint_as_float(lo.w)};
+        tc::tmem_st4(trow + C_A + (k0 >> 1), ph);
+        tc::tmem_st4(trow + C_A + (Hc >> 1) + (k0 >> 1), pl);
+        if (hrec) {
+          *reinterpret_cast<uint4*>(hrec + ((size_t)(k0 >> 3) * TP + p) * 16) = hi;
+          *reinterpret_cast<uint4*>(hrec + P.hid_lo + ((size_t)(k0 >> 3) * TP + p) * 16) = lo;
+        }
+      }
+    }
+    // ---- heads: A from tensor memory ----
+    tc::fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      tc::fence_after_sync();
+      const uint32_t idesc = tc::make_idesc(128, Oc, 0, 0);
+      uint32_t acc = 0;
+      for (int t = 0; t < 3; ++t) {
+        const uint32_t abase = tb + C_A + (t == 1 ? (uint32_t)(Hc >> 1) : 0u);
+        const uint32_t wb = oW1.base + (t == 2 ? oW1.lo_off : 0u);
+        for (int k = 0; k < Hc; k += 16) {
+          tc::mma_f16_ts(tb + C_O, abase + (uint32_t)(k >> 1), tc::desc_kmajor(wb, Oc, k >> 3), idesc, acc);
+          acc = 1;
+        }
+      }
+      tc::commit(bar);
+    }
+    __syncwarp();
+    tc::mbar_wait(bar, phase);
+    phase ^= 1u;
+    __syncwarp();
+    tc::fence_after_sync();
+    // ---- head pre-activations out: headpre[row(o)][B], coalesced along the minibatch rows ----
+    for (int c = 0; c < (ocols >> 3); ++c) {
+      const int o0 = hh * ocols + 8 * c;
+      float v[8];
+      tc::tmem_ld8(trow + C_O + o0, v);
+      if (valid) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = OROW[o0 + i];
+          if (r >= 0) P.headpre[(long long)r * B + lrow] = v[i] * inv1 + B1[o0 + i];
+        }
+      }
+    }
+    tc::fence_before_sync();
+    __syncthreads();   // X operand / TMEM columns are reused by the next tile
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tb, 512);
+}
+
+void launch_enc_tc_fwd(const EncTcParams& p, int grid, cudaStream_t s) { enc_tc_fwd_kernel<<<grid, ENT, p.total, s>>>(p); }
+int configure_enc_tc_kernels() {
+  return (int)cudaFuncSetAttribute(enc_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+}
+
+}  // namespace dpv

@@ -112,6 +112,7 @@ size_t lat_smem_bytes(const DecParams& p, bool bwd);
 void launch_lat_fwd(const DecParams& p, long long n_tiles, cudaStream_t s);
 void launch_lat_bwd(const DecParams& p, long long n_tiles, cudaStream_t s);
 int configure_lat_kernels();
+void launch_lat_encode(const DecParams& p, cudaStream_t s);
 bool dec_tc_has_variant(int phys_kind, int nd_x);
 
 // ---- encoder-side kernels (forward and backward over "MLP2 units") ------------------------------
@@ -141,6 +142,27 @@ struct EncParams {
   long long n_params;
   int with_hid;     // forward: also store hidden activations (needed by the backward)
 };
+
+// ---- tensor-core encoder kernels (enc_tc_kernels.cu) ----------------------------------------------
+struct EncTcParams {
+  int n_units, K0, KX, Hc, Oc, terms;
+  int H[3], O[3], h_off[4], o_off[3], out_row[3];
+  long long g_w0[3], g_b0[3], g_w1[3], g_b1[3];
+  float mean_x[64], std_x[64];
+  int x_is_standardised;
+  const float* params;
+  const float* x;
+  const long long* idx;
+  long long B;
+  float* headpre;
+  unsigned char* hidrec;   // optional per-tile record of the hidden activations (X8 hi/lo planes) for the backward
+  long long hid_stride;
+  int hid_lo;
+  // shared-memory plan (bytes)
+  int w_0, l_0, w_1, l_1, a_x, l_x, f_b1, f_red, f_orow, o_bar, total;
+};
+void launch_enc_tc_fwd(const EncTcParams& p, int grid, cudaStream_t s);
+int configure_enc_tc_kernels();
 
 // ---- reduce + Adam ------------------------------------------------------------------------------
 struct ReduceParams {

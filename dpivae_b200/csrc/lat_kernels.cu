@@ -393,6 +393,62 @@ __global__ void __launch_bounds__(LNT) lat_bwd_kernel(const __grid_constant__ De
   }
 }
 
+// Encode-only inference (models/vae.py:161-162, 125-151): one thread per (MC sample, row) pair, head pre-activations read
+// feature-major (coalesced along the rows), latents and density written in the reference's (n, B, .) layout.  No
+// decoder, no priors: the HBM-streaming kernel of BASELINE.json config 5.
+__global__ void __launch_bounds__(LNT) lat_encode_kernel(const __grid_constant__ DecParams P) {
+  extern __shared__ __align__(16) float lsm[];   // EPS[Z][LNT]
+  const int tid = threadIdx.x;
+  const long long B = P.B;
+  const long long q = (long long)blockIdx.x * LNT + tid;
+  if (q >= (long long)P.n_mc * B) return;
+  const long long m = q / B, r = q - m * B;
+  const unsigned long long grow = (unsigned long long)(P.row_off + r);
+  for (int i = 0; i < P.Z; ++i) {
+    const int b = block_of_l(P, i), il = i - P.blk_start[b], nzb = P.blk_size[b];
+    const unsigned long long li = ((unsigned long long)m * (unsigned long long)P.Bg + grow) * nzb + il;
+    lsm[i * LNT + tid] = P.rng.mode == 0 ? P.rng.eps[b][li] : philox_normal_l(P.rng.seed, P.rng.offset[b], P.rng.grid_threads[b], li);
+  }
+  float dens = 0.0f;
+  for (int b = 0; b < P.n_blk; ++b) {
+    const int s = P.blk_start[b], nzb = P.blk_size[b];
+    float ss = 0.0f, hld = 0.0f, ld1 = 0.0f, ld2 = 0.0f;
+    for (int i = 0; i < nzb; ++i) {
+      float acc = clampf_(P.headpre[(long long)(P.henc[b] + i) * B + r], -50.0f, 50.0f);
+      for (int j = 0; j < i; ++j) {
+        const float lij = clampf_(P.headpre[(long long)(P.henc[b] + 2 * nzb + i * nzb + j) * B + r], -20.0f, 20.0f);
+        acc = fmaf(lij, lsm[(s + j) * LNT + tid], acc);
+      }
+      const float lii = expf(clampf_(P.headpre[(long long)(P.henc[b] + nzb + i) * B + r], -7.0f, 3.0f)) + 1e-8f;
+      const float e = lsm[(s + i) * LNT + tid];
+      acc = fmaf(lii, e, acc);
+      ss = fmaf(e, e, ss);
+      hld += logf(lii);
+      const int gi = s + i;
+      if (gi < P.nz_x) {
+        const float u = sigmoidf_(acc);
+        const float a = P.ub[gi] - P.lb[gi];
+        ld1 += acc - 2.0f * softplusf_(acc);
+        ld2 += logf(fabsf(a));
+        if (P.out.zx) P.out.zx[q * P.nz_x + gi] = fmaf(u, a, P.lb[gi]);
+      } else if (gi < P.nz_x + P.nz_c) {
+        if (P.out.zc) P.out.zc[q * P.nz_c + (gi - P.nz_x)] = acc;
+      } else {
+        if (P.out.zy) P.out.zy[q * P.nz_y + (gi - P.nz_x - P.nz_c)] = acc;
+      }
+    }
+    const float lq = -0.5f * ((float)nzb * LOG_2PI + ss) - hld;
+    if (b == 0) dens = lq - (ld1 + ld2);
+    else dens += lq;
+  }
+  if (P.out.dens) P.out.dens[q] = dens;
+}
+
+void launch_lat_encode(const DecParams& p, cudaStream_t s) {
+  const long long total = (long long)p.n_mc * p.B;
+  lat_encode_kernel<<<(unsigned)((total + LNT - 1) / LNT), LNT, (size_t)p.Z * LNT * sizeof(float), s>>>(p);
+}
+
 size_t lat_smem_bytes(const DecParams& p, bool bwd) { return (size_t)lat_smem_floats(p, bwd) * sizeof(float); }
 void launch_lat_fwd(const DecParams& p, long long n_tiles, cudaStream_t s) {
   lat_fwd_kernel<<<(unsigned)n_tiles, LNT, lat_smem_bytes(p, false), s>>>(p);

@@ -60,6 +60,17 @@ __device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64
       : "memory");
 }
 
+// same with the A operand in tensor memory (128 lanes x K/2 packed 32-bit columns: column j = halves (2j, 2j+1))
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 __device__ __forceinline__ void commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -162,6 +173,12 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
   tmem_wait_st();
 }
 
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const float* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(__float_as_uint(v[0])),
+               "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3]))
+               : "memory");
+  tmem_wait_st();
+}
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
                "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),

@@ -148,3 +148,22 @@ def test_tc_training_tracks_fp32_kernel():
     for k in finals["fp32"]:
         err = gu.rel_l2(finals["tc_fp16x3"][k].cpu(), finals["fp32"][k].cpu())
         assert err < 1e-4, (k, err)
+
+
+@pytest.mark.parametrize("case,mtype", gu.CONFIGS)
+def test_tc_encoder_forward_and_encode(case, mtype):
+    """Tensor-core ENCODER kernel (enc_tc_fwd_kernel, used by forward / validation / encode-only calls in the tensor-core
+    modes): all 10 forward outputs and the encode-only latents against the reference's golden forward, 1e-5."""
+    g, spec, sd, args, case_mod, vae, (x, c, y) = build_from_golden(case, mtype)
+    n = g["eps0"].shape[0]
+    vae.engine().set_math_mode("tc_fp16x3")
+    with vae.inject_noise(_dev_eps(g, spec)):
+        fw = vae.forward(x.cuda(), c.cuda(), cond=False, n=n)
+        x_t = vae.transform_inputs(x.cuda())[0]
+        zx, zc, zy, dens = vae.encode(x_t, n=n)
+    for name, t in zip(gu.FW_NAMES, fw):
+        err = gu.rel_l2(t.cpu(), g[f"fw.{name}"])
+        assert err < 1e-5, (name, err)
+    for name, t in (("zx", zx), ("zc", zc), ("zy", zy), ("dens_z", dens)):
+        err = gu.rel_l2(t.cpu(), g[f"fw.{name}"])
+        assert err < 1e-5, (name, err)

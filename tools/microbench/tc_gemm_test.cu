@@ -40,11 +40,43 @@ __global__ void __launch_bounds__(128, 1) test_kernel(int mode, int terms, const
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
+  if (mode == 3) {
+    // stage A (row = this thread's TMEM lane) as packed halves: hi plane then lo plane
+    const uint32_t tb0 = *tptr;
+    const int row = tid;
+    for (int c0 = 0; c0 < CX; c0 += 16) {
+      float vh[8], vl[8];
+      for (int j = 0; j < 8; ++j) {
+        const float a0 = X[row * CX + c0 + 2 * j], a1 = X[row * CX + c0 + 2 * j + 1];
+        const __half2 h = __floats2half2_rn(a0, a1);
+        const float2 hf = __half22float2(h);
+        const __half2 l = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
+        vh[j] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h));
+        vl[j] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&l));
+      }
+      tc::tmem_st8(tb0 + ((uint32_t)((tid >> 5) * 32) << 16) + 64 + c0 / 2, vh);
+      tc::tmem_st8(tb0 + ((uint32_t)((tid >> 5) * 32) << 16) + 64 + CX / 2 + c0 / 2, vl);
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
   const uint32_t tbase = *tptr;
   const tc::Op xo{tc::smem_u32(Xh), (uint32_t)((CX / 8) * RX * 16), RX}, yo{tc::smem_u32(Yh), (uint32_t)((CY / 8) * RY * 16), RY};
   if (tid == 0) {
     if (mode == 0) tc::issue_fwd(tbase, xo, yo, RY, CX, 0, terms);
     if (mode == 1) tc::issue_dgrad(tbase, xo, yo, RY, CY, 0, terms);
+    if (mode == 3) {
+      // A from tensor memory (columns 64.. : hi plane K/2 columns, then lo plane), W K-major in shared memory
+      const uint32_t idesc = tc::make_idesc(128, RY, 0, 0);
+      uint32_t acc = 0;
+      for (int t = 0; t < terms; ++t)
+        for (int k = 0; k < CX; k += 16) {
+          const uint32_t a_t = tbase + 64 + (t == 1 ? CX / 2 : 0) + k / 2;
+          tc::mma_f16_ts(tbase, a_t, tc::desc_kmajor(yo.base + (t == 2 ? yo.lo_off : 0u), RY, k >> 3), idesc, acc);
+          acc = 1;
+        }
+    }
     if (mode == 2) {
       tc::issue_wgrad(tbase, xo, yo, CY, 0, terms);
       tc::issue_wgrad(tbase, xo, yo, CY, 1, terms);  // second pass accumulates: result = 2x
@@ -82,7 +114,7 @@ static void run(const char* name, int mode, int terms, int RX, int CX, int RY, i
   for (int m = 0; m < 128; ++m)
     for (int n = 0; n < ND; ++n) {
       double s = 0;
-      if (mode == 0) for (int k = 0; k < CX; ++k) s += (double)X[m * CX + k] * Y[n * CY + k];
+      if (mode == 0 || mode == 3) for (int k = 0; k < CX; ++k) s += (double)X[m * CX + k] * Y[n * CY + k];
       if (mode == 1) for (int k = 0; k < CX; ++k) s += (double)X[m * CX + k] * Y[k * CY + n];
       if (mode == 2) { for (int r = 0; r < RX; ++r) s += (double)X[r * CX + m] * Y[r * CY + n]; s *= 2; }
       ref[m * ND + n] = s;
@@ -122,6 +154,8 @@ int main() {
     run("dgrad M128 Nout64 Kin32", 1, terms, 128, 64, 64, 32, 32);
     run("wgrad R128 M128 N64", 2, terms, 128, 128, 128, 64, 64);
     run("wgrad R128 M128 N16", 2, terms, 128, 128, 128, 16, 16);
+    run("fwd A-in-TMEM N64 K64", 3, terms, 128, 64, 64, 64, 64);
+    run("fwd A-in-TMEM N32 K128", 3, terms, 128, 128, 32, 128, 32);
   }
   // small-magnitude operands (precision of the lo halves near the fp16 subnormal range)
   run("fwd small x (1e-2) K64", 0, 3, 128, 64, 64, 64, 64, 1e-2f, 1.f);
