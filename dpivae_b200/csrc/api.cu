@@ -48,7 +48,7 @@ struct dpivae_model {
   int last_launches = 0;
   long long part_stride = 0;
   EncTcParams enc_tc;       // tensor-core encoder plan
-  int enc_tc_ok = 0;
+  int enc_tc_ok = 0, enc_tc_bwd_ok = 0;
   int math_mode = 0;        // DPIVAE_MATH_*
   TcParams tc;              // tensor-core decoder plan
   int tc_ok = 0;            // model shape supported by dec_tc_kernel
@@ -295,6 +295,19 @@ static int build_plan(dpivae_model* h) {
     Q.hid_lo = (Q.Hc / 8) * 128 * 16;
     Q.hid_stride = 2 * (long long)Q.hid_lo;
     if (ok && Q.total <= 232448) h->enc_tc_ok = 1;
+    // backward plan
+    b = 0;
+    plane2(Q.Hc / 8, Q.Oc, Q.wb_1, Q.lb_1);
+    Q.ab_h = b; b += (int)Q.hid_stride;
+    plane2(Q.Oc / 8, 128, Q.ab_g, Q.lb_g);
+    plane2(Q.KX / 8, 128, Q.ab_x, Q.lb_x);
+    Q.fb_orow = b; b += Q.Oc * 4;
+    Q.fb_red = b; b += 256;
+    Q.ob_bar = b; b += 32;
+    Q.total_b = (b + 127) & ~127;
+    const int nchunk = Q.Hc > 128 ? 2 : 1;
+    h->enc_tc_bwd_ok = h->enc_tc_ok && Q.total_b <= 232448 && Q.Oc <= 64 && Q.Hc + nchunk * (Q.Oc + Q.KX) <= 512 &&
+                       256 * 32 * 4 <= (int)Q.hid_stride;
   }
 
   // ---- shared-memory plan of the tensor-core decoder kernel (byte offsets) ----
@@ -365,10 +378,11 @@ int dpivae_create(const dpivae_model_desc_t* desc, dpivae_handle_t* out) {
   std::vector<unsigned char> owner((size_t)desc->n_params, 0);
   for (int u = 0; u < h->enc.n_units; ++u) {
     const EncUnit& U = h->enc.u[u];
-    for (long long e = 0; e < (long long)U.K0 * U.H; ++e) owner[U.g_w0 + e] = 1;
-    for (long long e = 0; e < U.H; ++e) owner[U.g_b0 + e] = 1;
-    for (long long e = 0; e < (long long)U.H * U.O; ++e) owner[U.g_w1 + e] = 1;
-    for (long long e = 0; e < U.O; ++e) owner[U.g_b1 + e] = 1;
+    const unsigned char cls = u < h->n_enc_units ? 2 : 1;
+    for (long long e = 0; e < (long long)U.K0 * U.H; ++e) owner[U.g_w0 + e] = cls;
+    for (long long e = 0; e < U.H; ++e) owner[U.g_b0 + e] = cls;
+    for (long long e = 0; e < (long long)U.H * U.O; ++e) owner[U.g_w1 + e] = cls;
+    for (long long e = 0; e < U.O; ++e) owner[U.g_b1 + e] = cls;
   }
   CUDA_OK(cudaMalloc(&h->d_owner, owner.size()));
   CUDA_OK(cudaMemcpy(h->d_owner, owner.data(), owner.size(), cudaMemcpyHostToDevice));
@@ -434,7 +448,7 @@ int dpivae_set_groups(dpivae_handle_t h, int32_t n_groups, const int64_t* begin,
 }
 
 struct WsLayout {
-  size_t hid, headpre, gpre, rowloss, part, scal, rec, dzrec, epsbuf, rowkl, total;
+  size_t hid, headpre, gpre, rowloss, part, scal, rec, dzrec, epsbuf, rowkl, hidrec, total;
   int grid_enc, grid_dec, RB, n_chunks;
   long long n_rowblocks;
   int tc_RB, tc_grid;           // tensor-core decoder kernel: rows per 128-pair tile, CTAs
@@ -467,7 +481,7 @@ static WsLayout ws_layout(dpivae_handle_t h, int64_t B, int32_t n_mc) {
   if (L.grid_enc < 1) L.grid_enc = 1;
   if (L.grid_dec < 1) L.grid_dec = 1;
 
-  L.part = take((size_t)(3 * h->sm_count) * h->part_stride);
+  L.part = take((size_t)(4 * h->sm_count) * h->part_stride);
   L.scal = take(16);
   L.rec = L.dzrec = L.epsbuf = L.rowkl = 0;
   if (h->tc_ok && n_mc >= 8 && n_mc <= 128) {
@@ -478,6 +492,8 @@ static WsLayout ws_layout(dpivae_handle_t h, int64_t B, int32_t n_mc) {
     L.epsbuf = take(nt * (size_t)Z * 128);
     L.rowkl = take((size_t)B);
   }
+  L.hidrec = 0;
+  if (h->enc_tc_bwd_ok) L.hidrec = take((size_t)((B + 127) / 128) * (size_t)h->enc_tc.hid_stride / 4);
   L.total = o;
   return L;
 }
@@ -533,16 +549,17 @@ static int run_loss(dpivae_handle_t h, const dpivae_batch_t* bt, const dpivae_rn
   h->ev_used[5] = h->ev_used[6] = 0;
   // encoder forward: tensor-core kernel for the encoder units (+ the FFMA kernel for the two prior nets) in the
   // tensor-core math modes when no backward follows; the FFMA kernel for everything otherwise
-  const bool enc_tc = h->math_mode != DPIVAE_MATH_FP32 && h->enc_tc_ok && !with_grad;
+  const bool enc_tc = h->math_mode != DPIVAE_MATH_FP32 && h->enc_tc_ok && (!with_grad || h->enc_tc_bwd_ok);
+  const long long nt128 = (bt->B + 127) / 128;
+  const int grid_etc = (int)(nt128 < h->sm_count ? nt128 : h->sm_count);
   {
     KTimer t(h, 0, st);
     if (enc_tc) {
       EncTcParams Q = h->enc_tc;
       Q.params = h->params; Q.x = bt->x; Q.idx = (const long long*)bt->idx; Q.B = bt->B;
-      Q.headpre = headpre; Q.hidrec = nullptr; Q.x_is_standardised = x_std;
+      Q.headpre = headpre; Q.hidrec = with_grad ? (unsigned char*)(base + L.hidrec) : nullptr; Q.x_is_standardised = x_std;
       Q.terms = h->math_mode == DPIVAE_MATH_TC_FP16X3 ? 3 : 1;
-      const long long nt = (bt->B + 127) / 128;
-      launch_enc_tc_fwd(Q, (int)(nt < h->sm_count ? nt : h->sm_count), st);
+      launch_enc_tc_fwd(Q, grid_etc, st);
       ++launches;
       if (!latent_only) {
         EncParams E2 = E;
@@ -603,13 +620,33 @@ static int run_loss(dpivae_handle_t h, const dpivae_batch_t* bt, const dpivae_rn
   ++launches;
 
   if (with_grad) {
-    { KTimer t(h, 2, st); launch_enc_bwd(E, L.grid_enc, enc_smem, st); }
-    ++launches;
+    KTimer t(h, 2, st);
+    if (enc_tc) {
+      EncTcParams Q = h->enc_tc;
+      Q.params = h->params; Q.x = bt->x; Q.idx = (const long long*)bt->idx; Q.B = bt->B;
+      Q.x_is_standardised = x_std; Q.hidrec = (unsigned char*)(base + L.hidrec); Q.gpre = gpre;
+      Q.part = part + (long long)(grid_dec + L.grid_enc) * h->part_stride; Q.part_stride = h->part_stride;
+      // gpre ~ O(1) / (B_global * D): bring it to O(16) before the fp16 split
+      Q.e_g = (int)lrint(log2((double)bt->B_global * (double)(h->d.nd_x + h->d.nd_c + h->d.nd_y))) + 4;
+      launch_enc_tc_bwd(Q, grid_etc, st);
+      ++launches;
+      EncParams E2 = E;
+      E2.n_units = E.n_units - h->n_enc_units;
+      for (int u = 0; u < E2.n_units; ++u) E2.u[u] = E.u[h->n_enc_units + u];
+      launch_enc_bwd(E2, L.grid_enc, enc_smem, st);
+      ++launches;
+    } else {
+      launch_enc_bwd(E, L.grid_enc, enc_smem, st);
+      ++launches;
+    }
   }
   if (!latent_only) {
     ReduceParams R;
     R.part = part; R.part_stride = h->part_stride;
-    R.n_cta_dec = grid_dec; R.n_cta_enc = L.grid_enc;
+    R.n_cta[0] = grid_dec; R.base[0] = 0;
+    R.n_cta[1] = L.grid_enc; R.base[1] = grid_dec;
+    if (with_grad && enc_tc) { R.n_cta[2] = grid_etc; R.base[2] = grid_dec + L.grid_enc; }
+    else { R.n_cta[2] = L.grid_enc; R.base[2] = grid_dec; }
     R.n_params = h->d.n_params;
     R.owner = h->d_owner;
     R.grads = with_grad ? h->grads : nullptr;

@@ -263,9 +263,286 @@ __global__ void __launch_bounds__(ENT, 1) enc_tc_fwd_kernel(const __grid_constan
   if (warp == 0) tc::tmem_dealloc(tb, 512);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Backward of the encoder units: per 128-row tile
+//   G   = gpre tile (gradients w.r.t. the head pre-activations, written by lat_bwd_kernel), scaled by 2^e_g, X8 hi/lo
+//   HID = hidden activations of the forward (bulk-copied record, already X8 hi/lo, scale 2^E_HID)
+//   wgrad heads : D_W1[chunk][k][o] += sum_r HID[r][k] G[r][o]            (A, B MN-major; hidden in chunks of 128)
+//   dgrad heads : GH[r][k] = sum_o G[r][o] W1[o][k], masked by HID > 0    (epilogue overwrites HID in place)
+//   wgrad layer0: D_W0[chunk][k][j] += sum_r GH[r][k] X[r][j]             (constant-one column of X -> bias gradient)
+// Weight gradients stay in tensor memory across all tiles of the CTA.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ENT, 1) enc_tc_bwd_kernel(const __grid_constant__ EncTcParams P) {
+  extern __shared__ __align__(1024) unsigned char smb[];
+  float* smf = reinterpret_cast<float*>(smb);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int q = warp & 3, hh = warp >> 2;
+  const int p = 32 * q + lane;
+  const int K0 = P.K0, KX = P.KX, Hc = P.Hc, Oc = P.Oc;
+  const long long B = P.B;
+  float* RED = smf + (P.fb_red >> 2);
+  int* OROW = reinterpret_cast<int*>(smb + P.fb_orow);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smb + P.ob_bar);
+  uint64_t* hbar = bar + 1;
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(smb + P.ob_bar + 16);
+  float* part = P.part + (long long)blockIdx.x * P.part_stride;
+
+  for (int e = tid; e < (P.total_b >> 2); e += ENT) smf[e] = 0.0f;
+  __syncthreads();
+  if (tid == 0) {
+    tc::mbar_init(bar, 1);
+    tc::mbar_init(hbar, 1);
+    tc::mbar_fence_init();
+  }
+  __syncwarp();
+  if (warp == 0) tc::tmem_alloc(tptr, 512);
+  const float* prm = P.params;
+  auto unit_of_h = [&](int n, int& local) -> int {
+    int u = 0;
+    while (u + 1 < P.n_units && n >= P.h_off[u + 1]) ++u;
+    local = n - P.h_off[u];
+    return u;
+  };
+  auto unit_of_o = [&](int o, int& local) -> int {
+    for (int u = 0; u < P.n_units; ++u)
+      if (o >= P.o_off[u] && o < P.o_off[u] + P.O[u]) {
+        local = o - P.o_off[u];
+        return u;
+      }
+    local = 0;
+    return -1;
+  };
+  auto g_w1 = [&](int o, int k) -> float {
+    int l, lk;
+    const int u = unit_of_o(o, l);
+    if (u < 0) return 0.0f;
+    const int uk = unit_of_h(k, lk);
+    return uk == u ? prm[P.g_w1[u] + (long long)l * P.H[u] + lk] : 0.0f;
+  };
+  const int k_w1 = scale_exp_e(block_absmax_e(Oc * Hc, [&](int e) { return g_w1(e / Hc, e % Hc); }, RED));
+  stage_weight_e(smb + P.wb_1, P.lb_1, Oc, Hc, k_w1, g_w1);
+  for (int o = tid; o < Oc; o += ENT) {
+    int l;
+    const int u = unit_of_o(o, l);
+    OROW[o] = u >= 0 ? P.out_row[u] + l : -1;
+  }
+  // zero this CTA's partial gradients of the encoder units
+  for (int u = 0; u < P.n_units; ++u) {
+    for (long long e = tid; e < (long long)K0 * P.H[u]; e += ENT) part[P.g_w0[u] + e] = 0.0f;
+    for (int e = tid; e < P.H[u]; e += ENT) part[P.g_b0[u] + e] = 0.0f;
+    for (long long e = tid; e < (long long)P.H[u] * P.O[u]; e += ENT) part[P.g_w1[u] + e] = 0.0f;
+    for (int e = tid; e < P.O[u]; e += ENT) part[P.g_b1[u] + e] = 0.0f;
+  }
+  tc::fence_async_smem();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tb = *tptr;
+  const uint32_t trow = tb + ((uint32_t)(32 * q) << 16);
+  const int nchunk = Hc > 128 ? 2 : 1;
+  const int ch1 = Hc - 128;                       // first hidden column of the second (overlapping) chunk
+  const uint32_t C_GH = 0, C_W1 = (uint32_t)Hc, C_W0 = C_W1 + (uint32_t)(nchunk * Oc);
+  uint32_t phase = 0, hphase = 0;
+  const float sgp = exp2f((float)P.e_g);
+  const float inv1d = exp2f(-(float)k_w1);
+  const float s_x = exp2f((float)E_X);
+  unsigned char* pX = smb + P.ab_x;
+  unsigned char* pG = smb + P.ab_g;
+  unsigned char* pH = smb + P.ab_h;
+  tc::Op oX, oG, oH, oW1;
+  oX.base = tc::smem_u32(pX); oX.lo_off = P.lb_x; oX.R = TP;
+  oG.base = tc::smem_u32(pG); oG.lo_off = P.lb_g; oG.R = TP;
+  oH.base = tc::smem_u32(pH); oH.lo_off = P.hid_lo; oH.R = TP;
+  oW1.base = tc::smem_u32(smb + P.wb_1); oW1.lo_off = P.lb_1; oW1.R = Oc;
+  const int hcols = Hc >> 1, ocols = Oc >> 1;
+  const long long ntiles = (B + TP - 1) / TP;
+  float db1[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) db1[i] = 0.0f;
+  uint32_t wacc = 0;
+  const uint32_t hid_bytes = (uint32_t)P.hid_stride;
+  if (tid == 0 && (long long)blockIdx.x < ntiles) {
+    tc::mbar_expect_tx(hbar, hid_bytes);
+    tc::bulk_g2s(pH, P.hidrec + (long long)blockIdx.x * P.hid_stride, hid_bytes, hbar);
+  }
+
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long row0 = tile * TP;
+    const long long lrow = row0 + p;
+    const bool valid = lrow < B;
+    // ---- G operand: gpre rows of the encoder heads for this row, scaled; running sums for the head-bias gradients ----
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (c < (ocols >> 3)) {
+        const int o0 = hh * ocols + 8 * c;
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = OROW[o0 + i];
+          v[i] = (valid && r >= 0) ? P.gpre[(long long)r * B + lrow] * sgp : 0.0f;
+          db1[c * 8 + i] += v[i];
+        }
+        put8e(pG, P.lb_g, TP, o0 >> 3, p, v);
+      }
+    }
+    // ---- x tile (as in the forward) ----
+    {
+      const long long drow = valid ? (P.idx ? P.idx[lrow] : lrow) : 0;
+      const float* xr = P.x + drow * K0 + hh * (K0 >> 1);
+      const int nch = K0 >> 4;
+      for (int c = 0; c < nch; ++c) {
+        float v[8];
+        const int k0 = hh * (K0 >> 1) + 8 * c;
+        if (valid) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(xr + 8 * c)), b = __ldg(reinterpret_cast<const float4*>(xr + 8 * c) + 1);
+          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float t = P.x_is_standardised ? v[i] : (v[i] - P.mean_x[k0 + i]) / P.std_x[k0 + i];
+            v[i] = t * s_x;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = 0.0f;
+        }
+        put8e(pX, P.lb_x, TP, k0 >> 3, p, v);
+      }
+      if (hh == 0) {
+        float v[8] = {valid ? s_x : 0.0f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        put8e(pX, P.lb_x, TP, K0 >> 3, p, v);
+      } else {
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        put8e(pX, P.lb_x, TP, (K0 >> 3) + 1, p, v);
+      }
+    }
+    // ---- hidden record of this tile has landed? ----
+    tc::mbar_wait(hbar, hphase);
+    hphase ^= 1u;
+    __syncwarp();
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      tc::fence_after_sync();
+      for (int ck = 0; ck < nchunk; ++ck) {
+        tc::Op a = oH;
+        a.base += (uint32_t)(((ck ? ch1 : 0) >> 3) * TP) * 16u;
+        tc::issue_wgrad(tb + C_W1 + (uint32_t)(ck * Oc), a, oG, Oc, wacc, 3);
+      }
+      tc::issue_dgrad(tb + C_GH, oG, oW1, Oc, Hc, 0, 3);
+      tc::commit(bar);
+    }
+    __syncwarp();
+    tc::mbar_wait(bar, phase);
+    phase ^= 1u;
+    __syncwarp();
+    tc::fence_after_sync();
+    // ---- ReLU mask (from the hidden record) on the dgrad result, written over the record in place ----
+    for (int c = 0; c < (hcols >> 3); ++c) {
+      const int k0 = hh * hcols + 8 * c;
+      float g[8];
+      tc::tmem_ld8(trow + C_GH + k0, g);
+      const uint4 hv = *reinterpret_cast<const uint4*>(pH + ((size_t)(k0 >> 3) * TP + p) * 16);
+      const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t hbits = (hw[i >> 1] >> ((i & 1) * 16)) & 0x7FFFu;   // |hi half| : zero <=> ReLU inactive
+        g[i] = hbits != 0u ? g[i] * inv1d : 0.0f;
+      }
+      put8e(pH, P.hid_lo, TP, k0 >> 3, p, g);
+    }
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      tc::fence_after_sync();
+      for (int ck = 0; ck < nchunk; ++ck) {
+        tc::Op a = oH;
+        a.base += (uint32_t)(((ck ? ch1 : 0) >> 3) * TP) * 16u;
+        tc::issue_wgrad(tb + C_W0 + (uint32_t)(ck * KX), a, oX, KX, wacc, 3);
+      }
+      tc::commit(bar);
+    }
+    __syncwarp();
+    tc::mbar_wait(bar, phase);
+    phase ^= 1u;
+    __syncwarp();
+    tc::fence_after_sync();
+    wacc = 1u;
+    if (tid == 0 && tile + gridDim.x < ntiles) {
+      tc::fence_async_smem();
+      tc::mbar_expect_tx(hbar, hid_bytes);
+      tc::bulk_g2s(pH, P.hidrec + (tile + gridDim.x) * P.hid_stride, hid_bytes, hbar);
+    }
+    __syncthreads();
+  }
+
+  // ---- flush: weight gradients out of tensor memory (lane = hidden unit within the chunk) ----
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const float sc1 = exp2f(-(float)(E_HID + P.e_g)), sc0 = exp2f(-(float)(E_X + P.e_g));
+  for (int ck = 0; ck < nchunk; ++ck) {
+    const int k = (ck ? ch1 : 0) + p;                        // hidden column held by this TMEM lane
+    const bool mine = nchunk == 1 || (ck == 0 ? k < 128 : k >= 128);   // the overlap is taken from chunk 0
+    int lk;
+    const int uk = unit_of_h(k, lk);
+    // heads: columns o of unit uk
+    for (int c = 0; c < (ocols >> 3); ++c) {
+      const int o0 = hh * ocols + 8 * c;
+      float v[8];
+      tc::tmem_ld8(trow + C_W1 + (uint32_t)(ck * Oc) + o0, v);
+      if (mine) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int o = o0 + i;
+          if (o >= P.o_off[uk] && o < P.o_off[uk] + P.O[uk]) part[P.g_w1[uk] + (long long)(o - P.o_off[uk]) * P.H[uk] + lk] = v[i] * sc1;
+        }
+      }
+    }
+    // first layers: columns j < K0, bias in column K0
+    for (int c = hh; c < (KX >> 3); c += 2) {
+      float v[8];
+      tc::tmem_ld8(trow + C_W0 + (uint32_t)(ck * KX) + 8 * c, v);
+      if (mine) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int j = 8 * c + i;
+          if (j < K0) part[P.g_w0[uk] + (long long)lk * K0 + j] = v[i] * sc0;
+          else if (j == K0) part[P.g_b0[uk] + lk] = v[i] * sc0;
+        }
+      }
+    }
+  }
+  // head-bias gradients: per-thread running sums -> fixed-order sum over the 128 row slots
+  __syncthreads();
+  float* R0 = reinterpret_cast<float*>(pH);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) R0[tid * 32 + i] = db1[i];
+  __syncthreads();
+  if (tid < Oc) {
+    const int h2 = tid / ocols, i = tid - h2 * ocols;
+    int l;
+    const int u = unit_of_o(tid, l);
+    if (u >= 0 && i < 32) {
+      float s = 0.0f;
+      for (int j = 0; j < TP; ++j) s += R0[(h2 * TP + j) * 32 + i];
+      part[P.g_b1[u] + l] = s * exp2f(-(float)P.e_g);
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tb, 512);
+}
+
+void launch_enc_tc_bwd(const EncTcParams& p, int grid, cudaStream_t s) { enc_tc_bwd_kernel<<<grid, ENT, p.total_b, s>>>(p); }
+
 void launch_enc_tc_fwd(const EncTcParams& p, int grid, cudaStream_t s) { enc_tc_fwd_kernel<<<grid, ENT, p.total, s>>>(p); }
 int configure_enc_tc_kernels() {
-  return (int)cudaFuncSetAttribute(enc_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  int e = (int)cudaFuncSetAttribute(enc_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  if (!e) e = (int)cudaFuncSetAttribute(enc_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  return e;
 }
 
 }  // namespace dpv

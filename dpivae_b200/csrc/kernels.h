@@ -160,7 +160,14 @@ struct EncTcParams {
   int hid_lo;
   // shared-memory plan (bytes)
   int w_0, l_0, w_1, l_1, a_x, l_x, f_b1, f_red, f_orow, o_bar, total;
+  // backward kernel: inputs, plan
+  const float* gpre;
+  float* part;
+  long long part_stride;
+  int e_g;                 // gpre is scaled by 2^e_g before the fp16 split
+  int wb_1, lb_1, ab_h, ab_g, lb_g, ab_x, lb_x, fb_red, fb_orow, ob_bar, total_b;
 };
+void launch_enc_tc_bwd(const EncTcParams& p, int grid, cudaStream_t s);
 void launch_enc_tc_fwd(const EncTcParams& p, int grid, cudaStream_t s);
 int configure_enc_tc_kernels();
 
@@ -168,9 +175,10 @@ int configure_enc_tc_kernels();
 struct ReduceParams {
   const float* part;
   long long part_stride;
-  int n_cta_dec, n_cta_enc;     // number of CTA partials written by each kernel
+  int n_cta[3];                 // number of CTA partials per owner class
+  long long base[3];            // first partial vector (in units of part_stride) of each owner class
   long long n_params;
-  const unsigned char* owner;   // per param: 0 = decoder kernel wrote it, 1 = encoder kernel
+  const unsigned char* owner;   // per param: 0 = decoder kernel, 1 = prior-net units, 2 = encoder units
   float* grads;
   float* scalars;               // 8 floats
   float inv_B, inv_BD;

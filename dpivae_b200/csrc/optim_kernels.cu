@@ -11,9 +11,9 @@ namespace dpv {
 __global__ void __launch_bounds__(256) reduce_kernel(const ReduceParams P) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (P.grads != nullptr && i < P.n_params) {
-    const bool enc = P.owner[i] != 0;
-    const float* base = P.part + (enc ? (long long)P.n_cta_dec * P.part_stride : 0ll) + i;
-    const int ncta = enc ? P.n_cta_enc : P.n_cta_dec;
+    const int cls = P.owner[i];
+    const float* base = P.part + P.base[cls] * P.part_stride + i;
+    const int ncta = P.n_cta[cls];
     float s = 0.0f;
     for (int c = 0; c < ncta; ++c) s += base[(long long)c * P.part_stride];
     P.grads[i] = s;
@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(256) reduce_kernel(const ReduceParams P) {
   if (blockIdx.x == 0 && threadIdx.x < 6 && P.scalars != nullptr) {
     const int k = threadIdx.x;
     float s = 0.0f;
-    for (int c = 0; c < P.n_cta_dec; ++c) s += P.part[(long long)c * P.part_stride + P.n_params + k];
+    for (int c = 0; c < P.n_cta[0]; ++c) s += P.part[(P.base[0] + c) * P.part_stride + P.n_params + k];
     // order: ELBO, KLx, KLc(0), KLy(0), Rx, Rc, Ry, reg
     if (k == 0) P.scalars[0] = s * P.inv_BD;
     else if (k == 1) { P.scalars[1] = s * P.inv_B; P.scalars[2] = 0.0f; P.scalars[3] = 0.0f; }
