@@ -12,6 +12,7 @@
 // most of the CTA idle at the next barrier.
 #pragma once
 #include <cuda_runtime.h>
+#include <curand_kernel.h>
 #include <stdint.h>
 
 namespace dpv {
@@ -30,6 +31,27 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf
 // torch.nn.functional.softplus(beta=1, threshold=20)
 __device__ __forceinline__ float softplusf_(float x) { return x > 20.0f ? x : log1pf(expf(x)); }
 __device__ __forceinline__ float clampf_(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+
+// One element of torch.cuda's normal_() stream (ATen/native/cuda/DistributionTemplates.h,
+// distribution_elementwise_grid_stride_kernel): thread `sub` of a grid of T threads draws 4 normals per
+// curand_normal4 call; call number `it` serves elements sub + T * (4 it + comp).  Equivalent to
+//   curand_init(seed, sub, offset + 4 it, &st); curand_normal4(&st)[comp]
+// but with ONE Philox4x32-10 evaluation and ONE Box-Muller pair instead of the four evaluations curand_init +
+// curand4 perform (skipahead_sequence, skipahead, the draw and the look-ahead): counter = (offset / 4 + it, sub),
+// key = seed; offsets of torch's generator are multiples of 4, so curand's intra-counter position is 0.
+// Bitwise identity with torch is pinned by tests/test_gpu_parity.py::test_philox_reproduces_torch_cuda_stream.
+__device__ __forceinline__ float philox_normal_elem(unsigned long long seed, unsigned long long offset, unsigned int T,
+                                                    unsigned long long li) {
+  const unsigned long long sub = li % T;
+  const unsigned long long q4 = li / T;
+  const unsigned long long n = (offset >> 2) + (q4 >> 2);
+  const int comp = (int)(q4 & 3ull);
+  const uint4 ctr = make_uint4((unsigned int)n, (unsigned int)(n >> 32), (unsigned int)sub, (unsigned int)(sub >> 32));
+  const uint2 key = make_uint2((unsigned int)seed, (unsigned int)(seed >> 32));
+  const uint4 r = curand_Philox4x32_10(ctr, key);
+  const float2 g = _curand_box_muller(comp < 2 ? r.x : r.z, comp < 2 ? r.y : r.w);
+  return (comp & 1) ? g.y : g.x;
+}
 
 // contiguous vector load / store of V floats (V = 1, 2, 4) from shared memory
 template <int V>

@@ -35,20 +35,6 @@ enum { PH_SETUP = 0, PH_ROWPAR, PH_EPS, PH_LATENT_FWD, PH_AUX_FWD, PH_AUX_LOSS, 
     }                                                     \
   } while (0)
 
-__device__ __forceinline__ float philox_normal(unsigned long long seed, unsigned long long offset, unsigned int T,
-                                               unsigned long long li) {
-  // torch.cuda normal_(): thread `sub` of a grid of T threads draws 4 normals per curand_normal4
-  // call; call number `it` serves elements sub + T*(4*it + comp)
-  // (ATen/native/cuda/DistributionTemplates.h, distribution_elementwise_grid_stride_kernel).
-  const unsigned long long sub = li % T;
-  const unsigned long long q4 = li / T;
-  const unsigned long long it = q4 >> 2;
-  const int comp = (int)(q4 & 3ull);
-  curandStatePhilox4_32_10_t st;
-  curand_init(seed, sub, offset + 4ull * it, &st);
-  const float4 r = curand_normal4(&st);
-  return comp == 0 ? r.x : (comp == 1 ? r.y : (comp == 2 ? r.z : r.w));
-}
 
 __device__ __forceinline__ void zero_range(float* p, long long cnt) {
   for (long long e = threadIdx.x; e < cnt; e += NT) p[e] = 0.0f;
@@ -233,7 +219,7 @@ __global__ void __launch_bounds__(NT, 1) dec_kernel(const __grid_constant__ DecP
           const unsigned long long grow = (unsigned long long)(P.row_off + row0 + r);
           const int b = block_of(P, i), il = i - P.blk_start[b], nzb = P.blk_size[b];
           const unsigned long long li = ((unsigned long long)m * (unsigned long long)P.Bg + grow) * nzb + il;
-          v = P.rng.mode == 0 ? P.rng.eps[b][li] : philox_normal(P.rng.seed, P.rng.offset[b], P.rng.grid_threads[b], li);
+          v = P.rng.mode == 0 ? P.rng.eps[b][li] : philox_normal_elem(P.rng.seed, P.rng.offset[b], P.rng.grid_threads[b], li);
         }
         EPS[i * LDP + p] = v;
       }
@@ -246,7 +232,7 @@ __global__ void __launch_bounds__(NT, 1) dec_kernel(const __grid_constant__ DecP
             const long long r = q / n, m = q - r * n;
             const unsigned long long grow = (unsigned long long)(P.row_off + row0 + r);
             const unsigned long long li = ((unsigned long long)m * (unsigned long long)P.Bg + grow) * P.nz_c + i;
-            v = P.rng.mode == 0 ? P.rng.eps[3][li] : philox_normal(P.rng.seed, P.rng.offset[3], P.rng.grid_threads[3], li);
+            v = P.rng.mode == 0 ? P.rng.eps[3][li] : philox_normal_elem(P.rng.seed, P.rng.offset[3], P.rng.grid_threads[3], li);
           }
           EPSC[i * LDP + p] = v;
         }

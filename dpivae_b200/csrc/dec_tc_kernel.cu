@@ -51,17 +51,6 @@ enum { TPH_SETUP = 0, TPH_ROWPAR_EPS, TPH_LATENT, TPH_AUX1, TPH_A0, TPH_AUX2, TP
     }                                              \
   } while (0)
 
-__device__ __forceinline__ float philox_normal_tc(unsigned long long seed, unsigned long long offset, unsigned int T,
-                                                  unsigned long long li) {
-  const unsigned long long sub = li % T;
-  const unsigned long long q4 = li / T;
-  const unsigned long long it = q4 >> 2;
-  const int comp = (int)(q4 & 3ull);
-  curandStatePhilox4_32_10_t st;
-  curand_init(seed, sub, offset + 4ull * it, &st);
-  const float4 r = curand_normal4(&st);
-  return comp == 0 ? r.x : (comp == 1 ? r.y : (comp == 2 ? r.z : r.w));
-}
 
 __device__ __forceinline__ int block_of_tc(const DecParams& P, int i) {
   int b = 0;

@@ -27,18 +27,6 @@ namespace {
 constexpr int TP = 128;
 constexpr int LNT = 256;
 
-__device__ __forceinline__ float philox_normal_l(unsigned long long seed, unsigned long long offset, unsigned int T,
-                                                 unsigned long long li) {
-  // torch.cuda normal_() element -> (subsequence, call, lane) map, see dec_kernel.cu
-  const unsigned long long sub = li % T;
-  const unsigned long long q4 = li / T;
-  const unsigned long long it = q4 >> 2;
-  const int comp = (int)(q4 & 3ull);
-  curandStatePhilox4_32_10_t st;
-  curand_init(seed, sub, offset + 4ull * it, &st);
-  const float4 r = curand_normal4(&st);
-  return comp == 0 ? r.x : (comp == 1 ? r.y : (comp == 2 ? r.z : r.w));
-}
 
 __device__ __forceinline__ int block_of_l(const DecParams& P, int i) {
   int b = 0;
@@ -194,7 +182,7 @@ __global__ void __launch_bounds__(LNT) lat_fwd_kernel(const __grid_constant__ De
       const unsigned long long grow = (unsigned long long)(P.row_off + row0 + r);
       const int b = block_of_l(P, i), il = i - P.blk_start[b], nzb = P.blk_size[b];
       const unsigned long long li = ((unsigned long long)m * (unsigned long long)P.Bg + grow) * nzb + il;
-      v = P.rng.mode == 0 ? P.rng.eps[b][li] : philox_normal_l(P.rng.seed, P.rng.offset[b], P.rng.grid_threads[b], li);
+      v = P.rng.mode == 0 ? P.rng.eps[b][li] : philox_normal_elem(P.rng.seed, P.rng.offset[b], P.rng.grid_threads[b], li);
     }
     S.EPS[e] = v;
     epsg[e] = v;
@@ -407,7 +395,7 @@ __global__ void __launch_bounds__(LNT) lat_encode_kernel(const __grid_constant__
   for (int i = 0; i < P.Z; ++i) {
     const int b = block_of_l(P, i), il = i - P.blk_start[b], nzb = P.blk_size[b];
     const unsigned long long li = ((unsigned long long)m * (unsigned long long)P.Bg + grow) * nzb + il;
-    lsm[i * LNT + tid] = P.rng.mode == 0 ? P.rng.eps[b][li] : philox_normal_l(P.rng.seed, P.rng.offset[b], P.rng.grid_threads[b], li);
+    lsm[i * LNT + tid] = P.rng.mode == 0 ? P.rng.eps[b][li] : philox_normal_elem(P.rng.seed, P.rng.offset[b], P.rng.grid_threads[b], li);
   }
   float dens = 0.0f;
   for (int b = 0; b < P.n_blk; ++b) {
