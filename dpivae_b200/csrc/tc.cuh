@@ -173,6 +173,28 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
   tmem_wait_st();
 }
 
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+  tmem_wait_ld();
+}
+// 8 fp32 values -> packed fp16 hi / lo planes in tensor memory (A operand of a TS-mode MMA): 4 columns each
+__device__ __forceinline__ void tmem_put8_packed(uint32_t t_hi, uint32_t t_lo, const float* v);
+// and back: value = (hi + lo) * inv_scale
+__device__ __forceinline__ void tmem_get8_packed(uint32_t t_hi, uint32_t t_lo, float inv_scale, float* v) {
+  uint32_t h[4], l[4];
+  tmem_ld4(t_hi, h);
+  tmem_ld4(t_lo, l);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h[i]));
+    const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&l[i]));
+    v[2 * i] = (hf.x + lf.x) * inv_scale;
+    v[2 * i + 1] = (hf.y + lf.y) * inv_scale;
+  }
+}
 __device__ __forceinline__ void tmem_st4(uint32_t taddr, const float* v) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(__float_as_uint(v[0])),
                "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3]))
@@ -212,6 +234,15 @@ __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
   }
   hi = make_uint4(h[0], h[1], h[2], h[3]);
   lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+__device__ __forceinline__ void tmem_put8_packed(uint32_t t_hi, uint32_t t_lo, const float* v) {
+  uint4 hi, lo;
+  split8(v, hi, lo);
+  const float ph[4] = {__uint_as_float(hi.x), __uint_as_float(hi.y), __uint_as_float(hi.z), __uint_as_float(hi.w)};
+  const float pl[4] = {__uint_as_float(lo.x), __uint_as_float(lo.y), __uint_as_float(lo.z), __uint_as_float(lo.w)};
+  tmem_st4(t_hi, ph);
+  tmem_st4(t_lo, pl);
 }
 
 // A split operand: hi plane at `base`, lo plane at `base + lo_off` (bytes), both X8 with R rows.
@@ -259,6 +290,39 @@ static __device__ __noinline__ void issue_dgrad(uint32_t d_tmem, Op g, Op w, int
       accumulate = 1;
       glo += gstep;
       wlo += wstep;
+    }
+  }
+}
+//   TS forms: A (128 x K) in tensor memory as packed fp16 pairs, hi plane at a_tmem, lo plane at a_tmem + K / 2
+static __device__ __noinline__ void issue_fwd_ts(uint32_t d_tmem, uint32_t a_tmem, Op w, int N, int K, uint32_t accumulate, int terms) {
+  const uint32_t idesc = make_idesc(128, N, 0, 0);
+  const uint32_t whi = 8u | DESC_VERSION_HI, wstep = 2u * (uint32_t)w.R;
+  const int ks = K >> 4;
+  for (int t = 0; t < terms; ++t) {
+    uint32_t a = a_tmem + (t == 1 ? (uint32_t)(K >> 1) : 0u);
+    uint32_t wlo = (((w.base + (t == 2 ? w.lo_off : 0u)) >> 4) & 0x3FFFu) | ((uint32_t)w.R << 16);
+#pragma unroll 4
+    for (int k = 0; k < ks; ++k) {
+      mma_f16_ts(d_tmem, a, pack64(wlo, whi), idesc, accumulate);
+      accumulate = 1;
+      a += 8u;
+      wlo += wstep;
+    }
+  }
+}
+static __device__ __noinline__ void issue_dgrad_ts(uint32_t d_tmem, uint32_t g_tmem, Op w, int Nout, int Kin, uint32_t accumulate, int terms) {
+  const uint32_t idesc = make_idesc(128, Kin, 0, 1);
+  const uint32_t whi = (uint32_t)w.R | DESC_VERSION_HI;
+  const int ks = Nout >> 4;
+  for (int t = 0; t < terms; ++t) {
+    uint32_t a = g_tmem + (t == 1 ? (uint32_t)(Nout >> 1) : 0u);
+    uint32_t wlo = (((w.base + (t == 2 ? w.lo_off : 0u)) >> 4) & 0x3FFFu) | (8u << 16);
+#pragma unroll 4
+    for (int k = 0; k < ks; ++k) {
+      mma_f16_ts(d_tmem, a, pack64(wlo, whi), idesc, accumulate);
+      accumulate = 1;
+      a += 8u;
+      wlo += 16u;
     }
   }
 }

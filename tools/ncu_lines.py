@@ -23,7 +23,7 @@ lines = []  # per instruction: (file, line, inlined_at)
 cur = ("?", 0, "")
 inl = ""
 in_kernel = False
-kname = rows[0][1].split("(")[0].split("::")[-1]
+kname = sys.argv[4] if len(sys.argv) > 4 else rows[0][1].split("(")[0].split("::")[-1].rstrip("<")
 for l in dis:
     if l.startswith("\t.section") or l.startswith(".section"):
         in_kernel = kname in l and ".text." in l
