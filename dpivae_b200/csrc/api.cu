@@ -318,7 +318,7 @@ static int build_plan(dpivae_model* h) {
     const bool mlp = d.phys_kind == DPIVAE_PHYS_MLP;
     const int need = nzd + 1 + (mlp ? nzin : 0);
     bool ok = need <= 16 && dec_tc_has_variant(d.phys_kind, d.nd_x) && !d.has_lambda_x && d.nd_c <= 2 && d.nd_y <= 2 &&
-              d.nz_c <= 4 && d.nz_y <= 4;
+              d.nz_c <= 4 && d.nz_y <= 4 && d.nz_x <= 4;
     if (mlp) ok = ok && d.phys_n_layers == 4 && d.phys_dims[1] == 64 && d.phys_dims[2] == 32 && d.phys_dims[3] == 64;
     if (ok) {
       const int KZ = 16, d1 = mlp ? 64 : 0, d2 = mlp ? 32 : 0, d3 = mlp ? 64 : 0;
@@ -344,6 +344,7 @@ static int build_plan(dpivae_model* h) {
       auto f32 = [&](int floats) { int off = b; b += ((floats + 3) & ~3) * 4; return off; };
       T.f_inv = f32(16); T.f_bias_x = f32(64); T.f_bias_p1 = f32(32); T.f_bias_p2 = f32(64);
       T.f_aw0 = f32(2 * 64 * 4); T.f_ab0 = f32(2 * 64); T.f_aw1 = f32(2 * 64 * 4); T.f_ab1 = f32(8);
+      T.f_w0f = f32(128 * 8); T.f_wp0f = f32(64 * 4);
       T.f_dza = f32(nzd * 128); T.f_sc = f32(8 * 128); T.f_red = f32(256);
       T.o_bar = b; b += 64;
       T.total = (b + 127) & ~127;

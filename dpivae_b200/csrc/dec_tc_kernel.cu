@@ -31,7 +31,8 @@ namespace {
 constexpr int TP = 128;    // pairs per tile
 constexpr int TNT = 256;   // threads per CTA
 // TMEM column map (fp32 columns, 128 lanes)
-enum { C_W1 = 0, C_W0 = 64, C_AW1 = 80, C_AW0 = 96, C_H = 112, C_X = 240, C_S = 304, C_A0 = 336, C_A1 = 400, C_A2 = 432, C_ALLOC = 512 };
+enum { C_W1 = 0, C_W0 = 64, C_AW1 = 80, C_AW0 = 96, C_H = 112, C_X = 240, C_S = 304, C_A0 = 336, C_A1 = 400, C_A2 = 432, C_T = 496,
+       C_ALLOC = 512 };
 // power-of-two operand scales (exponents)
 constexpr int E_LAT = 4, E_H = 6, E_T = 8;
 // scalar rows (one value per pair)
@@ -193,6 +194,10 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
   float* AB0 = smf + (T.f_ab0 >> 2);      //                   [side][64]
   float* AW1 = smf + (T.f_aw1 >> 2);      // aux heads, transposed [side][64][4]: mean_0, mean_1, ls_0, ls_1 per hidden unit
   float* AB1 = smf + (T.f_ab1 >> 2);      //                   [side][4]
+  float* W0F = smf + (T.f_w0f >> 2);      // fx0 weights, fp32 [128][8] (dgrad to the latents on the CUDA cores)
+  float* WP0F = smf + (T.f_wp0f >> 2);    // physics layer 0 weights w.r.t. the physics latents, fp32 [64][4]
+  const float4* W0F4 = reinterpret_cast<const float4*>(W0F);
+  const float4* WP0F4 = reinterpret_cast<const float4*>(WP0F);
   float* DZA = smf + (T.f_dza >> 2);
   float* SC = smf + (T.f_sc >> 2);
   float* RED = smf + (T.f_red >> 2);
@@ -259,6 +264,16 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
   if constexpr (mlp) {
     for (int e = tid; e < d2; e += TNT) BP1[e] = P.frozen[P.pl[1].g_b + e];
     for (int e = tid; e < d3; e += TNT) BP2[e] = P.frozen[P.pl[2].g_b + e];
+  }
+  for (int e = tid; e < 128 * 8; e += TNT) {
+    const int k = e >> 3, j = e & 7;
+    W0F[e] = j < nzd ? prm[P.fx.g_w0 + (long long)k * nzd + j] : 0.0f;
+  }
+  if constexpr (mlp) {
+    for (int e = tid; e < d1 * 4; e += TNT) {
+      const int k = e >> 2, j = e & 3;
+      WP0F[e] = j < P.nz_x ? P.frozen[P.pl[0].g_w + (long long)k * nzin + j] : 0.0f;
+    }
   }
   // auxiliary decoders (fp32, CUDA cores): side 0 = decoder_c, side 1 = decoder_y
   for (int e = tid; e < 2 * 64 * 4; e += TNT) {
@@ -366,7 +381,7 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
     // ---- first layers of the data-driven decoder and of the physics surrogate: issued now, consumed later ----
     stage_issue(bar0, [&] {
       tc::issue_fwd(tb + C_H, oLAT, oWFX0, 128, KZ, 0, terms);
-      if constexpr (mlp) tc::issue_fwd(tb + C_A0, oLAT, oWP0, d1, KZ, 0, terms);
+      if constexpr (mlp) tc::issue_fwd(tb + C_X, oLAT, oWP0, d1, KZ, 0, terms);
     });
     TPHASE(TPH_LATENT);
 
@@ -433,15 +448,14 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
 #pragma unroll 2
       for (int c = 0; c < 4; ++c) {
         float v[8];
-        tc::tmem_ld8(trow + C_A0 + 32 * hh + 8 * c, v);
+        tc::tmem_ld8(trow + C_X + 32 * hh + 8 * c, v);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = tanh_fast(v[i] * inv);
-        tc::tmem_st8(trow + C_A0 + 32 * hh + 8 * c, v);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] *= s_t;
-        put8(pG, T.l_g, TP, 4 * hh + c, p, v);
+        for (int i = 0; i < 8; ++i) v[i] = tanh_fast(v[i] * inv) * s_t;
+        // tanh outputs stay in tensor memory as packed fp16 hi / lo planes: A operand of the next layer (TS-mode MMA,
+        // no shared-memory copy) and the saved activation of the backward
+        tc::tmem_put8_packed(trow + C_A0 + 16 * hh + 4 * c, trow + C_A0 + 32 + 16 * hh + 4 * c, v);
       }
-      stage_issue(bar0, [&] { tc::issue_fwd(tb + C_A1, oG, oWP1, d2, d1, 0, terms); });
+      stage_issue(bar0, [&] { tc::issue_fwd_ts(tb + C_S, tb + C_A0, oWP1, d2, d1, 0, terms); });
     }
     TPHASE(TPH_A0);
 
@@ -481,16 +495,13 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           float v[8];
-          tc::tmem_ld8(trow + C_A1 + 16 * hh + 8 * c, v);
+          tc::tmem_ld8(trow + C_S + 16 * hh + 8 * c, v);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = tanh_fast(v[i] * inv + BP1[16 * hh + 8 * c + i]);
-          tc::tmem_st8(trow + C_A1 + 16 * hh + 8 * c, v);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] *= s_t;
-          put8(pG, T.l_g, TP, 2 * hh + c, p, v);
+          for (int i = 0; i < 8; ++i) v[i] = tanh_fast(v[i] * inv + BP1[16 * hh + 8 * c + i]) * s_t;
+          tc::tmem_put8_packed(trow + C_A1 + 8 * hh + 4 * c, trow + C_A1 + 16 + 8 * hh + 4 * c, v);
         }
       }
-      stage_issue(bar0, [&] { tc::issue_fwd(tb + C_A2, oG, oWP2, d3, d2, 0, terms); });
+      stage_issue(bar0, [&] { tc::issue_fwd_ts(tb + C_X, tb + C_A1, oWP2, d3, d2, 0, terms); });
     }
     TPHASE(TPH_A1);
 
@@ -524,20 +535,17 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
 #pragma unroll 2
         for (int c = 0; c < 4; ++c) {
           float v[8];
-          tc::tmem_ld8(trow + C_A2 + 32 * hh + 8 * c, v);
+          tc::tmem_ld8(trow + C_X + 32 * hh + 8 * c, v);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = tanh_fast(v[i] * inv + BP2[32 * hh + 8 * c + i]);
-          tc::tmem_st8(trow + C_A2 + 32 * hh + 8 * c, v);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] *= s_h;
-          put8(pG, T.l_g, TP, 4 * hh + c, p, v);
+          for (int i = 0; i < 8; ++i) v[i] = tanh_fast(v[i] * inv + BP2[32 * hh + 8 * c + i]) * s_h;
+          tc::tmem_put8_packed(trow + C_A2 + 16 * hh + 4 * c, trow + C_A2 + 32 + 16 * hh + 4 * c, v);
         }
       }
     }
     // x head = data-driven decoder output (+ last physics layer) into the same accumulator
     stage_issue(bar0, [&] {
       tc::issue_fwd(tb + C_X, oBIG, oWFX1, ndx, 128, 0, terms);
-      if constexpr (mlp) tc::issue_fwd(tb + C_X, oG, oWP3, ndx, d3, 1, terms);
+      if constexpr (mlp) tc::issue_fwd_ts(tb + C_X, tb + C_A2, oWP3, ndx, d3, 1, terms);
     });
     TPHASE(TPH_A2);
     stage_wait(bar0, ph0);
@@ -594,11 +602,20 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
     }
     if (P.with_grad) {
       // ================= backward ============================================================================
-      stage_issue(bar0, [&] {
-        tc::issue_wgrad(tb + C_W1, oBIG, oG, ndx, wacc, terms);
+      // the dgrads the next epilogues wait for go first (bar0); the weight gradient of fx1 follows on bar1 and is only
+      // waited for when its operand buffers are overwritten
+      tc::fence_async_smem();
+      tc::fence_before_sync();
+      __syncthreads();
+      if (tid == 0) {
+        tc::fence_after_sync();
         tc::issue_dgrad(tb + C_H, oG, oWFX1, ndx, 128, 0, terms);
         if constexpr (mlp) tc::issue_dgrad(tb + C_X, oG, oWP3, ndx, d3, 0, terms);
-      });
+        tc::commit(bar0);
+        tc::issue_wgrad(tb + C_W1, oBIG, oG, ndx, wacc, terms);
+        tc::commit(bar1);
+      }
+      __syncwarp();
     } else {
       __syncthreads();
     }
@@ -611,91 +628,115 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
     TPHASE(TPH_XHEAD);
 
     if (P.with_grad) {
-      stage_wait(bar0, ph0);
+      stage_wait(bar0, ph0);   // dgrad fx1 (C_H) and dgrad of the last physics layer (C_X)
       if constexpr (mlp) {
-        // d tanh of physics layer 2 (operand for the next dgrad), then let that dgrad run under the ReLU-mask epilogue
+        // d tanh of physics layer 2: the gradient replaces the saved activation in place (this thread's own packed
+        // columns) and is the TS-mode A operand of the next dgrad, which then runs under the ReLU-mask epilogue
         const float inv = INV[I_XD];
 #pragma unroll 2
         for (int c = 0; c < 4; ++c) {
           float g[8], a[8];
           tc::tmem_ld8(trow + C_X + 32 * hh + 8 * c, g);
-          tc::tmem_ld8(trow + C_A2 + 32 * hh + 8 * c, a);
+          const uint32_t th = trow + C_A2 + 16 * hh + 4 * c, tl = th + 32;
+          tc::tmem_get8_packed(th, tl, 1.0f / s_h, a);
 #pragma unroll
           for (int i = 0; i < 8; ++i) g[i] = g[i] * inv * (1.0f - a[i] * a[i]);
-          put8(pG, T.l_g, TP, 4 * hh + c, p, g);
+          tc::tmem_put8_packed(th, tl, g);
         }
-        stage_issue(bar1, [&] { tc::issue_dgrad(tb + C_X, oG, oWP2, d3, d2, 0, terms); });
+        stage_issue(bar0, [&] { tc::issue_dgrad_ts(tb + C_S, tb + C_A2, oWP2, d3, d2, 0, terms); });
       }
+      stage_wait(bar1, ph1);   // wgrad fx1 done: BIG (hidden activations) may be overwritten
       {
+        // ReLU mask on dL/dh; the first-layer dgrad dL/dz = dL/dh . W0 (K = 64 per thread, N = nzd <= 8) stays on the
+        // CUDA cores: this thread's partial sum over its 64 hidden units, halves combined through tensor memory
         const float inv = INV[I_XD];
+        float gz[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 2
         for (int c = 0; c < 8; ++c) {
           float v[8];
           tc::tmem_ld8(trow + C_H + 64 * hh + 8 * c, v);
           const uint32_t m8 = (uint32_t)(mkH >> (8 * c)) & 0xFFu;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = ((m8 >> i) & 1u) ? v[i] * inv : 0.0f;
+          for (int i = 0; i < 8; ++i) {
+            v[i] = ((m8 >> i) & 1u) ? v[i] * inv : 0.0f;
+            const float4 w0 = W0F4[2 * (64 * hh + 8 * c + i)], w1 = W0F4[2 * (64 * hh + 8 * c + i) + 1];
+            gz[0] = fmaf(v[i], w0.x, gz[0]); gz[1] = fmaf(v[i], w0.y, gz[1]); gz[2] = fmaf(v[i], w0.z, gz[2]); gz[3] = fmaf(v[i], w0.w, gz[3]);
+            gz[4] = fmaf(v[i], w1.x, gz[4]); gz[5] = fmaf(v[i], w1.y, gz[5]); gz[6] = fmaf(v[i], w1.z, gz[6]); gz[7] = fmaf(v[i], w1.w, gz[7]);
+          }
           put8(pBIG, T.l_big, TP, 8 * hh + c, p, v);
+        }
+        if (hh == 1) tc::tmem_st8(trow + C_T, gz);
+        tc::fence_before_sync();
+        tc::fence_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+          tc::fence_after_sync();
+          tc::issue_wgrad(tb + C_W0, oBIG, oLAT, KZ, wacc, terms);   // fire and forget: waited for at the end of the tile
+          tc::commit(bar1);
+        }
+        __syncwarp();
+        tc::fence_after_sync();
+        if (hh == 0) {
+          // total dL/d(zc|zy): reversed + scaled gradient of the data-driven decoder (utils/transforms.py:207-219)
+          // plus the auxiliary decoders' gradient
+          float g1[8];
+          tc::tmem_ld8(trow + C_T, g1);
+          const float sc = -P.lambda_g0 * cx;
+          float* dz = P.dzrec + (long long)rb * (nzd + P.nz_x) * TP;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (k < nzd) dz[k * TP + p] = fmaf(gz[k] + g1[k], sc, (k < P.nz_c ? awc : awy) * DZA[k * TP + p]);
         }
       }
       TPHASE(TPH_BWD1);
       if constexpr (mlp) {
-        stage_wait(bar1, ph1);
-        const float inv = INV[I_P2D];
+        stage_wait(bar0, ph0);   // dgrad physics layer 2
+        {
+          const float inv = INV[I_P2D];
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          float g[8], a[8];
-          tc::tmem_ld8(trow + C_X + 16 * hh + 8 * c, g);
-          tc::tmem_ld8(trow + C_A1 + 16 * hh + 8 * c, a);
+          for (int c = 0; c < 2; ++c) {
+            float g[8], a[8];
+            tc::tmem_ld8(trow + C_S + 16 * hh + 8 * c, g);
+            const uint32_t th = trow + C_A1 + 8 * hh + 4 * c, tl = th + 16;
+            tc::tmem_get8_packed(th, tl, 1.0f / s_t, a);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) g[i] = g[i] * inv * (1.0f - a[i] * a[i]);
-          put8(pG, T.l_g, TP, 2 * hh + c, p, g);
-        }
-      }
-      stage_issue(bar0, [&] {
-        if constexpr (mlp) tc::issue_dgrad(tb + C_X, oG, oWP1, d2, d1, 0, terms);
-        tc::issue_wgrad(tb + C_W0, oBIG, oLAT, KZ, wacc, terms);
-        tc::issue_dgrad(tb + C_S, oBIG, oWFX0, 128, KZ, 0, terms);
-      });
-      TPHASE(TPH_BWD2);
-      stage_wait(bar0, ph0);
-      if constexpr (mlp) {
-        const float inv = INV[I_P1D];
-#pragma unroll 2
-        for (int c = 0; c < 4; ++c) {
-          float g[8], a[8];
-          tc::tmem_ld8(trow + C_X + 32 * hh + 8 * c, g);
-          tc::tmem_ld8(trow + C_A0 + 32 * hh + 8 * c, a);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) g[i] = g[i] * inv * (1.0f - a[i] * a[i]);
-          put8(pG, T.l_g, TP, 4 * hh + c, p, g);
-        }
-        stage_issue(bar1, [&] { tc::issue_dgrad(tb + C_S + 16, oG, oWP0, d1, KZ, 0, terms); });
-      }
-      if (hh == 0) {
-        // total dL/d(zc|zy): reversed + scaled gradient of the data-driven decoder (utils/transforms.py:207-219)
-        // plus the auxiliary decoders' gradient
-        float v[16];
-        tc::tmem_ld16(trow + C_S, v);
-        const float inv = -P.lambda_g0 * cx * INV[I_FX0D];
-        float* dz = P.dzrec + (long long)rb * (nzd + P.nz_x) * TP;
-#pragma unroll
-        for (int k = 0; k < 16; ++k)
-          if (k < nzd) dz[k * TP + p] = fmaf(v[k], inv, (k < P.nz_c ? awc : awy) * DZA[k * TP + p]);
-      }
-      TPHASE(TPH_BWD3);
-      if constexpr (mlp) {
-        stage_wait(bar1, ph1);
-        if (hh == 0) {
-          float v[16];
-          tc::tmem_ld16(trow + C_S + 16, v);
-          const float inv = INV[I_P0D] * cx;
-#pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            const int k = c - cs0;
-            if (k >= 0 && k < P.nz_x) P.dzrec[((long long)rb * (nzd + P.nz_x) + nzd + k) * TP + p] = v[c] * inv / P.phys_in_std[k];
+            for (int i = 0; i < 8; ++i) g[i] = g[i] * inv * (1.0f - a[i] * a[i]);
+            tc::tmem_put8_packed(th, tl, g);
           }
         }
+        stage_issue(bar0, [&] { tc::issue_dgrad_ts(tb + C_X, tb + C_A1, oWP1, d2, d1, 0, terms); });
+        TPHASE(TPH_BWD2);
+        stage_wait(bar0, ph0);   // dgrad physics layer 1
+        {
+          // d tanh of layer 0 and, on the CUDA cores, the dgrad to the physics latents: dL/ds0[j] = sum_k g[k] W_p0[k][j]
+          const float inv = INV[I_P1D];
+          float gs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+          for (int c = 0; c < 4; ++c) {
+            float g[8], a[8];
+            tc::tmem_ld8(trow + C_X + 32 * hh + 8 * c, g);
+            tc::tmem_get8_packed(trow + C_A0 + 16 * hh + 4 * c, trow + C_A0 + 32 + 16 * hh + 4 * c, 1.0f / s_t, a);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float gv = g[i] * inv * (1.0f - a[i] * a[i]);
+              const float4 w = WP0F4[32 * hh + 8 * c + i];
+              gs[0] = fmaf(gv, w.x, gs[0]); gs[1] = fmaf(gv, w.y, gs[1]); gs[2] = fmaf(gv, w.z, gs[2]); gs[3] = fmaf(gv, w.w, gs[3]);
+            }
+          }
+          if (hh == 1) tc::tmem_st4(trow + C_T + 8, gs);
+          tc::fence_before_sync();
+          __syncthreads();
+          tc::fence_after_sync();
+          if (hh == 0) {
+            uint32_t r1[4];
+            tc::tmem_ld4(trow + C_T + 8, r1);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (k < P.nz_x)
+                P.dzrec[((long long)rb * (nzd + P.nz_x) + nzd + k) * TP + p] = (gs[k] + __uint_as_float(r1[k])) * cx / P.phys_in_std[k];
+          }
+        }
+        TPHASE(TPH_BWD3);
       } else {
         // closed-form physics backward: d xh_p / d zx contracted with g~ (this thread's half of the x columns)
         float s0 = 0.0f, s1 = 0.0f;
@@ -740,6 +781,7 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
           if (P.nz_x > 1) dzx[TP + tid] = (Q2[tid] + Q2[TP + tid]) * cx;
         }
       }
+      stage_wait(bar1, ph1);   // wgrad fx0 done: BIG and the record buffer are free for the next tile
       __syncthreads();
       TPHASE(TPH_BWD4);
 

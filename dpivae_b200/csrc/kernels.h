@@ -101,7 +101,7 @@ struct TcParams {
   int l_fx0, l_fx1, l_p[4];
   int a_big, a_g, a_oa, l_big, l_g, l_oa;   // activation / gradient operands
   int a_rec, rec_buf;        // two tile-record buffers of rec_buf bytes each
-  int f_inv, f_bias_x, f_bias_p1, f_bias_p2, f_aw0, f_ab0, f_aw1, f_ab1;
+  int f_inv, f_bias_x, f_bias_p1, f_bias_p2, f_aw0, f_ab0, f_aw1, f_ab1, f_w0f, f_wp0f;
   int f_dza, f_sc, f_red;
   int o_bar;
   int total;
