@@ -425,18 +425,35 @@ def main():
     def step_resident(i):
         dp.step(x, c, y, n, w, B_global, row_off, i)
 
-    # pinned host copies for the end-to-end arm
+    # End-to-end arm: every step's inputs come from pinned host memory and its 8 loss scalars go back to the host, where
+    # the caller waits for them.  Two device input sets: while step i computes, a copy stream uploads the inputs of step
+    # i + 1 (the per-step H2D copy stays inside the timed region, it is just not serialised with the kernels).
     xh, ch, yh = (t.cpu().pin_memory() for t in (x, c, y))
     scal_host = torch.empty(8, dtype=torch.float32).pin_memory()
-    xd, cd, yd = (torch.empty_like(t) for t in (x, c, y))
+    dev_in = [tuple(torch.empty_like(t) for t in (x, c, y)) for _ in range(2)]
+    copy_stream = torch.cuda.Stream(dev)
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    e2e_state = {"k": 0, "primed": False}
+
+    def upload(slot):
+        with torch.cuda.stream(copy_stream):
+            for dst, src in zip(dev_in[slot], (xh, ch, yh)):
+                dst.copy_(src, non_blocking=True)
+            ready[slot].record(copy_stream)
 
     def step_e2e(i):
-        xd.copy_(xh, non_blocking=True)
-        cd.copy_(ch, non_blocking=True)
-        yd.copy_(yh, non_blocking=True)
+        k = e2e_state["k"]
+        if not e2e_state["primed"]:
+            upload(k & 1)
+            e2e_state["primed"] = True
+        main = torch.cuda.current_stream()
+        main.wait_event(ready[k & 1])
+        xd, cd, yd = dev_in[k & 1]
         s = dp.step(xd, cd, yd, n, w, B_global, row_off, i)
+        upload((k + 1) & 1)        # step k - 1, the last reader of that slot, was synchronised below
         scal_host.copy_(s, non_blocking=True)
-        torch.cuda.current_stream().synchronize()  # the user reads the loss every step
+        main.synchronize()         # the user reads the loss every step
+        e2e_state["k"] = k + 1
 
     def timed(fn, steps, first_step):
         sync_all()
