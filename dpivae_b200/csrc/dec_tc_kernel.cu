@@ -97,19 +97,22 @@ __device__ __forceinline__ tc::Op mkop(const unsigned char* sm, int off, uint32_
   return o;
 }
 
-// one MMA batch: make the operands written so far visible, let thread 0 issue + commit to `bar`; no wait
-template <class F>
-__device__ __forceinline__ void stage_issue(uint64_t* bar, F issue) {
+constexpr int NTHR = TNT + 32;   // 8 epilogue warps + 1 MMA-issue warp
+// Warp-specialised MMA issue: the 256 epilogue threads only SIGNAL that the operands of stage `sid` are in place
+// (non-blocking bar.arrive on a rotating named barrier); the dedicated issue warp waits for the signal, issues the
+// MMAs and commits them to an mbarrier.  The epilogue warps never spend issue slots on descriptor arithmetic and never
+// wait for the issue itself, only for the results they consume.
+__device__ __forceinline__ void stage_signal(uint32_t sid) {
   tc::fence_async_smem();
   tc::fence_before_sync();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    tc::fence_after_sync();
-    issue();
-    tc::commit(bar);
-  }
-  __syncwarp();
+  asm volatile("bar.arrive %0, %1;" ::"r"(2u + (sid & 7u)), "r"((uint32_t)NTHR) : "memory");
 }
+__device__ __forceinline__ void issuer_wait(uint32_t sid) {
+  asm volatile("bar.sync %0, %1;" ::"r"(2u + (sid & 7u)), "r"((uint32_t)NTHR) : "memory");
+  tc::fence_after_sync();
+}
+// barrier among the 256 epilogue threads only
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" ::"r"((uint32_t)TNT) : "memory"); }
 __device__ __forceinline__ void stage_wait(uint64_t* bar, uint32_t& phase) {
   tc::mbar_wait(bar, phase);
   phase ^= 1u;
@@ -169,7 +172,7 @@ __device__ void stage_weight(unsigned char* plane, uint32_t lo_off, int N, int K
 // PHYS: physics decoder kind (0 MLP surrogate, 1 mass_spring, 2 beam); NDX: response length -- compile-time so
 // that the epilogues are straight-line code (a taken branch in this large kernel costs an I-cache miss)
 template <bool PROF, int PHYS, int NDX>
-__global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ TcParams T) {
+__global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__ TcParams T) {
   const DecParams& P = T.d;
   extern __shared__ __align__(1024) unsigned char smb[];
   float* smf = reinterpret_cast<float*>(smb);
@@ -353,12 +356,106 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
   long long t_last = (PROF && tid == 0) ? clock64() : 0;
   TPHASE(TPH_SETUP);
 
+
+  if (warp == 8) {
+    // ================= MMA-issue warp: mirrors the stage sequence of the epilogue warps =================================
+    int it = 0;
+    uint32_t sid = 0, wacc = 0;
+    for (long long rb = blockIdx.x; rb < P.n_rowblocks; rb += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const unsigned char* rec = RECB + (size_t)buf * T.rec_buf;
+      const tc::Op oLAT = mkop(rec, 0, 4096u, TP);
+      tc::mbar_wait(rbar + buf, (uint32_t)(it >> 1) & 1u);   // the tile record (latent operand) has landed
+      __syncwarp();
+      issuer_wait(sid++);   // S0
+      if (lane == 0) {
+        tc::issue_fwd(tb + C_H, oLAT, oWFX0, 128, KZ, 0, terms);
+        if constexpr (mlp) tc::issue_fwd(tb + C_X, oLAT, oWP0, d1, KZ, 0, terms);
+        tc::commit(bar0);
+      }
+      __syncwarp();
+      if (P.with_grad) {
+        issuer_wait(sid++);   // S1
+        if (lane == 0) {
+          tc::issue_wgrad(tb + C_AW1, oBIG, oOA, 16, wacc, terms);
+          tc::commit(bar1);
+        }
+        __syncwarp();
+      }
+      if constexpr (mlp) {
+        issuer_wait(sid++);   // S2
+        if (lane == 0) {
+          tc::issue_fwd_ts(tb + C_S, tb + C_A0, oWP1, d2, d1, 0, terms);
+          tc::commit(bar0);
+        }
+        __syncwarp();
+      }
+      if (P.with_grad) {
+        issuer_wait(sid++);   // S3
+        if (lane == 0) {
+          tc::issue_wgrad(tb + C_AW0, oBIG, oLAT, KZ, wacc, terms);
+          tc::commit(bar1);
+        }
+        __syncwarp();
+      }
+      if constexpr (mlp) {
+        issuer_wait(sid++);   // S4
+        if (lane == 0) {
+          tc::issue_fwd_ts(tb + C_X, tb + C_A1, oWP2, d3, d2, 0, terms);
+          tc::commit(bar0);
+        }
+        __syncwarp();
+      }
+      issuer_wait(sid++);   // S5
+      if (lane == 0) {
+        tc::issue_fwd(tb + C_X, oBIG, oWFX1, ndx, 128, 0, terms);
+        if constexpr (mlp) tc::issue_fwd_ts(tb + C_X, tb + C_A2, oWP3, ndx, d3, 1, terms);
+        tc::commit(bar0);
+      }
+      __syncwarp();
+      if (P.with_grad) {
+        issuer_wait(sid++);   // S6: the dgrads the next epilogues wait for go first (bar0), the weight gradient of fx1 on bar1
+        if (lane == 0) {
+          tc::issue_dgrad(tb + C_H, oG, oWFX1, ndx, 128, 0, terms);
+          if constexpr (mlp) tc::issue_dgrad(tb + C_X, oG, oWP3, ndx, d3, 0, terms);
+          tc::commit(bar0);
+          tc::issue_wgrad(tb + C_W1, oBIG, oG, ndx, wacc, terms);
+          tc::commit(bar1);
+        }
+        __syncwarp();
+        if constexpr (mlp) {
+          issuer_wait(sid++);   // S7
+          if (lane == 0) {
+            tc::issue_dgrad_ts(tb + C_S, tb + C_A2, oWP2, d3, d2, 0, terms);
+            tc::commit(bar0);
+          }
+          __syncwarp();
+        }
+        issuer_wait(sid++);   // S8
+        if (lane == 0) {
+          tc::issue_wgrad(tb + C_W0, oBIG, oLAT, KZ, wacc, terms);
+          tc::commit(bar1);
+        }
+        __syncwarp();
+        if constexpr (mlp) {
+          issuer_wait(sid++);   // S9
+          if (lane == 0) {
+            tc::issue_dgrad_ts(tb + C_X, tb + C_A1, oWP1, d2, d1, 0, terms);
+            tc::commit(bar0);
+          }
+          __syncwarp();
+        }
+      }
+      wacc = 1u;
+    }
+  } else {
   const uint32_t rec_bytes = (uint32_t)P.rec_stride;
   if (tid == 0 && (long long)blockIdx.x < P.n_rowblocks) {
     tc::mbar_expect_tx(rbar, rec_bytes);
     tc::bulk_g2s(RECB, P.rec + (long long)blockIdx.x * P.rec_stride, rec_bytes, rbar);
   }
   int it = 0;
+  uint32_t sid = 0;
   for (long long rb = blockIdx.x; rb < P.n_rowblocks; rb += gridDim.x, ++it) {
     const long long row0 = rb * RB;
     const int nrows = (int)min((long long)RB, B - row0);
@@ -379,10 +476,7 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
     const bool pvalid = p < npairs;
     const int prow = (pvalid ? p : npairs - 1) / n;
     // ---- first layers of the data-driven decoder and of the physics surrogate: issued now, consumed later ----
-    stage_issue(bar0, [&] {
-      tc::issue_fwd(tb + C_H, oLAT, oWFX0, 128, KZ, 0, terms);
-      if constexpr (mlp) tc::issue_fwd(tb + C_X, oLAT, oWP0, d1, KZ, 0, terms);
-    });
+    stage_signal(sid++);   // S0: previous tile fully consumed
     TPHASE(TPH_LATENT);
 
     // ================= auxiliary decoder of side hh, forward, on the CUDA cores (fp32) =======================
@@ -438,7 +532,7 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
         for (int i = 0; i < 4; ++i) dba[i] += g4[i];
       }
     }
-    if (P.with_grad) stage_issue(bar1, [&] { tc::issue_wgrad(tb + C_AW1, oBIG, oOA, 16, wacc, terms); });
+    if (P.with_grad) stage_signal(sid++);   // S1
     TPHASE(TPH_AUX1);
 
     // ================= physics layer 0 -> tanh (bias folded into the constant-one column) =====================
@@ -455,7 +549,7 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
         // no shared-memory copy) and the saved activation of the backward
         tc::tmem_put8_packed(trow + C_A0 + 16 * hh + 4 * c, trow + C_A0 + 32 + 16 * hh + 4 * c, v);
       }
-      stage_issue(bar0, [&] { tc::issue_fwd_ts(tb + C_S, tb + C_A0, oWP1, d2, d1, 0, terms); });
+      stage_signal(sid++);   // S2
     }
     TPHASE(TPH_A0);
 
@@ -483,7 +577,7 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         if (j < a_nz) DZA[(a_j0 + j) * TP + p] = gz[j];
-      stage_issue(bar1, [&] { tc::issue_wgrad(tb + C_AW0, oBIG, oLAT, KZ, wacc, terms); });
+      stage_signal(sid++);   // S3
     }
     TPHASE(TPH_AUX2);
 
@@ -501,7 +595,7 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
           tc::tmem_put8_packed(trow + C_A1 + 8 * hh + 4 * c, trow + C_A1 + 16 + 8 * hh + 4 * c, v);
         }
       }
-      stage_issue(bar0, [&] { tc::issue_fwd_ts(tb + C_X, tb + C_A1, oWP2, d3, d2, 0, terms); });
+      stage_signal(sid++);   // S4
     }
     TPHASE(TPH_A1);
 
@@ -543,10 +637,7 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
       }
     }
     // x head = data-driven decoder output (+ last physics layer) into the same accumulator
-    stage_issue(bar0, [&] {
-      tc::issue_fwd(tb + C_X, oBIG, oWFX1, ndx, 128, 0, terms);
-      if constexpr (mlp) tc::issue_fwd_ts(tb + C_X, tb + C_A2, oWP3, ndx, d3, 1, terms);
-    });
+    stage_signal(sid++);   // S5
     TPHASE(TPH_A2);
     stage_wait(bar0, ph0);
 
@@ -604,20 +695,10 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
       // ================= backward ============================================================================
       // the dgrads the next epilogues wait for go first (bar0); the weight gradient of fx1 follows on bar1 and is only
       // waited for when its operand buffers are overwritten
-      tc::fence_async_smem();
-      tc::fence_before_sync();
-      __syncthreads();
-      if (tid == 0) {
-        tc::fence_after_sync();
-        tc::issue_dgrad(tb + C_H, oG, oWFX1, ndx, 128, 0, terms);
-        if constexpr (mlp) tc::issue_dgrad(tb + C_X, oG, oWP3, ndx, d3, 0, terms);
-        tc::commit(bar0);
-        tc::issue_wgrad(tb + C_W1, oBIG, oG, ndx, wacc, terms);
-        tc::commit(bar1);
-      }
-      __syncwarp();
+      stage_signal(sid++);   // S6
+      epi_sync();            // the per-pair sums of squares below are read across threads
     } else {
-      __syncthreads();
+      epi_sync();
     }
     if (tid < TP) {
       const bool valid = tid < npairs;
@@ -643,7 +724,7 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
           for (int i = 0; i < 8; ++i) g[i] = g[i] * inv * (1.0f - a[i] * a[i]);
           tc::tmem_put8_packed(th, tl, g);
         }
-        stage_issue(bar0, [&] { tc::issue_dgrad_ts(tb + C_S, tb + C_A2, oWP2, d3, d2, 0, terms); });
+        stage_signal(sid++);   // S7
       }
       stage_wait(bar1, ph1);   // wgrad fx1 done: BIG (hidden activations) may be overwritten
       {
@@ -666,15 +747,8 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
           put8(pBIG, T.l_big, TP, 8 * hh + c, p, v);
         }
         if (hh == 1) tc::tmem_st8(trow + C_T, gz);
-        tc::fence_before_sync();
-        tc::fence_async_smem();
-        __syncthreads();
-        if (tid == 0) {
-          tc::fence_after_sync();
-          tc::issue_wgrad(tb + C_W0, oBIG, oLAT, KZ, wacc, terms);   // fire and forget: waited for at the end of the tile
-          tc::commit(bar1);
-        }
-        __syncwarp();
+        stage_signal(sid++);   // S8: wgrad fx0, fire and forget (waited for at the end of the tile)
+        epi_sync();
         tc::fence_after_sync();
         if (hh == 0) {
           // total dL/d(zc|zy): reversed + scaled gradient of the data-driven decoder (utils/transforms.py:207-219)
@@ -704,7 +778,7 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
             tc::tmem_put8_packed(th, tl, g);
           }
         }
-        stage_issue(bar0, [&] { tc::issue_dgrad_ts(tb + C_X, tb + C_A1, oWP1, d2, d1, 0, terms); });
+        stage_signal(sid++);   // S9
         TPHASE(TPH_BWD2);
         stage_wait(bar0, ph0);   // dgrad physics layer 1
         {
@@ -725,7 +799,7 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
           }
           if (hh == 1) tc::tmem_st4(trow + C_T + 8, gs);
           tc::fence_before_sync();
-          __syncthreads();
+          epi_sync();
           tc::fence_after_sync();
           if (hh == 0) {
             uint32_t r1[4];
@@ -770,11 +844,11 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
             }
           }
         }
-        __syncthreads();
+        epi_sync();
         SC[(S_Q0 + hh) * TP + p] = s0;
         float* Q2 = RED;  // second component, [2][TP]
         Q2[hh * TP + p] = s1;
-        __syncthreads();
+        epi_sync();
         if (tid < TP) {
           float* dzx = P.dzrec + ((long long)rb * (nzd + P.nz_x) + nzd) * TP;
           dzx[tid] = (SC[S_Q0 * TP + tid] + SC[S_Q1 * TP + tid]) * cx;
@@ -782,11 +856,11 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
         }
       }
       stage_wait(bar1, ph1);   // wgrad fx0 done: BIG and the record buffer are free for the next tile
-      __syncthreads();
+      epi_sync();
       TPHASE(TPH_BWD4);
 
     }
-    __syncthreads();
+    epi_sync();
     TPHASE(TPH_LATENT_BWD);
     // ---- per-row outputs: MC means of the three reconstruction terms + the KL of lat_fwd_kernel ---------------------
     if (tid < nrows) {
@@ -808,7 +882,7 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
       SC[S_Q0 * TP + r] = loss; SC[S_Q1 * TP + r] = kl;
       SC[S_KL * TP + r] = rx; SC[S_KL2 * TP + r] = rc; SC[S_W * TP + r] = ry;
     }
-    __syncthreads();
+    epi_sync();
     if (tid == 0) {
       for (int r = 0; r < nrows; ++r) {
         tot[0] += SC[S_Q0 * TP + r];
@@ -818,7 +892,7 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
         tot[4] += SC[S_W * TP + r];
       }
     }
-    __syncthreads();
+    epi_sync();
     wacc = 1u;
     TPHASE(TPH_ROWOUT);
   }  // tiles
@@ -828,7 +902,7 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
     for (int k = 0; k < 6; ++k) part[P.n_params + k] = tot[k];
   if (P.with_grad && !P.latent_only) {
     tc::fence_before_sync();
-    __syncthreads();
+    epi_sync();
     tc::fence_after_sync();
     const int k = p;  // TMEM lane = hidden unit of the 128-wide layers
     // fx1: dW[n][k] (nd_x x 128)
@@ -871,21 +945,21 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
       }
     }
     // per-thread running sums -> fixed-order sums over the 128 pair slots of each column
-    __syncthreads();
+    epi_sync();
 #pragma unroll
     for (int i = 0; i < 32; ++i) R0[tid * 32 + i] = dbx[i];
-    __syncthreads();
+    epi_sync();
     if (tid < ndx) {
       const int h2 = tid / nxh, i = tid - h2 * nxh;
       float s = 0.0f;
       for (int j = 0; j < TP; ++j) s += R0[(h2 * TP + j) * 32 + i];
       part[P.fx.g_b1 + tid] = s * cx;
     }
-    __syncthreads();
+    epi_sync();
 #pragma unroll
     for (int i = 0; i < 4; ++i) R0[tid * 4 + i] = dba[i];
     R0[TNT * 4 + tid] = dlsx;
-    __syncthreads();
+    epi_sync();
     if (tid < 8) {
       const int side = tid >> 2, jj = tid & 3;
       const int nd = side ? P.nd_y : P.nd_c;
@@ -901,7 +975,8 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
       part[P.g_lsx] = s;
     }
   }
-  TPHASE(TPH_FLUSH);
+  }  // epilogue warps
+  if (warp < 8) TPHASE(TPH_FLUSH);
   if (PROF && tid == 0)
 #pragma unroll
     for (int k = 0; k < (PROF ? TPH_COUNT : 1); ++k) atomicAdd(reinterpret_cast<unsigned long long*>(P.phase) + k, (unsigned long long)phs[k]);
@@ -912,7 +987,7 @@ __global__ void __launch_bounds__(TNT, 1) dec_tc_kernel(const __grid_constant__ 
 
 template <bool PROF, int PHYS, int NDX>
 static void launch_one(const TcParams& p, int grid, cudaStream_t s) {
-  dec_tc_kernel<PROF, PHYS, NDX><<<grid, TNT, p.total, s>>>(p);
+  dec_tc_kernel<PROF, PHYS, NDX><<<grid, NTHR, p.total, s>>>(p);
 }
 
 // supported (physics kind, nd_x) pairs: (MLP, 64) bridge, (mass_spring, 64) damped_oscillator, (beam, 32) simple_beam,
