@@ -102,8 +102,11 @@ constexpr int NTHR = TNT + 32;   // 8 epilogue warps + 1 MMA-issue warp
 // (non-blocking bar.arrive on a rotating named barrier); the dedicated issue warp waits for the signal, issues the
 // MMAs and commits them to an mbarrier.  The epilogue warps never spend issue slots on descriptor arithmetic and never
 // wait for the issue itself, only for the results they consume.
+// SMEM_OPS: the stage's MMAs read shared-memory operands written by these threads (generic proxy -> async proxy fence);
+// stages whose new operands live in tensor memory (TS-mode MMAs) or arrived by bulk copy skip that fence
+template <bool SMEM_OPS = true>
 __device__ __forceinline__ void stage_signal(uint32_t sid) {
-  tc::fence_async_smem();
+  if (SMEM_OPS) tc::fence_async_smem();
   tc::fence_before_sync();
   asm volatile("bar.arrive %0, %1;" ::"r"(2u + (sid & 7u)), "r"((uint32_t)NTHR) : "memory");
 }
@@ -476,7 +479,7 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
     const bool pvalid = p < npairs;
     const int prow = (pvalid ? p : npairs - 1) / n;
     // ---- first layers of the data-driven decoder and of the physics surrogate: issued now, consumed later ----
-    stage_signal(sid++);   // S0: previous tile fully consumed
+    stage_signal<false>(sid++);   // S0: previous tile fully consumed (operand = the bulk-copied record)
     TPHASE(TPH_LATENT);
 
     // ================= auxiliary decoder of side hh, forward, on the CUDA cores (fp32) =======================
@@ -549,7 +552,7 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
         // no shared-memory copy) and the saved activation of the backward
         tc::tmem_put8_packed(trow + C_A0 + 16 * hh + 4 * c, trow + C_A0 + 32 + 16 * hh + 4 * c, v);
       }
-      stage_signal(sid++);   // S2
+      stage_signal<false>(sid++);   // S2
     }
     TPHASE(TPH_A0);
 
@@ -595,7 +598,7 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
           tc::tmem_put8_packed(trow + C_A1 + 8 * hh + 4 * c, trow + C_A1 + 16 + 8 * hh + 4 * c, v);
         }
       }
-      stage_signal(sid++);   // S4
+      stage_signal<false>(sid++);   // S4
     }
     TPHASE(TPH_A1);
 
@@ -639,21 +642,24 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
     // x head = data-driven decoder output (+ last physics layer) into the same accumulator
     stage_signal(sid++);   // S5
     TPHASE(TPH_A2);
-    stage_wait(bar0, ph0);
-
-    // ---- x head: xh = xh_p + xh_d, Gaussian log-likelihood of raw x, residual gradient -----------------
+    // the raw data row is fetched BEFORE waiting for the head MMAs (the global-load latency hides under them)
+    float xv[nxh];
     {
-      const float inv = INV[I_X];
       const long long lrow = row0 + prow;
       const long long drow = P.idx ? P.idx[lrow] : lrow;
       const float* xr = P.x + drow * ndx + nxh * hh;
-      float ssq = 0.0f;
-      float xv[nxh];
 #pragma unroll
       for (int c = 0; c < nxh / 4; ++c) {
         const float4 t4 = __ldg(reinterpret_cast<const float4*>(xr) + c);
         xv[4 * c] = t4.x; xv[4 * c + 1] = t4.y; xv[4 * c + 2] = t4.z; xv[4 * c + 3] = t4.w;
       }
+    }
+    stage_wait(bar0, ph0);
+
+    // ---- x head: xh = xh_p + xh_d, Gaussian log-likelihood of raw x, residual gradient -----------------
+    {
+      const float inv = INV[I_X];
+      float ssq = 0.0f;
       float v[nxh];
       tld<nxh>(trow + C_X + nxh * hh, v);
       const float gsc = pvalid ? sg : 0.0f;
@@ -724,7 +730,7 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
           for (int i = 0; i < 8; ++i) g[i] = g[i] * inv * (1.0f - a[i] * a[i]);
           tc::tmem_put8_packed(th, tl, g);
         }
-        stage_signal(sid++);   // S7
+        stage_signal<false>(sid++);   // S7
       }
       stage_wait(bar1, ph1);   // wgrad fx1 done: BIG (hidden activations) may be overwritten
       {
@@ -778,7 +784,7 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
             tc::tmem_put8_packed(th, tl, g);
           }
         }
-        stage_signal(sid++);   // S9
+        stage_signal<false>(sid++);   // S9
         TPHASE(TPH_BWD2);
         stage_wait(bar0, ph0);   // dgrad physics layer 1
         {
