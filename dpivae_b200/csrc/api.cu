@@ -56,6 +56,21 @@ struct dpivae_model {
   int timing = 0;
   cudaEvent_t ev[14] = {};   // start/stop pairs: enc_fwd, dec, enc_bwd, reduce, adam, lat_fwd, lat_bwd
   int ev_used[7] = {0, 0, 0, 0, 0, 0, 0};
+  // set while a step graph is being captured: kernels read step / offsets from this device-resident state
+  StepState* cur_ss = nullptr;
+  float* cur_log = nullptr;
+  long long cur_log_cap = 0;
+};
+
+// A captured training step (advance -> loss fwd/bwd -> Adam) replayable without host arguments.
+struct dpivae_step_graph {
+  dpivae_model* h = nullptr;
+  StepState* d_state = nullptr;
+  cudaGraph_t graph = nullptr, graph_u = nullptr;
+  cudaGraphExec_t exec = nullptr, exec_u = nullptr;   // one step / `unroll` consecutive steps
+  int unroll = 1;
+  uint64_t philox_inc = 0;
+  int launches_per_step = 0;
 };
 
 struct KTimer {
@@ -582,6 +597,7 @@ static int run_loss(dpivae_handle_t h, const dpivae_batch_t* bt, const dpivae_rn
   D.n_mc = bt->n_mc; D.cond = bt->cond; D.with_grad = with_grad;
   D.RB = L.RB; D.n_chunks = L.n_chunks; D.n_rowblocks = L.n_rowblocks;
   D.latent_only = latent_only;
+  D.rng.ss = h->cur_ss;
   D.rng.mode = rng->mode; D.rng.seed = rng->seed;
   for (int k = 0; k < 4; ++k) { D.rng.eps[k] = rng->eps[k]; D.rng.offset[k] = rng->offset[k]; D.rng.grid_threads[k] = rng->grid_threads[k] ? rng->grid_threads[k] : 256; }
   if (w) { D.beta_x = w->beta_x; D.alpha_x = w->alpha_x; D.alpha_c = w->alpha_c; D.alpha_y = w->alpha_y; }
@@ -682,6 +698,8 @@ int dpivae_adam_step(dpivae_handle_t h, int64_t step, float max_grad_norm, void*
   A.beta1 = 0.9f; A.beta2 = 0.999f; A.eps = 1e-8f;
   A.n_params = h->d.n_params;
   A.clip_coef = nullptr;
+  A.ss = h->cur_ss; A.log = h->cur_log; A.log_cap = h->cur_log_cap; A.lsx_index = h->d.log_sigma_x;
+  A.scalars = h->grads + h->d.n_params;   // captured-step mode requires the [grads | 8 scalars] layout (checked there)
   if (max_grad_norm > 0.0f) {
     launch_gradnorm(h->grads, h->d.n_params, max_grad_norm, h->d_clip, st);
     A.clip_coef = h->d_clip;
@@ -702,6 +720,97 @@ int dpivae_train_step(dpivae_handle_t h, const dpivae_batch_t* batch, const dpiv
   const int l0 = h->last_launches;
   if (dpivae_adam_step(h, step, max_grad_norm, stream)) return 1;
   h->last_launches += l0;
+  return 0;
+}
+
+int dpivae_step_graph_create(dpivae_handle_t h, const dpivae_batch_t* batch, const dpivae_rng_t* rng, uint64_t philox_inc,
+                             const dpivae_loss_weights_t* w, int64_t first_step, float max_grad_norm,
+                             const int64_t* idx_pool, int64_t pool_rows, int64_t* idx_cur, float* scalars, float* step_log,
+                             int64_t log_cap, int32_t unroll, void* workspace, size_t workspace_bytes, void* stream,
+                             dpivae_step_graph_t* out) {
+  if (!h || !batch || !rng || !out || !scalars) return fail("null argument");
+  if (unroll < 1 || unroll > 64) return fail("unroll must be in 1..64");
+  if (rng->mode != 1) return fail("a captured step draws its noise in-kernel (rng mode 1)");
+  if (first_step < 1) return fail("first_step is 1-based");
+  if (idx_pool && (!idx_cur || pool_rows < 1)) return fail("idx_pool needs idx_cur and pool_rows >= 1");
+  if (step_log && log_cap < 1) return fail("step_log needs log_cap >= 1");
+  if (scalars != h->grads + h->d.n_params) return fail("captured steps need the scalars right behind the gradient buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  dpivae_step_graph* g = new dpivae_step_graph();
+  g->h = h;
+  g->philox_inc = philox_inc;
+  if (cudaMalloc(&g->d_state, sizeof(StepState)) != cudaSuccess) { delete g; return fail("cudaMalloc(step state) failed"); }
+  *out = g;
+  if (dpivae_step_graph_reset(g, rng, first_step, stream)) { dpivae_step_graph_destroy(g); *out = nullptr; return 1; }
+  CUDA_OK(cudaStreamSynchronize(st));
+  const int timing = h->timing;
+  h->timing = 0;
+  h->cur_ss = g->d_state; h->cur_log = step_log; h->cur_log_cap = log_cap;
+  int rc = 0;
+  auto capture = [&](int reps, cudaGraph_t* graph_out) -> int {
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) return fail("cudaStreamBeginCapture failed");
+    int r = 0;
+    for (int rep = 0; rep < reps && !r; ++rep) {
+      AdvanceParams A;
+      memset(&A, 0, sizeof(A));
+      A.ss = g->d_state; A.philox_inc = philox_inc; A.n_groups = h->n_groups;
+      for (int k = 0; k < h->n_groups; ++k) A.lr[k] = h->lr[k];
+      A.idx_pool = (const long long*)idx_pool; A.pool_rows = pool_rows; A.B = batch->B; A.idx_cur = (long long*)idx_cur;
+      launch_advance(A, st);
+      dpivae_batch_t b = *batch;
+      if (idx_pool) b.idx = idx_cur;
+      dpivae_outputs_t o;
+      memset(&o, 0, sizeof(o));
+      o.scalars = scalars;
+      r = dpivae_train_step(h, &b, rng, w, first_step, max_grad_norm, &o, workspace, workspace_bytes, stream);
+      g->launches_per_step = h->last_launches + 1;
+    }
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(st, &graph);
+    if (!r && e != cudaSuccess) r = fail(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    *graph_out = graph;
+    return r;
+  };
+  rc = capture(1, &g->graph);
+  if (!rc && unroll > 1) rc = capture(unroll, &g->graph_u);
+  g->unroll = unroll > 1 ? unroll : 1;
+  h->cur_ss = nullptr; h->cur_log = nullptr; h->cur_log_cap = 0;
+  h->timing = timing;
+  if (!rc && cudaGraphInstantiate(&g->exec, g->graph, 0) != cudaSuccess) rc = fail("cudaGraphInstantiate failed");
+  if (!rc && g->graph_u && cudaGraphInstantiate(&g->exec_u, g->graph_u, 0) != cudaSuccess) rc = fail("cudaGraphInstantiate failed");
+  if (rc) { dpivae_step_graph_destroy(g); *out = nullptr; return 1; }
+  return 0;
+}
+
+int dpivae_step_graph_reset(dpivae_step_graph_t g, const dpivae_rng_t* rng, int64_t next_step, void* stream) {
+  if (!g || !rng || next_step < 1) return fail("bad argument");
+  StepState s;
+  memset(&s, 0, sizeof(s));
+  s.step = next_step - 1;                                                  // advance_kernel increments before use
+  for (int k = 0; k < 4; ++k) s.philox_off[k] = rng->offset[k] - g->philox_inc;
+  // pageable host source: the copy is staged before the call returns
+  CUDA_OK(cudaMemcpyAsync(g->d_state, &s, sizeof(s), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return 0;
+}
+
+int dpivae_step_graph_launch(dpivae_step_graph_t g, int32_t n_steps, void* stream) {
+  if (!g || !g->exec || n_steps < 0) return fail("bad argument");
+  int left = n_steps;
+  if (g->exec_u)
+    for (; left >= g->unroll; left -= g->unroll) CUDA_OK(cudaGraphLaunch(g->exec_u, (cudaStream_t)stream));
+  for (; left > 0; --left) CUDA_OK(cudaGraphLaunch(g->exec, (cudaStream_t)stream));
+  g->h->last_launches = n_steps * g->launches_per_step;
+  return 0;
+}
+
+int dpivae_step_graph_destroy(dpivae_step_graph_t g) {
+  if (!g) return 0;
+  if (g->exec) cudaGraphExecDestroy(g->exec);
+  if (g->graph) cudaGraphDestroy(g->graph);
+  if (g->exec_u) cudaGraphExecDestroy(g->exec_u);
+  if (g->graph_u) cudaGraphDestroy(g->graph_u);
+  cudaFree(g->d_state);
+  delete g;
   return 0;
 }
 

@@ -191,6 +191,10 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
   constexpr bool mlp = PHYS == 0;
   const int d1 = mlp ? P.pl[0].N : 0, d2 = mlp ? P.pl[1].N : 0, d3 = mlp ? P.pl[2].N : 0;
   float* part = P.part + (long long)blockIdx.x * P.part_stride;
+  long long t_last = (PROF && tid == 0) ? clock64() : 0;   // phase accounting starts here: setup is phase 0
+  long long phs[PROF ? TPH_COUNT : 1];
+#pragma unroll
+  for (int i = 0; i < (PROF ? TPH_COUNT : 1); ++i) phs[i] = 0;
 
   float* INV = smf + (T.f_inv >> 2);
   float* BX = smf + (T.f_bias_x >> 2);    // fx1 bias (+ last physics-layer bias)
@@ -353,10 +357,6 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
   float dlsx = 0.0f;
   float tot[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   uint32_t wacc = 0;  // 0 on the first tile (weight-gradient accumulators start from zero)
-  long long phs[PROF ? TPH_COUNT : 1];
-#pragma unroll
-  for (int i = 0; i < (PROF ? TPH_COUNT : 1); ++i) phs[i] = 0;
-  long long t_last = (PROF && tid == 0) ? clock64() : 0;
   TPHASE(TPH_SETUP);
 
 

@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(NT, 2) enc_fwd_kernel(const __grid_constant__ 
   enc_max_dims(P, K0m, Hm, Om);
   const EncSmem S = enc_plan(K0m, Hm, Om);
   const long long ntiles = (P.B + TILE - 1) / TILE;
-  for (int u = 0; u < P.n_units; ++u) {
+  for (int u = blockIdx.y; u < P.n_units; u += gridDim.y) {   // small batches: one CTA column per unit
     const EncUnit& U = P.u[u];
     if (U.src == 2 && P.y == nullptr) continue;
     __syncthreads();
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(NT, 2) enc_bwd_kernel(const __grid_constant__ 
   const EncSmem S = enc_plan(K0m, Hm, Om);
   const long long ntiles = (P.B + TILE - 1) / TILE;
   float* part = P.part + (long long)blockIdx.x * P.part_stride;
-  for (int u = 0; u < P.n_units; ++u) {
+  for (int u = blockIdx.y; u < P.n_units; u += gridDim.y) {   // small batches: one CTA column per unit
     const EncUnit& U = P.u[u];
     __syncthreads();
     for (int e = threadIdx.x; e < S.total; e += NT) sm[e] = 0.0f;
@@ -152,11 +152,16 @@ size_t enc_smem_bytes(const EncParams& p, bool bwd) {
   return (size_t)enc_plan(K0m, Hm, Om).total * sizeof(float);
 }
 
+// Few tiles (small minibatches): the units run in parallel CTA columns (gridDim.y) instead of one after the other
+// in every CTA; many tiles: unit-outer loop in each persistent CTA (every weight matrix staged once per CTA).
+static dim3 enc_grid(const EncParams& p, int grid) {
+  return dim3((unsigned)grid, (unsigned)((long long)grid * p.n_units <= 2LL * 148 ? p.n_units : 1), 1);
+}
 void launch_enc_fwd(const EncParams& p, int grid, size_t smem, cudaStream_t s) {
-  enc_fwd_kernel<<<grid, NT, smem, s>>>(p);
+  enc_fwd_kernel<<<enc_grid(p, grid), NT, smem, s>>>(p);
 }
 void launch_enc_bwd(const EncParams& p, int grid, size_t smem, cudaStream_t s) {
-  enc_bwd_kernel<<<grid, NT, smem, s>>>(p);
+  enc_bwd_kernel<<<enc_grid(p, grid), NT, smem, s>>>(p);
 }
 
 int configure_enc_kernels() {

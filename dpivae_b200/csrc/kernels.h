@@ -23,7 +23,18 @@ struct PhysLayerS {
   long long g_w, g_b;      // offsets in the frozen-weights device buffer
 };
 
+// Device-resident values of a captured (CUDA-graph) training step: advanced on the device by advance_kernel, so a
+// replayed graph needs no per-step host arguments (dpivae.py:390-436 loop counter, Adam bias corrections, generator offset)
+struct StepState {
+  long long step;                      // 1-based optimizer step of the CURRENT replay
+  unsigned long long philox_off[4];    // generator offsets of the current step's noise tensors
+  float step_size[16];                 // lr_g / (1 - beta1^step)
+  float bc2_sqrt;                      // sqrt(1 - beta2^step)
+  float _pad;
+};
+
 struct RngP {
+  const StepState* ss;     // non-null: Philox offsets come from the device-resident step state
   int mode;                // 0 injected buffers, 1 philox (torch.cuda normal_ stream)
   const float* eps[4];
   unsigned long long seed;
@@ -195,7 +206,24 @@ struct AdamParams {
   float beta1, beta2, eps;
   long long n_params;
   const float* clip_coef;       // device scalar or nullptr
+  // captured-step mode: step sizes from the device state; per-step log row = 8 loss scalars + log_sigma_x
+  const StepState* ss;
+  const float* scalars;
+  float* log;                   // [log_cap][9] ring, or nullptr
+  long long log_cap;
+  long long lsx_index;
 };
+
+struct AdvanceParams {
+  StepState* ss;
+  unsigned long long philox_inc;    // generator offset consumed by one step
+  float lr[16];
+  int n_groups;
+  const long long* idx_pool;        // [pool_rows][B] minibatch indices, or nullptr
+  long long pool_rows, B;
+  long long* idx_cur;               // [B] indices of the current step (read by the step's kernels)
+};
+void launch_advance(const AdvanceParams& p, cudaStream_t s);
 
 size_t dec_smem_bytes(const DecParams& p);
 void launch_dec(const DecParams& p, int grid, cudaStream_t s);

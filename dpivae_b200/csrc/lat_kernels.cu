@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(LNT) lat_fwd_kernel(const __grid_constant__ De
       const unsigned long long grow = (unsigned long long)(P.row_off + row0 + r);
       const int b = block_of_l(P, i), il = i - P.blk_start[b], nzb = P.blk_size[b];
       const unsigned long long li = ((unsigned long long)m * (unsigned long long)P.Bg + grow) * nzb + il;
-      v = P.rng.mode == 0 ? P.rng.eps[b][li] : philox_normal_elem(P.rng.seed, P.rng.offset[b], P.rng.grid_threads[b], li);
+      v = P.rng.mode == 0 ? P.rng.eps[b][li] : philox_normal_elem(P.rng.seed, P.rng.ss ? P.rng.ss->philox_off[b] : P.rng.offset[b], P.rng.grid_threads[b], li);
     }
     S.EPS[e] = v;
     epsg[e] = v;
@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(LNT) lat_encode_kernel(const __grid_constant__
   for (int i = 0; i < P.Z; ++i) {
     const int b = block_of_l(P, i), il = i - P.blk_start[b], nzb = P.blk_size[b];
     const unsigned long long li = ((unsigned long long)m * (unsigned long long)P.Bg + grow) * nzb + il;
-    lsm[i * LNT + tid] = P.rng.mode == 0 ? P.rng.eps[b][li] : philox_normal_elem(P.rng.seed, P.rng.offset[b], P.rng.grid_threads[b], li);
+    lsm[i * LNT + tid] = P.rng.mode == 0 ? P.rng.eps[b][li] : philox_normal_elem(P.rng.seed, P.rng.ss ? P.rng.ss->philox_off[b] : P.rng.offset[b], P.rng.grid_threads[b], li);
   }
   float dens = 0.0f;
   for (int b = 0; b < P.n_blk; ++b) {

@@ -62,10 +62,39 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamParams P) {
   float m = P.m[i], v = P.v[i];
   m = fmaf(1.0f - P.beta1, g - m, m);              // exp_avg.lerp_(grad, 1 - beta1)
   v = fmaf(1.0f - P.beta2, g * g, v * P.beta2);    // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
-  const float denom = sqrtf(v) / P.bc2_sqrt + P.eps;
-  P.params[i] = p - P.step_size[gid] * (m / denom);
+  const float bc2_sqrt = P.ss ? P.ss->bc2_sqrt : P.bc2_sqrt;
+  const float step_size = P.ss ? P.ss->step_size[gid] : P.step_size[gid];
+  const float denom = sqrtf(v) / bc2_sqrt + P.eps;
+  const float pn = p - step_size * (m / denom);
+  P.params[i] = pn;
   P.m[i] = m;
   P.v[i] = v;
+  if (P.log != nullptr && P.ss != nullptr) {
+    // per-step log row of the device-resident loop (dpivae.py:439-451): 8 loss scalars + log_sigma_x after the update
+    float* row = P.log + ((P.ss->step - 1) % P.log_cap) * 9;
+    if (i < 8) row[i] = P.scalars[i];
+    if (i == P.lsx_index) row[8] = pn;
+  }
+}
+
+// Head of a captured step: advance the device-resident step state and stage the step's minibatch indices.
+__global__ void __launch_bounds__(1024) advance_kernel(const AdvanceParams P) {
+  __shared__ long long s_step;
+  if (threadIdx.x == 0) {
+    StepState* S = P.ss;
+    const long long step = S->step + 1;
+    S->step = step;
+    for (int k = 0; k < 4; ++k) S->philox_off[k] += P.philox_inc;
+    const double bc1 = 1.0 - pow(0.9, (double)step), bc2 = 1.0 - pow(0.999, (double)step);
+    for (int g = 0; g < P.n_groups; ++g) S->step_size[g] = (float)((double)P.lr[g] / bc1);
+    S->bc2_sqrt = (float)sqrt(bc2);
+    s_step = step;
+  }
+  __syncthreads();
+  if (P.idx_pool != nullptr) {
+    const long long* src = P.idx_pool + ((s_step - 1) % P.pool_rows) * P.B;
+    for (long long i = threadIdx.x; i < P.B; i += blockDim.x) P.idx_cur[i] = src[i];
+  }
 }
 
 // FP32 FFMA peak micro-benchmark: 16 independent accumulator chains per thread.
@@ -120,6 +149,7 @@ void launch_reduce(const ReduceParams& p, cudaStream_t s) {
 void launch_gradnorm(const float* grads, long long n, float max_norm, float* clip_coef, cudaStream_t s) {
   gradnorm_kernel<<<1, 1024, 0, s>>>(grads, n, max_norm, clip_coef);
 }
+void launch_advance(const AdvanceParams& p, cudaStream_t s) { advance_kernel<<<1, 1024, 0, s>>>(p); }
 void launch_adam(const AdamParams& p, cudaStream_t s) {
   adam_kernel<<<(unsigned)((p.n_params + 255) / 256), 256, 0, s>>>(p);
 }

@@ -338,11 +338,92 @@ class _Engine:
             _lib.check(self.lib.dpivae_ffma_peak_tflops(C.byref(v), C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)))
         return float(v.value)
 
+    def step_graph(self, x, c, y, n, weights, idx_pool=None, max_grad_norm=0.0, log_cap=1024, unroll=1):
+        return StepGraph(self, x, c, y, n, weights, idx_pool, max_grad_norm, log_cap, unroll)
+
     def adam_step(self, step, max_grad_norm=0.0):
         with torch.cuda.device(self.dev):
             stream = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
             _lib.check(self.lib.dpivae_adam_step(self.handle, int(step), float(max_grad_norm), stream))
             self.launches += self.lib.dpivae_last_launch_count(self.handle)
+
+
+class StepGraph:
+    """Device-resident training loop (include/dpivae_b200.h dpivae_step_graph_*): one captured training step --
+    minibatch gather from a resident index pool, loss, backward, clip, Adam -- whose step counter, Adam bias
+    corrections and generator offset live on the device.  `run(k)` enqueues k replays without any host
+    synchronisation; `log` is the (log_cap, 9) device ring of per-step [8 loss scalars | log_sigma_x]."""
+
+    def __init__(self, eng, x, c, y, n, weights, idx_pool=None, max_grad_norm=0.0, log_cap=1024, unroll=1):
+        self.eng, self.n = eng, int(n)
+        with torch.cuda.device(eng.dev):
+            self.pool = None if idx_pool is None else idx_pool.to(eng.dev, torch.int64).contiguous()
+            B = int(self.pool.shape[1]) if self.pool is not None else int(x.shape[0])
+            self.idx_cur = torch.zeros(B, dtype=torch.int64, device=eng.dev) if self.pool is not None else None
+            b, self._keep, _ = eng._batch(x, c, y, n, False, self.idx_cur, None, 0)
+            self.B = B
+            self.log = torch.zeros((int(log_cap), 9), dtype=torch.float32, device=eng.dev)
+            # private workspace: the graph holds its address for as long as it lives
+            self.ws = torch.empty(eng.lib.dpivae_workspace_bytes(eng.handle, B, n), dtype=torch.uint8, device=eng.dev)
+            # captured on a private stream (the legacy default stream cannot be captured); replays go to the caller's stream
+            self._cap_stream = torch.cuda.Stream(eng.dev)
+            self._cap_stream.wait_stream(torch.cuda.current_stream(eng.dev))
+            rng, self.inc = self._plan()
+            w = _lib.LossWeights(*[float(v) for v in weights])
+            self.handle = C.c_void_p(None)
+            st = C.c_void_p(self._cap_stream.cuda_stream)
+            _lib.check(eng.lib.dpivae_step_graph_create(
+                eng.handle, C.byref(b), C.byref(rng), self.inc, C.byref(w), eng.step_count + 1, float(max_grad_norm),
+                _ptr(self.pool), 0 if self.pool is None else int(self.pool.shape[0]), _ptr(self.idx_cur), _ptr(eng.scalars),
+                _ptr(self.log), int(log_cap), int(unroll), _ptr(self.ws), self.ws.numel(), st, C.byref(self.handle)))
+            torch.cuda.current_stream(eng.dev).wait_stream(self._cap_stream)
+
+    def _gen(self):
+        dev = self.eng.dev
+        return torch.cuda.default_generators[dev.index if dev.index is not None else torch.cuda.current_device()]
+
+    def _plan(self):
+        """Philox plan of the next step at the torch CUDA generator's current offset (generator left untouched)."""
+        eng, gen = self.eng, self._gen()
+        r = _lib.Rng()
+        r.mode, r.seed = 1, gen.initial_seed()
+        off = gen.get_offset()
+        new_off = eng.lib.dpivae_philox_plan(eng.handle, self.B, self.n, 0, off, eng.sm_count, eng.max_threads_per_sm, C.byref(r))
+        return r, int(new_off - off)
+
+    def set_pool(self, idx_pool):
+        """New minibatch rows for the coming steps (same shape; step t reads row (t - 1) % pool_rows)."""
+        self.pool.copy_(idx_pool.to(self.eng.dev, torch.int64), non_blocking=True)
+
+    def run(self, n_steps):
+        """Enqueue n_steps training steps; keeps eng.step_count and the torch CUDA generator in step with the device."""
+        eng = self.eng
+        with torch.cuda.device(eng.dev):
+            st = C.c_void_p(torch.cuda.current_stream(eng.dev).cuda_stream)
+            rng, _ = self._plan()
+            _lib.check(eng.lib.dpivae_step_graph_reset(self.handle, C.byref(rng), eng.step_count + 1, st))
+            _lib.check(eng.lib.dpivae_step_graph_launch(self.handle, int(n_steps), st))
+            gen = self._gen()
+            gen.set_offset(gen.get_offset() + self.inc * int(n_steps))
+            eng.launches += eng.lib.dpivae_last_launch_count(eng.handle)
+            eng.step_count += int(n_steps)
+
+    def log_rows(self, first_step, n_steps):
+        """Host copy of the log rows of optimizer steps first_step .. first_step + n_steps - 1 (1-based)."""
+        cap = self.log.shape[0]
+        rows = [(first_step - 1 + i) % cap for i in range(n_steps)]
+        return self.log[torch.tensor(rows, device=self.log.device)].cpu()
+
+    def close(self):
+        if self.handle:
+            self.eng.lib.dpivae_step_graph_destroy(self.handle)
+            self.handle = C.c_void_p(None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class _LossFn(torch.autograd.Function):

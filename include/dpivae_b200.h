@@ -151,6 +151,33 @@ int dpivae_train_step(dpivae_handle_t h, const dpivae_batch_t* batch, const dpiv
                       const dpivae_loss_weights_t* w, int64_t step, float max_grad_norm,
                       const dpivae_outputs_t* out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Device-resident training loop (dpivae.py:390-436 iterated): ONE training step -- minibatch gather from a
+ * resident index pool (dpivae.py:403-404), loss, backward, clip, Adam -- captured in a CUDA graph whose per-step
+ * values (optimizer step -> Adam bias corrections, generator offset, pool row) live in device memory and are
+ * advanced by the graph's first kernel, so replaying it needs no host arguments and no host synchronisation.
+ *   rng          mode 1; offset[] / grid_threads[] = plan of the FIRST step (dpivae_philox_plan)
+ *   philox_inc   generator offset one step consumes (plan's return value - its offset_in)
+ *   w            loss weights, constant over the captured steps (annealing == None, utils/annealing.py:12-14)
+ *   idx_pool     [pool_rows][B] int64 rows of the resident data set, step t uses row (t-1) % pool_rows; NULL = batch->idx / identity
+ *   idx_cur      [B] int64 scratch the step's kernels gather through (required with idx_pool)
+ *   scalars      the 8 loss scalars of the latest step; must directly follow the bound gradient buffer
+ *   step_log     optional [log_cap][9] ring: row (t-1) % log_cap = 8 loss scalars + log_sigma_x after step t
+ *                (the per-iteration values the reference logs, dpivae.py:439-451)
+ *   unroll       >= 1: besides the single-step graph, a second graph of `unroll` consecutive steps is captured;
+ *                dpivae_step_graph_launch uses it for every full group of `unroll` steps (fewer host launches)
+ * The workspace, data and index buffers must stay alive and unchanged in address while the graph exists. */
+typedef struct dpivae_step_graph* dpivae_step_graph_t;
+int dpivae_step_graph_create(dpivae_handle_t h, const dpivae_batch_t* batch, const dpivae_rng_t* rng, uint64_t philox_inc,
+                             const dpivae_loss_weights_t* w, int64_t first_step, float max_grad_norm,
+                             const int64_t* idx_pool, int64_t pool_rows, int64_t* idx_cur, float* scalars, float* step_log,
+                             int64_t log_cap, int32_t unroll, void* workspace, size_t workspace_bytes, void* stream,
+                             dpivae_step_graph_t* out);
+/* Re-base the device state: the next replay is optimizer step `next_step` and draws at rng->offset[]. */
+int dpivae_step_graph_reset(dpivae_step_graph_t g, const dpivae_rng_t* rng, int64_t next_step, void* stream);
+/* Enqueue n_steps replays on `stream` (no host synchronisation). */
+int dpivae_step_graph_launch(dpivae_step_graph_t g, int32_t n_steps, void* stream);
+int dpivae_step_graph_destroy(dpivae_step_graph_t g);
+
 /* transform_inputs -> encode (models/vae.py:161-162, 125-151): zx (n,B,nz_x), zc, zy, dens_z (n,B).
  * x_is_standardised != 0 mirrors DPIVAE.encode(x_t, n), which receives already-scaled inputs. */
 int dpivae_encode(dpivae_handle_t h, const dpivae_batch_t* batch, const dpivae_rng_t* rng,
