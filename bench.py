@@ -47,6 +47,23 @@ METRIC = "ELBO train samples/s (fwd+bwd+Adam)"
 UNIT = "datapoints/s"
 
 
+_JSON_FD = None
+
+
+def _guard_stdout():
+    """Library chatter on fd 1 (e.g. NCCL's version banner) goes to stderr: stdout carries the ONE JSON line only."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def synth(case_mod, n, gen_seed, device):
     """Synthetic minibatch of the case's shape: z ~ ground-truth priors, x = full_model(z) + noise
     (utils/data.py:9-52), generated on `device`."""
@@ -172,7 +189,7 @@ def run_reference(a, wl):
             "dtype": "f32", "data": "synthetic", "config": {"workload": a.workload, "rows_per_step": rows, "n_mc": wl["n_mc"]},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def _dist_setup():
@@ -279,7 +296,7 @@ def run_encode(a, wl):
                              "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
                              "peak_source": "measured copy bandwidth (MEASURED_PEAKS.json)" if peaks else "fallback 6.65 TB/s"},
                 "clocks": clk.summary()}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -352,7 +369,7 @@ def run_ensemble(a, wl):
                            "parallelism": f"{M * world} independent members, no collective"},
                 "gpu_launches": launches, "clocks": clk.summary(),
                 "elbo": [float(mb["eng"].scalars[0]) for mb in members]}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -373,6 +390,7 @@ def main():
                          "tc_fp16 = tcgen05 with plain fp16 operands (reduced precision, reported separately)")
     ap.add_argument("--no-other-modes", action="store_true", help="skip the short runs of the other math modes")
     a = ap.parse_args()
+    _guard_stdout()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     wl = dict(WORKLOADS[a.workload])
     if a.rows:
@@ -571,7 +589,7 @@ def main():
             line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"{crow} rows x {n} MC, 3 steps after 1 warm-up (oracle port, fp32 torch CPU)",
                                     "ms_per_step": sec * 1e3}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -822,6 +822,83 @@ int dpivae_encode(dpivae_handle_t h, const dpivae_batch_t* batch, const dpivae_r
   return run_loss(h, batch, rng, nullptr, 0, 1, x_is_standardised, &o, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+int dpivae_decode(dpivae_handle_t h, const float* zx_in, const float* zc, const float* zy, int64_t B, int32_t n_mc,
+                  const dpivae_outputs_t* out, void* ws, size_t ws_bytes, void* stream) {
+  if (!h || !zx_in || !zc || !zy || !out) return fail("null argument");
+  if (!h->params) return fail("dpivae_bind has not been called");
+  if (B < 1 || n_mc < 1) return fail("bad batch sizes");
+  if (h->d.phys_kind == DPIVAE_PHYS_MLP && !h->d_frozen) return fail("dpivae_set_physics_mlp has not been called");
+  const WsLayout L = ws_layout(h, B, n_mc);
+  if (!ws || ws_bytes < L.total) return fail("workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  char* base = (char*)ws;
+  // the fused FFMA decoder kernel in forward-only mode; its encoder-side inputs (head pre-activations, data rows)
+  // are zero-filled workspace regions, its losses are discarded
+  float* zeros = (float*)(base + L.hid);
+  CUDA_OK(cudaMemsetAsync(base + L.hid, 0, (size_t)h->H_tot * B * sizeof(float), st));
+  CUDA_OK(cudaMemsetAsync(base + L.headpre, 0, (size_t)h->O_tot * B * sizeof(float), st));
+  DecParams D = h->dec;
+  D.params = h->params; D.frozen = h->d_frozen;
+  D.x = zeros; D.c = zeros; D.y = zeros; D.idx = nullptr;
+  D.B = B; D.Bg = B; D.row_off = 0;
+  D.n_mc = n_mc; D.cond = 0; D.with_grad = 0;
+  D.RB = L.RB; D.n_chunks = L.n_chunks; D.n_rowblocks = L.n_rowblocks;
+  D.latent_only = 0;
+  D.rng.ss = nullptr; D.rng.mode = 1; D.rng.seed = 0;   // the sampled latents are overwritten by the caller's: any noise will do
+  for (int k = 0; k < 4; ++k) { D.rng.eps[k] = nullptr; D.rng.offset[k] = 0; D.rng.grid_threads[k] = 256; }
+  D.beta_x = D.alpha_x = D.alpha_c = D.alpha_y = 1.0f;
+  D.headpre = (float*)(base + L.headpre); D.gpre = (float*)(base + L.gpre);
+  D.part = (float*)(base + L.part); D.part_stride = h->part_stride;
+  D.phase = nullptr;
+  memset(&D.out, 0, sizeof(D.out));
+  D.out.xh_p = out->xh_p; D.out.xh_d = out->xh_d; D.out.ch = out->ch; D.out.lsc = out->log_sigma_c;
+  D.out.yh = out->yh; D.out.lsy = out->log_sigma_y;
+  D.zin_x = zx_in; D.zin_c = zc; D.zin_y = zy;
+  launch_dec(D, L.grid_dec, st);
+  h->last_launches = 1;
+  h->last_dec_tc = 0;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int dpivae_prior_net(dpivae_handle_t h, const float* c, const float* y, int64_t B, float* loc_c, float* scale_tril_c,
+                     float* loc_y, float* scale_tril_y, void* ws, size_t ws_bytes, void* stream) {
+  if (!h || !c || !loc_c || !scale_tril_c) return fail("null argument");
+  if (y && (!loc_y || !scale_tril_y)) return fail("y given without output buffers");
+  if (!h->params) return fail("dpivae_bind has not been called");
+  if (B < 1) return fail("bad batch size");
+  const WsLayout L = ws_layout(h, B, 1);
+  if (!ws || ws_bytes < L.total) return fail("workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  char* base = (char*)ws;
+  EncParams E = h->enc;
+  E.params = h->params;
+  E.x = nullptr; E.c = c; E.y = y; E.idx = nullptr;
+  E.B = B;
+  E.hid = (float*)(base + L.hid); E.headpre = (float*)(base + L.headpre); E.gpre = nullptr;
+  E.with_hid = 0; E.x_is_standardised = 0;
+  E.part = nullptr; E.part_stride = h->part_stride;
+  EncParams E2 = E;
+  E2.n_units = E.n_units - h->n_enc_units;
+  for (int u = 0; u < E2.n_units; ++u) E2.u[u] = E.u[h->n_enc_units + u];
+  launch_enc_fwd(E2, L.grid_enc, enc_smem_bytes(h->enc, true), st);
+  launch_prior_post(E.headpre, B, h->dec.hpri[0], h->d.nz_c, loc_c, scale_tril_c, st);
+  int launches = 2;
+  if (y) { launch_prior_post(E.headpre, B, h->dec.hpri[1], h->d.nz_y, loc_y, scale_tril_y, st); ++launches; }
+  h->last_launches = launches;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int dpivae_gaussian_sample(const float* loc, const float* scale_tril, const float* eps, int32_t n_mc, int64_t B, int32_t nz,
+                           float* z, float* dens, void* stream) {
+  if (!loc || !scale_tril || !eps || !z || !dens) return fail("null argument");
+  if (n_mc < 1 || B < 1 || nz < 1 || nz > DPIVAE_MAX_Z) return fail("bad sizes");
+  launch_gaussian_sample(loc, scale_tril, eps, n_mc, B, nz, z, dens, (cudaStream_t)stream);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 uint64_t dpivae_philox_plan(dpivae_handle_t h, int64_t B_global, int32_t n_mc, int32_t cond, uint64_t offset_in,
                             int32_t sm_count, int32_t max_threads_per_sm, dpivae_rng_t* rng) {
   if (!h || !rng) return offset_in;

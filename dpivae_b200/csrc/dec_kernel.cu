@@ -309,6 +309,14 @@ __global__ void __launch_bounds__(NT, 1) dec_kernel(const __grid_constant__ DecP
           }
           lpy = -0.5f * ((float)P.nz_y * LOG_2PI + mh) - hl;
         }
+        if (P.zin_x != nullptr && valid) {
+          // DPIVAE.decode (models/vae.py:153-158): the caller's latents (n, B, .) replace the sampled ones
+          const long long o = (long long)m * B + row0 + r;
+          const int nzi = P.nz_x + P.nd_p;
+          for (int k = 0; k < nzi; ++k) ZXIN[k * LDP + p] = P.zin_x[o * nzi + k];
+          for (int k = 0; k < P.nz_c; ++k) ZD[k * LDP + p] = P.zin_c[o * P.nz_c + k];
+          for (int k = 0; k < P.nz_y; ++k) ZD[(P.nz_c + k) * LDP + p] = P.zin_y[o * P.nz_y + k];
+        }
         const float klp = dens - ((lpx + lpc) + lpy);
         SC[SC_KL * LDP + p] = valid ? klp : 0.0f;
         SC[SC_W * LDP + p] = valid ? wpair : 0.0f;

@@ -101,7 +101,14 @@ struct DecParams {
   float* dzrec;            // [tiles][nz_c + nz_y + nz_x][128]: dL/dz per pair
   float* epsbuf;           // [tiles][Z][128]: reparameterisation noise
   float* rowkl;            // [B]: per-row KL (MC mean)
+  // decode-only calls (DPIVAE.decode, models/vae.py:153-158): user latents (n, B, .) replace the encoder's
+  const float *zin_x, *zin_c, *zin_y;
 };
+
+// DPIVAE.prior_net post-processing and GaussianEncoder.sample on given (loc, scale_tril) (optim_kernels.cu)
+void launch_prior_post(const float* headpre, long long B, int row0, int nz, float* loc, float* tril, cudaStream_t s);
+void launch_gaussian_sample(const float* loc, const float* tril, const float* eps, int n, long long B, int nz, float* z,
+                            float* dens, cudaStream_t s);
 
 // ---- tensor-core decoder kernel (dec_tc_kernel.cu): DecParams + its own shared-memory plan (BYTE offsets) ----
 struct TcParams {

@@ -97,6 +97,41 @@ __global__ void __launch_bounds__(1024) advance_kernel(const AdvanceParams P) {
   }
 }
 
+// FactorizedNN head post-processing (models/encoders.py:121-128): loc = clamp(pre, +-50), sigma = exp(clamp(pre, -7, 3)),
+// scale_tril = diag(sigma + 1e-8).  headpre rows [row0, row0 + nz) = mean head, [row0 + nz, row0 + 2 nz) = sigma head.
+__global__ void __launch_bounds__(256) prior_post_kernel(const float* __restrict__ headpre, long long B, int row0, int nz,
+                                                         float* __restrict__ loc, float* __restrict__ tril) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  for (int i = 0; i < nz; ++i) {
+    const float pm = headpre[(long long)(row0 + i) * B + b], ps = headpre[(long long)(row0 + nz + i) * B + b];
+    loc[b * nz + i] = fminf(fmaxf(pm, -50.0f), 50.0f);
+    const float sg = expf(fminf(fmaxf(ps, -7.0f), 3.0f)) + 1e-8f;
+    for (int j = 0; j < nz; ++j) tril[(b * nz + i) * nz + j] = i == j ? sg : 0.0f;
+  }
+}
+
+// GaussianEncoder.sample without output transform (models/encoders.py:73-93): z = loc + L eps,
+// log q = -1/2 (nz log 2 pi + |eps|^2) - sum log diag L; eps, z (n, B, nz), dens (n, B), L (B, nz, nz) lower-triangular.
+__global__ void __launch_bounds__(256) gaussian_sample_kernel(const float* __restrict__ loc, const float* __restrict__ tril,
+                                                              const float* __restrict__ eps, int n, long long B, int nz,
+                                                              float* __restrict__ z, float* __restrict__ dens) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= (long long)n * B) return;
+  const long long b = q % B;
+  const float* e = eps + q * nz;
+  const float* L = tril + b * nz * nz;
+  float ss = 0.0f, hld = 0.0f;
+  for (int i = 0; i < nz; ++i) {
+    float acc = loc[b * nz + i];
+    for (int j = 0; j <= i; ++j) acc = fmaf(L[i * nz + j], e[j], acc);
+    z[q * nz + i] = acc;
+    ss = fmaf(e[i], e[i], ss);
+    hld += logf(L[i * nz + i]);
+  }
+  dens[q] = -0.5f * ((float)nz * 1.8378770664093453f + ss) - hld;
+}
+
 // FP32 FFMA peak micro-benchmark: 16 independent accumulator chains per thread.
 __global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, float a, float b, int iters) {
   float acc[16];
@@ -148,6 +183,14 @@ void launch_reduce(const ReduceParams& p, cudaStream_t s) {
 }
 void launch_gradnorm(const float* grads, long long n, float max_norm, float* clip_coef, cudaStream_t s) {
   gradnorm_kernel<<<1, 1024, 0, s>>>(grads, n, max_norm, clip_coef);
+}
+void launch_prior_post(const float* headpre, long long B, int row0, int nz, float* loc, float* tril, cudaStream_t s) {
+  prior_post_kernel<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(headpre, B, row0, nz, loc, tril);
+}
+void launch_gaussian_sample(const float* loc, const float* tril, const float* eps, int n, long long B, int nz, float* z,
+                            float* dens, cudaStream_t s) {
+  const long long tot = (long long)n * B;
+  gaussian_sample_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(loc, tril, eps, n, B, nz, z, dens);
 }
 void launch_advance(const AdvanceParams& p, cudaStream_t s) { advance_kernel<<<1, 1024, 0, s>>>(p); }
 void launch_adam(const AdamParams& p, cudaStream_t s) {

@@ -314,6 +314,61 @@ class _Engine:
             del keep
             return zx, zc, zy, dens
 
+    def decode(self, zx_in, zc, zy):
+        with torch.cuda.device(self.dev):
+            v = self.vae
+            squeeze = zx_in.dim() == 2
+            zs = [t.to(self.dev, torch.float32).contiguous() for t in (zx_in, zc, zy)]
+            if squeeze:
+                zs = [t.unsqueeze(0) for t in zs]
+            n, B = int(zs[0].shape[0]), int(zs[0].shape[1])
+            want = (v.nz_x + len(v.idx_c_phys), v.nz_c, v.nz_y)
+            for t, d in zip(zs, want):
+                if tuple(t.shape) != (n, B, d):
+                    raise ValueError(f"decode: expected latents of shape ({n}, {B}, {d}), got {tuple(t.shape)}")
+            shp = {"xh_p": v.nd_x, "xh_d": v.nd_x, "ch": v.nd_c, "log_sigma_c": v.nd_c, "yh": v.nd_y, "log_sigma_y": v.nd_y}
+            outs = {k: torch.empty((n, B, d), dtype=torch.float32, device=self.dev) for k, d in shp.items()}
+            out = _lib.Outputs()
+            for k, t in outs.items():
+                setattr(out, k, t.data_ptr())
+            ws = self._workspace(B, n)
+            stream = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+            _lib.check(self.lib.dpivae_decode(self.handle, _ptr(zs[0]), _ptr(zs[1]), _ptr(zs[2]), B, n, C.byref(out), _ptr(ws),
+                                              ws.numel(), stream))
+            self.launches += self.lib.dpivae_last_launch_count(self.handle)
+            res = tuple(outs[k] for k in ("xh_p", "xh_d", "ch", "log_sigma_c", "yh", "log_sigma_y"))
+            return tuple(t.squeeze(0) for t in res) if squeeze else res
+
+    def prior_net(self, c, y=None):
+        with torch.cuda.device(self.dev):
+            v = self.vae
+            c = c.to(self.dev, torch.float32).contiguous()
+            y = None if y is None else y.to(self.dev, torch.float32).contiguous()
+            B = int(c.shape[0])
+            loc_c = torch.empty((B, v.nz_c), dtype=torch.float32, device=self.dev)
+            tril_c = torch.empty((B, v.nz_c, v.nz_c), dtype=torch.float32, device=self.dev)
+            loc_y = tril_y = None
+            if y is not None:
+                loc_y = torch.empty((B, v.nz_y), dtype=torch.float32, device=self.dev)
+                tril_y = torch.empty((B, v.nz_y, v.nz_y), dtype=torch.float32, device=self.dev)
+            ws = self._workspace(B, 1)
+            stream = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+            _lib.check(self.lib.dpivae_prior_net(self.handle, _ptr(c), _ptr(y), B, _ptr(loc_c), _ptr(tril_c), _ptr(loc_y),
+                                                 _ptr(tril_y), _ptr(ws), ws.numel(), stream))
+            self.launches += self.lib.dpivae_last_launch_count(self.handle)
+            return loc_c, tril_c, loc_y, tril_y
+
+    def gaussian_sample(self, loc, tril, eps):
+        with torch.cuda.device(self.dev):
+            n, B, nz = (int(d) for d in eps.shape)
+            z = torch.empty((n, B, nz), dtype=torch.float32, device=self.dev)
+            dens = torch.empty((n, B), dtype=torch.float32, device=self.dev)
+            stream = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+            _lib.check(self.lib.dpivae_gaussian_sample(_ptr(loc.contiguous()), _ptr(tril.contiguous()), _ptr(eps.contiguous()), n, B, nz,
+                                                       _ptr(z), _ptr(dens), stream))
+            self.launches += 1
+            return z, dens
+
     def set_math_mode(self, mode):
         """'fp32' (FFMA, default) | 'tc_fp16x3' (tcgen05, fp16 hi/lo split, fp32-accurate) | 'tc_fp16' (tcgen05, plain
         fp16 operands) -- include/dpivae_b200.h DPIVAE_MATH_*."""
@@ -561,10 +616,22 @@ class DPIVAE(nn.Module):
         return x_sample, xh_p, xh_d, c_sample, y_sample, zx, zc, zy, dens_z
 
     def decode(self, zx, zc, zy):
-        raise NotImplementedError("DPIVAE.decode on user-supplied latents is not part of the fused training-step path")
+        """models/vae.py:153-158: `zx` is the physics-decoder input [zx | c_phys]; (n, B, .) or (B, .) latents."""
+        return self.engine().decode(zx, zc, zy)
 
     def prior_net(self, c, y=None):
-        raise NotImplementedError("DPIVAE.prior_net is evaluated inside the fused kernels; use loss()/sample()")
+        """models/vae.py:99-110 -> (loc_c, scale_tril_c, loc_y | None, scale_tril_y | None)."""
+        return self.engine().prior_net(c, y)
 
     def sample_prior(self, c, y, n=1):
-        raise NotImplementedError("DPIVAE.sample_prior is outside the fused training-step path")
+        """models/vae.py:112-123: draws (n, B, nz_c) then (n, B, nz_y) from torch's CUDA generator (the reference's
+        order), z = loc + sigma * eps and its log-density in the fused sampling kernel."""
+        eng = self.engine()
+        loc_c, tril_c, loc_y, tril_y = eng.prior_net(c, y)
+        with torch.cuda.device(eng.dev):
+            B = loc_c.shape[0]
+            eps_c = torch.empty((n, B, self.nz_c), dtype=torch.float32, device=eng.dev).normal_()
+            eps_y = torch.empty((n, B, self.nz_y), dtype=torch.float32, device=eng.dev).normal_()
+        zc, dens_zc = eng.gaussian_sample(loc_c, tril_c, eps_c)
+        zy, dens_zy = eng.gaussian_sample(loc_y, tril_y, eps_y)
+        return zc, dens_zc, zy, dens_zy

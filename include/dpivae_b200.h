@@ -184,6 +184,22 @@ int dpivae_encode(dpivae_handle_t h, const dpivae_batch_t* batch, const dpivae_r
                   int32_t x_is_standardised, float* zx, float* zc, float* zy, float* dens_z,
                   void* workspace, size_t workspace_bytes, void* stream);
 
+/* DPIVAE.decode (models/vae.py:153-158) on caller-supplied latents: zx_in (n,B,nz_x+nd_p) = [zx | c_phys],
+ * zc (n,B,nz_c), zy (n,B,nz_y) -> out->xh_p, xh_d (n,B,nd_x), ch, log_sigma_c (n,B,nd_c), yh, log_sigma_y (n,B,nd_y)
+ * (NULL outputs are skipped).  Forward only, fp32 FFMA kernels. */
+int dpivae_decode(dpivae_handle_t h, const float* zx_in, const float* zc, const float* zy, int64_t B, int32_t n_mc,
+                  const dpivae_outputs_t* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* DPIVAE.prior_net (models/vae.py:99-110): raw c (B,nd_c) and optional raw y (B,nd_y) -> standardise ->
+ * FactorizedNN (models/encoders.py:121-128) -> loc (B,nz), scale_tril (B,nz,nz) = diag(sigma + 1e-8). */
+int dpivae_prior_net(dpivae_handle_t h, const float* c, const float* y, int64_t B, float* loc_c, float* scale_tril_c,
+                     float* loc_y, float* scale_tril_y, void* workspace, size_t workspace_bytes, void* stream);
+
+/* GaussianEncoder.sample without output transform (models/encoders.py:73-93) on given parameters:
+ * z = loc + L eps (n,B,nz), dens = log N(z; loc, L L^T) (n,B); eps (n,B,nz) standard normal draws. */
+int dpivae_gaussian_sample(const float* loc, const float* scale_tril, const float* eps, int32_t n_mc, int64_t B, int32_t nz,
+                           float* z, float* dens, void* stream);
+
 /* Philox bookkeeping for rng mode 1: given the torch CUDA generator's current offset and the SM
  * count / max threads per SM of the device, fill rng->offset / grid_threads for the draws of one
  * forward (P: 3 tensors, S: 1, +1 if cond) and return the generator offset after them. */
