@@ -69,6 +69,7 @@ EXPORTS = [
     "dpivae_set_timing", "dpivae_last_kernel_ms", "dpivae_ffma_peak_tflops", "dpivae_set_phase_buffer",
     "dpivae_set_math_mode", "dpivae_last_used_tensor_cores",
     "dpivae_decode", "dpivae_prior_net", "dpivae_gaussian_sample",
+    "dpivae_mc_mean", "dpivae_regression_metrics", "dpivae_linreg_r2",
     "dpivae_step_graph_create", "dpivae_step_graph_reset", "dpivae_step_graph_launch", "dpivae_step_graph_destroy",
 ]
 MATH_FP32, MATH_TC_FP16X3, MATH_TC_FP16 = 0, 1, 2
@@ -117,6 +118,9 @@ def load():
     lib.dpivae_decode.argtypes = [vp, vp, vp, vp, i64, i32, C.POINTER(Outputs), vp, C.c_size_t, vp]
     lib.dpivae_prior_net.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, vp, C.c_size_t, vp]
     lib.dpivae_gaussian_sample.argtypes = [vp, vp, vp, i32, i64, i32, vp, vp, vp]
+    lib.dpivae_mc_mean.argtypes = [vp, i32, i64, i32, vp, vp]
+    lib.dpivae_regression_metrics.argtypes = [vp, vp, i64, i32, vp, vp, vp]
+    lib.dpivae_linreg_r2.argtypes = [vp, vp, i64, i64, vp, vp, i64, i64, i32, vp, vp, vp]
     lib.dpivae_step_graph_reset.argtypes = [vp, C.POINTER(Rng), i64, vp]
     lib.dpivae_step_graph_launch.argtypes = [vp, i32, vp]
     lib.dpivae_step_graph_destroy.argtypes = [vp]

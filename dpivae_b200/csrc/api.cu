@@ -899,6 +899,31 @@ int dpivae_gaussian_sample(const float* loc, const float* scale_tril, const floa
   return 0;
 }
 
+int dpivae_mc_mean(const float* v, int32_t n_mc, int64_t B, int32_t d, float* out, void* stream) {
+  if (!v || !out || n_mc < 1 || B < 1 || d < 1) return fail("bad argument");
+  launch_mc_mean(v, n_mc, B * d, out, (cudaStream_t)stream);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int dpivae_regression_metrics(const float* y_true, const float* y_pred, int64_t N, int32_t d, double* scratch, float* out3,
+                              void* stream) {
+  if (!y_true || !y_pred || !scratch || !out3 || N < 1 || d < 1 || d > 16) return fail("bad argument");
+  launch_regression_metrics(y_true, y_pred, N, d, scratch, out3, (cudaStream_t)stream);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int dpivae_linreg_r2(const float* X_train, const float* y_train, int64_t ldy_train, int64_t N_train, const float* X_test,
+                     const float* y_test, int64_t ldy_test, int64_t N_test, int32_t k, double* scratch, float* r2_out,
+                     void* stream) {
+  if (!X_train || !y_train || !X_test || !y_test || !scratch || !r2_out) return fail("null argument");
+  if (k < 1 || k > 8 || N_train < 1 || N_test < 1 || ldy_train < 1 || ldy_test < 1) return fail("bad sizes (1 <= k <= 8)");
+  launch_linreg_r2(X_train, y_train, ldy_train, N_train, X_test, y_test, ldy_test, N_test, k, scratch, r2_out, (cudaStream_t)stream);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 uint64_t dpivae_philox_plan(dpivae_handle_t h, int64_t B_global, int32_t n_mc, int32_t cond, uint64_t offset_in,
                             int32_t sm_count, int32_t max_threads_per_sm, dpivae_rng_t* rng) {
   if (!h || !rng) return offset_in;

@@ -232,6 +232,12 @@ struct AdvanceParams {
 };
 void launch_advance(const AdvanceParams& p, cudaStream_t s);
 
+// ---- post-processing on the device (metrics_kernels.cu) -----------------------------------------
+void launch_mc_mean(const float* v, int n, long long BD, float* out, cudaStream_t s);
+void launch_regression_metrics(const float* y, const float* p, long long N, int d, double* scratch, float* out3, cudaStream_t s);
+void launch_linreg_r2(const float* Xtr, const float* ytr, long long ldy_tr, long long Ntr, const float* Xte, const float* yte,
+                      long long ldy_te, long long Nte, int k, double* scratch, float* r2, cudaStream_t s);
+
 size_t dec_smem_bytes(const DecParams& p);
 void launch_dec(const DecParams& p, int grid, cudaStream_t s);
 void launch_enc_fwd(const EncParams& p, int grid, size_t smem, cudaStream_t s);

@@ -11,6 +11,7 @@ import torch
 from .modules import Decoder, FactorizedNN, FullCovarianceNN, GaussianEncoder, GradRevAdditive
 from .utils import (Annealing, ChainTransform, ChainTransformMasked, EarlyStopping, LayerGradRev, Logistic,
                     MarginalDistribution, ScalarLogger, ShiftScale, StandardScaler, device)
+from .metrics import linreg_r2, mc_mean, regression_metrics_device
 from .vae import DPIVAE
 
 _NAMES8 = ["ELBO", "KLx", "KLc", "KLy", "Rx", "Rc", "Ry", "reg"]
@@ -127,11 +128,12 @@ def train_model(args, vae, definition, data_train, data_val, path_metrics=None, 
     early_stopping = EarlyStopping(patience=args.patience, min_delta=args.min_delta)
     max_norm = float(args.max_grad_norm) if args.clip_gradients == True else 0.0  # noqa: E712
     ones = torch.ones(args.n_train)
-    it_range = range(args.n_iter)
+    start_iter = int(getattr(args, "start_iter", 0))   # > 0 when resuming from a checkpoint (dpivae_b200/checkpoint.py)
+    it_range = range(start_iter, args.n_iter)
     if progress:
         from tqdm import trange
 
-        it_range = trange(args.n_iter)
+        it_range = trange(start_iter, args.n_iter)
     w_alpha = (float(args.alpha_x), float(args.alpha_c), float(args.alpha_y))
 
     def log_iteration(it, row9, lambda_x_i, beta_x_i, beta_c_i, beta_y_i):
@@ -159,7 +161,7 @@ def train_model(args, vae, definition, data_train, data_val, path_metrics=None, 
         vf = max(1, int(args.val_freq))
         graph = eng.step_graph(x_train, c_train, y_train, args.n_mc_train, w, idx_pool=torch.zeros((vf, args.n_batch), dtype=torch.int64),
                                max_grad_norm=max_norm, log_cap=vf, unroll=min(vf, 64))
-        it = 0
+        it = start_iter
         stop = False
         while it < args.n_iter and not stop:
             it_end = min(args.n_iter, it + 1 if it % vf == 0 else (it // vf + 1) * vf + 1)   # chunk ends after a validation iteration
@@ -217,8 +219,9 @@ def evaluate_model(args, definition, model, data_test, cond=False):
     model.eval()
     with torch.no_grad():
         out = model.sample(x_test, c_test, cond=cond, n=args.n_mc_test)
-    y_pred = out[4].mean(dim=0).detach().cpu().numpy()
-    return {args.name: regression_metrics(y_test, y_pred)}, {args.name: y_pred}
+    # MC mean and R2 / MSE / MAE on the device (dpivae_b200/metrics.py); only 3 scalars and the prediction cross to the host
+    y_pred_dev = mc_mean(out[4])
+    return {args.name: regression_metrics_device(y_test, y_pred_dev)}, {args.name: y_pred_dev.cpu().numpy()}
 
 
 def disentanglement_metric(args, model, definition, data_train, data_test, regressor="linear", cond=False, use_mean=False):
@@ -232,10 +235,18 @@ def disentanglement_metric(args, model, definition, data_train, data_test, regre
     lat = {}
     for tag, data in (("train", data_train), ("test", data_test)):
         out = model.sample(data[0], data[1], cond=cond, n=n)
-        lat[tag] = [out[k].mean(dim=0).detach().cpu() for k in (5, 6, 7)]
+        lat[tag] = [mc_mean(out[k]) for k in (5, 6, 7)]
     z_train = data_train[3].squeeze(0).detach().cpu()
     z_test = data_test[3].squeeze(0).detach().cpu()
     score_test = []
+    if regressor == "linear":
+        # batched least squares + test R2 on the device: one (group, factor) fit per launch series, no latent D2H copy
+        r2 = [linreg_r2(ztr, z_train, zte, z_test).cpu().tolist() for ztr, zte in zip(lat["train"], lat["test"])]
+        for i, factor_i in enumerate(gen_factors):
+            for gi, tag in enumerate(("zx", "zc", "zy")):
+                score_test.append([tag, factor_i, r2[gi][i]])
+        return score_test
+    lat = {tag: [t.cpu() for t in v] for tag, v in lat.items()}
     for i, factor_i in enumerate(gen_factors):
         for tag, ztr, zte in zip(("zx", "zc", "zy"), lat["train"], lat["test"]):
             if regressor == "linear":

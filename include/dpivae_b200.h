@@ -200,6 +200,21 @@ int dpivae_prior_net(dpivae_handle_t h, const float* c, const float* y, int64_t 
 int dpivae_gaussian_sample(const float* loc, const float* scale_tril, const float* eps, int32_t n_mc, int64_t B, int32_t nz,
                            float* z, float* dens, void* stream);
 
+/* Post-processing of sample / encode outputs on the device (the callers right behind the hot path).
+ * dpivae_mc_mean: out (B,d) = mean over the leading MC axis of v (n,B,d)  (dpivae.py:548 `y_sample.mean(0)`,
+ *   dpivae.py:640-661 `z.mean(0)`).
+ * dpivae_regression_metrics: utils/metrics.py:11-32 = sklearn r2_score (uniform average over the d outputs),
+ *   mean_squared_error, mean_absolute_error -> out3 = {r2, mse, mae}; scratch = 4*d doubles (device).
+ * dpivae_linreg_r2: dpivae.py:672-690 with regressor == "linear": ordinary least squares (with intercept) of one
+ *   target column on k <= 8 latent columns of the training set, R2 of the fit on the test set.  y_* point at the
+ *   target column, ldy_* = its row stride in floats.  scratch = 80 doubles (device). */
+int dpivae_mc_mean(const float* v, int32_t n_mc, int64_t B, int32_t d, float* out, void* stream);
+int dpivae_regression_metrics(const float* y_true, const float* y_pred, int64_t N, int32_t d, double* scratch, float* out3,
+                              void* stream);
+int dpivae_linreg_r2(const float* X_train, const float* y_train, int64_t ldy_train, int64_t N_train, const float* X_test,
+                     const float* y_test, int64_t ldy_test, int64_t N_test, int32_t k, double* scratch, float* r2_out,
+                     void* stream);
+
 /* Philox bookkeeping for rng mode 1: given the torch CUDA generator's current offset and the SM
  * count / max threads per SM of the device, fill rng->offset / grid_threads for the draws of one
  * forward (P: 3 tensors, S: 1, +1 if cond) and return the generator offset after them. */

@@ -89,3 +89,47 @@ def test_train_model_device_loop_matches_host_loop():
             assert abs(a - b) <= 2e-6 * max(1.0, abs(a)), (name, a, b)
     for k in pa:
         assert gu.rel_l2(pb[k], pa[k]) < 2e-6, k
+
+
+def test_checkpoint_resume_is_exact(tmp_path):
+    """dpivae_b200.checkpoint (SURVEY.md §8(f) N4): weights + scaler statistics + Adam state + generator positions;
+    a run resumed from the file ends bit-identical to the uninterrupted one."""
+    import importlib
+
+    import dpivae_b200 as dpv
+    from helpers import make_args
+
+    case_mod = importlib.import_module("dpivae_b200.cases.simple_beam")
+    d = case_mod.definition
+
+    def data():
+        torch.manual_seed(4)
+        return (dpv.sample_response(d, 256, sample_dist=dpv.get_prior_dist(d["dict_gt"])),
+                dpv.sample_response(d, 128, sample_dist=dpv.get_prior_dist(d["dict_gt"])))
+
+    def mk(n_iter, start=0):
+        return make_args(case_mod, "dpivae", use_seed=True, seed=21, n_train=256, n_val=128, n_batch=64, n_iter=n_iter,
+                         val_freq=5, n_mc_train=8, n_mc_val=8, start_iter=start)
+
+    tr, va = data()
+    vae = dpv.setup_model(mk(20), d, tr)
+    vae, _ = dpv.train_model(mk(20), vae, d, tr, va)
+    full = {k: p.detach().clone().cpu() for k, p in vae.named_parameters() if p.requires_grad}
+
+    tr, va = data()
+    vae1 = dpv.setup_model(mk(11), d, tr)
+    vae1, _ = dpv.train_model(mk(11), vae1, d, tr, va)
+    path = tmp_path / "ckpt.pt"
+    dpv.save_checkpoint(path, vae1)
+    st = torch.load(path, map_location="cpu", weights_only=False)
+    assert st["optim"]["step"] == 11 and set(st["scalers"]) == {"x", "c", "y"}
+    assert set(st["optim"]["exp_avg"]) == {k for k, p in vae1.named_parameters() if p.requires_grad}
+
+    tr2, va2 = data()
+    torch.manual_seed(12345)   # scramble: everything must come back from the file
+    vae2 = dpv.setup_model(mk(20, 11), d, (tr2[0] * 3.0 + 1.0, tr2[1], tr2[2], tr2[3]))   # deliberately wrong scaler fit
+    dpv.load_checkpoint(path, vae2)
+    vae2, _ = dpv.train_model(mk(20, 11), vae2, d, tr, va)
+    for k, p in vae2.named_parameters():
+        if p.requires_grad:
+            assert torch.equal(p.detach().cpu(), full[k]), k

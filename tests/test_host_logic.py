@@ -129,3 +129,34 @@ def test_case_physics_models_match_assets():
         ref = orc.PHYSICS[phys["kind"]](phys, z)
         out = case.definition["part_model"](z)
         assert torch.allclose(out, ref, rtol=1e-6, atol=1e-6), name
+
+
+def test_checkpoint_state_round_trip_on_host():
+    """checkpoint dict: reference state_dict names + scaler statistics survive a save / load without a GPU."""
+    import importlib
+    import io
+
+    import torch
+
+    import dpivae_b200 as dpv
+    from helpers import make_args
+
+    case_mod = importlib.import_module("dpivae_b200.cases.damped_oscillator")
+    d = case_mod.definition
+    torch.manual_seed(0)
+    tr = dpv.sample_response(d, 64, sample_dist=dpv.get_prior_dist(d["dict_gt"]))
+    args = make_args(case_mod, "vae", use_seed=True, seed=5, n_train=64, n_batch=16)
+    vae = dpv.setup_model(args, d, tr)
+    st = dpv.checkpoint_state(vae)
+    assert st["format"] == "dpivae_b200.checkpoint/1" and "optim" not in st   # no engine without a GPU
+    buf = io.BytesIO()
+    torch.save(st, buf)
+    buf.seek(0)
+    st2 = torch.load(buf, weights_only=False)
+    args2 = make_args(case_mod, "vae", use_seed=True, seed=6, n_train=64, n_batch=16)
+    vae2 = dpv.setup_model(args2, d, (tr[0] * 2.0, tr[1], tr[2], tr[3]))
+    dpv.load_checkpoint_state(vae2, st2)
+    for k, v in vae.state_dict().items():
+        assert torch.equal(v, vae2.state_dict()[k]), k
+    assert torch.equal(vae2.transform_x.mean_, vae.transform_x.mean_) and torch.equal(vae2.transform_x.scale_, vae.transform_x.scale_)
+    assert "log_sigma_x" in st["model"] and "encoder.net.f_cov.weight" in st["model"]

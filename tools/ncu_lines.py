@@ -13,11 +13,16 @@ from collections import Counter, defaultdict
 
 rep, cubin = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+import os
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + (["-k", os.environ["NCU_KERNEL"]] if os.environ.get("NCU_KERNEL") else []), capture_output=True, text=True).stdout
 rows = list(csv.reader(src.splitlines()))
 hdr = rows[1]
 ix = {h: i for i, h in enumerate(hdr)}
-data = rows[2:]
+data = []
+for r_ in rows[2:]:
+    if r_ and r_[0] == "Kernel Name":   # several captured launches: keep the first
+        break
+    data.append(r_)
 dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout.splitlines()
 lines = []  # per instruction: (file, line, inlined_at)
 cur = ("?", 0, "")
