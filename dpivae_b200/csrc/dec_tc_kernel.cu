@@ -362,8 +362,24 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
 
   if (warp == 8) {
     // ================= MMA-issue warp: mirrors the stage sequence of the epilogue warps =================================
+    // all 32 lanes run the descriptor arithmetic (uniform datapath); MMAs / commits are predicated on the elected lane.
+    // The tensor-memory base is a compile-time 0 here (one CTA per SM owning all 512 columns; checked below) and the
+    // operand bases are recomputed from the kernel parameters, so that every MMA operand is provably warp-uniform.
+    if (tb != 0u) __trap();
+    constexpr uint32_t tbu = 0u;
+    const uint32_t el = tc::elect_one();
     int it = 0;
     uint32_t sid = 0, wacc = 0;
+    // PROF: issuer-side accounting (lane 0): cycles blocked waiting for stage signals vs cycles spent issuing MMAs
+    long long iw = 0, ii = 0, itl = PROF ? clock64() : 0;
+#define ISSUER_MARK(acc)                 \
+  do {                                   \
+    if (PROF && lane == 0) {             \
+      const long long _t = clock64();    \
+      acc += _t - itl;                   \
+      itl = _t;                          \
+    }                                    \
+  } while (0)
     for (long long rb = blockIdx.x; rb < P.n_rowblocks; rb += gridDim.x, ++it) {
       const int buf = it & 1;
       const unsigned char* rec = RECB + (size_t)buf * T.rec_buf;
@@ -371,85 +387,109 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
       tc::mbar_wait(rbar + buf, (uint32_t)(it >> 1) & 1u);   // the tile record (latent operand) has landed
       __syncwarp();
       issuer_wait(sid++);   // S0
-      if (lane == 0) {
-        tc::issue_fwd(tb + C_H, oLAT, oWFX0, 128, KZ, 0, terms);
-        if constexpr (mlp) tc::issue_fwd(tb + C_X, oLAT, oWP0, d1, KZ, 0, terms);
-        tc::commit(bar0);
+        ISSUER_MARK(iw);
+      {
+        tc::issue_fwd_w(el, tbu + C_H, oLAT, oWFX0, 128, KZ, 0, terms);
+        if constexpr (mlp) tc::issue_fwd_w(el, tbu + C_X, oLAT, oWP0, d1, KZ, 0, terms);
+        tc::commit_w(el, bar0);
       }
       __syncwarp();
+      ISSUER_MARK(ii);
       if (P.with_grad) {
         issuer_wait(sid++);   // S1
-        if (lane == 0) {
-          tc::issue_wgrad(tb + C_AW1, oBIG, oOA, 16, wacc, terms);
-          tc::commit(bar1);
+        ISSUER_MARK(iw);
+        {
+          tc::issue_wgrad_w(el, tbu + C_AW1, oBIG, oOA, 16, wacc, terms);
+          tc::commit_w(el, bar1);
         }
         __syncwarp();
+        ISSUER_MARK(ii);
       }
       if constexpr (mlp) {
         issuer_wait(sid++);   // S2
-        if (lane == 0) {
-          tc::issue_fwd_ts(tb + C_S, tb + C_A0, oWP1, d2, d1, 0, terms);
-          tc::commit(bar0);
+        ISSUER_MARK(iw);
+        {
+          tc::issue_fwd_ts_w(el, tbu + C_S, tbu + C_A0, oWP1, d2, d1, 0, terms);
+          tc::commit_w(el, bar0);
         }
         __syncwarp();
+        ISSUER_MARK(ii);
       }
       if (P.with_grad) {
         issuer_wait(sid++);   // S3
-        if (lane == 0) {
-          tc::issue_wgrad(tb + C_AW0, oBIG, oLAT, KZ, wacc, terms);
-          tc::commit(bar1);
+        ISSUER_MARK(iw);
+        {
+          tc::issue_wgrad_w(el, tbu + C_AW0, oBIG, oLAT, KZ, wacc, terms);
+          tc::commit_w(el, bar1);
         }
         __syncwarp();
+        ISSUER_MARK(ii);
       }
       if constexpr (mlp) {
         issuer_wait(sid++);   // S4
-        if (lane == 0) {
-          tc::issue_fwd_ts(tb + C_X, tb + C_A1, oWP2, d3, d2, 0, terms);
-          tc::commit(bar0);
+        ISSUER_MARK(iw);
+        {
+          tc::issue_fwd_ts_w(el, tbu + C_X, tbu + C_A1, oWP2, d3, d2, 0, terms);
+          tc::commit_w(el, bar0);
         }
         __syncwarp();
+        ISSUER_MARK(ii);
       }
       issuer_wait(sid++);   // S5
-      if (lane == 0) {
-        tc::issue_fwd(tb + C_X, oBIG, oWFX1, ndx, 128, 0, terms);
-        if constexpr (mlp) tc::issue_fwd_ts(tb + C_X, tb + C_A2, oWP3, ndx, d3, 1, terms);
-        tc::commit(bar0);
+        ISSUER_MARK(iw);
+      {
+        tc::issue_fwd_w(el, tbu + C_X, oBIG, oWFX1, ndx, 128, 0, terms);
+        if constexpr (mlp) tc::issue_fwd_ts_w(el, tbu + C_X, tbu + C_A2, oWP3, ndx, d3, 1, terms);
+        tc::commit_w(el, bar0);
       }
       __syncwarp();
+      ISSUER_MARK(ii);
       if (P.with_grad) {
         issuer_wait(sid++);   // S6: the dgrads the next epilogues wait for go first (bar0), the weight gradient of fx1 on bar1
-        if (lane == 0) {
-          tc::issue_dgrad(tb + C_H, oG, oWFX1, ndx, 128, 0, terms);
-          if constexpr (mlp) tc::issue_dgrad(tb + C_X, oG, oWP3, ndx, d3, 0, terms);
-          tc::commit(bar0);
-          tc::issue_wgrad(tb + C_W1, oBIG, oG, ndx, wacc, terms);
-          tc::commit(bar1);
+        ISSUER_MARK(iw);
+        {
+          tc::issue_dgrad_w(el, tbu + C_H, oG, oWFX1, ndx, 128, 0, terms);
+          if constexpr (mlp) tc::issue_dgrad_w(el, tbu + C_X, oG, oWP3, ndx, d3, 0, terms);
+          tc::commit_w(el, bar0);
+          tc::issue_wgrad_w(el, tbu + C_W1, oBIG, oG, ndx, wacc, terms);
+          tc::commit_w(el, bar1);
         }
         __syncwarp();
+        ISSUER_MARK(ii);
         if constexpr (mlp) {
           issuer_wait(sid++);   // S7
-          if (lane == 0) {
-            tc::issue_dgrad_ts(tb + C_S, tb + C_A2, oWP2, d3, d2, 0, terms);
-            tc::commit(bar0);
+        ISSUER_MARK(iw);
+          {
+            tc::issue_dgrad_ts_w(el, tbu + C_S, tbu + C_A2, oWP2, d3, d2, 0, terms);
+            tc::commit_w(el, bar0);
           }
           __syncwarp();
+          ISSUER_MARK(ii);
         }
         issuer_wait(sid++);   // S8
-        if (lane == 0) {
-          tc::issue_wgrad(tb + C_W0, oBIG, oLAT, KZ, wacc, terms);
-          tc::commit(bar1);
+        ISSUER_MARK(iw);
+        {
+          tc::issue_wgrad_w(el, tbu + C_W0, oBIG, oLAT, KZ, wacc, terms);
+          tc::commit_w(el, bar1);
         }
         __syncwarp();
+        ISSUER_MARK(ii);
         if constexpr (mlp) {
           issuer_wait(sid++);   // S9
-          if (lane == 0) {
-            tc::issue_dgrad_ts(tb + C_X, tb + C_A1, oWP1, d2, d1, 0, terms);
-            tc::commit(bar0);
+        ISSUER_MARK(iw);
+          {
+            tc::issue_dgrad_ts_w(el, tbu + C_X, tbu + C_A1, oWP1, d2, d1, 0, terms);
+            tc::commit_w(el, bar0);
           }
           __syncwarp();
+          ISSUER_MARK(ii);
         }
       }
       wacc = 1u;
+    }
+    if (PROF && lane == 0) {
+      atomicAdd(reinterpret_cast<unsigned long long*>(P.phase) + 20, (unsigned long long)iw);
+      atomicAdd(reinterpret_cast<unsigned long long*>(P.phase) + 21, (unsigned long long)ii);
     }
   } else {
   const uint32_t rec_bytes = (uint32_t)P.rec_stride;
@@ -1004,7 +1044,10 @@ void launch_dec_tc(const TcParams& p, int grid, cudaStream_t s) {
     if (p.d.phase != nullptr) launch_one<true, 0, 64>(p, grid, s);
     else launch_one<false, 0, 64>(p, grid, s);
   } else if (ph == 1 && nx == 64) launch_one<false, 1, 64>(p, grid, s);
-  else if (ph == 2 && nx == 32) launch_one<false, 2, 32>(p, grid, s);
+  else if (ph == 2 && nx == 32) {
+    if (p.d.phase != nullptr) launch_one<true, 2, 32>(p, grid, s);
+    else launch_one<false, 2, 32>(p, grid, s);
+  }
 }
 
 bool dec_tc_has_variant(int phys_kind, int nd_x) {
@@ -1016,6 +1059,7 @@ int configure_dec_tc_kernel() {
   if (!e) e = (int)cudaFuncSetAttribute(dec_tc_kernel<false, 0, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
   if (!e) e = (int)cudaFuncSetAttribute(dec_tc_kernel<false, 1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
   if (!e) e = (int)cudaFuncSetAttribute(dec_tc_kernel<false, 2, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  if (!e) e = (int)cudaFuncSetAttribute(dec_tc_kernel<true, 2, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
   return e;
 }
 

@@ -344,5 +344,125 @@ static __device__ __noinline__ void issue_wgrad(uint32_t d_tmem, Op h, Op g, int
   }
 }
 
+
+// ---- warp-wide issue (uniform datapath) ------------------------------------------------------------------------------
+// The helpers above are called by ONE thread inside a divergent branch; there ptxas cannot prove the descriptors
+// warp-uniform and wraps every tcgen05.mma in an ELECT / 7 x R2UR.BROADCAST / BRA.U.ANY "waterfall" loop (~110 cycles
+// per MMA measured in the decoder kernel, above the 64-cycle tensor-pipe floor).  The *_w variants are executed by ALL
+// 32 converged lanes of the issue warp with operands derived only from kernel parameters, constants and uniform loop
+// counters: the descriptor arithmetic runs on the uniform datapath and only the MMA / commit themselves are predicated
+// on the lane elected once per stage (`el` != 0 in exactly one lane).
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t el;
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}\n" : "=r"(el));
+  return el;
+}
+__device__ __forceinline__ void mma_f16_w(uint32_t el, uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(el)
+      : "memory");
+}
+__device__ __forceinline__ void mma_f16_ts_w(uint32_t el, uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(el)
+      : "memory");
+}
+__device__ __forceinline__ void commit_w(uint32_t el, uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}\n" ::"r"(smem_u32(bar)), "r"(el)
+      : "memory");
+}
+__device__ __forceinline__ void issue_fwd_w(uint32_t el, uint32_t d_tmem, Op a, Op w, int N, int K, uint32_t accumulate, int terms) {
+  const uint32_t idesc = make_idesc(128, N, 0, 0);
+  const uint32_t ahi = 8u | DESC_VERSION_HI, whi = 8u | DESC_VERSION_HI;
+  const uint32_t astep = 2u * (uint32_t)a.R, wstep = 2u * (uint32_t)w.R;
+  const int ks = K >> 4;
+  for (int t = 0; t < terms; ++t) {
+    uint32_t alo = (((a.base + (t == 1 ? a.lo_off : 0u)) >> 4) & 0x3FFFu) | ((uint32_t)a.R << 16);
+    uint32_t wlo = (((w.base + (t == 2 ? w.lo_off : 0u)) >> 4) & 0x3FFFu) | ((uint32_t)w.R << 16);
+    for (int k = 0; k < ks; ++k) {
+      mma_f16_w(el, d_tmem, pack64(alo, ahi), pack64(wlo, whi), idesc, accumulate);
+      accumulate = 1;
+      alo += astep;
+      wlo += wstep;
+    }
+  }
+}
+__device__ __forceinline__ void issue_dgrad_w(uint32_t el, uint32_t d_tmem, Op g, Op w, int Nout, int Kin, uint32_t accumulate, int terms) {
+  const uint32_t idesc = make_idesc(128, Kin, 0, 1);
+  const uint32_t ghi = 8u | DESC_VERSION_HI, whi = (uint32_t)w.R | DESC_VERSION_HI;
+  const uint32_t gstep = 2u * (uint32_t)g.R, wstep = 16u;
+  const int ks = Nout >> 4;
+  for (int t = 0; t < terms; ++t) {
+    uint32_t glo = (((g.base + (t == 1 ? g.lo_off : 0u)) >> 4) & 0x3FFFu) | ((uint32_t)g.R << 16);
+    uint32_t wlo = (((w.base + (t == 2 ? w.lo_off : 0u)) >> 4) & 0x3FFFu) | (8u << 16);
+    for (int k = 0; k < ks; ++k) {
+      mma_f16_w(el, d_tmem, pack64(glo, ghi), pack64(wlo, whi), idesc, accumulate);
+      accumulate = 1;
+      glo += gstep;
+      wlo += wstep;
+    }
+  }
+}
+__device__ __forceinline__ void issue_fwd_ts_w(uint32_t el, uint32_t d_tmem, uint32_t a_tmem, Op w, int N, int K, uint32_t accumulate, int terms) {
+  const uint32_t idesc = make_idesc(128, N, 0, 0);
+  const uint32_t whi = 8u | DESC_VERSION_HI, wstep = 2u * (uint32_t)w.R;
+  const int ks = K >> 4;
+  for (int t = 0; t < terms; ++t) {
+    uint32_t a = a_tmem + (t == 1 ? (uint32_t)(K >> 1) : 0u);
+    uint32_t wlo = (((w.base + (t == 2 ? w.lo_off : 0u)) >> 4) & 0x3FFFu) | ((uint32_t)w.R << 16);
+    for (int k = 0; k < ks; ++k) {
+      mma_f16_ts_w(el, d_tmem, a, pack64(wlo, whi), idesc, accumulate);
+      accumulate = 1;
+      a += 8u;
+      wlo += wstep;
+    }
+  }
+}
+__device__ __forceinline__ void issue_dgrad_ts_w(uint32_t el, uint32_t d_tmem, uint32_t g_tmem, Op w, int Nout, int Kin, uint32_t accumulate, int terms) {
+  const uint32_t idesc = make_idesc(128, Kin, 0, 1);
+  const uint32_t whi = (uint32_t)w.R | DESC_VERSION_HI;
+  const int ks = Nout >> 4;
+  for (int t = 0; t < terms; ++t) {
+    uint32_t a = g_tmem + (t == 1 ? (uint32_t)(Nout >> 1) : 0u);
+    uint32_t wlo = (((w.base + (t == 2 ? w.lo_off : 0u)) >> 4) & 0x3FFFu) | (8u << 16);
+    for (int k = 0; k < ks; ++k) {
+      mma_f16_ts_w(el, d_tmem, a, pack64(wlo, whi), idesc, accumulate);
+      accumulate = 1;
+      a += 8u;
+      wlo += 16u;
+    }
+  }
+}
+__device__ __forceinline__ void issue_wgrad_w(uint32_t el, uint32_t d_tmem, Op h, Op g, int N, uint32_t accumulate, int terms) {
+  const uint32_t idesc = make_idesc(128, N, 1, 1);
+  const uint32_t hhi = (uint32_t)h.R | DESC_VERSION_HI, ghi = (uint32_t)g.R | DESC_VERSION_HI;
+  const int ks = h.R >> 4;
+  for (int t = 0; t < terms; ++t) {
+    uint32_t hlo = (((h.base + (t == 1 ? h.lo_off : 0u)) >> 4) & 0x3FFFu) | (8u << 16);
+    uint32_t glo = (((g.base + (t == 2 ? g.lo_off : 0u)) >> 4) & 0x3FFFu) | (8u << 16);
+    for (int k = 0; k < ks; ++k) {
+      mma_f16_w(el, d_tmem, pack64(hlo, hhi), pack64(glo, ghi), idesc, accumulate);
+      accumulate = 1;
+      hlo += 16u;
+      glo += 16u;
+    }
+  }
+}
+
 }  // namespace tc
 }  // namespace dpv

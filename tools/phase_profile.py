@@ -49,9 +49,13 @@ def main():
     tot = sum(v)
     tile = 64 if math == "fp32" else 128
     nchunks = rows * wl["n_mc"] / tile
-    print(f"workload {wl['case']} {wl['preset']} rows {rows} math {math}: {tot / nchunks:.0f} cycles per {tile}-pair tile")
+    print(f"workload {wl['case']} {wl['preset']} rows {rows} math {math}: {sum(v[:18]) / nchunks:.0f} cycles per {tile}-pair tile")
+    if math != "fp32":
+        tot = sum(v[:len(TC_NAMES)])
     for nme, c_ in zip(NAMES if math == "fp32" else TC_NAMES, v):
         print(f"  {nme:12s} {100.0 * c_ / tot:5.1f}%  {c_ / nchunks:9.0f} cyc/chunk")
+    if math != "fp32":
+        print(f"  MMA-issue warp: waiting for stage signals {v[20] / nchunks:9.0f} cyc/tile, issuing {v[21] / nchunks:9.0f} cyc/tile")
 
 
 if __name__ == "__main__":
