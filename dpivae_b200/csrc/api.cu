@@ -359,7 +359,7 @@ static int build_plan(dpivae_model* h) {
       auto f32 = [&](int floats) { int off = b; b += ((floats + 3) & ~3) * 4; return off; };
       T.f_inv = f32(16); T.f_bias_x = f32(64); T.f_bias_p1 = f32(32); T.f_bias_p2 = f32(64);
       T.f_aw0 = f32(2 * 64 * 4); T.f_ab0 = f32(2 * 64); T.f_aw1 = f32(2 * 64 * 4); T.f_ab1 = f32(8);
-      T.f_w0f = f32(128 * 8); T.f_wp0f = f32(64 * 4);
+      T.f_w0f = f32(4 * 128); T.f_wp0f = f32(64 * 4);   // f_w0f: exchange scratch of the physics-latent gradients
       T.f_dza = f32(nzd * 128); T.f_sc = f32(8 * 128); T.f_red = f32(256);
       T.o_bar = b; b += 64;
       T.total = (b + 127) & ~127;

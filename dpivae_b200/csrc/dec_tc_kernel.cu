@@ -204,11 +204,10 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
   float* AB0 = smf + (T.f_ab0 >> 2);      //                   [side][64]
   float* AW1 = smf + (T.f_aw1 >> 2);      // aux heads, transposed [side][64][4]: mean_0, mean_1, ls_0, ls_1 per hidden unit
   float* AB1 = smf + (T.f_ab1 >> 2);      //                   [side][4]
-  float* W0F = smf + (T.f_w0f >> 2);      // fx0 weights, fp32 [128][8] (dgrad to the latents on the CUDA cores)
   float* WP0F = smf + (T.f_wp0f >> 2);    // physics layer 0 weights w.r.t. the physics latents, fp32 [64][4]
-  const float4* W0F4 = reinterpret_cast<const float4*>(W0F);
   const float4* WP0F4 = reinterpret_cast<const float4*>(WP0F);
   float* DZA = smf + (T.f_dza >> 2);
+  float* GSX = smf + (T.f_w0f >> 2);      // [4][TP] exchange of the physics-latent gradient halves
   float* SC = smf + (T.f_sc >> 2);
   float* RED = smf + (T.f_red >> 2);
   float* R0 = smf + (T.a_big >> 2);      // end-of-kernel reduction scratch, aliases the BIG operand buffer
@@ -274,10 +273,6 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
   if constexpr (mlp) {
     for (int e = tid; e < d2; e += TNT) BP1[e] = P.frozen[P.pl[1].g_b + e];
     for (int e = tid; e < d3; e += TNT) BP2[e] = P.frozen[P.pl[2].g_b + e];
-  }
-  for (int e = tid; e < 128 * 8; e += TNT) {
-    const int k = e >> 3, j = e & 7;
-    W0F[e] = j < nzd ? prm[P.fx.g_w0 + (long long)k * nzd + j] : 0.0f;
   }
   if constexpr (mlp) {
     for (int e = tid; e < d1 * 4; e += TNT) {
@@ -466,24 +461,21 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
           __syncwarp();
           ISSUER_MARK(ii);
         }
-        issuer_wait(sid++);   // S8
+        issuer_wait(sid++);   // S8: first-layer dgrad dL/d(zc|zy) = dL/dh . W_fx0 (N = 16) and the weight gradient of fx0
         ISSUER_MARK(iw);
-        {
-          tc::issue_wgrad_w(el, tbu + C_W0, oBIG, oLAT, KZ, wacc, terms);
-          tc::commit_w(el, bar1);
-        }
-        __syncwarp();
-        ISSUER_MARK(ii);
+        // the small physics dgrad of stage S9 (its epilogue is next on the critical path) goes ahead of the 48 MMAs of
+        // stage S8, whose results are only needed at the end of the tile
         if constexpr (mlp) {
           issuer_wait(sid++);   // S9
-        ISSUER_MARK(iw);
-          {
-            tc::issue_dgrad_ts_w(el, tbu + C_X, tbu + C_A1, oWP1, d2, d1, 0, terms);
-            tc::commit_w(el, bar0);
-          }
-          __syncwarp();
-          ISSUER_MARK(ii);
+          ISSUER_MARK(iw);
+          tc::issue_dgrad_ts_w(el, tbu + C_X, tbu + C_A1, oWP1, d2, d1, 0, terms);
+          tc::commit_w(el, bar0);
         }
+        tc::issue_dgrad_w(el, tbu + C_T, oBIG, oWFX0, 128, KZ, 0, terms);
+        tc::issue_wgrad_w(el, tbu + C_W0, oBIG, oLAT, KZ, wacc, terms);
+        tc::commit_w(el, bar1);
+        __syncwarp();
+        ISSUER_MARK(ii);
       }
       wacc = 1u;
     }
@@ -774,39 +766,18 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
       }
       stage_wait(bar1, ph1);   // wgrad fx1 done: BIG (hidden activations) may be overwritten
       {
-        // ReLU mask on dL/dh; the first-layer dgrad dL/dz = dL/dh . W0 (K = 64 per thread, N = nzd <= 8) stays on the
-        // CUDA cores: this thread's partial sum over its 64 hidden units, halves combined through tensor memory
+        // ReLU mask on dL/dh -> operand of the fx0 weight gradient and of the first-layer dgrad (both MMAs of stage S8)
         const float inv = INV[I_XD];
-        float gz[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 2
         for (int c = 0; c < 8; ++c) {
           float v[8];
           tc::tmem_ld8(trow + C_H + 64 * hh + 8 * c, v);
           const uint32_t m8 = (uint32_t)(mkH >> (8 * c)) & 0xFFu;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            v[i] = ((m8 >> i) & 1u) ? v[i] * inv : 0.0f;
-            const float4 w0 = W0F4[2 * (64 * hh + 8 * c + i)], w1 = W0F4[2 * (64 * hh + 8 * c + i) + 1];
-            gz[0] = fmaf(v[i], w0.x, gz[0]); gz[1] = fmaf(v[i], w0.y, gz[1]); gz[2] = fmaf(v[i], w0.z, gz[2]); gz[3] = fmaf(v[i], w0.w, gz[3]);
-            gz[4] = fmaf(v[i], w1.x, gz[4]); gz[5] = fmaf(v[i], w1.y, gz[5]); gz[6] = fmaf(v[i], w1.z, gz[6]); gz[7] = fmaf(v[i], w1.w, gz[7]);
-          }
+          for (int i = 0; i < 8; ++i) v[i] = ((m8 >> i) & 1u) ? v[i] * inv : 0.0f;
           put8(pBIG, T.l_big, TP, 8 * hh + c, p, v);
         }
-        if (hh == 1) tc::tmem_st8(trow + C_T, gz);
-        stage_signal(sid++);   // S8: wgrad fx0, fire and forget (waited for at the end of the tile)
-        epi_sync();
-        tc::fence_after_sync();
-        if (hh == 0) {
-          // total dL/d(zc|zy): reversed + scaled gradient of the data-driven decoder (utils/transforms.py:207-219)
-          // plus the auxiliary decoders' gradient
-          float g1[8];
-          tc::tmem_ld8(trow + C_T, g1);
-          const float sc = -P.lambda_g0 * cx;
-          float* dz = P.dzrec + (long long)rb * (nzd + P.nz_x) * TP;
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            if (k < nzd) dz[k * TP + p] = fmaf(gz[k] + g1[k], sc, (k < P.nz_c ? awc : awy) * DZA[k * TP + p]);
-        }
+        stage_signal(sid++);   // S8: dgrad + wgrad fx0 (waited for at the end of the tile)
       }
       TPHASE(TPH_BWD1);
       if constexpr (mlp) {
@@ -843,17 +814,17 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
               gs[0] = fmaf(gv, w.x, gs[0]); gs[1] = fmaf(gv, w.y, gs[1]); gs[2] = fmaf(gv, w.z, gs[2]); gs[3] = fmaf(gv, w.w, gs[3]);
             }
           }
-          if (hh == 1) tc::tmem_st4(trow + C_T + 8, gs);
-          tc::fence_before_sync();
+          // halves combined through shared memory (the C_T columns of tensor memory belong to the fx0 dgrad MMA in flight)
+          if (hh == 1) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) GSX[k * TP + p] = gs[k];
+          }
           epi_sync();
-          tc::fence_after_sync();
           if (hh == 0) {
-            uint32_t r1[4];
-            tc::tmem_ld4(trow + C_T + 8, r1);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               if (k < P.nz_x)
-                P.dzrec[((long long)rb * (nzd + P.nz_x) + nzd + k) * TP + p] = (gs[k] + __uint_as_float(r1[k])) * cx / P.phys_in_std[k];
+                P.dzrec[((long long)rb * (nzd + P.nz_x) + nzd + k) * TP + p] = (gs[k] + GSX[k * TP + p]) * cx / P.phys_in_std[k];
           }
         }
         TPHASE(TPH_BWD3);
@@ -901,7 +872,18 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
           if (P.nz_x > 1) dzx[TP + tid] = (Q2[tid] + Q2[TP + tid]) * cx;
         }
       }
-      stage_wait(bar1, ph1);   // wgrad fx0 done: BIG and the record buffer are free for the next tile
+      stage_wait(bar1, ph1);   // dgrad + wgrad fx0 done: BIG and the record buffer are free for the next tile
+      if (hh == 0) {
+        // total dL/d(zc|zy): reversed + scaled gradient of the data-driven decoder (utils/transforms.py:207-219)
+        // plus the auxiliary decoders' gradient
+        float g1[8];
+        tc::tmem_ld8(trow + C_T, g1);
+        const float sc = -P.lambda_g0 * cx * INV[I_FX0D];
+        float* dz = P.dzrec + (long long)rb * (nzd + P.nz_x) * TP;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (k < nzd) dz[k * TP + p] = fmaf(g1[k], sc, (k < P.nz_c ? awc : awy) * DZA[k * TP + p]);
+      }
       epi_sync();
       TPHASE(TPH_BWD4);
 

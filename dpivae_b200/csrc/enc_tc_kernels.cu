@@ -137,7 +137,11 @@ __global__ void __launch_bounds__(ENT, 1) enc_tc_fwd_kernel(const __grid_constan
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
-  const uint32_t tb = *tptr;
+  // one CTA per SM owns all 512 tensor-memory columns: the base is 0, kept as a compile-time constant so that the
+  // MMA operands of the warp-wide issue are provably uniform
+  if (*tptr != 0u) __trap();
+  constexpr uint32_t tb = 0u;
+  const uint32_t el = tc::elect_one();
   const uint32_t trow = tb + ((uint32_t)(32 * q) << 16);
   const uint32_t C_H = 0, C_A = (uint32_t)Hc, C_O = (uint32_t)(2 * Hc);   // accumulator, packed hidden operand, heads
   uint32_t phase = 0;
@@ -189,10 +193,10 @@ __global__ void __launch_bounds__(ENT, 1) enc_tc_fwd_kernel(const __grid_constan
     tc::fence_async_smem();
     tc::fence_before_sync();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {   // warp-wide issue on the uniform datapath (tc.cuh), MMAs predicated on the elected lane
       tc::fence_after_sync();
-      tc::issue_fwd(tb + C_H, oX, oW0, Hc, KX, 0, 3);
-      tc::commit(bar);
+      tc::issue_fwd_w(el, C_H, oX, oW0, Hc, KX, 0, 3);
+      tc::commit_w(el, bar);
     }
     __syncwarp();
     tc::mbar_wait(bar, phase);
@@ -223,19 +227,10 @@ __global__ void __launch_bounds__(ENT, 1) enc_tc_fwd_kernel(const __grid_constan
     // ---- heads: A from tensor memory ----
     tc::fence_before_sync();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {
       tc::fence_after_sync();
-      const uint32_t idesc = tc::make_idesc(128, Oc, 0, 0);
-      uint32_t acc = 0;
-      for (int t = 0; t < 3; ++t) {
-        const uint32_t abase = tb + C_A + (t == 1 ? (uint32_t)(Hc >> 1) : 0u);
-        const uint32_t wb = oW1.base + (t == 2 ? oW1.lo_off : 0u);
-        for (int k = 0; k < Hc; k += 16) {
-          tc::mma_f16_ts(tb + C_O, abase + (uint32_t)(k >> 1), tc::desc_kmajor(wb, Oc, k >> 3), idesc, acc);
-          acc = 1;
-        }
-      }
-      tc::commit(bar);
+      tc::issue_fwd_ts_w(el, C_O, C_A, oW1, Oc, Hc, 0, 3);
+      tc::commit_w(el, bar);
     }
     __syncwarp();
     tc::mbar_wait(bar, phase);
@@ -338,7 +333,11 @@ __global__ void __launch_bounds__(ENT, 1) enc_tc_bwd_kernel(const __grid_constan
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
-  const uint32_t tb = *tptr;
+  // one CTA per SM owns all 512 tensor-memory columns: the base is 0, kept as a compile-time constant so that the
+  // MMA operands of the warp-wide issue are provably uniform
+  if (*tptr != 0u) __trap();
+  constexpr uint32_t tb = 0u;
+  const uint32_t el = tc::elect_one();
   const uint32_t trow = tb + ((uint32_t)(32 * q) << 16);
   const int nchunk = Hc > 128 ? 2 : 1;
   const int ch1 = Hc - 128;                       // first hidden column of the second (overlapping) chunk
@@ -423,15 +422,15 @@ __global__ void __launch_bounds__(ENT, 1) enc_tc_bwd_kernel(const __grid_constan
     tc::fence_async_smem();
     tc::fence_before_sync();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {
       tc::fence_after_sync();
       for (int ck = 0; ck < nchunk; ++ck) {
         tc::Op a = oH;
         a.base += (uint32_t)(((ck ? ch1 : 0) >> 3) * TP) * 16u;
-        tc::issue_wgrad(tb + C_W1 + (uint32_t)(ck * Oc), a, oG, Oc, wacc, 3);
+        tc::issue_wgrad_w(el, C_W1 + (uint32_t)(ck * Oc), a, oG, Oc, wacc, 3);
       }
-      tc::issue_dgrad(tb + C_GH, oG, oW1, Oc, Hc, 0, 3);
-      tc::commit(bar);
+      tc::issue_dgrad_w(el, C_GH, oG, oW1, Oc, Hc, 0, 3);
+      tc::commit_w(el, bar);
     }
     __syncwarp();
     tc::mbar_wait(bar, phase);
@@ -455,14 +454,14 @@ __global__ void __launch_bounds__(ENT, 1) enc_tc_bwd_kernel(const __grid_constan
     tc::fence_async_smem();
     tc::fence_before_sync();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {
       tc::fence_after_sync();
       for (int ck = 0; ck < nchunk; ++ck) {
         tc::Op a = oH;
         a.base += (uint32_t)(((ck ? ch1 : 0) >> 3) * TP) * 16u;
-        tc::issue_wgrad(tb + C_W0 + (uint32_t)(ck * KX), a, oX, KX, wacc, 3);
+        tc::issue_wgrad_w(el, C_W0 + (uint32_t)(ck * KX), a, oX, KX, wacc, 3);
       }
-      tc::commit(bar);
+      tc::commit_w(el, bar);
     }
     __syncwarp();
     tc::mbar_wait(bar, phase);
