@@ -566,6 +566,11 @@ static int run_loss(dpivae_handle_t h, const dpivae_batch_t* bt, const dpivae_rn
   // encoder forward: tensor-core kernel for the encoder units (+ the FFMA kernel for the two prior nets) in the
   // tensor-core math modes when no backward follows; the FFMA kernel for everything otherwise
   const bool enc_tc = h->math_mode != DPIVAE_MATH_FP32 && h->enc_tc_ok && (!with_grad || h->enc_tc_bwd_ok);
+  // the two conditional-prior nets: dedicated streaming kernels (prior_kernels.cu) when their shape allows
+  EncParams E2 = E;
+  E2.n_units = h->enc.n_units - h->n_enc_units;
+  for (int u = 0; u < E2.n_units; ++u) E2.u[u] = h->enc.u[h->n_enc_units + u];
+  const bool prior_fast = prior_kernels_support(E2) && bt->B >= 2048;   // small batches: units in parallel CTA columns instead
   const long long nt128 = (bt->B + 127) / 128;
   const int grid_etc = (int)(nt128 < h->sm_count ? nt128 : h->sm_count);
   {
@@ -578,12 +583,16 @@ static int run_loss(dpivae_handle_t h, const dpivae_batch_t* bt, const dpivae_rn
       launch_enc_tc_fwd(Q, grid_etc, st);
       ++launches;
       if (!latent_only) {
-        EncParams E2 = E;
-        E2.n_units = E.n_units - h->n_enc_units;
-        for (int u = 0; u < E2.n_units; ++u) E2.u[u] = E.u[h->n_enc_units + u];
-        launch_enc_fwd(E2, L.grid_enc, enc_smem, st);
+        if (prior_fast) launch_prior_fwd(E2, h->sm_count, st);
+        else launch_enc_fwd(E2, L.grid_enc, enc_smem, st);
         ++launches;
       }
+    } else if (prior_fast && !latent_only) {
+      EncParams E1 = E;
+      E1.n_units = h->n_enc_units;
+      launch_enc_fwd(E1, L.grid_enc, enc_smem, st);
+      launch_prior_fwd(E2, h->sm_count, st);
+      launches += 2;
     } else {
       launch_enc_fwd(E, L.grid_enc, enc_smem, st);
       ++launches;
@@ -647,11 +656,15 @@ static int run_loss(dpivae_handle_t h, const dpivae_batch_t* bt, const dpivae_rn
       Q.e_g = (int)lrint(log2((double)bt->B_global * (double)(h->d.nd_x + h->d.nd_c + h->d.nd_y))) + 4;
       launch_enc_tc_bwd(Q, grid_etc, st);
       ++launches;
-      EncParams E2 = E;
-      E2.n_units = E.n_units - h->n_enc_units;
-      for (int u = 0; u < E2.n_units; ++u) E2.u[u] = E.u[h->n_enc_units + u];
-      launch_enc_bwd(E2, L.grid_enc, enc_smem, st);
+      if (prior_fast) launch_prior_bwd(E2, L.grid_enc, st);
+      else launch_enc_bwd(E2, L.grid_enc, enc_smem, st);
       ++launches;
+    } else if (prior_fast) {
+      EncParams E1 = E;
+      E1.n_units = h->n_enc_units;
+      launch_enc_bwd(E1, L.grid_enc, enc_smem, st);
+      launch_prior_bwd(E2, L.grid_enc, st);
+      launches += 2;
     } else {
       launch_enc_bwd(E, L.grid_enc, enc_smem, st);
       ++launches;
@@ -881,7 +894,8 @@ int dpivae_prior_net(dpivae_handle_t h, const float* c, const float* y, int64_t 
   EncParams E2 = E;
   E2.n_units = E.n_units - h->n_enc_units;
   for (int u = 0; u < E2.n_units; ++u) E2.u[u] = E.u[h->n_enc_units + u];
-  launch_enc_fwd(E2, L.grid_enc, enc_smem_bytes(h->enc, true), st);
+  if (prior_kernels_support(E2)) launch_prior_fwd(E2, h->sm_count, st);
+  else launch_enc_fwd(E2, L.grid_enc, enc_smem_bytes(h->enc, true), st);
   launch_prior_post(E.headpre, B, h->dec.hpri[0], h->d.nz_c, loc_c, scale_tril_c, st);
   int launches = 2;
   if (y) { launch_prior_post(E.headpre, B, h->dec.hpri[1], h->d.nz_y, loc_y, scale_tril_y, st); ++launches; }

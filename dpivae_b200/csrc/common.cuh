@@ -42,8 +42,15 @@ __device__ __forceinline__ float clampf_(float x, float lo, float hi) { return f
 // Bitwise identity with torch is pinned by tests/test_gpu_parity.py::test_philox_reproduces_torch_cuda_stream.
 __device__ __forceinline__ float philox_normal_elem(unsigned long long seed, unsigned long long offset, unsigned int T,
                                                     unsigned long long li) {
-  const unsigned long long sub = li % T;
-  const unsigned long long q4 = li / T;
+  unsigned long long sub, q4;
+  if ((li >> 32) == 0ull) {   // common case: 32-bit division (a 64-bit divide costs ~100 instructions per element)
+    const unsigned int l32 = (unsigned int)li, q32 = l32 / T;
+    q4 = q32;
+    sub = l32 - q32 * T;
+  } else {
+    sub = li % T;
+    q4 = li / T;
+  }
   const unsigned long long n = (offset >> 2) + (q4 >> 2);
   const int comp = (int)(q4 & 3ull);
   const uint4 ctr = make_uint4((unsigned int)n, (unsigned int)(n >> 32), (unsigned int)sub, (unsigned int)(sub >> 32));

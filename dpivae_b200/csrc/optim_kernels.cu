@@ -8,24 +8,56 @@ namespace dpv {
 
 // grads[i] = sum over the owning kernel's CTAs (fixed order) of part[cta][i]; block 0 also folds
 // the 6 per-CTA loss sums into the 8 normalised scalars (dpivae.py:419-426).
-__global__ void __launch_bounds__(256) reduce_kernel(const ReduceParams P) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+// Thread (parameter lane, row group): 32 consecutive parameters per block (coalesced partial rows), the CTA rows
+// split over 8 row groups with 4 independent accumulators each, combined through shared memory in a fixed order
+// (deterministic; the serial 148..296-load chain per parameter made this kernel latency-bound at 70 us).
+constexpr int RED_P = 32, RED_G = 8;
+__global__ void __launch_bounds__(RED_P * RED_G) reduce_kernel(const ReduceParams P) {
+  __shared__ float sm[RED_G][RED_P];
+  const int lane = threadIdx.x & (RED_P - 1), rg = threadIdx.x / RED_P;
+  const long long i = (long long)blockIdx.x * RED_P + lane;
+  float s = 0.0f;
   if (P.grads != nullptr && i < P.n_params) {
     const int cls = P.owner[i];
     const float* base = P.part + P.base[cls] * P.part_stride + i;
     const int ncta = P.n_cta[cls];
-    float s = 0.0f;
-    for (int c = 0; c < ncta; ++c) s += base[(long long)c * P.part_stride];
-    P.grads[i] = s;
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+    int c = rg;
+    for (; c + 3 * RED_G < ncta; c += 4 * RED_G) {
+      a0 += base[(long long)c * P.part_stride];
+      a1 += base[(long long)(c + RED_G) * P.part_stride];
+      a2 += base[(long long)(c + 2 * RED_G) * P.part_stride];
+      a3 += base[(long long)(c + 3 * RED_G) * P.part_stride];
+    }
+    for (; c < ncta; c += RED_G) a0 += base[(long long)c * P.part_stride];
+    s = (a0 + a1) + (a2 + a3);
   }
-  if (blockIdx.x == 0 && threadIdx.x < 6 && P.scalars != nullptr) {
-    const int k = threadIdx.x;
-    float s = 0.0f;
-    for (int c = 0; c < P.n_cta[0]; ++c) s += P.part[(P.base[0] + c) * P.part_stride + P.n_params + k];
-    // order: ELBO, KLx, KLc(0), KLy(0), Rx, Rc, Ry, reg
-    if (k == 0) P.scalars[0] = s * P.inv_BD;
-    else if (k == 1) { P.scalars[1] = s * P.inv_B; P.scalars[2] = 0.0f; P.scalars[3] = 0.0f; }
-    else P.scalars[k + 2] = s * P.inv_B;
+  sm[rg][lane] = s;
+  __syncthreads();
+  if (rg == 0 && P.grads != nullptr && i < P.n_params) {
+    float t = sm[0][lane];
+#pragma unroll
+    for (int g = 1; g < RED_G; ++g) t += sm[g][lane];
+    P.grads[i] = t;
+  }
+  if (blockIdx.x == 0 && P.scalars != nullptr) {
+    // the 6 loss sums: 32 row groups per scalar, then a fixed-order sum of the 32 partials
+    __shared__ float ssum[32][8];
+    const int k = threadIdx.x & 7, g = threadIdx.x >> 3;
+    float t = 0.0f;
+    if (k < 6)
+      for (int c = g; c < P.n_cta[0]; c += 32) t += P.part[(P.base[0] + c) * P.part_stride + P.n_params + k];
+    ssum[g][k] = t;
+    __syncthreads();
+    if (threadIdx.x < 6) {
+      float tot = 0.0f;
+      for (int gg = 0; gg < 32; ++gg) tot += ssum[gg][threadIdx.x];
+      const int kk = threadIdx.x;
+      // order: ELBO, KLx, KLc(0), KLy(0), Rx, Rc, Ry, reg
+      if (kk == 0) P.scalars[0] = tot * P.inv_BD;
+      else if (kk == 1) { P.scalars[1] = tot * P.inv_B; P.scalars[2] = 0.0f; P.scalars[3] = 0.0f; }
+      else P.scalars[kk + 2] = tot * P.inv_B;
+    }
   }
 }
 
@@ -179,7 +211,7 @@ float ffma_peak_tflops(cudaStream_t st) {
 
 void launch_reduce(const ReduceParams& p, cudaStream_t s) {
   const long long n = p.grads ? p.n_params : 1;
-  reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p);
+  reduce_kernel<<<(unsigned)((n + RED_P - 1) / RED_P), RED_P * RED_G, 0, s>>>(p);
 }
 void launch_gradnorm(const float* grads, long long n, float max_norm, float* clip_coef, cudaStream_t s) {
   gradnorm_kernel<<<1, 1024, 0, s>>>(grads, n, max_norm, clip_coef);
