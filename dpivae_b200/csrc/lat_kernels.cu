@@ -28,9 +28,63 @@ constexpr int TP = 128;
 constexpr int LNT = 256;
 
 
+// Compile-time shapes.  The kernels below are written against run-time dimensions (any case / preset) through the
+// accessor class D; for the shapes of the reference's cases they are ALSO instantiated with the dimensions known to the
+// compiler, so that the block / triangular-index loops unroll, the index arithmetic folds and the divisions by n_mc
+// become shifts (85 % of the generic kernel's executed instructions were integer / control, ncu instruction mix).
+//   MT: 0 = P (three latent blocks), 1 = S (one block), -1 = generic (every accessor reads the descriptor)
+constexpr int tri(int n) { return n * (n + 1) / 2; }
+template <int MT, int NX, int NC, int NY, int NDC, int NDY, int NDP, int NMC>
+struct Shape {
+  static constexpr bool K = MT >= 0;
+  static constexpr int cZ = NX + NC + NY, cnzd = NC + NY, cnb = MT == 0 ? 3 : 1;
+  static constexpr int cnL = MT == 0 ? tri(NX) + tri(NC) + tri(NY) : tri(cZ);
+#define DPV_SCALAR(name, val) \
+  static __device__ __forceinline__ int name(const DecParams& P) { if constexpr (K) return (val); else return P.name; }
+  DPV_SCALAR(model_type, MT) DPV_SCALAR(nz_x, NX) DPV_SCALAR(nz_c, NC) DPV_SCALAR(nz_y, NY) DPV_SCALAR(Z, cZ)
+  DPV_SCALAR(nd_c, NDC) DPV_SCALAR(nd_y, NDY) DPV_SCALAR(nd_p, NDP) DPV_SCALAR(n_mc, NMC) DPV_SCALAR(RB, 128 / (NMC > 0 ? NMC : 1))
+  DPV_SCALAR(nL, cnL) DPV_SCALAR(n_blk, cnb)
+  DPV_SCALAR(rp_loc, 0) DPV_SCALAR(rp_L, cZ) DPV_SCALAR(rp_pmu, cZ + cnL) DPV_SCALAR(rp_psig, cZ + cnL + cnzd) DPV_SCALAR(n_rowpar, cZ + cnL + 2 * cnzd)
+  DPV_SCALAR(f_loc, 0) DPV_SCALAR(f_L, cZ) DPV_SCALAR(f_pmu, cZ + cnL) DPV_SCALAR(f_psig, cZ + cnL + cnzd) DPV_SCALAR(n_feat, cZ + cnL + 2 * cnzd)
+#undef DPV_SCALAR
+  static __device__ __forceinline__ int blk_size(const DecParams& P, int b) {
+    if constexpr (!K) return P.blk_size[b];
+    else if constexpr (MT == 1) return cZ;
+    else return b == 0 ? NX : (b == 1 ? NC : NY);
+  }
+  static __device__ __forceinline__ int blk_start(const DecParams& P, int b) {
+    if constexpr (!K) return P.blk_start[b];
+    else if constexpr (MT == 1) return 0;
+    else return b == 0 ? 0 : (b == 1 ? NX : NX + NC);
+  }
+  static __device__ __forceinline__ int blk_loff(const DecParams& P, int b) {
+    if constexpr (!K) return P.blk_loff[b];
+    else if constexpr (MT == 1) return 0;
+    else return b == 0 ? 0 : (b == 1 ? tri(NX) : tri(NX) + tri(NC));
+  }
+  static __device__ __forceinline__ int henc(const DecParams& P, int b) {   // head rows: [mean nz | sigma nz | cov nz*nz] per block
+    if constexpr (!K) return P.henc[b];
+    else if constexpr (MT == 1) return 0;
+    else return b == 0 ? 0 : (b == 1 ? 2 * NX + NX * NX : 2 * NX + NX * NX + 2 * NC + NC * NC);
+  }
+  static __device__ __forceinline__ int hpri(const DecParams& P, int k) {
+    if constexpr (!K) return P.hpri[k];
+    else {
+      constexpr int e = MT == 1 ? 2 * cZ + cZ * cZ : 2 * NX + NX * NX + 2 * NC + NC * NC + 2 * NY + NY * NY;
+      return k == 0 ? e : e + 2 * NC;
+    }
+  }
+  // packed lower-triangular tables stay descriptor reads (their index is a run-time value in the row-parameter loops)
+  static __device__ __forceinline__ int L_blk(const DecParams& P, int li) { return P.L_blk[li]; }
+  static __device__ __forceinline__ int L_i(const DecParams& P, int li) { return P.L_i[li]; }
+  static __device__ __forceinline__ int L_j(const DecParams& P, int li) { return P.L_j[li]; }
+};
+using ShGeneric = Shape<-1, 0, 0, 0, 0, 0, 0, 0>;
+
+template <class D>
 __device__ __forceinline__ int block_of_l(const DecParams& P, int i) {
   int b = 0;
-  while (b + 1 < P.n_blk && i >= P.blk_start[b + 1]) ++b;
+  while (b + 1 < D::n_blk(P) && i >= D::blk_start(P, b + 1)) ++b;
   return b;
 }
 
@@ -63,72 +117,74 @@ __device__ inline LatSmem lat_carve(float* sm, const DecParams& P, bool bwd) {
 }
 
 // per-row parameters of q(z|x) and of the conditional priors, raw c / y
-__device__ void load_row_params(const DecParams& P, const LatSmem& S, long long row0, int nrows) {
-  const int tid = threadIdx.x, RB = P.RB, nzd = P.nz_c + P.nz_y;
+template <class D>
+__device__ __forceinline__ void load_row_params(const DecParams& P, const LatSmem& S, long long row0, int nrows) {
+  const int tid = threadIdx.x, RB = D::RB(P), nzd = D::nz_c(P) + D::nz_y(P);
   const long long B = P.B;
-  for (int e = tid; e < RB * P.Z; e += LNT) {
+  for (int e = tid; e < RB * D::Z(P); e += LNT) {
     const int i = e / RB, r = e - i * RB;
     const long long lrow = row0 + min(r, nrows - 1);
-    const int b = block_of_l(P, i), il = i - P.blk_start[b];
-    const float pm = P.headpre[(long long)(P.henc[b] + il) * B + lrow];
-    S.ROWPAR[(P.rp_loc + i) * RBMAX + r] = clampf_(pm, -50.0f, 50.0f);
+    const int b = block_of_l<D>(P, i), il = i - D::blk_start(P, b);
+    const float pm = P.headpre[(long long)(D::henc(P, b) + il) * B + lrow];
+    S.ROWPAR[(D::rp_loc(P) + i) * RBMAX + r] = clampf_(pm, -50.0f, 50.0f);
   }
-  for (int e = tid; e < RB * P.nL; e += LNT) {
+  for (int e = tid; e < RB * D::nL(P); e += LNT) {
     const int li = e / RB, r = e - li * RB;
     const long long lrow = row0 + min(r, nrows - 1);
-    const int b = P.L_blk[li], i = P.L_i[li], j = P.L_j[li], nzb = P.blk_size[b];
+    const int b = D::L_blk(P, li), i = D::L_i(P, li), j = D::L_j(P, li), nzb = D::blk_size(P, b);
     float v;
     if (i == j) {
-      const float ps = P.headpre[(long long)(P.henc[b] + nzb + i) * B + lrow];
+      const float ps = P.headpre[(long long)(D::henc(P, b) + nzb + i) * B + lrow];
       v = expf(clampf_(ps, -7.0f, 3.0f)) + 1e-8f;
     } else {
-      const float pc = P.headpre[(long long)(P.henc[b] + 2 * nzb + i * nzb + j) * B + lrow];
+      const float pc = P.headpre[(long long)(D::henc(P, b) + 2 * nzb + i * nzb + j) * B + lrow];
       v = clampf_(pc, -20.0f, 20.0f);
     }
-    S.ROWPAR[(P.rp_L + li) * RBMAX + r] = v;
+    S.ROWPAR[(D::rp_L(P) + li) * RBMAX + r] = v;
   }
   for (int e = tid; e < RB * nzd; e += LNT) {
     const int k = e / RB, r = e - k * RB;
     const long long lrow = row0 + min(r, nrows - 1);
-    const int which = k < P.nz_c ? 0 : 1;
-    const int kk = which ? k - P.nz_c : k, nzk = which ? P.nz_y : P.nz_c;
+    const int which = k < D::nz_c(P) ? 0 : 1;
+    const int kk = which ? k - D::nz_c(P) : k, nzk = which ? D::nz_y(P) : D::nz_c(P);
     float mu = 0.0f, sgm = 1.0f;
     if (which == 0 || P.y != nullptr) {
-      const float pm = P.headpre[(long long)(P.hpri[which] + kk) * B + lrow];
-      const float ps = P.headpre[(long long)(P.hpri[which] + nzk + kk) * B + lrow];
+      const float pm = P.headpre[(long long)(D::hpri(P, which) + kk) * B + lrow];
+      const float ps = P.headpre[(long long)(D::hpri(P, which) + nzk + kk) * B + lrow];
       mu = clampf_(pm, -50.0f, 50.0f);
       sgm = expf(clampf_(ps, -7.0f, 3.0f)) + 1e-8f;
     }
-    S.ROWPAR[(P.rp_pmu + k) * RBMAX + r] = mu;
-    S.ROWPAR[(P.rp_psig + k) * RBMAX + r] = sgm;
+    S.ROWPAR[(D::rp_pmu(P) + k) * RBMAX + r] = mu;
+    S.ROWPAR[(D::rp_psig(P) + k) * RBMAX + r] = sgm;
   }
-  for (int e = tid; e < RB * (P.nd_c + P.nd_y); e += LNT) {
+  for (int e = tid; e < RB * (D::nd_c(P) + D::nd_y(P)); e += LNT) {
     const int j = e / RB, r = e - j * RB;
     const long long lrow = row0 + min(r, nrows - 1);
     const long long drow = P.idx ? P.idx[lrow] : lrow;
     float v = 0.0f;
-    if (j < P.nd_c) v = P.c[drow * P.nd_c + j];
-    else if (P.y != nullptr) v = P.y[drow * P.nd_y + (j - P.nd_c)];
+    if (j < D::nd_c(P)) v = P.c[drow * D::nd_c(P) + j];
+    else if (P.y != nullptr) v = P.y[drow * D::nd_y(P) + (j - D::nd_c(P))];
     S.ROWRAW[j * RBMAX + r] = v;
   }
 }
 
 // z = loc + L eps for the latent blocks b with (b & 1) == hh; returns this thread's share of
 // log q - bijector log-det - log p(zx)
+template <class D>
 __device__ __forceinline__ float sample_blocks(const DecParams& P, const LatSmem& S, int hh, int p, int prow, bool with_logs,
                                                float& dens_share) {
   float lq_part = 0.0f, ld1 = 0.0f, ld2 = 0.0f, lpx = 0.0f;
-  for (int b = hh; b < P.n_blk; b += 2) {
-    const int s = P.blk_start[b], nzb = P.blk_size[b];
+  for (int b = hh; b < D::n_blk(P); b += 2) {
+    const int s = D::blk_start(P, b), nzb = D::blk_size(P, b);
     float ss = 0.0f;
     for (int i = 0; i < nzb; ++i) {
-      float acc = S.ROWPAR[(P.rp_loc + s + i) * RBMAX + prow];
-      const int base = P.rp_L + P.blk_loff[b] + i * (i + 1) / 2;
+      float acc = S.ROWPAR[(D::rp_loc(P) + s + i) * RBMAX + prow];
+      const int base = D::rp_L(P) + D::blk_loff(P, b) + i * (i + 1) / 2;
       for (int j = 0; j <= i; ++j) acc = fmaf(S.ROWPAR[(base + j) * RBMAX + prow], S.EPS[(s + j) * TP + p], acc);
       const float e = S.EPS[(s + i) * TP + p];
       ss = fmaf(e, e, ss);
       const int gi = s + i;
-      if (gi < P.nz_x) {
+      if (gi < D::nz_x(P)) {
         const float u = sigmoidf_(acc);
         const float a = P.ub[gi] - P.lb[gi];
         const float zx = fmaf(u, a, P.lb[gi]);
@@ -146,7 +202,7 @@ __device__ __forceinline__ float sample_blocks(const DecParams& P, const LatSmem
           }
         }
       } else {
-        S.ZD[(gi - P.nz_x) * TP + p] = acc;
+        S.ZD[(gi - D::nz_x(P)) * TP + p] = acc;
       }
     }
     if (with_logs) lq_part += -0.5f * ((float)nzb * LOG_2PI + ss) - S.ROWLOG[b * RBMAX + prow];
@@ -157,12 +213,13 @@ __device__ __forceinline__ float sample_blocks(const DecParams& P, const LatSmem
 
 }  // namespace
 
+template <class D>
 __global__ void __launch_bounds__(LNT) lat_fwd_kernel(const __grid_constant__ DecParams P) {
   extern __shared__ __align__(16) float lsm[];
   const LatSmem S = lat_carve(lsm, P, false);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, hh = warp >> 2, p = 32 * q + lane;
-  const int n = P.n_mc, RB = P.RB, nzd = P.nz_c + P.nz_y, nzin = P.nz_x + P.nd_p;
+  const int n = D::n_mc(P), RB = D::RB(P), nzd = D::nz_c(P) + D::nz_y(P), nzin = D::nz_x(P) + D::nd_p(P);
   const long long B = P.B;
   const bool mlp = P.phys_kind == 0;
   const int c1 = nzd, cs0 = nzd + 1;
@@ -171,16 +228,16 @@ __global__ void __launch_bounds__(LNT) lat_fwd_kernel(const __grid_constant__ De
   const int nrows = (int)min((long long)RB, B - row0);
   const int npairs = nrows * n;
 
-  load_row_params(P, S, row0, nrows);
+  load_row_params<D>(P, S, row0, nrows);
   // reparameterisation noise (kept for the backward)
-  float* epsg = P.epsbuf + (long long)rb * P.Z * TP;
-  for (int e = tid; e < TP * P.Z; e += LNT) {
+  float* epsg = P.epsbuf + (long long)rb * D::Z(P) * TP;
+  for (int e = tid; e < TP * D::Z(P); e += LNT) {
     const int pp = e & (TP - 1), i = e >> 7;
     float v = 0.0f;
     if (pp < npairs) {
       const int r = pp / n, m = pp - r * n;
       const unsigned long long grow = (unsigned long long)(P.row_off + row0 + r);
-      const int b = block_of_l(P, i), il = i - P.blk_start[b], nzb = P.blk_size[b];
+      const int b = block_of_l<D>(P, i), il = i - D::blk_start(P, b), nzb = D::blk_size(P, b);
       const unsigned long long li = ((unsigned long long)m * (unsigned long long)P.Bg + grow) * nzb + il;
       v = P.rng.mode == 0 ? P.rng.eps[b][li] : philox_normal_elem(P.rng.seed, P.rng.ss ? P.rng.ss->philox_off[b] : P.rng.offset[b], P.rng.grid_threads[b], li);
     }
@@ -188,14 +245,14 @@ __global__ void __launch_bounds__(LNT) lat_fwd_kernel(const __grid_constant__ De
     epsg[e] = v;
   }
   __syncthreads();
-  for (int e = tid; e < RB * (P.n_blk + 2); e += LNT) {
+  for (int e = tid; e < RB * (D::n_blk(P) + 2); e += LNT) {
     const int t = e / RB, r = e - t * RB;
     float s = 0.0f;
-    if (t < P.n_blk) {
-      for (int i = 0; i < P.blk_size[t]; ++i) s += logf(S.ROWPAR[(P.rp_L + P.blk_loff[t] + i * (i + 1) / 2 + i) * RBMAX + r]);
+    if (t < D::n_blk(P)) {
+      for (int i = 0; i < D::blk_size(P, t); ++i) s += logf(S.ROWPAR[(D::rp_L(P) + D::blk_loff(P, t) + i * (i + 1) / 2 + i) * RBMAX + r]);
     } else {
-      const int k0 = t == P.n_blk ? 0 : P.nz_c, k1 = t == P.n_blk ? P.nz_c : nzd;
-      for (int k = k0; k < k1; ++k) s += logf(S.ROWPAR[(P.rp_psig + k) * RBMAX + r]);
+      const int k0 = t == D::n_blk(P) ? 0 : D::nz_c(P), k1 = t == D::n_blk(P) ? D::nz_c(P) : nzd;
+      for (int k = k0; k < k1; ++k) s += logf(S.ROWPAR[(D::rp_psig(P) + k) * RBMAX + r]);
     }
     S.ROWLOG[t * RBMAX + r] = s;
   }
@@ -205,27 +262,27 @@ __global__ void __launch_bounds__(LNT) lat_fwd_kernel(const __grid_constant__ De
   const int prow = (pvalid ? p : npairs - 1) / n;
   const int pm_ = (pvalid ? p : npairs - 1) - prow * n;
   float dens_share;
-  const float lq_part = sample_blocks(P, S, hh, p, prow, true, dens_share);
+  const float lq_part = sample_blocks<D>(P, S, hh, p, prow, true, dens_share);
   if (hh == 0)
-    for (int j = 0; j < P.nd_p; ++j) S.ZXIN[(P.nz_x + j) * TP + p] = S.ROWRAW[P.idx_c_phys[j] * RBMAX + prow];
+    for (int j = 0; j < D::nd_p(P); ++j) S.ZXIN[(D::nz_x(P) + j) * TP + p] = S.ROWRAW[P.idx_c_phys[j] * RBMAX + prow];
   S.SC[(2 + hh) * TP + p] = dens_share;
   __syncthreads();
   {
     // conditional prior of side hh: p(zc|c) (hh = 0) or p(zy|y) (hh = 1), diagonal Gaussian
-    const int a_nz = hh ? P.nz_y : P.nz_c, a_j0 = hh ? P.nz_c : 0;
+    const int a_nz = hh ? D::nz_y(P) : D::nz_c(P), a_j0 = hh ? D::nz_c(P) : 0;
     float mh = 0.0f;
     for (int k = a_j0; k < a_j0 + a_nz; ++k) {
-      const float t = (S.ZD[k * TP + p] - S.ROWPAR[(P.rp_pmu + k) * RBMAX + prow]) / S.ROWPAR[(P.rp_psig + k) * RBMAX + prow];
+      const float t = (S.ZD[k * TP + p] - S.ROWPAR[(D::rp_pmu(P) + k) * RBMAX + prow]) / S.ROWPAR[(D::rp_psig(P) + k) * RBMAX + prow];
       mh = fmaf(t, t, mh);
     }
-    const float lp = -0.5f * ((float)a_nz * LOG_2PI + mh) - S.ROWLOG[(P.n_blk + hh) * RBMAX + prow];
+    const float lp = -0.5f * ((float)a_nz * LOG_2PI + mh) - S.ROWLOG[(D::n_blk(P) + hh) * RBMAX + prow];
     S.SC[hh * TP + p] = pvalid ? lq_part - lp : 0.0f;
     if (hh == 0 && pvalid && (P.out.dens || P.out.zx || P.out.zc || P.out.zy)) {
       const long long o = (long long)pm_ * B + row0 + prow;
       if (P.out.dens) P.out.dens[o] = S.SC[2 * TP + p] + S.SC[3 * TP + p];
-      if (P.out.zx) for (int k = 0; k < P.nz_x; ++k) P.out.zx[o * P.nz_x + k] = S.ZXIN[k * TP + p];
-      if (P.out.zc) for (int k = 0; k < P.nz_c; ++k) P.out.zc[o * P.nz_c + k] = S.ZD[k * TP + p];
-      if (P.out.zy) for (int k = 0; k < P.nz_y; ++k) P.out.zy[o * P.nz_y + k] = S.ZD[(P.nz_c + k) * TP + p];
+      if (P.out.zx) for (int k = 0; k < D::nz_x(P); ++k) P.out.zx[o * D::nz_x(P) + k] = S.ZXIN[k * TP + p];
+      if (P.out.zc) for (int k = 0; k < D::nz_c(P); ++k) P.out.zc[o * D::nz_c(P) + k] = S.ZD[k * TP + p];
+      if (P.out.zy) for (int k = 0; k < D::nz_y(P); ++k) P.out.zy[o * D::nz_y(P) + k] = S.ZD[(D::nz_c(P) + k) * TP + p];
     }
     // decoder-kernel input record: latent operand row, chunk hh: [zd | 1 | physics input | 0] * 2^4, fp16 hi / lo
     // planes (physics input: standardised for the MLP surrogate, raw zx for the closed forms)
@@ -251,9 +308,9 @@ __global__ void __launch_bounds__(LNT) lat_fwd_kernel(const __grid_constant__ De
     // raw covariates / labels per pair (rows of 128 floats)
     float* raw = reinterpret_cast<float*>(rec + 8192);
     if (hh == 0) {
-      for (int j = 0; j < P.nd_c; ++j) raw[j * TP + p] = S.ROWRAW[j * RBMAX + prow];
+      for (int j = 0; j < D::nd_c(P); ++j) raw[j * TP + p] = S.ROWRAW[j * RBMAX + prow];
     } else {
-      for (int j = 0; j < P.nd_y; ++j) raw[(P.nd_c + j) * TP + p] = S.ROWRAW[(P.nd_c + j) * RBMAX + prow];
+      for (int j = 0; j < D::nd_y(P); ++j) raw[(D::nd_c(P) + j) * TP + p] = S.ROWRAW[(D::nd_c(P) + j) * RBMAX + prow];
     }
   }
   __syncthreads();
@@ -265,29 +322,30 @@ __global__ void __launch_bounds__(LNT) lat_fwd_kernel(const __grid_constant__ De
   }
 }
 
+template <class D>
 __global__ void __launch_bounds__(LNT) lat_bwd_kernel(const __grid_constant__ DecParams P) {
   extern __shared__ __align__(16) float lsm[];
   const LatSmem S = lat_carve(lsm, P, true);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, hh = warp >> 2, p = 32 * q + lane;
-  const int n = P.n_mc, RB = P.RB, nzd = P.nz_c + P.nz_y;
+  const int n = D::n_mc(P), RB = D::RB(P), nzd = D::nz_c(P) + D::nz_y(P);
   const long long B = P.B;
   const long long rb = blockIdx.x;
   const long long row0 = rb * RB;
   const int nrows = (int)min((long long)RB, B - row0);
   const int npairs = nrows * n;
-  const float wpair = 1.0f / ((float)P.Bg * (float)(P.nd_x + P.nd_c + P.nd_y) * (float)n);
+  const float wpair = 1.0f / ((float)P.Bg * (float)(P.nd_x + D::nd_c(P) + D::nd_y(P)) * (float)n);
 
-  load_row_params(P, S, row0, nrows);
-  const float* epsg = P.epsbuf + (long long)rb * P.Z * TP;
-  for (int e = tid; e < TP * P.Z; e += LNT) S.EPS[e] = epsg[e];
-  const float* dzg = P.dzrec + (long long)rb * (nzd + P.nz_x) * TP;
-  for (int e = tid; e < (nzd + P.nz_x) * TP; e += LNT) S.DZ[e] = dzg[e];
+  load_row_params<D>(P, S, row0, nrows);
+  const float* epsg = P.epsbuf + (long long)rb * D::Z(P) * TP;
+  for (int e = tid; e < TP * D::Z(P); e += LNT) S.EPS[e] = epsg[e];
+  const float* dzg = P.dzrec + (long long)rb * (nzd + D::nz_x(P)) * TP;
+  for (int e = tid; e < (nzd + D::nz_x(P)) * TP; e += LNT) S.DZ[e] = dzg[e];
   __syncthreads();
   const bool pvalid = p < npairs;
   const int prow = (pvalid ? p : npairs - 1) / n;
   float dens_share;
-  sample_blocks(P, S, hh, p, prow, false, dens_share);
+  sample_blocks<D>(P, S, hh, p, prow, false, dens_share);
   __syncthreads();
 
   // per-pair gradients w.r.t. loc / L / prior parameters
@@ -298,32 +356,32 @@ __global__ void __launch_bounds__(LNT) lat_bwd_kernel(const __grid_constant__ De
     const float wv = pp < npairs ? 1.0f : 0.0f;
     for (int k = prt; k < nzd; k += 2) {
       float g = wv * S.DZ[k * TP + pp];
-      const float sgm = S.ROWPAR[(P.rp_psig + k) * RBMAX + r];
-      const float t = (S.ZD[k * TP + pp] - S.ROWPAR[(P.rp_pmu + k) * RBMAX + r]) / sgm;
+      const float sgm = S.ROWPAR[(D::rp_psig(P) + k) * RBMAX + r];
+      const float t = (S.ZD[k * TP + pp] - S.ROWPAR[(D::rp_pmu(P) + k) * RBMAX + r]) / sgm;
       g += bw * t / sgm;
-      S.FEAT[(P.f_pmu + k) * TP + pp] = -bw * t / sgm;
-      S.FEAT[(P.f_psig + k) * TP + pp] = -bw * (t * t - 1.0f) / sgm;
-      S.FEAT[(P.f_loc + P.nz_x + k) * TP + pp] = g;
+      S.FEAT[(D::f_pmu(P) + k) * TP + pp] = -bw * t / sgm;
+      S.FEAT[(D::f_psig(P) + k) * TP + pp] = -bw * (t * t - 1.0f) / sgm;
+      S.FEAT[(D::f_loc(P) + D::nz_x(P) + k) * TP + pp] = g;
     }
-    for (int i = prt; i < P.nz_x; i += 2) {
+    for (int i = prt; i < D::nz_x(P); i += 2) {
       float g = wv * S.DZ[(nzd + i) * TP + pp];
       if (P.prior_kind[i] == 1) g += bw * (S.ZXIN[i * TP + pp] - P.prior_a[i]) / (P.prior_b[i] * P.prior_b[i]);
       const float u = S.U[i * TP + pp];
-      S.FEAT[(P.f_loc + i) * TP + pp] = g * (P.ub[i] - P.lb[i]) * u * (1.0f - u) + bw * (2.0f * u - 1.0f);
+      S.FEAT[(D::f_loc(P) + i) * TP + pp] = g * (P.ub[i] - P.lb[i]) * u * (1.0f - u) + bw * (2.0f * u - 1.0f);
     }
   }
   __syncthreads();
-  for (int e = tid; e < TP * P.nL; e += LNT) {
+  for (int e = tid; e < TP * D::nL(P); e += LNT) {
     const int pp = e & (TP - 1), li = e >> 7;
     const int r = (pp < npairs ? pp : npairs - 1) / n;
-    const int b = P.L_blk[li], i = P.L_i[li], j = P.L_j[li], s = P.blk_start[b];
-    float v = S.FEAT[(P.f_loc + s + i) * TP + pp] * S.EPS[(s + j) * TP + pp];
-    if (i == j) v -= (pp < npairs ? P.beta_x * wpair : 0.0f) / S.ROWPAR[(P.rp_L + li) * RBMAX + r];
-    S.FEAT[(P.f_L + li) * TP + pp] = v;
+    const int b = D::L_blk(P, li), i = D::L_i(P, li), j = D::L_j(P, li), s = D::blk_start(P, b);
+    float v = S.FEAT[(D::f_loc(P) + s + i) * TP + pp] * S.EPS[(s + j) * TP + pp];
+    if (i == j) v -= (pp < npairs ? P.beta_x * wpair : 0.0f) / S.ROWPAR[(D::rp_L(P) + li) * RBMAX + r];
+    S.FEAT[(D::f_L(P) + li) * TP + pp] = v;
   }
   __syncthreads();
   // reduce over the MC axis (n consecutive pairs per row, fixed order)
-  for (int e = tid; e < P.n_feat * RBMAX; e += LNT) {
+  for (int e = tid; e < D::n_feat(P) * RBMAX; e += LNT) {
     const int f = e / RBMAX, r = e - f * RBMAX;
     if (r < nrows) {
       const float* src = S.FEAT + f * TP + r * n;
@@ -342,41 +400,41 @@ __global__ void __launch_bounds__(LNT) lat_bwd_kernel(const __grid_constant__ De
   }
   __syncthreads();
   // gradients w.r.t. the head pre-activations (clamp / exp chain rule, models/encoders.py:35-43)
-  for (int e = tid; e < RB * P.Z; e += LNT) {
+  for (int e = tid; e < RB * D::Z(P); e += LNT) {
     const int i = e / RB, r = e - i * RB;
     if (r < nrows) {
       const long long lrow = row0 + r;
-      const int b = block_of_l(P, i), il = i - P.blk_start[b], nzb = P.blk_size[b];
-      const long long om = (long long)(P.henc[b] + il) * B + lrow;
+      const int b = block_of_l<D>(P, i), il = i - D::blk_start(P, b), nzb = D::blk_size(P, b);
+      const long long om = (long long)(D::henc(P, b) + il) * B + lrow;
       const float pm = P.headpre[om];
-      P.gpre[om] = (pm >= -50.0f && pm <= 50.0f) ? S.ROWACC[(P.f_loc + i) * RBMAX + r] : 0.0f;
+      P.gpre[om] = (pm >= -50.0f && pm <= 50.0f) ? S.ROWACC[(D::f_loc(P) + i) * RBMAX + r] : 0.0f;
       for (int j = 0; j < nzb; ++j) {
-        const long long oc = (long long)(P.henc[b] + 2 * nzb + il * nzb + j) * B + lrow;
+        const long long oc = (long long)(D::henc(P, b) + 2 * nzb + il * nzb + j) * B + lrow;
         float g = 0.0f;
         if (j < il) {
           const float pc = P.headpre[oc];
-          const int li = P.blk_loff[b] + il * (il + 1) / 2 + j;
-          g = (pc >= -20.0f && pc <= 20.0f) ? S.ROWACC[(P.f_L + li) * RBMAX + r] : 0.0f;
+          const int li = D::blk_loff(P, b) + il * (il + 1) / 2 + j;
+          g = (pc >= -20.0f && pc <= 20.0f) ? S.ROWACC[(D::f_L(P) + li) * RBMAX + r] : 0.0f;
         }
         P.gpre[oc] = g;
       }
-      const long long os = (long long)(P.henc[b] + nzb + il) * B + lrow;
+      const long long os = (long long)(D::henc(P, b) + nzb + il) * B + lrow;
       const float ps = P.headpre[os];
-      const int ld = P.blk_loff[b] + il * (il + 1) / 2 + il;
-      P.gpre[os] = (ps >= -7.0f && ps <= 3.0f) ? S.ROWACC[(P.f_L + ld) * RBMAX + r] * expf(ps) : 0.0f;
+      const int ld = D::blk_loff(P, b) + il * (il + 1) / 2 + il;
+      P.gpre[os] = (ps >= -7.0f && ps <= 3.0f) ? S.ROWACC[(D::f_L(P) + ld) * RBMAX + r] * expf(ps) : 0.0f;
     }
   }
   for (int e = tid; e < RB * nzd; e += LNT) {
     const int k = e / RB, r = e - k * RB;
     if (r < nrows) {
       const long long lrow = row0 + r;
-      const int which = k < P.nz_c ? 0 : 1;
-      const int kk = which ? k - P.nz_c : k, nzk = which ? P.nz_y : P.nz_c;
-      const long long om = (long long)(P.hpri[which] + kk) * B + lrow;
-      const long long os = (long long)(P.hpri[which] + nzk + kk) * B + lrow;
+      const int which = k < D::nz_c(P) ? 0 : 1;
+      const int kk = which ? k - D::nz_c(P) : k, nzk = which ? D::nz_y(P) : D::nz_c(P);
+      const long long om = (long long)(D::hpri(P, which) + kk) * B + lrow;
+      const long long os = (long long)(D::hpri(P, which) + nzk + kk) * B + lrow;
       const float pm = P.headpre[om], ps = P.headpre[os];
-      P.gpre[om] = (pm >= -50.0f && pm <= 50.0f) ? S.ROWACC[(P.f_pmu + k) * RBMAX + r] : 0.0f;
-      P.gpre[os] = (ps >= -7.0f && ps <= 3.0f) ? S.ROWACC[(P.f_psig + k) * RBMAX + r] * expf(ps) : 0.0f;
+      P.gpre[om] = (pm >= -50.0f && pm <= 50.0f) ? S.ROWACC[(D::f_pmu(P) + k) * RBMAX + r] : 0.0f;
+      P.gpre[os] = (ps >= -7.0f && ps <= 3.0f) ? S.ROWACC[(D::f_psig(P) + k) * RBMAX + r] * expf(ps) : 0.0f;
     }
   }
 }
@@ -393,7 +451,7 @@ __global__ void __launch_bounds__(LNT) lat_encode_kernel(const __grid_constant__
   const long long m = q / B, r = q - m * B;
   const unsigned long long grow = (unsigned long long)(P.row_off + r);
   for (int i = 0; i < P.Z; ++i) {
-    const int b = block_of_l(P, i), il = i - P.blk_start[b], nzb = P.blk_size[b];
+    const int b = block_of_l<ShGeneric>(P, i), il = i - P.blk_start[b], nzb = P.blk_size[b];
     const unsigned long long li = ((unsigned long long)m * (unsigned long long)P.Bg + grow) * nzb + il;
     lsm[i * LNT + tid] = P.rng.mode == 0 ? P.rng.eps[b][li] : philox_normal_elem(P.rng.seed, P.rng.ss ? P.rng.ss->philox_off[b] : P.rng.offset[b], P.rng.grid_threads[b], li);
   }
@@ -438,15 +496,50 @@ void launch_lat_encode(const DecParams& p, cudaStream_t s) {
 }
 
 size_t lat_smem_bytes(const DecParams& p, bool bwd) { return (size_t)lat_smem_floats(p, bwd) * sizeof(float); }
-void launch_lat_fwd(const DecParams& p, long long n_tiles, cudaStream_t s) {
-  lat_fwd_kernel<<<(unsigned)n_tiles, LNT, lat_smem_bytes(p, false), s>>>(p);
+// shapes of the reference's cases (cases/*/__init__.py presets): bridge / damped_oscillator / simple_beam, P and S,
+// at the training MC count n_mc = 16; everything else runs the generic instantiation
+using ShBridgeP = Shape<0, 2, 4, 4, 2, 2, 1, 16>;
+using ShBridgeS = Shape<1, 2, 4, 4, 2, 2, 1, 16>;
+using ShOscP = Shape<0, 1, 4, 4, 1, 1, 0, 16>;
+using ShOscS = Shape<1, 1, 4, 4, 1, 1, 0, 16>;
+using ShBeamP = Shape<0, 2, 2, 2, 1, 1, 0, 16>;
+using ShBeamS = Shape<1, 2, 2, 2, 1, 1, 0, 16>;
+
+template <int MT, int NX, int NC, int NY, int NDC, int NDY, int NDP, int NMC>
+static bool shape_matches(const DecParams& p, Shape<MT, NX, NC, NY, NDC, NDY, NDP, NMC>) {
+  return p.model_type == MT && p.nz_x == NX && p.nz_c == NC && p.nz_y == NY && p.nd_c == NDC && p.nd_y == NDY && p.nd_p == NDP &&
+         p.n_mc == NMC && p.RB == 128 / NMC;
 }
-void launch_lat_bwd(const DecParams& p, long long n_tiles, cudaStream_t s) {
-  lat_bwd_kernel<<<(unsigned)n_tiles, LNT, lat_smem_bytes(p, true), s>>>(p);
+template <class SH>
+static void launch_lat_pair(const DecParams& p, long long n_tiles, bool bwd, cudaStream_t s) {
+  if (bwd) lat_bwd_kernel<SH><<<(unsigned)n_tiles, LNT, lat_smem_bytes(p, true), s>>>(p);
+  else lat_fwd_kernel<SH><<<(unsigned)n_tiles, LNT, lat_smem_bytes(p, false), s>>>(p);
+}
+static void launch_lat(const DecParams& p, long long n_tiles, bool bwd, cudaStream_t s) {
+  if (shape_matches(p, ShBridgeP())) launch_lat_pair<ShBridgeP>(p, n_tiles, bwd, s);
+  else if (shape_matches(p, ShBridgeS())) launch_lat_pair<ShBridgeS>(p, n_tiles, bwd, s);
+  else if (shape_matches(p, ShOscP())) launch_lat_pair<ShOscP>(p, n_tiles, bwd, s);
+  else if (shape_matches(p, ShOscS())) launch_lat_pair<ShOscS>(p, n_tiles, bwd, s);
+  else if (shape_matches(p, ShBeamP())) launch_lat_pair<ShBeamP>(p, n_tiles, bwd, s);
+  else if (shape_matches(p, ShBeamS())) launch_lat_pair<ShBeamS>(p, n_tiles, bwd, s);
+  else launch_lat_pair<ShGeneric>(p, n_tiles, bwd, s);
+}
+void launch_lat_fwd(const DecParams& p, long long n_tiles, cudaStream_t s) { launch_lat(p, n_tiles, false, s); }
+void launch_lat_bwd(const DecParams& p, long long n_tiles, cudaStream_t s) { launch_lat(p, n_tiles, true, s); }
+template <class SH>
+static int configure_lat_pair() {
+  int e = (int)cudaFuncSetAttribute(lat_fwd_kernel<SH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  if (!e) e = (int)cudaFuncSetAttribute(lat_bwd_kernel<SH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  return e;
 }
 int configure_lat_kernels() {
-  int e = (int)cudaFuncSetAttribute(lat_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  if (!e) e = (int)cudaFuncSetAttribute(lat_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  int e = configure_lat_pair<ShGeneric>();
+  if (!e) e = configure_lat_pair<ShBridgeP>();
+  if (!e) e = configure_lat_pair<ShBridgeS>();
+  if (!e) e = configure_lat_pair<ShOscP>();
+  if (!e) e = configure_lat_pair<ShOscS>();
+  if (!e) e = configure_lat_pair<ShBeamP>();
+  if (!e) e = configure_lat_pair<ShBeamS>();
   return e;
 }
 
