@@ -90,13 +90,13 @@ __device__ __forceinline__ int block_of_l(const DecParams& P, int i) {
 
 // shared-memory carve-up (floats), identical for both kernels
 struct LatSmem {
-  float *ROWPAR, *ROWRAW, *ROWLOG, *EPS, *U, *ZXIN, *ZD, *DZ, *SC, *FEAT, *ROWACC;
+  float *ROWPAR, *ROWRAW, *ROWLOG, *EPS, *U, *ZXIN, *ZD, *DZ, *SC, *FEAT, *ROWACC, *ROWMSK;
 };
 __host__ __device__ inline int lat_smem_floats(const DecParams& P, bool bwd) {
   const int nzd = P.nz_c + P.nz_y, nzin = P.nz_x + P.nd_p;
   int f = P.n_rowpar * RBMAX + (P.nd_c + P.nd_y) * RBMAX + 5 * RBMAX + P.Z * TP + P.nz_x * TP + nzin * TP + nzd * TP +
           (nzd + P.nz_x) * TP + 4 * TP;
-  if (bwd) f += P.n_feat * TP + P.n_feat * RBMAX;
+  if (bwd) f += P.n_feat * TP + P.n_feat * RBMAX + P.n_rowpar * RBMAX;
   return f;
 }
 __device__ inline LatSmem lat_carve(float* sm, const DecParams& P, bool bwd) {
@@ -112,13 +112,14 @@ __device__ inline LatSmem lat_carve(float* sm, const DecParams& P, bool bwd) {
   S.DZ = sm; sm += (nzd + P.nz_x) * TP;
   S.SC = sm; sm += 4 * TP;
   S.FEAT = sm; sm += bwd ? P.n_feat * TP : 0;
-  S.ROWACC = sm;
+  S.ROWACC = sm; sm += bwd ? P.n_feat * RBMAX : 0;
+  S.ROWMSK = sm;   // backward: chain-rule factors of the head clamps / exps, same row layout as ROWPAR
   return S;
 }
 
 // per-row parameters of q(z|x) and of the conditional priors, raw c / y
 template <class D>
-__device__ __forceinline__ void load_row_params(const DecParams& P, const LatSmem& S, long long row0, int nrows) {
+__device__ __forceinline__ void load_row_params(const DecParams& P, const LatSmem& S, long long row0, int nrows, bool msk = false) {
   const int tid = threadIdx.x, RB = D::RB(P), nzd = D::nz_c(P) + D::nz_y(P);
   const long long B = P.B;
   for (int e = tid; e < RB * D::Z(P); e += LNT) {
@@ -127,35 +128,46 @@ __device__ __forceinline__ void load_row_params(const DecParams& P, const LatSme
     const int b = block_of_l<D>(P, i), il = i - D::blk_start(P, b);
     const float pm = P.headpre[(long long)(D::henc(P, b) + il) * B + lrow];
     S.ROWPAR[(D::rp_loc(P) + i) * RBMAX + r] = clampf_(pm, -50.0f, 50.0f);
+    // d clamp / d pre: 1 inside the clamp range (models/encoders.py:35-43); d exp(clamp(ps)) / d ps = exp(ps) inside
+    if (msk) S.ROWMSK[(D::rp_loc(P) + i) * RBMAX + r] = (pm >= -50.0f && pm <= 50.0f) ? 1.0f : 0.0f;
   }
   for (int e = tid; e < RB * D::nL(P); e += LNT) {
     const int li = e / RB, r = e - li * RB;
     const long long lrow = row0 + min(r, nrows - 1);
     const int b = D::L_blk(P, li), i = D::L_i(P, li), j = D::L_j(P, li), nzb = D::blk_size(P, b);
-    float v;
+    float v, mk;
     if (i == j) {
       const float ps = P.headpre[(long long)(D::henc(P, b) + nzb + i) * B + lrow];
       v = expf(clampf_(ps, -7.0f, 3.0f)) + 1e-8f;
+      mk = (ps >= -7.0f && ps <= 3.0f) ? expf(ps) : 0.0f;
     } else {
       const float pc = P.headpre[(long long)(D::henc(P, b) + 2 * nzb + i * nzb + j) * B + lrow];
       v = clampf_(pc, -20.0f, 20.0f);
+      mk = (pc >= -20.0f && pc <= 20.0f) ? 1.0f : 0.0f;
     }
     S.ROWPAR[(D::rp_L(P) + li) * RBMAX + r] = v;
+    if (msk) S.ROWMSK[(D::rp_L(P) + li) * RBMAX + r] = mk;
   }
   for (int e = tid; e < RB * nzd; e += LNT) {
     const int k = e / RB, r = e - k * RB;
     const long long lrow = row0 + min(r, nrows - 1);
     const int which = k < D::nz_c(P) ? 0 : 1;
     const int kk = which ? k - D::nz_c(P) : k, nzk = which ? D::nz_y(P) : D::nz_c(P);
-    float mu = 0.0f, sgm = 1.0f;
+    float mu = 0.0f, sgm = 1.0f, mkm = 0.0f, mks = 0.0f;
     if (which == 0 || P.y != nullptr) {
       const float pm = P.headpre[(long long)(D::hpri(P, which) + kk) * B + lrow];
       const float ps = P.headpre[(long long)(D::hpri(P, which) + nzk + kk) * B + lrow];
       mu = clampf_(pm, -50.0f, 50.0f);
       sgm = expf(clampf_(ps, -7.0f, 3.0f)) + 1e-8f;
+      mkm = (pm >= -50.0f && pm <= 50.0f) ? 1.0f : 0.0f;
+      mks = (ps >= -7.0f && ps <= 3.0f) ? expf(ps) : 0.0f;
     }
     S.ROWPAR[(D::rp_pmu(P) + k) * RBMAX + r] = mu;
     S.ROWPAR[(D::rp_psig(P) + k) * RBMAX + r] = sgm;
+    if (msk) {
+      S.ROWMSK[(D::rp_pmu(P) + k) * RBMAX + r] = mkm;
+      S.ROWMSK[(D::rp_psig(P) + k) * RBMAX + r] = mks;
+    }
   }
   for (int e = tid; e < RB * (D::nd_c(P) + D::nd_y(P)); e += LNT) {
     const int j = e / RB, r = e - j * RB;
@@ -336,7 +348,7 @@ __global__ void __launch_bounds__(LNT) lat_bwd_kernel(const __grid_constant__ De
   const int npairs = nrows * n;
   const float wpair = 1.0f / ((float)P.Bg * (float)(P.nd_x + D::nd_c(P) + D::nd_y(P)) * (float)n);
 
-  load_row_params<D>(P, S, row0, nrows);
+  load_row_params<D>(P, S, row0, nrows, true);
   const float* epsg = P.epsbuf + (long long)rb * D::Z(P) * TP;
   for (int e = tid; e < TP * D::Z(P); e += LNT) S.EPS[e] = epsg[e];
   const float* dzg = P.dzrec + (long long)rb * (nzd + D::nz_x(P)) * TP;
@@ -399,29 +411,27 @@ __global__ void __launch_bounds__(LNT) lat_bwd_kernel(const __grid_constant__ De
     }
   }
   __syncthreads();
-  // gradients w.r.t. the head pre-activations (clamp / exp chain rule, models/encoders.py:35-43)
+  // gradients w.r.t. the head pre-activations (clamp / exp chain rule, models/encoders.py:35-43): the factors were
+  // computed from the pre-activations when the row parameters were loaded -- no global re-read here
   for (int e = tid; e < RB * D::Z(P); e += LNT) {
     const int i = e / RB, r = e - i * RB;
     if (r < nrows) {
       const long long lrow = row0 + r;
       const int b = block_of_l<D>(P, i), il = i - D::blk_start(P, b), nzb = D::blk_size(P, b);
       const long long om = (long long)(D::henc(P, b) + il) * B + lrow;
-      const float pm = P.headpre[om];
-      P.gpre[om] = (pm >= -50.0f && pm <= 50.0f) ? S.ROWACC[(D::f_loc(P) + i) * RBMAX + r] : 0.0f;
+      P.gpre[om] = S.ROWMSK[(D::rp_loc(P) + i) * RBMAX + r] * S.ROWACC[(D::f_loc(P) + i) * RBMAX + r];
       for (int j = 0; j < nzb; ++j) {
         const long long oc = (long long)(D::henc(P, b) + 2 * nzb + il * nzb + j) * B + lrow;
         float g = 0.0f;
         if (j < il) {
-          const float pc = P.headpre[oc];
           const int li = D::blk_loff(P, b) + il * (il + 1) / 2 + j;
-          g = (pc >= -20.0f && pc <= 20.0f) ? S.ROWACC[(D::f_L(P) + li) * RBMAX + r] : 0.0f;
+          g = S.ROWMSK[(D::rp_L(P) + li) * RBMAX + r] * S.ROWACC[(D::f_L(P) + li) * RBMAX + r];
         }
         P.gpre[oc] = g;
       }
       const long long os = (long long)(D::henc(P, b) + nzb + il) * B + lrow;
-      const float ps = P.headpre[os];
       const int ld = D::blk_loff(P, b) + il * (il + 1) / 2 + il;
-      P.gpre[os] = (ps >= -7.0f && ps <= 3.0f) ? S.ROWACC[(D::f_L(P) + ld) * RBMAX + r] * expf(ps) : 0.0f;
+      P.gpre[os] = S.ROWMSK[(D::rp_L(P) + ld) * RBMAX + r] * S.ROWACC[(D::f_L(P) + ld) * RBMAX + r];
     }
   }
   for (int e = tid; e < RB * nzd; e += LNT) {
@@ -432,9 +442,8 @@ __global__ void __launch_bounds__(LNT) lat_bwd_kernel(const __grid_constant__ De
       const int kk = which ? k - D::nz_c(P) : k, nzk = which ? D::nz_y(P) : D::nz_c(P);
       const long long om = (long long)(D::hpri(P, which) + kk) * B + lrow;
       const long long os = (long long)(D::hpri(P, which) + nzk + kk) * B + lrow;
-      const float pm = P.headpre[om], ps = P.headpre[os];
-      P.gpre[om] = (pm >= -50.0f && pm <= 50.0f) ? S.ROWACC[(D::f_pmu(P) + k) * RBMAX + r] : 0.0f;
-      P.gpre[os] = (ps >= -7.0f && ps <= 3.0f) ? S.ROWACC[(D::f_psig(P) + k) * RBMAX + r] * expf(ps) : 0.0f;
+      P.gpre[om] = S.ROWMSK[(D::rp_pmu(P) + k) * RBMAX + r] * S.ROWACC[(D::f_pmu(P) + k) * RBMAX + r];
+      P.gpre[os] = S.ROWMSK[(D::rp_psig(P) + k) * RBMAX + r] * S.ROWACC[(D::f_psig(P) + k) * RBMAX + r];
     }
   }
 }
