@@ -62,6 +62,14 @@ class Outputs(C.Structure):
                 ("zy", C.c_void_p), ("dens_z", C.c_void_p)]
 
 
+class DataGenDesc(C.Structure):
+    _fields_ = [("n_factors", C.c_int32), ("n_layers", C.c_int32), ("nd_x", C.c_int32), ("nd_c", C.c_int32), ("nd_y", C.c_int32),
+                ("_pad", C.c_int32), ("dims", C.c_int32 * (MAX_PHYS_LAYERS + 2)),
+                ("lo", C.c_float * 16), ("hi", C.c_float * 16), ("in_mean", C.c_float * 16), ("in_std", C.c_float * 16),
+                ("idx_c", C.c_int32 * MAX_NDCY), ("idx_y", C.c_int32 * MAX_NDCY),
+                ("sigma_x", C.c_float), ("sigma_c", C.c_float), ("sigma_y", C.c_float), ("_pad2", C.c_float)]
+
+
 EXPORTS = [
     "dpivae_create", "dpivae_destroy", "dpivae_last_error", "dpivae_abi_version", "dpivae_set_physics_mlp",
     "dpivae_bind", "dpivae_set_groups", "dpivae_workspace_bytes", "dpivae_loss", "dpivae_adam_step",
@@ -70,6 +78,7 @@ EXPORTS = [
     "dpivae_set_math_mode", "dpivae_last_used_tensor_cores",
     "dpivae_decode", "dpivae_prior_net", "dpivae_gaussian_sample",
     "dpivae_mc_mean", "dpivae_regression_metrics", "dpivae_linreg_r2",
+    "dpivae_datagen_workspace_bytes", "dpivae_sample_response",
     "dpivae_step_graph_create", "dpivae_step_graph_reset", "dpivae_step_graph_launch", "dpivae_step_graph_destroy",
 ]
 MATH_FP32, MATH_TC_FP16X3, MATH_TC_FP16 = 0, 1, 2
@@ -121,6 +130,10 @@ def load():
     lib.dpivae_mc_mean.argtypes = [vp, i32, i64, i32, vp, vp]
     lib.dpivae_regression_metrics.argtypes = [vp, vp, i64, i32, vp, vp, vp]
     lib.dpivae_linreg_r2.argtypes = [vp, vp, i64, i64, vp, vp, i64, i64, i32, vp, vp, vp]
+    lib.dpivae_datagen_workspace_bytes.argtypes = [C.POINTER(DataGenDesc), i64]
+    lib.dpivae_datagen_workspace_bytes.restype = C.c_size_t
+    lib.dpivae_sample_response.argtypes = [C.POINTER(DataGenDesc), vp, vp, i64, u64, u64, i32, i32, vp, vp, vp, vp, vp, C.c_size_t, vp,
+                                           C.POINTER(u64)]
     lib.dpivae_step_graph_reset.argtypes = [vp, C.POINTER(Rng), i64, vp]
     lib.dpivae_step_graph_launch.argtypes = [vp, i32, vp]
     lib.dpivae_step_graph_destroy.argtypes = [vp]

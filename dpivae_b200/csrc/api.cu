@@ -938,6 +938,71 @@ int dpivae_linreg_r2(const float* X_train, const float* y_train, int64_t ldy_tra
   return 0;
 }
 
+static int datagen_maxw(const dpivae_datagen_desc_t* d) {
+  int m = 0;
+  for (int l = 0; l <= d->n_layers; ++l) m = d->dims[l] > m ? d->dims[l] : m;
+  return m;
+}
+
+size_t dpivae_datagen_workspace_bytes(const dpivae_datagen_desc_t* d, int64_t n) {
+  if (!d || n < 1) return 0;
+  return 2 * align_up((size_t)n * (size_t)datagen_maxw(d) * sizeof(float), 256);
+}
+
+int dpivae_sample_response(const dpivae_datagen_desc_t* d, const float* w, const float* b, int64_t n, uint64_t seed,
+                           uint64_t offset_in, int32_t sm_count, int32_t max_threads_per_sm, float* z, float* x, float* c,
+                           float* y, void* ws, size_t ws_bytes, void* stream, uint64_t* offset_out) {
+  if (!d || !w || !b || !z || !x || !c || !y || !ws) return fail("null argument");
+  if (n < 1 || d->n_factors < 1 || d->n_factors > 16 || d->n_layers < 1 || d->n_layers > DPIVAE_MAX_PHYS_LAYERS + 1)
+    return fail("bad generator sizes");
+  if (d->dims[0] != d->n_factors || d->dims[d->n_layers] != d->nd_x) return fail("surrogate dims must run from n_factors to nd_x");
+  if (d->nd_c < 1 || d->nd_c > DPIVAE_MAX_NDCY || d->nd_y < 1 || d->nd_y > DPIVAE_MAX_NDCY) return fail("bad nd_c / nd_y");
+  if (ws_bytes < dpivae_datagen_workspace_bytes(d, n)) return fail("workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  DataGenParams P;
+  memset(&P, 0, sizeof(P));
+  P.n = n; P.nf = d->n_factors; P.nd_x = d->nd_x; P.nd_c = d->nd_c; P.nd_y = d->nd_y;
+  for (int j = 0; j < d->n_factors; ++j) { P.lo[j] = d->lo[j]; P.hi[j] = d->hi[j]; P.in_mean[j] = d->in_mean[j]; P.in_std[j] = d->in_std[j]; }
+  for (int j = 0; j < DPIVAE_MAX_NDCY; ++j) { P.idx_c[j] = d->idx_c[j]; P.idx_y[j] = d->idx_y[j]; }
+  for (int j = 0; j < d->nd_c; ++j) if (d->idx_c[j] < 0 || d->idx_c[j] >= d->n_factors) return fail("idx_c out of range");
+  for (int j = 0; j < d->nd_y; ++j) if (d->idx_y[j] < 0 || d->idx_y[j] >= d->n_factors) return fail("idx_y out of range");
+  P.sigma_x = d->sigma_x; P.sigma_c = d->sigma_c; P.sigma_y = d->sigma_y;
+  P.seed = seed;
+  // generator bookkeeping of torch's distribution kernels (calc_execution_policy: 256 threads, unroll 4)
+  uint64_t cur = offset_in;
+  const uint64_t cap = (uint64_t)sm_count * ((uint64_t)max_threads_per_sm / 256);
+  auto plan = [&](uint64_t numel, unsigned long long& off, unsigned int& T) {
+    uint64_t grid = (numel + 255) / 256;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    off = cur; T = (unsigned int)(256 * grid);
+    cur += ((numel - 1) / (256 * grid * 4) + 1) * 4;
+  };
+  for (int j = 0; j < d->n_factors; ++j) plan((uint64_t)n, P.off_u[j], P.T_u);
+  plan((uint64_t)n * d->nd_x, P.off_x, P.T_x);
+  plan((uint64_t)n * d->nd_c, P.off_c, P.T_c);
+  plan((uint64_t)n * d->nd_y, P.off_y, P.T_y);
+  if (offset_out) *offset_out = cur;
+  const size_t half = align_up((size_t)n * (size_t)datagen_maxw(d) * sizeof(float), 256);
+  float* bufA = (float*)ws;
+  float* bufB = (float*)((char*)ws + half);
+  P.z = z; P.a0 = bufA; P.x = x; P.c = c; P.y = y;
+  launch_datagen_latents(P, st);
+  const float* in = bufA;
+  long long wo = 0, bo = 0;
+  for (int l = 0; l < d->n_layers; ++l) {
+    const int K = d->dims[l], N = d->dims[l + 1];
+    const bool last = l == d->n_layers - 1;
+    float* out = last ? x : (in == bufA ? bufB : bufA);
+    launch_mlp_layer(in, w + wo, b + bo, out, n, K, N, !last, st);
+    wo += (long long)K * N; bo += N;
+    in = out;
+  }
+  launch_datagen_finish(P, st);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 uint64_t dpivae_philox_plan(dpivae_handle_t h, int64_t B_global, int32_t n_mc, int32_t cond, uint64_t offset_in,
                             int32_t sm_count, int32_t max_threads_per_sm, dpivae_rng_t* rng) {
   if (!h || !rng) return offset_in;

@@ -238,6 +238,21 @@ void launch_regression_metrics(const float* y, const float* p, long long N, int 
 void launch_linreg_r2(const float* Xtr, const float* ytr, long long ldy_tr, long long Ntr, const float* Xte, const float* yte,
                       long long ldy_te, long long Nte, int k, double* scratch, float* r2, cudaStream_t s);
 
+// ---- on-device synthetic data generator (datagen_kernels.cu) -------------------------------------
+struct DataGenParams {
+  long long n;
+  int nf, nd_x, nd_c, nd_y;
+  float lo[16], hi[16], in_mean[16], in_std[16];
+  int idx_c[4], idx_y[4];
+  float sigma_x, sigma_c, sigma_y;
+  unsigned long long seed, off_u[16], off_x, off_c, off_y;
+  unsigned int T_u, T_x, T_c, T_y;
+  float *z, *a0, *x, *c, *y;
+};
+void launch_datagen_latents(const DataGenParams& p, cudaStream_t s);
+void launch_mlp_layer(const float* A, const float* W, const float* b, float* O, long long n, int K, int N, bool tanh_act, cudaStream_t s);
+void launch_datagen_finish(const DataGenParams& p, cudaStream_t s);
+
 size_t dec_smem_bytes(const DecParams& p);
 void launch_dec(const DecParams& p, int grid, cudaStream_t s);
 void launch_enc_fwd(const EncParams& p, int grid, size_t smem, cudaStream_t s);

@@ -215,6 +215,25 @@ int dpivae_linreg_r2(const float* X_train, const float* y_train, int64_t ldy_tra
                      const float* y_test, int64_t ldy_test, int64_t N_test, int32_t k, double* scratch, float* r2_out,
                      void* stream);
 
+/* On-device synthetic data generator = utils/data.py:9-52 `sample_response` for a Tanh-MLP `full_model` behind a
+ * StandardScaler (cases/<case>/__init__.py): z_j ~ Uniform(lo_j, hi_j) (utils/priors.py:32-36), x = full_model(z) + sigma_x N(0,1),
+ * c = z[idx_c] + sigma_c N(0,1), y = z[idx_y] + sigma_y N(0,1).  Random numbers are the torch.cuda Philox stream of
+ *   torch.rand(n) x n_factors ; torch.randn(n, nd_x) ; torch.randn(n, nd_c) ; torch.randn(n, nd_y)
+ * at generator (seed, offset_in); *offset_out is the generator offset after those draws.
+ *   w, b        surrogate weights (nn.Linear layouts, layer after layer) and biases, DEVICE pointers
+ *   workspace   dpivae_datagen_workspace_bytes(desc, n) bytes: two activation buffers n x max width */
+typedef struct {
+  int32_t n_factors, n_layers, nd_x, nd_c, nd_y, _pad;
+  int32_t dims[DPIVAE_MAX_PHYS_LAYERS + 2];   /* n_factors, hidden ..., nd_x */
+  float lo[16], hi[16], in_mean[16], in_std[16];
+  int32_t idx_c[DPIVAE_MAX_NDCY], idx_y[DPIVAE_MAX_NDCY];
+  float sigma_x, sigma_c, sigma_y, _pad2;
+} dpivae_datagen_desc_t;
+size_t dpivae_datagen_workspace_bytes(const dpivae_datagen_desc_t* desc, int64_t n);
+int dpivae_sample_response(const dpivae_datagen_desc_t* desc, const float* w, const float* b, int64_t n, uint64_t seed,
+                           uint64_t offset_in, int32_t sm_count, int32_t max_threads_per_sm, float* z, float* x, float* c,
+                           float* y, void* workspace, size_t workspace_bytes, void* stream, uint64_t* offset_out);
+
 /* Philox bookkeeping for rng mode 1: given the torch CUDA generator's current offset and the SM
  * count / max threads per SM of the device, fill rng->offset / grid_threads for the draws of one
  * forward (P: 3 tensors, S: 1, +1 if cond) and return the generator offset after them. */
