@@ -167,3 +167,28 @@ def test_tc_encoder_forward_and_encode(case, mtype):
     for name, t in (("zx", zx), ("zc", zc), ("zy", zy), ("dens_z", dens)):
         err = gu.rel_l2(t.cpu(), g[f"fw.{name}"])
         assert err < 1e-5, (name, err)
+
+
+@pytest.mark.parametrize("case,mtype", [("bridge", "P"), ("simple_beam", "S"), ("damped_oscillator", "S")])
+@pytest.mark.parametrize("B,n", [(1, 16), (5, 8), (37, 16), (131, 24), (9, 128), (3, 40)])
+def test_tc_ragged_shapes_match_fp32_kernel(case, mtype, B, n):
+    """Edge shapes of the tile walk: a single row, batches that do not fill the last 128-pair tile, MC counts that are
+    not powers of two (rows per tile = 128 // n with idle pair slots), n = 128 (one row per tile), a gathered minibatch.
+    The generic and the shape-specialised latent kernels, the tensor-core decoder and the encoder kernels must agree
+    with the fp32 FFMA path on the same in-kernel Philox stream (loss rows, scalars, every gradient)."""
+    g, spec, sd, args, case_mod, vae, (x, c, y) = build_from_golden(case, mtype)
+    eng = vae.engine()
+    rows = torch.arange(B) % x.shape[0]
+    X, C_, Y = x[rows].contiguous(), c[rows].contiguous(), y[rows].contiguous()
+    idx = torch.randperm(B, generator=torch.Generator().manual_seed(B + n))
+    out = {}
+    for mode in ("fp32", "tc_fp16x3"):
+        eng.set_math_mode(mode)
+        torch.manual_seed(17)
+        rl, s = eng.loss(X, C_, Y, n, (0.7, 1.0, 0.9, 1.1), True, idx=idx)
+        assert eng.used_tensor_cores() == (mode != "fp32")
+        out[mode] = (rl.cpu().clone(), s.cpu().clone(), eng.grads.cpu().clone())
+    assert torch.isfinite(out["fp32"][0]).all() and torch.isfinite(out["fp32"][2]).all()
+    assert gu.rel_l2(out["tc_fp16x3"][0], out["fp32"][0]) < 1e-5
+    assert gu.rel_l2(out["tc_fp16x3"][1], out["fp32"][1]) < 1e-5
+    assert gu.rel_l2(out["tc_fp16x3"][2], out["fp32"][2]) < 3e-5
