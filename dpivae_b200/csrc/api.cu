@@ -307,6 +307,20 @@ static int build_plan(dpivae_model* h) {
     Q.f_red = b; b += 256;
     Q.o_bar = b; b += 16;
     Q.total = (b + 127) & ~127;
+    // raw-weight scratch of the set-up: every unit's [w0 | b0 | w1 | b1] block (contiguous in the flat buffer)
+    {
+      long long raw = 0;
+      bool contiguous = true;
+      for (int u = 0; u < nu; ++u) {
+        const EncUnit& U = E.u[u];
+        raw += (long long)U.H * U.K0 + U.H + (long long)U.O * U.H + U.O;
+        contiguous = contiguous && U.g_b0 == U.g_w0 + (long long)U.H * U.K0 && U.g_w1 == U.g_b0 + U.H &&
+                     U.g_b1 == U.g_w1 + (long long)U.O * U.H;
+      }
+      ok = ok && contiguous;
+      Q.f_raw = -1;
+      if (Q.total + raw * 4 <= 232448) { Q.f_raw = Q.total; Q.total = (int)((Q.total + raw * 4 + 127) & ~127LL); }
+    }
     Q.hid_lo = (Q.Hc / 8) * 128 * 16;
     Q.hid_stride = 2 * (long long)Q.hid_lo;
     if (ok && Q.total <= 232448) h->enc_tc_ok = 1;
@@ -320,6 +334,12 @@ static int build_plan(dpivae_model* h) {
     Q.fb_red = b; b += 256;
     Q.ob_bar = b; b += 32;
     Q.total_b = (b + 127) & ~127;
+    {
+      long long raw = 0;
+      for (int u = 0; u < nu; ++u) raw += (long long)E.u[u].O * E.u[u].H;
+      Q.fb_raw = -1;
+      if (Q.total_b + raw * 4 <= 232448) { Q.fb_raw = Q.total_b; Q.total_b = (int)((Q.total_b + raw * 4 + 127) & ~127LL); }
+    }
     const int nchunk = Q.Hc > 128 ? 2 : 1;
     h->enc_tc_bwd_ok = h->enc_tc_ok && Q.total_b <= 232448 && Q.Oc <= 64 && Q.Hc + nchunk * (Q.Oc + Q.KX) <= 512 &&
                        256 * 32 * 4 <= (int)Q.hid_stride;

@@ -34,19 +34,19 @@ __device__ __forceinline__ void put8e(unsigned char* plane, uint32_t lo_off, int
   *reinterpret_cast<uint4*>(dst + lo_off) = lo;
 }
 
-template <class G>
-__device__ float block_absmax_e(int count, G get, float* red) {
-  float m = 0.0f;
-  for (int e = threadIdx.x; e < count; e += ENT) m = fmaxf(m, fabsf(get(e)));
+// block-wide max of two values at once (uses red[16])
+__device__ __forceinline__ void block_max2(float& a, float& b, float* red) {
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+  for (int off = 16; off > 0; off >>= 1) {
+    a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, off));
+    b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, off));
+  }
   __syncthreads();
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = a; red[8 + (threadIdx.x >> 5)] = b; }
   __syncthreads();
-  float r = red[0];
+  a = red[0]; b = red[8];
 #pragma unroll
-  for (int w = 1; w < ENT / 32; ++w) r = fmaxf(r, red[w]);
-  return r;
+  for (int w = 1; w < ENT / 32; ++w) { a = fmaxf(a, red[w]); b = fmaxf(b, red[8 + w]); }
 }
 __device__ __forceinline__ int scale_exp_e(float mx) {
   if (!(mx > 0.0f) || !isfinite(mx)) return 0;
@@ -54,19 +54,6 @@ __device__ __forceinline__ int scale_exp_e(float mx) {
   frexpf(mx, &e);
   return 9 - e;
 }
-template <class G>
-__device__ void stage_weight_e(unsigned char* plane, uint32_t lo_off, int N, int KP, int kexp, G get) {
-  const float s = exp2f((float)kexp);
-  const int nch = KP >> 3;
-  for (int e = threadIdx.x; e < nch * N; e += ENT) {
-    const int ch = e / N, n = e - ch * N;
-    float v[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = get(n, 8 * ch + i) * s;
-    put8e(plane, lo_off, N, ch, n, v);
-  }
-}
-
 }  // namespace
 
 __global__ void __launch_bounds__(ENT, 1) enc_tc_fwd_kernel(const __grid_constant__ EncTcParams P) {
@@ -93,18 +80,28 @@ __global__ void __launch_bounds__(ENT, 1) enc_tc_fwd_kernel(const __grid_constan
   if (warp == 0) tc::tmem_alloc(tptr, 512);
 
   const float* prm = P.params;
+  // Raw weights first: every unit's parameters are one contiguous block [w0 | b0 | w1 | b1] of the flat buffer; it is
+  // copied ONCE with coalesced loads into shared memory (when the plan has room), and the scale search / operand
+  // staging below read it from there -- the per-element global loads of the old set-up cost ~90 us per launch.
+  const float* ub[3] = {prm + P.g_w0[0], prm + P.g_w0[P.n_units > 1 ? 1 : 0], prm + P.g_w0[P.n_units > 2 ? 2 : 0]};
+  if (P.f_raw >= 0) {
+    float* RAW = smf + (P.f_raw >> 2);
+    int ro = 0;
+    for (int u = 0; u < P.n_units; ++u) {
+      const int nblk = P.H[u] * K0 + P.H[u] + P.O[u] * P.H[u] + P.O[u];
+      const float* src = prm + P.g_w0[u];
+      for (int e = tid; e < nblk; e += ENT) RAW[ro + e] = src[e];
+      ub[u] = RAW + ro;
+      ro += nblk;
+    }
+    __syncthreads();
+  }
   // hidden unit n of the concatenated first layers: unit u(n), local index; column K0 of the operand carries the bias
   auto unit_of_h = [&](int n, int& local) -> int {
     int u = 0;
     while (u + 1 < P.n_units && n >= P.h_off[u + 1]) ++u;
     local = n - P.h_off[u];
     return u;
-  };
-  auto g_w0 = [&](int n, int k) -> float {
-    int l;
-    const int u = unit_of_h(n, l);
-    if (k < K0) return prm[P.g_w0[u] + (long long)l * K0 + k];
-    return k == K0 ? prm[P.g_b0[u] + l] : 0.0f;
   };
   // head row o of the concatenated (block-diagonal) heads
   auto unit_of_o = [&](int o, int& local) -> int {
@@ -116,21 +113,51 @@ __global__ void __launch_bounds__(ENT, 1) enc_tc_fwd_kernel(const __grid_constan
     local = 0;
     return -1;
   };
-  auto g_w1 = [&](int o, int k) -> float {
-    int l, lk;
-    const int u = unit_of_o(o, l);
-    if (u < 0) return 0.0f;
-    const int uk = unit_of_h(k, lk);
-    return uk == u ? prm[P.g_w1[u] + (long long)l * P.H[u] + lk] : 0.0f;
-  };
-  const int k_w0 = scale_exp_e(block_absmax_e(Hc * KX, [&](int e) { return g_w0(e / KX, e % KX); }, RED));
-  const int k_w1 = scale_exp_e(block_absmax_e(Oc * Hc, [&](int e) { return g_w1(e / Hc, e % Hc); }, RED));
-  stage_weight_e(smb + P.w_0, P.l_0, Hc, KX, k_w0, g_w0);
-  stage_weight_e(smb + P.w_1, P.l_1, Oc, Hc, k_w1, g_w1);
+  // power-of-two operand scales from the block maxima: plain linear scans of each unit's [w0 | b0] and [w1] ranges
+  float m0 = 0.0f, m1 = 0.0f;
+  for (int u = 0; u < P.n_units; ++u) {
+    const int n0 = P.H[u] * K0 + P.H[u], n1 = P.O[u] * P.H[u];
+    for (int e = tid; e < n0; e += ENT) m0 = fmaxf(m0, fabsf(ub[u][e]));
+    for (int e = tid; e < n1; e += ENT) m1 = fmaxf(m1, fabsf(ub[u][n0 + e]));
+  }
+  block_max2(m0, m1, RED);
+  const int k_w0 = scale_exp_e(m0), k_w1 = scale_exp_e(m1);
+  // operand staging, unit by unit (no per-element unit search / division): first layers = rows h_off[u] + l of the
+  // [Hc x KX] operand, 8 consecutive inputs per item, bias in column K0; heads = block-diagonal [Oc x Hc]
+  {
+    const float s0 = exp2f((float)k_w0), s1 = exp2f((float)k_w1);
+    const int nch0 = (K0 >> 3) + 1;   // data chunks + the bias chunk (the remaining padding chunks stay zero)
+    for (int u = 0; u < P.n_units; ++u) {
+      const float* w0 = ub[u];
+      const float* b0 = ub[u] + P.H[u] * K0;
+      const float* w1 = b0 + P.H[u];
+      for (int e = tid; e < P.H[u] * nch0; e += ENT) {
+        const int l = e / nch0, ch = e - l * nch0;
+        float v[8];
+        if (ch < (K0 >> 3)) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = w0[l * K0 + 8 * ch + i] * s0;
+        } else {
+          v[0] = b0[l] * s0;
+#pragma unroll
+          for (int i = 1; i < 8; ++i) v[i] = 0.0f;
+        }
+        put8e(smb + P.w_0, P.l_0, Hc, ch, P.h_off[u] + l, v);
+      }
+      const int nch1 = P.H[u] >> 3;
+      for (int e = tid; e < P.O[u] * nch1; e += ENT) {
+        const int lo = e / nch1, ch = e - lo * nch1;
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = w1[lo * P.H[u] + 8 * ch + i] * s1;
+        put8e(smb + P.w_1, P.l_1, Oc, (P.h_off[u] >> 3) + ch, P.o_off[u] + lo, v);
+      }
+    }
+  }
   for (int o = tid; o < Oc; o += ENT) {
     int l;
     const int u = unit_of_o(o, l);
-    B1[o] = u >= 0 ? prm[P.g_b1[u] + l] : 0.0f;
+    B1[o] = u >= 0 ? ub[u][P.H[u] * K0 + P.H[u] + P.O[u] * P.H[u] + l] : 0.0f;
     OROW[o] = u >= 0 ? P.out_row[u] + l : -1;
   }
   tc::fence_async_smem();
@@ -308,15 +335,40 @@ __global__ void __launch_bounds__(ENT, 1) enc_tc_bwd_kernel(const __grid_constan
     local = 0;
     return -1;
   };
-  auto g_w1 = [&](int o, int k) -> float {
-    int l, lk;
-    const int u = unit_of_o(o, l);
-    if (u < 0) return 0.0f;
-    const int uk = unit_of_h(k, lk);
-    return uk == u ? prm[P.g_w1[u] + (long long)l * P.H[u] + lk] : 0.0f;
-  };
-  const int k_w1 = scale_exp_e(block_absmax_e(Oc * Hc, [&](int e) { return g_w1(e / Hc, e % Hc); }, RED));
-  stage_weight_e(smb + P.wb_1, P.lb_1, Oc, Hc, k_w1, g_w1);
+  // raw head weights of every unit: one coalesced copy into shared memory (see the forward kernel)
+  const float* wb[3] = {prm + P.g_w1[0], prm + P.g_w1[P.n_units > 1 ? 1 : 0], prm + P.g_w1[P.n_units > 2 ? 2 : 0]};
+  if (P.fb_raw >= 0) {
+    float* RAW = smf + (P.fb_raw >> 2);
+    int ro = 0;
+    for (int u = 0; u < P.n_units; ++u) {
+      const int nblk = P.O[u] * P.H[u];
+      const float* src = prm + P.g_w1[u];
+      for (int e = tid; e < nblk; e += ENT) RAW[ro + e] = src[e];
+      wb[u] = RAW + ro;
+      ro += nblk;
+    }
+    __syncthreads();
+  }
+  float m1 = 0.0f, m_unused = 0.0f;
+  for (int u = 0; u < P.n_units; ++u) {
+    const int n1 = P.O[u] * P.H[u];
+    for (int e = tid; e < n1; e += ENT) m1 = fmaxf(m1, fabsf(wb[u][e]));
+  }
+  block_max2(m1, m_unused, RED);
+  const int k_w1 = scale_exp_e(m1);
+  {
+    const float s1 = exp2f((float)k_w1);
+    for (int u = 0; u < P.n_units; ++u) {
+      const int nch1 = P.H[u] >> 3;
+      for (int e = tid; e < P.O[u] * nch1; e += ENT) {
+        const int lo = e / nch1, ch = e - lo * nch1;
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = wb[u][lo * P.H[u] + 8 * ch + i] * s1;
+        put8e(smb + P.wb_1, P.lb_1, Oc, (P.h_off[u] >> 3) + ch, P.o_off[u] + lo, v);
+      }
+    }
+  }
   for (int o = tid; o < Oc; o += ENT) {
     int l;
     const int u = unit_of_o(o, l);

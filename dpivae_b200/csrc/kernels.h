@@ -178,6 +178,7 @@ struct EncTcParams {
   int hid_lo;
   // shared-memory plan (bytes)
   int w_0, l_0, w_1, l_1, a_x, l_x, f_b1, f_red, f_orow, o_bar, total;
+  int f_raw, fb_raw;       // raw-weight scratch of the set-up (byte offset, -1 = no room: read the flat buffer directly)
   // backward kernel: inputs, plan
   const float* gpre;
   float* part;
