@@ -383,7 +383,7 @@ static int build_plan(dpivae_model* h) {
       T.f_dza = f32(nzd * 128); T.f_sc = f32(8 * 128); T.f_red = f32(256);
       T.o_bar = b; b += 64;
       T.total = (b + 127) & ~127;
-      if (T.total <= 232448 && 256 * 33 * 4 <= 2 * T.l_big && lat_smem_bytes(P, true) <= 160 * 1024) h->tc_ok = 1;
+      if (T.total <= 232448 && 256 * 39 * 4 <= 2 * T.l_big && lat_smem_bytes(P, true) <= 160 * 1024) h->tc_ok = 1;
     }
   }
   return 0;

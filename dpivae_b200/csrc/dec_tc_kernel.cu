@@ -133,21 +133,6 @@ __device__ __forceinline__ void put4(unsigned char* plane, uint32_t lo_off, int 
   *reinterpret_cast<uint2*>(dst + lo_off) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
 }
 
-// block-wide max of |v| over a strided getter; result broadcast (uses red[8])
-template <class G>
-__device__ float block_absmax(int count, G get, float* red) {
-  float m = 0.0f;
-  for (int e = threadIdx.x; e < count; e += TNT) m = fmaxf(m, fabsf(get(e)));
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
-  __syncthreads();
-  float r = red[0];
-#pragma unroll
-  for (int w = 1; w < TNT / 32; ++w) r = fmaxf(r, red[w]);
-  return r;
-}
 // exponent k with max * 2^k in [256, 512)
 __device__ __forceinline__ int scale_exp(float mx) {
   if (!(mx > 0.0f) || !isfinite(mx)) return 0;
@@ -232,34 +217,73 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
 
   const float* prm = P.params;
   const int c1 = T.c_ones, cs0 = T.c_s0;
+  // Raw weights first: the data-driven decoder's [w0 | b0 | w1 | b1] block of the flat buffer and the frozen physics
+  // surrogate are copied ONCE with coalesced loads into the (still unused) operand buffers; the scale search and the
+  // operand staging read them from shared memory, and the scratch is zeroed again before the first tile.
+  float* FX = smf + (T.a_big >> 2);
+  const int n_fx = 128 * nzd + 128 + ndx * 128 + ndx;
+  const int n_fr = mlp ? (int)(P.pl[3].g_b + ndx) : 0;
+  float* FR = FX + ((n_fx + 3) & ~3);
+  {
+    const float* src = prm + P.fx.g_w0;
+    for (int e = tid; e < n_fx; e += TNT) FX[e] = src[e];
+    if constexpr (mlp)
+      for (int e = tid; e < n_fr; e += TNT) FR[e] = P.frozen[e];
+  }
+  __syncthreads();
+  const int o_b0 = 128 * nzd, o_w1 = o_b0 + 128, o_b1 = o_w1 + ndx * 128;
   // element getters of the padded first-layer matrices (bias in the constant-one column)
   auto g_fx0 = [&](int nn, int k) -> float {
-    if (k < nzd) return prm[P.fx.g_w0 + (long long)nn * nzd + k];
-    return k == c1 ? prm[P.fx.g_b0 + nn] : 0.0f;
+    if (k < nzd) return FX[nn * nzd + k];
+    return k == c1 ? FX[o_b0 + nn] : 0.0f;
   };
-  auto g_fx1 = [&](int nn, int k) -> float { return prm[P.fx.g_w1 + (long long)nn * 128 + k]; };
+  auto g_fx1 = [&](int nn, int k) -> float { return FX[o_w1 + nn * 128 + k]; };
   auto g_p0 = [&](int nn, int k) -> float {
-    if (k >= cs0 && k < cs0 + nzin) return P.frozen[P.pl[0].g_w + (long long)nn * nzin + (k - cs0)];
-    return k == c1 ? P.frozen[P.pl[0].g_b + nn] : 0.0f;
+    if (k >= cs0 && k < cs0 + nzin) return FR[P.pl[0].g_w + nn * nzin + (k - cs0)];
+    return k == c1 ? FR[P.pl[0].g_b + nn] : 0.0f;
   };
-  auto g_p1 = [&](int nn, int k) -> float { return P.frozen[P.pl[1].g_w + (long long)nn * d1 + k]; };
-  auto g_p2 = [&](int nn, int k) -> float { return P.frozen[P.pl[2].g_w + (long long)nn * d2 + k]; };
-  auto g_p3 = [&](int nn, int k) -> float { return P.frozen[P.pl[3].g_w + (long long)nn * d3 + k]; };
+  auto g_p1 = [&](int nn, int k) -> float { return FR[P.pl[1].g_w + nn * d1 + k]; };
+  auto g_p2 = [&](int nn, int k) -> float { return FR[P.pl[2].g_w + nn * d2 + k]; };
+  auto g_p3 = [&](int nn, int k) -> float { return FR[P.pl[3].g_w + nn * d3 + k]; };
 
   auto bias_p3 = [&](int e) -> float {
-    if constexpr (mlp) return P.frozen[P.pl[3].g_b + e];
+    if constexpr (mlp) return FR[P.pl[3].g_b + e];
     else return 0.0f;
   };
   const int KZ = T.KZ;
-  const int k_fx0 = scale_exp(block_absmax(128 * KZ, [&](int e) { return g_fx0(e / KZ, e % KZ); }, RED));
-  int k_x = scale_exp(block_absmax(ndx * 128, [&](int e) { return g_fx1(e >> 7, e & 127); }, RED));
-  int k_p0 = 0, k_p1 = 0, k_p2 = 0;
-  if constexpr (mlp) {
-    k_p0 = scale_exp(block_absmax(d1 * KZ, [&](int e) { return g_p0(e / KZ, e % KZ); }, RED));
-    k_p1 = scale_exp(block_absmax(d2 * d1, [&](int e) { return g_p1(e / d1, e % d1); }, RED));
-    k_p2 = scale_exp(block_absmax(d3 * d2, [&](int e) { return g_p2(e / d2, e % d2); }, RED));
-    const int k_p3 = scale_exp(block_absmax(ndx * d3, [&](int e) { return g_p3(e / d3, e % d3); }, RED));
-    k_x = min(k_x, k_p3);  // fx1 and the last physics layer accumulate into the same TMEM columns
+  // power-of-two operand scales from the block maxima: linear scans of the raw ranges, ONE block reduction for all six
+  int k_fx0, k_x, k_p0 = 0, k_p1 = 0, k_p2 = 0;
+  {
+    float m[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int e = tid; e < o_w1; e += TNT) m[0] = fmaxf(m[0], fabsf(FX[e]));                      // fx0: w0 and b0
+    for (int e = tid; e < ndx * 128; e += TNT) m[1] = fmaxf(m[1], fabsf(FX[o_w1 + e]));          // fx1: w1
+    if constexpr (mlp) {
+      for (int e = tid; e < d1 * nzin; e += TNT) m[2] = fmaxf(m[2], fabsf(FR[P.pl[0].g_w + e]));
+      for (int e = tid; e < d1; e += TNT) m[2] = fmaxf(m[2], fabsf(FR[P.pl[0].g_b + e]));
+      for (int e = tid; e < d2 * d1; e += TNT) m[3] = fmaxf(m[3], fabsf(FR[P.pl[1].g_w + e]));
+      for (int e = tid; e < d3 * d2; e += TNT) m[4] = fmaxf(m[4], fabsf(FR[P.pl[2].g_w + e]));
+      for (int e = tid; e < ndx * d3; e += TNT) m[5] = fmaxf(m[5], fabsf(FR[P.pl[3].g_w + e]));
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) m[i] = fmaxf(m[i], __shfl_xor_sync(0xffffffffu, m[i], off));
+    if (lane == 0 && warp < TNT / 32)
+#pragma unroll
+      for (int i = 0; i < 6; ++i) RED[warp * 6 + i] = m[i];
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      float r = RED[i];
+      for (int w = 1; w < TNT / 32; ++w) r = fmaxf(r, RED[w * 6 + i]);
+      m[i] = r;
+    }
+    k_fx0 = scale_exp(m[0]);
+    k_x = scale_exp(m[1]);
+    if constexpr (mlp) {
+      k_p0 = scale_exp(m[2]); k_p1 = scale_exp(m[3]); k_p2 = scale_exp(m[4]);
+      k_x = min(k_x, scale_exp(m[5]));  // fx1 and the last physics layer accumulate into the same TMEM columns
+    }
   }
   stage_weight(smb + T.w_fx0, T.l_fx0, 128, KZ, k_fx0, g_fx0);
   stage_weight(smb + T.w_fx1, T.l_fx1, ndx, 128, k_x, g_fx1);
@@ -269,15 +293,15 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
     stage_weight(smb + T.w_p[2], T.l_p[2], d3, d2, k_p2, g_p2);
     stage_weight(smb + T.w_p[3], T.l_p[3], ndx, d3, k_x, g_p3);
   }
-  for (int e = tid; e < ndx; e += TNT) BX[e] = prm[P.fx.g_b1 + e] + bias_p3(e);
+  for (int e = tid; e < ndx; e += TNT) BX[e] = FX[o_b1 + e] + bias_p3(e);
   if constexpr (mlp) {
-    for (int e = tid; e < d2; e += TNT) BP1[e] = P.frozen[P.pl[1].g_b + e];
-    for (int e = tid; e < d3; e += TNT) BP2[e] = P.frozen[P.pl[2].g_b + e];
+    for (int e = tid; e < d2; e += TNT) BP1[e] = FR[P.pl[1].g_b + e];
+    for (int e = tid; e < d3; e += TNT) BP2[e] = FR[P.pl[2].g_b + e];
   }
   if constexpr (mlp) {
     for (int e = tid; e < d1 * 4; e += TNT) {
       const int k = e >> 2, j = e & 3;
-      WP0F[e] = j < P.nz_x ? P.frozen[P.pl[0].g_w + (long long)k * nzin + j] : 0.0f;
+      WP0F[e] = j < P.nz_x ? FR[P.pl[0].g_w + k * nzin + j] : 0.0f;
     }
   }
   // auxiliary decoders (fp32, CUDA cores): side 0 = decoder_c, side 1 = decoder_y
@@ -313,6 +337,9 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
   }
   if (P.with_grad && tid == 0) part[P.g_lsx] = 0.0f;
   for (int e = tid; e < NSCAL; e += TNT) part[P.n_params + e] = 0.0f;
+  // the raw-weight scratch goes back to zero: the operand buffers rely on zero padding
+  __syncthreads();
+  for (int e = tid; e < ((n_fx + 3) & ~3) + n_fr; e += TNT) FX[e] = 0.0f;
   tc::fence_async_smem();
   tc::fence_before_sync();
   __syncthreads();
@@ -972,36 +999,50 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
         }
       }
     }
-    // per-thread running sums -> fixed-order sums over the 128 pair slots of each column
+    // per-thread running sums -> fixed-order sums over the 128 pair slots of each column, two levels deep
+    // (4 pair groups of 32 per column, then the 4 partials) so that no thread walks a 128-long dependent chain
     epi_sync();
 #pragma unroll
     for (int i = 0; i < 32; ++i) R0[tid * 32 + i] = dbx[i];
-    epi_sync();
-    if (tid < ndx) {
-      const int h2 = tid / nxh, i = tid - h2 * nxh;
-      float s = 0.0f;
-      for (int j = 0; j < TP; ++j) s += R0[(h2 * TP + j) * 32 + i];
-      part[P.fx.g_b1 + tid] = s * cx;
-    }
-    epi_sync();
 #pragma unroll
-    for (int i = 0; i < 4; ++i) R0[tid * 4 + i] = dba[i];
-    R0[TNT * 4 + tid] = dlsx;
+    for (int i = 0; i < 4; ++i) R0[TNT * 32 + tid * 4 + i] = dba[i];
+    R0[TNT * 36 + tid] = dlsx;
     epi_sync();
-    if (tid < 8) {
-      const int side = tid >> 2, jj = tid & 3;
-      const int nd = side ? P.nd_y : P.nd_c;
-      if ((jj & 1) < nd) {
+    float* R1 = R0 + TNT * 37;   // partials [4 groups][ndx + 8 + 1]
+    {
+      const int col = tid & 63, grp = tid >> 6;   // 64 columns x 4 pair groups
+      if (col < ndx) {
+        const int h2 = col / nxh, i = col - h2 * nxh;
         float s = 0.0f;
-        for (int j = 0; j < TP; ++j) s += R0[(side * TP + j) * 4 + jj];
-        part[(side ? P.dy.g_b1 : P.dc.g_b1) + (jj >> 1) * nd + (jj & 1)] = s * (side ? awy : awc);
+#pragma unroll 8
+        for (int j = 32 * grp; j < 32 * grp + 32; ++j) s += R0[(h2 * TP + j) * 32 + i];
+        R1[grp * 80 + col] = s;
+      }
+      if (col < 8) {   // aux head biases: side = col >> 2, output jj = col & 3
+        const int side2 = col >> 2, jj = col & 3;
+        float s = 0.0f;
+#pragma unroll 8
+        for (int j = 32 * grp; j < 32 * grp + 32; ++j) s += R0[TNT * 32 + (side2 * TP + j) * 4 + jj];
+        R1[grp * 80 + 64 + col] = s;
+      }
+      if (col == 8) {
+        float s = 0.0f;
+#pragma unroll 8
+        for (int j = 32 * grp; j < 32 * grp + 32; ++j) s += R0[TNT * 36 + j];
+        R1[grp * 80 + 72] = s;
       }
     }
-    if (tid == 32) {
-      float s = 0.0f;
-      for (int j = 0; j < TP; ++j) s += R0[TNT * 4 + j];
-      part[P.g_lsx] = s;
+    epi_sync();
+    if (tid < ndx) part[P.fx.g_b1 + tid] = ((R1[tid] + R1[80 + tid]) + (R1[160 + tid] + R1[240 + tid])) * cx;
+    if (tid >= 64 && tid < 72) {
+      const int col = tid - 64, side2 = col >> 2, jj = col & 3;
+      const int nd = side2 ? P.nd_y : P.nd_c;
+      if ((jj & 1) < nd) {
+        const float s = (R1[64 + col] + R1[80 + 64 + col]) + (R1[160 + 64 + col] + R1[240 + 64 + col]);
+        part[(side2 ? P.dy.g_b1 : P.dc.g_b1) + (jj >> 1) * nd + (jj & 1)] = s * (side2 ? awy : awc);
+      }
     }
+    if (tid == 96) part[P.g_lsx] = (R1[72] + R1[80 + 72]) + (R1[160 + 72] + R1[240 + 72]);
   }
   }  // epilogue warps
   if (warp < 8) TPHASE(TPH_FLUSH);
