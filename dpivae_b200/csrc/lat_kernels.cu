@@ -90,13 +90,13 @@ __device__ __forceinline__ int block_of_l(const DecParams& P, int i) {
 
 // shared-memory carve-up (floats), identical for both kernels
 struct LatSmem {
-  float *ROWPAR, *ROWRAW, *ROWLOG, *EPS, *U, *ZXIN, *ZD, *DZ, *SC, *FEAT, *ROWACC, *ROWMSK;
+  float *ROWPAR, *ROWRAW, *ROWLOG, *EPS, *U, *ZXIN, *ZD, *DZ, *SC, *FEAT, *ROWACC, *ROWMSK, *EPS2, *DZ2, *BAR;
 };
 __host__ __device__ inline int lat_smem_floats(const DecParams& P, bool bwd) {
   const int nzd = P.nz_c + P.nz_y, nzin = P.nz_x + P.nd_p;
   int f = P.n_rowpar * RBMAX + (P.nd_c + P.nd_y) * RBMAX + 5 * RBMAX + P.Z * TP + P.nz_x * TP + nzin * TP + nzd * TP +
           (nzd + P.nz_x) * TP + 4 * TP;
-  if (bwd) f += P.n_feat * TP + P.n_feat * RBMAX + P.n_rowpar * RBMAX;
+  if (bwd) f += P.n_feat * TP + P.n_feat * RBMAX + P.n_rowpar * RBMAX + P.Z * TP + (nzd + P.nz_x) * TP + 4;
   return f;
 }
 __device__ inline LatSmem lat_carve(float* sm, const DecParams& P, bool bwd) {
@@ -113,7 +113,10 @@ __device__ inline LatSmem lat_carve(float* sm, const DecParams& P, bool bwd) {
   S.SC = sm; sm += 4 * TP;
   S.FEAT = sm; sm += bwd ? P.n_feat * TP : 0;
   S.ROWACC = sm; sm += bwd ? P.n_feat * RBMAX : 0;
-  S.ROWMSK = sm;   // backward: chain-rule factors of the head clamps / exps, same row layout as ROWPAR
+  S.ROWMSK = sm; sm += bwd ? P.n_rowpar * RBMAX : 0;   // backward: chain-rule factors of the head clamps / exps, same row layout as ROWPAR
+  S.EPS2 = sm; sm += bwd ? P.Z * TP : 0;               // backward: second buffers of the prefetched noise / dL/dz records
+  S.DZ2 = sm; sm += bwd ? (nzd + P.nz_x) * TP : 0;
+  S.BAR = sm;                                          // two mbarriers (16 bytes)
   return S;
 }
 
@@ -337,22 +340,41 @@ __global__ void __launch_bounds__(LNT) lat_fwd_kernel(const __grid_constant__ De
 template <class D>
 __global__ void __launch_bounds__(LNT) lat_bwd_kernel(const __grid_constant__ DecParams P) {
   extern __shared__ __align__(16) float lsm[];
-  const LatSmem S = lat_carve(lsm, P, true);
+  const LatSmem S0 = lat_carve(lsm, P, true);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, hh = warp >> 2, p = 32 * q + lane;
   const int n = D::n_mc(P), RB = D::RB(P), nzd = D::nz_c(P) + D::nz_y(P);
   const long long B = P.B;
-  const long long rb = blockIdx.x;
+  const float wpair = 1.0f / ((float)P.Bg * (float)(P.nd_x + D::nd_c(P) + D::nd_y(P)) * (float)n);
+  // Persistent CTA over tiles; the two per-tile records (noise, dL/dz: 10 KB) of the NEXT tile are bulk-copied
+  // (cp.async.bulk + mbarrier) while the current one is processed -- the one-tile-per-CTA version spent half of its
+  // time waiting for these loads and for the barrier behind them.
+  uint64_t* lbar = reinterpret_cast<uint64_t*>(S0.BAR);
+  const uint32_t eps_bytes = (uint32_t)(D::Z(P) * TP * 4), dz_bytes = (uint32_t)((nzd + D::nz_x(P)) * TP * 4);
+  if (tid == 0) {
+    tc::mbar_init(lbar, 1);
+    tc::mbar_init(lbar + 1, 1);
+    tc::mbar_fence_init();
+  }
+  __syncthreads();
+  auto prefetch = [&](long long tile, int buf) {
+    tc::fence_async_smem();   // generic-proxy reads of this buffer (previous tile) before the async-proxy refill
+    tc::mbar_expect_tx(lbar + buf, eps_bytes + dz_bytes);
+    tc::bulk_g2s(buf ? S0.EPS2 : S0.EPS, P.epsbuf + tile * D::Z(P) * TP, eps_bytes, lbar + buf);
+    tc::bulk_g2s(buf ? S0.DZ2 : S0.DZ, P.dzrec + tile * (nzd + D::nz_x(P)) * TP, dz_bytes, lbar + buf);
+  };
+  if (tid == 0 && (long long)blockIdx.x < P.n_rowblocks) prefetch(blockIdx.x, 0);
+  int it = 0;
+  for (long long rb = blockIdx.x; rb < P.n_rowblocks; rb += gridDim.x, ++it) {
+  const int buf = it & 1;
+  LatSmem S = S0;
+  if (buf) { S.EPS = S0.EPS2; S.DZ = S0.DZ2; }
   const long long row0 = rb * RB;
   const int nrows = (int)min((long long)RB, B - row0);
   const int npairs = nrows * n;
-  const float wpair = 1.0f / ((float)P.Bg * (float)(P.nd_x + D::nd_c(P) + D::nd_y(P)) * (float)n);
-
+  if (tid == 0 && rb + gridDim.x < P.n_rowblocks) prefetch(rb + gridDim.x, buf ^ 1);   // its last readers passed the barrier below
   load_row_params<D>(P, S, row0, nrows, true);
-  const float* epsg = P.epsbuf + (long long)rb * D::Z(P) * TP;
-  for (int e = tid; e < TP * D::Z(P); e += LNT) S.EPS[e] = epsg[e];
-  const float* dzg = P.dzrec + (long long)rb * (nzd + D::nz_x(P)) * TP;
-  for (int e = tid; e < (nzd + D::nz_x(P)) * TP; e += LNT) S.DZ[e] = dzg[e];
+  tc::mbar_wait(lbar + buf, (uint32_t)(it >> 1) & 1u);
   __syncthreads();
   const bool pvalid = p < npairs;
   const int prow = (pvalid ? p : npairs - 1) / n;
@@ -446,6 +468,8 @@ __global__ void __launch_bounds__(LNT) lat_bwd_kernel(const __grid_constant__ De
       P.gpre[os] = S.ROWMSK[(D::rp_psig(P) + k) * RBMAX + r] * S.ROWACC[(D::f_psig(P) + k) * RBMAX + r];
     }
   }
+  __syncthreads();   // every buffer of this tile is free again
+  }  // tiles
 }
 
 // Encode-only inference (models/vae.py:161-162, 125-151): one thread per (MC sample, row) pair, head pre-activations read
@@ -521,7 +545,15 @@ static bool shape_matches(const DecParams& p, Shape<MT, NX, NC, NY, NDC, NDY, ND
 }
 template <class SH>
 static void launch_lat_pair(const DecParams& p, long long n_tiles, bool bwd, cudaStream_t s) {
-  if (bwd) lat_bwd_kernel<SH><<<(unsigned)n_tiles, LNT, lat_smem_bytes(p, true), s>>>(p);
+  if (bwd) {
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    const size_t smem = lat_smem_bytes(p, true);
+    long long per_sm = (long long)(227 * 1024) / (long long)(smem + 1024);
+    per_sm = per_sm < 1 ? 1 : (per_sm > 6 ? 6 : per_sm);
+    const long long grid = n_tiles < per_sm * sms ? n_tiles : per_sm * sms;
+    lat_bwd_kernel<SH><<<(unsigned)grid, LNT, smem, s>>>(p);
+  }
   else lat_fwd_kernel<SH><<<(unsigned)n_tiles, LNT, lat_smem_bytes(p, false), s>>>(p);
 }
 static void launch_lat(const DecParams& p, long long n_tiles, bool bwd, cudaStream_t s) {
