@@ -60,28 +60,39 @@ __global__ void __launch_bounds__(PNT) prior_fwd_kernel(const __grid_constant__ 
     __syncthreads();
     stage_prior(P, U, W, threadIdx.x, PNT);
     __syncthreads();
-    for (long long row = (long long)blockIdx.x * PNT + threadIdx.x; row < P.B; row += (long long)gridDim.x * PNT) {
-      float ct[PK];
+    // two rows per thread (row, row + stride): every broadcast weight read from shared memory serves both
+    const long long stride = (long long)gridDim.x * PNT;
+    for (long long row = (long long)blockIdx.x * PNT + threadIdx.x; row < P.B; row += 2 * stride) {
+      const long long row2 = row + stride;
+      const bool has2 = row2 < P.B;
+      float ct[PK], ct2[PK] = {0.f, 0.f, 0.f, 0.f};
       load_ct(P, U, row, ct);
-      float out[PO];
+      if (has2) load_ct(P, U, row2, ct2);
+      float out[PO], out2[PO];
 #pragma unroll
-      for (int o = 0; o < PO; ++o) out[o] = W.b1[o];
+      for (int o = 0; o < PO; ++o) out[o] = out2[o] = W.b1[o];
 #pragma unroll 4
       for (int k = 0; k < PH; ++k) {
         const float4 w = *reinterpret_cast<const float4*>(W.w0[k]);
-        const float pre = fmaf(ct[3], w.w, fmaf(ct[2], w.z, fmaf(ct[1], w.y, fmaf(ct[0], w.x, W.b0[k]))));
-        const float h = fmaxf(pre, 0.0f);
+        const float bk = W.b0[k];
+        const float h = fmaxf(fmaf(ct[3], w.w, fmaf(ct[2], w.z, fmaf(ct[1], w.y, fmaf(ct[0], w.x, bk)))), 0.0f);
+        const float h2 = fmaxf(fmaf(ct2[3], w.w, fmaf(ct2[2], w.z, fmaf(ct2[1], w.y, fmaf(ct2[0], w.x, bk)))), 0.0f);
         const float4* t = reinterpret_cast<const float4*>(W.w1t[k]);
 #pragma unroll
         for (int q4 = 0; q4 < PO / 4; ++q4) {
           const float4 tv = t[q4];
           out[4 * q4] = fmaf(h, tv.x, out[4 * q4]); out[4 * q4 + 1] = fmaf(h, tv.y, out[4 * q4 + 1]);
           out[4 * q4 + 2] = fmaf(h, tv.z, out[4 * q4 + 2]); out[4 * q4 + 3] = fmaf(h, tv.w, out[4 * q4 + 3]);
+          out2[4 * q4] = fmaf(h2, tv.x, out2[4 * q4]); out2[4 * q4 + 1] = fmaf(h2, tv.y, out2[4 * q4 + 1]);
+          out2[4 * q4 + 2] = fmaf(h2, tv.z, out2[4 * q4 + 2]); out2[4 * q4 + 3] = fmaf(h2, tv.w, out2[4 * q4 + 3]);
         }
       }
 #pragma unroll
       for (int o = 0; o < PO; ++o)
-        if (o < U.O) P.headpre[(long long)(U.out_row + o) * P.B + row] = out[o];
+        if (o < U.O) {
+          P.headpre[(long long)(U.out_row + o) * P.B + row] = out[o];
+          if (has2) P.headpre[(long long)(U.out_row + o) * P.B + row2] = out2[o];
+        }
     }
   }
 }
@@ -127,16 +138,16 @@ __global__ void __launch_bounds__(PRG * 2 * PH) prior_bwd_kernel(const __grid_co
       const float4 c4 = *reinterpret_cast<const float4*>(CT[u][r]);
       const float pre = fmaf(c4.w, w0[3], fmaf(c4.z, w0[2], fmaf(c4.y, w0[1], fmaf(c4.x, w0[0], b0))));
       const float h = fmaxf(pre, 0.0f);
-      float gh = 0.0f;
+      float gq[PO / 4];   // four independent partial sums: no 16-deep dependent FMA chain per row
       const float4* g4 = reinterpret_cast<const float4*>(G[u][r]);
 #pragma unroll
       for (int q4 = 0; q4 < PO / 4; ++q4) {
         const float4 g = g4[q4];
-        gh = fmaf(g.x, w1[4 * q4], gh); gh = fmaf(g.y, w1[4 * q4 + 1], gh); gh = fmaf(g.z, w1[4 * q4 + 2], gh); gh = fmaf(g.w, w1[4 * q4 + 3], gh);
+        gq[q4] = fmaf(g.w, w1[4 * q4 + 3], fmaf(g.z, w1[4 * q4 + 2], fmaf(g.y, w1[4 * q4 + 1], g.x * w1[4 * q4])));
         a_w1[4 * q4] = fmaf(g.x, h, a_w1[4 * q4]); a_w1[4 * q4 + 1] = fmaf(g.y, h, a_w1[4 * q4 + 1]);
         a_w1[4 * q4 + 2] = fmaf(g.z, h, a_w1[4 * q4 + 2]); a_w1[4 * q4 + 3] = fmaf(g.w, h, a_w1[4 * q4 + 3]);
       }
-      gh = pre > 0.0f ? gh : 0.0f;
+      const float gh = pre > 0.0f ? (gq[0] + gq[1]) + (gq[2] + gq[3]) : 0.0f;
       a_w0[0] = fmaf(gh, c4.x, a_w0[0]); a_w0[1] = fmaf(gh, c4.y, a_w0[1]); a_w0[2] = fmaf(gh, c4.z, a_w0[2]); a_w0[3] = fmaf(gh, c4.w, a_w0[3]);
       a_b0 += gh;
       if (k < PO) a_b1 += G[u][r][k];   // head-bias gradient of output k
@@ -190,7 +201,7 @@ bool prior_kernels_support(const EncParams& p) {
 }
 
 void launch_prior_fwd(const EncParams& p, int sm_count, cudaStream_t s) {
-  long long g = (p.B + PNT - 1) / PNT;
+  long long g = (p.B + 2 * PNT - 1) / (2 * PNT);   // two rows per thread
   if (g > 4LL * sm_count) g = 4LL * sm_count;
   prior_fwd_kernel<<<(unsigned)(g < 1 ? 1 : g), PNT, 0, s>>>(p);
 }
