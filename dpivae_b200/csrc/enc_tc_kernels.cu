@@ -182,32 +182,58 @@ __global__ void __launch_bounds__(ENT, 1) enc_tc_fwd_kernel(const __grid_constan
   const int hcols = Hc >> 1, ocols = Oc >> 1;   // columns per thread (multiples of 8)
   const long long ntiles = (B + TP - 1) / TP;
 
+  // The raw x rows of a tile are fetched one tile AHEAD into registers (the gathered global loads were the largest
+  // stall of this kernel: nothing else hides their latency inside the serial per-tile chain); the per-column scaler
+  // statistics of this thread's 4 x 8 columns live in registers for the whole kernel.
+  constexpr int XC = 4;                 // chunks of 8 columns per thread, K0 <= 64
+  const int nch = K0 >> 4;
+  float4 xa[XC], xb[XC];
+  float mr[XC][8], sr[XC][8];
+#pragma unroll
+  for (int c = 0; c < XC; ++c)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = hh * (K0 >> 1) + 8 * c + i;
+      mr[c][i] = (c < nch) ? P.mean_x[k] : 0.0f;
+      sr[c][i] = (c < nch) ? P.std_x[k] : 1.0f;
+    }
+  auto fetch_x = [&](long long tile) {
+    const long long lr = tile * TP + p;
+    const bool ok = tile < ntiles && lr < B;
+    const long long drow = ok ? (P.idx ? P.idx[lr] : lr) : 0;
+    const float* xr = P.x + drow * K0 + hh * (K0 >> 1);
+#pragma unroll
+    for (int c = 0; c < XC; ++c) {
+      xa[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      xb[c] = xa[c];
+      if (ok && c < nch) {
+        xa[c] = __ldg(reinterpret_cast<const float4*>(xr + 8 * c));
+        xb[c] = __ldg(reinterpret_cast<const float4*>(xr + 8 * c) + 1);
+      }
+    }
+  };
+  fetch_x(blockIdx.x);
+
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long row0 = tile * TP;
     const long long lrow = row0 + p;
     const bool valid = lrow < B;
     // ---- x tile: standardise, scale, split -> X8 operand (thread = row x half of the columns) ----
     {
-      const long long drow = valid ? (P.idx ? P.idx[lrow] : lrow) : 0;
-      const float* xr = P.x + drow * K0 + hh * (K0 >> 1);
-      const int nch = K0 >> 4;  // chunks of 8 columns per thread
-      for (int c = 0; c < nch; ++c) {
-        float v[8];
-        const int k0 = hh * (K0 >> 1) + 8 * c;
-        if (valid) {
-          const float4 a = __ldg(reinterpret_cast<const float4*>(xr + 8 * c)), b = __ldg(reinterpret_cast<const float4*>(xr + 8 * c) + 1);
-          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+#pragma unroll
+      for (int c = 0; c < XC; ++c) {
+        if (c < nch) {
+          float v[8] = {xa[c].x, xa[c].y, xa[c].z, xa[c].w, xb[c].x, xb[c].y, xb[c].z, xb[c].w};
+          const int k0 = hh * (K0 >> 1) + 8 * c;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float t = P.x_is_standardised ? v[i] : (v[i] - P.mean_x[k0 + i]) / P.std_x[k0 + i];
-            v[i] = t * s_x;
+            const float t = P.x_is_standardised ? v[i] : (v[i] - mr[c][i]) / sr[c][i];
+            v[i] = valid ? t * s_x : 0.0f;
           }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = 0.0f;
+          put8e(pX, P.l_x, TP, k0 >> 3, p, v);
         }
-        put8e(pX, P.l_x, TP, k0 >> 3, p, v);
       }
+      fetch_x(tile + gridDim.x);   // next tile's rows: in flight under this tile's MMAs and epilogues
       if (hh == 0) {  // constant-one column (bias of the first layers) + zero padding up to KX
         float v[8] = {s_x, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         put8e(pX, P.l_x, TP, K0 >> 3, p, v);
