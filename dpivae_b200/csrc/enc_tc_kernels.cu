@@ -444,11 +444,53 @@ __global__ void __launch_bounds__(ENT, 1) enc_tc_bwd_kernel(const __grid_constan
     tc::bulk_g2s(pH, P.hidrec + (long long)blockIdx.x * P.hid_stride, hid_bytes, hbar);
   }
 
+  // inputs of a tile (raw x rows, gradients of the head pre-activations) are fetched one tile ahead into registers
+  constexpr int XC = 4;
+  const int nch = K0 >> 4;
+  float4 xa[XC], xb[XC];
+  float gq[32];
+  float mr[XC][8], sr[XC][8];
+#pragma unroll
+  for (int c = 0; c < XC; ++c)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = hh * (K0 >> 1) + 8 * c + i;
+      mr[c][i] = (c < nch) ? P.mean_x[k] : 0.0f;
+      sr[c][i] = (c < nch) ? P.std_x[k] : 1.0f;
+    }
+  auto fetch_in = [&](long long tile) {
+    const long long lr = tile * TP + p;
+    const bool ok = tile < ntiles && lr < B;
+    const long long drow = ok ? (P.idx ? P.idx[lr] : lr) : 0;
+    const float* xr = P.x + drow * K0 + hh * (K0 >> 1);
+#pragma unroll
+    for (int c = 0; c < XC; ++c) {
+      xa[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      xb[c] = xa[c];
+      if (ok && c < nch) {
+        xa[c] = __ldg(reinterpret_cast<const float4*>(xr + 8 * c));
+        xb[c] = __ldg(reinterpret_cast<const float4*>(xr + 8 * c) + 1);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        gq[c * 8 + i] = 0.0f;
+        if (ok && c < (ocols >> 3)) {
+          const int r = OROW[hh * ocols + 8 * c + i];
+          if (r >= 0) gq[c * 8 + i] = P.gpre[(long long)r * B + lr];
+        }
+      }
+  };
+  fetch_in(blockIdx.x);
+
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long row0 = tile * TP;
     const long long lrow = row0 + p;
     const bool valid = lrow < B;
-    // ---- G operand: gpre rows of the encoder heads for this row, scaled; running sums for the head-bias gradients ----
+    // ---- G operand: gpre rows of the encoder heads for this row (prefetched), scaled; running sums for the head-bias
+    //      gradients ----
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       if (c < (ocols >> 3)) {
@@ -456,35 +498,28 @@ __global__ void __launch_bounds__(ENT, 1) enc_tc_bwd_kernel(const __grid_constan
         float v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int r = OROW[o0 + i];
-          v[i] = (valid && r >= 0) ? P.gpre[(long long)r * B + lrow] * sgp : 0.0f;
+          v[i] = valid ? gq[c * 8 + i] * sgp : 0.0f;
           db1[c * 8 + i] += v[i];
         }
         put8e(pG, P.lb_g, TP, o0 >> 3, p, v);
       }
     }
-    // ---- x tile (as in the forward) ----
+    // ---- x tile (as in the forward, prefetched) ----
     {
-      const long long drow = valid ? (P.idx ? P.idx[lrow] : lrow) : 0;
-      const float* xr = P.x + drow * K0 + hh * (K0 >> 1);
-      const int nch = K0 >> 4;
-      for (int c = 0; c < nch; ++c) {
-        float v[8];
-        const int k0 = hh * (K0 >> 1) + 8 * c;
-        if (valid) {
-          const float4 a = __ldg(reinterpret_cast<const float4*>(xr + 8 * c)), b = __ldg(reinterpret_cast<const float4*>(xr + 8 * c) + 1);
-          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+#pragma unroll
+      for (int c = 0; c < XC; ++c) {
+        if (c < nch) {
+          float v[8] = {xa[c].x, xa[c].y, xa[c].z, xa[c].w, xb[c].x, xb[c].y, xb[c].z, xb[c].w};
+          const int k0 = hh * (K0 >> 1) + 8 * c;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float t = P.x_is_standardised ? v[i] : (v[i] - P.mean_x[k0 + i]) / P.std_x[k0 + i];
-            v[i] = t * s_x;
+            const float t = P.x_is_standardised ? v[i] : (v[i] - mr[c][i]) / sr[c][i];
+            v[i] = valid ? t * s_x : 0.0f;
           }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = 0.0f;
+          put8e(pX, P.lb_x, TP, k0 >> 3, p, v);
         }
-        put8e(pX, P.lb_x, TP, k0 >> 3, p, v);
       }
+      fetch_in(tile + gridDim.x);   // next tile's x rows and head gradients: in flight under this tile's MMAs
       if (hh == 0) {
         float v[8] = {valid ? s_x : 0.0f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         put8e(pX, P.lb_x, TP, K0 >> 3, p, v);
