@@ -119,21 +119,42 @@ __global__ void __launch_bounds__(PRG * 2 * PH) prior_bwd_kernel(const __grid_co
   // contiguous row range of this CTA
   const long long per = (P.B + gridDim.x - 1) / gridDim.x;
   const long long r0 = (long long)blockIdx.x * per, r1 = min(P.B, r0 + per);
+  // staging registers: the next tile's standardised inputs and head gradients are loaded while the current tile is
+  // processed (blockDim = PRG * 64 * n_units threads cover the 2 * PTILE input rows and 2 * PO * PTILE gradients)
+  constexpr int NG = (2 * PO * PTILE) / (PRG * 2 * PH);   // gradient elements per thread (8)
+  float pct[PK] = {0.f, 0.f, 0.f, 0.f}, pg[NG];
+  auto fetch = [&](long long t0) {
+    const int nr = (int)min((long long)PTILE, r1 - t0);
+    if (tid < P.n_units * PTILE) {
+      const int uu = tid / PTILE, r = tid - uu * PTILE;
+#pragma unroll
+      for (int j = 0; j < PK; ++j) pct[j] = 0.0f;
+      if (t0 < r1 && r < nr) load_ct(P, P.u[uu], t0 + r, pct);
+    }
+#pragma unroll
+    for (int i = 0; i < NG; ++i) {
+      const int e = tid + i * (int)blockDim.x;
+      const int r = e % PTILE, o = (e / PTILE) % PO, uu = e / (PTILE * PO);
+      pg[i] = (t0 < r1 && uu < P.n_units && r < nr && o < P.u[uu].O) ? P.gpre[(long long)(P.u[uu].out_row + o) * P.B + t0 + r] : 0.0f;
+    }
+  };
+  fetch(r0);
   for (long long t0 = r0; t0 < r1; t0 += PTILE) {
     const int nr = (int)min((long long)PTILE, r1 - t0);
     __syncthreads();
-    for (int e = tid; e < P.n_units * PTILE; e += blockDim.x) {
-      const int uu = e / PTILE, r = e - uu * PTILE;
-      float ct[PK] = {0.f, 0.f, 0.f, 0.f};
-      if (r < nr) load_ct(P, P.u[uu], t0 + r, ct);
+    if (tid < P.n_units * PTILE) {
+      const int uu = tid / PTILE, r = tid - uu * PTILE;
 #pragma unroll
-      for (int j = 0; j < PK; ++j) CT[uu][r][j] = ct[j];
+      for (int j = 0; j < PK; ++j) CT[uu][r][j] = pct[j];
     }
-    for (int e = tid; e < P.n_units * PO * PTILE; e += blockDim.x) {
+#pragma unroll
+    for (int i = 0; i < NG; ++i) {
+      const int e = tid + i * (int)blockDim.x;
       const int r = e % PTILE, o = (e / PTILE) % PO, uu = e / (PTILE * PO);
-      G[uu][r][o] = (r < nr && o < P.u[uu].O) ? P.gpre[(long long)(P.u[uu].out_row + o) * P.B + t0 + r] : 0.0f;
+      if (uu < 2) G[uu][r][o] = pg[i];
     }
     __syncthreads();
+    fetch(t0 + PTILE);
     for (int r = rg; r < nr; r += PRG) {
       const float4 c4 = *reinterpret_cast<const float4*>(CT[u][r]);
       const float pre = fmaf(c4.w, w0[3], fmaf(c4.z, w0[2], fmaf(c4.y, w0[1], fmaf(c4.x, w0[0], b0))));
