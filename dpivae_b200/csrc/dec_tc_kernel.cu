@@ -918,24 +918,41 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
     epi_sync();
     TPHASE(TPH_LATENT_BWD);
     // ---- per-row outputs: MC means of the three reconstruction terms + the KL of lat_fwd_kernel ---------------------
-    if (tid < nrows) {
-      const int r = tid;
+    {
       float rx = 0.0f, rc = 0.0f, ry = 0.0f;
-      for (int m = 0; m < n; ++m) {
-        rx += SC[S_RX * TP + r * n + m];
-        rc += SC[S_RC * TP + r * n + m];
-        ry += SC[S_RY * TP + r * n + m];
+      int r = -1;
+      const bool pow2 = (n & (n - 1)) == 0 && n <= 32;
+      if (pow2) {
+        // n consecutive pairs of a row sit in n consecutive lanes: segmented butterfly over the warp (fixed order)
+        if (tid < TP) {
+          rx = SC[S_RX * TP + tid]; rc = SC[S_RC * TP + tid]; ry = SC[S_RY * TP + tid];
+          for (int off = n >> 1; off > 0; off >>= 1) {
+            rx += __shfl_xor_sync(0xffffffffu, rx, off);
+            rc += __shfl_xor_sync(0xffffffffu, rc, off);
+            ry += __shfl_xor_sync(0xffffffffu, ry, off);
+          }
+          if ((tid & (n - 1)) == 0 && tid / n < nrows) r = tid / n;
+        }
+      } else if (tid < nrows) {
+        r = tid;
+        for (int m = 0; m < n; ++m) {
+          rx += SC[S_RX * TP + r * n + m];
+          rc += SC[S_RC * TP + r * n + m];
+          ry += SC[S_RY * TP + r * n + m];
+        }
       }
-      const float inv_n = 1.0f / (float)n;
-      rx *= inv_n; rc *= inv_n; ry *= inv_n;
-      const float kl = P.rowkl[row0 + r];
-      const float loss = P.beta_x * kl - P.alpha_x * rx - P.alpha_c * rc - P.alpha_y * ry;
-      if (P.out.row_loss) {
-        float* o = P.out.row_loss + row0 + r;
-        o[0] = loss; o[B] = kl; o[2 * B] = rx; o[3 * B] = rc; o[4 * B] = ry; o[5 * B] = 0.0f;
+      if (r >= 0) {
+        const float inv_n = 1.0f / (float)n;
+        rx *= inv_n; rc *= inv_n; ry *= inv_n;
+        const float kl = P.rowkl[row0 + r];
+        const float loss = P.beta_x * kl - P.alpha_x * rx - P.alpha_c * rc - P.alpha_y * ry;
+        if (P.out.row_loss) {
+          float* o = P.out.row_loss + row0 + r;
+          o[0] = loss; o[B] = kl; o[2 * B] = rx; o[3 * B] = rc; o[4 * B] = ry; o[5 * B] = 0.0f;
+        }
+        SC[S_Q0 * TP + r] = loss; SC[S_Q1 * TP + r] = kl;
+        SC[S_KL * TP + r] = rx; SC[S_KL2 * TP + r] = rc; SC[S_W * TP + r] = ry;
       }
-      SC[S_Q0 * TP + r] = loss; SC[S_Q1 * TP + r] = kl;
-      SC[S_KL * TP + r] = rx; SC[S_KL2 * TP + r] = rc; SC[S_W * TP + r] = ry;
     }
     epi_sync();
     if (tid == 0) {
