@@ -228,7 +228,8 @@ __global__ void __launch_bounds__(ENT, 1) enc_tc_fwd_kernel(const __grid_constan
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float t = P.x_is_standardised ? v[i] : (v[i] - mr[c][i]) / sr[c][i];
-            v[i] = valid ? t * s_x : 0.0f;
+            // |standardised input| > 3750 sigma would overflow the fp16 operand (inf -> NaN gradients): saturate instead
+            v[i] = valid ? fminf(fmaxf(t * s_x, -60000.0f), 60000.0f) : 0.0f;
           }
           put8e(pX, P.l_x, TP, k0 >> 3, p, v);
         }
@@ -264,7 +265,7 @@ __global__ void __launch_bounds__(ENT, 1) enc_tc_fwd_kernel(const __grid_constan
         float v[8];
         tc::tmem_ld8(trow + C_H + k0, v);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i] * inv0, 0.0f) * s_h;
+        for (int i = 0; i < 8; ++i) v[i] = fminf(fmaxf(v[i] * inv0, 0.0f) * s_h, 60000.0f);   // saturate instead of overflowing the fp16 operand
         uint4 hi, lo;
         tc::split8(v, hi, lo);
         float ph[4] = {__uint_as_float(hi.x), __uint_as_float(hi.y), __uint_as_float(hi.z), __uint_as_float(hi.w)};
@@ -514,7 +515,8 @@ __global__ void __launch_bounds__(ENT, 1) enc_tc_bwd_kernel(const __grid_constan
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float t = P.x_is_standardised ? v[i] : (v[i] - mr[c][i]) / sr[c][i];
-            v[i] = valid ? t * s_x : 0.0f;
+            // |standardised input| > 3750 sigma would overflow the fp16 operand (inf -> NaN gradients): saturate instead
+            v[i] = valid ? fminf(fmaxf(t * s_x, -60000.0f), 60000.0f) : 0.0f;
           }
           put8e(pX, P.lb_x, TP, k0 >> 3, p, v);
         }

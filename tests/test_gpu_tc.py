@@ -192,3 +192,51 @@ def test_tc_ragged_shapes_match_fp32_kernel(case, mtype, B, n):
     assert gu.rel_l2(out["tc_fp16x3"][0], out["fp32"][0]) < 1e-5
     assert gu.rel_l2(out["tc_fp16x3"][1], out["fp32"][1]) < 1e-5
     assert gu.rel_l2(out["tc_fp16x3"][2], out["fp32"][2]) < 3e-5
+
+
+def test_tc_large_batch_is_deterministic_and_matches_fp32():
+    """Many tiles per persistent CTA (double-buffered bulk-copy prefetch in lat_bwd / dec_tc / enc_tc_bwd, register
+    prefetch in the encoder and prior kernels): the same call twice gives the same bits for every gradient, and the
+    result agrees with the fp32 FFMA path -- a race in the buffer hand-over would show up as either."""
+    g, spec, sd, args, case_mod, vae, (x, c, y) = build_from_golden("bridge", "P")
+    eng = vae.engine()
+    reps = 1500   # 36,000 rows x 16 MC = 4,500 tiles -> ~30 tiles per CTA
+    X, C_, Y = _tile(x, reps).cuda(), _tile(c, reps).cuda(), _tile(y, reps).cuda()
+    X = X + 2e-5 * torch.randn(X.shape, generator=torch.Generator().manual_seed(1)).cuda()   # ~0.2 sigma of the fitted scaler
+    w = (1.0, 1.0, 1.0, 1.0)
+    eng.set_math_mode("tc_fp16x3")
+    runs = []
+    for _ in range(3):
+        torch.manual_seed(123)
+        rl, s = eng.loss(X, C_, Y, 16, w, True)
+        runs.append((rl.clone(), s.clone(), eng.grads.clone()))
+    assert eng.used_tensor_cores()
+    assert torch.isfinite(runs[0][2]).all() and torch.isfinite(runs[0][0]).all()
+    for r in runs[1:]:
+        assert torch.equal(r[0], runs[0][0]) and torch.equal(r[1], runs[0][1]) and torch.equal(r[2], runs[0][2])
+    eng.set_math_mode("fp32")
+    torch.manual_seed(123)
+    rl32, s32 = eng.loss(X, C_, Y, 16, w, True)
+    assert gu.rel_l2(runs[0][0].cpu(), rl32.cpu()) < 1e-5
+    assert gu.rel_l2(runs[0][1].cpu(), s32.cpu()) < 1e-5
+    assert gu.rel_l2(runs[0][2].cpu(), eng.grads.cpu()) < 3e-5
+
+
+def test_tc_outlier_inputs_give_finite_gradients():
+    """Rows tens of scaler sigmas away from the training distribution (bad sensors, unit mix-ups): the fp16 hi/lo
+    operands keep their range (|standardised input| up to 3750 sigma before they saturate), gradients stay finite and
+    the tensor-core path still tracks the fp32 path."""
+    g, spec, sd, args, case_mod, vae, (x, c, y) = build_from_golden("bridge", "P")
+    eng = vae.engine()
+    X = x.clone()
+    X[::3] += 0.003    # ~30 sigma of the fitted scaler
+    out = {}
+    for mode in ("fp32", "tc_fp16x3"):
+        eng.set_math_mode(mode)
+        torch.manual_seed(3)
+        rl, s = eng.loss(X, c, y, 16, (1.0, 1.0, 1.0, 1.0), True)
+        assert torch.isfinite(eng.grads).all(), mode
+        out[mode] = (rl.cpu().clone(), eng.grads.cpu().clone())
+    fin = torch.isfinite(out["fp32"][0][0])
+    assert gu.rel_l2(out["tc_fp16x3"][0][0][fin], out["fp32"][0][0][fin]) < 1e-5
+    assert gu.rel_l2(out["tc_fp16x3"][1], out["fp32"][1]) < 5e-5
