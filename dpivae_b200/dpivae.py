@@ -136,14 +136,14 @@ def train_model(args, vae, definition, data_train, data_val, path_metrics=None, 
         it_range = trange(start_iter, args.n_iter)
     w_alpha = (float(args.alpha_x), float(args.alpha_c), float(args.alpha_y))
 
-    def log_iteration(it, row9, lambda_x_i, beta_x_i, beta_c_i, beta_y_i):
+    def log_iteration(it, row9, lambda_x_i, beta_x_i, beta_c_i, beta_y_i, sigma_x=None):
         for k, nme in enumerate(_NAMES8):
             logger.log_scalar(nme, row9[k], it)
         logger.log_scalar("lambda_x", lambda_x_i, it)
         logger.log_scalar("beta_x", beta_x_i, it)
         logger.log_scalar("beta_c", beta_c_i, it)
         logger.log_scalar("beta_y", beta_y_i, it)
-        logger.log_scalar("sigma_x", row9[8].exp(), it)
+        logger.log_scalar("sigma_x", row9[8].exp() if sigma_x is None else sigma_x, it)
 
     def validate(it, w):
         _, sv = eng.loss(x_val, c_val, y_val, args.n_mc_val, w, False)
@@ -172,12 +172,13 @@ def train_model(args, vae, definition, data_train, data_val, path_metrics=None, 
             graph.set_pool(pool)
             first = eng.step_count + 1
             graph.run(k)
-            rows = graph.log_rows(first, k)
+            rows = graph.log_rows_device(first, k)   # stays on the device: the logger converts in one batch when read
+            sig = rows[:, 8].exp()   # one launch per chunk
             for j in range(k):
                 lam = lambda_annealer.forward(it + j) * args.lambda_g0
                 vae.decoder_x.grad_reverse.alpha_ = lam  # logged only; the GRL uses _alpha
                 log_iteration(it + j, rows[j], lam, beta_x_i, args.beta_c0 * beta_c_annealer.forward(it + j),
-                              args.beta_y0 * beta_y_annealer.forward(it + j))
+                              args.beta_y0 * beta_y_annealer.forward(it + j), sig[j])
             it = it_end
             if (it - 1) % vf == 0:
                 stop = validate(it - 1, w)

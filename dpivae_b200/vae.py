@@ -447,8 +447,22 @@ class StepGraph:
         return r, int(new_off - off)
 
     def set_pool(self, idx_pool):
-        """New minibatch rows for the coming steps (same shape; step t reads row (t - 1) % pool_rows)."""
-        self.pool.copy_(idx_pool.to(self.eng.dev, torch.int64), non_blocking=True)
+        """New minibatch rows for the coming steps (same shape; step t reads row (t - 1) % pool_rows).  Host tensors
+        go through a pinned staging buffer with an asynchronous copy (no host wait for the device)."""
+        if idx_pool.is_cuda:
+            self.pool.copy_(idx_pool.to(torch.int64), non_blocking=True)
+            return
+        if getattr(self, "_pin", None) is None:
+            self._pin = torch.empty(tuple(self.pool.shape), dtype=torch.int64, pin_memory=True)
+            self._pin_free = torch.cuda.Event()
+            self._pin_used = False
+        if self._pin_used:
+            self._pin_free.synchronize()   # the previous asynchronous copy has read the staging buffer
+        self._pin.copy_(idx_pool)
+        with torch.cuda.device(self.eng.dev):
+            self.pool.copy_(self._pin, non_blocking=True)
+            self._pin_free.record(torch.cuda.current_stream(self.eng.dev))
+        self._pin_used = True
 
     def run(self, n_steps):
         """Enqueue n_steps training steps; keeps eng.step_count and the torch CUDA generator in step with the device."""
@@ -463,11 +477,18 @@ class StepGraph:
             eng.launches += eng.lib.dpivae_last_launch_count(eng.handle)
             eng.step_count += int(n_steps)
 
+    def log_rows_device(self, first_step, n_steps):
+        """Device copy (stream-ordered, no host synchronisation) of the log rows of optimizer steps
+        first_step .. first_step + n_steps - 1 (1-based); must be taken before the ring wraps around."""
+        cap = self.log.shape[0]
+        a = (first_step - 1) % cap
+        if a + n_steps <= cap:
+            return self.log[a:a + n_steps].clone()
+        return torch.cat([self.log[a:], self.log[:a + n_steps - cap]], dim=0)
+
     def log_rows(self, first_step, n_steps):
         """Host copy of the log rows of optimizer steps first_step .. first_step + n_steps - 1 (1-based)."""
-        cap = self.log.shape[0]
-        rows = [(first_step - 1 + i) % cap for i in range(n_steps)]
-        return self.log[torch.tensor(rows, device=self.log.device)].cpu()
+        return self.log_rows_device(first_step, n_steps).cpu()
 
     def close(self):
         if self.handle:
