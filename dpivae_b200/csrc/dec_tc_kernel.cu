@@ -53,12 +53,6 @@ enum { TPH_SETUP = 0, TPH_ROWPAR_EPS, TPH_LATENT, TPH_AUX1, TPH_A0, TPH_AUX2, TP
   } while (0)
 
 
-__device__ __forceinline__ int block_of_tc(const DecParams& P, int i) {
-  int b = 0;
-  while (b + 1 < P.n_blk && i >= P.blk_start[b + 1]) ++b;
-  return b;
-}
-
 // write 8 consecutive columns (chunk) of row `row` of an X8 operand: hi plane + lo plane
 __device__ __forceinline__ void put8(unsigned char* plane, uint32_t lo_off, int R, int chunk, int row, const float* v) {
   uint4 hi, lo;
