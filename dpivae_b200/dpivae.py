@@ -154,7 +154,8 @@ def train_model(args, vae, definition, data_train, data_val, path_metrics=None, 
     # Device-resident loop (include/dpivae_b200.h dpivae_step_graph_*): with constant loss weights (annealing None, the
     # reference default) the iterations between two validation passes replay ONE captured step graph -- no per-step
     # host work beyond the reference's own CPU minibatch draw, one log read-back per chunk instead of 13 syncs per step.
-    device_loop = bool(getattr(args, "device_loop", True)) and beta_x_annealer.type in (None, "none", "None")
+    # (capturing the step graphs costs ~0.1 s once: by default only runs of >= 2000 iterations use them)
+    device_loop = bool(getattr(args, "device_loop", args.n_iter >= 2000)) and beta_x_annealer.type in (None, "none", "None")
     if device_loop:
         beta_x_i = args.beta_x0 * beta_x_annealer.forward(0)
         w = (float(beta_x_i),) + w_alpha

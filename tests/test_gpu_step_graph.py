@@ -109,7 +109,7 @@ def test_checkpoint_resume_is_exact(tmp_path):
 
     def mk(n_iter, start=0):
         return make_args(case_mod, "dpivae", use_seed=True, seed=21, n_train=256, n_val=128, n_batch=64, n_iter=n_iter,
-                         val_freq=5, n_mc_train=8, n_mc_val=8, start_iter=start)
+                         val_freq=5, n_mc_train=8, n_mc_val=8, start_iter=start, device_loop=True)
 
     tr, va = data()
     vae = dpv.setup_model(mk(20), d, tr)
