@@ -38,6 +38,8 @@ def test_struct_sizes_match_header():
     # ModelDesc: 8 int32 + 4 int32 + 8 mlp2 + 2 int64 + floats/ints as declared
     n = 8 * 4 + 4 * 4 + 8 * 48 + 16 + (64 * 2 + 4 * 4) * 4 + (4 + 4) * 4 + 4 * 4 + 8 * 4 + 12 + 8 + 7 * 4 + 64 * 4
     assert ctypes.sizeof(_lib.ModelDesc) == (n + 7) // 8 * 8
+    # dpivae_datagen_desc_t: 6 int32 + dims[8] + 4 x float[16] + idx_c[4] + idx_y[4] + 4 floats
+    assert ctypes.sizeof(_lib.DataGenDesc) == 6 * 4 + 8 * 4 + 4 * 16 * 4 + 4 * 4 + 4 * 4 + 4 * 4
 
 
 def test_no_cpu_fallback():
