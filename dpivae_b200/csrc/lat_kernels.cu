@@ -90,13 +90,13 @@ __device__ __forceinline__ int block_of_l(const DecParams& P, int i) {
 
 // shared-memory carve-up (floats), identical for both kernels
 struct LatSmem {
-  float *ROWPAR, *ROWRAW, *ROWLOG, *EPS, *U, *ZXIN, *ZD, *DZ, *SC, *FEAT, *ROWACC, *ROWMSK, *EPS2, *DZ2, *BAR;
+  float *ROWPAR, *ROWRAW, *ROWLOG, *EPS, *U, *ZXIN, *ZD, *DZ, *SC, *FEAT, *ROWACC, *ROWMSK, *EPS2, *DZ2, *BAR, *RAWH;
 };
 __host__ __device__ inline int lat_smem_floats(const DecParams& P, bool bwd) {
   const int nzd = P.nz_c + P.nz_y, nzin = P.nz_x + P.nd_p;
   int f = P.n_rowpar * RBMAX + (P.nd_c + P.nd_y) * RBMAX + 5 * RBMAX + P.Z * TP + P.nz_x * TP + nzin * TP + nzd * TP +
           (nzd + P.nz_x) * TP + 4 * TP;
-  if (bwd) f += P.n_feat * TP + P.n_feat * RBMAX + P.n_rowpar * RBMAX + P.Z * TP + (nzd + P.nz_x) * TP + 4;
+  if (bwd) f += P.n_feat * TP + P.n_feat * RBMAX + P.n_rowpar * RBMAX + P.Z * TP + (nzd + P.nz_x) * TP + 4 + 2 * P.O_tot * RBMAX;
   return f;
 }
 __device__ inline LatSmem lat_carve(float* sm, const DecParams& P, bool bwd) {
@@ -116,20 +116,24 @@ __device__ inline LatSmem lat_carve(float* sm, const DecParams& P, bool bwd) {
   S.ROWMSK = sm; sm += bwd ? P.n_rowpar * RBMAX : 0;   // backward: chain-rule factors of the head clamps / exps, same row layout as ROWPAR
   S.EPS2 = sm; sm += bwd ? P.Z * TP : 0;               // backward: second buffers of the prefetched noise / dL/dz records
   S.DZ2 = sm; sm += bwd ? (nzd + P.nz_x) * TP : 0;
-  S.BAR = sm;                                          // two mbarriers (16 bytes)
+  S.BAR = sm; sm += 4;                                 // two mbarriers (16 bytes)
+  S.RAWH = sm;                                         // backward: 2 x [O_tot][RBMAX] raw head pre-activations (cp.async)
   return S;
 }
 
 // per-row parameters of q(z|x) and of the conditional priors, raw c / y
 template <class D>
-__device__ __forceinline__ void load_row_params(const DecParams& P, const LatSmem& S, long long row0, int nrows, bool msk = false) {
+__device__ __forceinline__ void load_row_params(const DecParams& P, const LatSmem& S, long long row0, int nrows, bool msk = false,
+                                                const float* rawh = nullptr) {
   const int tid = threadIdx.x, RB = D::RB(P), nzd = D::nz_c(P) + D::nz_y(P);
   const long long B = P.B;
+  // head pre-activation of feature row f for tile row r: from the staged tile (backward, prefetched) or from global
+  auto hp = [&](int f, int r, long long lrow) -> float { return rawh ? rawh[f * RBMAX + r] : P.headpre[(long long)f * B + lrow]; };
   for (int e = tid; e < RB * D::Z(P); e += LNT) {
     const int i = e / RB, r = e - i * RB;
     const long long lrow = row0 + min(r, nrows - 1);
     const int b = block_of_l<D>(P, i), il = i - D::blk_start(P, b);
-    const float pm = P.headpre[(long long)(D::henc(P, b) + il) * B + lrow];
+    const float pm = hp(D::henc(P, b) + il, r, lrow);
     S.ROWPAR[(D::rp_loc(P) + i) * RBMAX + r] = clampf_(pm, -50.0f, 50.0f);
     // d clamp / d pre: 1 inside the clamp range (models/encoders.py:35-43); d exp(clamp(ps)) / d ps = exp(ps) inside
     if (msk) S.ROWMSK[(D::rp_loc(P) + i) * RBMAX + r] = (pm >= -50.0f && pm <= 50.0f) ? 1.0f : 0.0f;
@@ -140,11 +144,11 @@ __device__ __forceinline__ void load_row_params(const DecParams& P, const LatSme
     const int b = D::L_blk(P, li), i = D::L_i(P, li), j = D::L_j(P, li), nzb = D::blk_size(P, b);
     float v, mk;
     if (i == j) {
-      const float ps = P.headpre[(long long)(D::henc(P, b) + nzb + i) * B + lrow];
+      const float ps = hp(D::henc(P, b) + nzb + i, r, lrow);
       v = expf(clampf_(ps, -7.0f, 3.0f)) + 1e-8f;
       mk = (ps >= -7.0f && ps <= 3.0f) ? expf(ps) : 0.0f;
     } else {
-      const float pc = P.headpre[(long long)(D::henc(P, b) + 2 * nzb + i * nzb + j) * B + lrow];
+      const float pc = hp(D::henc(P, b) + 2 * nzb + i * nzb + j, r, lrow);
       v = clampf_(pc, -20.0f, 20.0f);
       mk = (pc >= -20.0f && pc <= 20.0f) ? 1.0f : 0.0f;
     }
@@ -158,8 +162,8 @@ __device__ __forceinline__ void load_row_params(const DecParams& P, const LatSme
     const int kk = which ? k - D::nz_c(P) : k, nzk = which ? D::nz_y(P) : D::nz_c(P);
     float mu = 0.0f, sgm = 1.0f, mkm = 0.0f, mks = 0.0f;
     if (which == 0 || P.y != nullptr) {
-      const float pm = P.headpre[(long long)(D::hpri(P, which) + kk) * B + lrow];
-      const float ps = P.headpre[(long long)(D::hpri(P, which) + nzk + kk) * B + lrow];
+      const float pm = hp(D::hpri(P, which) + kk, r, lrow);
+      const float ps = hp(D::hpri(P, which) + nzk + kk, r, lrow);
       mu = clampf_(pm, -50.0f, 50.0f);
       sgm = expf(clampf_(ps, -7.0f, 3.0f)) + 1e-8f;
       mkm = (pm >= -50.0f && pm <= 50.0f) ? 1.0f : 0.0f;
@@ -172,6 +176,7 @@ __device__ __forceinline__ void load_row_params(const DecParams& P, const LatSme
       S.ROWMSK[(D::rp_psig(P) + k) * RBMAX + r] = mks;
     }
   }
+  if (!msk)   // raw c / y are only used by the forward (decoder record)
   for (int e = tid; e < RB * (D::nd_c(P) + D::nd_y(P)); e += LNT) {
     const int j = e / RB, r = e - j * RB;
     const long long lrow = row0 + min(r, nrows - 1);
@@ -364,6 +369,21 @@ __global__ void __launch_bounds__(LNT) lat_bwd_kernel(const __grid_constant__ De
     tc::bulk_g2s(buf ? S0.DZ2 : S0.DZ, P.dzrec + tile * (nzd + D::nz_x(P)) * TP, dz_bytes, lbar + buf);
   };
   if (tid == 0 && (long long)blockIdx.x < P.n_rowblocks) prefetch(blockIdx.x, 0);
+  // raw head pre-activations of a tile ([O_tot] feature rows x RB minibatch rows, 32-byte segments of the feature-major
+  // `headpre`): staged one tile ahead with 4-byte cp.async copies, so that the row-parameter pass reads shared memory
+  const int n_raw = P.O_tot * RB;
+  auto stage_heads = [&](long long tile, int buf) {
+    float* dst = S0.RAWH + buf * P.O_tot * RBMAX;
+    const long long r0 = tile * RB;
+    const int nr = (int)min((long long)RB, B - r0);
+    for (int e = tid; e < n_raw; e += LNT) {
+      const int f = e / RB, r = e - f * RB;
+      const float* src = P.headpre + (long long)f * B + r0 + min(r, nr - 1);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(tc::smem_u32(dst + f * RBMAX + r)), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if ((long long)blockIdx.x < P.n_rowblocks) stage_heads(blockIdx.x, 0);
   int it = 0;
   for (long long rb = blockIdx.x; rb < P.n_rowblocks; rb += gridDim.x, ++it) {
   const int buf = it & 1;
@@ -373,7 +393,10 @@ __global__ void __launch_bounds__(LNT) lat_bwd_kernel(const __grid_constant__ De
   const int nrows = (int)min((long long)RB, B - row0);
   const int npairs = nrows * n;
   if (tid == 0 && rb + gridDim.x < P.n_rowblocks) prefetch(rb + gridDim.x, buf ^ 1);   // its last readers passed the barrier below
-  load_row_params<D>(P, S, row0, nrows, true);
+  asm volatile("cp.async.wait_group 0;" ::: "memory");   // this tile's staged heads (own copies), then everybody's
+  __syncthreads();
+  if (rb + gridDim.x < P.n_rowblocks) stage_heads(rb + gridDim.x, buf ^ 1);
+  load_row_params<D>(P, S, row0, nrows, true, S0.RAWH + buf * P.O_tot * RBMAX);
   tc::mbar_wait(lbar + buf, (uint32_t)(it >> 1) & 1u);
   __syncthreads();
   const bool pvalid = p < npairs;
