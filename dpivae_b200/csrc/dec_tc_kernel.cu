@@ -53,6 +53,26 @@ enum { TPH_SETUP = 0, TPH_ROWPAR_EPS, TPH_LATENT, TPH_AUX1, TPH_A0, TPH_AUX2, TP
   } while (0)
 
 
+// Packed fp32 pairs (sm_100 FFMA2: two IEEE fp32 FMAs per instruction) for the CUDA-core auxiliary decoders: a pair of
+// hidden units is processed at once, weights are stored pair-interleaved in shared memory.
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t pk2(float a, float b) {
+  f2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(f2_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f2_t ffma2(f2_t a, f2_t b, f2_t c) {
+  f2_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f2_t fmul2(f2_t a, f2_t b) {
+  f2_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
 // write 8 consecutive columns (chunk) of row `row` of an X8 operand: hi plane + lo plane
 __device__ __forceinline__ void put8(unsigned char* plane, uint32_t lo_off, int R, int chunk, int row, const float* v) {
   uint4 hi, lo;
@@ -179,9 +199,9 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
   float* BX = smf + (T.f_bias_x >> 2);    // fx1 bias (+ last physics-layer bias)
   float* BP1 = smf + (T.f_bias_p1 >> 2);
   float* BP2 = smf + (T.f_bias_p2 >> 2);
-  float* AW0 = smf + (T.f_aw0 >> 2);      // aux first layers  [side][64][4]
+  float* AW0 = smf + (T.f_aw0 >> 2);      // aux first layers, unit pairs interleaved [side][32 pairs][4 inputs][2 units]
   float* AB0 = smf + (T.f_ab0 >> 2);      //                   [side][64]
-  float* AW1 = smf + (T.f_aw1 >> 2);      // aux heads, transposed [side][64][4]: mean_0, mean_1, ls_0, ls_1 per hidden unit
+  float* AW1 = smf + (T.f_aw1 >> 2);      // aux heads [side][32 pairs][4 outputs: mean_0, mean_1, ls_0, ls_1][2 units]
   float* AB1 = smf + (T.f_ab1 >> 2);      //                   [side][4]
   float* WP0F = smf + (T.f_wp0f >> 2);    // physics layer 0 weights w.r.t. the physics latents, fp32 [64][4]
   const float4* WP0F4 = reinterpret_cast<const float4*>(WP0F);
@@ -303,9 +323,10 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
     const int side = e >> 8, k = (e >> 2) & 63, j = e & 3;
     const Mlp2S& M = side ? P.dy : P.dc;
     const int nzs = side ? P.nz_y : P.nz_c, nd = side ? P.nd_y : P.nd_c;
-    AW0[e] = j < nzs ? prm[M.g_w0 + (long long)k * nzs + j] : 0.0f;
+    const int ep = ((side * 32 + (k >> 1)) * 4 + j) * 2 + (k & 1);   // pair-interleaved slot of (side, unit k, column j)
+    AW0[ep] = j < nzs ? prm[M.g_w0 + (long long)k * nzs + j] : 0.0f;
     const int o = (j & 1) < nd ? ((j >> 1) * nd + (j & 1)) : -1;  // head column j: mean_(j&1) (j < 2) or log_sigma_(j&1)
-    AW1[e] = o >= 0 ? prm[M.g_w1 + (long long)o * 64 + k] : 0.0f;
+    AW1[ep] = o >= 0 ? prm[M.g_w1 + (long long)o * 64 + k] : 0.0f;
     if (j == 0) AB0[side * 64 + k] = prm[M.g_b0 + k];
     if (k == 0) AB1[side * 4 + j] = o >= 0 ? prm[M.g_b1 + o] : 0.0f;
   }
@@ -361,9 +382,9 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
 
   // aux side of this thread
   const int a_nz = hh ? P.nz_y : P.nz_c, a_j0 = hh ? P.nz_c : 0, a_nd = hh ? P.nd_y : P.nd_c;
-  const float4* aW0 = reinterpret_cast<const float4*>(AW0) + hh * 64;
-  const float4* aW1 = reinterpret_cast<const float4*>(AW1) + hh * 64;
-  const float* aB0 = AB0 + hh * 64;
+  const ulonglong2* aW0 = reinterpret_cast<const ulonglong2*>(AW0) + hh * 64;   // [pair][2]: inputs (0,1), (2,3)
+  const ulonglong2* aW1 = reinterpret_cast<const ulonglong2*>(AW1) + hh * 64;   // [pair][2]: outputs (0,1), (2,3)
+  const f2_t* aB0 = reinterpret_cast<const f2_t*>(AB0) + hh * 32;
 
   // per-thread running sums over all tiles (fixed thread <-> column assignment: deterministic)
   float dbx[32];
@@ -545,24 +566,38 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
     unsigned long long mkA = 0ull;
     float g4[4] = {0.f, 0.f, 0.f, 0.f};
     {
-      float o0 = AB1[hh * 4 + 0], o1 = AB1[hh * 4 + 1], o2 = AB1[hh * 4 + 2], o3 = AB1[hh * 4 + 3];
+      // two hidden units per step on packed pairs (FFMA2); the head sums are kept as (even-unit, odd-unit) partials
+      const f2_t zz0 = pk2(z4[0], z4[0]), zz1 = pk2(z4[1], z4[1]), zz2 = pk2(z4[2], z4[2]), zz3 = pk2(z4[3], z4[3]);
+      f2_t oP0 = 0ull, oP1 = 0ull, oP2 = 0ull, oP3 = 0ull;
 #pragma unroll 2
       for (int c = 0; c < 8; ++c) {
         float hv[8];
         uint32_t m8 = 0u;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int k = 8 * c + i;
-          const float4 w = aW0[k];
-          const float pre = fmaf(z4[3], w.w, fmaf(z4[2], w.z, fmaf(z4[1], w.y, fmaf(z4[0], w.x, aB0[k]))));
-          const float h = fmaxf(pre, 0.0f);
-          m8 |= (pre > 0.0f ? 1u : 0u) << i;
-          const float4 t = aW1[k];
-          o0 = fmaf(h, t.x, o0); o1 = fmaf(h, t.y, o1); o2 = fmaf(h, t.z, o2); o3 = fmaf(h, t.w, o3);
-          hv[i] = h * s_h;
+        for (int i2 = 0; i2 < 4; ++i2) {
+          const int kp = 4 * c + i2;   // unit pair (2 kp, 2 kp + 1)
+          const ulonglong2 wa = aW0[2 * kp], wb = aW0[2 * kp + 1];
+          const f2_t pre2 = ffma2(zz3, wb.y, ffma2(zz2, wb.x, ffma2(zz1, wa.y, ffma2(zz0, wa.x, aB0[kp]))));
+          float pa, pb;
+          upk2(pre2, pa, pb);
+          const float ha = fmaxf(pa, 0.0f), hb = fmaxf(pb, 0.0f);
+          m8 |= ((pa > 0.0f ? 1u : 0u) | (pb > 0.0f ? 2u : 0u)) << (2 * i2);
+          const f2_t h2 = pk2(ha, hb);
+          const ulonglong2 ta = aW1[2 * kp], tb = aW1[2 * kp + 1];
+          oP0 = ffma2(h2, ta.x, oP0); oP1 = ffma2(h2, ta.y, oP1); oP2 = ffma2(h2, tb.x, oP2); oP3 = ffma2(h2, tb.y, oP3);
+          hv[2 * i2] = ha * s_h;
+          hv[2 * i2 + 1] = hb * s_h;
         }
         mkA |= (unsigned long long)m8 << (8 * c);
         if (P.with_grad) put8(pBIG, T.l_big, TP, 8 * hh + c, p, hv);
+      }
+      float o0, o1, o2, o3;
+      {
+        float a, b;
+        upk2(oP0, a, b); o0 = (a + b) + AB1[hh * 4 + 0];
+        upk2(oP1, a, b); o1 = (a + b) + AB1[hh * 4 + 1];
+        upk2(oP2, a, b); o2 = (a + b) + AB1[hh * 4 + 2];
+        upk2(oP3, a, b); o3 = (a + b) + AB1[hh * 4 + 3];
       }
       // Gaussian log-likelihood of the raw covariate / label and its gradient w.r.t. (mean, log sigma)
       float R = 0.0f;
@@ -612,24 +647,37 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
     // ================= auxiliary decoder backward (dgrad on the CUDA cores) =====================================
     if (P.with_grad) {
       stage_wait(bar1, ph1);  // wgrad aux1 done: BIG may be overwritten
-      float gz0 = 0.f, gz1 = 0.f, gz2 = 0.f, gz3 = 0.f;
+      const f2_t gg0 = pk2(g4[0], g4[0]), gg1 = pk2(g4[1], g4[1]), gg2 = pk2(g4[2], g4[2]), gg3 = pk2(g4[3], g4[3]);
+      f2_t gP0 = 0ull, gP1 = 0ull, gP2 = 0ull, gP3 = 0ull;   // (even-unit, odd-unit) partials of dL/dz
 #pragma unroll 2
       for (int c = 0; c < 8; ++c) {
         float hv[8];
         const uint32_t m8 = (uint32_t)(mkA >> (8 * c)) & 0xFFu;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int k = 8 * c + i;
-          const float4 t = aW1[k];
-          float gh = fmaf(g4[3], t.w, fmaf(g4[2], t.z, fmaf(g4[1], t.y, g4[0] * t.x)));
-          gh = ((m8 >> i) & 1u) ? gh : 0.0f;
-          const float4 w = aW0[k];
-          gz0 = fmaf(gh, w.x, gz0); gz1 = fmaf(gh, w.y, gz1); gz2 = fmaf(gh, w.z, gz2); gz3 = fmaf(gh, w.w, gz3);
-          hv[i] = gh;
+        for (int i2 = 0; i2 < 4; ++i2) {
+          const int kp = 4 * c + i2;
+          const ulonglong2 ta = aW1[2 * kp], tb = aW1[2 * kp + 1];
+          const f2_t gh2 = ffma2(gg3, tb.y, ffma2(gg2, tb.x, ffma2(gg1, ta.y, fmul2(gg0, ta.x))));
+          float ga, gb;
+          upk2(gh2, ga, gb);
+          ga = ((m8 >> (2 * i2)) & 1u) ? ga : 0.0f;
+          gb = ((m8 >> (2 * i2 + 1)) & 1u) ? gb : 0.0f;
+          const f2_t ghm = pk2(ga, gb);
+          const ulonglong2 wa = aW0[2 * kp], wb = aW0[2 * kp + 1];
+          gP0 = ffma2(ghm, wa.x, gP0); gP1 = ffma2(ghm, wa.y, gP1); gP2 = ffma2(ghm, wb.x, gP2); gP3 = ffma2(ghm, wb.y, gP3);
+          hv[2 * i2] = ga;
+          hv[2 * i2 + 1] = gb;
         }
         put8(pBIG, T.l_big, TP, 8 * hh + c, p, hv);
       }
-      const float gz[4] = {gz0, gz1, gz2, gz3};
+      float gz[4];
+      {
+        float a, b;
+        upk2(gP0, a, b); gz[0] = a + b;
+        upk2(gP1, a, b); gz[1] = a + b;
+        upk2(gP2, a, b); gz[2] = a + b;
+        upk2(gP3, a, b); gz[3] = a + b;
+      }
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         if (j < a_nz) DZA[(a_j0 + j) * TP + p] = gz[j];
