@@ -129,7 +129,7 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_oracle_throughput(wl, steps, warmup, threads=None):
+def cpu_oracle_throughput(wl, steps, warmup, threads=None, device="cpu", rows=None):
     """Reference algorithm on the host cores: oracle port (fp32 torch CPU tensor algebra) of
     loss -> backward -> Adam on a bounded sample of the workload."""
     import importlib
@@ -142,7 +142,7 @@ def cpu_oracle_throughput(wl, steps, warmup, threads=None):
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
     case_mod = importlib.import_module(f"dpivae_b200.cases.{wl['case']}")
-    rows, n = wl["cpu_rows"], wl["n_mc"]
+    rows, n = rows or wl["cpu_rows"], wl["n_mc"]
     x, c, y = synth(case_mod, rows, 123, "cpu")
     args = make_args(case_mod, wl["preset"], n_train=rows, n_batch=rows)
     import contextlib, io
@@ -160,22 +160,39 @@ def cpu_oracle_throughput(wl, steps, warmup, threads=None):
             "mean_x": vec(vae.transform_x.mean_), "std_x": vec(vae.transform_x.scale_), "mean_c": vec(vae.transform_c.mean_),
             "std_c": vec(vae.transform_c.scale_), "mean_y": vec(vae.transform_y.mean_), "std_y": vec(vae.transform_y.scale_)}
     spec = orc.cast_spec(spec, torch.float32)
+    if device != "cpu":
+        # the same torch tensor algebra as eager CUDA ops: the "existing Blackwell path" of SURVEY.md §8(d)
+        def mv(o):
+            if torch.is_tensor(o):
+                return o.to(device)
+            if isinstance(o, dict):
+                return {k: mv(v) for k, v in o.items()}
+            if isinstance(o, (list, tuple)):
+                return type(o)(mv(v) for v in o)
+            return o
+        spec = mv(spec)
+        sd = {k: v.to(device).requires_grad_(v.requires_grad) for k, v in sd.items()}
+        x, c, y = x.to(device), c.to(device), y.to(device)
     names = spec["trainable"]
     m = {k: torch.zeros_like(sd[k]) for k in names}
     v = {k: torch.zeros_like(sd[k]) for k in names}
     lr = {k: (5e-3 if k == "log_sigma_x" else 1e-3) for k in names}
     wd = {k: 0.0 for k in names}
-    g = torch.Generator().manual_seed(0)
+    g = torch.Generator(device=device).manual_seed(0)
     widths = (vae.nz_x, vae.nz_c, vae.nz_y)
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
+        if device != "cpu":
+            torch.cuda.synchronize()
         if args.model_type == "P":
-            eps = tuple(torch.randn(n, rows, k, generator=g) for k in widths)
+            eps = tuple(torch.randn(n, rows, k, generator=g, device=device) for k in widths)
         else:
-            eps = torch.randn(n, rows, sum(widths), generator=g)
+            eps = torch.randn(n, rows, sum(widths), generator=g, device=device)
         _, _, _, grads = orc.loss_and_grads(sd, spec, x, c, y, eps)
         orc.adam_step({k: sd[k] for k in names}, grads, m, v, it + 1, lr, wd)
+        if device != "cpu":
+            torch.cuda.synchronize()
         if it >= warmup:
             times.append(time.perf_counter() - t0)
     sec = sum(times) / len(times)
@@ -594,6 +611,15 @@ def main():
             line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"{crow} rows x {n} MC, 3 steps after 1 warm-up (oracle port, fp32 torch CPU)",
                                     "ms_per_step": sec * 1e3}
+            # informational: the same torch tensor algebra as eager CUDA ops on this GPU -- the "existing Blackwell path"
+            # of SURVEY.md §8(d) (the reference itself is not installable here; this is the oracle port, as in the CPU leg)
+            try:
+                torch.cuda.empty_cache()
+                ev, esec, _, erow = cpu_oracle_throughput(wl, 3, 2, device=f"cuda:{local_rank}", rows=min(rows, 65536))
+                line["torch_eager_gpu_baseline"] = {"value": ev, "unit": UNIT, "kind": "port (torch eager ops, fp32, same GPU)",
+                                                    "sample": f"{erow} rows x {n} MC, 3 steps after 2 warm-ups", "ms_per_step": esec * 1e3}
+            except Exception as exc:   # never let the informational leg break the bench line
+                line["torch_eager_gpu_baseline"] = {"unavailable": str(exc)[:200]}
         emit(line)
     if world > 1:
         dist.barrier()

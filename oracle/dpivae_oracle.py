@@ -94,7 +94,7 @@ def log_prior_zx(zx, prior_x):
     """utils/priors.py:19-23 summed over the last dim (models/vae.py:201).
 
     prior_x: list of ("uniform", low, high) | ("normal", loc, scale)."""
-    tot = torch.zeros(zx.shape[:-1], dtype=zx.dtype)
+    tot = torch.zeros(zx.shape[:-1], dtype=zx.dtype, device=zx.device)
     for i, (kind, a, b) in enumerate(prior_x):
         zi = zx[..., i]
         if kind == "uniform":
@@ -251,12 +251,12 @@ def loss(sd, spec, x, c, y, eps, beta_x=1.0, alpha_x=1.0, alpha_c=1.0, alpha_y=1
     R_x = normal_log_prob(x, xh, sd["log_sigma_x"]).sum(-1).mean(0)
     R_c = normal_log_prob(c, ch, lsc).sum(-1).mean(0)
     R_y = normal_log_prob(y, yh, lsy).sum(-1).mean(0)
-    reg = torch.zeros(x.shape[0], dtype=x.dtype)
+    reg = torch.zeros(x.shape[0], dtype=x.dtype, device=x.device)
     if spec.get("lambda_x") is not None:
         lam = float(spec["lambda_x"])
         reg = reg + (-(xh_d**2) / (2.0 * lam * lam) - math.log(lam) - LOG_SQRT_2PI).sum(-1).mean(0)
     total = beta_x * KL_x - alpha_x * R_x - alpha_c * R_c - alpha_y * R_y - reg
-    zero = torch.tensor(0.0, dtype=x.dtype)
+    zero = torch.tensor(0.0, dtype=x.dtype, device=x.device)
     return (total, KL_x, zero, zero, R_x, R_c, R_y, reg), fw
 
 
