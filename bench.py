@@ -611,15 +611,15 @@ def main():
             line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"{crow} rows x {n} MC, 3 steps after 1 warm-up (oracle port, fp32 torch CPU)",
                                     "ms_per_step": sec * 1e3}
-            # informational: the same torch tensor algebra as eager CUDA ops on this GPU -- the "existing Blackwell path"
+            # baseline leg, second device: the same port's torch tensor algebra as eager CUDA ops on this GPU -- the "existing Blackwell path"
             # of SURVEY.md §8(d) (the reference itself is not installable here; this is the oracle port, as in the CPU leg)
             try:
                 torch.cuda.empty_cache()
                 ev, esec, _, erow = cpu_oracle_throughput(wl, 3, 2, device=f"cuda:{local_rank}", rows=min(rows, 65536))
-                line["torch_eager_gpu_baseline"] = {"value": ev, "unit": UNIT, "kind": "port (torch eager ops, fp32, same GPU)",
+                line["cpu_baseline"]["torch_eager_same_gpu"] = {"value": ev, "unit": UNIT, "kind": "port (torch eager ops, fp32, same GPU)",
                                                     "sample": f"{erow} rows x {n} MC, 3 steps after 2 warm-ups", "ms_per_step": esec * 1e3}
             except Exception as exc:   # never let the informational leg break the bench line
-                line["torch_eager_gpu_baseline"] = {"unavailable": str(exc)[:200]}
+                line["cpu_baseline"]["torch_eager_same_gpu"] = {"unavailable": str(exc)[:200]}
         emit(line)
     if world > 1:
         dist.barrier()
