@@ -603,8 +603,9 @@ static int run_loss(dpivae_handle_t h, const dpivae_batch_t* bt, const dpivae_rn
       launch_enc_tc_fwd(Q, grid_etc, st);
       ++launches;
       if (!latent_only) {
-        if (prior_fast) launch_prior_fwd(E2, h->sm_count, st);
-        else launch_enc_fwd(E2, L.grid_enc, enc_smem, st);
+        // independent of the encoder kernel (other units, other output rows): launched to run alongside it
+        if (prior_fast) launch_prior_fwd(E2, h->sm_count, st, true);
+        else launch_enc_fwd(E2, L.grid_enc, enc_smem, st, true);
         ++launches;
       }
     } else if (prior_fast && !latent_only) {
@@ -676,8 +677,9 @@ static int run_loss(dpivae_handle_t h, const dpivae_batch_t* bt, const dpivae_rn
       Q.e_g = (int)lrint(log2((double)bt->B_global * (double)(h->d.nd_x + h->d.nd_c + h->d.nd_y))) + 4;
       launch_enc_tc_bwd(Q, grid_etc, st);
       ++launches;
-      if (prior_fast) launch_prior_bwd(E2, L.grid_enc, st);
-      else launch_enc_bwd(E2, L.grid_enc, enc_smem, st);
+      // runs alongside the encoder backward kernel (released once that kernel has seen lat_bwd complete)
+      if (prior_fast) launch_prior_bwd(E2, L.grid_enc, st, true);
+      else launch_enc_bwd(E2, L.grid_enc, enc_smem, st, true);
       ++launches;
     } else if (prior_fast) {
       EncParams E1 = E;

@@ -285,3 +285,31 @@ __device__ __forceinline__ void gemm_wgrad(const float* __restrict__ A, const fl
 }
 
 }  // namespace dpv
+// Programmatic dependent launch (PDL): a kernel launched with launch_pdl() may start while the kernel before it on the
+// stream is still running -- its prologue (shared-memory zeroing, weight staging: inputs that the previous kernel does
+// not write) overlaps the previous kernel's tail. pdl_wait() blocks until the previous kernel has completed and its
+// writes are visible; EVERY thread block of the dependent kernel must execute it before touching those writes (and
+// at least once in any case, so that the dependent cannot complete before its predecessor). The predecessor calls
+// pdl_launch_dependents() at its top to release the early launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#ifdef __CUDACC__
+template <typename K, typename PT>
+static inline void launch_pdl3(K kernel, dim3 grid, int block, size_t smem, cudaStream_t s, const PT& params) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, params);
+}
+template <typename K, typename PT>
+static inline void launch_pdl(K kernel, int grid, int block, size_t smem, cudaStream_t s, const PT& params) {
+  launch_pdl3(kernel, dim3((unsigned)grid), block, smem, s, params);
+}
+#endif

@@ -396,6 +396,8 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
   uint32_t wacc = 0;  // 0 on the first tile (weight-gradient accumulators start from zero)
   TPHASE(TPH_SETUP);
 
+  // everything above read only the parameters and the targets; the tile records below come from lat_fwd (PDL)
+  pdl_wait();
 
   if (warp == 8) {
     // ================= MMA-issue warp: mirrors the stage sequence of the epilogue warps =================================
@@ -1115,7 +1117,7 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
 
 template <bool PROF, int PHYS, int NDX>
 static void launch_one(const TcParams& p, int grid, cudaStream_t s) {
-  dec_tc_kernel<PROF, PHYS, NDX><<<grid, NTHR, p.total, s>>>(p);
+  launch_pdl(dec_tc_kernel<PROF, PHYS, NDX>, grid, NTHR, (size_t)p.total, s, p);
 }
 
 // supported (physics kind, nd_x) pairs: (MLP, 64) bridge, (mass_spring, 64) damped_oscillator, (beam, 32) simple_beam,

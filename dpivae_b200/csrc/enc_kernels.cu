@@ -101,6 +101,7 @@ __global__ void __launch_bounds__(NT, 2) enc_fwd_kernel(const __grid_constant__ 
       __syncthreads();
     }
   }
+  pdl_wait();   // no-op unless launched with overlap = true (see launch_enc_fwd in kernels.h)
 }
 
 __global__ void __launch_bounds__(NT, 2) enc_bwd_kernel(const __grid_constant__ EncParams P) {
@@ -143,6 +144,7 @@ __global__ void __launch_bounds__(NT, 2) enc_bwd_kernel(const __grid_constant__ 
       __syncthreads();
     }
   }
+  pdl_wait();   // no-op unless launched with overlap = true (see launch_enc_fwd in kernels.h)
 }
 
 size_t enc_smem_bytes(const EncParams& p, bool bwd) {
@@ -157,11 +159,13 @@ size_t enc_smem_bytes(const EncParams& p, bool bwd) {
 static dim3 enc_grid(const EncParams& p, int grid) {
   return dim3((unsigned)grid, (unsigned)((long long)grid * p.n_units <= 2LL * 148 ? p.n_units : 1), 1);
 }
-void launch_enc_fwd(const EncParams& p, int grid, size_t smem, cudaStream_t s) {
-  enc_fwd_kernel<<<enc_grid(p, grid), NT, smem, s>>>(p);
+void launch_enc_fwd(const EncParams& p, int grid, size_t smem, cudaStream_t s, bool overlap) {
+  if (overlap) launch_pdl3(enc_fwd_kernel, enc_grid(p, grid), NT, smem, s, p);
+  else enc_fwd_kernel<<<enc_grid(p, grid), NT, smem, s>>>(p);
 }
-void launch_enc_bwd(const EncParams& p, int grid, size_t smem, cudaStream_t s) {
-  enc_bwd_kernel<<<enc_grid(p, grid), NT, smem, s>>>(p);
+void launch_enc_bwd(const EncParams& p, int grid, size_t smem, cudaStream_t s, bool overlap) {
+  if (overlap) launch_pdl3(enc_bwd_kernel, enc_grid(p, grid), NT, smem, s, p);
+  else enc_bwd_kernel<<<enc_grid(p, grid), NT, smem, s>>>(p);
 }
 
 int configure_enc_kernels() {

@@ -58,6 +58,7 @@ __device__ __forceinline__ int scale_exp_e(float mx) {
 
 __global__ void __launch_bounds__(ENT, 1) enc_tc_fwd_kernel(const __grid_constant__ EncTcParams P) {
   extern __shared__ __align__(1024) unsigned char smb[];
+  pdl_launch_dependents();   // the prior-net forward kernel is independent of this one and runs alongside it
   float* smf = reinterpret_cast<float*>(smb);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int q = warp & 3, hh = warp >> 2;
@@ -484,6 +485,10 @@ __global__ void __launch_bounds__(ENT, 1) enc_tc_bwd_kernel(const __grid_constan
         }
       }
   };
+  // the setup above read only the parameters; the head gradients fetched from here on come from lat_bwd (PDL)
+  pdl_wait();
+  // lat_bwd is complete from here on: the prior-net backward kernel (independent of this one) may run alongside
+  pdl_launch_dependents();
   fetch_in(blockIdx.x);
 
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -650,7 +655,7 @@ __global__ void __launch_bounds__(ENT, 1) enc_tc_bwd_kernel(const __grid_constan
   if (warp == 0) tc::tmem_dealloc(tb, 512);
 }
 
-void launch_enc_tc_bwd(const EncTcParams& p, int grid, cudaStream_t s) { enc_tc_bwd_kernel<<<grid, ENT, p.total_b, s>>>(p); }
+void launch_enc_tc_bwd(const EncTcParams& p, int grid, cudaStream_t s) { launch_pdl(enc_tc_bwd_kernel, grid, ENT, (size_t)p.total_b, s, p); }
 
 void launch_enc_tc_fwd(const EncTcParams& p, int grid, cudaStream_t s) { enc_tc_fwd_kernel<<<grid, ENT, p.total, s>>>(p); }
 int configure_enc_tc_kernels() {

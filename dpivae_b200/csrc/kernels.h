@@ -256,13 +256,15 @@ void launch_datagen_finish(const DataGenParams& p, cudaStream_t s);
 
 size_t dec_smem_bytes(const DecParams& p);
 void launch_dec(const DecParams& p, int grid, cudaStream_t s);
-void launch_enc_fwd(const EncParams& p, int grid, size_t smem, cudaStream_t s);
-void launch_enc_bwd(const EncParams& p, int grid, size_t smem, cudaStream_t s);
+// overlap = true: programmatic dependent launch that runs CONCURRENTLY with the kernel before it on the stream (the
+// caller guarantees that the two are independent; the kernels wait for their predecessor only at their very end)
+void launch_enc_fwd(const EncParams& p, int grid, size_t smem, cudaStream_t s, bool overlap = false);
+void launch_enc_bwd(const EncParams& p, int grid, size_t smem, cudaStream_t s, bool overlap = false);
 size_t enc_smem_bytes(const EncParams& p, bool bwd);
 // dedicated kernels of the two conditional-prior nets (prior_kernels.cu)
 bool prior_kernels_support(const EncParams& prior_units);
-void launch_prior_fwd(const EncParams& prior_units, int sm_count, cudaStream_t s);
-void launch_prior_bwd(const EncParams& prior_units, int grid, cudaStream_t s);   // grid = number of per-CTA partial rows
+void launch_prior_fwd(const EncParams& prior_units, int sm_count, cudaStream_t s, bool overlap = false);
+void launch_prior_bwd(const EncParams& prior_units, int grid, cudaStream_t s, bool overlap = false);   // grid = number of per-CTA partial rows
 void launch_reduce(const ReduceParams& p, cudaStream_t s);
 void launch_gradnorm(const float* grads, long long n, float max_norm, float* clip_coef, cudaStream_t s);
 void launch_adam(const AdamParams& p, cudaStream_t s);

@@ -236,6 +236,7 @@ __device__ __forceinline__ float sample_blocks(const DecParams& P, const LatSmem
 template <class D>
 __global__ void __launch_bounds__(LNT) lat_fwd_kernel(const __grid_constant__ DecParams P) {
   extern __shared__ __align__(16) float lsm[];
+  pdl_launch_dependents();   // the decoder kernel may stage its weights while these tiles are processed
   const LatSmem S = lat_carve(lsm, P, false);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, hh = warp >> 2, p = 32 * q + lane;
@@ -345,6 +346,7 @@ __global__ void __launch_bounds__(LNT) lat_fwd_kernel(const __grid_constant__ De
 template <class D>
 __global__ void __launch_bounds__(LNT) lat_bwd_kernel(const __grid_constant__ DecParams P) {
   extern __shared__ __align__(16) float lsm[];
+  pdl_launch_dependents();   // the encoder backward kernel may stage its weights while these tiles are processed
   const LatSmem S0 = lat_carve(lsm, P, true);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, hh = warp >> 2, p = 32 * q + lane;

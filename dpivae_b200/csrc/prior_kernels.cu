@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(PNT) prior_fwd_kernel(const __grid_constant__ 
         }
     }
   }
+  pdl_wait();   // no-op unless launched with overlap = true (see launch_enc_fwd in kernels.h)
 }
 
 // blockDim = PRG * 64 * n_units: thread (row group rg, net u, hidden unit k)
@@ -212,6 +213,7 @@ __global__ void __launch_bounds__(PRG * 2 * PH) prior_bwd_kernel(const __grid_co
     }
     if (k < U.O) part[U.g_b1 + k] = a_b1;
   }
+  pdl_wait();   // no-op unless launched with overlap = true (see launch_enc_fwd in kernels.h)
 }
 
 bool prior_kernels_support(const EncParams& p) {
@@ -221,12 +223,16 @@ bool prior_kernels_support(const EncParams& p) {
   return true;
 }
 
-void launch_prior_fwd(const EncParams& p, int sm_count, cudaStream_t s) {
+void launch_prior_fwd(const EncParams& p, int sm_count, cudaStream_t s, bool overlap) {
   long long g = (p.B + 2 * PNT - 1) / (2 * PNT);   // two rows per thread
   if (g > 4LL * sm_count) g = 4LL * sm_count;
-  prior_fwd_kernel<<<(unsigned)(g < 1 ? 1 : g), PNT, 0, s>>>(p);
+  if (overlap) launch_pdl(prior_fwd_kernel, (int)(g < 1 ? 1 : g), PNT, 0, s, p);
+  else prior_fwd_kernel<<<(unsigned)(g < 1 ? 1 : g), PNT, 0, s>>>(p);
 }
 
-void launch_prior_bwd(const EncParams& p, int grid, cudaStream_t s) { prior_bwd_kernel<<<grid, PRG * PH * p.n_units, 0, s>>>(p); }
+void launch_prior_bwd(const EncParams& p, int grid, cudaStream_t s, bool overlap) {
+  if (overlap) launch_pdl(prior_bwd_kernel, grid, PRG * PH * p.n_units, 0, s, p);
+  else prior_bwd_kernel<<<grid, PRG * PH * p.n_units, 0, s>>>(p);
+}
 
 }  // namespace dpv
