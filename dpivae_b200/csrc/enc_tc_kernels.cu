@@ -504,7 +504,8 @@ __global__ void __launch_bounds__(ENT, 1) enc_tc_bwd_kernel(const __grid_constan
         float v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          v[i] = valid ? gq[c * 8 + i] * sgp : 0.0f;
+          // head gradients of outlier rows can exceed the fp16 range after scaling (inf - inf = NaN in the split): saturate
+          v[i] = valid ? fminf(fmaxf(gq[c * 8 + i] * sgp, -60000.0f), 60000.0f) : 0.0f;
           db1[c * 8 + i] += v[i];
         }
         put8e(pG, P.lb_g, TP, o0 >> 3, p, v);
@@ -567,7 +568,7 @@ __global__ void __launch_bounds__(ENT, 1) enc_tc_bwd_kernel(const __grid_constan
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const uint32_t hbits = (hw[i >> 1] >> ((i & 1) * 16)) & 0x7FFFu;   // |hi half| : zero <=> ReLU inactive
-        g[i] = hbits != 0u ? g[i] * inv1d : 0.0f;
+        g[i] = hbits != 0u ? fminf(fmaxf(g[i] * inv1d, -60000.0f), 60000.0f) : 0.0f;
       }
       put8e(pH, P.hid_lo, TP, k0 >> 3, p, g);
     }

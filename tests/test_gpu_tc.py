@@ -240,3 +240,20 @@ def test_tc_outlier_inputs_give_finite_gradients():
     fin = torch.isfinite(out["fp32"][0][0])
     assert gu.rel_l2(out["tc_fp16x3"][0][0][fin], out["fp32"][0][0][fin]) < 1e-5
     assert gu.rel_l2(out["tc_fp16x3"][1], out["fp32"][1]) < 5e-5
+
+
+@pytest.mark.gpu
+def test_tc_extreme_outliers_do_not_poison_the_gradients():
+    """Rows ~100 scaler sigmas out (row losses overflow to +-inf in the fp32 kernels as well): the head gradients of
+    those rows exceed the fp16 operand range of the encoder backward; they saturate instead of turning the whole
+    weight gradient into NaN (the fp32 kernels give finite gradients on the same data)."""
+    g, spec, sd, args, case_mod, vae, (x, c, y) = build_from_golden("bridge", "P")
+    eng = vae.engine()
+    reps = 40
+    X, C_, Y = (torch.cat([t] * reps, 0).cuda() for t in (x, c, y))
+    X = X + 0.01 * torch.randn(X.shape, generator=torch.Generator().manual_seed(1)).cuda()
+    for mode in ("fp32", "tc_fp16x3"):
+        eng.set_math_mode(mode)
+        torch.manual_seed(123)
+        eng.loss(X, C_, Y, 16, (1.0, 1.0, 1.0, 1.0), True)
+        assert not torch.isnan(eng.grads).any(), mode
