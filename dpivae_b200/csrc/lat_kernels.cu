@@ -500,45 +500,70 @@ __global__ void __launch_bounds__(LNT) lat_bwd_kernel(const __grid_constant__ De
 // Encode-only inference (models/vae.py:161-162, 125-151): one thread per (MC sample, row) pair, head pre-activations read
 // feature-major (coalesced along the rows), latents and density written in the reference's (n, B, .) layout.  No
 // decoder, no priors: the HBM-streaming kernel of BASELINE.json config 5.
+template <class D>
 __global__ void __launch_bounds__(LNT) lat_encode_kernel(const __grid_constant__ DecParams P) {
-  extern __shared__ __align__(16) float lsm[];   // EPS[Z][LNT]
+  extern __shared__ __align__(16) float lsm[];   // EPS[Z][LNT] | HP[heads used][LNT]
   const int tid = threadIdx.x;
   const long long B = P.B;
   const long long q = (long long)blockIdx.x * LNT + tid;
   if (q >= (long long)P.n_mc * B) return;
   const long long m = q / B, r = q - m * B;
   const unsigned long long grow = (unsigned long long)(P.row_off + r);
-  for (int i = 0; i < P.Z; ++i) {
-    const int b = block_of_l<ShGeneric>(P, i), il = i - P.blk_start[b], nzb = P.blk_size[b];
+  // All head pre-activations of this row go to shared memory with 4-byte async copies (own column, read back by the
+  // same thread in the same order): ~33 independent loads in flight under the Philox work, instead of loads that the
+  // output stores (possible aliases for the compiler) keep in program order.
+  float* HP = lsm + (size_t)D::Z(P) * LNT;
+  {
+    int nh = 0;
+    auto stage = [&](int row) {
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(tc::smem_u32(HP + (size_t)(nh++) * LNT + tid)),
+                   "l"(P.headpre + (long long)row * B + r) : "memory");
+    };
+#pragma unroll
+    for (int b = 0; b < D::n_blk(P); ++b) {
+      const int nzb = D::blk_size(P, b);
+      for (int i = 0; i < nzb; ++i) {
+        stage(D::henc(P, b) + i);
+        for (int j = 0; j < i; ++j) stage(D::henc(P, b) + 2 * nzb + i * nzb + j);
+        stage(D::henc(P, b) + nzb + i);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  for (int i = 0; i < D::Z(P); ++i) {
+    const int b = block_of_l<D>(P, i), il = i - D::blk_start(P, b), nzb = D::blk_size(P, b);
     const unsigned long long li = ((unsigned long long)m * (unsigned long long)P.Bg + grow) * nzb + il;
     lsm[i * LNT + tid] = P.rng.mode == 0 ? P.rng.eps[b][li] : philox_normal_elem(P.rng.seed, P.rng.ss ? P.rng.ss->philox_off[b] : P.rng.offset[b], P.rng.grid_threads[b], li);
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   float dens = 0.0f;
-  for (int b = 0; b < P.n_blk; ++b) {
-    const int s = P.blk_start[b], nzb = P.blk_size[b];
+  int nh = 0;
+#pragma unroll
+  for (int b = 0; b < D::n_blk(P); ++b) {
+    const int s = D::blk_start(P, b), nzb = D::blk_size(P, b);
     float ss = 0.0f, hld = 0.0f, ld1 = 0.0f, ld2 = 0.0f;
     for (int i = 0; i < nzb; ++i) {
-      float acc = clampf_(P.headpre[(long long)(P.henc[b] + i) * B + r], -50.0f, 50.0f);
+      float acc = clampf_(HP[(size_t)(nh++) * LNT + tid], -50.0f, 50.0f);
       for (int j = 0; j < i; ++j) {
-        const float lij = clampf_(P.headpre[(long long)(P.henc[b] + 2 * nzb + i * nzb + j) * B + r], -20.0f, 20.0f);
+        const float lij = clampf_(HP[(size_t)(nh++) * LNT + tid], -20.0f, 20.0f);
         acc = fmaf(lij, lsm[(s + j) * LNT + tid], acc);
       }
-      const float lii = expf(clampf_(P.headpre[(long long)(P.henc[b] + nzb + i) * B + r], -7.0f, 3.0f)) + 1e-8f;
+      const float lii = expf(clampf_(HP[(size_t)(nh++) * LNT + tid], -7.0f, 3.0f)) + 1e-8f;
       const float e = lsm[(s + i) * LNT + tid];
       acc = fmaf(lii, e, acc);
       ss = fmaf(e, e, ss);
       hld += logf(lii);
       const int gi = s + i;
-      if (gi < P.nz_x) {
+      if (gi < D::nz_x(P)) {
         const float u = sigmoidf_(acc);
         const float a = P.ub[gi] - P.lb[gi];
         ld1 += acc - 2.0f * softplusf_(acc);
         ld2 += logf(fabsf(a));
-        if (P.out.zx) P.out.zx[q * P.nz_x + gi] = fmaf(u, a, P.lb[gi]);
-      } else if (gi < P.nz_x + P.nz_c) {
-        if (P.out.zc) P.out.zc[q * P.nz_c + (gi - P.nz_x)] = acc;
+        if (P.out.zx) P.out.zx[q * D::nz_x(P) + gi] = fmaf(u, a, P.lb[gi]);
+      } else if (gi < D::nz_x(P) + D::nz_c(P)) {
+        if (P.out.zc) P.out.zc[q * D::nz_c(P) + (gi - D::nz_x(P))] = acc;
       } else {
-        if (P.out.zy) P.out.zy[q * P.nz_y + (gi - P.nz_x - P.nz_c)] = acc;
+        if (P.out.zy) P.out.zy[q * D::nz_y(P) + (gi - D::nz_x(P) - D::nz_c(P))] = acc;
       }
     }
     const float lq = -0.5f * ((float)nzb * LOG_2PI + ss) - hld;
@@ -546,11 +571,6 @@ __global__ void __launch_bounds__(LNT) lat_encode_kernel(const __grid_constant__
     else dens += lq;
   }
   if (P.out.dens) P.out.dens[q] = dens;
-}
-
-void launch_lat_encode(const DecParams& p, cudaStream_t s) {
-  const long long total = (long long)p.n_mc * p.B;
-  lat_encode_kernel<<<(unsigned)((total + LNT - 1) / LNT), LNT, (size_t)p.Z * LNT * sizeof(float), s>>>(p);
 }
 
 size_t lat_smem_bytes(const DecParams& p, bool bwd) { return (size_t)lat_smem_floats(p, bwd) * sizeof(float); }
@@ -589,6 +609,33 @@ static void launch_lat(const DecParams& p, long long n_tiles, bool bwd, cudaStre
   else if (shape_matches(p, ShBeamP())) launch_lat_pair<ShBeamP>(p, n_tiles, bwd, s);
   else if (shape_matches(p, ShBeamS())) launch_lat_pair<ShBeamS>(p, n_tiles, bwd, s);
   else launch_lat_pair<ShGeneric>(p, n_tiles, bwd, s);
+}
+template <class SH>
+static void launch_lat_encode_t(const DecParams& p, cudaStream_t s) {
+  const long long total = (long long)p.n_mc * p.B;
+  int nh = 0;
+  for (int b = 0; b < p.n_blk; ++b) nh += 2 * p.blk_size[b] + p.blk_size[b] * (p.blk_size[b] - 1) / 2;
+  const size_t smem = (size_t)(p.Z + nh) * LNT * sizeof(float);
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    cudaFuncSetAttribute(lat_encode_kernel<SH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    smem_set = smem;
+  }
+  lat_encode_kernel<SH><<<(unsigned)((total + LNT - 1) / LNT), LNT, smem, s>>>(p);
+}
+// the encode kernel only depends on the latent layout (model type and block sizes), not on n_mc or the data widths
+template <int MT, int NX, int NC, int NY, int NDC, int NDY, int NDP, int NMC>
+static bool latent_layout_matches(const DecParams& p, Shape<MT, NX, NC, NY, NDC, NDY, NDP, NMC>) {
+  return p.model_type == MT && p.nz_x == NX && p.nz_c == NC && p.nz_y == NY;
+}
+void launch_lat_encode(const DecParams& p, cudaStream_t s) {
+  if (latent_layout_matches(p, ShBridgeP())) launch_lat_encode_t<ShBridgeP>(p, s);
+  else if (latent_layout_matches(p, ShBridgeS())) launch_lat_encode_t<ShBridgeS>(p, s);
+  else if (latent_layout_matches(p, ShOscP())) launch_lat_encode_t<ShOscP>(p, s);
+  else if (latent_layout_matches(p, ShOscS())) launch_lat_encode_t<ShOscS>(p, s);
+  else if (latent_layout_matches(p, ShBeamP())) launch_lat_encode_t<ShBeamP>(p, s);
+  else if (latent_layout_matches(p, ShBeamS())) launch_lat_encode_t<ShBeamS>(p, s);
+  else launch_lat_encode_t<ShGeneric>(p, s);
 }
 void launch_lat_fwd(const DecParams& p, long long n_tiles, cudaStream_t s) { launch_lat(p, n_tiles, false, s); }
 void launch_lat_bwd(const DecParams& p, long long n_tiles, cudaStream_t s) { launch_lat(p, n_tiles, true, s); }
