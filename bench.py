@@ -30,9 +30,9 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 WORKLOADS = {
-    "bridge_p": dict(case="bridge", preset="DPIVAE-A", rows=131072, n_mc=16, cpu_rows=8192,
+    "bridge_p": dict(case="bridge", preset="DPIVAE-A", rows=131072, n_mc=16, cpu_rows=8192, ref_rows=65536,
                      flop_step=1_597_440, flop_dec=1_519_616, bytes_row=296),
-    "beam_s": dict(case="simple_beam", preset="dpivae", rows=65536, n_mc=16, cpu_rows=16384,
+    "beam_s": dict(case="simple_beam", preset="dpivae", rows=65536, n_mc=16, cpu_rows=16384, ref_rows=65536,
                    flop_step=548_352, flop_dec=2 * 16 * ((4 * 128 + 128 * 32) * 3 + (2 * 64 + 128) * 2 * 3), bytes_row=160),
 }
 MATH_DOC = {
@@ -43,6 +43,11 @@ MATH_DOC = {
 }
 WORKLOADS["bridge_encode"] = dict(case="bridge", preset="DPIVAE-A", rows=524288, n_mc=1, bytes_row=300, flop_row=31_744)
 WORKLOADS["ensemble"] = dict(case="damped_oscillator", preset="dpivae", rows=64, n_mc=16, members=8, inner_steps=16)
+ENCODE_KERNEL_DOC = {
+    "fp32": "enc_fwd_kernel (fp32 FFMA) + lat_encode_kernel",
+    "tc_fp16x3": "enc_tc_fwd_kernel (tcgen05) + lat_encode_kernel",
+    "tc_fp16": "enc_tc_fwd_kernel (tcgen05) + lat_encode_kernel",
+}
 METRIC = "ELBO train samples/s (fwd+bwd+Adam)"
 UNIT = "datapoints/s"
 
@@ -199,16 +204,96 @@ def cpu_oracle_throughput(wl, steps, warmup, threads=None, device="cpu", rows=No
     return rows / sec, sec, threads, rows
 
 
+def reference_available():
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import ref_harness
+
+    return ref_harness.available()
+
+
+def reference_throughput(wl, steps, warmup, rows, threads=None):
+    """The UNMODIFIED reference (baseline/_ref, or /root/reference in the build container) on the host cores: its own
+    `setup_model` and `train_model` (dpivae.py:89,285) on `rows` rows x n_mc samples per iteration, n_batch = n_train
+    (the reference's own multinomial draw then returns a permutation).  Per-iteration wall time is read off the
+    reference's one `torch.multinomial` call per iteration (dpivae.py:403); the first `warmup` iterations are dropped.
+    Import shims only (tools/ref_harness.py); `torch.cuda.is_available` is masked while the reference's modules are
+    imported so that utils/__init__.py:5 picks the CPU."""
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import ref_harness
+
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    cwd = os.getcwd()
+    avail = torch.cuda.is_available
+    torch.cuda.is_available = lambda: False
+    try:
+        dp, case = ref_harness.load(wl["case"])
+        from utils.data import sample_response as ref_sample_response
+        from utils.priors import get_prior_dist as ref_get_prior_dist
+    finally:
+        torch.cuda.is_available = avail
+    try:
+        definition = case.definition
+        args = ref_harness.make_args(case, wl["preset"], use_seed=True, seed=123, n_train=rows, n_batch=rows, n_val=8,
+                                     n_mc_train=wl["n_mc"], n_mc_val=1, n_iter=warmup + steps, val_freq=10 ** 9)
+        torch.manual_seed(123)
+        prior = ref_get_prior_dist(definition["dict_gt"])
+        import contextlib, io
+        with contextlib.redirect_stdout(io.StringIO()):
+            data = ref_sample_response(definition, rows, sample_dist=prior)
+            data_val = ref_sample_response(definition, 8, sample_dist=prior)
+            vae = dp.setup_model(args, definition, data)
+            stamps = []
+            orig = torch.multinomial
+
+            def tap(*a, **k):
+                stamps.append(time.perf_counter())
+                return orig(*a, **k)
+
+            torch.multinomial = tap
+            try:
+                dp.train_model(args, vae, definition, data, data_val)
+            finally:
+                torch.multinomial = orig
+            stamps.append(time.perf_counter())
+    finally:
+        os.chdir(cwd)
+    per = [b - a for a, b in zip(stamps[:-1], stamps[1:])][warmup:]
+    sec = sum(per) / len(per)
+    return rows / sec, sec, threads, rows
+
+
+def workload_config(a, wl, n_gpus):
+    """`config` of the bench line: shared by both arms (the reference arm times a bounded sample of this workload)."""
+    rows = wl["rows"]
+    return {"workload": a.workload, "math": MATH_DOC[a.math], "case": wl["case"], "preset": wl["preset"], "rows_per_gpu": rows,
+            "global_batch": rows * n_gpus if a.scaling == "weak" else rows, "n_mc": wl["n_mc"], "parallelism": f"dp{n_gpus}",
+            "minibatch_order": "identity (loss is a row sum; the reference's CPU multinomial draw is hoisted)",
+            "data_generator": "on-device dpivae_sample_response (torch-stream Philox + surrogate MLP kernels)",
+            "l2": "per-step working set (inputs + activations workspace) ~0.3 GB > 126 MB L2, no flush",
+            "noise": "in-kernel Philox4x32-10, torch.cuda normal_ stream"}
+
+
 def run_reference(a, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    val, sec, threads, rows = cpu_oracle_throughput(wl, a.steps, a.warmup)
-    sample = f"{rows} rows x {wl['n_mc']} MC of the {wl['case']} {wl['preset']} step per timed step"
+    rows = a.ref_rows or wl.get("ref_rows", wl["cpu_rows"])
+    if reference_available():
+        val, sec, threads, rows = reference_throughput(wl, a.steps, a.warmup, rows)
+        kind = "reference"
+        what = "the reference's own setup_model + train_model (unmodified code, baseline/_ref), fp32 torch CPU"
+    else:
+        val, sec, threads, rows = cpu_oracle_throughput(wl, a.steps, a.warmup, rows=rows)
+        kind = "port"
+        what = "oracle port (baseline/_ref not installed), fp32 torch CPU"
+    sample = f"{rows} rows x {wl['n_mc']} MC of the {wl['case']} {wl['preset']} step per timed step; {what}"
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": {"workload": a.workload, "rows_per_step": rows, "n_mc": wl["n_mc"]},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(a, wl, a.gpus),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     emit(line)
 
@@ -255,16 +340,15 @@ def _timed_region(fn, steps, world, dev):
     return float(ms)
 
 
-def run_encode(a, wl):
+def run_encode(a, wl, ctx):
     """Config 5: encode-only inference, rows sharded as independent replicas (no collective)."""
     import contextlib, importlib, io
 
     import torch
-    import torch.distributed as dist
 
     import dpivae_b200 as dpv
 
-    world, rank, local_rank, dev = _dist_setup()
+    world, rank, local_rank, dev = ctx
     case_mod = importlib.import_module(f"dpivae_b200.cases.{wl['case']}")
     rows = wl["rows"]
     xs, cs, ys = synth(case_mod, 4096, 7, dev)
@@ -297,12 +381,9 @@ def run_encode(a, wl):
         launches = eng.launches - l0
         step_e2e(0)
         ms_e2e = _timed_region(step_e2e, a.steps, world, dev) / a.steps
+    line = None
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
+        peaks = load_peaks()
         hbm = peaks.get("hbm_gbs", 6650.0)
         achieved = wl["bytes_row"] * rows / (ms * 1e-3) / 1e9
         line = {"metric": "encode-only datapoints/s (transform_inputs -> encode, n=1)", "value": rows * world / (ms * 1e-3),
@@ -313,26 +394,24 @@ def run_encode(a, wl):
                 "e2e": {"value": rows * world / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": int(rows * vae.nd_x * 4), "d2h_bytes_per_step": int(rows * 10 * 4)},
                 "gpu_launches": launches,
-                "roofline": {"bound": "hbm", "kernel": "enc_fwd_kernel + dec_kernel(latent_only)", "achieved": achieved, "peak": hbm,
+                "roofline": {"bound": "hbm", "kernel": ENCODE_KERNEL_DOC.get(a.math, ENCODE_KERNEL_DOC["fp32"]), "achieved": achieved, "peak": hbm,
                              "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
                              "peak_source": "measured copy bandwidth (MEASURED_PEAKS.json)" if peaks else "fallback 6.65 TB/s"},
                 "clocks": clk.summary()}
-        emit(line)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    del eng, vae
+    torch.cuda.empty_cache()
+    return line
 
 
-def run_ensemble(a, wl):
+def run_ensemble(a, wl, ctx):
     """Config 4: independent small trainings, several members per GPU on separate CUDA streams, no communication."""
     import contextlib, importlib, io
 
     import torch
-    import torch.distributed as dist
 
     import dpivae_b200 as dpv
 
-    world, rank, local_rank, dev = _dist_setup()
+    world, rank, local_rank, dev = ctx
     case_mod = importlib.import_module(f"dpivae_b200.cases.{wl['case']}")
     M, n, nb = wl["members"], wl["n_mc"], wl["rows"]
     M = int(os.environ.get("DPIVAE_BENCH_MEMBERS", M))
@@ -380,6 +459,7 @@ def run_ensemble(a, wl):
     with ClockSampler(local_rank) as clk:
         ms = _timed_region(round_synced, a.steps, world, dev) / a.steps
     launches = sum(mb["eng"].launches for mb in members) - l0
+    line = None
     if rank == 0:
         line = {"metric": "ensemble train samples/s (independent small models, fwd+bwd+Adam)", "value": M * nb * inner * world / (ms * 1e-3),
                 "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True,
@@ -390,41 +470,72 @@ def run_ensemble(a, wl):
                            "parallelism": f"{M * world} independent members, no collective"},
                 "gpu_launches": launches, "clocks": clk.summary(),
                 "elbo": [float(mb["eng"].scalars[0]) for mb in members]}
-        emit(line)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    for mb in members:
+        mb["graph"].close()
+    members.clear()
+    torch.cuda.empty_cache()
+    return line
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="bridge_p", choices=list(WORKLOADS))
-    ap.add_argument("--rows", type=int, default=0, help="override rows per GPU")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--math", default="tc_fp16x3", choices=["fp32", "tc_fp16x3", "tc_fp16"],
-                    help="decoder GEMM arithmetic (include/dpivae_b200.h DPIVAE_MATH_*): tc_fp16x3 = tcgen05 with the fp16 hi/lo "
-                         "operand split (fp32-accurate, same 1e-5 parity bar as the FFMA kernel), fp32 = CUDA-core FFMA, "
-                         "tc_fp16 = tcgen05 with plain fp16 operands (reduced precision, reported separately)")
-    ap.add_argument("--no-other-modes", action="store_true", help="skip the short runs of the other math modes")
-    a = ap.parse_args()
-    _guard_stdout()
-    a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
-    wl = dict(WORKLOADS[a.workload])
-    if a.rows:
-        wl["rows"] = a.rows
-    if a.workload in ("bridge_encode", "ensemble") and a.impl == "reference":
-        raise SystemExit("--impl reference covers the training-step workloads (bridge_p, beam_s)")
-    if a.impl == "reference":
-        return run_reference(a, wl)
-    if a.workload == "bridge_encode":
-        return run_encode(a, wl)
-    if a.workload == "ensemble":
-        return run_ensemble(a, wl)
+def rank_check(a, wl, case_mod, vae_factory, world, rank, dev, n, w):
+    """N-rank correctness of the data-parallel step on hardware: two optimizer steps of one global
+    batch, sharded over the ranks with the NCCL allreduce, against the same two steps of the WHOLE global batch on rank 0
+    alone.  Returns a dict (rank 0) with the gradient / parameter differences; raises if the ranks disagree bitwise."""
+    import torch
+    import torch.distributed as dist
 
+    import dpivae_b200 as dpv
+    from dpivae_b200.parallel import DataParallelStep
+
+    rows = min(wl["rows"], 16384)
+    Bg = rows * world
+    shards = [synth(case_mod, rows, 5000 + r, dev) for r in ([rank] if rank else range(world))]
+    mine = shards[0] if rank else shards[rank]
+    vae, args = vae_factory()
+    dp = DataParallelStep(vae, dpv.param_groups(args))
+    dp.eng.set_math_mode(a.math)
+    torch.manual_seed(4242)
+    gen = torch.cuda.default_generators[dev.index]
+    off0 = gen.get_offset()
+    for k in range(2):
+        dp.step(mine[0], mine[1], mine[2], n, w, Bg, rank * rows, k + 1)
+    grads_n = dp.eng.gradbuf.clone()
+    params_n = dp.eng.params.clone()
+    # every rank must hold bitwise identical parameters (same allreduced gradient, same fused Adam)
+    lo, hi = params_n.clone(), params_n.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    if not torch.equal(lo, hi):
+        raise RuntimeError("data-parallel ranks hold different parameters after the allreduced Adam steps")
+    cks = torch.tensor([float(params_n.double().sum())], dtype=torch.float64, device=dev)
+    allck = [torch.zeros_like(cks) for _ in range(world)]
+    dist.all_gather(allck, cks)
+    res = None
+    if rank == 0:
+        vae1, args1 = vae_factory()
+        eng1 = vae1.engine()
+        eng1.set_groups(dpv.param_groups(args1))
+        eng1.set_math_mode(a.math)
+        gen.set_offset(off0)
+        X, C_, Y = (torch.cat([sh[i] for sh in shards]) for i in range(3))
+        for k in range(2):
+            eng1.loss(X, C_, Y, n, w, True, B_global=Bg, row_offset=0, adam_step=k + 1)
+        g1, p1 = eng1.gradbuf, eng1.params
+        gerr = float((grads_n.double() - g1.double()).norm() / g1.double().norm())
+        perr = float((params_n.double() - p1.double()).abs().max())
+        res = {"ranks": world, "global_rows": Bg, "steps": 2, "params_bitwise_equal_across_ranks": True,
+               "param_checksums": [float(t) for t in allck],
+               "grad_rel_l2_vs_1rank": gerr, "param_max_abs_diff_vs_1rank": perr,
+               "tolerance": {"grad_rel_l2": 1e-5, "param_max_abs": 1e-5}, "ok": bool(gerr < 1e-5 and perr < 1e-5)}
+        del eng1, vae1
+    del dp, vae
+    torch.cuda.empty_cache()
+    dist.barrier()
+    return res
+
+
+def run_train(a, wl, ctx, sub=False):
+    """Training-step workloads (bridge_p, beam_s).  Returns the bench line (rank 0) or None."""
     import importlib
 
     import torch
@@ -433,31 +544,28 @@ def main():
     import dpivae_b200 as dpv
     from dpivae_b200.parallel import DataParallelStep
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the host baseline")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout (rank 0 prints ONE JSON line)
-        dist.init_process_group("nccl", device_id=dev)
-    if a.gpus != world and rank == 0 and world > 1:
-        print(f"warning: --gpus {a.gpus} but WORLD_SIZE {world}", file=sys.stderr)
+    world, rank, local_rank, dev = ctx
     n_gpus = world
-
     case_mod = importlib.import_module(f"dpivae_b200.cases.{wl['case']}")
-    rows, n = wl["rows"], wl["n_mc"]
-    B_global = rows * n_gpus
+    n = wl["n_mc"]
+    if a.scaling == "strong" and not sub:
+        B_global = wl.get("strong_rows", 1048576)
+        rows = B_global // n_gpus
+    else:
+        rows = wl["rows"]
+        B_global = rows * n_gpus
+    wl = dict(wl, rows=rows)
     row_off = rank * rows
-    # scalers are fitted on a fixed global sample so every rank builds the identical model
-    xs, cs, ys = synth(case_mod, 4096, 7, dev)
-    args = make_args(case_mod, wl["preset"], use_seed=True, seed=123, n_train=4096, n_batch=4096)
     import contextlib, io
-    with contextlib.redirect_stdout(io.StringIO()):
-        vae = dpv.setup_model(args, case_mod.definition, (xs, cs, ys))
+
+    def vae_factory():
+        # scalers are fitted on a fixed global sample so every rank builds the identical model
+        xs, cs, ys = synth(case_mod, 4096, 7, dev)
+        args = make_args(case_mod, wl["preset"], use_seed=True, seed=123, n_train=4096, n_batch=4096)
+        with contextlib.redirect_stdout(io.StringIO()):
+            return dpv.setup_model(args, case_mod.definition, (xs, cs, ys)), args
+
+    vae, args = vae_factory()
     x, c, y = synth(case_mod, rows, 1000 + rank, dev)  # this rank's shard, resident in HBM
     dp = DataParallelStep(vae, dpv.param_groups(args))
     eng = dp.eng
@@ -476,30 +584,35 @@ def main():
 
     # End-to-end arm: every step's inputs come from pinned host memory and its 8 loss scalars go back to the host, where
     # the caller waits for them.  Two device input sets: while step i computes, a copy stream uploads the inputs of step
-    # i + 1 (the per-step H2D copy stays inside the timed region, it is just not serialised with the kernels).
+    # i + 1 (the per-step H2D copy stays inside the timed region, it is just not serialised with the kernels).  The host
+    # holds TWO different minibatches which alternate, and every step gathers its rows through a fresh int64 index
+    # vector (the reference's `x_train[sample_idx]`, dpivae.py:403-404) that is uploaded with the inputs.
     xh, ch, yh = (t.cpu().pin_memory() for t in (x, c, y))
+    host_sets = [(xh, ch, yh), tuple(t.flip(0).contiguous().pin_memory() for t in (xh, ch, yh))]
+    gcpu = torch.Generator().manual_seed(17 + rank)
+    idx_host = [torch.randperm(rows, generator=gcpu).pin_memory() for _ in range(2)]
     scal_host = torch.empty(8, dtype=torch.float32).pin_memory()
-    dev_in = [tuple(torch.empty_like(t) for t in (x, c, y)) for _ in range(2)]
+    dev_in = [tuple(torch.empty_like(t) for t in (x, c, y)) + (torch.empty(rows, dtype=torch.int64, device=dev),) for _ in range(2)]
     copy_stream = torch.cuda.Stream(dev)
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     e2e_state = {"k": 0, "primed": False}
 
-    def upload(slot):
+    def upload(slot, k):
         with torch.cuda.stream(copy_stream):
-            for dst, src in zip(dev_in[slot], (xh, ch, yh)):
+            for dst, src in zip(dev_in[slot], host_sets[k & 1] + (idx_host[k & 1],)):
                 dst.copy_(src, non_blocking=True)
             ready[slot].record(copy_stream)
 
     def step_e2e(i):
         k = e2e_state["k"]
         if not e2e_state["primed"]:
-            upload(k & 1)
+            upload(k & 1, k)
             e2e_state["primed"] = True
         main = torch.cuda.current_stream()
         main.wait_event(ready[k & 1])
-        xd, cd, yd = dev_in[k & 1]
-        s = dp.step(xd, cd, yd, n, w, B_global, row_off, i)
-        upload((k + 1) & 1)        # step k - 1, the last reader of that slot, was synchronised below
+        xd, cd, yd, idxd = dev_in[k & 1]
+        s = dp.step(xd, cd, yd, n, w, B_global, row_off, i, idx=idxd)
+        upload((k + 1) & 1, k + 1)        # step k - 1, the last reader of that slot, was synchronised below
         scal_host.copy_(s, non_blocking=True)
         main.synchronize()         # the user reads the loss every step
         e2e_state["k"] = k + 1
@@ -522,6 +635,7 @@ def main():
         step_resident(step_no)
         step_no += 1
     l0 = eng.launches
+    sustained = None
     with ClockSampler(local_rank) as clk:
         ms_total = timed(step_resident, a.steps, step_no)
         launches = eng.launches - l0
@@ -536,6 +650,13 @@ def main():
         ms_e2e = timed(step_e2e, a.steps, step_no) / a.steps
         step_no += a.steps
         e2e_val = B_global / (ms_e2e * 1e-3)
+
+        if not sub and a.sustain_s > 0:
+            # the same resident step back to back for >= sustain_s seconds: clocks sampled under sustained load
+            k_sus = max(a.steps, int(a.sustain_s * 1e3 / ms_step) + 1)
+            ms_sus = timed(step_resident, k_sus, step_no) / k_sus
+            step_no += k_sus
+            sustained = {"steps": k_sus, "seconds": ms_sus * k_sus * 1e-3, "ms_per_step": ms_sus, "value": B_global / (ms_sus * 1e-3)}
 
     # per-kernel durations of the dominant kernel, CUDA events on the launching stream
     eng.set_timing(True)
@@ -552,7 +673,7 @@ def main():
 
     # the other arithmetic modes of the same step, short runs (reported beside the headline, never as it)
     modes = {}
-    if not a.no_other_modes:
+    if not a.no_other_modes and not sub:
         for m in ("fp32", "tc_fp16x3", "tc_fp16"):
             if m == a.math:
                 continue
@@ -566,60 +687,152 @@ def main():
             modes[m] = {"value": B_global / (ms_m * 1e-3), "ms_per_step": ms_m, "tensor_cores": eng.used_tensor_cores()}
         eng.set_math_mode(a.math)
 
-    if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        tensor_peak = peaks.get("bf16_tflops_sustained", 1400.0)
-        peak_src = "measured bf16 sustained (MEASURED_PEAKS.json)" if peaks else "fallback 1.4 PFLOP/s sustained"
-        ffma_peak = eng.ffma_peak_tflops()
-        achieved = wl["flop_dec"] * rows / (dec_ms * 1e-3) / 1e12
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "dec_traffic.json"))).get(f"{a.workload}:{a.math}", {}).get("total")
-        except Exception:
-            pass
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": a.workload, "math": MATH_DOC[a.math], "case": wl["case"], "preset": wl["preset"], "rows_per_gpu": rows,
-                       "global_batch": B_global, "n_mc": n, "parallelism": f"dp{n_gpus}",
-                       "minibatch_order": "identity (loss is a row sum; the reference's CPU multinomial draw is hoisted)",
-                       "data_generator": "on-device dpivae_sample_response (torch-stream Philox + surrogate MLP kernels)",
-                       "l2": "per-step working set (inputs + activations workspace) ~0.3 GB > 126 MB L2, no flush",
-                       "noise": "in-kernel Philox4x32-10, torch.cuda normal_ stream"},
-            "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": int(rows * (vae.nd_x + vae.nd_c + vae.nd_y) * 4), "d2h_bytes_per_step": 32},
-            "gpu_launches": launches,
-            "roofline": {"bound": "tensor",
-                         "kernel": ("dec_tc_kernel (fused decoders fwd+bwd, tcgen05 kind::f16, TMEM accumulators)" if used_tc
-                                    else "dec_kernel (fused decoders fwd+bwd, fp32 FFMA)"),
-                         "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
-                         "peak_source": peak_src, "traffic": traffic,
-                         "algorithmic_flop_per_launch": wl["flop_dec"] * rows, "launch_ms": dec_ms,
-                         "ffma_peak_tflops_measured": ffma_peak, "frac_of_ffma_peak": achieved / ffma_peak if ffma_peak else None,
-                         "hbm_gbs_achieved": wl["bytes_row"] * rows / (ms_step * 1e-3) / 1e9,
-                         "kernel_ms": kshare},
-            "clocks": clk.summary(),
-            "elbo": loss_now, "math": a.math, "tensor_cores": used_tc, "other_modes": modes,
-        }
-        if not a.no_cpu_baseline and n_gpus == 1:
-            val, sec, threads, crow = cpu_oracle_throughput(wl, 3, 1)
-            line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": f"{crow} rows x {n} MC, 3 steps after 1 warm-up (oracle port, fp32 torch CPU)",
-                                    "ms_per_step": sec * 1e3}
-            # baseline leg, second device: the same port's torch tensor algebra as eager CUDA ops on this GPU -- the "existing Blackwell path"
-            # of SURVEY.md §8(d) (the reference itself is not installable here; this is the oracle port, as in the CPU leg)
+    check = None
+    if world > 1 and not sub and not a.no_rank_check:
+        check = rank_check(a, wl, case_mod, vae_factory, world, rank, dev, n, w)
+
+    if rank != 0:
+        return None
+    peaks = load_peaks()
+    tensor_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "measured bf16 sustained (MEASURED_PEAKS.json)" if peaks else "fallback 1.4 PFLOP/s sustained"
+    ffma_peak = eng.ffma_peak_tflops()
+    achieved = wl["flop_dec"] * rows / (dec_ms * 1e-3) / 1e12
+    traffic, traffic_src = None, None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "dec_traffic.json")))
+        ent = tr.get(f"{a.workload}:{a.math}", {})
+        traffic = ent.get("total")
+        traffic_src = f"profiles/dec_traffic.json ({ent.get('source', 'ncu --set full capture')}, commit {ent.get('commit', tr.get('commit', '?'))})"
+        if traffic is not None and ent.get("rows") and ent["rows"] != rows:
+            traffic = traffic * rows / ent["rows"]
+    except Exception:
+        pass
+    cfg = workload_config(a, wl, n_gpus)
+    cfg["global_batch"] = B_global
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": a.scaling if not sub else "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": cfg,
+        "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": int(rows * (vae.nd_x + vae.nd_c + vae.nd_y) * 4 + rows * 8), "d2h_bytes_per_step": 32,
+                "gather": "per-step int64 row indices uploaded with the inputs (fused gather, dpivae.py:403-404); two host minibatches alternate"},
+        "gpu_launches": launches,
+        "roofline": {"bound": "tensor",
+                     "kernel": ("dec_tc_kernel (fused decoders fwd+bwd, tcgen05 kind::f16, TMEM accumulators)" if used_tc
+                                else "dec_kernel (fused decoders fwd+bwd, fp32 FFMA)"),
+                     "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
+                     "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
+                     "algorithmic_flop_per_launch": wl["flop_dec"] * rows, "launch_ms": dec_ms,
+                     "ffma_peak_tflops_measured": ffma_peak, "frac_of_ffma_peak": achieved / ffma_peak if ffma_peak else None,
+                     "hbm_gbs_achieved": wl["bytes_row"] * rows / (ms_step * 1e-3) / 1e9,
+                     "kernel_ms": kshare},
+        "clocks": clk.summary(),
+        "elbo": loss_now, "math": a.math, "tensor_cores": used_tc,
+    }
+    if modes:
+        line["other_modes"] = modes
+    if sustained:
+        line["sustained"] = sustained
+    if check is not None:
+        line["rank_check"] = check
+    del dp, eng, vae
+    torch.cuda.empty_cache()
+    return line
+
+
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="bridge_p", choices=list(WORKLOADS))
+    ap.add_argument("--rows", type=int, default=0, help="override rows per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--math", default="tc_fp16x3", choices=["fp32", "tc_fp16x3", "tc_fp16"],
+                    help="decoder GEMM arithmetic (include/dpivae_b200.h DPIVAE_MATH_*): tc_fp16x3 = tcgen05 with the fp16 hi/lo "
+                         "operand split (fp32-accurate, same 1e-5 parity bar as the FFMA kernel), fp32 = CUDA-core FFMA, "
+                         "tc_fp16 = tcgen05 with plain fp16 operands (reduced precision, reported separately)")
+    ap.add_argument("--no-other-modes", action="store_true", help="skip the short runs of the other math modes")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --rows (131,072) rows per GPU; strong: the global batch is fixed at 1,048,576 rows (config 3) and "
+                         "sharded over the ranks (N = 1 runs all of it)")
+    ap.add_argument("--ref-rows", type=int, default=0, help="rows per timed step of the reference arm (default 65,536)")
+    ap.add_argument("--no-workloads", action="store_true", help="skip the short beam_s / bridge_encode / ensemble sub-runs of the default line")
+    ap.add_argument("--no-rank-check", action="store_true", help="skip the N-rank vs 1-rank correctness check (N > 1)")
+    ap.add_argument("--sustain-s", type=float, default=2.0, help="extra back-to-back run of the resident step (seconds) for the sustained-clock record")
+    a = ap.parse_args()
+    _guard_stdout()
+    a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
+    wl = dict(WORKLOADS[a.workload])
+    if a.rows:
+        wl["rows"] = a.rows
+    if a.workload in ("bridge_encode", "ensemble") and a.impl == "reference":
+        raise SystemExit("--impl reference covers the training-step workloads (bridge_p, beam_s)")
+    if a.impl == "reference":
+        return run_reference(a, wl)
+
+    import torch
+    import torch.distributed as dist
+
+    ctx = _dist_setup()
+    world, rank, local_rank, dev = ctx
+    if a.gpus != world and rank == 0 and world > 1:
+        print(f"warning: --gpus {a.gpus} but WORLD_SIZE {world}", file=sys.stderr)
+    if a.workload == "bridge_encode":
+        line = run_encode(a, wl, ctx)
+    elif a.workload == "ensemble":
+        line = run_ensemble(a, wl, ctx)
+    else:
+        line = run_train(a, wl, ctx)
+        if a.workload == "bridge_p" and not a.no_workloads and a.scaling == "weak":
+            # BASELINE.json configs 2, 5 and 4 beside the headline (short runs, same process, same GPUs)
+            subs = {}
+            sa = argparse.Namespace(**vars(a))
+            sa.steps, sa.warmup = max(5, min(a.steps, 10)), 3
+            for name, fn in (("beam_s", run_train), ("bridge_encode", run_encode), ("ensemble", run_ensemble)):
+                sa.workload = name
+                try:
+                    sl = fn(sa, dict(WORKLOADS[name]), ctx, True) if fn is run_train else fn(sa, dict(WORKLOADS[name]), ctx)
+                except Exception as exc:   # a sub-run never takes the headline down
+                    sl = {"error": str(exc)[:300]}
+                if rank == 0 and sl is not None:
+                    subs[name] = {k: sl[k] for k in ("metric", "value", "unit", "ms_per_step", "config", "roofline", "e2e", "gpu_launches", "error")
+                                  if k in sl}
+            if rank == 0:
+                line["workloads"] = subs
+        if rank == 0 and not a.no_cpu_baseline and world == 1:
+            n = wl["n_mc"]
+            if reference_available():
+                crow = 32768
+                val, sec, threads, crow = reference_throughput(wl, 3, 1, crow)
+                line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "reference",
+                                        "sample": f"{crow} rows x {n} MC, 3 iterations after 1 warm-up of the reference's own train_model "
+                                                  "(unmodified code from baseline/_ref, fp32 torch CPU)", "ms_per_step": sec * 1e3}
+            else:
+                val, sec, threads, crow = cpu_oracle_throughput(wl, 3, 1)
+                line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                                        "sample": f"{crow} rows x {n} MC, 3 steps after 1 warm-up (oracle port, fp32 torch CPU)",
+                                        "ms_per_step": sec * 1e3}
+            # baseline leg, second device: the port's torch tensor algebra as eager CUDA ops on this GPU -- the "existing
+            # Blackwell path" of SURVEY.md §8(d)
             try:
                 torch.cuda.empty_cache()
-                ev, esec, _, erow = cpu_oracle_throughput(wl, 3, 2, device=f"cuda:{local_rank}", rows=min(rows, 65536))
+                ev, esec, _, erow = cpu_oracle_throughput(wl, 3, 2, device=f"cuda:{local_rank}", rows=min(wl["rows"], 65536))
                 line["cpu_baseline"]["torch_eager_same_gpu"] = {"value": ev, "unit": UNIT, "kind": "port (torch eager ops, fp32, same GPU)",
-                                                    "sample": f"{erow} rows x {n} MC, 3 steps after 2 warm-ups", "ms_per_step": esec * 1e3}
+                                                                "sample": f"{erow} rows x {n} MC, 3 steps after 2 warm-ups", "ms_per_step": esec * 1e3}
             except Exception as exc:   # never let the informational leg break the bench line
                 line["cpu_baseline"]["torch_eager_same_gpu"] = {"unavailable": str(exc)[:200]}
+    if rank == 0 and line is not None:
         emit(line)
     if world > 1:
         dist.barrier()

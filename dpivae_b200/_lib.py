@@ -71,7 +71,7 @@ class DataGenDesc(C.Structure):
 
 
 EXPORTS = [
-    "dpivae_create", "dpivae_destroy", "dpivae_last_error", "dpivae_abi_version", "dpivae_set_physics_mlp",
+    "dpivae_create", "dpivae_destroy", "dpivae_last_error", "dpivae_abi_version", "dpivae_sizeof_model_desc", "dpivae_set_physics_mlp",
     "dpivae_bind", "dpivae_set_groups", "dpivae_workspace_bytes", "dpivae_loss", "dpivae_adam_step",
     "dpivae_train_step", "dpivae_encode", "dpivae_philox_plan", "dpivae_last_launch_count",
     "dpivae_set_timing", "dpivae_last_kernel_ms", "dpivae_ffma_peak_tflops", "dpivae_set_phase_buffer",
@@ -82,22 +82,37 @@ EXPORTS = [
     "dpivae_step_graph_create", "dpivae_step_graph_reset", "dpivae_step_graph_launch", "dpivae_step_graph_destroy",
 ]
 MATH_FP32, MATH_TC_FP16X3, MATH_TC_FP16 = 0, 1, 2
+ABI_VERSION = 2   # include/dpivae_b200.h DPIVAE_ABI_VERSION
 
 _lib = None
 
 
 def load():
-    """Load the shared library (building it first when nvcc and the sources are newer)."""
+    """Load the shared library, (re)building it first when it is missing or older than its sources (build.py's
+    staleness check; a box without nvcc uses the shipped binary as it is).  The ABI version the binding was written
+    against and the size of the model descriptor are checked against the binary: a stale library fails here."""
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        from . import build as _build
+    from . import build as _build
 
-        _build.build_library()
+    if os.path.exists(os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")) or not os.path.exists(LIB_PATH):
+        try:
+            _build.build_library()   # no-op unless a source is newer than the binary
+        except Exception:
+            if not os.path.exists(LIB_PATH):
+                raise
     if not os.path.exists(LIB_PATH):
         raise ImportError(f"{LIB_PATH} is missing: run `python -m dpivae_b200.build` (no fallback path exists)")
     lib = C.CDLL(LIB_PATH)
+    lib.dpivae_abi_version.restype = C.c_int
+    if lib.dpivae_abi_version() != ABI_VERSION:
+        raise ImportError(f"{LIB_PATH}: ABI version {lib.dpivae_abi_version()} != binding version {ABI_VERSION} "
+                          "(stale binary: run `python -m dpivae_b200.build --force`)")
+    lib.dpivae_sizeof_model_desc.restype = C.c_size_t
+    if lib.dpivae_sizeof_model_desc() != C.sizeof(ModelDesc):
+        raise ImportError(f"{LIB_PATH}: dpivae_model_desc_t is {lib.dpivae_sizeof_model_desc()} bytes in the binary, "
+                          f"{C.sizeof(ModelDesc)} in the binding")
     vp, i32, i64, u64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_float
     lib.dpivae_create.argtypes = [C.POINTER(ModelDesc), C.POINTER(vp)]
     lib.dpivae_destroy.argtypes = [vp]

@@ -82,4 +82,4 @@ def load_checkpoint_state(vae, state, restore_rng=True):
 
 
 def load_checkpoint(path, vae, restore_rng=True):
-    return load_checkpoint_state(vae, torch.load(path, map_location="cpu", weights_only=False), restore_rng)
+    return load_checkpoint_state(vae, torch.load(path, map_location="cpu", weights_only=True), restore_rng)

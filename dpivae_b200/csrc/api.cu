@@ -391,7 +391,8 @@ static int build_plan(dpivae_model* h) {
 
 extern "C" {
 
-int dpivae_abi_version(void) { return 1; }
+int dpivae_abi_version(void) { return DPIVAE_ABI_VERSION; }
+size_t dpivae_sizeof_model_desc(void) { return sizeof(dpivae_model_desc_t); }
 const char* dpivae_last_error(void) { return g_err.c_str(); }
 
 int dpivae_create(const dpivae_model_desc_t* desc, dpivae_handle_t* out) {

@@ -49,17 +49,16 @@ __global__ void __launch_bounds__(MT) metric_sums_kernel(const float* __restrict
   }
 }
 
-// sklearn r2_score (uniform average over outputs), mean_squared_error, mean_absolute_error
-__global__ void metric_final_kernel(const double* __restrict__ acc, long long N, int d, float* __restrict__ out3) {
-  double r2 = 0.0, mse = 0.0, mae = 0.0;
+// sklearn r2_score / mean_squared_error / mean_absolute_error with multioutput="raw_values" (utils/metrics.py:29-31):
+// out = [R2_0 .. R2_{d-1} | MSE_0 .. | MAE_0 ..], one value per output column
+__global__ void metric_final_kernel(const double* __restrict__ acc, long long N, int d, float* __restrict__ out3d) {
   for (int j = 0; j < d; ++j) {
     const double sy = acc[4 * j], syy = acc[4 * j + 1], sr = acc[4 * j + 2], sa = acc[4 * j + 3];
     const double sst = syy - sy * sy / (double)N;
-    r2 += sst != 0.0 ? 1.0 - sr / sst : (sr == 0.0 ? 1.0 : 0.0);
-    mse += sr / (double)N;
-    mae += sa / (double)N;
+    out3d[j] = (float)(sst != 0.0 ? 1.0 - sr / sst : (sr == 0.0 ? 1.0 : 0.0));
+    out3d[d + j] = (float)(sr / (double)N);
+    out3d[2 * d + j] = (float)(sa / (double)N);
   }
-  out3[0] = (float)(r2 / d); out3[1] = (float)(mse / d); out3[2] = (float)(mae / d);
 }
 
 // normal equations of y ~ [1, x_0 .. x_{k-1}]: acc = upper triangle of A^T A ((k+1)(k+2)/2 values) followed by A^T y (k+1)

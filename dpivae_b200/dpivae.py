@@ -135,6 +135,9 @@ def train_model(args, vae, definition, data_train, data_val, path_metrics=None, 
 
         it_range = trange(start_iter, args.n_iter)
     w_alpha = (float(args.alpha_x), float(args.alpha_c), float(args.alpha_y))
+    # optional injected reparameterisation noise (parity runs against recorded draws of the reference): a callable
+    # ("train" | "val", iteration) -> eps in `DPIVAE.inject_noise` form; None = the in-kernel Philox stream
+    eps_provider = getattr(args, "eps_provider", None)
 
     def log_iteration(it, row9, lambda_x_i, beta_x_i, beta_c_i, beta_y_i, sigma_x=None):
         for k, nme in enumerate(_NAMES8):
@@ -146,7 +149,7 @@ def train_model(args, vae, definition, data_train, data_val, path_metrics=None, 
         logger.log_scalar("sigma_x", row9[8].exp() if sigma_x is None else sigma_x, it)
 
     def validate(it, w):
-        _, sv = eng.loss(x_val, c_val, y_val, args.n_mc_val, w, False)
+        _, sv = eng.loss(x_val, c_val, y_val, args.n_mc_val, w, False, eps=eps_provider("val", it) if eps_provider else None)
         for k, nme in enumerate(_NAMES8):
             logger.log_scalar(nme + "_val", sv[k], it)
         return early_stopping.early_stop(float(sv[0]))
@@ -155,7 +158,8 @@ def train_model(args, vae, definition, data_train, data_val, path_metrics=None, 
     # reference default) the iterations between two validation passes replay ONE captured step graph -- no per-step
     # host work beyond the reference's own CPU minibatch draw, one log read-back per chunk instead of 13 syncs per step.
     # (capturing the step graphs costs ~0.1 s once: by default only runs of >= 2000 iterations use them)
-    device_loop = bool(getattr(args, "device_loop", args.n_iter >= 2000)) and beta_x_annealer.type in (None, "none", "None")
+    device_loop = bool(getattr(args, "device_loop", args.n_iter >= 2000)) and beta_x_annealer.type in (None, "none", "None") \
+        and eps_provider is None
     if device_loop:
         beta_x_i = args.beta_x0 * beta_x_annealer.forward(0)
         w = (float(beta_x_i),) + w_alpha
@@ -198,7 +202,7 @@ def train_model(args, vae, definition, data_train, data_val, path_metrics=None, 
         eng.step_count += 1
         w = (float(beta_x_i),) + w_alpha
         _, scal = eng.loss(x_train, c_train, y_train, args.n_mc_train, w, True, idx=sample_idx,
-                           adam_step=eng.step_count, max_grad_norm=max_norm)
+                           adam_step=eng.step_count, max_grad_norm=max_norm, eps=eps_provider("train", it) if eps_provider else None)
         row9 = torch.cat([scal, eng.params[eng.ranges["log_sigma_x"][0]].reshape(1)])
         log_iteration(it, row9, lambda_x_i, beta_x_i, beta_c_i, beta_y_i)
         if it % args.val_freq == 0 and validate(it, w):
@@ -211,8 +215,10 @@ def regression_metrics(y_true, y_pred):
     from sklearn import metrics
 
     y_true = y_true.detach().cpu().numpy() if torch.is_tensor(y_true) else np.asarray(y_true)
-    return {"r2": metrics.r2_score(y_true, y_pred), "mse": metrics.mean_squared_error(y_true, y_pred),
-            "mae": metrics.mean_absolute_error(y_true, y_pred)}
+    y_pred = y_pred.detach().cpu().numpy() if torch.is_tensor(y_pred) else np.asarray(y_pred)
+    return {"R2": metrics.r2_score(y_true, y_pred, multioutput="raw_values"),
+            "MSE": metrics.mean_squared_error(y_true, y_pred, multioutput="raw_values"),
+            "MAE": metrics.mean_absolute_error(y_true, y_pred, multioutput="raw_values")}
 
 
 def evaluate_model(args, definition, model, data_test, cond=False):

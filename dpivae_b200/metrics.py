@@ -33,18 +33,19 @@ def mc_mean(v):
 
 
 def regression_metrics_device(y_true, y_pred):
-    """utils/metrics.py:11-32 -> {"r2", "mse", "mae"} (sklearn semantics: uniform average over outputs)."""
+    """utils/metrics.py:11-32 -> {"R2", "MSE", "MAE"}, each a numpy array with one value per output column (sklearn
+    `multioutput="raw_values"`, the reference's keys and shapes)."""
     lib = _lib.load()
     dev = y_pred.device
     y_pred = _prep(y_pred, dev)
     y_true = _prep(torch.as_tensor(y_true), dev).reshape(y_pred.shape)
     N, d = int(y_pred.shape[0]), int(y_pred.shape[1])
     scratch = torch.empty(4 * d, dtype=torch.float64, device=dev)
-    out = torch.empty(3, dtype=torch.float32, device=dev)
+    out = torch.empty(3 * d, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         _lib.check(lib.dpivae_regression_metrics(_ptr(y_true), _ptr(y_pred), N, d, _ptr(scratch), _ptr(out), _stream(dev)))
-    r2, mse, mae = out.cpu().tolist()
-    return {"r2": r2, "mse": mse, "mae": mae}
+    vals = out.cpu().numpy().astype("float64").reshape(3, d)
+    return {"R2": vals[0], "MSE": vals[1], "MAE": vals[2]}
 
 
 def linreg_r2(z_train, t_train, z_test, t_test):

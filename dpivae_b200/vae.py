@@ -226,9 +226,10 @@ class _Engine:
         if eps is not None:
             r.mode = 0
             eps = list(eps) if isinstance(eps, (tuple, list)) else [eps]
-            self._keep = [e.to(self.dev, torch.float32).contiguous() for e in eps]
+            self._keep = [None if e is None else e.to(self.dev, torch.float32).contiguous() for e in eps]
             for k, e in enumerate(self._keep):
-                r.eps[k] = e.data_ptr()
+                if e is not None:
+                    r.eps[k] = e.data_ptr()
             return r
         r.mode = 1
         gen = torch.cuda.default_generators[self.dev.index if self.dev.index is not None else torch.cuda.current_device()]

@@ -115,7 +115,9 @@ typedef struct {
 int dpivae_create(const dpivae_model_desc_t* desc, dpivae_handle_t* out);
 int dpivae_destroy(dpivae_handle_t h);
 const char* dpivae_last_error(void);
+#define DPIVAE_ABI_VERSION 2   /* 2: dpivae_regression_metrics returns per-output raw values; dpivae_sizeof_model_desc */
 int dpivae_abi_version(void);
+size_t dpivae_sizeof_model_desc(void);   /* sizeof(dpivae_model_desc_t) in the binary: bindings check their struct layout */
 
 /* Frozen physics surrogate (cases/bridge/__init__.py:163-174, models/nn.py:67-80): host arrays in
  * nn.Linear layout, concatenated layer by layer; input scaler mean/std of length phys_dims[0]. */
@@ -203,13 +205,14 @@ int dpivae_gaussian_sample(const float* loc, const float* scale_tril, const floa
 /* Post-processing of sample / encode outputs on the device (the callers right behind the hot path).
  * dpivae_mc_mean: out (B,d) = mean over the leading MC axis of v (n,B,d)  (dpivae.py:548 `y_sample.mean(0)`,
  *   dpivae.py:640-661 `z.mean(0)`).
- * dpivae_regression_metrics: utils/metrics.py:11-32 = sklearn r2_score (uniform average over the d outputs),
- *   mean_squared_error, mean_absolute_error -> out3 = {r2, mse, mae}; scratch = 4*d doubles (device).
+ * dpivae_regression_metrics: utils/metrics.py:11-32 = sklearn r2_score, mean_squared_error, mean_absolute_error with
+ *   multioutput="raw_values" (one value per output column) -> out3d = [R2 (d) | MSE (d) | MAE (d)], 3*d floats;
+ *   scratch = 4*d doubles (device).
  * dpivae_linreg_r2: dpivae.py:672-690 with regressor == "linear": ordinary least squares (with intercept) of one
  *   target column on k <= 8 latent columns of the training set, R2 of the fit on the test set.  y_* point at the
  *   target column, ldy_* = its row stride in floats.  scratch = 80 doubles (device). */
 int dpivae_mc_mean(const float* v, int32_t n_mc, int64_t B, int32_t d, float* out, void* stream);
-int dpivae_regression_metrics(const float* y_true, const float* y_pred, int64_t N, int32_t d, double* scratch, float* out3,
+int dpivae_regression_metrics(const float* y_true, const float* y_pred, int64_t N, int32_t d, double* scratch, float* out3d,
                               void* stream);
 int dpivae_linreg_r2(const float* X_train, const float* y_train, int64_t ldy_train, int64_t N_train, const float* X_test,
                      const float* y_test, int64_t ldy_test, int64_t N_test, int32_t k, double* scratch, float* r2_out,

@@ -25,6 +25,11 @@ Reference lines each function follows (paths relative to the reference root):
   loss                   models/vae.py:160-231
   normalise              dpivae.py:419-426
   adam_step              dpivae.py:335-373,436 (+ torch.optim.Adam, non-amsgrad, L2 weight decay)
+  clip_grad_norm         dpivae.py:432-433 (+ torch.nn.utils.clip_grad_norm_)
+
+A second fixture set (`tests/golden/make_golden_ext.py` -> `*_ext.npz`, `tests/test_oracle_golden_ext.py`) pins the
+branches the reference's default run never takes: `cond=True`, `lambda_x`, weight decay, gradient clipping, annealed
+loss weights, the validation pass, clamp saturation and the Uniform-prior `-inf` edge.
 """
 import math
 
@@ -238,7 +243,7 @@ def forward(sd, spec, x, c, eps, cond=False, eps_cond=None):
 
 def loss(sd, spec, x, c, y, eps, beta_x=1.0, alpha_x=1.0, alpha_c=1.0, alpha_y=1.0):
     """models/vae.py:177-231 (DPIVAE.loss) -> the reference's 8-tuple, plus the forward 10-tuple."""
-    fw = forward(sd, spec, x, c, eps)
+    fw = forward(sd, spec, x, c, eps)   # loss always calls forward with cond=False (models/vae.py:194)
     xh_p, xh_d, ch, lsc, yh, lsy, zx, zc, zy, dens_z = fw
     xh = xh_p + xh_d
     c_t = standardise(c, spec["mean_c"], spec["std_c"])
@@ -298,15 +303,34 @@ def adam_step(params, grads, m, v, step, lr, wd, beta1=0.9, beta2=0.999, eps=1e-
         params[k].addcdiv_(m[k], denom, value=-(lr[k] / bc1))
 
 
-def train_steps(sd, spec, batches, eps_list, lr, wd, n_batch=None, **kw):
-    """K Adam steps from `sd` over fixed minibatches / injected noise (dpivae.py:390-436)."""
+def clip_grad_norm(grads, max_norm, norm_eps=1e-6):
+    """torch.nn.utils.clip_grad_norm_ (dpivae.py:432-433): one global L2 norm over every gradient tensor,
+    coefficient max_norm / (norm + 1e-6) clamped to 1.  Returns (clipped grads, total norm)."""
+    total = torch.sqrt(sum((g.double() ** 2).sum() for g in grads.values())).to(next(iter(grads.values())).dtype)
+    coef = torch.clamp(max_norm / (total + norm_eps), max=1.0)
+    return {k: g * coef for k, g in grads.items()}, float(total)
+
+
+def train_steps(sd, spec, batches, eps_list, lr, wd, n_batch=None, max_grad_norm=None, weights=None, on_step=None, **kw):
+    """K Adam steps from `sd` over fixed minibatches / injected noise (dpivae.py:390-436).
+
+    weights: optional per-step list of dict(beta_x=, alpha_x=, alpha_c=, alpha_y=) (annealing, dpivae.py:397-400);
+    max_grad_norm: clip_grad_norm_ before the step (dpivae.py:432-433); on_step(it, sd) runs after the optimizer step
+    (the validation pass of dpivae.py:454-501 reads the updated parameters)."""
     names = spec["trainable"]
     sd = {k: v.detach().clone() for k, v in sd.items()}
     m = {k: torch.zeros_like(sd[k]) for k in names}
     v = {k: torch.zeros_like(sd[k]) for k in names}
     hist = []
     for it, ((x, c, y), eps) in enumerate(zip(batches, eps_list)):
-        scal, _, _, grads = loss_and_grads(sd, spec, x, c, y, eps, n_batch=n_batch, **kw)
+        kw_it = dict(kw)
+        if weights is not None:
+            kw_it.update(weights[it])
+        scal, _, _, grads = loss_and_grads(sd, spec, x, c, y, eps, n_batch=n_batch, **kw_it)
+        if max_grad_norm is not None:
+            grads, _ = clip_grad_norm(grads, max_grad_norm)
         adam_step({k: sd[k] for k in names}, grads, m, v, it + 1, lr, wd)
         hist.append([float(s) for s in scal])
+        if on_step is not None:
+            on_step(it, sd)
     return sd, hist

@@ -25,8 +25,14 @@ def physics_spec(case):
     return {"kind": "beam", "t": torch.linspace(0.0, 1.0, 32).numpy()}
 
 
-def load(case, mtype):
-    g = np.load(os.path.join(GOLDEN, f"{case}_{mtype}.npz"))
+EXT_CONFIGS = [("bridge", "P"), ("bridge", "S"), ("damped_oscillator", "P"), ("simple_beam", "S")]
+TRAIN_LOG = ["ELBO", "KLx", "KLc", "KLy", "Rx", "Rc", "Ry", "reg", "lambda_x", "beta_x", "beta_c", "beta_y", "sigma_x"]
+VAL_LOG = ["ELBO_val", "KLx_val", "KLc_val", "KLy_val", "Rx_val", "Rc_val", "Ry_val", "reg_val"]
+
+
+def load(case, mtype, ext=False):
+    """ext=True: the second fixture set (make_golden_ext.py): n_mc = 8, cond / lambda_x / saturation / edge / flagged trajectory."""
+    g = np.load(os.path.join(GOLDEN, f"{case}_{mtype}{'_ext' if ext else ''}.npz"))
     nz_x, nz_c, nz_y, nd_x, nd_c, nd_y = [int(v) for v in g["spec.dims"]]
     prior = [("uniform" if k == 0.0 else "normal", float(a), float(b)) for k, a, b in g["spec.prior_x"]]
     spec = {
@@ -40,6 +46,20 @@ def load(case, mtype):
         spec[k] = g[f"spec.{k}"]
     sd = {k: torch.from_numpy(g[f"init.{k}"].copy()) for k in spec["trainable"]}
     return g, spec, sd
+
+
+def state_of(g, spec, prefix):
+    """Alternative weights of a fixture section (e.g. "sat.init", "edge.init")."""
+    return {k: torch.from_numpy(g[f"{prefix}.{k}"].copy()) for k in spec["trainable"]}
+
+
+def traj_flags(g):
+    """The non-default flags the ext trajectory was run with -> dict of python values."""
+    out = {}
+    for item in g["traj.flags"]:
+        k, v = str(item).split("=", 1)
+        out[k] = True if v == "True" else (False if v == "False" else (v if not v.replace(".", "").replace("e-", "").replace("-", "").isdigit() else (float(v) if ("." in v or "e" in v) else int(v))))
+    return out
 
 
 def eps_of(g, spec, prefix="eps", start=0):

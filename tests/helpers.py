@@ -20,16 +20,16 @@ def make_args(case_mod, preset, **over):
     return args
 
 
-def build_from_golden(case, mtype, device="cuda"):
+def build_from_golden(case, mtype, device="cuda", ext=False, **over):
     """setup_model on the golden minibatch (so the scalers are fitted exactly like the reference's),
-    then load the reference's initial weights."""
+    then load the reference's initial weights.  ext=True: the second fixture set (tests/golden/make_golden_ext.py)."""
     import dpivae_b200 as dpv
 
-    g, spec, sd = gu.load(case, mtype)
+    g, spec, sd = gu.load(case, mtype, ext=ext)
     case_mod = importlib.import_module(f"dpivae_b200.cases.{case}")
     x, c, y = (torch.from_numpy(g[k].copy()) for k in "xcy")
     B = x.shape[0]
-    args = make_args(case_mod, PRESET[(case, mtype)], use_seed=True, seed=123, n_train=B, n_batch=B)
+    args = make_args(case_mod, PRESET[(case, mtype)], use_seed=True, seed=123, n_train=B, n_batch=B, **over)
     vae = dpv.setup_model(args, case_mod.definition, (x, c, y))
     missing = vae.load_state_dict(sd, strict=False)
     assert not [k for k in missing.missing_keys if not k.startswith("decoder_x.model.")], missing

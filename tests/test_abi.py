@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, s), s
     # the ctypes binding lists the same set
     assert sorted(_lib.EXPORTS) == syms
-    assert lib.dpivae_abi_version() == 1
+    assert lib.dpivae_abi_version() == 2
 
 
 def test_struct_sizes_match_header():

@@ -19,12 +19,16 @@ def test_mc_mean_and_regression_metrics_match_sklearn():
     y = torch.randn(1000, 2, generator=g) * torch.tensor([1.0, 30.0]) + torch.tensor([5.0, -100.0])
     p = y + 0.3 * torch.randn(1000, 2, generator=g)
     out = regression_metrics_device(y, p.cuda())
-    assert abs(out["r2"] - metrics.r2_score(y.numpy(), p.numpy())) < 1e-5
-    assert abs(out["mse"] - metrics.mean_squared_error(y.numpy(), p.numpy())) < 1e-5 * max(1.0, out["mse"])
-    assert abs(out["mae"] - metrics.mean_absolute_error(y.numpy(), p.numpy())) < 1e-5 * max(1.0, out["mae"])
-    # a single column, and the degenerate constant target
+    # the reference's keys and per-output arrays (utils/metrics.py:29-31, multioutput="raw_values")
+    assert set(out) == {"R2", "MSE", "MAE"} and all(v.shape == (2,) for v in out.values())
+    ref = {"R2": metrics.r2_score(y.numpy(), p.numpy(), multioutput="raw_values"),
+           "MSE": metrics.mean_squared_error(y.numpy(), p.numpy(), multioutput="raw_values"),
+           "MAE": metrics.mean_absolute_error(y.numpy(), p.numpy(), multioutput="raw_values")}
+    for k in ref:
+        assert np.allclose(out[k], ref[k], rtol=1e-5, atol=1e-6), (k, out[k], ref[k])
+    # a single column
     out1 = regression_metrics_device(y[:, :1], p[:, :1].cuda())
-    assert abs(out1["r2"] - metrics.r2_score(y[:, :1].numpy(), p[:, :1].numpy())) < 1e-5
+    assert out1["R2"].shape == (1,) and abs(out1["R2"][0] - metrics.r2_score(y[:, :1].numpy(), p[:, :1].numpy())) < 1e-5
 
 
 @pytest.mark.parametrize("k", [1, 2, 4, 8])

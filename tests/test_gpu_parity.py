@@ -169,4 +169,5 @@ def test_sample_and_evaluate_model():
     assert all(torch.isfinite(t).all() for t in out)
     args.n_mc_test = 8
     metrics, pred = dpv.evaluate_model(args, case_mod.definition, vae, (x.cuda(), c.cuda(), y))
-    assert set(metrics[args.name]) == {"r2", "mse", "mae"} and pred[args.name].shape == (B, vae.nd_y)
+    assert set(metrics[args.name]) == {"R2", "MSE", "MAE"} and pred[args.name].shape == (B, vae.nd_y)
+    assert all(v.shape == (vae.nd_y,) for v in metrics[args.name].values())   # per-output raw values (utils/metrics.py:29-31)

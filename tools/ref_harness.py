@@ -19,6 +19,30 @@ import types
 
 REF_SRC = "/root/reference"
 WORK = "/tmp/dpivae_ref_work"
+# git-ignored in-repo copy made by tools/install_reference.py: travels to the GPU box with the snapshot, so that
+# `bench.py --impl reference` can time the reference's OWN code there (nothing else reads it)
+INSTALLED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "baseline", "_ref")
+PLACEHOLDERS = [
+    ("cases/damped_oscillator/y.pt", (20000, 200)),
+    ("cases/simple_beam/y.pt", (20000, 200)),
+    ("cases/bridge/y.pt", (5000, 200)),
+    ("cases/bridge/y_partial.pt", (5000, 200)),
+]
+
+
+def copy_reference(dst):
+    """Unmodified copy of the reference tree + zero placeholders for the four missing simulator blobs."""
+    import torch
+
+    if not os.path.exists(dst):
+        shutil.copytree(REF_SRC, dst, ignore=shutil.ignore_patterns("output", "figures", ".git"))
+        os.system(f"chmod -R u+w {dst}")
+    for rel, shape in PLACEHOLDERS:
+        p = os.path.join(dst, rel)
+        if not os.path.exists(p):
+            # stride-0 view: the file holds one row, the loaded tensor has the full shape (only the shape is read)
+            torch.save(torch.zeros((1, shape[1])).expand(*shape), p)
+    return dst
 
 
 def _stub(name, **attrs):
@@ -70,21 +94,22 @@ class _CSVLogger:
         self.experiment.scalars[name].append((step, float(value)))
 
 
-def prepare():
+def available():
+    return os.path.isdir(REF_SRC) or os.path.isdir(INSTALLED)
+
+
+def prepare(root=None):
+    """root: None = the installed copy when /root/reference is absent (GPU box), else a /tmp working copy."""
     import torch
 
-    if not os.path.exists(WORK):
-        shutil.copytree(REF_SRC, WORK, ignore=shutil.ignore_patterns("output", "figures", ".git"))
-        os.system(f"chmod -R u+w {WORK}")
-        for rel, shape in [
-            ("cases/damped_oscillator/y.pt", (20000, 200)),
-            ("cases/simple_beam/y.pt", (20000, 200)),
-            ("cases/bridge/y.pt", (5000, 200)),
-            ("cases/bridge/y_partial.pt", (5000, 200)),
-        ]:
-            p = os.path.join(WORK, rel)
-            if not os.path.exists(p):
-                torch.save(torch.zeros(shape), p)
+    global WORK
+    if root is None:
+        root = WORK if os.path.isdir(REF_SRC) else os.path.abspath(INSTALLED)
+    if root == WORK:
+        copy_reference(WORK)
+    elif not os.path.isdir(root):
+        raise RuntimeError(f"reference copy not found at {root} (run tools/install_reference.py in the build container)")
+    WORK = root
 
     # stubs
     import torch.nn as nn
