@@ -372,18 +372,18 @@ static int build_plan(dpivae_model* h) {
         plane2(d3 / 8, d.nd_x, T.w_p[3], T.l_p[3]);
       }
       plane2(16, 128, T.a_big, T.l_big);
-      plane2(8, 128, T.a_g, T.l_g);
-      plane2(2, 128, T.a_oa, T.l_oa);      // aux head gradients: 8 columns used, columns 8..15 stay zero (N = 16)
+      plane2(8, 128, T.a_g, T.l_g);        // 32 KB; between two x heads it holds the auxiliary decoders' wgrad operands
       T.rec_buf = 8192 + (d.nd_c + d.nd_y) * 512;   // tile record: latent operand hi/lo planes + raw c|y per pair
       T.a_rec = b; b += 2 * T.rec_buf;
       auto f32 = [&](int floats) { int off = b; b += ((floats + 3) & ~3) * 4; return off; };
       T.f_inv = f32(16); T.f_bias_x = f32(64); T.f_bias_p1 = f32(32); T.f_bias_p2 = f32(64);
       T.f_aw0 = f32(2 * 64 * 4); T.f_ab0 = f32(2 * 64); T.f_aw1 = f32(2 * 64 * 4); T.f_ab1 = f32(8);
       T.f_w0f = f32(4 * 128); T.f_wp0f = f32(64 * 4);   // f_w0f: exchange scratch of the physics-latent gradients
-      T.f_dza = f32(nzd * 128); T.f_sc = f32(8 * 128); T.f_red = f32(256);
-      T.o_bar = b; b += 64;
+      T.f_dza = f32(2 * nzd * 128); T.f_sc = f32(8 * 128); T.f_sca = f32(2 * 2 * 128); T.f_red = f32(256);
+      T.o_bar = b; b += 96;
       T.total = (b + 127) & ~127;
-      if (T.total <= 232448 && 256 * 39 * 4 <= 2 * T.l_big && lat_smem_bytes(P, true) <= 160 * 1024) h->tc_ok = 1;
+      // R0 / R1 end-of-kernel scratch inside BIG; aux operands (64 x 128 mask plane + 24-column hi / lo product planes) inside G
+      if (T.total <= 232448 && 256 * 44 * 4 <= 2 * T.l_big && 16384 + 2 * 6144 <= 2 * T.l_g && lat_smem_bytes(P, true) <= 160 * 1024) h->tc_ok = 1;
     }
   }
   return 0;
@@ -485,7 +485,7 @@ int dpivae_set_groups(dpivae_handle_t h, int32_t n_groups, const int64_t* begin,
 }
 
 struct WsLayout {
-  size_t hid, headpre, gpre, rowloss, part, scal, rec, dzrec, epsbuf, rowkl, hidrec, total;
+  size_t hid, headpre, gpre, rowloss, part, scal, rec, dzrec, epsbuf, rowkl, hidrec, gmax, total;
   int grid_enc, grid_dec, RB, n_chunks;
   long long n_rowblocks;
   int tc_RB, tc_grid;           // tensor-core decoder kernel: rows per 128-pair tile, CTAs
@@ -520,6 +520,7 @@ static WsLayout ws_layout(dpivae_handle_t h, int64_t B, int32_t n_mc) {
 
   L.part = take((size_t)(4 * h->sm_count) * h->part_stride);
   L.scal = take(16);
+  L.gmax = take(4);
   L.rec = L.dzrec = L.epsbuf = L.rowkl = 0;
   if (h->tc_ok && n_mc >= 8 && n_mc <= 128) {
     const size_t nt = (size_t)L.tc_rowblocks;
@@ -584,6 +585,7 @@ static int run_loss(dpivae_handle_t h, const dpivae_batch_t* bt, const dpivae_rn
   const size_t enc_smem = enc_smem_bytes(h->enc, true);
   for (int k = 0; k < 4; ++k) h->ev_used[k] = 0;
   h->ev_used[5] = h->ev_used[6] = 0;
+  if (use_tc && with_grad) CUDA_OK(cudaMemsetAsync(base + L.gmax, 0, 4, st));   // max |gpre| of this batch (lat_bwd -> enc_tc_bwd)
   // encoder forward: tensor-core kernel for the encoder units (+ the FFMA kernel for the two prior nets) in the
   // tensor-core math modes when no backward follows; the FFMA kernel for everything otherwise
   const bool enc_tc = h->math_mode != DPIVAE_MATH_FP32 && h->enc_tc_ok && (!with_grad || h->enc_tc_bwd_ok);
@@ -652,6 +654,7 @@ static int run_loss(dpivae_handle_t h, const dpivae_batch_t* bt, const dpivae_rn
     D.RB = L.tc_RB; D.n_chunks = 1; D.n_rowblocks = L.tc_rowblocks;
     D.rec = (unsigned char*)(base + L.rec); D.rec_stride = h->tc.rec_buf;
     D.dzrec = (float*)(base + L.dzrec); D.epsbuf = (float*)(base + L.epsbuf); D.rowkl = (float*)(base + L.rowkl);
+    D.gpre_max = (with_grad && enc_tc) ? (unsigned int*)(base + L.gmax) : nullptr;
     { KTimer t(h, 5, st); launch_lat_fwd(D, L.tc_rowblocks, st); }
     ++launches;
     T.d = D;
@@ -676,6 +679,7 @@ static int run_loss(dpivae_handle_t h, const dpivae_batch_t* bt, const dpivae_rn
       Q.part = part + (long long)(grid_dec + L.grid_enc) * h->part_stride; Q.part_stride = h->part_stride;
       // gpre ~ O(1) / (B_global * D): bring it to O(16) before the fp16 split
       Q.e_g = (int)lrint(log2((double)bt->B_global * (double)(h->d.nd_x + h->d.nd_c + h->d.nd_y))) + 4;
+      Q.gpre_max = use_tc ? (const unsigned int*)(base + L.gmax) : nullptr;   // measured by lat_bwd_kernel (tensor-core decoder path)
       launch_enc_tc_bwd(Q, grid_etc, st);
       ++launches;
       // runs alongside the encoder backward kernel (released once that kernel has seen lat_bwd complete)

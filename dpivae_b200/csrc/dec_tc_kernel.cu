@@ -13,10 +13,18 @@
 //   * weight gradients of the trainable decoders accumulate in TMEM across ALL tiles of the CTA and are
 //     read back once at the end of the kernel (no per-tile reduction traffic); bias gradients ride on a
 //     constant-one input column (first layers) or on per-thread running sums (output layers);
-//   * the 256 threads are the epilogue: thread (quadrant q, lane, half hh) owns pair p = 32 q + lane and
-//     one half of the accumulator columns, applies bias / ReLU / tanh / likelihood gradients and writes
-//     the next operand straight back to shared memory.
-// The auxiliary decoders c and y run as ONE block-diagonal MLP (zc|zy -> 64|64 -> c-head|y-head).
+//   * 256 threads (8 warps) are the epilogue of the x path: thread (quadrant q, lane, half hh) owns pair p = 32 q + lane
+//     and one half of the accumulator columns, applies bias / ReLU / tanh / likelihood gradients and writes the next
+//     operand straight back to shared memory; one more warp issues their MMAs;
+//   * the auxiliary decoders c and y (models/decoders.py:36-49, 4 -> 64 -> 4 each) run on FOUR MORE WARPS, one tile ahead
+//     of the x path and off its critical chain: forward, likelihood and dgrad are register-resident fp32 math (thread =
+//     pair); their weight gradients are ONE masked outer-product reduction on the tensor cores:
+//         S[k][j][i] = sum_p m[p][k] g[p][j] ze[p][i]      m = ReLU mask (EXACT in fp16: a single operand plane),
+//                                                          g = head gradient, ze = [z | 1]
+//         dW1[j][k] = sum_i W0e[k][i] S[k][j][i],  dW0e[k][i] = sum_j W1[j][k] S[k][j][i]   (contracted once, at kernel end)
+//     (h = m * (W0e ze) is linear in ze given the mask), so no hidden-activation operand is ever written: the operands
+//     are the 16 KB mask plane and a 24-column product plane per side, staged in the x-residual gradient buffer while
+//     that buffer is idle between two x heads (no extra shared memory), issued by the aux warps themselves as M = 64 MMAs.
 #include <cuda_fp16.h>
 #include <curand_kernel.h>
 
@@ -31,7 +39,10 @@ namespace {
 constexpr int TP = 128;    // pairs per tile
 constexpr int TNT = 256;   // threads per CTA
 // TMEM column map (fp32 columns, 128 lanes)
-enum { C_W1 = 0, C_W0 = 64, C_AW1 = 80, C_AW0 = 96, C_H = 112, C_X = 240, C_S = 304, C_A0 = 336, C_A1 = 400, C_A2 = 432, C_T = 496,
+// C_AS: aux masked reductions S, two M = 64 accumulators of NAUX columns (side c, side y); C_T (first-layer dgrad of the
+// data-driven decoder) shares the columns of C_S, which is idle by the time stage S8 is issued
+constexpr int NAUX = 24;   // product columns per side: (head output j < 4) x (input i < 5: z_0..z_3, 1), padded to 3 chunks
+enum { C_W1 = 0, C_W0 = 64, C_AS = 80, C_H = 128, C_X = 256, C_S = 320, C_T = 320, C_A0 = 352, C_A1 = 416, C_A2 = 448,
        C_ALLOC = 512 };
 // power-of-two operand scales (exponents)
 constexpr int E_LAT = 4, E_H = 6, E_T = 8;
@@ -111,7 +122,9 @@ __device__ __forceinline__ tc::Op mkop(const unsigned char* sm, int off, uint32_
   return o;
 }
 
-constexpr int NTHR = TNT + 32;   // 8 epilogue warps + 1 MMA-issue warp
+constexpr int NTHR = TNT + 32;    // 8 epilogue warps + 1 MMA-issue warp: participants of the stage-signal barriers
+constexpr int NAUXT = 128;        // 4 auxiliary-decoder warps (thread = pair)
+constexpr int NALL = NTHR + NAUXT;   // threads per CTA
 // Warp-specialised MMA issue: the 256 epilogue threads only SIGNAL that the operands of stage `sid` are in place
 // (non-blocking bar.arrive on a rotating named barrier); the dedicated issue warp waits for the signal, issues the
 // MMAs and commits them to an mbarrier.  The epilogue warps never spend issue slots on descriptor arithmetic and never
@@ -174,12 +187,12 @@ __device__ void stage_weight(unsigned char* plane, uint32_t lo_off, int N, int K
 // PHYS: physics decoder kind (0 MLP surrogate, 1 mass_spring, 2 beam); NDX: response length -- compile-time so
 // that the epilogues are straight-line code (a taken branch in this large kernel costs an I-cache miss)
 template <bool PROF, int PHYS, int NDX>
-__global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__ TcParams T) {
+__global__ void __launch_bounds__(NALL, 1) dec_tc_kernel(const __grid_constant__ TcParams T) {
   const DecParams& P = T.d;
   extern __shared__ __align__(1024) unsigned char smb[];
   float* smf = reinterpret_cast<float*>(smb);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int q = warp & 3, hh = warp >> 2;
+  const int q = warp & 3, hh = (warp >> 2) & 1;   // warps 0..7: x-path epilogue, 8: MMA issue, 9..12: auxiliary decoders
   const int p = 32 * q + lane;  // pair (TMEM lane) owned in the epilogues; hh = column half / aux side (0 = c, 1 = y)
   const int n = P.n_mc;
   const int nzd = P.nz_c + P.nz_y;
@@ -208,6 +221,7 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
   float* DZA = smf + (T.f_dza >> 2);
   float* GSX = smf + (T.f_w0f >> 2);      // [4][TP] exchange of the physics-latent gradient halves
   float* SC = smf + (T.f_sc >> 2);
+  float* SCA = smf + (T.f_sca >> 2);      // [2 tile parities][2 sides][TP]: R_c, R_y per pair, written by the aux warps
   float* RED = smf + (T.f_red >> 2);
   float* R0 = smf + (T.a_big >> 2);      // end-of-kernel reduction scratch, aliases the BIG operand buffer
   unsigned char* RECB = smb + T.a_rec;   // two tile-record buffers (bulk-copied from the latent kernel's output)
@@ -215,6 +229,11 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
   uint64_t* bar0 = reinterpret_cast<uint64_t*>(smb + T.o_bar);
   uint64_t* bar1 = bar0 + 1;
   uint32_t* tptr = reinterpret_cast<uint32_t*>(smb + T.o_bar + 16);
+  // aux warps <-> x path: gfree = the x-residual gradient buffer G is idle (every x-path thread arrives once per tile),
+  // adone = the aux results of a tile (R_c / R_y, dL/dz, weight-gradient MMAs) are complete, abar = the aux MMAs of side c
+  uint64_t* gfree = reinterpret_cast<uint64_t*>(smb + T.o_bar + 48);
+  uint64_t* adone = gfree + 1;
+  uint64_t* abar = gfree + 2;
 
   // ---- one-time: zero smem, barriers, TMEM, weights -------------------------------------------------
   for (int e = tid; e < (T.total >> 2); e += TNT) smf[e] = 0.0f;
@@ -224,6 +243,9 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
     tc::mbar_init(bar1, 1);
     tc::mbar_init(rbar, 1);
     tc::mbar_init(rbar + 1, 1);
+    tc::mbar_init(gfree, TNT);
+    tc::mbar_init(adone, P.with_grad ? NAUXT + 1 : NAUXT);   // every aux thread + (training) the commit of its last MMAs
+    tc::mbar_init(abar, 1);
     tc::mbar_fence_init();
   }
   __syncwarp();
@@ -372,25 +394,17 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
   // operands
   const tc::Op oBIG = mkop(smb, T.a_big, T.l_big, TP);
   const tc::Op oG = mkop(smb, T.a_g, T.l_g, TP);
-  const tc::Op oOA = mkop(smb, T.a_oa, T.l_oa, TP);
   const tc::Op oWFX0 = mkop(smb, T.w_fx0, T.l_fx0, 128), oWFX1 = mkop(smb, T.w_fx1, T.l_fx1, ndx);
   const tc::Op oWP0 = mkop(smb, T.w_p[0], T.l_p[0], d1 ? d1 : 16), oWP1 = mkop(smb, T.w_p[1], T.l_p[1], d2 ? d2 : 16);
   const tc::Op oWP2 = mkop(smb, T.w_p[2], T.l_p[2], d3 ? d3 : 16), oWP3 = mkop(smb, T.w_p[3], T.l_p[3], ndx);
   unsigned char* pBIG = smb + T.a_big;
   unsigned char* pG = smb + T.a_g;
-  unsigned char* pOA = smb + T.a_oa;
-
-  // aux side of this thread
-  const int a_nz = hh ? P.nz_y : P.nz_c, a_j0 = hh ? P.nz_c : 0, a_nd = hh ? P.nd_y : P.nd_c;
-  const ulonglong2* aW0 = reinterpret_cast<const ulonglong2*>(AW0) + hh * 64;   // [pair][2]: inputs (0,1), (2,3)
-  const ulonglong2* aW1 = reinterpret_cast<const ulonglong2*>(AW1) + hh * 64;   // [pair][2]: outputs (0,1), (2,3)
-  const f2_t* aB0 = reinterpret_cast<const f2_t*>(AB0) + hh * 32;
 
   // per-thread running sums over all tiles (fixed thread <-> column assignment: deterministic)
   float dbx[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) dbx[i] = 0.0f;
-  float dba[4] = {0.f, 0.f, 0.f, 0.f};
+  float dbc[4] = {0.f, 0.f, 0.f, 0.f}, dby[4] = {0.f, 0.f, 0.f, 0.f};   // aux warps: head-bias gradient sums (side c, side y)
   float dlsx = 0.0f;
   float tot[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   uint32_t wacc = 0;  // 0 on the first tile (weight-gradient accumulators start from zero)
@@ -419,70 +433,57 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
       itl = _t;                          \
     }                                    \
   } while (0)
+    // first layers of a tile (S0): fx0 -> C_H, physics layer 0 -> C_X, operand = the bulk-copied tile record.  Issued at
+    // the top of the first tile and, when a backward follows, EARLY for every later tile: the x path signals as soon as
+    // the previous tile's last reader of C_X is through, so these MMAs queue behind that tile's last weight gradients
+    // and their results are ready when the next tile starts.
+    auto issue_s0 = [&](int it_) {
+      const int buf_ = it_ & 1;
+      const tc::Op oL = mkop(RECB + (size_t)buf_ * T.rec_buf, 0, 4096u, TP);
+      tc::mbar_wait(rbar + buf_, (uint32_t)(it_ >> 1) & 1u);   // the tile record (latent operand) has landed
+      __syncwarp();
+      issuer_wait(sid++);   // S0
+      ISSUER_MARK(iw);
+      tc::issue_fwd_w(el, tbu + C_H, oL, oWFX0, 128, KZ, 0, terms);
+      if constexpr (mlp) tc::issue_fwd_w(el, tbu + C_X, oL, oWP0, d1, KZ, 0, terms);
+      tc::commit_w(el, bar0);
+      __syncwarp();
+      ISSUER_MARK(ii);
+    };
+    const bool early_s0 = P.with_grad != 0;
     for (long long rb = blockIdx.x; rb < P.n_rowblocks; rb += gridDim.x, ++it) {
       const int buf = it & 1;
       const unsigned char* rec = RECB + (size_t)buf * T.rec_buf;
       const tc::Op oLAT = mkop(rec, 0, 4096u, TP);
-      tc::mbar_wait(rbar + buf, (uint32_t)(it >> 1) & 1u);   // the tile record (latent operand) has landed
-      __syncwarp();
-      issuer_wait(sid++);   // S0
+      if (it == 0 || !early_s0) issue_s0(it);
+      if constexpr (mlp) {
+        issuer_wait(sid++);   // S2: physics layer 1
         ISSUER_MARK(iw);
-      {
-        tc::issue_fwd_w(el, tbu + C_H, oLAT, oWFX0, 128, KZ, 0, terms);
-        if constexpr (mlp) tc::issue_fwd_w(el, tbu + C_X, oLAT, oWP0, d1, KZ, 0, terms);
+        tc::issue_fwd_ts_w(el, tbu + C_S, tbu + C_A0, oWP1, d2, d1, 0, terms);
         tc::commit_w(el, bar0);
+        __syncwarp();
+        ISSUER_MARK(ii);
       }
+      issuer_wait(sid++);   // S5a: output layer of the data-driven decoder, as soon as its hidden activations are staged
+      ISSUER_MARK(iw);
+      tc::issue_fwd_w(el, tbu + C_X, oBIG, oWFX1, ndx, 128, 0, terms);
+      if constexpr (!mlp) tc::commit_w(el, bar0);   // (MLP physics: the commit of S5b covers these MMAs too)
       __syncwarp();
       ISSUER_MARK(ii);
-      if (P.with_grad) {
-        issuer_wait(sid++);   // S1
-        ISSUER_MARK(iw);
-        {
-          tc::issue_wgrad_w(el, tbu + C_AW1, oBIG, oOA, 16, wacc, terms);
-          tc::commit_w(el, bar1);
-        }
-        __syncwarp();
-        ISSUER_MARK(ii);
-      }
       if constexpr (mlp) {
-        issuer_wait(sid++);   // S2
+        issuer_wait(sid++);   // S4: physics layer 2 -> first half of C_H (the fx0 accumulator has been consumed)
         ISSUER_MARK(iw);
-        {
-          tc::issue_fwd_ts_w(el, tbu + C_S, tbu + C_A0, oWP1, d2, d1, 0, terms);
-          tc::commit_w(el, bar0);
-        }
-        __syncwarp();
-        ISSUER_MARK(ii);
-      }
-      if (P.with_grad) {
-        issuer_wait(sid++);   // S3
-        ISSUER_MARK(iw);
-        {
-          tc::issue_wgrad_w(el, tbu + C_AW0, oBIG, oLAT, KZ, wacc, terms);
-          tc::commit_w(el, bar1);
-        }
-        __syncwarp();
-        ISSUER_MARK(ii);
-      }
-      if constexpr (mlp) {
-        issuer_wait(sid++);   // S4
-        ISSUER_MARK(iw);
-        {
-          tc::issue_fwd_ts_w(el, tbu + C_X, tbu + C_A1, oWP2, d3, d2, 0, terms);
-          tc::commit_w(el, bar0);
-        }
-        __syncwarp();
-        ISSUER_MARK(ii);
-      }
-      issuer_wait(sid++);   // S5
-        ISSUER_MARK(iw);
-      {
-        tc::issue_fwd_w(el, tbu + C_X, oBIG, oWFX1, ndx, 128, 0, terms);
-        if constexpr (mlp) tc::issue_fwd_ts_w(el, tbu + C_X, tbu + C_A2, oWP3, ndx, d3, 1, terms);
+        tc::issue_fwd_ts_w(el, tbu + C_H, tbu + C_A1, oWP2, d3, d2, 0, terms);
         tc::commit_w(el, bar0);
+        __syncwarp();
+        ISSUER_MARK(ii);
+        issuer_wait(sid++);   // S5b: last physics layer on top of the data-driven decoder's output
+        ISSUER_MARK(iw);
+        tc::issue_fwd_ts_w(el, tbu + C_X, tbu + C_A2, oWP3, ndx, d3, 1, terms);
+        tc::commit_w(el, bar0);
+        __syncwarp();
+        ISSUER_MARK(ii);
       }
-      __syncwarp();
-      ISSUER_MARK(ii);
       if (P.with_grad) {
         issuer_wait(sid++);   // S6: the dgrads the next epilogues wait for go first (bar0), the weight gradient of fx1 on bar1
         ISSUER_MARK(iw);
@@ -497,7 +498,7 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
         ISSUER_MARK(ii);
         if constexpr (mlp) {
           issuer_wait(sid++);   // S7
-        ISSUER_MARK(iw);
+          ISSUER_MARK(iw);
           {
             tc::issue_dgrad_ts_w(el, tbu + C_S, tbu + C_A2, oWP2, d3, d2, 0, terms);
             tc::commit_w(el, bar0);
@@ -520,12 +521,217 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
         tc::commit_w(el, bar1);
         __syncwarp();
         ISSUER_MARK(ii);
+        if (rb + gridDim.x < P.n_rowblocks) issue_s0(it + 1);
       }
       wacc = 1u;
     }
     if (PROF && lane == 0) {
       atomicAdd(reinterpret_cast<unsigned long long*>(P.phase) + 20, (unsigned long long)iw);
       atomicAdd(reinterpret_cast<unsigned long long*>(P.phase) + 21, (unsigned long long)ii);
+    }
+  } else if (warp > 8) {
+    // ================= auxiliary-decoder warps (thread = pair): decoder_c then decoder_y of tile `it`, one tile ahead of
+    // the x path.  Forward, Gaussian likelihood and dgrad in registers (packed fp32 pairs); the weight-gradient operands
+    // (ReLU mask plane, head-gradient x input products) go into the idle G buffer and are reduced over the pairs by
+    // M = 64 MMAs issued from here.
+    const int ap = tid - NTHR;
+    const int aw = warp - 9;
+    if (tb != 0u) __trap();
+    constexpr uint32_t tbu = 0u;
+    const uint32_t el = tc::elect_one();
+    unsigned char* pM = smb + T.a_g;                  // X8[8 chunks = 64 hidden units][TP pairs], fp16 0 / 1
+    unsigned char* pB = smb + T.a_g + 16384;          // X8[3 chunks = NAUX product columns][TP pairs], hi plane; lo plane behind it
+    constexpr uint32_t B_LO = 3u * TP * 16u;
+    long long xw = 0, xb = 0, xtl = PROF ? clock64() : 0;   // PROF: cycles waiting (records, buffer hand-overs) vs working
+#define AUX_MARK(acc)                        \
+  do {                                       \
+    if (PROF && ap == 0) {                   \
+      const long long _t = clock64();        \
+      acc += _t - xtl;                       \
+      xtl = _t;                              \
+    }                                        \
+  } while (0)
+    uint32_t wacc = 0;
+    int it = 0;
+    for (long long rb = blockIdx.x; rb < P.n_rowblocks; rb += gridDim.x, ++it) {
+      const long long row0 = rb * RB;
+      const int npairs = (int)min((long long)RB, B - row0) * n;
+      const int buf = it & 1;
+      const unsigned char* rec = RECB + (size_t)buf * T.rec_buf;
+      AUX_MARK(xb);
+      tc::mbar_wait(rbar + buf, (uint32_t)(it >> 1) & 1u);
+      __syncwarp();
+      AUX_MARK(xw);
+      const float* RAW = reinterpret_cast<const float*>(rec + 8192);
+      const bool pvalid = ap < npairs;
+      float* dza = DZA + (size_t)(it & 1) * nzd * TP;
+      float* sca = SCA + (size_t)(it & 1) * 2 * TP;
+#pragma unroll 1
+      for (int s = 0; s < 2; ++s) {
+        const int a_nz = s ? P.nz_y : P.nz_c, a_j0 = s ? P.nz_c : 0, a_nd = s ? P.nd_y : P.nd_c;
+        const ulonglong2* aW0 = reinterpret_cast<const ulonglong2*>(AW0) + s * 64;   // [unit pair][2]: inputs (0,1), (2,3)
+        const ulonglong2* aW1 = reinterpret_cast<const ulonglong2*>(AW1) + s * 64;   // [unit pair][2]: outputs (0,1), (2,3)
+        const f2_t* aB0 = reinterpret_cast<const f2_t*>(AB0) + s * 32;
+        float z4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) z4[j] = (j < a_nz && pvalid) ? lat_elem(rec, a_j0 + j, ap) : 0.0f;
+        unsigned long long mkA = 0ull;
+        float g4[4] = {0.f, 0.f, 0.f, 0.f};
+        {
+          // two hidden units per step on packed pairs (FFMA2); the head sums are kept as (even-unit, odd-unit) partials
+          const f2_t zz0 = pk2(z4[0], z4[0]), zz1 = pk2(z4[1], z4[1]), zz2 = pk2(z4[2], z4[2]), zz3 = pk2(z4[3], z4[3]);
+          f2_t oP0 = 0ull, oP1 = 0ull, oP2 = 0ull, oP3 = 0ull;
+#pragma unroll 2
+          for (int c = 0; c < 8; ++c) {
+            uint32_t m8 = 0u;
+#pragma unroll
+            for (int i2 = 0; i2 < 4; ++i2) {
+              const int kp = 4 * c + i2;   // unit pair (2 kp, 2 kp + 1)
+              const ulonglong2 wa = aW0[2 * kp], wb = aW0[2 * kp + 1];
+              const f2_t pre2 = ffma2(zz3, wb.y, ffma2(zz2, wb.x, ffma2(zz1, wa.y, ffma2(zz0, wa.x, aB0[kp]))));
+              float pa, pb;
+              upk2(pre2, pa, pb);
+              const float ha = fmaxf(pa, 0.0f), hb = fmaxf(pb, 0.0f);
+              m8 |= ((pa > 0.0f ? 1u : 0u) | (pb > 0.0f ? 2u : 0u)) << (2 * i2);
+              const f2_t h2 = pk2(ha, hb);
+              const ulonglong2 ta = aW1[2 * kp], tb2 = aW1[2 * kp + 1];
+              oP0 = ffma2(h2, ta.x, oP0); oP1 = ffma2(h2, ta.y, oP1); oP2 = ffma2(h2, tb2.x, oP2); oP3 = ffma2(h2, tb2.y, oP3);
+            }
+            mkA |= (unsigned long long)m8 << (8 * c);
+          }
+          float o0, o1, o2, o3;
+          {
+            float a, b;
+            upk2(oP0, a, b); o0 = (a + b) + AB1[s * 4 + 0];
+            upk2(oP1, a, b); o1 = (a + b) + AB1[s * 4 + 1];
+            upk2(oP2, a, b); o2 = (a + b) + AB1[s * 4 + 2];
+            upk2(oP3, a, b); o3 = (a + b) + AB1[s * 4 + 3];
+          }
+          // Gaussian log-likelihood of the raw covariate / label and its gradient w.r.t. (mean, log sigma)
+          float R = 0.0f;
+          if (s == 0 || P.y != nullptr) {
+            const float om[2] = {o0, o1}, ol[2] = {o2, o3};
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              if (j < a_nd) {
+                const float val = RAW[((s ? P.nd_c : 0) + j) * TP + ap];
+                const float es = expf(ol[j]), var = es * es, d = val - om[j];
+                R += -(d * d) / (2.0f * var) - ol[j] - LOG_SQRT_2PI;
+                if (pvalid) {
+                  g4[j] = fminf(fmaxf(-d / var, -60000.0f), 60000.0f);
+                  g4[2 + j] = fminf(fmaxf(-(d * d / var - 1.0f), -60000.0f), 60000.0f);
+                }
+              }
+            }
+          }
+          sca[s * TP + ap] = pvalid ? R : 0.0f;
+        }
+        if (P.with_grad) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            dbc[i] += s ? 0.0f : g4[i];
+            dby[i] += s ? g4[i] : 0.0f;
+          }
+          // dgrad: dL/dz = W0^T (mask * (W1^T g))
+          {
+            const f2_t gg0 = pk2(g4[0], g4[0]), gg1 = pk2(g4[1], g4[1]), gg2 = pk2(g4[2], g4[2]), gg3 = pk2(g4[3], g4[3]);
+            f2_t gP0 = 0ull, gP1 = 0ull, gP2 = 0ull, gP3 = 0ull;   // (even-unit, odd-unit) partials of dL/dz
+#pragma unroll 2
+            for (int c = 0; c < 8; ++c) {
+              const uint32_t m8 = (uint32_t)(mkA >> (8 * c)) & 0xFFu;
+#pragma unroll
+              for (int i2 = 0; i2 < 4; ++i2) {
+                const int kp = 4 * c + i2;
+                const ulonglong2 ta = aW1[2 * kp], tb2 = aW1[2 * kp + 1];
+                const f2_t gh2 = ffma2(gg3, tb2.y, ffma2(gg2, tb2.x, ffma2(gg1, ta.y, fmul2(gg0, ta.x))));
+                float ga, gb;
+                upk2(gh2, ga, gb);
+                ga = ((m8 >> (2 * i2)) & 1u) ? ga : 0.0f;
+                gb = ((m8 >> (2 * i2 + 1)) & 1u) ? gb : 0.0f;
+                const f2_t ghm = pk2(ga, gb);
+                const ulonglong2 wa = aW0[2 * kp], wb = aW0[2 * kp + 1];
+                gP0 = ffma2(ghm, wa.x, gP0); gP1 = ffma2(ghm, wa.y, gP1); gP2 = ffma2(ghm, wb.x, gP2); gP3 = ffma2(ghm, wb.y, gP3);
+              }
+            }
+            float gz[4];
+            {
+              float a, b;
+              upk2(gP0, a, b); gz[0] = a + b;
+              upk2(gP1, a, b); gz[1] = a + b;
+              upk2(gP2, a, b); gz[2] = a + b;
+              upk2(gP3, a, b); gz[3] = a + b;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (j < a_nz) dza[(a_j0 + j) * TP + ap] = gz[j];
+          }
+          // the operand buffer: side c waits until the x path is through with G (tile it - 1), side y until the MMAs
+          // of side c have read it
+          AUX_MARK(xb);
+          if (s == 0) {
+            if (it > 0) tc::mbar_wait(gfree, (uint32_t)(it - 1) & 1u);
+          } else {
+            tc::mbar_wait(abar, (uint32_t)it & 1u);
+          }
+          __syncwarp();
+          tc::fence_after_sync();
+          AUX_MARK(xw);
+          // Per-pair power-of-two balance between the two operands: the mask plane carries 2^e, the products 2^-e, with
+          // e chosen from the largest product of the pair so that it lands in [2^12, 2^13): exact (powers of two), keeps
+          // both fp16 planes of every product in the normal range whatever the magnitude of the head gradient
+          // (|g z| from 2^-2 to 2^27 without loss; beyond that the products saturate at +-60000 * 2^e)
+          const float gmx = fmaxf(fmaxf(fabsf(g4[0]), fabsf(g4[1])), fmaxf(fabsf(g4[2]), fabsf(g4[3])));
+          const float zmx = fmaxf(fmaxf(fabsf(z4[0]), fabsf(z4[1])), fmaxf(fmaxf(fabsf(z4[2]), fabsf(z4[3])), 1.0f));
+          int e_p = (int)((__float_as_uint(gmx * zmx) >> 23) & 0xFFu) - 127 - 12;
+          e_p = max(-14, min(e_p, 15));
+          const uint32_t hone = (uint32_t)(e_p + 15) << 10;                      // fp16 bits of 2^e_p
+          const float s_b = __uint_as_float((uint32_t)(127 - e_p) << 23);       // 2^-e_p
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint32_t m8 = (uint32_t)(mkA >> (8 * c)) & 0xFFu;
+            uint32_t wv[4];
+#pragma unroll
+            for (int w2 = 0; w2 < 4; ++w2) {
+              const uint32_t t2 = (m8 >> (2 * w2)) & 3u;
+              wv[w2] = ((t2 & 1u) | ((t2 & 2u) << 15)) * hone;   // 2^e_p in the low / high half where the unit is active
+            }
+            *reinterpret_cast<uint4*>(pM + ((size_t)c * TP + ap) * 16) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+          }
+          {
+            // product columns 5 j + i = g_j * [z_0 .. z_3, 1]_i * 2^-e_p
+            float v[NAUX];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float gs = g4[j] * s_b;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) v[5 * j + i] = fminf(fmaxf(gs * z4[i], -60000.0f), 60000.0f);
+              v[5 * j + 4] = fminf(fmaxf(gs, -60000.0f), 60000.0f);
+            }
+#pragma unroll
+            for (int i = 20; i < NAUX; ++i) v[i] = 0.0f;
+#pragma unroll
+            for (int c = 0; c < NAUX / 8; ++c) put8(pB, B_LO, TP, c, ap, v + 8 * c);
+          }
+          tc::fence_async_smem();
+          tc::fence_before_sync();
+          asm volatile("bar.sync 10, %0;" ::"r"((uint32_t)NAUXT) : "memory");
+          tc::fence_after_sync();
+          if (aw == 0) {
+            tc::issue_mask_wgrad64_w(el, tbu + C_AS + NAUX * s, tc::smem_u32(smb + T.a_g), tc::smem_u32(smb + T.a_g + 16384), B_LO, TP,
+                                     NAUX, wacc);
+            tc::commit_w(el, s == 0 ? abar : adone);
+          }
+          __syncwarp();
+        }
+      }
+      if (!P.with_grad && it > 0) tc::mbar_wait(gfree, (uint32_t)(it - 1) & 1u);   // never more than one tile ahead of the consumer
+      tc::mbar_arrive(adone);
+      wacc = 1u;
+    }
+    AUX_MARK(xb);
+    if (PROF && ap == 0) {
+      atomicAdd(reinterpret_cast<unsigned long long*>(P.phase) + 22, (unsigned long long)xw);
+      atomicAdd(reinterpret_cast<unsigned long long*>(P.phase) + 23, (unsigned long long)xb);
     }
   } else {
   const uint32_t rec_bytes = (uint32_t)P.rec_stride;
@@ -551,82 +757,11 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
     tc::mbar_wait(rbar + buf, (uint32_t)(it >> 1) & 1u);
     __syncwarp();
     const tc::Op oLAT = mkop(rec, 0, 4096u, TP);   // latent operand [zd | 1 | physics input] as written by lat_fwd_kernel
-    const float* RAW = reinterpret_cast<const float*>(rec + 8192);
     const bool pvalid = p < npairs;
     const int prow = (pvalid ? p : npairs - 1) / n;
     // ---- first layers of the data-driven decoder and of the physics surrogate: issued now, consumed later ----
-    stage_signal<false>(sid++);   // S0: previous tile fully consumed (operand = the bulk-copied record)
+    if (it == 0 || !P.with_grad) stage_signal<false>(sid++);   // S0 (later tiles of a training step: signalled early, end of the previous tile)
     TPHASE(TPH_LATENT);
-
-    // ================= auxiliary decoder of side hh, forward, on the CUDA cores (fp32) =======================
-    // Block-diagonal ownership: thread (p, hh) owns all 64 hidden units and the head of decoder hh for pair p, so
-    // forward and dgrad need no cross-thread traffic; only the two weight gradients (sums over pairs) go to the
-    // tensor cores, as fire-and-forget MMAs on the operand copies written here.
-    float z4[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) z4[j] = (j < a_nz && pvalid) ? lat_elem(rec, a_j0 + j, p) : 0.0f;
-    unsigned long long mkA = 0ull;
-    float g4[4] = {0.f, 0.f, 0.f, 0.f};
-    {
-      // two hidden units per step on packed pairs (FFMA2); the head sums are kept as (even-unit, odd-unit) partials
-      const f2_t zz0 = pk2(z4[0], z4[0]), zz1 = pk2(z4[1], z4[1]), zz2 = pk2(z4[2], z4[2]), zz3 = pk2(z4[3], z4[3]);
-      f2_t oP0 = 0ull, oP1 = 0ull, oP2 = 0ull, oP3 = 0ull;
-#pragma unroll 2
-      for (int c = 0; c < 8; ++c) {
-        float hv[8];
-        uint32_t m8 = 0u;
-#pragma unroll
-        for (int i2 = 0; i2 < 4; ++i2) {
-          const int kp = 4 * c + i2;   // unit pair (2 kp, 2 kp + 1)
-          const ulonglong2 wa = aW0[2 * kp], wb = aW0[2 * kp + 1];
-          const f2_t pre2 = ffma2(zz3, wb.y, ffma2(zz2, wb.x, ffma2(zz1, wa.y, ffma2(zz0, wa.x, aB0[kp]))));
-          float pa, pb;
-          upk2(pre2, pa, pb);
-          const float ha = fmaxf(pa, 0.0f), hb = fmaxf(pb, 0.0f);
-          m8 |= ((pa > 0.0f ? 1u : 0u) | (pb > 0.0f ? 2u : 0u)) << (2 * i2);
-          const f2_t h2 = pk2(ha, hb);
-          const ulonglong2 ta = aW1[2 * kp], tb = aW1[2 * kp + 1];
-          oP0 = ffma2(h2, ta.x, oP0); oP1 = ffma2(h2, ta.y, oP1); oP2 = ffma2(h2, tb.x, oP2); oP3 = ffma2(h2, tb.y, oP3);
-          hv[2 * i2] = ha * s_h;
-          hv[2 * i2 + 1] = hb * s_h;
-        }
-        mkA |= (unsigned long long)m8 << (8 * c);
-        if (P.with_grad) put8(pBIG, T.l_big, TP, 8 * hh + c, p, hv);
-      }
-      float o0, o1, o2, o3;
-      {
-        float a, b;
-        upk2(oP0, a, b); o0 = (a + b) + AB1[hh * 4 + 0];
-        upk2(oP1, a, b); o1 = (a + b) + AB1[hh * 4 + 1];
-        upk2(oP2, a, b); o2 = (a + b) + AB1[hh * 4 + 2];
-        upk2(oP3, a, b); o3 = (a + b) + AB1[hh * 4 + 3];
-      }
-      // Gaussian log-likelihood of the raw covariate / label and its gradient w.r.t. (mean, log sigma)
-      float R = 0.0f;
-      if (hh == 0 || P.y != nullptr) {
-        const float om[2] = {o0, o1}, ol[2] = {o2, o3};
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          if (j < a_nd) {
-            const float val = RAW[((hh ? P.nd_c : 0) + j) * TP + p];
-            const float es = expf(ol[j]), var = es * es, d = val - om[j];
-            R += -(d * d) / (2.0f * var) - ol[j] - LOG_SQRT_2PI;
-            if (pvalid) {
-              g4[j] = fminf(fmaxf(-d / var, -60000.0f), 60000.0f);
-              g4[2 + j] = fminf(fmaxf(-(d * d / var - 1.0f), -60000.0f), 60000.0f);
-            }
-          }
-        }
-      }
-      SC[(hh ? S_RY : S_RC) * TP + p] = pvalid ? R : 0.0f;
-      if (P.with_grad) {
-        put4(pOA, T.l_oa, TP, 0, p, hh, g4);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) dba[i] += g4[i];
-      }
-    }
-    if (P.with_grad) stage_signal(sid++);   // S1
-    TPHASE(TPH_AUX1);
 
     // ================= physics layer 0 -> tanh (bias folded into the constant-one column) =====================
     stage_wait(bar0, ph0);
@@ -645,68 +780,7 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
       stage_signal<false>(sid++);   // S2
     }
     TPHASE(TPH_A0);
-
-    // ================= auxiliary decoder backward (dgrad on the CUDA cores) =====================================
-    if (P.with_grad) {
-      stage_wait(bar1, ph1);  // wgrad aux1 done: BIG may be overwritten
-      const f2_t gg0 = pk2(g4[0], g4[0]), gg1 = pk2(g4[1], g4[1]), gg2 = pk2(g4[2], g4[2]), gg3 = pk2(g4[3], g4[3]);
-      f2_t gP0 = 0ull, gP1 = 0ull, gP2 = 0ull, gP3 = 0ull;   // (even-unit, odd-unit) partials of dL/dz
-#pragma unroll 2
-      for (int c = 0; c < 8; ++c) {
-        float hv[8];
-        const uint32_t m8 = (uint32_t)(mkA >> (8 * c)) & 0xFFu;
-#pragma unroll
-        for (int i2 = 0; i2 < 4; ++i2) {
-          const int kp = 4 * c + i2;
-          const ulonglong2 ta = aW1[2 * kp], tb = aW1[2 * kp + 1];
-          const f2_t gh2 = ffma2(gg3, tb.y, ffma2(gg2, tb.x, ffma2(gg1, ta.y, fmul2(gg0, ta.x))));
-          float ga, gb;
-          upk2(gh2, ga, gb);
-          ga = ((m8 >> (2 * i2)) & 1u) ? ga : 0.0f;
-          gb = ((m8 >> (2 * i2 + 1)) & 1u) ? gb : 0.0f;
-          const f2_t ghm = pk2(ga, gb);
-          const ulonglong2 wa = aW0[2 * kp], wb = aW0[2 * kp + 1];
-          gP0 = ffma2(ghm, wa.x, gP0); gP1 = ffma2(ghm, wa.y, gP1); gP2 = ffma2(ghm, wb.x, gP2); gP3 = ffma2(ghm, wb.y, gP3);
-          hv[2 * i2] = ga;
-          hv[2 * i2 + 1] = gb;
-        }
-        put8(pBIG, T.l_big, TP, 8 * hh + c, p, hv);
-      }
-      float gz[4];
-      {
-        float a, b;
-        upk2(gP0, a, b); gz[0] = a + b;
-        upk2(gP1, a, b); gz[1] = a + b;
-        upk2(gP2, a, b); gz[2] = a + b;
-        upk2(gP3, a, b); gz[3] = a + b;
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (j < a_nz) DZA[(a_j0 + j) * TP + p] = gz[j];
-      stage_signal(sid++);   // S3
-    }
-    TPHASE(TPH_AUX2);
-
-    if constexpr (mlp) {
-      // ================= physics layer 1 -> tanh ===================================================================
-      stage_wait(bar0, ph0);
-      {
-        const float inv = INV[I_P1];
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          float v[8];
-          tc::tmem_ld8(trow + C_S + 16 * hh + 8 * c, v);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = tanh_fast(v[i] * inv + BP1[16 * hh + 8 * c + i]) * s_t;
-          tc::tmem_put8_packed(trow + C_A1 + 8 * hh + 4 * c, trow + C_A1 + 16 + 8 * hh + 4 * c, v);
-        }
-      }
-      stage_signal<false>(sid++);   // S4
-    }
-    TPHASE(TPH_A1);
-
     // ================= hidden layer of the data-driven decoder: ReLU (bias folded), mask in registers ============
-    if (P.with_grad) stage_wait(bar1, ph1);  // wgrad aux0 done: BIG may be overwritten
     unsigned long long mkH = 0ull;
     {
       const float inv = INV[I_FX0];
@@ -726,7 +800,25 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
       }
     }
     TPHASE(TPH_HD);
+    stage_signal(sid++);   // S5a: the output layer of the data-driven decoder runs under the rest of the physics chain
 
+    if constexpr (mlp) {
+      // ================= physics layer 1 -> tanh ===================================================================
+      stage_wait(bar0, ph0);
+      {
+        const float inv = INV[I_P1];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          float v[8];
+          tc::tmem_ld8(trow + C_S + 16 * hh + 8 * c, v);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = tanh_fast(v[i] * inv + BP1[16 * hh + 8 * c + i]) * s_t;
+          tc::tmem_put8_packed(trow + C_A1 + 8 * hh + 4 * c, trow + C_A1 + 16 + 8 * hh + 4 * c, v);
+        }
+      }
+      stage_signal<false>(sid++);   // S4
+    }
+    TPHASE(TPH_A1);
     if constexpr (mlp) {
       // ================= physics layer 2 -> tanh ===================================================================
       stage_wait(bar0, ph0);
@@ -735,15 +827,14 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
 #pragma unroll 2
         for (int c = 0; c < 4; ++c) {
           float v[8];
-          tc::tmem_ld8(trow + C_X + 32 * hh + 8 * c, v);
+          tc::tmem_ld8(trow + C_H + 32 * hh + 8 * c, v);   // layer 2 accumulates in the first half of C_H (C_X holds the x head)
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[i] = tanh_fast(v[i] * inv + BP2[32 * hh + 8 * c + i]) * s_h;
           tc::tmem_put8_packed(trow + C_A2 + 16 * hh + 4 * c, trow + C_A2 + 32 + 16 * hh + 4 * c, v);
         }
       }
+      stage_signal<false>(sid++);   // S5b: last physics layer, accumulated on top of the data-driven output
     }
-    // x head = data-driven decoder output (+ last physics layer) into the same accumulator
-    stage_signal(sid++);   // S5
     TPHASE(TPH_A2);
     // the raw data row is fetched BEFORE waiting for the head MMAs (the global-load latency hides under them)
     float xv[nxh];
@@ -794,9 +885,14 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
         v[i] = fminf(fmaxf(gsc * res, -60000.0f), 60000.0f);
         dbx[i] += v[i];
       }
+      // the aux warps are through with tile `it` (their weight-gradient MMAs have read the operands staged in G,
+      // R_c / R_y / dL/dz of this tile are in shared memory)
+      tc::mbar_wait(adone, (uint32_t)it & 1u);
       if (P.with_grad) {
 #pragma unroll
         for (int c = 0; c < nxh / 8; ++c) put8(pG, T.l_g, TP, (nxh * hh) / 8 + c, p, v + 8 * c);
+      } else {
+        tc::mbar_arrive(gfree);   // forward only: nothing of G is in use; the arrive only paces the aux warps
       }
       SC[(S_Q0 + hh) * TP + p] = ssq;
     }
@@ -836,6 +932,7 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
         stage_signal<false>(sid++);   // S7
       }
       stage_wait(bar1, ph1);   // wgrad fx1 done: BIG (hidden activations) may be overwritten
+      if constexpr (mlp) tc::mbar_arrive(gfree);   // ... and G is idle until the next x head: the aux warps may stage their operands
       {
         // ReLU mask on dL/dh -> operand of the fx0 weight gradient and of the first-layer dgrad (both MMAs of stage S8)
         const float inv = INV[I_XD];
@@ -932,6 +1029,7 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
             }
           }
         }
+        tc::mbar_arrive(gfree);   // closed-form physics: this was the last read of G
         epi_sync();
         SC[(S_Q0 + hh) * TP + p] = s0;
         float* Q2 = RED;  // second component, [2][TP]
@@ -943,6 +1041,9 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
           if (P.nz_x > 1) dzx[TP + tid] = (Q2[tid] + Q2[TP + tid]) * cx;
         }
       }
+      // the first layers of the NEXT tile may go now (C_H and C_X have been read for the last time in this tile): they
+      // queue behind this tile's last weight gradients and are complete when the next tile starts
+      if (rb + gridDim.x < P.n_rowblocks) stage_signal<false>(sid++);   // S0 of tile it + 1
       stage_wait(bar1, ph1);   // dgrad + wgrad fx0 done: BIG and the record buffer are free for the next tile
       if (hh == 0) {
         // total dL/d(zc|zy): reversed + scaled gradient of the data-driven decoder (utils/transforms.py:207-219)
@@ -953,9 +1054,8 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
         float* dz = P.dzrec + (long long)rb * (nzd + P.nz_x) * TP;
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          if (k < nzd) dz[k * TP + p] = fmaf(g1[k], sc, (k < P.nz_c ? awc : awy) * DZA[k * TP + p]);
+          if (k < nzd) dz[k * TP + p] = fmaf(g1[k], sc, (k < P.nz_c ? awc : awy) * DZA[((it & 1) * nzd + k) * TP + p]);
       }
-      epi_sync();
       TPHASE(TPH_BWD4);
 
     }
@@ -969,7 +1069,7 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
       if (pow2) {
         // n consecutive pairs of a row sit in n consecutive lanes: segmented butterfly over the warp (fixed order)
         if (tid < TP) {
-          rx = SC[S_RX * TP + tid]; rc = SC[S_RC * TP + tid]; ry = SC[S_RY * TP + tid];
+          rx = SC[S_RX * TP + tid]; rc = SCA[((it & 1) * 2 + 0) * TP + tid]; ry = SCA[((it & 1) * 2 + 1) * TP + tid];
           for (int off = n >> 1; off > 0; off >>= 1) {
             rx += __shfl_xor_sync(0xffffffffu, rx, off);
             rc += __shfl_xor_sync(0xffffffffu, rc, off);
@@ -981,8 +1081,8 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
         r = tid;
         for (int m = 0; m < n; ++m) {
           rx += SC[S_RX * TP + r * n + m];
-          rc += SC[S_RC * TP + r * n + m];
-          ry += SC[S_RY * TP + r * n + m];
+          rc += SCA[((it & 1) * 2 + 0) * TP + r * n + m];
+          ry += SCA[((it & 1) * 2 + 1) * TP + r * n + m];
         }
       }
       if (r >= 0) {
@@ -994,32 +1094,76 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
           float* o = P.out.row_loss + row0 + r;
           o[0] = loss; o[B] = kl; o[2 * B] = rx; o[3 * B] = rc; o[4 * B] = ry; o[5 * B] = 0.0f;
         }
-        SC[S_Q0 * TP + r] = loss; SC[S_Q1 * TP + r] = kl;
-        SC[S_KL * TP + r] = rx; SC[S_KL2 * TP + r] = rc; SC[S_W * TP + r] = ry;
+        // running sums of the row slot this thread owns (fixed thread <-> slot map: deterministic), added up over the
+        // threads in a fixed order at the end of the kernel
+        tot[0] += loss; tot[1] += kl; tot[2] += rx; tot[3] += rc; tot[4] += ry;
       }
     }
-    epi_sync();
-    if (tid == 0) {
-      for (int r = 0; r < nrows; ++r) {
-        tot[0] += SC[S_Q0 * TP + r];
-        tot[1] += SC[S_Q1 * TP + r];
-        tot[2] += SC[S_KL * TP + r];
-        tot[3] += SC[S_KL2 * TP + r];
-        tot[4] += SC[S_W * TP + r];
-      }
-    }
-    epi_sync();
     wacc = 1u;
     TPHASE(TPH_ROWOUT);
   }  // tiles
 
+  }  // roles
+  // ---- end of kernel --------------------------------------------------------------------------------------------
+  // every role is through with its last tile (the reduction scratch R0 aliases the BIG operand buffer)
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+    // ---- end of kernel: head-bias sums to the reduction scratch, masked reductions S -> dW0 / db0 / dW1 ----------------
+  if (warp > 8 && P.with_grad) {
+    const int ap = tid - NTHR;
+    constexpr uint32_t tbu = 0u;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        R0[TNT * 32 + (0 * TP + ap) * 4 + i] = dbc[i];
+        R0[TNT * 32 + (1 * TP + ap) * 4 + i] = dby[i];
+      }
+      tc::fence_after_sync();
+      {
+        // M = 64 accumulator row u lives in tensor-memory lane 32 (u / 16) + u % 16: this warp's quadrant holds units
+        // 16 (warp % 4) .. + 15 of each side in its lanes 0 .. 15 (the tensor-memory loads are warp-wide)
+        const int qq = warp & 3, kk = 16 * qq + (lane & 15);
+        const bool own = lane < 16;
+        const uint32_t tl = tbu + ((uint32_t)(32 * qq) << 16);
+        for (int s = 0; s < 2; ++s) {
+          const Mlp2S& M = s ? P.dy : P.dc;
+          const int nzk = s ? P.nz_y : P.nz_c, nd = s ? P.nd_y : P.nd_c;
+          const float awt = s ? awy : awc;
+          float S[NAUX];
+          tc::tmem_ld8(tl + C_AS + NAUX * s, S);
+          tc::tmem_ld8(tl + C_AS + NAUX * s + 8, S + 8);
+          tc::tmem_ld8(tl + C_AS + NAUX * s + 16, S + 16);
+          float w0e[5], w1[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) w0e[i] = i < nzk ? prm[M.g_w0 + (long long)kk * nzk + i] : 0.0f;
+          w0e[4] = prm[M.g_b0 + kk];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int o = (j & 1) < nd ? ((j >> 1) * nd + (j & 1)) : -1;
+            w1[j] = o >= 0 ? prm[M.g_w1 + (long long)o * 64 + kk] : 0.0f;
+            if (o >= 0 && own) {
+              float a = 0.0f;
+#pragma unroll
+              for (int i = 0; i < 5; ++i) a = fmaf(w0e[i], S[5 * j + i], a);
+              part[M.g_w1 + (long long)o * 64 + kk] = a * awt;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 5; ++i) {
+            float a = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) a = fmaf(w1[j], S[5 * j + i], a);
+            if (i < nzk && own) part[M.g_w0 + (long long)kk * nzk + i] = a * awt;
+            if (i == 4 && own) part[M.g_b0 + kk] = a * awt;
+          }
+        }
+      }
+    }
+  if (warp < 8) {
   // ---- end of kernel: loss sums, weight gradients out of TMEM, bias / log_sigma_x sums ---------------------
-  if (tid == 0)
-    for (int k = 0; k < 6; ++k) part[P.n_params + k] = tot[k];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) R0[TNT * 39 + k * TNT + tid] = tot[k];
   if (P.with_grad && !P.latent_only) {
-    tc::fence_before_sync();
-    epi_sync();
-    tc::fence_after_sync();
     const int k = p;  // TMEM lane = hidden unit of the 128-wide layers
     // fx1: dW[n][k] (nd_x x 128)
     {
@@ -1030,11 +1174,9 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
       for (int i = 0; i < nxh; ++i) part[P.fx.g_w1 + (long long)(nxh * hh + i) * 128 + k] = v[i] * sc;
     }
     {
-      float v0[16], va1[16], va0[16];
-      tc::tmem_ld16(trow + C_W0, v0);
-      tc::tmem_ld16(trow + C_AW1, va1);
-      tc::tmem_ld16(trow + C_AW0, va0);
       if (hh == 0) {
+        float v0[16];
+        tc::tmem_ld16(trow + C_W0, v0);
         // fx0: dW[k][j] (128 x nzd), bias from the constant-one column; the decoder's own weights see the
         // un-reversed gradient (utils/transforms.py:207-219 reverses only d/dz)
         const float sc = exp2f(-(float)E_LAT) * cx;
@@ -1043,32 +1185,25 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
           if (j < nzd) part[P.fx.g_w0 + (long long)k * nzd + j] = v0[j] * sc;
           if (j == c1) part[P.fx.g_b0 + k] = v0[j] * sc;
         }
-      } else {
-        // aux decoders: hidden unit k of side (k >> 6); heads in columns 4 side + {mean_0, mean_1, ls_0, ls_1}
-        const int side = k >> 6, kk = k & 63;
-        const Mlp2S& M = side ? P.dy : P.dc;
-        const float aw = side ? awy : awc;
-        const int nzk = side ? P.nz_y : P.nz_c, j0 = side ? P.nz_c : 0, nd = side ? P.nd_y : P.nd_c;
-        const float s1 = exp2f(-(float)E_H) * aw, s0 = exp2f(-(float)E_LAT) * aw;
-#pragma unroll
-        for (int col = 0; col < 16; ++col) {
-          const int jj = col & 3;
-          if ((col >> 2) == side && (jj & 1) < nd) part[M.g_w1 + (long long)((jj >> 1) * nd + (jj & 1)) * 64 + kk] = va1[col] * s1;
-          const int j = col - j0;
-          if (j >= 0 && j < nzk) part[M.g_w0 + (long long)kk * nzk + j] = va0[col] * s0;
-          if (col == c1) part[M.g_b0 + kk] = va0[col] * s0;
-        }
       }
     }
     // per-thread running sums -> fixed-order sums over the 128 pair slots of each column, two levels deep
     // (4 pair groups of 32 per column, then the 4 partials) so that no thread walks a 128-long dependent chain
-    epi_sync();
 #pragma unroll
     for (int i = 0; i < 32; ++i) R0[tid * 32 + i] = dbx[i];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) R0[TNT * 32 + tid * 4 + i] = dba[i];
     R0[TNT * 36 + tid] = dlsx;
-    epi_sync();
+  }
+  }  // x-path epilogue warps: first half of the flush
+  tc::fence_before_sync();
+  __syncthreads();   // the running sums of every role are in the scratch
+  if (tid < 5) {
+    // loss scalars of this CTA: loss, KL, R_x, R_c, R_y summed over the row slots in thread order
+    const float* src = R0 + TNT * 39 + tid * TNT;
+    float a4[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < TNT; j += 4) { a4[0] += src[j]; a4[1] += src[j + 1]; a4[2] += src[j + 2]; a4[3] += src[j + 3]; }
+    part[P.n_params + tid] = (a4[0] + a4[1]) + (a4[2] + a4[3]);
+  }
+  if (warp < 8 && P.with_grad && !P.latent_only) {
     float* R1 = R0 + TNT * 37;   // partials [4 groups][ndx + 8 + 1]
     {
       const int col = tid & 63, grp = tid >> 6;   // 64 columns x 4 pair groups
@@ -1105,7 +1240,6 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
     }
     if (tid == 96) part[P.g_lsx] = (R1[72] + R1[80 + 72]) + (R1[160 + 72] + R1[240 + 72]);
   }
-  }  // epilogue warps
   if (warp < 8) TPHASE(TPH_FLUSH);
   if (PROF && tid == 0)
 #pragma unroll
@@ -1117,7 +1251,7 @@ __global__ void __launch_bounds__(NTHR, 1) dec_tc_kernel(const __grid_constant__
 
 template <bool PROF, int PHYS, int NDX>
 static void launch_one(const TcParams& p, int grid, cudaStream_t s) {
-  launch_pdl(dec_tc_kernel<PROF, PHYS, NDX>, grid, NTHR, (size_t)p.total, s, p);
+  launch_pdl(dec_tc_kernel<PROF, PHYS, NDX>, grid, NALL, (size_t)p.total, s, p);
 }
 
 // supported (physics kind, nd_x) pairs: (MLP, 64) bridge, (mass_spring, 64) damped_oscillator, (beam, 32) simple_beam,

@@ -423,7 +423,7 @@ __global__ void __launch_bounds__(ENT, 1) enc_tc_bwd_kernel(const __grid_constan
   const int ch1 = Hc - 128;                       // first hidden column of the second (overlapping) chunk
   const uint32_t C_GH = 0, C_W1 = (uint32_t)Hc, C_W0 = C_W1 + (uint32_t)(nchunk * Oc);
   uint32_t phase = 0, hphase = 0;
-  const float sgp = exp2f((float)P.e_g);
+  int e_g = P.e_g;   // refined below once lat_bwd's measured maximum is visible
   const float inv1d = exp2f(-(float)k_w1);
   const float s_x = exp2f((float)E_X);
   unsigned char* pX = smb + P.ab_x;
@@ -489,6 +489,14 @@ __global__ void __launch_bounds__(ENT, 1) enc_tc_bwd_kernel(const __grid_constan
   pdl_wait();
   // lat_bwd is complete from here on: the prior-net backward kernel (independent of this one) may run alongside
   pdl_launch_dependents();
+  if (P.gpre_max != nullptr) {
+    // operand scale from the measured max |gpre| of this batch: the largest head gradient lands in [2^11, 2^12) -- five
+    // binades of headroom for the dgrad through the head weights, whatever the magnitude of the gradients (a fixed
+    // scale saturates when a few rows carry very large gradients, e.g. heads pinned at their clamp bounds)
+    const uint32_t gb = __ldcg(P.gpre_max);
+    if (gb != 0u) e_g = max(-100, min(11 - ((int)((gb >> 23) & 0xFFu) - 127), 100));
+  }
+  const float sgp = exp2f((float)e_g);
   fetch_in(blockIdx.x);
 
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -602,7 +610,7 @@ __global__ void __launch_bounds__(ENT, 1) enc_tc_bwd_kernel(const __grid_constan
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
-  const float sc1 = exp2f(-(float)(E_HID + P.e_g)), sc0 = exp2f(-(float)(E_X + P.e_g));
+  const float sc1 = exp2f(-(float)(E_HID + e_g)), sc0 = exp2f(-(float)(E_X + e_g));
   for (int ck = 0; ck < nchunk; ++ck) {
     const int k = (ck ? ch1 : 0) + p;                        // hidden column held by this TMEM lane
     const bool mine = nchunk == 1 || (ck == 0 ? k < 128 : k >= 128);   // the overlap is taken from chunk 0
@@ -648,7 +656,7 @@ __global__ void __launch_bounds__(ENT, 1) enc_tc_bwd_kernel(const __grid_constan
     if (u >= 0 && i < 32) {
       float s = 0.0f;
       for (int j = 0; j < TP; ++j) s += R0[(h2 * TP + j) * 32 + i];
-      part[P.g_b1[u] + l] = s * exp2f(-(float)P.e_g);
+      part[P.g_b1[u] + l] = s * exp2f(-(float)e_g);
     }
   }
   tc::fence_before_sync();

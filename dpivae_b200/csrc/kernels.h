@@ -101,6 +101,7 @@ struct DecParams {
   float* dzrec;            // [tiles][nz_c + nz_y + nz_x][128]: dL/dz per pair
   float* epsbuf;           // [tiles][Z][128]: reparameterisation noise
   float* rowkl;            // [B]: per-row KL (MC mean)
+  unsigned int* gpre_max;  // bits of max |gpre| over the encoder heads of the batch (lat_bwd -> enc_tc_bwd operand scale), or nullptr
   // decode-only calls (DPIVAE.decode, models/vae.py:153-158): user latents (n, B, .) replace the encoder's
   const float *zin_x, *zin_c, *zin_y;
 };
@@ -117,10 +118,10 @@ struct TcParams {
   int KZ, c_ones, c_s0;      // latent operand: columns, constant-one column, first physics-input column
   int w_fx0, w_fx1, w_p[4];  // weight operands (hi plane), lo plane at + l_*
   int l_fx0, l_fx1, l_p[4];
-  int a_big, a_g, a_oa, l_big, l_g, l_oa;   // activation / gradient operands
+  int a_big, a_g, l_big, l_g;   // activation / gradient operands (the auxiliary decoders' mask / product operands alias a_g)
   int a_rec, rec_buf;        // two tile-record buffers of rec_buf bytes each
   int f_inv, f_bias_x, f_bias_p1, f_bias_p2, f_aw0, f_ab0, f_aw1, f_ab1, f_w0f, f_wp0f;
-  int f_dza, f_sc, f_red;
+  int f_dza, f_sc, f_sca, f_red;   // f_dza: [2][nz_c + nz_y][128] aux dL/dz, f_sca: [2][2][128] aux R_c / R_y (double-buffered by tile parity)
   int o_bar;
   int total;
 };
@@ -183,7 +184,8 @@ struct EncTcParams {
   const float* gpre;
   float* part;
   long long part_stride;
-  int e_g;                 // gpre is scaled by 2^e_g before the fp16 split
+  int e_g;                 // gpre is scaled by 2^e_g before the fp16 split (static estimate from the batch size) ...
+  const unsigned int* gpre_max;   // ... unless lat_bwd_kernel measured max |gpre| of this batch: then 2^e_g max = 2^11
   int wb_1, lb_1, ab_h, ab_g, lb_g, ab_x, lb_x, fb_red, fb_orow, ob_bar, total_b;
 };
 void launch_enc_tc_bwd(const EncTcParams& p, int grid, cudaStream_t s);

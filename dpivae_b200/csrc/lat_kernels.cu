@@ -353,6 +353,7 @@ __global__ void __launch_bounds__(LNT) lat_bwd_kernel(const __grid_constant__ De
   const int n = D::n_mc(P), RB = D::RB(P), nzd = D::nz_c(P) + D::nz_y(P);
   const long long B = P.B;
   const float wpair = 1.0f / ((float)P.Bg * (float)(P.nd_x + D::nd_c(P) + D::nd_y(P)) * (float)n);
+  float gmax = 0.0f;
   // Persistent CTA over tiles; the two per-tile records (noise, dL/dz: 10 KB) of the NEXT tile are bulk-copied
   // (cp.async.bulk + mbarrier) while the current one is processed -- the one-tile-per-CTA version spent half of its
   // time waiting for these loads and for the barrier behind them.
@@ -466,7 +467,9 @@ __global__ void __launch_bounds__(LNT) lat_bwd_kernel(const __grid_constant__ De
       const long long lrow = row0 + r;
       const int b = block_of_l<D>(P, i), il = i - D::blk_start(P, b), nzb = D::blk_size(P, b);
       const long long om = (long long)(D::henc(P, b) + il) * B + lrow;
-      P.gpre[om] = S.ROWMSK[(D::rp_loc(P) + i) * RBMAX + r] * S.ROWACC[(D::f_loc(P) + i) * RBMAX + r];
+      const float gm_ = S.ROWMSK[(D::rp_loc(P) + i) * RBMAX + r] * S.ROWACC[(D::f_loc(P) + i) * RBMAX + r];
+      P.gpre[om] = gm_;
+      gmax = fmaxf(gmax, fabsf(gm_));
       for (int j = 0; j < nzb; ++j) {
         const long long oc = (long long)(D::henc(P, b) + 2 * nzb + il * nzb + j) * B + lrow;
         float g = 0.0f;
@@ -475,10 +478,13 @@ __global__ void __launch_bounds__(LNT) lat_bwd_kernel(const __grid_constant__ De
           g = S.ROWMSK[(D::rp_L(P) + li) * RBMAX + r] * S.ROWACC[(D::f_L(P) + li) * RBMAX + r];
         }
         P.gpre[oc] = g;
+        gmax = fmaxf(gmax, fabsf(g));
       }
       const long long os = (long long)(D::henc(P, b) + nzb + il) * B + lrow;
       const int ld = D::blk_loff(P, b) + il * (il + 1) / 2 + il;
-      P.gpre[os] = S.ROWMSK[(D::rp_L(P) + ld) * RBMAX + r] * S.ROWACC[(D::f_L(P) + ld) * RBMAX + r];
+      const float gs_ = S.ROWMSK[(D::rp_L(P) + ld) * RBMAX + r] * S.ROWACC[(D::f_L(P) + ld) * RBMAX + r];
+      P.gpre[os] = gs_;
+      gmax = fmaxf(gmax, fabsf(gs_));
     }
   }
   for (int e = tid; e < RB * nzd; e += LNT) {
@@ -495,6 +501,13 @@ __global__ void __launch_bounds__(LNT) lat_bwd_kernel(const __grid_constant__ De
   }
   __syncthreads();   // every buffer of this tile is free again
   }  // tiles
+  // largest |gradient of an encoder-head pre-activation| of the batch: the tensor-core encoder backward scales its
+  // fp16 operand from it (order-independent maximum of non-negative floats: deterministic)
+  if (P.gpre_max != nullptr) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, off));
+    if (lane == 0 && gmax > 0.0f && gmax < __int_as_float(0x7f800000)) atomicMax(P.gpre_max, __float_as_uint(gmax));
+  }
 }
 
 // Encode-only inference (models/vae.py:161-162, 125-151): one thread per (MC sample, row) pair, head pre-activations read

@@ -96,6 +96,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+// plain arrive (release at CTA scope): pairs with the acquire of mbar_wait on the waiting side
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // transaction-count arrive + 1-D bulk async copy global -> shared (TMA engine, completes on `bar`)
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -460,6 +465,27 @@ __device__ __forceinline__ void issue_wgrad_w(uint32_t el, uint32_t d_tmem, Op h
       accumulate = 1;
       hlo += 16u;
       glo += 16u;
+    }
+  }
+}
+
+// Masked weight gradient, M = 64: D[64 units][N] (+)= sum over R pair rows of A[r][unit] * (B_hi[r][n] + B_lo[r][n]).
+// A is an EXACT fp16 plane (0 / 1 ReLU masks: no lo plane, two terms instead of three), both operands MN-major X8
+// buffers with R rows.  An M = 64 accumulator row u sits in tensor-memory lane 32 (u / 16) + u % 16
+// (tools/microbench/tc_m64_probe.cu).
+__device__ __forceinline__ void issue_mask_wgrad64_w(uint32_t el, uint32_t d_tmem, uint32_t a_base, uint32_t b_base, uint32_t b_lo_off,
+                                                     int R, int N, uint32_t accumulate) {
+  const uint32_t idesc = make_idesc(64, N, 1, 1);
+  const uint32_t hi = (uint32_t)R | DESC_VERSION_HI;   // MN-major: SBO = R * 16 B, LBO = 128 B
+  const int ks = R >> 4;
+  for (int t = 0; t < 2; ++t) {
+    uint32_t alo = ((a_base >> 4) & 0x3FFFu) | (8u << 16);
+    uint32_t blo = (((b_base + (t == 1 ? b_lo_off : 0u)) >> 4) & 0x3FFFu) | (8u << 16);
+    for (int k = 0; k < ks; ++k) {
+      mma_f16_w(el, d_tmem, pack64(alo, hi), pack64(blo, hi), idesc, accumulate);
+      accumulate = 1;
+      alo += 16u;
+      blo += 16u;
     }
   }
 }

@@ -56,6 +56,7 @@ def main():
         print(f"  {nme:12s} {100.0 * c_ / tot:5.1f}%  {c_ / nchunks:9.0f} cyc/chunk")
     if math != "fp32":
         print(f"  MMA-issue warp: waiting for stage signals {v[20] / nchunks:9.0f} cyc/tile, issuing {v[21] / nchunks:9.0f} cyc/tile")
+        print(f"  aux-decoder warps: waiting (records, operand-buffer hand-overs) {v[22] / nchunks:9.0f} cyc/tile, working {v[23] / nchunks:9.0f} cyc/tile")
 
 
 if __name__ == "__main__":
