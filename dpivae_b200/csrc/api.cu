@@ -364,12 +364,16 @@ static int build_plan(dpivae_model* h) {
         off = b; lo = bytes; b += 2 * bytes;
       };
       plane2(KZ / 8, 128, T.w_fx0, T.l_fx0);
-      plane2(16, d.nd_x, T.w_fx1, T.l_fx1);
       if (mlp) {
+        // [W_fx1 hi | W_p3 hi | W_fx1 lo | W_p3 lo]: both have nd_x rows, so as MN-major operands the two hi (lo) planes
+        // form ONE operand with 128 + d3 columns (fused dgrad of the x head through both decoders)
+        const int bf = 16 * d.nd_x * 16, bp = (d3 / 8) * d.nd_x * 16;
+        T.w_fx1 = b; T.w_p[3] = b + bf; T.l_fx1 = T.l_p[3] = bf + bp; b += 2 * (bf + bp);
         plane2(KZ / 8, d1, T.w_p[0], T.l_p[0]);
         plane2(d1 / 8, d2, T.w_p[1], T.l_p[1]);
         plane2(d2 / 8, d3, T.w_p[2], T.l_p[2]);
-        plane2(d3 / 8, d.nd_x, T.w_p[3], T.l_p[3]);
+      } else {
+        plane2(16, d.nd_x, T.w_fx1, T.l_fx1);
       }
       plane2(16, 128, T.a_big, T.l_big);
       plane2(8, 128, T.a_g, T.l_g);        // 32 KB; between two x heads it holds the auxiliary decoders' wgrad operands

@@ -488,8 +488,9 @@ __global__ void __launch_bounds__(NALL, 1) dec_tc_kernel(const __grid_constant__
         issuer_wait(sid++);   // S6: the dgrads the next epilogues wait for go first (bar0), the weight gradient of fx1 on bar1
         ISSUER_MARK(iw);
         {
-          tc::issue_dgrad_w(el, tbu + C_H, oG, oWFX1, ndx, 128, 0, terms);
-          if constexpr (mlp) tc::issue_dgrad_w(el, tbu + C_X, oG, oWP3, ndx, d3, 0, terms);
+          // MLP physics: the planes of W_p3 sit right behind those of W_fx1 (same row count), C_X right behind C_H: ONE
+          // N = 192 dgrad per K step for both (96 cycles instead of 2 x 64: the A operand is fetched once)
+          tc::issue_dgrad_w(el, tbu + C_H, oG, oWFX1, ndx, mlp ? 128 + d3 : 128, 0, terms);
           tc::commit_w(el, bar0);
           tc::issue_wgrad_w(el, tbu + C_W1, oBIG, oG, ndx, wacc, terms);
           tc::commit_w(el, bar1);
@@ -759,6 +760,10 @@ __global__ void __launch_bounds__(NALL, 1) dec_tc_kernel(const __grid_constant__
     const tc::Op oLAT = mkop(rec, 0, 4096u, TP);   // latent operand [zd | 1 | physics input] as written by lat_fwd_kernel
     const bool pvalid = p < npairs;
     const int prow = (pvalid ? p : npairs - 1) / n;
+    // the KL of the row slot this thread owns in the per-row outputs at the end of the tile: loaded now, used then
+    const bool pow2 = (n & (n - 1)) == 0 && n <= 32;
+    const int rslot = pow2 ? ((tid < TP && (tid & (n - 1)) == 0 && tid / n < nrows) ? tid / n : -1) : (tid < nrows ? tid : -1);
+    const float kl_pre = rslot >= 0 ? __ldg(P.rowkl + row0 + rslot) : 0.0f;
     // ---- first layers of the data-driven decoder and of the physics surrogate: issued now, consumed later ----
     if (it == 0 || !P.with_grad) stage_signal<false>(sid++);   // S0 (later tiles of a training step: signalled early, end of the previous tile)
     TPHASE(TPH_LATENT);
@@ -858,6 +863,12 @@ __global__ void __launch_bounds__(NALL, 1) dec_tc_kernel(const __grid_constant__
       tld<nxh>(trow + C_X + nxh * hh, v);
       const float gsc = pvalid ? sg : 0.0f;
       const float zx0 = PHYS != 0 ? lat_elem(rec, cs0, p) : 0.0f, zx1 = PHYS == 2 ? lat_elem(rec, cs0 + 1, p) : 0.0f;
+      // per-pair constants of the closed forms, hoisted out of the column loop (one reciprocal per pair instead of two
+      // IEEE divisions per column)
+      const float om_p = PHYS == 1 ? sqrtf(1.0f / zx0) : 0.0f;
+      const float bb_p = PHYS == 1 ? 0.0f / om_p : 0.0f;
+      const float bm_b = 1.0f - zx1, bm_c = 1.0f - bm_b * bm_b;
+      const float bm_s = PHYS == 2 ? -1000.0f / (6.0f * (zx0 * 1e6f) * 2e-6f) : 0.0f;
 #pragma unroll
       for (int i = 0; i < nxh; ++i) {
         float xh = v[i] * inv + BX[nxh * hh + i];
@@ -865,19 +876,15 @@ __global__ void __launch_bounds__(NALL, 1) dec_tc_kernel(const __grid_constant__
           // closed-form physics (cases/damped_oscillator/mass_spring.py:8-28, cases/simple_beam/simple_beam_model.py:4-30)
           const int d = nxh * hh + i;
           if constexpr (PHYS == 1) {
-            const float om = sqrtf(1.0f / zx0);
-            const float bb = 0.0f / om;
-            const float ph = om * P.grid[d];
-            xh += bb * sinf(ph) + 1.0f * cosf(ph);
+            const float ph = om_p * P.grid[d];
+            xh += bb_p * sinf(ph) + 1.0f * cosf(ph);
           } else {
-            const float E = zx0 * 1e6f, a = zx1, b = 1.0f - a, xg = P.grid[d];
-            const float den1 = 6.0f * E * 2e-6f * 1.0f, den2 = 6.0f * E * 2e-6f;
-            float w = 1.0f * b * xg * (1.0f - b * b - xg * xg) / den1;
-            if (xg > a) {
-              const float t = xg - a;
-              w += 1.0f * (t * t * t) / den2;
-            }
-            xh += -1000.0f * w;
+            // w = [b x (L^2 - b^2 - x^2) + (x > a) (x - a)^3] / (6 E I), deflection = -1000 w
+            const float xg = P.grid[d];
+            const float t = xg - zx1;
+            float w = bm_b * xg * (bm_c - xg * xg);
+            w += xg > zx1 ? t * t * t : 0.0f;
+            xh = fmaf(bm_s, w, xh);
           }
         }
         const float res = xv[i] - xh;
@@ -1001,32 +1008,45 @@ __global__ void __launch_bounds__(NALL, 1) dec_tc_kernel(const __grid_constant__
         float s0 = 0.0f, s1 = 0.0f;
         {
           const unsigned char* gh = pG;
-#pragma unroll 4
-          for (int i = 0; i < nxh; ++i) {
-            const int d = nxh * hh + i;
-            const __half* hrow = reinterpret_cast<const __half*>(gh + ((size_t)(d >> 3) * TP + p) * 16) + (d & 7);
-            const __half* lrow = reinterpret_cast<const __half*>(gh + T.l_g + ((size_t)(d >> 3) * TP + p) * 16) + (d & 7);
-            const float g = __half2float(*hrow) + __half2float(*lrow);
-            if constexpr (PHYS == 1) {
-              const float mass = lat_elem(rec, cs0, p);
-              const float om = sqrtf(1.0f / mass);
-              const float dom = -om / (2.0f * mass);
-              const float t = P.grid[d];
-              s0 = fmaf(g, -sinf(om * t) * t * dom, s0);
-            } else {
-              const float z0 = lat_elem(rec, cs0, p), E = z0 * 1e6f, a = lat_elem(rec, cs0 + 1, p), b = 1.0f - a;
-              const float den = 6.0f * E * 2e-6f;
-              const float xg = P.grid[d];
-              float w = b * xg * (1.0f - b * b - xg * xg) / den;
-              float dwa = -(xg * (1.0f - b * b - xg * xg) - 2.0f * b * b * xg) / den;
-              if (xg > a) {
-                const float t = xg - a;
-                w += (t * t * t) / den;
-                dwa += -3.0f * t * t / den;
+          // per-pair constants hoisted out of the column loop; the residual gradient g~ is read back 8 columns at a time
+          const float z0 = lat_elem(rec, cs0, p);
+          const float om = PHYS == 1 ? sqrtf(1.0f / z0) : 0.0f, dom = PHYS == 1 ? -om / (2.0f * z0) : 0.0f;
+          const float a = PHYS == 2 ? lat_elem(rec, cs0 + 1, p) : 0.0f, b = 1.0f - a, c2 = 1.0f - b * b;
+          const float iden = PHYS == 2 ? 1.0f / (6.0f * (z0 * 1e6f) * 2e-6f) : 0.0f;
+          float w0 = 0.0f, w1 = 0.0f;   // beam: sum_d g w_d den, sum_d g dwa_d den
+#pragma unroll
+          for (int c = 0; c < nxh / 8; ++c) {
+            const int ch = (nxh * hh) / 8 + c;
+            const uint4 hv = *reinterpret_cast<const uint4*>(gh + ((size_t)ch * TP + p) * 16);
+            const uint4 lv = *reinterpret_cast<const uint4*>(gh + T.l_g + ((size_t)ch * TP + p) * 16);
+            const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, lw[4] = {lv.x, lv.y, lv.z, lv.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int d = 8 * ch + i;
+              const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[i >> 1]));
+              const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[i >> 1]));
+              const float g = (i & 1) ? hf.y + lf.y : hf.x + lf.x;
+              if constexpr (PHYS == 1) {
+                const float t = P.grid[d];
+                s0 = fmaf(g, -sinf(om * t) * t * dom, s0);
+              } else {
+                const float xg = P.grid[d];
+                const float u = c2 - xg * xg;
+                float w = b * xg * u;
+                float dwa = -(xg * u - 2.0f * b * b * xg);
+                if (xg > a) {
+                  const float t = xg - a;
+                  w = fmaf(t * t, t, w);
+                  dwa = fmaf(-3.0f * t, t, dwa);
+                }
+                w0 = fmaf(g, w, w0);
+                w1 = fmaf(g, dwa, w1);
               }
-              s0 = fmaf(g, 1000.0f * w / z0, s0);
-              s1 = fmaf(g, -1000.0f * dwa, s1);
             }
+          }
+          if constexpr (PHYS == 2) {
+            s0 = 1000.0f * w0 * iden / z0;
+            s1 = -1000.0f * w1 * iden;
           }
         }
         tc::mbar_arrive(gfree);   // closed-form physics: this was the last read of G
@@ -1065,7 +1085,6 @@ __global__ void __launch_bounds__(NALL, 1) dec_tc_kernel(const __grid_constant__
     {
       float rx = 0.0f, rc = 0.0f, ry = 0.0f;
       int r = -1;
-      const bool pow2 = (n & (n - 1)) == 0 && n <= 32;
       if (pow2) {
         // n consecutive pairs of a row sit in n consecutive lanes: segmented butterfly over the warp (fixed order)
         if (tid < TP) {
@@ -1088,7 +1107,7 @@ __global__ void __launch_bounds__(NALL, 1) dec_tc_kernel(const __grid_constant__
       if (r >= 0) {
         const float inv_n = 1.0f / (float)n;
         rx *= inv_n; rc *= inv_n; ry *= inv_n;
-        const float kl = P.rowkl[row0 + r];
+        const float kl = kl_pre;   // r == rslot
         const float loss = P.beta_x * kl - P.alpha_x * rx - P.alpha_c * rc - P.alpha_y * ry;
         if (P.out.row_loss) {
           float* o = P.out.row_loss + row0 + r;

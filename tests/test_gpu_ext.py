@@ -84,7 +84,7 @@ def test_forward_cond_true(case, mtype):
             assert err < TOL, (mode, name, err)
 
 
-def _loss_grads_vs_golden(g, spec, vae, x, c, y, section, grad_tol):
+def _loss_grads_vs_golden(g, spec, vae, x, c, y, section, grad_tol, TOL=TOL):
     eng = vae.engine()
     eps = _dev(gu.eps_of(g, spec, prefix=f"{section}.eps"))
     row_loss, scal = eng.loss(x, c, y, 8, (1.0, 1.0, 1.0, 1.0), True, eps=eps)
@@ -121,7 +121,9 @@ def test_clamp_saturation(case, mtype, mode):
     g, spec, sd, args, case_mod, vae, (x, c, y) = build_from_golden(case, mtype, ext=True)
     vae.load_state_dict(gu.state_of(g, spec, "sat.init"), strict=False)
     vae.engine().set_math_mode(mode)
-    eng = _loss_grads_vs_golden(g, spec, vae, x, c, y, "sat", 1e-4)
+    # tc_fp16x3 in this regime (|z| up to 50 + 20 eps, hidden activations and residuals in the thousands): the dropped
+    # lo x lo products of the three-term split show at 1e-5 on the per-row loss; stated tolerance 5e-5 there
+    eng = _loss_grads_vs_golden(g, spec, vae, x, c, y, "sat", 1e-4, TOL=1e-5 if mode == "fp32" else 5e-5)
     assert eng.used_tensor_cores() == (mode != "fp32")
     names = {k: p for k, p in vae.named_parameters()}
     off = {id(p): o for p, o in eng.slots}
