@@ -480,7 +480,11 @@ def run_ensemble(a, wl, ctx):
 def rank_check(a, wl, case_mod, vae_factory, world, rank, dev, n, w):
     """N-rank correctness of the data-parallel step on hardware: two optimizer steps of one global
     batch, sharded over the ranks with the NCCL allreduce, against the same two steps of the WHOLE global batch on rank 0
-    alone.  Returns a dict (rank 0) with the gradient / parameter differences; raises if the ranks disagree bitwise."""
+    alone -- once with the fp32 kernels (sharding only changes the order of fp32 partial sums: 1e-6 on the allreduced
+    gradient) and once in the bench's arithmetic mode (tensor-core hi/lo split: tile composition and operand scales
+    follow the shard, stated tolerance 5e-5).  Parameters must be BITWISE equal across the ranks; against the 1-rank run
+    the Adam update is compared (relative L2 of p_after - p_before: Adam's m / sqrt(v) turns round-off on near-zero
+    gradients into O(lr) differences on those few elements, so the bar there is 1e-2)."""
     import torch
     import torch.distributed as dist
 
@@ -490,48 +494,57 @@ def rank_check(a, wl, case_mod, vae_factory, world, rank, dev, n, w):
     rows = min(wl["rows"], 16384)
     Bg = rows * world
     shards = [synth(case_mod, rows, 5000 + r, dev) for r in ([rank] if rank else range(world))]
-    mine = shards[0] if rank else shards[rank]
-    vae, args = vae_factory()
-    dp = DataParallelStep(vae, dpv.param_groups(args))
-    dp.eng.set_math_mode(a.math)
-    torch.manual_seed(4242)
+    mine = shards[0]
     gen = torch.cuda.default_generators[dev.index]
-    off0 = gen.get_offset()
-    for k in range(2):
-        dp.step(mine[0], mine[1], mine[2], n, w, Bg, rank * rows, k + 1)
-    grads_n = dp.eng.gradbuf.clone()
-    params_n = dp.eng.params.clone()
-    # every rank must hold bitwise identical parameters (same allreduced gradient, same fused Adam)
-    lo, hi = params_n.clone(), params_n.clone()
-    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
-    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-    if not torch.equal(lo, hi):
-        raise RuntimeError("data-parallel ranks hold different parameters after the allreduced Adam steps")
-    cks = torch.tensor([float(params_n.double().sum())], dtype=torch.float64, device=dev)
-    allck = [torch.zeros_like(cks) for _ in range(world)]
-    dist.all_gather(allck, cks)
-    res = None
-    if rank == 0:
-        vae1, args1 = vae_factory()
-        eng1 = vae1.engine()
-        eng1.set_groups(dpv.param_groups(args1))
-        eng1.set_math_mode(a.math)
-        gen.set_offset(off0)
-        X, C_, Y = (torch.cat([sh[i] for sh in shards]) for i in range(3))
+    out = {"ranks": world, "global_rows": Bg, "steps": 2, "modes": {}}
+    ok_all = True
+    for mode, gtol in (("fp32", 1e-6), (a.math, 5e-5)):
+        if mode in out["modes"]:
+            continue
+        vae, args = vae_factory()
+        dp = DataParallelStep(vae, dpv.param_groups(args))
+        dp.eng.set_math_mode(mode)
+        p0 = dp.eng.params.clone()
+        torch.manual_seed(4242)
+        off0 = gen.get_offset()
         for k in range(2):
-            eng1.loss(X, C_, Y, n, w, True, B_global=Bg, row_offset=0, adam_step=k + 1)
-        g1, p1 = eng1.gradbuf, eng1.params
-        gerr = float((grads_n.double() - g1.double()).norm() / g1.double().norm())
-        perr = float((params_n.double() - p1.double()).abs().max())
-        res = {"ranks": world, "global_rows": Bg, "steps": 2, "params_bitwise_equal_across_ranks": True,
-               "param_checksums": [float(t) for t in allck],
-               "grad_rel_l2_vs_1rank": gerr, "param_max_abs_diff_vs_1rank": perr,
-               "tolerance": {"grad_rel_l2": 1e-5, "param_max_abs": 1e-5}, "ok": bool(gerr < 1e-5 and perr < 1e-5)}
-        del eng1, vae1
-    del dp, vae
-    torch.cuda.empty_cache()
-    dist.barrier()
-    return res
+            dp.step(mine[0], mine[1], mine[2], n, w, Bg, rank * rows, k + 1)
+        grads_n = dp.eng.gradbuf.clone()
+        params_n = dp.eng.params.clone()
+        # every rank must hold bitwise identical parameters (same allreduced gradient, same fused Adam)
+        lo, hi = params_n.clone(), params_n.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        if not torch.equal(lo, hi):
+            raise RuntimeError("data-parallel ranks hold different parameters after the allreduced Adam steps")
+        cks = torch.tensor([float(params_n.double().sum())], dtype=torch.float64, device=dev)
+        allck = [torch.zeros_like(cks) for _ in range(world)]
+        dist.all_gather(allck, cks)
+        if rank == 0:
+            vae1, args1 = vae_factory()
+            eng1 = vae1.engine()
+            eng1.set_groups(dpv.param_groups(args1))
+            eng1.set_math_mode(mode)
+            gen.set_offset(off0)
+            X, C_, Y = (torch.cat([sh[i] for sh in shards]) for i in range(3))
+            for k in range(2):
+                eng1.loss(X, C_, Y, n, w, True, B_global=Bg, row_offset=0, adam_step=k + 1)
+            g1, p1 = eng1.gradbuf, eng1.params
+            gerr = float((grads_n.double() - g1.double()).norm() / g1.double().norm())
+            uerr = float(((params_n - p0).double() - (p1 - p0).double()).norm() / (p1 - p0).double().norm())
+            ok = bool(gerr < gtol and uerr < 1e-2)
+            ok_all = ok_all and ok
+            out["modes"][mode] = {"params_bitwise_equal_across_ranks": True, "param_checksums": [float(t) for t in allck],
+                                  "grad_rel_l2_vs_1rank": gerr, "adam_update_rel_l2_vs_1rank": uerr,
+                                  "tolerance": {"grad_rel_l2": gtol, "adam_update_rel_l2": 1e-2}, "ok": ok}
+            del eng1, vae1
+        else:
+            out["modes"][mode] = None
+        del dp, vae
+        torch.cuda.empty_cache()
+        dist.barrier()
+    out["ok"] = ok_all
+    return out if rank == 0 else None
 
 
 def run_train(a, wl, ctx, sub=False):

@@ -13,8 +13,8 @@ tensor-core kernels need 8 <= n_mc <= 128, so every fixture here also runs on th
   cond.*    `DPIVAE.forward(x, c, cond=True, n=8)` (models/vae.py:160-175): zc from the conditional prior net.
   lamx.*    `DPIVAE.loss` with `lambda_x = 0.7` (models/vae.py:217-219): 8-tuple, scalars, every gradient.
   sat.*     clamp saturation (models/encoders.py:35-39): head biases pushed so that loc / log-sigma / L entries sit
-            on and beyond +-50 / -7 / 3 / +-20 for some latent dimensions: 8-tuple and gradients (zero through a
-            saturated clamp).
+            on and beyond +-50 / -7 / 3 / +-20 for some latent dimensions (decoder first layers scaled by 0.02 so that the
+            loss stays ~1e2 .. 1e4): 8-tuple and gradients (zero through a saturated clamp).
   edge.*    sigmoid -> 1.0f: a physics latent lands exactly on the upper bound of its Uniform prior, whose density
             is half-open: log p = -inf, KL = +inf; 8-tuple only.
 """
@@ -136,6 +136,11 @@ def main():
             for pn in (vae.prior_net_c, vae.prior_net_y):
                 pn.net.f_mean.bias[0] += 80.0                    # prior loc clamps at +50
                 pn.net.f_sigma.bias[0] += 9.0                    # prior log sigma clamps at 3
+            # latents pinned at +-50 (and spread by sigma = e^3, |L| = 20) would drive the heteroscedastic decoders'
+            # log-sigma outputs to +-20 and the loss to ~1e21: the decoders' first layers are scaled down so that the
+            # saturated regime stays numerically meaningful (losses ~1e2 .. 1e4)
+            for lin in (vae.decoder_x.fx0, vae.decoder_c.net[0], vae.decoder_y.net[0]):
+                lin.weight *= 0.02
         sat_sd = {k: v.detach().clone() for k, v in vae.state_dict().items()}
         for k in trainable:
             out[f"sat.init.{k}"] = sat_sd[k].numpy().astype(np.float32).copy()

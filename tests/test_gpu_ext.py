@@ -84,7 +84,8 @@ def test_forward_cond_true(case, mtype):
             assert err < TOL, (mode, name, err)
 
 
-def _loss_grads_vs_golden(g, spec, vae, x, c, y, section, grad_tol, TOL=TOL):
+def _loss_grads_vs_golden(g, spec, vae, x, c, y, section, grad_tol, TOL=TOL, grads_ref=None):
+    """grads_ref: compare the gradients with these (fp64 oracle) instead of the reference's fp32 autograd values."""
     eng = vae.engine()
     eps = _dev(gu.eps_of(g, spec, prefix=f"{section}.eps"))
     row_loss, scal = eng.loss(x, c, y, 8, (1.0, 1.0, 1.0, 1.0), True, eps=eps)
@@ -98,10 +99,11 @@ def _loss_grads_vs_golden(g, spec, vae, x, c, y, section, grad_tol, TOL=TOL):
     names = {id(p): k for k, p in vae.named_parameters()}
     bad = {}
     for p, o in eng.slots:
-        err = gu.rel_l2(eng.grads[o:o + p.numel()].cpu(), g[f"{section}.grad.{names[id(p)]}"])
+        ref = g[f"{section}.grad.{names[id(p)]}"] if grads_ref is None else grads_ref[names[id(p)]]
+        err = gu.rel_l2(eng.grads[o:o + p.numel()].cpu(), ref)
         if err > grad_tol:
             bad[names[id(p)]] = err
-    assert not bad, (section, bad)
+    assert not bad, (section, sorted(bad.items(), key=lambda kv: -kv[1])[:6])
     return eng
 
 
@@ -117,13 +119,20 @@ def test_lambda_x_regulariser(case, mtype):
 @pytest.mark.parametrize("case,mtype", gu.EXT_CONFIGS)
 def test_clamp_saturation(case, mtype, mode):
     """models/encoders.py:35-39,123-124: heads on / beyond +-50, [-7, 3], +-20 -- values clamp, gradients through a
-    saturated clamp are exactly zero (reference tolerance 1e-4 on gradients here: tests/test_oracle_golden_ext.py)."""
+    saturated clamp are exactly zero.  Per-row losses and scalars against the reference's golden values; gradients
+    against the fp64 oracle (the reference's own fp32 gradients carry ~5e-4 of round-off noise in this regime, see
+    tests/test_oracle_golden_ext.py), 2e-5 per tensor in both modes."""
+    from oracle import dpivae_oracle as orc
+
     g, spec, sd, args, case_mod, vae, (x, c, y) = build_from_golden(case, mtype, ext=True)
-    vae.load_state_dict(gu.state_of(g, spec, "sat.init"), strict=False)
+    sat = gu.state_of(g, spec, "sat.init")
+    vae.load_state_dict(sat, strict=False)
     vae.engine().set_math_mode(mode)
-    # tc_fp16x3 in this regime (|z| up to 50 + 20 eps, hidden activations and residuals in the thousands): the dropped
-    # lo x lo products of the three-term split show at 1e-5 on the per-row loss; stated tolerance 5e-5 there
-    eng = _loss_grads_vs_golden(g, spec, vae, x, c, y, "sat", 1e-4, TOL=1e-5 if mode == "fp32" else 5e-5)
+    eps64 = gu.eps_of(g, spec, prefix="sat.eps")
+    eps64 = tuple(e.double() for e in eps64) if isinstance(eps64, tuple) else eps64.double()
+    _, _, _, o_grads = orc.loss_and_grads({k: v.double() for k, v in sat.items()}, orc.cast_spec(spec, torch.float64),
+                                          x.double(), c.double(), y.double(), eps64)
+    eng = _loss_grads_vs_golden(g, spec, vae, x, c, y, "sat", 2e-5, grads_ref=o_grads)
     assert eng.used_tensor_cores() == (mode != "fp32")
     names = {k: p for k, p in vae.named_parameters()}
     off = {id(p): o for p, o in eng.slots}
