@@ -124,7 +124,12 @@ __device__ __forceinline__ tc::Op mkop(const unsigned char* sm, int off, uint32_
 
 constexpr int NTHR = TNT + 32;    // 8 epilogue warps + 1 MMA-issue warp: participants of the stage-signal barriers
 constexpr int NAUXT = 128;        // 4 auxiliary-decoder warps (thread = pair)
-constexpr int NALL = NTHR + NAUXT;   // threads per CTA
+// Four warpgroups: 0, 1 = x-path epilogue (warps 0..7), 2 = auxiliary decoders (warps 8..11), 3 = MMA issue (warp 12; warps
+// 13..15 only take part in the CTA-wide barriers).  Registers are re-balanced per warpgroup with setmaxnreg: the launch
+// gives every thread 128, the epilogue warpgroups grow to R_MAIN, the other two shrink.
+constexpr int NALL = 512;
+constexpr int R_MAIN = 176, R_AUX = 104, R_ISSUE = 56;
+constexpr int W_ISSUE = 12;       // the MMA-issue warp
 // Warp-specialised MMA issue: the 256 epilogue threads only SIGNAL that the operands of stage `sid` are in place
 // (non-blocking bar.arrive on a rotating named barrier); the dedicated issue warp waits for the signal, issues the
 // MMAs and commits them to an mbarrier.  The epilogue warps never spend issue slots on descriptor arithmetic and never
@@ -192,7 +197,7 @@ __global__ void __launch_bounds__(NALL, 1) dec_tc_kernel(const __grid_constant__
   extern __shared__ __align__(1024) unsigned char smb[];
   float* smf = reinterpret_cast<float*>(smb);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int q = warp & 3, hh = (warp >> 2) & 1;   // warps 0..7: x-path epilogue, 8: MMA issue, 9..12: auxiliary decoders
+  const int q = warp & 3, hh = (warp >> 2) & 1;   // warps 0..7: x-path epilogue, 8..11: auxiliary decoders, 12: MMA issue
   const int p = 32 * q + lane;  // pair (TMEM lane) owned in the epilogues; hh = column half / aux side (0 = c, 1 = y)
   const int n = P.n_mc;
   const int nzd = P.nz_c + P.nz_y;
@@ -413,7 +418,10 @@ __global__ void __launch_bounds__(NALL, 1) dec_tc_kernel(const __grid_constant__
   // everything above read only the parameters and the targets; the tile records below come from lat_fwd (PDL)
   pdl_wait();
 
-  if (warp == 8) {
+  if (warp >= W_ISSUE) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R_ISSUE));
+  }
+  if (warp == W_ISSUE) {
     // ================= MMA-issue warp: mirrors the stage sequence of the epilogue warps =================================
     // all 32 lanes run the descriptor arithmetic (uniform datapath); MMAs / commits are predicated on the elected lane.
     // The tensor-memory base is a compile-time 0 here (one CTA per SM owning all 512 columns; checked below) and the
@@ -530,13 +538,26 @@ __global__ void __launch_bounds__(NALL, 1) dec_tc_kernel(const __grid_constant__
       atomicAdd(reinterpret_cast<unsigned long long*>(P.phase) + 20, (unsigned long long)iw);
       atomicAdd(reinterpret_cast<unsigned long long*>(P.phase) + 21, (unsigned long long)ii);
     }
-  } else if (warp > 8) {
+    tc::fence_before_sync();
+    __syncthreads();   // (A) every role is through with its last tile (the reduction scratch R0 aliases the BIG operand buffer)
+    tc::fence_after_sync();
+    tc::fence_before_sync();
+    __syncthreads();   // (B) the running sums of every role are in the scratch
+  } else if (warp > W_ISSUE) {
+    // idle warps of the issue warpgroup: CTA-wide barriers only
+    tc::fence_before_sync();
+    __syncthreads();   // (A) every role is through with its last tile (the reduction scratch R0 aliases the BIG operand buffer)
+    tc::fence_after_sync();
+    tc::fence_before_sync();
+    __syncthreads();   // (B) the running sums of every role are in the scratch
+  } else if (warp >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R_AUX));
     // ================= auxiliary-decoder warps (thread = pair): decoder_c then decoder_y of tile `it`, one tile ahead of
     // the x path.  Forward, Gaussian likelihood and dgrad in registers (packed fp32 pairs); the weight-gradient operands
     // (ReLU mask plane, head-gradient x input products) go into the idle G buffer and are reduced over the pairs by
     // M = 64 MMAs issued from here.
-    const int ap = tid - NTHR;
-    const int aw = warp - 9;
+    const int ap = tid - TNT;
+    const int aw = warp - 8;
     if (tb != 0u) __trap();
     constexpr uint32_t tbu = 0u;
     const uint32_t el = tc::elect_one();
@@ -734,7 +755,63 @@ __global__ void __launch_bounds__(NALL, 1) dec_tc_kernel(const __grid_constant__
       atomicAdd(reinterpret_cast<unsigned long long*>(P.phase) + 22, (unsigned long long)xw);
       atomicAdd(reinterpret_cast<unsigned long long*>(P.phase) + 23, (unsigned long long)xb);
     }
+    tc::fence_before_sync();
+    __syncthreads();   // (A) every role is through with its last tile (the reduction scratch R0 aliases the BIG operand buffer)
+    tc::fence_after_sync();
+    // ---- end of kernel: head-bias sums to the reduction scratch, masked reductions S -> dW0 / db0 / dW1 ----------------
+  if (P.with_grad) {
+    const int ap = tid - TNT;
+    constexpr uint32_t tbu = 0u;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        R0[TNT * 32 + (0 * TP + ap) * 4 + i] = dbc[i];
+        R0[TNT * 32 + (1 * TP + ap) * 4 + i] = dby[i];
+      }
+      tc::fence_after_sync();
+      {
+        // M = 64 accumulator row u lives in tensor-memory lane 32 (u / 16) + u % 16: this warp's quadrant holds units
+        // 16 (warp % 4) .. + 15 of each side in its lanes 0 .. 15 (the tensor-memory loads are warp-wide)
+        const int qq = warp & 3, kk = 16 * qq + (lane & 15);
+        const bool own = lane < 16;
+        const uint32_t tl = tbu + ((uint32_t)(32 * qq) << 16);
+        for (int s = 0; s < 2; ++s) {
+          const Mlp2S& M = s ? P.dy : P.dc;
+          const int nzk = s ? P.nz_y : P.nz_c, nd = s ? P.nd_y : P.nd_c;
+          const float awt = s ? awy : awc;
+          float S[NAUX];
+          tc::tmem_ld8(tl + C_AS + NAUX * s, S);
+          tc::tmem_ld8(tl + C_AS + NAUX * s + 8, S + 8);
+          tc::tmem_ld8(tl + C_AS + NAUX * s + 16, S + 16);
+          float w0e[5], w1[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) w0e[i] = i < nzk ? prm[M.g_w0 + (long long)kk * nzk + i] : 0.0f;
+          w0e[4] = prm[M.g_b0 + kk];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int o = (j & 1) < nd ? ((j >> 1) * nd + (j & 1)) : -1;
+            w1[j] = o >= 0 ? prm[M.g_w1 + (long long)o * 64 + kk] : 0.0f;
+            if (o >= 0 && own) {
+              float a = 0.0f;
+#pragma unroll
+              for (int i = 0; i < 5; ++i) a = fmaf(w0e[i], S[5 * j + i], a);
+              part[M.g_w1 + (long long)o * 64 + kk] = a * awt;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 5; ++i) {
+            float a = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) a = fmaf(w1[j], S[5 * j + i], a);
+            if (i < nzk && own) part[M.g_w0 + (long long)kk * nzk + i] = a * awt;
+            if (i == 4 && own) part[M.g_b0 + kk] = a * awt;
+          }
+        }
+      }
+    }
+    tc::fence_before_sync();
+    __syncthreads();   // (B) the running sums of every role are in the scratch
   } else {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R_MAIN));
   const uint32_t rec_bytes = (uint32_t)P.rec_stride;
   if (tid == 0 && (long long)blockIdx.x < P.n_rowblocks) {
     tc::mbar_expect_tx(rbar, rec_bytes);
@@ -1122,63 +1199,9 @@ __global__ void __launch_bounds__(NALL, 1) dec_tc_kernel(const __grid_constant__
     TPHASE(TPH_ROWOUT);
   }  // tiles
 
-  }  // roles
-  // ---- end of kernel --------------------------------------------------------------------------------------------
-  // every role is through with its last tile (the reduction scratch R0 aliases the BIG operand buffer)
-  tc::fence_before_sync();
-  __syncthreads();
-  tc::fence_after_sync();
-    // ---- end of kernel: head-bias sums to the reduction scratch, masked reductions S -> dW0 / db0 / dW1 ----------------
-  if (warp > 8 && P.with_grad) {
-    const int ap = tid - NTHR;
-    constexpr uint32_t tbu = 0u;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        R0[TNT * 32 + (0 * TP + ap) * 4 + i] = dbc[i];
-        R0[TNT * 32 + (1 * TP + ap) * 4 + i] = dby[i];
-      }
-      tc::fence_after_sync();
-      {
-        // M = 64 accumulator row u lives in tensor-memory lane 32 (u / 16) + u % 16: this warp's quadrant holds units
-        // 16 (warp % 4) .. + 15 of each side in its lanes 0 .. 15 (the tensor-memory loads are warp-wide)
-        const int qq = warp & 3, kk = 16 * qq + (lane & 15);
-        const bool own = lane < 16;
-        const uint32_t tl = tbu + ((uint32_t)(32 * qq) << 16);
-        for (int s = 0; s < 2; ++s) {
-          const Mlp2S& M = s ? P.dy : P.dc;
-          const int nzk = s ? P.nz_y : P.nz_c, nd = s ? P.nd_y : P.nd_c;
-          const float awt = s ? awy : awc;
-          float S[NAUX];
-          tc::tmem_ld8(tl + C_AS + NAUX * s, S);
-          tc::tmem_ld8(tl + C_AS + NAUX * s + 8, S + 8);
-          tc::tmem_ld8(tl + C_AS + NAUX * s + 16, S + 16);
-          float w0e[5], w1[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) w0e[i] = i < nzk ? prm[M.g_w0 + (long long)kk * nzk + i] : 0.0f;
-          w0e[4] = prm[M.g_b0 + kk];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int o = (j & 1) < nd ? ((j >> 1) * nd + (j & 1)) : -1;
-            w1[j] = o >= 0 ? prm[M.g_w1 + (long long)o * 64 + kk] : 0.0f;
-            if (o >= 0 && own) {
-              float a = 0.0f;
-#pragma unroll
-              for (int i = 0; i < 5; ++i) a = fmaf(w0e[i], S[5 * j + i], a);
-              part[M.g_w1 + (long long)o * 64 + kk] = a * awt;
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < 5; ++i) {
-            float a = 0.0f;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) a = fmaf(w1[j], S[5 * j + i], a);
-            if (i < nzk && own) part[M.g_w0 + (long long)kk * nzk + i] = a * awt;
-            if (i == 4 && own) part[M.g_b0 + kk] = a * awt;
-          }
-        }
-      }
-    }
-  if (warp < 8) {
+    tc::fence_before_sync();
+    __syncthreads();   // (A) every role is through with its last tile (the reduction scratch R0 aliases the BIG operand buffer)
+    tc::fence_after_sync();
   // ---- end of kernel: loss sums, weight gradients out of TMEM, bias / log_sigma_x sums ---------------------
 #pragma unroll
   for (int k = 0; k < 5; ++k) R0[TNT * 39 + k * TNT + tid] = tot[k];
@@ -1212,9 +1235,8 @@ __global__ void __launch_bounds__(NALL, 1) dec_tc_kernel(const __grid_constant__
     for (int i = 0; i < 32; ++i) R0[tid * 32 + i] = dbx[i];
     R0[TNT * 36 + tid] = dlsx;
   }
-  }  // x-path epilogue warps: first half of the flush
-  tc::fence_before_sync();
-  __syncthreads();   // the running sums of every role are in the scratch
+    tc::fence_before_sync();
+    __syncthreads();   // (B) the running sums of every role are in the scratch
   if (tid < 5) {
     // loss scalars of this CTA: loss, KL, R_x, R_c, R_y summed over the row slots in thread order
     const float* src = R0 + TNT * 39 + tid * TNT;
@@ -1222,7 +1244,7 @@ __global__ void __launch_bounds__(NALL, 1) dec_tc_kernel(const __grid_constant__
     for (int j = 0; j < TNT; j += 4) { a4[0] += src[j]; a4[1] += src[j + 1]; a4[2] += src[j + 2]; a4[3] += src[j + 3]; }
     part[P.n_params + tid] = (a4[0] + a4[1]) + (a4[2] + a4[3]);
   }
-  if (warp < 8 && P.with_grad && !P.latent_only) {
+  if (P.with_grad && !P.latent_only) {
     float* R1 = R0 + TNT * 37;   // partials [4 groups][ndx + 8 + 1]
     {
       const int col = tid & 63, grp = tid >> 6;   // 64 columns x 4 pair groups
@@ -1259,6 +1281,7 @@ __global__ void __launch_bounds__(NALL, 1) dec_tc_kernel(const __grid_constant__
     }
     if (tid == 96) part[P.g_lsx] = (R1[72] + R1[80 + 72]) + (R1[160 + 72] + R1[240 + 72]);
   }
+  }  // roles
   if (warp < 8) TPHASE(TPH_FLUSH);
   if (PROF && tid == 0)
 #pragma unroll
