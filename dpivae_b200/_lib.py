@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdpivae_b200.so")
+# DPIVAE_B200_LIB: load another build of the same ABI (A/B timing of kernel variants); never set in tests / bench runs
+LIB_PATH = os.environ.get("DPIVAE_B200_LIB") or os.path.join(HERE, "libdpivae_b200.so")
 
 MAX_ZX, MAX_ZCY, MAX_Z, MAX_NDX, MAX_NDCY, MAX_PHYS_LAYERS = 4, 8, 16, 64, 4, 6
 MODEL_P, MODEL_S = 0, 1
@@ -96,7 +97,7 @@ def load():
         return _lib
     from . import build as _build
 
-    if os.path.exists(os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")) or not os.path.exists(LIB_PATH):
+    if not os.environ.get("DPIVAE_B200_LIB") and (os.path.exists(os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")) or not os.path.exists(LIB_PATH)):
         try:
             _build.build_library()   # no-op unless a source is newer than the binary
         except Exception:

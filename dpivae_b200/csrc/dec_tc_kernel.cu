@@ -178,7 +178,7 @@ template <class G>
 __device__ void stage_weight(unsigned char* plane, uint32_t lo_off, int N, int KP, int kexp, G get) {
   const float s = exp2f((float)kexp);
   const int nch = KP >> 3;
-  for (int e = threadIdx.x; e < nch * N; e += TNT) {
+  for (int e = threadIdx.x; e < nch * N; e += NALL) {
     const int ch = e / N, n = e - ch * N;
     float v[8];
 #pragma unroll
@@ -188,6 +188,186 @@ __device__ void stage_weight(unsigned char* plane, uint32_t lo_off, int N, int K
 }
 
 }  // namespace
+
+// One-time set-up of a CTA (all 512 threads): zero shared memory, barriers, tensor-memory allocation, operand staging of
+// the weights (fp16 hi / lo planes, power-of-two scales from the block maxima), fp32 tables of the auxiliary decoders.
+// Deliberately NOT inlined: its register allocation stays apart from the role loops of the kernel (inlined, the values
+// live across it were spilled to local memory and reloaded inside the tile loop: +5 % kernel time).
+template <int PHYS, int NDX>
+static __device__ __noinline__ void dec_tc_setup(const TcParams& T, unsigned char* smb) {
+  const DecParams& P = T.d;
+  float* smf = reinterpret_cast<float*>(smb);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nzd = P.nz_c + P.nz_y;
+  const int nzin = P.nz_x + P.nd_p;
+  constexpr int ndx = NDX;
+  constexpr bool mlp = PHYS == 0;
+  const int d1 = mlp ? P.pl[0].N : 0, d2 = mlp ? P.pl[1].N : 0, d3 = mlp ? P.pl[2].N : 0;
+  float* part = P.part + (long long)blockIdx.x * P.part_stride;
+  float* INV = smf + (T.f_inv >> 2);
+  float* BX = smf + (T.f_bias_x >> 2);
+  float* BP1 = smf + (T.f_bias_p1 >> 2);
+  float* BP2 = smf + (T.f_bias_p2 >> 2);
+  float* AW0 = smf + (T.f_aw0 >> 2);
+  float* AB0 = smf + (T.f_ab0 >> 2);
+  float* AW1 = smf + (T.f_aw1 >> 2);
+  float* AB1 = smf + (T.f_ab1 >> 2);
+  float* WP0F = smf + (T.f_wp0f >> 2);
+  float* RED = smf + (T.f_red >> 2);
+  uint64_t* rbar = reinterpret_cast<uint64_t*>(smb + T.o_bar + 32);
+  uint64_t* bar0 = reinterpret_cast<uint64_t*>(smb + T.o_bar);
+  uint64_t* bar1 = bar0 + 1;
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(smb + T.o_bar + 16);
+  uint64_t* gfree = reinterpret_cast<uint64_t*>(smb + T.o_bar + 48);
+  uint64_t* adone = gfree + 1;
+  uint64_t* abar = gfree + 2;
+  // ---- one-time: zero smem, barriers, TMEM, weights -------------------------------------------------
+  for (int e = tid; e < (T.total >> 4); e += NALL) reinterpret_cast<uint4*>(smb)[e] = make_uint4(0u, 0u, 0u, 0u);   // T.total is a multiple of 128
+  __syncthreads();
+  if (tid == 0) {
+    tc::mbar_init(bar0, 1);
+    tc::mbar_init(bar1, 1);
+    tc::mbar_init(rbar, 1);
+    tc::mbar_init(rbar + 1, 1);
+    tc::mbar_init(gfree, TNT);
+    tc::mbar_init(adone, P.with_grad ? NAUXT + 1 : NAUXT);   // every aux thread + (training) the commit of its last MMAs
+    tc::mbar_init(abar, 1);
+    tc::mbar_fence_init();
+  }
+  __syncwarp();
+  if (warp == 0) tc::tmem_alloc(tptr, C_ALLOC);
+
+  const float* prm = P.params;
+  const int c1 = T.c_ones, cs0 = T.c_s0;
+  // Raw weights first: the data-driven decoder's [w0 | b0 | w1 | b1] block of the flat buffer and the frozen physics
+  // surrogate are copied ONCE with coalesced loads into the (still unused) operand buffers; the scale search and the
+  // operand staging read them from shared memory, and the scratch is zeroed again before the first tile.
+  float* FX = smf + (T.a_big >> 2);
+  const int n_fx = 128 * nzd + 128 + ndx * 128 + ndx;
+  const int n_fr = mlp ? (int)(P.pl[3].g_b + ndx) : 0;
+  float* FR = FX + ((n_fx + 3) & ~3);
+  {
+    const float* src = prm + P.fx.g_w0;
+    for (int e = tid; e < n_fx; e += NALL) FX[e] = src[e];
+    if constexpr (mlp)
+      for (int e = tid; e < n_fr; e += NALL) FR[e] = P.frozen[e];
+  }
+  __syncthreads();
+  const int o_b0 = 128 * nzd, o_w1 = o_b0 + 128, o_b1 = o_w1 + ndx * 128;
+  // element getters of the padded first-layer matrices (bias in the constant-one column)
+  auto g_fx0 = [&](int nn, int k) -> float {
+    if (k < nzd) return FX[nn * nzd + k];
+    return k == c1 ? FX[o_b0 + nn] : 0.0f;
+  };
+  auto g_fx1 = [&](int nn, int k) -> float { return FX[o_w1 + nn * 128 + k]; };
+  auto g_p0 = [&](int nn, int k) -> float {
+    if (k >= cs0 && k < cs0 + nzin) return FR[P.pl[0].g_w + nn * nzin + (k - cs0)];
+    return k == c1 ? FR[P.pl[0].g_b + nn] : 0.0f;
+  };
+  auto g_p1 = [&](int nn, int k) -> float { return FR[P.pl[1].g_w + nn * d1 + k]; };
+  auto g_p2 = [&](int nn, int k) -> float { return FR[P.pl[2].g_w + nn * d2 + k]; };
+  auto g_p3 = [&](int nn, int k) -> float { return FR[P.pl[3].g_w + nn * d3 + k]; };
+
+  auto bias_p3 = [&](int e) -> float {
+    if constexpr (mlp) return FR[P.pl[3].g_b + e];
+    else return 0.0f;
+  };
+  const int KZ = T.KZ;
+  // power-of-two operand scales from the block maxima: linear scans of the raw ranges, ONE block reduction for all six
+  int k_fx0, k_x, k_p0 = 0, k_p1 = 0, k_p2 = 0;
+  {
+    float m[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int e = tid; e < o_w1; e += NALL) m[0] = fmaxf(m[0], fabsf(FX[e]));                      // fx0: w0 and b0
+    for (int e = tid; e < ndx * 128; e += NALL) m[1] = fmaxf(m[1], fabsf(FX[o_w1 + e]));          // fx1: w1
+    if constexpr (mlp) {
+      for (int e = tid; e < d1 * nzin; e += NALL) m[2] = fmaxf(m[2], fabsf(FR[P.pl[0].g_w + e]));
+      for (int e = tid; e < d1; e += NALL) m[2] = fmaxf(m[2], fabsf(FR[P.pl[0].g_b + e]));
+      for (int e = tid; e < d2 * d1; e += NALL) m[3] = fmaxf(m[3], fabsf(FR[P.pl[1].g_w + e]));
+      for (int e = tid; e < d3 * d2; e += NALL) m[4] = fmaxf(m[4], fabsf(FR[P.pl[2].g_w + e]));
+      for (int e = tid; e < ndx * d3; e += NALL) m[5] = fmaxf(m[5], fabsf(FR[P.pl[3].g_w + e]));
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) m[i] = fmaxf(m[i], __shfl_xor_sync(0xffffffffu, m[i], off));
+    if (lane == 0)
+#pragma unroll
+      for (int i = 0; i < 6; ++i) RED[warp * 6 + i] = m[i];
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      float r = RED[i];
+      for (int w = 1; w < NALL / 32; ++w) r = fmaxf(r, RED[w * 6 + i]);
+      m[i] = r;
+    }
+    k_fx0 = scale_exp(m[0]);
+    k_x = scale_exp(m[1]);
+    if constexpr (mlp) {
+      k_p0 = scale_exp(m[2]); k_p1 = scale_exp(m[3]); k_p2 = scale_exp(m[4]);
+      k_x = min(k_x, scale_exp(m[5]));  // fx1 and the last physics layer accumulate into the same TMEM columns
+    }
+  }
+  stage_weight(smb + T.w_fx0, T.l_fx0, 128, KZ, k_fx0, g_fx0);
+  stage_weight(smb + T.w_fx1, T.l_fx1, ndx, 128, k_x, g_fx1);
+  if constexpr (mlp) {
+    stage_weight(smb + T.w_p[0], T.l_p[0], d1, KZ, k_p0, g_p0);
+    stage_weight(smb + T.w_p[1], T.l_p[1], d2, d1, k_p1, g_p1);
+    stage_weight(smb + T.w_p[2], T.l_p[2], d3, d2, k_p2, g_p2);
+    stage_weight(smb + T.w_p[3], T.l_p[3], ndx, d3, k_x, g_p3);
+  }
+  for (int e = tid; e < ndx; e += NALL) BX[e] = FX[o_b1 + e] + bias_p3(e);
+  if constexpr (mlp) {
+    for (int e = tid; e < d2; e += NALL) BP1[e] = FR[P.pl[1].g_b + e];
+    for (int e = tid; e < d3; e += NALL) BP2[e] = FR[P.pl[2].g_b + e];
+  }
+  if constexpr (mlp) {
+    for (int e = tid; e < d1 * 4; e += NALL) {
+      const int k = e >> 2, j = e & 3;
+      WP0F[e] = j < P.nz_x ? FR[P.pl[0].g_w + k * nzin + j] : 0.0f;
+    }
+  }
+  // auxiliary decoders (fp32, CUDA cores): side 0 = decoder_c, side 1 = decoder_y
+  for (int e = tid; e < 2 * 64 * 4; e += NALL) {
+    const int side = e >> 8, k = (e >> 2) & 63, j = e & 3;
+    const Mlp2S& M = side ? P.dy : P.dc;
+    const int nzs = side ? P.nz_y : P.nz_c, nd = side ? P.nd_y : P.nd_c;
+    const int ep = ((side * 32 + (k >> 1)) * 4 + j) * 2 + (k & 1);   // pair-interleaved slot of (side, unit k, column j)
+    AW0[ep] = j < nzs ? prm[M.g_w0 + (long long)k * nzs + j] : 0.0f;
+    const int o = (j & 1) < nd ? ((j >> 1) * nd + (j & 1)) : -1;  // head column j: mean_(j&1) (j < 2) or log_sigma_(j&1)
+    AW1[ep] = o >= 0 ? prm[M.g_w1 + (long long)o * 64 + k] : 0.0f;
+    if (j == 0) AB0[side * 64 + k] = prm[M.g_b0 + k];
+    if (k == 0) AB1[side * 4 + j] = o >= 0 ? prm[M.g_b1 + o] : 0.0f;
+  }
+
+  const float lsx = prm[P.g_lsx];
+  const float sx = expf(lsx);
+  const float var_x = sx * sx;
+  // gradient scale of the x residual: sg = 2^round(log2(64 / sigma_x)), kept inside the fp16 range
+  int e_g = (int)rintf(6.0f - lsx * 1.4426950408889634f);
+  e_g = max(-8, min(e_g, 24));
+  const float sg = exp2f((float)e_g);
+  if (tid == 0) {
+    INV[I_FX0] = exp2f(-(float)(k_fx0 + E_LAT));
+    INV[I_P0] = exp2f(-(float)(k_p0 + E_LAT));
+    INV[I_P1] = exp2f(-(float)(k_p1 + E_T));
+    INV[I_P2] = exp2f(-(float)(k_p2 + E_T));
+    INV[I_X] = exp2f(-(float)(k_x + E_H));
+    INV[I_XD] = exp2f(-(float)k_x);
+    INV[I_FX0D] = exp2f(-(float)k_fx0);
+    INV[I_P2D] = exp2f(-(float)k_p2);
+    INV[I_P1D] = exp2f(-(float)k_p1);
+    INV[I_P0D] = exp2f(-(float)k_p0);
+  }
+  if (P.with_grad && tid == 0) part[P.g_lsx] = 0.0f;
+  for (int e = tid; e < NSCAL; e += NALL) part[P.n_params + e] = 0.0f;
+  // the raw-weight scratch goes back to zero: the operand buffers rely on zero padding
+  __syncthreads();
+  for (int e = tid; e < ((n_fx + 3) & ~3) + n_fr; e += NALL) FX[e] = 0.0f;
+  tc::fence_async_smem();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+}
 
 // PHYS: physics decoder kind (0 MLP surrogate, 1 mass_spring, 2 beam); NDX: response length -- compile-time so
 // that the epilogues are straight-line code (a taken branch in this large kernel costs an I-cache miss)
@@ -240,124 +420,10 @@ __global__ void __launch_bounds__(NALL, 1) dec_tc_kernel(const __grid_constant__
   uint64_t* adone = gfree + 1;
   uint64_t* abar = gfree + 2;
 
-  // ---- one-time: zero smem, barriers, TMEM, weights -------------------------------------------------
-  for (int e = tid; e < (T.total >> 2); e += TNT) smf[e] = 0.0f;
-  __syncthreads();
-  if (tid == 0) {
-    tc::mbar_init(bar0, 1);
-    tc::mbar_init(bar1, 1);
-    tc::mbar_init(rbar, 1);
-    tc::mbar_init(rbar + 1, 1);
-    tc::mbar_init(gfree, TNT);
-    tc::mbar_init(adone, P.with_grad ? NAUXT + 1 : NAUXT);   // every aux thread + (training) the commit of its last MMAs
-    tc::mbar_init(abar, 1);
-    tc::mbar_fence_init();
-  }
-  __syncwarp();
-  if (warp == 0) tc::tmem_alloc(tptr, C_ALLOC);
-
+  dec_tc_setup<PHYS, NDX>(T, smb);
   const float* prm = P.params;
   const int c1 = T.c_ones, cs0 = T.c_s0;
-  // Raw weights first: the data-driven decoder's [w0 | b0 | w1 | b1] block of the flat buffer and the frozen physics
-  // surrogate are copied ONCE with coalesced loads into the (still unused) operand buffers; the scale search and the
-  // operand staging read them from shared memory, and the scratch is zeroed again before the first tile.
-  float* FX = smf + (T.a_big >> 2);
-  const int n_fx = 128 * nzd + 128 + ndx * 128 + ndx;
-  const int n_fr = mlp ? (int)(P.pl[3].g_b + ndx) : 0;
-  float* FR = FX + ((n_fx + 3) & ~3);
-  {
-    const float* src = prm + P.fx.g_w0;
-    for (int e = tid; e < n_fx; e += TNT) FX[e] = src[e];
-    if constexpr (mlp)
-      for (int e = tid; e < n_fr; e += TNT) FR[e] = P.frozen[e];
-  }
-  __syncthreads();
-  const int o_b0 = 128 * nzd, o_w1 = o_b0 + 128, o_b1 = o_w1 + ndx * 128;
-  // element getters of the padded first-layer matrices (bias in the constant-one column)
-  auto g_fx0 = [&](int nn, int k) -> float {
-    if (k < nzd) return FX[nn * nzd + k];
-    return k == c1 ? FX[o_b0 + nn] : 0.0f;
-  };
-  auto g_fx1 = [&](int nn, int k) -> float { return FX[o_w1 + nn * 128 + k]; };
-  auto g_p0 = [&](int nn, int k) -> float {
-    if (k >= cs0 && k < cs0 + nzin) return FR[P.pl[0].g_w + nn * nzin + (k - cs0)];
-    return k == c1 ? FR[P.pl[0].g_b + nn] : 0.0f;
-  };
-  auto g_p1 = [&](int nn, int k) -> float { return FR[P.pl[1].g_w + nn * d1 + k]; };
-  auto g_p2 = [&](int nn, int k) -> float { return FR[P.pl[2].g_w + nn * d2 + k]; };
-  auto g_p3 = [&](int nn, int k) -> float { return FR[P.pl[3].g_w + nn * d3 + k]; };
-
-  auto bias_p3 = [&](int e) -> float {
-    if constexpr (mlp) return FR[P.pl[3].g_b + e];
-    else return 0.0f;
-  };
   const int KZ = T.KZ;
-  // power-of-two operand scales from the block maxima: linear scans of the raw ranges, ONE block reduction for all six
-  int k_fx0, k_x, k_p0 = 0, k_p1 = 0, k_p2 = 0;
-  {
-    float m[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int e = tid; e < o_w1; e += TNT) m[0] = fmaxf(m[0], fabsf(FX[e]));                      // fx0: w0 and b0
-    for (int e = tid; e < ndx * 128; e += TNT) m[1] = fmaxf(m[1], fabsf(FX[o_w1 + e]));          // fx1: w1
-    if constexpr (mlp) {
-      for (int e = tid; e < d1 * nzin; e += TNT) m[2] = fmaxf(m[2], fabsf(FR[P.pl[0].g_w + e]));
-      for (int e = tid; e < d1; e += TNT) m[2] = fmaxf(m[2], fabsf(FR[P.pl[0].g_b + e]));
-      for (int e = tid; e < d2 * d1; e += TNT) m[3] = fmaxf(m[3], fabsf(FR[P.pl[1].g_w + e]));
-      for (int e = tid; e < d3 * d2; e += TNT) m[4] = fmaxf(m[4], fabsf(FR[P.pl[2].g_w + e]));
-      for (int e = tid; e < ndx * d3; e += TNT) m[5] = fmaxf(m[5], fabsf(FR[P.pl[3].g_w + e]));
-    }
-#pragma unroll
-    for (int i = 0; i < 6; ++i)
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) m[i] = fmaxf(m[i], __shfl_xor_sync(0xffffffffu, m[i], off));
-    if (lane == 0 && warp < TNT / 32)
-#pragma unroll
-      for (int i = 0; i < 6; ++i) RED[warp * 6 + i] = m[i];
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      float r = RED[i];
-      for (int w = 1; w < TNT / 32; ++w) r = fmaxf(r, RED[w * 6 + i]);
-      m[i] = r;
-    }
-    k_fx0 = scale_exp(m[0]);
-    k_x = scale_exp(m[1]);
-    if constexpr (mlp) {
-      k_p0 = scale_exp(m[2]); k_p1 = scale_exp(m[3]); k_p2 = scale_exp(m[4]);
-      k_x = min(k_x, scale_exp(m[5]));  // fx1 and the last physics layer accumulate into the same TMEM columns
-    }
-  }
-  stage_weight(smb + T.w_fx0, T.l_fx0, 128, KZ, k_fx0, g_fx0);
-  stage_weight(smb + T.w_fx1, T.l_fx1, ndx, 128, k_x, g_fx1);
-  if constexpr (mlp) {
-    stage_weight(smb + T.w_p[0], T.l_p[0], d1, KZ, k_p0, g_p0);
-    stage_weight(smb + T.w_p[1], T.l_p[1], d2, d1, k_p1, g_p1);
-    stage_weight(smb + T.w_p[2], T.l_p[2], d3, d2, k_p2, g_p2);
-    stage_weight(smb + T.w_p[3], T.l_p[3], ndx, d3, k_x, g_p3);
-  }
-  for (int e = tid; e < ndx; e += TNT) BX[e] = FX[o_b1 + e] + bias_p3(e);
-  if constexpr (mlp) {
-    for (int e = tid; e < d2; e += TNT) BP1[e] = FR[P.pl[1].g_b + e];
-    for (int e = tid; e < d3; e += TNT) BP2[e] = FR[P.pl[2].g_b + e];
-  }
-  if constexpr (mlp) {
-    for (int e = tid; e < d1 * 4; e += TNT) {
-      const int k = e >> 2, j = e & 3;
-      WP0F[e] = j < P.nz_x ? FR[P.pl[0].g_w + k * nzin + j] : 0.0f;
-    }
-  }
-  // auxiliary decoders (fp32, CUDA cores): side 0 = decoder_c, side 1 = decoder_y
-  for (int e = tid; e < 2 * 64 * 4; e += TNT) {
-    const int side = e >> 8, k = (e >> 2) & 63, j = e & 3;
-    const Mlp2S& M = side ? P.dy : P.dc;
-    const int nzs = side ? P.nz_y : P.nz_c, nd = side ? P.nd_y : P.nd_c;
-    const int ep = ((side * 32 + (k >> 1)) * 4 + j) * 2 + (k & 1);   // pair-interleaved slot of (side, unit k, column j)
-    AW0[ep] = j < nzs ? prm[M.g_w0 + (long long)k * nzs + j] : 0.0f;
-    const int o = (j & 1) < nd ? ((j >> 1) * nd + (j & 1)) : -1;  // head column j: mean_(j&1) (j < 2) or log_sigma_(j&1)
-    AW1[ep] = o >= 0 ? prm[M.g_w1 + (long long)o * 64 + k] : 0.0f;
-    if (j == 0) AB0[side * 64 + k] = prm[M.g_b0 + k];
-    if (k == 0) AB1[side * 4 + j] = o >= 0 ? prm[M.g_b1 + o] : 0.0f;
-  }
-
   const float lsx = prm[P.g_lsx];
   const float sx = expf(lsx);
   const float var_x = sx * sx;
@@ -365,27 +431,6 @@ __global__ void __launch_bounds__(NALL, 1) dec_tc_kernel(const __grid_constant__
   int e_g = (int)rintf(6.0f - lsx * 1.4426950408889634f);
   e_g = max(-8, min(e_g, 24));
   const float sg = exp2f((float)e_g);
-  if (tid == 0) {
-    INV[I_FX0] = exp2f(-(float)(k_fx0 + E_LAT));
-    INV[I_P0] = exp2f(-(float)(k_p0 + E_LAT));
-    INV[I_P1] = exp2f(-(float)(k_p1 + E_T));
-    INV[I_P2] = exp2f(-(float)(k_p2 + E_T));
-    INV[I_X] = exp2f(-(float)(k_x + E_H));
-    INV[I_XD] = exp2f(-(float)k_x);
-    INV[I_FX0D] = exp2f(-(float)k_fx0);
-    INV[I_P2D] = exp2f(-(float)k_p2);
-    INV[I_P1D] = exp2f(-(float)k_p1);
-    INV[I_P0D] = exp2f(-(float)k_p0);
-  }
-  if (P.with_grad && tid == 0) part[P.g_lsx] = 0.0f;
-  for (int e = tid; e < NSCAL; e += TNT) part[P.n_params + e] = 0.0f;
-  // the raw-weight scratch goes back to zero: the operand buffers rely on zero padding
-  __syncthreads();
-  for (int e = tid; e < ((n_fx + 3) & ~3) + n_fr; e += TNT) FX[e] = 0.0f;
-  tc::fence_async_smem();
-  tc::fence_before_sync();
-  __syncthreads();
-  tc::fence_after_sync();
   const uint32_t tb = *tptr;
   const uint32_t trow = tb + ((uint32_t)(32 * q) << 16);
   uint32_t ph0 = 0, ph1 = 0;

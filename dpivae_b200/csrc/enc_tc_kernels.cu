@@ -22,7 +22,7 @@ namespace dpv {
 namespace {
 
 constexpr int TP = 128;
-constexpr int ENT = 256;
+constexpr int ENT = 256;    // backward kernel: 8 warps
 constexpr int E_X = 4;   // operand scale exponents: standardised inputs
 constexpr int E_HID = 6;  // hidden activations
 
@@ -34,7 +34,8 @@ __device__ __forceinline__ void put8e(unsigned char* plane, uint32_t lo_off, int
   *reinterpret_cast<uint4*>(dst + lo_off) = lo;
 }
 
-// block-wide max of two values at once (uses red[16])
+// block-wide max of two values at once (uses red[2 NW], NW = warps in the block)
+template <int NW = ENT / 32>
 __device__ __forceinline__ void block_max2(float& a, float& b, float* red) {
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) {
@@ -42,11 +43,11 @@ __device__ __forceinline__ void block_max2(float& a, float& b, float* red) {
     b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, off));
   }
   __syncthreads();
-  if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = a; red[8 + (threadIdx.x >> 5)] = b; }
+  if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = a; red[NW + (threadIdx.x >> 5)] = b; }
   __syncthreads();
-  a = red[0]; b = red[8];
+  a = red[0]; b = red[NW];
 #pragma unroll
-  for (int w = 1; w < ENT / 32; ++w) { a = fmaxf(a, red[w]); b = fmaxf(b, red[8 + w]); }
+  for (int w = 1; w < NW; ++w) { a = fmaxf(a, red[w]); b = fmaxf(b, red[NW + w]); }
 }
 __device__ __forceinline__ int scale_exp_e(float mx) {
   if (!(mx > 0.0f) || !isfinite(mx)) return 0;
@@ -56,12 +57,19 @@ __device__ __forceinline__ int scale_exp_e(float mx) {
 }
 }  // namespace
 
-__global__ void __launch_bounds__(ENT, 1) enc_tc_fwd_kernel(const __grid_constant__ EncTcParams P) {
+// NW warps: 8 (two column halves per row) or 16 (four column quarters; pays when the per-tile epilogues are long: K0 = 64
+// inputs and head columns in multiples of 32, i.e. the bridge / damped_oscillator P presets)
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, 1) enc_tc_fwd_kernel(const __grid_constant__ EncTcParams P) {
+  constexpr int ENTF = NW * 32, CS = NW / 4;   // threads, column splits per row
   extern __shared__ __align__(1024) unsigned char smb[];
   pdl_launch_dependents();   // the prior-net forward kernel is independent of this one and runs alongside it
   float* smf = reinterpret_cast<float*>(smb);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int q = warp & 3, hh = warp >> 2;
+  // 16 warps: thread (TMEM lane quadrant q, lane, column quarter qc) owns row p = 32 q + lane of the tile and one quarter of
+  // the columns in every epilogue (four warps per scheduler hide the TMEM / shared-memory / global latencies of the serial
+  // per-tile chain; with two column halves on 8 warps the issue slots were 32 % used)
+  const int q = warp & 3, qc = warp >> 2;
   const int p = 32 * q + lane;
   const int K0 = P.K0, KX = P.KX, Hc = P.Hc, Oc = P.Oc;
   const long long B = P.B;
@@ -71,7 +79,7 @@ __global__ void __launch_bounds__(ENT, 1) enc_tc_fwd_kernel(const __grid_constan
   uint64_t* bar = reinterpret_cast<uint64_t*>(smb + P.o_bar);
   uint32_t* tptr = reinterpret_cast<uint32_t*>(smb + P.o_bar + 8);
 
-  for (int e = tid; e < (P.total >> 2); e += ENT) smf[e] = 0.0f;
+  for (int e = tid; e < (P.total >> 2); e += ENTF) smf[e] = 0.0f;
   __syncthreads();
   if (tid == 0) {
     tc::mbar_init(bar, 1);
@@ -91,7 +99,7 @@ __global__ void __launch_bounds__(ENT, 1) enc_tc_fwd_kernel(const __grid_constan
     for (int u = 0; u < P.n_units; ++u) {
       const int nblk = P.H[u] * K0 + P.H[u] + P.O[u] * P.H[u] + P.O[u];
       const float* src = prm + P.g_w0[u];
-      for (int e = tid; e < nblk; e += ENT) RAW[ro + e] = src[e];
+      for (int e = tid; e < nblk; e += ENTF) RAW[ro + e] = src[e];
       ub[u] = RAW + ro;
       ro += nblk;
     }
@@ -118,10 +126,10 @@ __global__ void __launch_bounds__(ENT, 1) enc_tc_fwd_kernel(const __grid_constan
   float m0 = 0.0f, m1 = 0.0f;
   for (int u = 0; u < P.n_units; ++u) {
     const int n0 = P.H[u] * K0 + P.H[u], n1 = P.O[u] * P.H[u];
-    for (int e = tid; e < n0; e += ENT) m0 = fmaxf(m0, fabsf(ub[u][e]));
-    for (int e = tid; e < n1; e += ENT) m1 = fmaxf(m1, fabsf(ub[u][n0 + e]));
+    for (int e = tid; e < n0; e += ENTF) m0 = fmaxf(m0, fabsf(ub[u][e]));
+    for (int e = tid; e < n1; e += ENTF) m1 = fmaxf(m1, fabsf(ub[u][n0 + e]));
   }
-  block_max2(m0, m1, RED);
+  block_max2<ENTF / 32>(m0, m1, RED);
   const int k_w0 = scale_exp_e(m0), k_w1 = scale_exp_e(m1);
   // operand staging, unit by unit (no per-element unit search / division): first layers = rows h_off[u] + l of the
   // [Hc x KX] operand, 8 consecutive inputs per item, bias in column K0; heads = block-diagonal [Oc x Hc]
@@ -132,7 +140,7 @@ __global__ void __launch_bounds__(ENT, 1) enc_tc_fwd_kernel(const __grid_constan
       const float* w0 = ub[u];
       const float* b0 = ub[u] + P.H[u] * K0;
       const float* w1 = b0 + P.H[u];
-      for (int e = tid; e < P.H[u] * nch0; e += ENT) {
+      for (int e = tid; e < P.H[u] * nch0; e += ENTF) {
         const int l = e / nch0, ch = e - l * nch0;
         float v[8];
         if (ch < (K0 >> 3)) {
@@ -146,7 +154,7 @@ __global__ void __launch_bounds__(ENT, 1) enc_tc_fwd_kernel(const __grid_constan
         put8e(smb + P.w_0, P.l_0, Hc, ch, P.h_off[u] + l, v);
       }
       const int nch1 = P.H[u] >> 3;
-      for (int e = tid; e < P.O[u] * nch1; e += ENT) {
+      for (int e = tid; e < P.O[u] * nch1; e += ENTF) {
         const int lo = e / nch1, ch = e - lo * nch1;
         float v[8];
 #pragma unroll
@@ -155,7 +163,7 @@ __global__ void __launch_bounds__(ENT, 1) enc_tc_fwd_kernel(const __grid_constan
       }
     }
   }
-  for (int o = tid; o < Oc; o += ENT) {
+  for (int o = tid; o < Oc; o += ENTF) {
     int l;
     const int u = unit_of_o(o, l);
     B1[o] = u >= 0 ? ub[u][P.H[u] * K0 + P.H[u] + P.O[u] * P.H[u] + l] : 0.0f;
@@ -180,29 +188,31 @@ __global__ void __launch_bounds__(ENT, 1) enc_tc_fwd_kernel(const __grid_constan
   oX.base = tc::smem_u32(pX); oX.lo_off = P.l_x; oX.R = TP;
   oW0.base = tc::smem_u32(smb + P.w_0); oW0.lo_off = P.l_0; oW0.R = Hc;
   oW1.base = tc::smem_u32(smb + P.w_1); oW1.lo_off = P.l_1; oW1.R = Oc;
-  const int hcols = Hc >> 1, ocols = Oc >> 1;   // columns per thread (multiples of 8)
+  const int hcols = Hc / CS;                    // hidden columns per thread (multiple of 8)
+  const int osplit = (Oc % (8 * CS)) == 0 ? CS : 2;    // head columns per thread: multiples of 8 (else halves, on 8 of the warps)
+  const int ocols = Oc / osplit;
   const long long ntiles = (B + TP - 1) / TP;
 
   // The raw x rows of a tile are fetched one tile AHEAD into registers (the gathered global loads were the largest
   // stall of this kernel: nothing else hides their latency inside the serial per-tile chain); the per-column scaler
   // statistics of this thread's 4 x 8 columns live in registers for the whole kernel.
-  constexpr int XC = 4;                 // chunks of 8 columns per thread, K0 <= 64
-  const int nch = K0 >> 4;
+  constexpr int XC = 8 / CS;            // chunks of 8 columns per thread, K0 <= 64
+  const int nch = K0 / (8 * CS);
   float4 xa[XC], xb[XC];
-  float mr[XC][8], sr[XC][8];
+  float mr[XC][8], sr[XC][8];           // mean and RECIPROCAL standard deviation (one multiply per element instead of a division)
 #pragma unroll
   for (int c = 0; c < XC; ++c)
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int k = hh * (K0 >> 1) + 8 * c + i;
+      const int k = qc * (K0 / CS) + 8 * c + i;
       mr[c][i] = (c < nch) ? P.mean_x[k] : 0.0f;
-      sr[c][i] = (c < nch) ? P.std_x[k] : 1.0f;
+      sr[c][i] = (c < nch) ? 1.0f / P.std_x[k] : 1.0f;
     }
   auto fetch_x = [&](long long tile) {
     const long long lr = tile * TP + p;
     const bool ok = tile < ntiles && lr < B;
     const long long drow = ok ? (P.idx ? P.idx[lr] : lr) : 0;
-    const float* xr = P.x + drow * K0 + hh * (K0 >> 1);
+    const float* xr = P.x + drow * K0 + qc * (K0 / CS);
 #pragma unroll
     for (int c = 0; c < XC; ++c) {
       xa[c] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -225,10 +235,10 @@ __global__ void __launch_bounds__(ENT, 1) enc_tc_fwd_kernel(const __grid_constan
       for (int c = 0; c < XC; ++c) {
         if (c < nch) {
           float v[8] = {xa[c].x, xa[c].y, xa[c].z, xa[c].w, xb[c].x, xb[c].y, xb[c].z, xb[c].w};
-          const int k0 = hh * (K0 >> 1) + 8 * c;
+          const int k0 = qc * (K0 / CS) + 8 * c;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float t = P.x_is_standardised ? v[i] : (v[i] - mr[c][i]) / sr[c][i];
+            const float t = P.x_is_standardised ? v[i] : (v[i] - mr[c][i]) * sr[c][i];
             // |standardised input| > 3750 sigma would overflow the fp16 operand (inf -> NaN gradients): saturate instead
             v[i] = valid ? fminf(fmaxf(t * s_x, -60000.0f), 60000.0f) : 0.0f;
           }
@@ -236,10 +246,10 @@ __global__ void __launch_bounds__(ENT, 1) enc_tc_fwd_kernel(const __grid_constan
         }
       }
       fetch_x(tile + gridDim.x);   // next tile's rows: in flight under this tile's MMAs and epilogues
-      if (hh == 0) {  // constant-one column (bias of the first layers) + zero padding up to KX
+      if (qc == 0) {  // constant-one column (bias of the first layers) + zero padding up to KX
         float v[8] = {s_x, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         put8e(pX, P.l_x, TP, K0 >> 3, p, v);
-      } else {
+      } else if (qc == 1) {
         float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         put8e(pX, P.l_x, TP, (K0 >> 3) + 1, p, v);
       }
@@ -262,7 +272,7 @@ __global__ void __launch_bounds__(ENT, 1) enc_tc_fwd_kernel(const __grid_constan
     {
       unsigned char* hrec = P.hidrec ? P.hidrec + (long long)tile * P.hid_stride : nullptr;
       for (int c = 0; c < (hcols >> 3); ++c) {
-        const int k0 = hh * hcols + 8 * c;
+        const int k0 = qc * hcols + 8 * c;
         float v[8];
         tc::tmem_ld8(trow + C_H + k0, v);
 #pragma unroll
@@ -293,8 +303,8 @@ __global__ void __launch_bounds__(ENT, 1) enc_tc_fwd_kernel(const __grid_constan
     __syncwarp();
     tc::fence_after_sync();
     // ---- head pre-activations out: headpre[row(o)][B], coalesced along the minibatch rows ----
-    for (int c = 0; c < (ocols >> 3); ++c) {
-      const int o0 = hh * ocols + 8 * c;
+    for (int c = 0; c < (qc < osplit ? (ocols >> 3) : 0); ++c) {
+      const int o0 = qc * ocols + 8 * c;
       float v[8];
       tc::tmem_ld8(trow + C_O + o0, v);
       if (valid) {
@@ -667,9 +677,13 @@ __global__ void __launch_bounds__(ENT, 1) enc_tc_bwd_kernel(const __grid_constan
 
 void launch_enc_tc_bwd(const EncTcParams& p, int grid, cudaStream_t s) { launch_pdl(enc_tc_bwd_kernel, grid, ENT, (size_t)p.total_b, s, p); }
 
-void launch_enc_tc_fwd(const EncTcParams& p, int grid, cudaStream_t s) { enc_tc_fwd_kernel<<<grid, ENT, p.total, s>>>(p); }
+void launch_enc_tc_fwd(const EncTcParams& p, int grid, cudaStream_t s) {
+  if (p.K0 == 64 && (p.Oc & 31) == 0 && (p.Hc & 31) == 0) enc_tc_fwd_kernel<16><<<grid, 512, p.total, s>>>(p);
+  else enc_tc_fwd_kernel<8><<<grid, 256, p.total, s>>>(p);
+}
 int configure_enc_tc_kernels() {
-  int e = (int)cudaFuncSetAttribute(enc_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  int e = (int)cudaFuncSetAttribute(enc_tc_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  if (!e) e = (int)cudaFuncSetAttribute(enc_tc_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
   if (!e) e = (int)cudaFuncSetAttribute(enc_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
   return e;
 }
