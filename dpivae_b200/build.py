@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdpivae_b200.so")
-SOURCES = ["api.cu", "dec_kernel.cu", "dec_tc_kernel.cu", "lat_kernels.cu", "enc_kernels.cu", "enc_tc_kernels.cu", "optim_kernels.cu", "metrics_kernels.cu", "prior_kernels.cu", "datagen_kernels.cu"]
+SOURCES = ["api.cu", "dec_kernel.cu", "dec_tc_kernel.cu", "lat_kernels.cu", "enc_kernels.cu", "enc_tc_kernels.cu", "enc_fused_kernel.cu", "optim_kernels.cu", "metrics_kernels.cu", "prior_kernels.cu", "datagen_kernels.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

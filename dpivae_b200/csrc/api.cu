@@ -2,6 +2,7 @@
 // workspace planning and the launch sequences of the hot path.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -48,6 +49,8 @@ struct dpivae_model {
   int last_launches = 0;
   long long part_stride = 0;
   EncTcParams enc_tc;       // tensor-core encoder plan
+  EncFusedParams enc_fused; // fused encode-only kernel (encoder MMAs + latent sampling)
+  int enc_fused_ok = 0;
   int enc_tc_ok = 0, enc_tc_bwd_ok = 0;
   int math_mode = 0;        // DPIVAE_MATH_*
   TcParams tc;              // tensor-core decoder plan
@@ -324,6 +327,18 @@ static int build_plan(dpivae_model* h) {
     Q.hid_lo = (Q.Hc / 8) * 128 * 16;
     Q.hid_stride = 2 * (long long)Q.hid_lo;
     if (ok && Q.total <= 232448) h->enc_tc_ok = 1;
+    // fused encode-only kernel: same plan + its mbarrier block
+    {
+      EncFusedParams& F = h->enc_fused;
+      memset(&F, 0, sizeof(F));
+      F.q = Q;
+      for (int i = 0; i < d.nd_x; ++i) F.istd_x[i] = 1.0f / d.std_x[i];
+      F.model_type = d.model_type;
+      F.nz[0] = d.nz_x; F.nz[1] = d.nz_c; F.nz[2] = d.nz_y;
+      for (int i = 0; i < d.nz_x && i < 4; ++i) { F.lb[i] = h->dec.lb[i]; F.ub[i] = h->dec.ub[i]; }
+      F.o_bars = Q.total;
+      h->enc_fused_ok = h->enc_tc_ok && enc_fused_supports(F);
+    }
     // backward plan
     b = 0;
     plane2(Q.Hc / 8, Q.Oc, Q.wb_1, Q.lb_1);
@@ -414,7 +429,7 @@ int dpivae_create(const dpivae_model_desc_t* desc, dpivae_handle_t* out) {
   h->sm_count = prop.multiProcessorCount;
   if (build_plan(h)) { delete h; return 1; }
   if (configure_dec_kernel() || configure_enc_kernels() || configure_dec_tc_kernel() || configure_lat_kernels() ||
-      configure_enc_tc_kernels()) { delete h; return fail("cudaFuncSetAttribute(max dynamic smem) failed"); }
+      configure_enc_tc_kernels() || configure_enc_fused_kernels()) { delete h; return fail("cudaFuncSetAttribute(max dynamic smem) failed"); }
   // owner map: which kernel's partials hold each parameter's gradient
   std::vector<unsigned char> owner((size_t)desc->n_params, 0);
   for (int u = 0; u < h->enc.n_units; ++u) {
@@ -600,6 +615,28 @@ static int run_loss(dpivae_handle_t h, const dpivae_batch_t* bt, const dpivae_rn
   const bool prior_fast = prior_kernels_support(E2) && bt->B >= 2048;   // small batches: units in parallel CTA columns instead
   const long long nt128 = (bt->B + 127) / 128;
   const int grid_etc = (int)(nt128 < h->sm_count ? nt128 : h->sm_count);
+  const bool fused_encode = latent_only && enc_tc && h->enc_fused_ok && !getenv("DPIVAE_NO_FUSED_ENCODE");
+  if (fused_encode) {
+    // encode-only: encoder MMAs and latent sampling in one warp-specialised kernel (enc_fused_kernel.cu)
+    KTimer t(h, 0, st);
+    EncFusedParams F = h->enc_fused;
+    F.q.params = h->params; F.q.x = bt->x; F.q.idx = (const long long*)bt->idx; F.q.B = bt->B;
+    F.q.x_is_standardised = x_std; F.q.terms = h->math_mode == DPIVAE_MATH_TC_FP16X3 ? 3 : 1;
+    F.rng.ss = h->cur_ss; F.rng.mode = rng->mode; F.rng.seed = rng->seed;
+    for (int k = 0; k < 4; ++k) { F.rng.eps[k] = rng->eps[k]; F.rng.offset[k] = rng->offset[k]; F.rng.grid_threads[k] = rng->grid_threads[k] ? rng->grid_threads[k] : 256; }
+    F.Bg = bt->B_global; F.row_off = bt->row_offset; F.n_mc = bt->n_mc;
+    F.zx = out ? out->zx : nullptr; F.zc = out ? out->zc : nullptr; F.zy = out ? out->zy : nullptr; F.dens = out ? out->dens_z : nullptr;
+    // in-kernel Philox noise: generated ahead by noise_fill_kernel (one evaluation per four elements, torch's own
+    // mapping) into the hidden-activation region of the workspace, which this path does not use
+    const long long Zt = h->d.nz_x + h->d.nz_c + h->d.nz_y;
+    if (rng->mode == 1 && (long long)bt->n_mc * Zt <= (long long)h->H_tot && !getenv("DPIVAE_NO_NOISE_PREPASS")) {
+      float* e0 = hid;
+      for (int b = 0; b < 3; ++b) { F.eps_local[b] = e0; e0 += ((size_t)bt->n_mc * bt->B * F.nz[b] + 3) & ~(size_t)3; }   // 16-byte aligned blocks (the few floats of rounding spill into headpre, equally unused here)
+    }
+    h->last_launches = launch_enc_fused(F, grid_etc, st);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   {
     KTimer t(h, 0, st);
     if (enc_tc) {

@@ -189,6 +189,23 @@ struct EncTcParams {
   int wb_1, lb_1, ab_h, ab_g, lb_g, ab_x, lb_x, fb_red, fb_orow, ob_bar, total_b;
 };
 void launch_enc_tc_bwd(const EncTcParams& p, int grid, cudaStream_t s);
+
+// ---- fused encode-only kernel (enc_fused_kernel.cu): encoder MMAs + latent sampling, one launch ----
+struct EncFusedParams {
+  EncTcParams q;
+  float istd_x[64];
+  int model_type, nz[3];
+  float lb[4], ub[4];
+  RngP rng;
+  long long Bg, row_off;
+  int n_mc;
+  int o_bars;                  // byte offset of the mbarrier block (after the EncTcParams plan)
+  float *zx, *zc, *zy, *dens;  // (n_mc, B, nz_*) latents and (n_mc, B) density, any may be null
+  float* eps_local[3];         // pre-generated noise per latent block, local (n_mc, B, nz_b) order (noise_fill_kernel), or null
+};
+bool enc_fused_supports(const EncFusedParams& p);
+int launch_enc_fused(const EncFusedParams& p, int grid, cudaStream_t s);
+int configure_enc_fused_kernels();
 void launch_enc_tc_fwd(const EncTcParams& p, int grid, cudaStream_t s);
 int configure_enc_tc_kernels();
 

@@ -232,3 +232,35 @@ def test_tc_extreme_outliers_do_not_poison_the_gradients():
         torch.manual_seed(123)
         eng.loss(X, C_, Y, 16, (1.0, 1.0, 1.0, 1.0), True)
         assert not torch.isnan(eng.grads).any(), mode
+
+
+@pytest.mark.parametrize("case", ["bridge", "damped_oscillator", "simple_beam"])
+@pytest.mark.parametrize("B,n", [(1, 1), (127, 1), (128, 3), (129, 1), (1000, 2), (40000, 1)])
+def test_fused_encode_kernel_matches_two_kernel_path(case, B, n, monkeypatch):
+    """Encode-only calls of the P presets run ONE warp-specialised kernel (enc_fused_kernel: encoder MMAs + latent sampling,
+    tiles pipelined through TMEM; its noise comes from noise_fill_kernel, one Philox evaluation per four elements, or --
+    DPIVAE_NO_NOISE_PREPASS -- from the per-element generator).  Same arithmetic as enc_tc_fwd_kernel -> headpre ->
+    lat_encode_kernel on the same Philox stream, so latents and density must be BITWISE equal: single row, ragged last tile,
+    several MC samples, more tiles than CTAs (40,000 rows = 313 tiles on 148 SMs)."""
+    g, spec, sd, args, case_mod, vae, (x, c, y) = build_from_golden(case, "P")
+    eng = vae.engine()
+    eng.set_math_mode("tc_fp16x3")
+    rows = torch.arange(B) % x.shape[0]
+    gen = torch.Generator().manual_seed(B)
+    X = (x[rows] + 0.05 * torch.randn(B, x.shape[1], generator=gen)).contiguous().cuda()
+    out = {}
+    for mode in ("fused", "fused_inline_noise", "two_kernels"):
+        monkeypatch.delenv("DPIVAE_NO_FUSED_ENCODE", raising=False)
+        monkeypatch.delenv("DPIVAE_NO_NOISE_PREPASS", raising=False)
+        if mode == "two_kernels":
+            monkeypatch.setenv("DPIVAE_NO_FUSED_ENCODE", "1")
+        if mode == "fused_inline_noise":
+            monkeypatch.setenv("DPIVAE_NO_NOISE_PREPASS", "1")
+        torch.manual_seed(5)
+        l0 = eng.launches
+        out[mode] = [t.cpu().clone() for t in eng.encode(X, n, False)]
+        assert eng.launches - l0 == (1 if mode == "fused_inline_noise" else 2)
+    for mode in ("fused", "fused_inline_noise"):
+        for a, b, name in zip(out[mode], out["two_kernels"], ("zx", "zc", "zy", "dens_z")):
+            assert a.shape == b.shape and torch.isfinite(a).all(), (mode, name)
+            assert torch.equal(a, b), (mode, name, (a - b).abs().max())

@@ -160,3 +160,18 @@ def test_checkpoint_state_round_trip_on_host():
         assert torch.equal(v, vae2.state_dict()[k]), k
     assert torch.equal(vae2.transform_x.mean_, vae.transform_x.mean_) and torch.equal(vae2.transform_x.scale_, vae.transform_x.scale_)
     assert "log_sigma_x" in st["model"] and "encoder.net.f_cov.weight" in st["model"]
+
+
+def test_setup_model_refuses_full_cov_prior_up_front():
+    """`--full_cov_prior` (dpivae.py:151-153) selects FullCovarianceNN conditional priors, which the fused kernels do not
+    implement: the flag is refused in `setup_model`, before any device work, with a ValueError."""
+    import importlib
+
+    import dpivae_b200 as dpv
+
+    case_mod = importlib.import_module("dpivae_b200.cases.simple_beam")
+    g, spec, sd = gu.load("simple_beam", "S")
+    x, c, y = (torch.from_numpy(g[k].copy()) for k in "xcy")
+    args = make_args(case_mod, PRESET[("simple_beam", "S")], n_train=x.shape[0], n_batch=x.shape[0], full_cov_prior=True)
+    with pytest.raises(ValueError, match="full_cov_prior"):
+        dpv.setup_model(args, case_mod.definition, (x, c, y))
