@@ -336,7 +336,8 @@ static int build_plan(dpivae_model* h) {
       F.model_type = d.model_type;
       F.nz[0] = d.nz_x; F.nz[1] = d.nz_c; F.nz[2] = d.nz_y;
       for (int i = 0; i < d.nz_x && i < 4; ++i) { F.lb[i] = h->dec.lb[i]; F.ub[i] = h->dec.ub[i]; }
-      F.o_bars = Q.total;
+      F.o_ms = Q.total;
+      F.o_bars = Q.total + 512;
       h->enc_fused_ok = h->enc_tc_ok && enc_fused_supports(F);
     }
     // backward plan
@@ -625,6 +626,7 @@ static int run_loss(dpivae_handle_t h, const dpivae_batch_t* bt, const dpivae_rn
     F.rng.ss = h->cur_ss; F.rng.mode = rng->mode; F.rng.seed = rng->seed;
     for (int k = 0; k < 4; ++k) { F.rng.eps[k] = rng->eps[k]; F.rng.offset[k] = rng->offset[k]; F.rng.grid_threads[k] = rng->grid_threads[k] ? rng->grid_threads[k] : 256; }
     F.Bg = bt->B_global; F.row_off = bt->row_offset; F.n_mc = bt->n_mc;
+    F.phase = h->d_phase;
     F.zx = out ? out->zx : nullptr; F.zc = out ? out->zc : nullptr; F.zy = out ? out->zy : nullptr; F.dens = out ? out->dens_z : nullptr;
     // in-kernel Philox noise: generated ahead by noise_fill_kernel (one evaluation per four elements, torch's own
     // mapping) into the hidden-activation region of the workspace, which this path does not use

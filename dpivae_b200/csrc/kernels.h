@@ -199,8 +199,9 @@ struct EncFusedParams {
   RngP rng;
   long long Bg, row_off;
   int n_mc;
-  int o_bars;                  // byte offset of the mbarrier block (after the EncTcParams plan)
+  int o_ms, o_bars;            // byte offsets: scaler statistics [2][64] floats, mbarrier block (both after the EncTcParams plan)
   float *zx, *zc, *zy, *dens;  // (n_mc, B, nz_*) latents and (n_mc, B) density, any may be null
+  long long* phase;            // optional [16] cycle counters of CTA 0 (tools/encode_probe.py), else nullptr
   float* eps_local[3];         // pre-generated noise per latent block, local (n_mc, B, nz_b) order (noise_fill_kernel), or null
 };
 bool enc_fused_supports(const EncFusedParams& p);

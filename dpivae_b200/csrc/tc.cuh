@@ -178,6 +178,21 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
   tmem_wait_st();
 }
 
+// asynchronous forms: the registers are valid only after tmem_wait_ld() / the stores are complete after tmem_wait_st()
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8_nowait(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+               "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
@@ -404,6 +419,37 @@ __device__ __forceinline__ void issue_fwd_w(uint32_t el, uint32_t d_tmem, Op a, 
       accumulate = 1;
       alo += astep;
       wlo += wstep;
+    }
+  }
+}
+// compile-time shapes: both loops unroll completely, every descriptor is base + immediate (the run-time loops above cost
+// ~100 cycles of issue per MMA in the encoder kernels -- more than the MMAs themselves)
+template <int N, int K, int TERMS, int AR>
+__device__ __forceinline__ void issue_fwd_s(uint32_t el, uint32_t d_tmem, Op a, Op w, uint32_t accumulate) {
+  constexpr uint32_t idesc = make_idesc(128, N, 0, 0);
+  constexpr uint32_t hi = 8u | DESC_VERSION_HI;
+  const uint32_t a0 = ((a.base >> 4) & 0x3FFFu) | ((uint32_t)AR << 16), a1 = (((a.base + a.lo_off) >> 4) & 0x3FFFu) | ((uint32_t)AR << 16);
+  const uint32_t w0 = ((w.base >> 4) & 0x3FFFu) | ((uint32_t)N << 16), w1 = (((w.base + w.lo_off) >> 4) & 0x3FFFu) | ((uint32_t)N << 16);
+#pragma unroll
+  for (int t = 0; t < TERMS; ++t) {
+#pragma unroll
+    for (int k = 0; k < (K >> 4); ++k) {
+      mma_f16_w(el, d_tmem, pack64((t == 1 ? a1 : a0) + (uint32_t)(k * 2 * AR), hi), pack64((t == 2 ? w1 : w0) + (uint32_t)(k * 2 * N), hi), idesc,
+                (t == 0 && k == 0) ? accumulate : 1u);
+    }
+  }
+}
+template <int N, int K, int TERMS>
+__device__ __forceinline__ void issue_fwd_ts_s(uint32_t el, uint32_t d_tmem, uint32_t a_tmem, Op w, uint32_t accumulate) {
+  constexpr uint32_t idesc = make_idesc(128, N, 0, 0);
+  constexpr uint32_t hi = 8u | DESC_VERSION_HI;
+  const uint32_t w0 = ((w.base >> 4) & 0x3FFFu) | ((uint32_t)N << 16), w1 = (((w.base + w.lo_off) >> 4) & 0x3FFFu) | ((uint32_t)N << 16);
+#pragma unroll
+  for (int t = 0; t < TERMS; ++t) {
+#pragma unroll
+    for (int k = 0; k < (K >> 4); ++k) {
+      mma_f16_ts_w(el, d_tmem, a_tmem + (uint32_t)((t == 1 ? (K >> 1) : 0) + 8 * k), pack64((t == 2 ? w1 : w0) + (uint32_t)(k * 2 * N), hi), idesc,
+                   (t == 0 && k == 0) ? accumulate : 1u);
     }
   }
 }
