@@ -48,8 +48,8 @@ WORKLOADS["bridge_encode"] = dict(case="bridge", preset="DPIVAE-A", rows=524288,
 WORKLOADS["ensemble"] = dict(case="damped_oscillator", preset="dpivae", rows=64, n_mc=16, members=8, inner_steps=16)
 ENCODE_KERNEL_DOC = {
     "fp32": "enc_fwd_kernel (fp32 FFMA) + lat_encode_kernel",
-    "tc_fp16x3": "enc_tc_fwd_kernel (tcgen05) + lat_encode_kernel",
-    "tc_fp16": "enc_tc_fwd_kernel (tcgen05) + lat_encode_kernel",
+    "tc_fp16x3": "noise_fill_kernel + enc_fused_kernel (tcgen05 encoder MMAs + latent sampling, warp-specialised, one launch per call)",
+    "tc_fp16": "noise_fill_kernel + enc_fused_kernel (tcgen05 encoder MMAs + latent sampling, warp-specialised, one launch per call)",
 }
 METRIC = "ELBO train samples/s (fwd+bwd+Adam)"
 UNIT = "datapoints/s"

@@ -336,8 +336,31 @@ static int build_plan(dpivae_model* h) {
       F.model_type = d.model_type;
       F.nz[0] = d.nz_x; F.nz[1] = d.nz_c; F.nz[2] = d.nz_y;
       for (int i = 0; i < d.nz_x && i < 4; ++i) { F.lb[i] = h->dec.lb[i]; F.ub[i] = h->dec.ub[i]; }
-      F.o_ms = Q.total;
-      F.o_bars = Q.total + 512;
+      // own shared-memory plan: two X operand buffers (the raw-weight scratch of the set-up aliases them)
+      {
+        EncTcParams& G = F.q;
+        int bb = 0;
+        auto plane2f = [&](int chunks, int rows, int& off, int& lo) { const int bytes = chunks * rows * 16; off = bb; lo = bytes; bb += 2 * bytes; };
+        plane2f(G.KX / 8, G.Hc, G.w_0, G.l_0);
+        plane2f(G.Hc / 8, G.Oc, G.w_1, G.l_1);
+        plane2f(G.KX / 8, 128, G.a_x, G.l_x);
+        bb += 2 * G.l_x;                                   // second X buffer
+        G.f_b1 = bb; bb += G.Oc * 4;
+        G.f_orow = bb; bb += G.Oc * 4;
+        G.f_red = bb; bb += 256;
+        G.o_bar = bb; bb += 16;
+        G.total = (bb + 127) & ~127;
+        long long raw = 0;
+        for (int u = 0; u < nu; ++u) raw += (long long)E.u[u].H * E.u[u].K0 + E.u[u].H + (long long)E.u[u].O * E.u[u].H + E.u[u].O;
+        G.f_raw = raw * 4 <= 4LL * G.l_x ? G.a_x : -1;
+        F.o_ms = G.total;
+        F.o_bars = G.total + 512;
+        for (int u = 0; u < 3 && u < nu; ++u) {
+          F.hn0[u] = G.o_off[u] & ~7;
+          F.hN[u] = ((G.o_off[u] + G.O[u] - F.hn0[u]) + 15) & ~15;
+          if (F.hn0[u] + F.hN[u] > G.Oc) F.hn0[u] = (G.Oc - F.hN[u]) & ~7;
+        }
+      }
       h->enc_fused_ok = h->enc_tc_ok && enc_fused_supports(F);
     }
     // backward plan
@@ -627,6 +650,8 @@ static int run_loss(dpivae_handle_t h, const dpivae_batch_t* bt, const dpivae_rn
     for (int k = 0; k < 4; ++k) { F.rng.eps[k] = rng->eps[k]; F.rng.offset[k] = rng->offset[k]; F.rng.grid_threads[k] = rng->grid_threads[k] ? rng->grid_threads[k] : 256; }
     F.Bg = bt->B_global; F.row_off = bt->row_offset; F.n_mc = bt->n_mc;
     F.phase = h->d_phase;
+    F.dbg = (h->d_phase && getenv("DPIVAE_ENC_DBG")) ? atoi(getenv("DPIVAE_ENC_DBG")) : 0;
+    F.trace = (h->d_phase && getenv("DPIVAE_ENCODE_TRACE")) ? h->d_phase + 32 : nullptr;   // the probe's buffer holds 32 + 6 * 402 counters
     F.zx = out ? out->zx : nullptr; F.zc = out ? out->zc : nullptr; F.zy = out ? out->zy : nullptr; F.dens = out ? out->dens_z : nullptr;
     // in-kernel Philox noise: generated ahead by noise_fill_kernel (one evaluation per four elements, torch's own
     // mapping) into the hidden-activation region of the workspace, which this path does not use

@@ -195,6 +195,7 @@ struct EncFusedParams {
   EncTcParams q;
   float istd_x[64];
   int model_type, nz[3];
+  int hn0[3], hN[3];           // head MMA of unit u: accumulator columns [hn0, hn0 + hN) (8-aligned start, multiple of 16 wide)
   float lb[4], ub[4];
   RngP rng;
   long long Bg, row_off;
@@ -202,6 +203,8 @@ struct EncFusedParams {
   int o_ms, o_bars;            // byte offsets: scaler statistics [2][64] floats, mbarrier block (both after the EncTcParams plan)
   float *zx, *zc, *zy, *dens;  // (n_mc, B, nz_*) latents and (n_mc, B) density, any may be null
   long long* phase;            // optional [16] cycle counters of CTA 0 (tools/encode_probe.py), else nullptr
+  int dbg;                     // PROF instantiation only: 1 skip x staging, 2 skip ReLU epilogue, 4 skip latent math (timing experiments)
+  long long* trace;            // optional [6][402] event trace of CTA 0 (phase + 32), else nullptr
   float* eps_local[3];         // pre-generated noise per latent block, local (n_mc, B, nz_b) order (noise_fill_kernel), or null
 };
 bool enc_fused_supports(const EncFusedParams& p);

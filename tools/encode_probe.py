@@ -43,19 +43,40 @@ for rows in rows_list:
     print(f"rows {rows:8d}: {us:8.1f} us per call, {tiles_per_cta:6.1f} tiles per CTA, {rows / us * 1e-3:6.2f} G rows/s, "
           f"{rows * 300 / us * 1e-3:7.1f} GB/s algorithmic")
 
-# per-role cycle accounting of CTA 0 (enc_fused_kernel's PH counters)
-rows = 524288
-x, _, _ = bench.synth(case_mod, rows, 2000, dev)
-buf = torch.zeros(32, dtype=torch.int64, device=dev)
-_lib.check(eng.lib.dpivae_set_phase_buffer(eng.handle, C.c_void_p(buf.data_ptr())))
-eng.encode(x, 1, False)
-torch.cuda.synchronize()
-_lib.check(eng.lib.dpivae_set_phase_buffer(eng.handle, C.c_void_p(None)))
-v = buf.cpu().tolist()
-names = ["front: wait L1", "front: wait A free", "front: relu", "front: stage x", "latent: wait heads", "latent: load heads", "latent: sample + store",
-         "issue: wait x", "issue: L1 MMAs", "issue: wait relu", "issue: wait O free", "issue: head MMAs", "(tiles)",
-         "front: stage x: split + st.shared", "front: stage x: proxy fence + arrive", "front: relu: first tcgen05.ld"]
-nt = max(v[12], 1)
-print(f"CTA 0, {nt} tiles of {rows} rows; cycles per tile:")
-for nme, c_ in zip(names, v):
-    print(f"  {nme:24s} {c_ / nt:8.0f}")
+def phase_run(dbg):
+    os.environ["DPIVAE_ENC_DBG"] = str(dbg)
+    rows = 524288
+    x, _, _ = bench.synth(case_mod, rows, 2000, dev)
+    os.environ["DPIVAE_ENCODE_TRACE"] = "1"
+    buf = torch.zeros(32 + 6 * 402, dtype=torch.int64, device=dev)
+    _lib.check(eng.lib.dpivae_set_phase_buffer(eng.handle, C.c_void_p(buf.data_ptr())))
+    eng.encode(x, 1, False)
+    torch.cuda.synchronize()
+    _lib.check(eng.lib.dpivae_set_phase_buffer(eng.handle, C.c_void_p(None)))
+    v = buf.cpu().tolist()
+    names = ["front (unit 0): wait L1", "front: wait A free", "front: relu", "front: wait X free + stage x + fetch", "latent: wait heads", "latent: load heads",
+             "latent: sample + store", "issue: wait x", "issue: wait O free", "issue: wait relu (3 units)", "issue: head MMAs", "issue: L1 MMAs"]
+    nt = max(v[12], 1)
+    print(f"dbg={dbg} (1 skip x staging, 2 skip ReLU epilogue, 4 skip latent math): CTA 0, {nt} tiles of {rows} rows; cycles per tile:")
+    for nme, c_ in zip(names, v):
+        print(f"  {nme:40s} {c_ / nt:8.0f}")
+    return v
+
+
+for dbg in (1, 2, 3, 4, 7):
+    phase_run(dbg)
+v = phase_run(0)
+# event timeline of CTA 0 (first tiles): per role, (cycle since the first event, event code)
+roles = ["relu g0", "relu g1", "relu g2", "latent s0", "latent s1", "issue"]
+ev = []
+for ri, nme in enumerate(roles):
+    t = v[32 + ri * 402: 32 + (ri + 1) * 402]
+    n = int(t[400])
+    ev += [(t[2 * i], nme, t[2 * i + 1]) for i in range(n)]
+ev.sort()
+t0 = ev[0][0] if ev else 0
+legend = ("front: 1xx L1 done seen, 2xx A free seen, 3xx relu done, 4xx X free seen, 5xx staged, 6xx fetched | latent: 1xx heads seen, 2xx loaded, 3xx done | "
+          "issue: 1xx x ready, 2xx O free, u3xx relu_u seen, u4xx head_u issued, u5xx L1_u issued (xx = tile)")
+print(legend)
+for t, nme, code in ev[:260]:
+    print(f"{t - t0:8d}  {nme:10s} {code}")
