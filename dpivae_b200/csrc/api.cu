@@ -147,8 +147,13 @@ static int build_plan(dpivae_model* h) {
     hrow += 2 * nzb + nzb * nzb;
   }
   P.nL = nL;
-  P.hpri[0] = hrow; hrow += 2 * d.nz_c;
-  P.hpri[1] = hrow; hrow += 2 * d.nz_y;
+  // conditional prior nets: FactorizedNN heads [mean | sigma] or, with --full_cov_prior, FullCovarianceNN heads [mean | sigma | cov]
+  const bool pfull = d.prior[0].out_dim == 2 * d.nz_c + d.nz_c * d.nz_c && d.prior[1].out_dim == 2 * d.nz_y + d.nz_y * d.nz_y;
+  P.prior_full = pfull ? 1 : 0;
+  P.pl_off[0] = 0; P.pl_off[1] = d.nz_c * (d.nz_c - 1) / 2;
+  P.npL = pfull ? P.pl_off[1] + d.nz_y * (d.nz_y - 1) / 2 : 0;
+  P.hpri[0] = hrow; hrow += 2 * d.nz_c + (pfull ? d.nz_c * d.nz_c : 0);
+  P.hpri[1] = hrow; hrow += 2 * d.nz_y + (pfull ? d.nz_y * d.nz_y : 0);
   P.O_tot = hrow;
   h->O_tot = hrow;
   for (int i = 0; i < DPIVAE_MAX_ZX; ++i) {
@@ -166,8 +171,8 @@ static int build_plan(dpivae_model* h) {
   if (check_mlp2(d.fx, nzd, 128, d.nd_x, d.n_params, "decoder_x")) return 1;
   if (check_mlp2(d.dec_c, d.nz_c, 64, 2 * d.nd_c, d.n_params, "decoder_c")) return 1;
   if (check_mlp2(d.dec_y, d.nz_y, 64, 2 * d.nd_y, d.n_params, "decoder_y")) return 1;
-  if (check_mlp2(d.prior[0], d.nd_c, 64, 2 * d.nz_c, d.n_params, "prior_net_c")) return 1;
-  if (check_mlp2(d.prior[1], d.nd_y, 64, 2 * d.nz_y, d.n_params, "prior_net_y")) return 1;
+  if (check_mlp2(d.prior[0], d.nd_c, 64, 2 * d.nz_c + (pfull ? d.nz_c * d.nz_c : 0), d.n_params, "prior_net_c")) return 1;
+  if (check_mlp2(d.prior[1], d.nd_y, 64, 2 * d.nz_y + (pfull ? d.nz_y * d.nz_y : 0), d.n_params, "prior_net_y")) return 1;
   if (d.model_type == DPIVAE_MODEL_P) {
     const int nzs[3] = {d.nz_x, d.nz_c, d.nz_y};
     for (int e = 0; e < 3; ++e)
@@ -215,8 +220,8 @@ static int build_plan(dpivae_model* h) {
   P.s_HD = o; o += 128 * LDP; act_rows += 128;
   P.s_XHD = o; o += pad4(d.nd_x) * LDP; act_rows += pad4(d.nd_x);
   P.s_FEAT = act_start;
-  P.rp_loc = 0; P.rp_L = Z; P.rp_pmu = Z + nL; P.rp_psig = P.rp_pmu + nzd; P.n_rowpar = P.rp_psig + nzd;
-  P.f_loc = 0; P.f_L = Z; P.f_pmu = Z + nL; P.f_psig = P.f_pmu + nzd; P.n_feat = P.f_psig + nzd;
+  P.rp_loc = 0; P.rp_L = Z; P.rp_pmu = Z + nL; P.rp_psig = P.rp_pmu + nzd; P.rp_pL = P.rp_psig + nzd; P.n_rowpar = P.rp_pL + P.npL;
+  P.f_loc = 0; P.f_L = Z; P.f_pmu = Z + nL; P.f_psig = P.f_pmu + nzd; P.f_pL = P.f_psig + nzd; P.n_feat = P.f_pL + P.npL;
   if (P.n_feat > act_rows) return fail("internal: gradient feature rows exceed the activation region");
   auto rows = [&](int r) { int s = o; o += r * LDP; return s; };
   P.s_EPS = rows(pad4(Z));
@@ -610,8 +615,10 @@ static int run_loss(dpivae_handle_t h, const dpivae_batch_t* bt, const dpivae_rn
   int launches = 0;
 
   const bool extra_out = out && (out->xh_p || out->xh_d || out->ch || out->log_sigma_c || out->yh || out->log_sigma_y);
+  // (full-covariance conditional priors, --full_cov_prior, run the fp32 decoder kernel: the latent kernels of the
+  // tensor-core path implement the diagonal priors of the reference's default)
   const bool use_tc = h->math_mode != DPIVAE_MATH_FP32 && h->tc_ok && !latent_only && !bt->cond && !extra_out &&
-                      bt->n_mc >= 8 && bt->n_mc <= 128;
+                      bt->n_mc >= 8 && bt->n_mc <= 128 && !h->dec.prior_full;
   h->last_dec_tc = use_tc ? 1 : 0;
   const int grid_dec = use_tc ? L.tc_grid : L.grid_dec;
 
@@ -636,7 +643,7 @@ static int run_loss(dpivae_handle_t h, const dpivae_batch_t* bt, const dpivae_rn
   EncParams E2 = E;
   E2.n_units = h->enc.n_units - h->n_enc_units;
   for (int u = 0; u < E2.n_units; ++u) E2.u[u] = h->enc.u[h->n_enc_units + u];
-  const bool prior_fast = prior_kernels_support(E2) && bt->B >= 2048;   // small batches: units in parallel CTA columns instead
+  const bool prior_fast = prior_kernels_support(E2) && bt->B >= 2048 && !h->dec.prior_full;   // small batches: units in parallel CTA columns instead
   const long long nt128 = (bt->B + 127) / 128;
   const int grid_etc = (int)(nt128 < h->sm_count ? nt128 : h->sm_count);
   const bool fused_encode = latent_only && enc_tc && h->enc_fused_ok && !getenv("DPIVAE_NO_FUSED_ENCODE");
@@ -991,9 +998,9 @@ int dpivae_prior_net(dpivae_handle_t h, const float* c, const float* y, int64_t 
   for (int u = 0; u < E2.n_units; ++u) E2.u[u] = E.u[h->n_enc_units + u];
   if (prior_kernels_support(E2)) launch_prior_fwd(E2, h->sm_count, st);
   else launch_enc_fwd(E2, L.grid_enc, enc_smem_bytes(h->enc, true), st);
-  launch_prior_post(E.headpre, B, h->dec.hpri[0], h->d.nz_c, loc_c, scale_tril_c, st);
+  launch_prior_post(E.headpre, B, h->dec.hpri[0], h->d.nz_c, h->dec.prior_full, loc_c, scale_tril_c, st);
   int launches = 2;
-  if (y) { launch_prior_post(E.headpre, B, h->dec.hpri[1], h->d.nz_y, loc_y, scale_tril_y, st); ++launches; }
+  if (y) { launch_prior_post(E.headpre, B, h->dec.hpri[1], h->d.nz_y, h->dec.prior_full, loc_y, scale_tril_y, st); ++launches; }
   h->last_launches = launches;
   CUDA_OK(cudaGetLastError());
   return 0;

@@ -185,6 +185,18 @@ __global__ void __launch_bounds__(NT, 1) dec_kernel(const __grid_constant__ DecP
       ROWPAR[(P.rp_pmu + k) * RBMAX + r] = mu;
       ROWPAR[(P.rp_psig + k) * RBMAX + r] = sg;
     }
+    // --full_cov_prior: strict lower triangle of the conditional priors' factors (clamped f_cov head, models/encoders.py:38-43)
+    for (int e = tid; e < RBMAX * P.npL; e += NT) {
+      const int li = e / RBMAX, r = e - li * RBMAX;
+      const long long lrow = row0 + min(r, nrows - 1);
+      const int which = li < P.pl_off[1] ? 0 : 1;
+      const int nzk = which ? P.nz_y : P.nz_c;
+      int l = li - P.pl_off[which], i = 1;
+      while (l >= i) { l -= i; ++i; }   // l = j < i
+      float v = 0.0f;
+      if (which == 0 || P.y != nullptr) v = clampf_(P.headpre[(long long)(P.hpri[which] + 2 * nzk + i * nzk + l) * B + lrow], -20.0f, 20.0f);
+      ROWPAR[(P.rp_pL + li) * RBMAX + r] = v;
+    }
     for (int e = tid; e < RBMAX * (P.nd_c + P.nd_y); e += NT) {
       const int j = e / RBMAX, r = e - j * RBMAX;
       const long long lrow = row0 + min(r, nrows - 1);
@@ -284,30 +296,38 @@ __global__ void __launch_bounds__(NT, 1) dec_kernel(const __grid_constant__ DecP
           if (b == 0) dens = lq - (ld1 + ld2);
           else dens += lq;
         }
+        // strict-lower factor entry (i, j), j < i, of conditional prior `which` (zero for the default diagonal priors)
+        auto pL = [&](int which, int i, int j) -> float {
+          return P.prior_full ? ROWPAR[(P.rp_pL + P.pl_off[which] + i * (i - 1) / 2 + j) * RBMAX + r] : 0.0f;
+        };
         if (P.cond) {
-          for (int k = 0; k < P.nz_c; ++k)
-            ZD[k * LDP + p] = fmaf(ROWPAR[(P.rp_psig + k) * RBMAX + r], EPSC[k * LDP + p], ROWPAR[(P.rp_pmu + k) * RBMAX + r]);
+          // zc = prior loc + prior scale_tril eps (models/vae.py:165-167, models/encoders.py:84-86)
+          for (int k = P.nz_c - 1; k >= 0; --k) {
+            float acc = fmaf(ROWPAR[(P.rp_psig + k) * RBMAX + r], EPSC[k * LDP + p], ROWPAR[(P.rp_pmu + k) * RBMAX + r]);
+            if (P.prior_full)
+              for (int j = 0; j < k; ++j) acc = fmaf(pL(0, k, j), EPSC[j * LDP + p], acc);
+            ZD[k * LDP + p] = acc;
+          }
         }
         for (int j = 0; j < P.nd_p; ++j) ZXIN[(P.nz_x + j) * LDP + p] = ROWRAW[P.idx_c_phys[j] * RBMAX + r];
-        // conditional priors p(zc|c), p(zy|y): diagonal MultivariateNormal.log_prob
+        // conditional priors p(zc|c), p(zy|y): MultivariateNormal(loc, scale_tril).log_prob (models/vae.py:202-203) with
+        // t = L^-1 (z - loc) by forward substitution (diagonal L for the default FactorizedNN priors)
         float lpc = 0.0f, lpy = 0.0f;
-        {
-          float mh = 0.0f, hl = 0.0f;
-          for (int k = 0; k < P.nz_c; ++k) {
-            const float sg = ROWPAR[(P.rp_psig + k) * RBMAX + r];
-            const float t = (ZD[k * LDP + p] - ROWPAR[(P.rp_pmu + k) * RBMAX + r]) / sg;
+        for (int which = 0; which < 2; ++which) {
+          const int k0 = which ? P.nz_c : 0, nzk = which ? P.nz_y : P.nz_c;
+          float mh = 0.0f, hl = 0.0f, tv[MAXZ];
+          for (int i = 0; i < nzk; ++i) {
+            const float sg = ROWPAR[(P.rp_psig + k0 + i) * RBMAX + r];
+            float d = ZD[(k0 + i) * LDP + p] - ROWPAR[(P.rp_pmu + k0 + i) * RBMAX + r];
+            if (P.prior_full)
+              for (int j = 0; j < i; ++j) d = fmaf(-pL(which, i, j), tv[j], d);
+            const float t = d / sg;
+            tv[i] = t;
             mh = fmaf(t, t, mh);
             hl += logf(sg);
           }
-          lpc = -0.5f * ((float)P.nz_c * LOG_2PI + mh) - hl;
-          mh = 0.0f; hl = 0.0f;
-          for (int k = P.nz_c; k < nzd; ++k) {
-            const float sg = ROWPAR[(P.rp_psig + k) * RBMAX + r];
-            const float t = (ZD[k * LDP + p] - ROWPAR[(P.rp_pmu + k) * RBMAX + r]) / sg;
-            mh = fmaf(t, t, mh);
-            hl += logf(sg);
-          }
-          lpy = -0.5f * ((float)P.nz_y * LOG_2PI + mh) - hl;
+          const float lp = -0.5f * ((float)nzk * LOG_2PI + mh) - hl;
+          if (which) lpy = lp; else lpc = lp;
         }
         if (P.zin_x != nullptr && valid) {
           // DPIVAE.decode (models/vae.py:153-158): the caller's latents (n, B, .) replace the sampled ones
@@ -557,6 +577,7 @@ __global__ void __launch_bounds__(NT, 1) dec_kernel(const __grid_constant__ DecP
           const long long q = q0 + p;
           const int r = (int)((q < npairs ? q : npairs - 1) / n);
           const float bw = P.beta_x * SC[SC_W * LDP + p];
+          if (!P.prior_full) {
           for (int k = prt; k < nzd; k += 4) {
             float g = -P.lambda_g0 * DZD[k * LDP + p] + (k < P.nz_c ? DZC[k * LDP + p] : DZY[(k - P.nz_c) * LDP + p]);
             const float sg = ROWPAR[(P.rp_psig + k) * RBMAX + r];
@@ -565,6 +586,33 @@ __global__ void __launch_bounds__(NT, 1) dec_kernel(const __grid_constant__ DecP
             FEAT[(P.f_pmu + k) * LDP + p] = -bw * t / sg;
             FEAT[(P.f_psig + k) * LDP + p] = -bw * (t * t - 1.0f) / sg;
             FEAT[(P.f_loc + P.nz_x + k) * LDP + p] = g;
+          }
+          } else if (prt < 2) {
+            // full factor L of prior `which` = prt: t = L^-1 (z - loc), s = L^-T t;  d log p / d z = -s, d / d loc = s,
+            // d / d L_ij = s_i t_j - [i == j] / L_ii  (i >= j); the loss carries -bw log p
+            const int which = prt, k0 = which ? P.nz_c : 0, nzk = which ? P.nz_y : P.nz_c;
+            auto pLb = [&](int i, int j) -> float { return ROWPAR[(P.rp_pL + P.pl_off[which] + i * (i - 1) / 2 + j) * RBMAX + r]; };
+            float tv[MAXZ], sv[MAXZ];
+            for (int i = 0; i < nzk; ++i) {
+              float d = ZD[(k0 + i) * LDP + p] - ROWPAR[(P.rp_pmu + k0 + i) * RBMAX + r];
+              for (int j = 0; j < i; ++j) d = fmaf(-pLb(i, j), tv[j], d);
+              tv[i] = d / ROWPAR[(P.rp_psig + k0 + i) * RBMAX + r];
+            }
+            for (int i = nzk - 1; i >= 0; --i) {
+              float d = tv[i];
+              for (int j = i + 1; j < nzk; ++j) d = fmaf(-pLb(j, i), sv[j], d);
+              sv[i] = d / ROWPAR[(P.rp_psig + k0 + i) * RBMAX + r];
+            }
+            for (int i = 0; i < nzk; ++i) {
+              const int k = k0 + i;
+              const float sg = ROWPAR[(P.rp_psig + k) * RBMAX + r];
+              float g = -P.lambda_g0 * DZD[k * LDP + p] + (which == 0 ? DZC[i * LDP + p] : DZY[i * LDP + p]);
+              g += bw * sv[i];
+              FEAT[(P.f_pmu + k) * LDP + p] = -bw * sv[i];
+              FEAT[(P.f_psig + k) * LDP + p] = -bw * (sv[i] * tv[i] - 1.0f / sg);
+              for (int j = 0; j < i; ++j) FEAT[(P.f_pL + P.pl_off[which] + i * (i - 1) / 2 + j) * LDP + p] = -bw * sv[i] * tv[j];
+              FEAT[(P.f_loc + P.nz_x + k) * LDP + p] = g;
+            }
           }
           for (int i = prt; i < P.nz_x; i += 4) {
             float g = DZX[i * LDP + p];
@@ -682,6 +730,18 @@ __global__ void __launch_bounds__(NT, 1) dec_kernel(const __grid_constant__ DecP
           const float pm = P.headpre[om], ps = P.headpre[os];
           P.gpre[om] = (pm >= -50.0f && pm <= 50.0f) ? ROWACC[(P.f_pmu + k) * racc_ld + r] : 0.0f;
           P.gpre[os] = (ps >= -7.0f && ps <= 3.0f) ? ROWACC[(P.f_psig + k) * racc_ld + r] * expf(ps) : 0.0f;
+          if (P.prior_full) {
+            // f_cov entries of factor row kk: the strict lower triangle gets the L gradient (through the clamp), the rest zero
+            for (int j = 0; j < nzk; ++j) {
+              const long long oc = (long long)(P.hpri[which] + 2 * nzk + kk * nzk + j) * B + lrow;
+              float g = 0.0f;
+              if (j < kk) {
+                const float pc = P.headpre[oc];
+                g = (pc >= -20.0f && pc <= 20.0f) ? ROWACC[(P.f_pL + P.pl_off[which] + kk * (kk - 1) / 2 + j) * racc_ld + r] : 0.0f;
+              }
+              P.gpre[oc] = g;
+            }
+          }
         }
       }
     }

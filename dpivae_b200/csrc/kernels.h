@@ -68,6 +68,9 @@ struct DecParams {
   Mlp2S fx, dc, dy;
   long long g_lsx;              // offset of log_sigma_x in the flat buffers
   int henc[3], hpri[2], O_tot;  // feature rows in headpre / gpre
+  // --full_cov_prior (dpivae.py:151-153): the conditional priors carry a full lower-triangular factor; strict-lower entries of
+  // prior `which` at rp_pL / f_pL + pl_off[which] + i (i - 1) / 2 + j, head rows hpri[which] + [mean nz | sigma nz | cov nz * nz]
+  int prior_full, npL, pl_off[2], rp_pL, f_pL;
   // smem plan (float offsets); rows have leading dimension LDP
   int s_zero_end;               // everything below is zero-filled once
   int s_A[4];                   // physics MLP hidden activations (layer outputs 0..n-2)
@@ -107,7 +110,7 @@ struct DecParams {
 };
 
 // DPIVAE.prior_net post-processing and GaussianEncoder.sample on given (loc, scale_tril) (optim_kernels.cu)
-void launch_prior_post(const float* headpre, long long B, int row0, int nz, float* loc, float* tril, cudaStream_t s);
+void launch_prior_post(const float* headpre, long long B, int row0, int nz, int full, float* loc, float* tril, cudaStream_t s);
 void launch_gaussian_sample(const float* loc, const float* tril, const float* eps, int n, long long B, int nz, float* z,
                             float* dens, cudaStream_t s);
 

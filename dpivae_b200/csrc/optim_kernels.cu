@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(1024) advance_kernel(const AdvanceParams P) {
 
 // FactorizedNN head post-processing (models/encoders.py:121-128): loc = clamp(pre, +-50), sigma = exp(clamp(pre, -7, 3)),
 // scale_tril = diag(sigma + 1e-8).  headpre rows [row0, row0 + nz) = mean head, [row0 + nz, row0 + 2 nz) = sigma head.
-__global__ void __launch_bounds__(256) prior_post_kernel(const float* __restrict__ headpre, long long B, int row0, int nz,
+__global__ void __launch_bounds__(256) prior_post_kernel(const float* __restrict__ headpre, long long B, int row0, int nz, int full,
                                                          float* __restrict__ loc, float* __restrict__ tril) {
   const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
@@ -139,7 +139,12 @@ __global__ void __launch_bounds__(256) prior_post_kernel(const float* __restrict
     const float pm = headpre[(long long)(row0 + i) * B + b], ps = headpre[(long long)(row0 + nz + i) * B + b];
     loc[b * nz + i] = fminf(fmaxf(pm, -50.0f), 50.0f);
     const float sg = expf(fminf(fmaxf(ps, -7.0f), 3.0f)) + 1e-8f;
-    for (int j = 0; j < nz; ++j) tril[(b * nz + i) * nz + j] = i == j ? sg : 0.0f;
+    // FullCovarianceNN (--full_cov_prior): strict lower triangle from the clamped f_cov head (models/encoders.py:38-43)
+    for (int j = 0; j < nz; ++j) {
+      float v = i == j ? sg : 0.0f;
+      if (full && j < i) v = fminf(fmaxf(headpre[(long long)(row0 + 2 * nz + i * nz + j) * B + b], -20.0f), 20.0f);
+      tril[(b * nz + i) * nz + j] = v;
+    }
   }
 }
 
@@ -216,8 +221,8 @@ void launch_reduce(const ReduceParams& p, cudaStream_t s) {
 void launch_gradnorm(const float* grads, long long n, float max_norm, float* clip_coef, cudaStream_t s) {
   gradnorm_kernel<<<1, 1024, 0, s>>>(grads, n, max_norm, clip_coef);
 }
-void launch_prior_post(const float* headpre, long long B, int row0, int nz, float* loc, float* tril, cudaStream_t s) {
-  prior_post_kernel<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(headpre, B, row0, nz, loc, tril);
+void launch_prior_post(const float* headpre, long long B, int row0, int nz, int full, float* loc, float* tril, cudaStream_t s) {
+  prior_post_kernel<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(headpre, B, row0, nz, full, loc, tril);
 }
 void launch_gaussian_sample(const float* loc, const float* tril, const float* eps, int n, long long B, int nz, float* z,
                             float* dens, cudaStream_t s) {

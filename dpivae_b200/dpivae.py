@@ -42,10 +42,8 @@ def setup_model(args, definition, data_train):
     input_transform_y = StandardScaler().fit(y_train)
 
     if args.full_cov_prior == True:  # noqa: E712
-        # dpivae.py:151-153 builds FullCovarianceNN prior nets here.  The fused kernels implement the diagonal
-        # (FactorizedNN) conditional priors only -- the reference default and every shipped preset -- so the flag is
-        # refused up front rather than at the first engine call
-        raise ValueError("full_cov_prior=True is not supported by the fused sm_100a kernels (diagonal conditional priors only)")
+        prior_net_c = GaussianEncoder(FullCovarianceNN(nz_c, nd_c, [64]))
+        prior_net_y = GaussianEncoder(FullCovarianceNN(nz_y, nd_y, [64]))
     elif args.full_cov_prior == False:  # noqa: E712
         prior_net_c = GaussianEncoder(FactorizedNN(nz_c, nd_c, [64]))
         prior_net_y = GaussianEncoder(FactorizedNN(nz_y, nd_y, [64]))

@@ -53,8 +53,8 @@ class _Engine:
             return dict(in_dim=l0.in_features, hid=l0.out_features, out_dim=l1.out_features,
                         w0=[l0.weight], b0=[l0.bias], w1=[l1.weight], b1=[l1.bias])
 
-        if isinstance(vae.prior_net_c.net, FullCovarianceNN) or isinstance(vae.prior_net_y.net, FullCovarianceNN):
-            raise ValueError("full_cov_prior=True is not supported by the fused kernels (diagonal prior nets only)")
+        if isinstance(vae.prior_net_c.net, FullCovarianceNN) != isinstance(vae.prior_net_y.net, FullCovarianceNN):
+            raise ValueError("the two conditional prior nets must be of the same kind (both FactorizedNN or both FullCovarianceNN)")
         enc_mods = [vae.encoder] + ([vae.encoder_c, vae.encoder_y] if vae.model_type == "P" else [])
         groups = []  # (name, unit dict)
         for name, m in zip(["encoder", "encoder_c", "encoder_y"], enc_mods):

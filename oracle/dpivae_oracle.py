@@ -70,6 +70,25 @@ def factorized_heads(sd, prefix, v_t, jitter=1e-8):
     return loc, sigma + jitter
 
 
+def prior_heads(sd, spec, prefix, v_t, nz):
+    """Conditional prior net -> (loc (B,nz), scale_tril (B,nz,nz)): FactorizedNN by default (dpivae.py:155-157),
+    FullCovarianceNN with `--full_cov_prior True` (dpivae.py:151-153)."""
+    if spec.get("full_cov_prior"):
+        return full_cov_heads(sd, prefix, v_t, nz)
+    loc, sig = factorized_heads(sd, prefix, v_t)
+    return loc, torch.diag_embed(sig)
+
+
+def tril_mvn_log_prob(z, loc, tril):
+    """MultivariateNormal(loc, scale_tril=tril).log_prob(z) (models/vae.py:202-203): z (n,B,nz), loc (B,nz), tril (B,nz,nz).
+    t = L^-1 (z - loc) by forward substitution; log p = -1/2 (nz log 2 pi + |t|^2) - sum log diag L."""
+    nz = loc.shape[-1]
+    d = (z - loc.unsqueeze(0)).unsqueeze(-1)                                   # (n,B,nz,1)
+    t = torch.linalg.solve_triangular(tril.unsqueeze(0).expand(z.shape[0], -1, -1, -1), d, upper=False).squeeze(-1)
+    hld = torch.diagonal(tril, dim1=-2, dim2=-1).log().sum(-1)
+    return -0.5 * (nz * LOG_2PI + (t * t).sum(-1)) - hld.unsqueeze(0)
+
+
 def sample_latent(loc, scale_tril, eps):
     """models/encoders.py:84-86 with injected eps (n,B,nz).
 
@@ -224,8 +243,8 @@ def forward(sd, spec, x, c, eps, cond=False, eps_cond=None):
         dens_z = (lq_x - ld) + lq_c + lq_y
     if cond:
         c_t = standardise(c, spec["mean_c"], spec["std_c"])
-        ploc, psig = factorized_heads(sd, "prior_net_c", c_t)
-        zc = ploc.unsqueeze(0) + psig.unsqueeze(0) * eps_cond
+        ploc, ptril = prior_heads(sd, spec, "prior_net_c", c_t, nz_c)
+        zc = ploc.unsqueeze(0) + torch.einsum("bij,nbj->nbi", ptril, eps_cond)
     n = zx.shape[0]
     c_phys = c[..., spec["idx_c_phys"]].unsqueeze(0).repeat(n, 1, 1)
     zx_in = torch.cat((zx, c_phys), dim=-1)
@@ -248,10 +267,16 @@ def loss(sd, spec, x, c, y, eps, beta_x=1.0, alpha_x=1.0, alpha_c=1.0, alpha_y=1
     xh = xh_p + xh_d
     c_t = standardise(c, spec["mean_c"], spec["std_c"])
     y_t = standardise(y, spec["mean_y"], spec["std_y"])
-    ploc_c, psig_c = factorized_heads(sd, "prior_net_c", c_t)
-    ploc_y, psig_y = factorized_heads(sd, "prior_net_y", y_t)
-    log_prior_z = log_prior_zx(zx, spec["prior_x"]) + diag_mvn_log_prob(zc, ploc_c, psig_c) \
-        + diag_mvn_log_prob(zy, ploc_y, psig_y)
+    if spec.get("full_cov_prior"):
+        ploc_c, ptril_c = prior_heads(sd, spec, "prior_net_c", c_t, spec["nz_c"])
+        ploc_y, ptril_y = prior_heads(sd, spec, "prior_net_y", y_t, spec["nz_y"])
+        log_prior_z = log_prior_zx(zx, spec["prior_x"]) + tril_mvn_log_prob(zc, ploc_c, ptril_c) \
+            + tril_mvn_log_prob(zy, ploc_y, ptril_y)
+    else:
+        ploc_c, psig_c = factorized_heads(sd, "prior_net_c", c_t)
+        ploc_y, psig_y = factorized_heads(sd, "prior_net_y", y_t)
+        log_prior_z = log_prior_zx(zx, spec["prior_x"]) + diag_mvn_log_prob(zc, ploc_c, psig_c) \
+            + diag_mvn_log_prob(zy, ploc_y, psig_y)
     KL_x = torch.mean(dens_z - log_prior_z, dim=0)
     R_x = normal_log_prob(x, xh, sd["log_sigma_x"]).sum(-1).mean(0)
     R_c = normal_log_prob(c, ch, lsc).sum(-1).mean(0)

@@ -30,9 +30,14 @@ TRAIN_LOG = ["ELBO", "KLx", "KLc", "KLy", "Rx", "Rc", "Ry", "reg", "lambda_x", "
 VAL_LOG = ["ELBO_val", "KLx_val", "KLc_val", "KLy_val", "Rx_val", "Rc_val", "Ry_val", "reg_val"]
 
 
+FULLCOV_CONFIGS = [("bridge", "P"), ("simple_beam", "S")]
+
+
 def load(case, mtype, ext=False):
-    """ext=True: the second fixture set (make_golden_ext.py): n_mc = 8, cond / lambda_x / saturation / edge / flagged trajectory."""
-    g = np.load(os.path.join(GOLDEN, f"{case}_{mtype}{'_ext' if ext else ''}.npz"))
+    """ext=True: the second fixture set (make_golden_ext.py): n_mc = 8, cond / lambda_x / saturation / edge / flagged trajectory.
+    ext="fullcov": the `--full_cov_prior True` fixtures (make_golden_fullcov.py)."""
+    suffix = "_fullcov" if ext == "fullcov" else ("_ext" if ext else "")
+    g = np.load(os.path.join(GOLDEN, f"{case}_{mtype}{suffix}.npz"))
     nz_x, nz_c, nz_y, nd_x, nd_c, nd_y = [int(v) for v in g["spec.dims"]]
     prior = [("uniform" if k == 0.0 else "normal", float(a), float(b)) for k, a, b in g["spec.prior_x"]]
     spec = {
@@ -41,6 +46,7 @@ def load(case, mtype, ext=False):
         "idx_c_phys": [int(i) for i in g["spec.idx_c_phys"]], "lambda_g0": float(g["spec.lambda_g0"]),
         "lambda_x": None, "lb": g["spec.lb"], "ub": g["spec.ub"], "prior_x": prior,
         "physics": physics_spec(case), "trainable": [str(k) for k in g["trainable"]],
+        "full_cov_prior": bool(int(g["spec.full_cov_prior"])) if "spec.full_cov_prior" in g.files else False,
     }
     for k in ["mean_x", "std_x", "mean_c", "std_c", "mean_y", "std_y"]:
         spec[k] = g[f"spec.{k}"]

@@ -162,16 +162,21 @@ def test_checkpoint_state_round_trip_on_host():
     assert "log_sigma_x" in st["model"] and "encoder.net.f_cov.weight" in st["model"]
 
 
-def test_setup_model_refuses_full_cov_prior_up_front():
-    """`--full_cov_prior` (dpivae.py:151-153) selects FullCovarianceNN conditional priors, which the fused kernels do not
-    implement: the flag is refused in `setup_model`, before any device work, with a ValueError."""
+def test_setup_model_builds_full_cov_prior_nets():
+    """`--full_cov_prior True` (dpivae.py:151-153): the conditional prior nets are FullCovarianceNN modules with an `f_cov`
+    head of nz * nz rows, under the reference's parameter names (host-side construction only; the kernels are exercised by
+    tests/test_gpu_fullcov.py)."""
     import importlib
 
     import dpivae_b200 as dpv
+    from dpivae_b200.modules import FullCovarianceNN
 
     case_mod = importlib.import_module("dpivae_b200.cases.simple_beam")
     g, spec, sd = gu.load("simple_beam", "S")
     x, c, y = (torch.from_numpy(g[k].copy()) for k in "xcy")
     args = make_args(case_mod, PRESET[("simple_beam", "S")], n_train=x.shape[0], n_batch=x.shape[0], full_cov_prior=True)
-    with pytest.raises(ValueError, match="full_cov_prior"):
-        dpv.setup_model(args, case_mod.definition, (x, c, y))
+    vae = dpv.setup_model(args, case_mod.definition, (x, c, y))
+    assert isinstance(vae.prior_net_c.net, FullCovarianceNN) and isinstance(vae.prior_net_y.net, FullCovarianceNN)
+    names = dict(vae.named_parameters())
+    assert tuple(names["prior_net_c.net.f_cov.weight"].shape) == (vae.nz_c * vae.nz_c, 64)
+    assert tuple(names["prior_net_y.net.f_cov.bias"].shape) == (vae.nz_y * vae.nz_y,)
