@@ -1,18 +1,20 @@
 // The MMA issue sequence of enc_fused_kernel's issue warp, alone on the SM (no waits on other warps): per tile
 // 3 x [head_u: 12 TS MMAs (N = 64 / 32 / 32) + commit ; L1_u: 15 SS MMAs (N = 64, K = 80) + commit].  Variants:
 //   0: the kernel's lambdas (run-time loops)   1: fully unrolled, immediates   2: as 1 but ONE commit per tile
+//   3: as 0 + tcgen05.fence::after_thread_sync before every group   4: as 3 + an mbarrier wait on an already completed phase
+//   5: as 4 + 20 more warps waiting on a barrier that never completes
 #include <cstdio>
 #include "tc.cuh"
 using namespace dpv;
 
 template <int VAR>
-__global__ void __launch_bounds__(128, 1) pat(long long* out, int ntiles, int terms, int ksx, int Hc, int Oc) {
+__global__ void __launch_bounds__(768, 1) pat(long long* out, int ntiles, int terms, int ksx, int Hc, int Oc, int rnd) {
   extern __shared__ __align__(1024) unsigned char smraw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + 200 * 1024);
   uint32_t* tptr = reinterpret_cast<uint32_t*>(bars + 16);
   const int tid = threadIdx.x;
-  for (int e = tid; e < 200 * 1024 / 4; e += 128) reinterpret_cast<uint32_t*>(smraw)[e] = 0x3c003c00u;
-  if (tid == 0) { for (int i = 0; i < 16; ++i) tc::mbar_init(bars + i, 1); tc::mbar_fence_init(); }
+  for (int e = tid; e < 200 * 1024 / 4; e += 768) { uint32_t h = (uint32_t)e * 2654435761u; h ^= h >> 15; reinterpret_cast<uint32_t*>(smraw)[e] = rnd ? ((h & 0x83ff83ffu) | 0x30003000u) : 0x3c003c00u; }
+  if (tid == 0) { for (int i = 0; i < 16; ++i) tc::mbar_init(bars + i, 1); tc::mbar_fence_init(); tc::mbar_arrive(bars + 10); }
   if (tid < 32) tc::tmem_alloc(tptr, 512);
   tc::fence_async_smem(); tc::fence_before_sync(); __syncthreads(); tc::fence_after_sync();
   if (*tptr != 0u) __trap();
@@ -56,9 +58,13 @@ __global__ void __launch_bounds__(128, 1) pat(long long* out, int ntiles, int te
       const int par = it & 1;
 #pragma unroll
       for (int u = 0; u < 3; ++u) {
-        if (VAR == 0) {
+        if (VAR == 0 || VAR >= 3) {
+          if (VAR >= 4) tc::mbar_wait(bars + 10, 0);
+          if (VAR >= 3) tc::fence_after_sync();
           issue_head(u, par);
           tc::commit_w(el, bars + u);
+          if (VAR >= 4) tc::mbar_wait(bars + 10, 0);
+          if (VAR >= 3) tc::fence_after_sync();
           issue_l1(u, par ^ 1);
           tc::commit_w(el, bars + 3 + u);
         } else {
@@ -96,7 +102,9 @@ __global__ void __launch_bounds__(128, 1) pat(long long* out, int ntiles, int te
     tc::commit_w(el, bars + 8);
     const long long t1 = clock64();
     tc::mbar_wait(bars + 8, 0);
-    if (tid == 0) { out[0] = t1 - t0; out[1] = clock64() - t0; }
+    if (tid == 0) { out[0] = t1 - t0; out[1] = clock64() - t0; tc::mbar_arrive(bars + 11); }
+  } else if (VAR == 5 && tid >= 128) {
+    tc::mbar_wait(bars + 11, 0);
   }
   tc::fence_before_sync(); __syncthreads();
   if (tid < 32) tc::tmem_dealloc(0u, 512);
@@ -105,7 +113,7 @@ __global__ void __launch_bounds__(128, 1) pat(long long* out, int ntiles, int te
 template <int V>
 static void run(long long* d, const char* name) {
   cudaFuncSetAttribute(pat<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024);
-  for (int rep = 0; rep < 2; ++rep) pat<V><<<1, 128, 201 * 1024>>>(d, 64, 3, 5, 192, 64);
+  for (int rep = 0; rep < 2; ++rep) pat<V><<<1, 768, 201 * 1024>>>(d, 64, 3, 5, 192, 64, V == 6 ? 1 : 0);
   cudaError_t e = cudaDeviceSynchronize();
   long long h[2]; cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
   printf("%-44s: issue %.0f cyc/tile, complete %.0f cyc/tile (81 MMAs; pipe floor 45 x 48 + 12 x 32 + 24 x 16 = 2928) [%s]\n", name, h[0] / 64.0, h[1] / 64.0,
@@ -116,5 +124,9 @@ int main() {
   run<0>(d, "kernel lambdas (run-time loops)");
   run<1>(d, "unrolled, immediates, 6 commits per tile");
   run<2>(d, "unrolled, immediates, 1 commit per tile");
+  run<3>(d, "lambdas + fence::after_thread_sync per group");
+  run<4>(d, "lambdas + fence + satisfied mbarrier wait");
+  run<5>(d, "  ... + 20 warps waiting on an mbarrier");
+  run<6>(d, "as 4 with pseudo-random operand data");
   return 0;
 }
