@@ -60,6 +60,20 @@ __device__ __forceinline__ float philox_normal_elem(unsigned long long seed, uns
   return (comp & 1) ? g.y : g.x;
 }
 
+// Block-wide copy of n floats global -> shared with EIGHT independent loads in flight per thread (a rolled copy loop waits
+// a full memory latency, ~0.6 us, per trip: the kernels' set-up copies of 10-16 k weights took 15-20 us that way).
+template <int NT>
+__device__ __forceinline__ void copy_g2s_batched(float* __restrict__ dst, const float* __restrict__ src, int n) {
+  const int tid = threadIdx.x;
+  for (int e0 = 0; e0 < n; e0 += 8 * NT) {
+    float t[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const int e = e0 + k * NT + tid; t[k] = e < n ? __ldg(src + e) : 0.0f; }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const int e = e0 + k * NT + tid; if (e < n) dst[e] = t[k]; }
+  }
+}
+
 // contiguous vector load / store of V floats (V = 1, 2, 4) from shared memory
 template <int V>
 __device__ __forceinline__ void ldv(const float* p, float* out) {

@@ -248,9 +248,8 @@ static __device__ __noinline__ void dec_tc_setup(const TcParams& T, unsigned cha
   float* FR = FX + ((n_fx + 3) & ~3);
   {
     const float* src = prm + P.fx.g_w0;
-    for (int e = tid; e < n_fx; e += NALL) FX[e] = src[e];
-    if constexpr (mlp)
-      for (int e = tid; e < n_fr; e += NALL) FR[e] = P.frozen[e];
+    copy_g2s_batched<NALL>(FX, src, n_fx);
+    if constexpr (mlp) copy_g2s_batched<NALL>(FR, P.frozen, n_fr);
   }
   __syncthreads();
   const int o_b0 = 128 * nzd, o_w1 = o_b0 + 128, o_b1 = o_w1 + ndx * 128;

@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(ENT, 1) enc_tc_bwd_kernel(const __grid_constan
     for (int u = 0; u < P.n_units; ++u) {
       const int nblk = P.O[u] * P.H[u];
       const float* src = prm + P.g_w1[u];
-      for (int e = tid; e < nblk; e += ENT) RAW[ro + e] = src[e];
+      copy_g2s_batched<ENT>(RAW + ro, src, nblk);
       wb[u] = RAW + ro;
       ro += nblk;
     }

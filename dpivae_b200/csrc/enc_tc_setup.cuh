@@ -67,14 +67,7 @@ __device__ __noinline__ void enc_tc_stage_fwd(const EncTcParams& P, unsigned cha
     for (int u = 0; u < P.n_units; ++u) {
       const int nblk = P.H[u] * K0 + P.H[u] + P.O[u] * P.H[u] + P.O[u];
       const float* src = prm + P.g_w0[u];
-      // independent loads, eight in flight per thread (a rolled loop waited ~0.6 us for each of its ~30 trips)
-      for (int e0 = 0; e0 < nblk; e0 += 8 * ENTF) {
-        float t[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { const int e = e0 + k * ENTF + tid; t[k] = e < nblk ? __ldg(src + e) : 0.0f; }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { const int e = e0 + k * ENTF + tid; if (e < nblk) RAW[ro + e] = t[k]; }
-      }
+      copy_g2s_batched<ENTF>(RAW + ro, src, nblk);
       ub[u] = RAW + ro;
       ro += nblk;
     }
