@@ -575,7 +575,7 @@ static WsLayout ws_layout(dpivae_handle_t h, int64_t B, int32_t n_mc) {
     const int Z = h->d.nz_x + h->d.nz_c + h->d.nz_y;
     L.rec = take(nt * (size_t)h->tc.rec_buf / 4);
     L.dzrec = take(nt * (size_t)Z * 128);
-    L.epsbuf = take(nt * (size_t)Z * 128);
+    L.epsbuf = take(nt * (size_t)Z * 128 + 16);   // tile records, or per-block local-order buffers (16-byte aligned blocks)
     L.rowkl = take((size_t)B);
   }
   L.hidrec = 0;
@@ -730,7 +730,22 @@ static int run_loss(dpivae_handle_t h, const dpivae_batch_t* bt, const dpivae_rn
     D.rec = (unsigned char*)(base + L.rec); D.rec_stride = h->tc.rec_buf;
     D.dzrec = (float*)(base + L.dzrec); D.epsbuf = (float*)(base + L.epsbuf); D.rowkl = (float*)(base + L.rowkl);
     D.gpre_max = (with_grad && enc_tc) ? (unsigned int*)(base + L.gmax) : nullptr;
-    { KTimer t(h, 5, st); launch_lat_fwd(D, L.tc_rowblocks, st); }
+    // compile-time shapes: thread-per-pair latent kernels, noise in the local (m, row, i) order of each noise tensor;
+    // an unsharded Philox call fills it ahead with one Philox evaluation per four elements (torch's own mapping)
+    static const bool lat_v1 = getenv("DPIVAE_LAT_V1") != nullptr, no_prepass = getenv("DPIVAE_NO_NOISE_PREPASS") != nullptr;
+    {
+      KTimer t(h, 5, st);
+      if (!lat_v1 && lat_pair_supported(D)) {
+        float* e0 = (float*)(base + L.epsbuf);
+        for (int b = 0; b < D.n_blk; ++b) { D.eps_local[b] = e0; e0 += ((size_t)bt->n_mc * bt->B * D.blk_size[b] + 3) & ~(size_t)3; }
+        if (rng->mode == 1 && bt->B_global == bt->B && bt->row_offset == 0 && !no_prepass) {
+          launch_lat_noise_fill(D, st);
+          D.eps_ready = 1;
+          ++launches;
+        }
+      }
+      launch_lat_fwd(D, L.tc_rowblocks, st);
+    }
     ++launches;
     T.d = D;
     T.terms = h->math_mode == DPIVAE_MATH_TC_FP16X3 ? 3 : 1;

@@ -107,6 +107,10 @@ struct DecParams {
   unsigned int* gpre_max;  // bits of max |gpre| over the encoder heads of the batch (lat_bwd -> enc_tc_bwd operand scale), or nullptr
   // decode-only calls (DPIVAE.decode, models/vae.py:153-158): user latents (n, B, .) replace the encoder's
   const float *zin_x, *zin_c, *zin_y;
+  // thread-per-pair latent kernels (lat_kernels.cu): noise in the LOCAL (m, row, i) order of each noise tensor, one buffer
+  // per latent block; eps_ready = already filled by lat_noise_fill_kernel (else the forward fills it when a backward follows)
+  float* eps_local[3];
+  int eps_ready;
 };
 
 // DPIVAE.prior_net post-processing and GaussianEncoder.sample on given (loc, scale_tril) (optim_kernels.cu)
@@ -133,6 +137,8 @@ int configure_dec_tc_kernel();
 size_t lat_smem_bytes(const DecParams& p, bool bwd);
 void launch_lat_fwd(const DecParams& p, long long n_tiles, cudaStream_t s);
 void launch_lat_bwd(const DecParams& p, long long n_tiles, cudaStream_t s);
+bool lat_pair_supported(const DecParams& p);
+void launch_lat_noise_fill(const DecParams& p, cudaStream_t s);
 int configure_lat_kernels();
 void launch_lat_encode(const DecParams& p, cudaStream_t s);
 bool dec_tc_has_variant(int phys_kind, int nd_x);

@@ -39,6 +39,8 @@ struct Shape {
   static constexpr bool K = MT >= 0;
   static constexpr int cZ = NX + NC + NY, cnzd = NC + NY, cnb = MT == 0 ? 3 : 1;
   static constexpr int cnL = MT == 0 ? tri(NX) + tri(NC) + tri(NY) : tri(cZ);
+  static constexpr int cNX = NX, cNC = NC, cNY = NY, cndc = NDC, cndy = NDY, cndp = NDP, cn_mc = NMC;
+  static constexpr int cn_rowpar = cZ + cnL + 2 * cnzd;   // == n_feat: row parameters and per-pair gradient features share one indexing
 #define DPV_SCALAR(name, val) \
   static __device__ __forceinline__ int name(const DecParams& P) { if constexpr (K) return (val); else return P.name; }
   DPV_SCALAR(model_type, MT) DPV_SCALAR(nz_x, NX) DPV_SCALAR(nz_c, NC) DPV_SCALAR(nz_y, NY) DPV_SCALAR(Z, cZ)
@@ -122,14 +124,14 @@ __device__ inline LatSmem lat_carve(float* sm, const DecParams& P, bool bwd) {
 }
 
 // per-row parameters of q(z|x) and of the conditional priors, raw c / y
-template <class D>
+template <class D, int NTH = LNT>
 __device__ __forceinline__ void load_row_params(const DecParams& P, const LatSmem& S, long long row0, int nrows, bool msk = false,
                                                 const float* rawh = nullptr) {
   const int tid = threadIdx.x, RB = D::RB(P), nzd = D::nz_c(P) + D::nz_y(P);
   const long long B = P.B;
   // head pre-activation of feature row f for tile row r: from the staged tile (backward, prefetched) or from global
   auto hp = [&](int f, int r, long long lrow) -> float { return rawh ? rawh[f * RBMAX + r] : P.headpre[(long long)f * B + lrow]; };
-  for (int e = tid; e < RB * D::Z(P); e += LNT) {
+  for (int e = tid; e < RB * D::Z(P); e += NTH) {
     const int i = e / RB, r = e - i * RB;
     const long long lrow = row0 + min(r, nrows - 1);
     const int b = block_of_l<D>(P, i), il = i - D::blk_start(P, b);
@@ -138,7 +140,7 @@ __device__ __forceinline__ void load_row_params(const DecParams& P, const LatSme
     // d clamp / d pre: 1 inside the clamp range (models/encoders.py:35-43); d exp(clamp(ps)) / d ps = exp(ps) inside
     if (msk) S.ROWMSK[(D::rp_loc(P) + i) * RBMAX + r] = (pm >= -50.0f && pm <= 50.0f) ? 1.0f : 0.0f;
   }
-  for (int e = tid; e < RB * D::nL(P); e += LNT) {
+  for (int e = tid; e < RB * D::nL(P); e += NTH) {
     const int li = e / RB, r = e - li * RB;
     const long long lrow = row0 + min(r, nrows - 1);
     const int b = D::L_blk(P, li), i = D::L_i(P, li), j = D::L_j(P, li), nzb = D::blk_size(P, b);
@@ -155,7 +157,7 @@ __device__ __forceinline__ void load_row_params(const DecParams& P, const LatSme
     S.ROWPAR[(D::rp_L(P) + li) * RBMAX + r] = v;
     if (msk) S.ROWMSK[(D::rp_L(P) + li) * RBMAX + r] = mk;
   }
-  for (int e = tid; e < RB * nzd; e += LNT) {
+  for (int e = tid; e < RB * nzd; e += NTH) {
     const int k = e / RB, r = e - k * RB;
     const long long lrow = row0 + min(r, nrows - 1);
     const int which = k < D::nz_c(P) ? 0 : 1;
@@ -177,7 +179,7 @@ __device__ __forceinline__ void load_row_params(const DecParams& P, const LatSme
     }
   }
   if (!msk)   // raw c / y are only used by the forward (decoder record)
-  for (int e = tid; e < RB * (D::nd_c(P) + D::nd_y(P)); e += LNT) {
+  for (int e = tid; e < RB * (D::nd_c(P) + D::nd_y(P)); e += NTH) {
     const int j = e / RB, r = e - j * RB;
     const long long lrow = row0 + min(r, nrows - 1);
     const long long drow = P.idx ? P.idx[lrow] : lrow;
@@ -586,6 +588,388 @@ __global__ void __launch_bounds__(LNT) lat_encode_kernel(const __grid_constant__
   if (P.out.dens) P.out.dens[q] = dens;
 }
 
+namespace {
+
+// =====================================================================================================================
+// Thread-per-pair kernels for the compile-time shapes (Shape::K): the same math as lat_fwd_kernel / lat_bwd_kernel above,
+// but one thread owns one (row, MC-sample) pair END TO END, with its noise, latents and gradients in registers and every
+// block / triangular loop unrolled; only the per-ROW quantities (clamped / exponentiated head outputs, their chain-rule
+// factors, log-determinants) are staged in shared memory, once per tile of RB rows.  The kernels above move every
+// intermediate through shared-memory planes between strided passes of 256 threads (two threads per pair, run-time index
+// arithmetic per element): 3840 / 2880 executed instructions per pair against ~700 here (plus the noise).
+//
+// Noise: the tile-ordered `epsbuf` record is replaced by a buffer in the LOCAL (m, row, i) order of each noise tensor
+// (P.eps_local[b]); on an unsharded Philox call it is filled AHEAD by lat_noise_fill_kernel with torch's own mapping --
+// one Philox4x32-10 evaluation + two Box-Muller pairs per FOUR elements -- instead of one evaluation per element (the
+// per-element generator was ~half of lat_fwd_kernel's instructions).  Row-sharded calls (elements of one evaluation
+// belong to different ranks) and injected noise keep the per-element path; the forward then stores what it drew.
+constexpr int PNT = 128;   // threads per CTA = pairs per tile
+
+template <int N>
+__device__ __forceinline__ void ldg_vec(const float* __restrict__ src, float* v) {
+  if constexpr (N % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < N / 4; ++i) { const float4 t = __ldg(reinterpret_cast<const float4*>(src) + i); v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w; }
+  } else if constexpr (N % 2 == 0) {
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) { const float2 t = __ldg(reinterpret_cast<const float2*>(src) + i); v[2 * i] = t.x; v[2 * i + 1] = t.y; }
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = __ldg(src + i);
+  }
+}
+template <int N>
+__device__ __forceinline__ void stg_vec(float* dst, const float* v) {
+  if constexpr (N % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < N / 4; ++i) reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  } else if constexpr (N % 2 == 0) {
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) reinterpret_cast<float2*>(dst)[i] = make_float2(v[2 * i], v[2 * i + 1]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) dst[i] = v[i];
+  }
+}
+
+// compile-time block geometry of shape D
+template <class D, int b> struct Blk {
+  static constexpr int nz = D::cnb == 1 ? D::cZ : (b == 0 ? D::cNX : (b == 1 ? D::cNC : D::cNY));
+  static constexpr int s = D::cnb == 1 ? 0 : (b == 0 ? 0 : (b == 1 ? D::cNX : D::cNX + D::cNC));
+  static constexpr int loff = D::cnb == 1 ? 0 : (b == 0 ? 0 : (b == 1 ? tri(D::cNX) : tri(D::cNX) + tri(D::cNC)));
+};
+
+// noise of latent block b for pair (m, local row lrow): eps[s .. s + nz)
+template <class D, int b>
+__device__ __forceinline__ void pair_eps_fwd(const DecParams& P, int m, long long lrow, bool store, float* eps) {
+  constexpr int nz = Blk<D, b>::nz, s = Blk<D, b>::s;
+  float* loc = P.eps_local[b] + ((long long)m * P.B + lrow) * nz;
+  if (P.eps_ready) {
+    ldg_vec<nz>(loc, eps + s);
+  } else {
+    const unsigned long long li0 = ((unsigned long long)m * (unsigned long long)P.Bg + (unsigned long long)(P.row_off + lrow)) * nz;
+    const unsigned long long off = P.rng.ss ? P.rng.ss->philox_off[b] : P.rng.offset[b];
+#pragma unroll
+    for (int i = 0; i < nz; ++i)
+      eps[s + i] = P.rng.mode == 0 ? P.rng.eps[b][li0 + i] : philox_normal_elem(P.rng.seed, off, P.rng.grid_threads[b], li0 + i);
+    if (store) stg_vec<nz>(loc, eps + s);
+  }
+}
+
+template <class D, int b>
+__device__ __forceinline__ void pair_sample_block(const DecParams& P, const float* ROWPAR, const float* ROWLOG, int prow, const float* eps,
+                                                  float* z, float* u, float& lq, float& ld1, float& ld2, float& lpx) {
+  constexpr int nz = Blk<D, b>::nz, s = Blk<D, b>::s, loff = Blk<D, b>::loff;
+  float ss = 0.0f;
+#pragma unroll
+  for (int i = 0; i < nz; ++i) {
+    float acc = ROWPAR[(s + i) * RBMAX + prow];
+#pragma unroll
+    for (int j = 0; j <= i; ++j) acc = fmaf(ROWPAR[(D::cZ + loff + i * (i + 1) / 2 + j) * RBMAX + prow], eps[s + j], acc);
+    ss = fmaf(eps[s + i], eps[s + i], ss);
+    const int gi = s + i;
+    if (gi < D::cNX) {
+      const float uu = sigmoidf_(acc);
+      const float a = P.ub[gi] - P.lb[gi];
+      const float zx = fmaf(uu, a, P.lb[gi]);
+      u[gi < D::cNX ? gi : 0] = uu;
+      z[gi] = zx;
+      if (ROWLOG != nullptr) {
+        ld1 += acc - 2.0f * softplusf_(acc);
+        ld2 += logf(fabsf(a));
+        if (P.prior_kind[gi] == 0) {
+          const bool inside = (zx >= P.prior_a[gi]) && (zx < P.prior_b[gi]);
+          lpx += (inside ? 0.0f : -INFINITY) - logf(P.prior_b[gi] - P.prior_a[gi]);
+        } else {
+          const float d = zx - P.prior_a[gi];
+          lpx += -(d * d) / (2.0f * P.prior_b[gi] * P.prior_b[gi]) - logf(P.prior_b[gi]) - LOG_SQRT_2PI;
+        }
+      }
+    } else {
+      z[gi] = acc;
+    }
+  }
+  if (ROWLOG != nullptr) lq += -0.5f * ((float)nz * LOG_2PI + ss) - ROWLOG[b * RBMAX + prow];
+}
+
+template <class D>
+__global__ void __launch_bounds__(PNT) lat_pair_fwd_kernel(const __grid_constant__ DecParams P) {
+  extern __shared__ __align__(16) float lsm[];
+  pdl_launch_dependents();   // the decoder kernel may stage its weights while these tiles are processed
+  constexpr int n = D::cn_mc, RB = TP / n, Z = D::cZ, NX = D::cNX, nzd = D::cnzd, nb = D::cnb, ndc = D::cndc, ndy = D::cndy;
+  constexpr int nzin = NX + D::cndp, c1 = nzd, cs0 = nzd + 1;
+  static_assert((n & (n - 1)) == 0 && n <= 32 && RB <= RBMAX, "MC count must be a power of two that fills whole warps");
+  LatSmem S;
+  S.ROWPAR = lsm;
+  S.ROWRAW = S.ROWPAR + D::cn_rowpar * RBMAX;
+  S.ROWLOG = S.ROWRAW + (ndc + ndy) * RBMAX;
+  const int p = threadIdx.x;
+  const long long B = P.B, rb = blockIdx.x, row0 = rb * RB;
+  const int nrows = (int)min((long long)RB, B - row0), npairs = nrows * n;
+  const bool pvalid = p < npairs;
+  const int pc = pvalid ? p : npairs - 1;
+  const int prow = pc / n, pm = pc - prow * n;
+  const bool mlp = P.phys_kind == 0;
+
+  // noise first: these loads (or the Philox evaluations) do not depend on the row parameters staged below
+  float eps[Z];
+  {
+    const bool store = pvalid && P.with_grad;
+    pair_eps_fwd<D, 0>(P, pm, row0 + prow, store, eps);
+    if constexpr (nb > 1) {
+      pair_eps_fwd<D, 1>(P, pm, row0 + prow, store, eps);
+      pair_eps_fwd<D, 2>(P, pm, row0 + prow, store, eps);
+    }
+  }
+  load_row_params<D, PNT>(P, S, row0, nrows);
+  __syncthreads();
+  for (int e = p; e < RB * (nb + 2); e += PNT) {
+    const int t = e / RB, r = e - t * RB;
+    float s = 0.0f;
+    if (t < nb) {
+      for (int i = 0; i < D::blk_size(P, t); ++i) s += logf(S.ROWPAR[(D::rp_L(P) + D::blk_loff(P, t) + i * (i + 1) / 2 + i) * RBMAX + r]);
+    } else {
+      const int k0 = t == nb ? 0 : D::cNC, k1 = t == nb ? D::cNC : nzd;
+      for (int k = k0; k < k1; ++k) s += logf(S.ROWPAR[(D::rp_psig(P) + k) * RBMAX + r]);
+    }
+    S.ROWLOG[t * RBMAX + r] = s;
+  }
+  __syncthreads();
+
+  float z[Z], u[NX > 0 ? NX : 1];
+  float lq = 0.0f, ld1 = 0.0f, ld2 = 0.0f, lpx = 0.0f;
+  pair_sample_block<D, 0>(P, S.ROWPAR, S.ROWLOG, prow, eps, z, u, lq, ld1, ld2, lpx);
+  if constexpr (nb > 1) {
+    pair_sample_block<D, 1>(P, S.ROWPAR, S.ROWLOG, prow, eps, z, u, lq, ld1, ld2, lpx);
+    pair_sample_block<D, 2>(P, S.ROWPAR, S.ROWLOG, prow, eps, z, u, lq, ld1, ld2, lpx);
+  }
+  const float dens = lq - (ld1 + ld2);
+  // conditional priors p(zc|c), p(zy|y): diagonal Gaussians (models/vae.py:200-207)
+  float kl = dens - lpx;
+#pragma unroll
+  for (int side = 0; side < 2; ++side) {
+    const int a_nz = side ? D::cNY : D::cNC, a_j0 = side ? D::cNC : 0;
+    float mh = 0.0f;
+#pragma unroll
+    for (int k = 0; k < (D::cNC > D::cNY ? D::cNC : D::cNY); ++k)
+      if (k < a_nz) {
+        const int kk = a_j0 + k;
+        const float t = (z[NX + kk] - S.ROWPAR[(D::rp_pmu(P) + kk) * RBMAX + prow]) / S.ROWPAR[(D::rp_psig(P) + kk) * RBMAX + prow];
+        mh = fmaf(t, t, mh);
+      }
+    kl -= -0.5f * ((float)a_nz * LOG_2PI + mh) - S.ROWLOG[(nb + side) * RBMAX + prow];
+  }
+  // per-row KL = mean over the MC axis (models/vae.py:207): the n samples of a row are n consecutive lanes
+  {
+    float s = pvalid ? kl : 0.0f;
+#pragma unroll
+    for (int off = n >> 1; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (pvalid && (p & (n - 1)) == 0) P.rowkl[row0 + prow] = s / (float)n;
+  }
+  if (pvalid && (P.out.dens || P.out.zx || P.out.zc || P.out.zy)) {
+    const long long o = (long long)pm * B + row0 + prow;
+    if (P.out.dens) P.out.dens[o] = dens;
+    if (P.out.zx) for (int k = 0; k < NX; ++k) P.out.zx[o * NX + k] = z[k];
+    if (P.out.zc) for (int k = 0; k < D::cNC; ++k) P.out.zc[o * D::cNC + k] = z[NX + k];
+    if (P.out.zy) for (int k = 0; k < D::cNY; ++k) P.out.zy[o * D::cNY + k] = z[NX + D::cNC + k];
+  }
+  // decoder-kernel input record: latent operand row [zd | 1 | physics input | 0] * 2^4 as fp16 hi / lo planes (physics
+  // input: standardised for the MLP surrogate, raw zx for the closed forms), then the raw covariates / labels per pair
+  unsigned char* rec = P.rec + rb * P.rec_stride;
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = 8 * hh + i;
+      float x = 0.0f;
+      if (k < nzd) x = pvalid ? z[NX + k] : 0.0f;
+      else if (k == c1) x = 1.0f;
+      else if (k >= cs0 && k < cs0 + nzin) {
+        const int q = k - cs0;
+        const float zz = q < NX ? z[q < NX ? q : 0] : S.ROWRAW[P.idx_c_phys[q - NX < 0 ? 0 : q - NX] * RBMAX + prow];
+        x = mlp ? (zz - P.phys_in_mean[q]) / P.phys_in_std[q] : zz;
+        if (!pvalid && mlp) x = 0.0f;
+      }
+      v[i] = x * 16.0f;
+    }
+    uint4 hi, lo;
+    tc::split8(v, hi, lo);
+    *reinterpret_cast<uint4*>(rec + (hh * TP + p) * 16) = hi;
+    *reinterpret_cast<uint4*>(rec + 4096 + (hh * TP + p) * 16) = lo;
+  }
+  float* raw = reinterpret_cast<float*>(rec + 8192);
+#pragma unroll
+  for (int j = 0; j < ndc + ndy; ++j) raw[j * TP + p] = S.ROWRAW[j * RBMAX + prow];
+}
+
+// feature row (shared index of ROWPAR / ROWMSK / FEAT) behind head-output row o of headpre / gpre, or -1 (the unused upper
+// triangle of a covariance head: zero gradient)
+template <class D>
+__device__ __forceinline__ int pair_src_feature(const DecParams& P, int o) {
+  int f = -1;
+  for (int b = 0; b < D::cnb; ++b) {
+    const int nzb = D::blk_size(P, b), s = D::blk_start(P, b), h0 = D::henc(P, b), loff = D::blk_loff(P, b);
+    if (o >= h0 && o < h0 + 2 * nzb + nzb * nzb) {
+      const int l = o - h0;
+      if (l < nzb) f = D::f_loc(P) + s + l;
+      else if (l < 2 * nzb) { const int il = l - nzb; f = D::f_L(P) + loff + il * (il + 1) / 2 + il; }
+      else { const int q = l - 2 * nzb, il = q / nzb, j = q - il * nzb; if (j < il) f = D::f_L(P) + loff + il * (il + 1) / 2 + j; }
+    }
+  }
+  for (int which = 0; which < 2; ++which) {
+    const int nzk = which ? D::cNY : D::cNC, h0 = D::hpri(P, which), k0 = which ? D::cNC : 0;
+    if (o >= h0 && o < h0 + 2 * nzk) { const int l = o - h0; f = l < nzk ? D::f_pmu(P) + k0 + l : D::f_psig(P) + k0 + (l - nzk); }
+  }
+  return f;
+}
+
+template <class D, int b>
+__device__ __forceinline__ void pair_grad_block(const DecParams& P, const float* ROWPAR, int prow, int p, float bw, const float* eps,
+                                                const float* z, const float* u, const float* dz, float* FEAT) {
+  constexpr int nz = Blk<D, b>::nz, s = Blk<D, b>::s, loff = Blk<D, b>::loff, NX = D::cNX, nzd = D::cnzd, Z = D::cZ;
+  constexpr int f_L = Z, f_pmu = Z + D::cnL, f_psig = f_pmu + nzd;
+#pragma unroll
+  for (int i = 0; i < nz; ++i) {
+    const int gi = s + i;
+    float gl;
+    if (gi < NX) {
+      float g = dz[nzd + gi];
+      if (P.prior_kind[gi] == 1) g += bw * (z[gi] - P.prior_a[gi]) / (P.prior_b[gi] * P.prior_b[gi]);
+      const float uu = u[gi < NX ? gi : 0];
+      gl = g * (P.ub[gi] - P.lb[gi]) * uu * (1.0f - uu) + bw * (2.0f * uu - 1.0f);
+    } else {
+      const int k = gi - NX;
+      const float sgm = ROWPAR[(f_psig + k) * RBMAX + prow];
+      const float t = (z[gi] - ROWPAR[(f_pmu + k) * RBMAX + prow]) / sgm;
+      gl = dz[k] + bw * t / sgm;
+      FEAT[(f_pmu + k) * PNT + p] = -bw * t / sgm;
+      FEAT[(f_psig + k) * PNT + p] = -bw * (t * t - 1.0f) / sgm;
+    }
+    FEAT[gi * PNT + p] = gl;
+#pragma unroll
+    for (int j = 0; j <= i; ++j) {
+      const int li = loff + i * (i + 1) / 2 + j;
+      float v = gl * eps[s + j];
+      if (j == i) v -= bw / ROWPAR[(f_L + li) * RBMAX + prow];
+      FEAT[(f_L + li) * PNT + p] = v;
+    }
+  }
+}
+
+template <class D>
+__global__ void __launch_bounds__(PNT) lat_pair_bwd_kernel(const __grid_constant__ DecParams P) {
+  extern __shared__ __align__(16) float lsm[];
+  pdl_launch_dependents();   // the encoder backward kernel may stage its weights while these tiles are processed
+  constexpr int n = D::cn_mc, RB = TP / n, Z = D::cZ, NX = D::cNX, nzd = D::cnzd, nb = D::cnb, NF = D::cn_rowpar;
+  static_assert(n % 4 == 0, "MC reduction reads float4 groups");
+  LatSmem S;
+  S.ROWPAR = lsm;
+  S.ROWMSK = S.ROWPAR + NF * RBMAX;
+  S.ROWRAW = nullptr;
+  S.FEAT = S.ROWMSK + NF * RBMAX;
+  int* SRC = reinterpret_cast<int*>(S.FEAT + NF * PNT);
+  const int p = threadIdx.x;
+  const long long B = P.B, rb = blockIdx.x, row0 = rb * RB;
+  const int nrows = (int)min((long long)RB, B - row0), npairs = nrows * n;
+  const bool pvalid = p < npairs;
+  const int pc = pvalid ? p : npairs - 1;
+  const int prow = pc / n, pm = pc - prow * n;
+  const float wpair = 1.0f / ((float)P.Bg * (float)(P.nd_x + D::cndc + D::cndy) * (float)n);
+  const float bw = pvalid ? P.beta_x * wpair : 0.0f;
+
+  // this pair's noise (local order, written by the forward or by the noise pre-pass) and dL/dz (decoder kernel's record)
+  float eps[Z], dz[Z];
+  ldg_vec<Blk<D, 0>::nz>(P.eps_local[0] + ((long long)pm * B + row0 + prow) * Blk<D, 0>::nz, eps + Blk<D, 0>::s);
+  if constexpr (nb > 1) {
+    ldg_vec<Blk<D, 1>::nz>(P.eps_local[1] + ((long long)pm * B + row0 + prow) * Blk<D, 1>::nz, eps + Blk<D, 1>::s);
+    ldg_vec<Blk<D, 2>::nz>(P.eps_local[2] + ((long long)pm * B + row0 + prow) * Blk<D, 2>::nz, eps + Blk<D, 2>::s);
+  }
+  {
+    const float* DZ = P.dzrec + rb * (long long)Z * TP;
+#pragma unroll
+    for (int k = 0; k < Z; ++k) dz[k] = pvalid ? __ldg(DZ + k * TP + p) : 0.0f;
+  }
+  for (int o = p; o < P.O_tot; o += PNT) SRC[o] = pair_src_feature<D>(P, o);
+  load_row_params<D, PNT>(P, S, row0, nrows, true);
+  __syncthreads();
+
+  {
+    float z[Z], u[NX > 0 ? NX : 1];
+    float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;
+    pair_sample_block<D, 0>(P, S.ROWPAR, nullptr, prow, eps, z, u, d0, d1, d2, d3);
+    pair_grad_block<D, 0>(P, S.ROWPAR, prow, p, bw, eps, z, u, dz, S.FEAT);
+    if constexpr (nb > 1) {
+      pair_sample_block<D, 1>(P, S.ROWPAR, nullptr, prow, eps, z, u, d0, d1, d2, d3);
+      pair_grad_block<D, 1>(P, S.ROWPAR, prow, p, bw, eps, z, u, dz, S.FEAT);
+      pair_sample_block<D, 2>(P, S.ROWPAR, nullptr, prow, eps, z, u, d0, d1, d2, d3);
+      pair_grad_block<D, 2>(P, S.ROWPAR, prow, p, bw, eps, z, u, dz, S.FEAT);
+    }
+  }
+  __syncthreads();
+  // head-output gradients: MC-axis sum of the feature (n consecutive pairs, fixed order) times the clamp / exp chain-rule
+  // factor of the head (models/encoders.py:35-43); consecutive threads write consecutive rows of one feature row of gpre
+  float gmax = 0.0f;
+  const int henc_end = D::hpri(P, 0);
+  for (int e = p; e < P.O_tot * RB; e += PNT) {
+    const int o = e / RB, r = e - o * RB;
+    if (r < nrows) {
+      const int f = SRC[o];
+      float g = 0.0f;
+      if (f >= 0) {
+        const float4* s4 = reinterpret_cast<const float4*>(S.FEAT + f * PNT + r * n);
+        float s = 0.0f;
+#pragma unroll
+        for (int m = 0; m < (n >> 2); ++m) {
+          const float4 t = s4[m];
+          s += (t.x + t.y) + (t.z + t.w);
+        }
+        g = S.ROWMSK[f * RBMAX + r] * s;
+      }
+      P.gpre[(long long)o * B + row0 + r] = g;
+      if (o < henc_end) gmax = fmaxf(gmax, fabsf(g));
+    }
+  }
+  if (P.gpre_max != nullptr) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, off));
+    if ((p & 31) == 0 && gmax > 0.0f && gmax < __int_as_float(0x7f800000)) atomicMax(P.gpre_max, __float_as_uint(gmax));
+  }
+}
+
+// Reparameterisation noise of an unsharded Philox call, generated the way torch's normal_ kernel generates it: ONE
+// Philox4x32-10 evaluation + two Box-Muller pairs per FOUR elements (generator thread idx, loop iteration j -> elements
+// (4 j + k) GT + idx, k = 0..3; the same stream as philox_normal_elem, common.cuh, which spends one evaluation per
+// element).  grid = (generator threads / 256, loop iterations, latent blocks); output order == torch's (m, row, i).
+__global__ void __launch_bounds__(256) lat_noise_fill_kernel(const __grid_constant__ DecParams P) {
+  const int b = blockIdx.z;
+  const unsigned int GT = P.rng.grid_threads[b];
+  const unsigned long long numel = (unsigned long long)P.n_mc * (unsigned long long)P.Bg * (unsigned long long)P.blk_size[b];
+  const unsigned int idx = blockIdx.x * 256u + threadIdx.x;
+  const unsigned long long j = blockIdx.y;
+  const unsigned long long li0 = (4ull * j) * GT + idx;
+  if (idx >= GT || li0 >= numel) return;
+  const unsigned long long off = P.rng.ss ? P.rng.ss->philox_off[b] : P.rng.offset[b];
+  const unsigned long long nn = (off >> 2) + j;
+  const uint4 ctr = make_uint4((unsigned int)nn, (unsigned int)(nn >> 32), idx, 0u);
+  const uint2 key = make_uint2((unsigned int)P.rng.seed, (unsigned int)(P.rng.seed >> 32));
+  const uint4 r = curand_Philox4x32_10(ctr, key);
+  const float2 g0 = _curand_box_muller(r.x, r.y), g1 = _curand_box_muller(r.z, r.w);
+  float* out = P.eps_local[b];
+  out[li0] = g0.x;
+  if (li0 + GT < numel) out[li0 + GT] = g0.y;
+  if (li0 + 2ull * GT < numel) out[li0 + 2ull * GT] = g1.x;
+  if (li0 + 3ull * GT < numel) out[li0 + 3ull * GT] = g1.y;
+}
+
+template <class D>
+static size_t pair_smem_bytes(const DecParams& p, bool bwd) {
+  if (bwd) return (size_t)(2 * D::cn_rowpar * RBMAX + D::cn_rowpar * PNT + p.O_tot) * sizeof(float);
+  return (size_t)(D::cn_rowpar * RBMAX + (D::cndc + D::cndy) * RBMAX + 5 * RBMAX) * sizeof(float);
+}
+
+}  // namespace
+
 size_t lat_smem_bytes(const DecParams& p, bool bwd) { return (size_t)lat_smem_floats(p, bwd) * sizeof(float); }
 // shapes of the reference's cases (cases/*/__init__.py presets): bridge / damped_oscillator / simple_beam, P and S,
 // at the training MC count n_mc = 16; everything else runs the generic instantiation
@@ -603,6 +987,13 @@ static bool shape_matches(const DecParams& p, Shape<MT, NX, NC, NY, NDC, NDY, ND
 }
 template <class SH>
 static void launch_lat_pair(const DecParams& p, long long n_tiles, bool bwd, cudaStream_t s) {
+  if constexpr (SH::K) {
+    if (p.eps_local[0] != nullptr) {   // thread-per-pair kernels (api.cu hands out the local-order noise buffer when lat_pair_supported)
+      if (bwd) lat_pair_bwd_kernel<SH><<<(unsigned)n_tiles, PNT, pair_smem_bytes<SH>(p, true), s>>>(p);
+      else lat_pair_fwd_kernel<SH><<<(unsigned)n_tiles, PNT, pair_smem_bytes<SH>(p, false), s>>>(p);
+      return;
+    }
+  }
   if (bwd) {
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
@@ -650,12 +1041,29 @@ void launch_lat_encode(const DecParams& p, cudaStream_t s) {
   else if (latent_layout_matches(p, ShBeamS())) launch_lat_encode_t<ShBeamS>(p, s);
   else launch_lat_encode_t<ShGeneric>(p, s);
 }
+// the thread-per-pair kernels cover the compile-time shapes (the MC count and the tile geometry are part of the shape)
+bool lat_pair_supported(const DecParams& p) {
+  return shape_matches(p, ShBridgeP()) || shape_matches(p, ShBridgeS()) || shape_matches(p, ShOscP()) || shape_matches(p, ShOscS()) ||
+         shape_matches(p, ShBeamP()) || shape_matches(p, ShBeamS());
+}
+void launch_lat_noise_fill(const DecParams& p, cudaStream_t s) {
+  unsigned long long gt = 0, iters = 0;
+  for (int b = 0; b < p.n_blk; ++b) {
+    const unsigned long long GT = p.rng.grid_threads[b], numel = (unsigned long long)p.n_mc * (unsigned long long)p.Bg * (unsigned long long)p.blk_size[b];
+    const unsigned long long it = (numel + 4ull * GT - 1) / (4ull * GT);
+    gt = GT > gt ? GT : gt;
+    iters = it > iters ? it : iters;
+  }
+  lat_noise_fill_kernel<<<dim3((unsigned)((gt + 255) / 256), (unsigned)iters, (unsigned)p.n_blk), 256, 0, s>>>(p);
+}
 void launch_lat_fwd(const DecParams& p, long long n_tiles, cudaStream_t s) { launch_lat(p, n_tiles, false, s); }
 void launch_lat_bwd(const DecParams& p, long long n_tiles, cudaStream_t s) { launch_lat(p, n_tiles, true, s); }
 template <class SH>
 static int configure_lat_pair() {
   int e = (int)cudaFuncSetAttribute(lat_fwd_kernel<SH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   if (!e) e = (int)cudaFuncSetAttribute(lat_bwd_kernel<SH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  if constexpr (SH::K)
+    if (!e) e = (int)cudaFuncSetAttribute(lat_pair_bwd_kernel<SH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   return e;
 }
 int configure_lat_kernels() {
