@@ -92,7 +92,7 @@ __device__ __forceinline__ int block_of_l(const DecParams& P, int i) {
 
 // shared-memory carve-up (floats), identical for both kernels
 struct LatSmem {
-  float *ROWPAR, *ROWRAW, *ROWLOG, *EPS, *U, *ZXIN, *ZD, *DZ, *SC, *FEAT, *ROWACC, *ROWMSK, *EPS2, *DZ2, *BAR, *RAWH;
+  float *ROWPAR, *ROWRAW, *ROWLOG, *EPS, *U, *ZXIN, *ZD, *DZ, *SC, *FEAT, *ROWACC, *ROWMSK, *EPS2, *DZ2, *BAR, *RAWH, *ROWAUX;
 };
 __host__ __device__ inline int lat_smem_floats(const DecParams& P, bool bwd) {
   const int nzd = P.nz_c + P.nz_y, nzin = P.nz_x + P.nd_p;
@@ -632,6 +632,129 @@ __device__ __forceinline__ void stg_vec(float* dst, const float* v) {
   }
 }
 
+// Row parameters of one tile for the thread-per-pair kernels: same values as load_row_params, but every global load of a
+// thread is issued BEFORE the first dependent instruction (the four strided passes of load_row_params each waited a full
+// memory latency: 27 % of the forward kernel's stall samples), and the per-row derived quantities the pair threads would
+// otherwise recompute 16 times are staged next to them in ROWAUX (same indexing as ROWPAR):
+//   MODE 1 (forward):  log L_ii, log sigma_prior, 1 / sigma_prior (in the prior-mean slot), raw c / y rows
+//   MODE 2 (backward): 1 / L_ii, 1 / sigma_prior, and the clamp / exp chain-rule factors in ROWMSK
+template <class D, int MODE>
+__device__ __forceinline__ void pair_stage_rows(const DecParams& P, const LatSmem& S, long long row0, int nrows) {
+  constexpr int RB = TP / D::cn_mc, Z = D::cZ, nL = D::cnL, nzd = D::cnzd, NC = D::cNC, NY = D::cNY, ndc = D::cndc, ndy = D::cndy;
+  constexpr int rpL = Z, rpM = Z + nL, rpS = Z + nL + nzd;
+  constexpr int N1 = (RB * Z + PNT - 1) / PNT, N2 = (RB * nL + PNT - 1) / PNT, N3 = (RB * nzd + PNT - 1) / PNT;
+  constexpr int N4 = MODE == 1 ? (RB * (ndc + ndy) + PNT - 1) / PNT : 0;
+  const int tid = threadIdx.x;
+  const long long B = P.B;
+  float a1[N1], a2[N2], a3m[N3], a3s[N3], a4[N4 > 0 ? N4 : 1];
+  const bool has_y = P.y != nullptr;
+#pragma unroll
+  for (int t = 0; t < N1; ++t) {
+    const int e = tid + t * PNT, i = e / RB, r = e - i * RB;
+    a1[t] = 0.0f;
+    if (e < RB * Z) {
+      const int b = block_of_l<D>(P, i), il = i - D::blk_start(P, b);
+      a1[t] = __ldg(P.headpre + (long long)(D::henc(P, b) + il) * B + row0 + min(r, nrows - 1));
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < N2; ++t) {
+    const int e = tid + t * PNT, li = e / RB, r = e - li * RB;
+    a2[t] = 0.0f;
+    if (e < RB * nL) {
+      const int b = D::L_blk(P, li), i = D::L_i(P, li), j = D::L_j(P, li), nzb = D::blk_size(P, b);
+      const int f = D::henc(P, b) + (i == j ? nzb + i : 2 * nzb + i * nzb + j);
+      a2[t] = __ldg(P.headpre + (long long)f * B + row0 + min(r, nrows - 1));
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < N3; ++t) {
+    const int e = tid + t * PNT, k = e / RB, r = e - k * RB;
+    a3m[t] = 0.0f; a3s[t] = 0.0f;
+    if (e < RB * nzd) {
+      const int which = k < NC ? 0 : 1, kk = which ? k - NC : k, nzk = which ? NY : NC;
+      if (which == 0 || has_y) {
+        const float* h0 = P.headpre + (long long)(D::hpri(P, which) + kk) * B + row0 + min(r, nrows - 1);
+        a3m[t] = __ldg(h0);
+        a3s[t] = __ldg(h0 + (long long)nzk * B);
+      }
+    }
+  }
+  if constexpr (MODE == 1) {
+#pragma unroll
+    for (int t = 0; t < N4; ++t) {
+      const int e = tid + t * PNT, j = e / RB, r = e - j * RB;
+      a4[t] = 0.0f;
+      if (e < RB * (ndc + ndy)) {
+        const long long lrow = row0 + min(r, nrows - 1);
+        const long long drow = P.idx ? P.idx[lrow] : lrow;
+        if (j < ndc) a4[t] = __ldg(P.c + drow * ndc + j);
+        else if (has_y) a4[t] = __ldg(P.y + drow * ndy + (j - ndc));
+      }
+    }
+  }
+  // ---- dependent part ----
+#pragma unroll
+  for (int t = 0; t < N1; ++t) {
+    const int e = tid + t * PNT, i = e / RB, r = e - i * RB;
+    if (e < RB * Z) {
+      const float pm = a1[t];
+      S.ROWPAR[i * RBMAX + r] = clampf_(pm, -50.0f, 50.0f);
+      // d clamp / d pre: 1 inside the clamp range (models/encoders.py:35-43)
+      if constexpr (MODE == 2) S.ROWMSK[i * RBMAX + r] = (pm >= -50.0f && pm <= 50.0f) ? 1.0f : 0.0f;
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < N2; ++t) {
+    const int e = tid + t * PNT, li = e / RB, r = e - li * RB;
+    if (e < RB * nL) {
+      const bool diag = D::L_i(P, li) == D::L_j(P, li);
+      const float pre = a2[t];
+      float v, mk;
+      if (diag) {
+        v = expf(clampf_(pre, -7.0f, 3.0f)) + 1e-8f;
+        mk = (pre >= -7.0f && pre <= 3.0f) ? expf(pre) : 0.0f;   // d exp(clamp(ps)) / d ps = exp(ps) inside the range
+        S.ROWAUX[(rpL + li) * RBMAX + r] = MODE == 1 ? logf(v) : 1.0f / v;
+      } else {
+        v = clampf_(pre, -20.0f, 20.0f);
+        mk = (pre >= -20.0f && pre <= 20.0f) ? 1.0f : 0.0f;
+      }
+      S.ROWPAR[(rpL + li) * RBMAX + r] = v;
+      if constexpr (MODE == 2) S.ROWMSK[(rpL + li) * RBMAX + r] = mk;
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < N3; ++t) {
+    const int e = tid + t * PNT, k = e / RB, r = e - k * RB;
+    if (e < RB * nzd) {
+      const int which = k < NC ? 0 : 1;
+      float mu = 0.0f, sgm = 1.0f, mkm = 0.0f, mks = 0.0f;
+      if (which == 0 || has_y) {
+        const float pm = a3m[t], ps = a3s[t];
+        mu = clampf_(pm, -50.0f, 50.0f);
+        sgm = expf(clampf_(ps, -7.0f, 3.0f)) + 1e-8f;
+        mkm = (pm >= -50.0f && pm <= 50.0f) ? 1.0f : 0.0f;
+        mks = (ps >= -7.0f && ps <= 3.0f) ? expf(ps) : 0.0f;
+      }
+      S.ROWPAR[(rpM + k) * RBMAX + r] = mu;
+      S.ROWPAR[(rpS + k) * RBMAX + r] = sgm;
+      S.ROWAUX[(rpM + k) * RBMAX + r] = 1.0f / sgm;
+      if constexpr (MODE == 1) S.ROWAUX[(rpS + k) * RBMAX + r] = logf(sgm);
+      if constexpr (MODE == 2) {
+        S.ROWMSK[(rpM + k) * RBMAX + r] = mkm;
+        S.ROWMSK[(rpS + k) * RBMAX + r] = mks;
+      }
+    }
+  }
+  if constexpr (MODE == 1) {
+#pragma unroll
+    for (int t = 0; t < N4; ++t) {
+      const int e = tid + t * PNT, j = e / RB, r = e - j * RB;
+      if (e < RB * (ndc + ndy)) S.ROWRAW[j * RBMAX + r] = a4[t];
+    }
+  }
+}
+
 // compile-time block geometry of shape D
 template <class D, int b> struct Blk {
   static constexpr int nz = D::cnb == 1 ? D::cZ : (b == 0 ? D::cNX : (b == 1 ? D::cNC : D::cNY));
@@ -656,30 +779,33 @@ __device__ __forceinline__ void pair_eps_fwd(const DecParams& P, int m, long lon
   }
 }
 
-template <class D, int b>
-__device__ __forceinline__ void pair_sample_block(const DecParams& P, const float* ROWPAR, const float* ROWLOG, int prow, const float* eps,
-                                                  float* z, float* u, float& lq, float& ld1, float& ld2, float& lpx) {
+// z = loc + L eps of block b (+ bijector on the z_x dimensions).  LOGS: also log q, the bijector's log-determinant and the
+// per-pair part of log p(z_x) (the parts that are constant per dimension arrive through CONSTS, staged once per tile)
+template <class D, int b, bool LOGS>
+__device__ __forceinline__ void pair_sample_block(const DecParams& P, const float* ROWPAR, const float* ROWAUX, int prow, const float* eps,
+                                                  float* z, float* u, float& lq, float& ld1, float& lpx) {
   constexpr int nz = Blk<D, b>::nz, s = Blk<D, b>::s, loff = Blk<D, b>::loff;
-  float ss = 0.0f;
+  float ss = 0.0f, sl = 0.0f;
 #pragma unroll
   for (int i = 0; i < nz; ++i) {
     float acc = ROWPAR[(s + i) * RBMAX + prow];
 #pragma unroll
     for (int j = 0; j <= i; ++j) acc = fmaf(ROWPAR[(D::cZ + loff + i * (i + 1) / 2 + j) * RBMAX + prow], eps[s + j], acc);
-    ss = fmaf(eps[s + i], eps[s + i], ss);
     const int gi = s + i;
+    if constexpr (LOGS) {
+      ss = fmaf(eps[s + i], eps[s + i], ss);
+      sl += ROWAUX[(D::cZ + loff + i * (i + 1) / 2 + i) * RBMAX + prow];   // log L_ii (sum in index order: = log|det L| of the block)
+    }
     if (gi < D::cNX) {
       const float uu = sigmoidf_(acc);
-      const float a = P.ub[gi] - P.lb[gi];
-      const float zx = fmaf(uu, a, P.lb[gi]);
+      const float zx = fmaf(uu, P.ub[gi] - P.lb[gi], P.lb[gi]);
       u[gi < D::cNX ? gi : 0] = uu;
       z[gi] = zx;
-      if (ROWLOG != nullptr) {
+      if constexpr (LOGS) {
         ld1 += acc - 2.0f * softplusf_(acc);
-        ld2 += logf(fabsf(a));
         if (P.prior_kind[gi] == 0) {
           const bool inside = (zx >= P.prior_a[gi]) && (zx < P.prior_b[gi]);
-          lpx += (inside ? 0.0f : -INFINITY) - logf(P.prior_b[gi] - P.prior_a[gi]);
+          lpx += inside ? 0.0f : -INFINITY;
         } else {
           const float d = zx - P.prior_a[gi];
           lpx += -(d * d) / (2.0f * P.prior_b[gi] * P.prior_b[gi]) - logf(P.prior_b[gi]) - LOG_SQRT_2PI;
@@ -689,7 +815,7 @@ __device__ __forceinline__ void pair_sample_block(const DecParams& P, const floa
       z[gi] = acc;
     }
   }
-  if (ROWLOG != nullptr) lq += -0.5f * ((float)nz * LOG_2PI + ss) - ROWLOG[b * RBMAX + prow];
+  if constexpr (LOGS) lq += -0.5f * ((float)nz * LOG_2PI + ss) - sl;
 }
 
 template <class D>
@@ -697,12 +823,13 @@ __global__ void __launch_bounds__(PNT) lat_pair_fwd_kernel(const __grid_constant
   extern __shared__ __align__(16) float lsm[];
   pdl_launch_dependents();   // the decoder kernel may stage its weights while these tiles are processed
   constexpr int n = D::cn_mc, RB = TP / n, Z = D::cZ, NX = D::cNX, nzd = D::cnzd, nb = D::cnb, ndc = D::cndc, ndy = D::cndy;
-  constexpr int nzin = NX + D::cndp, c1 = nzd, cs0 = nzd + 1;
+  constexpr int nzin = NX + D::cndp, c1 = nzd, cs0 = nzd + 1, NF = D::cn_rowpar, rpM = Z + D::cnL, rpS = rpM + nzd;
   static_assert((n & (n - 1)) == 0 && n <= 32 && RB <= RBMAX, "MC count must be a power of two that fills whole warps");
   LatSmem S;
   S.ROWPAR = lsm;
-  S.ROWRAW = S.ROWPAR + D::cn_rowpar * RBMAX;
-  S.ROWLOG = S.ROWRAW + (ndc + ndy) * RBMAX;
+  S.ROWAUX = S.ROWPAR + NF * RBMAX;
+  S.ROWRAW = S.ROWAUX + NF * RBMAX;
+  float* CONSTS = S.ROWRAW + (ndc + ndy) * RBMAX;   // [0] sum log|ub - lb|, [1] constant part of log p(z_x), [2..] 1 / physics-input std
   const int p = threadIdx.x;
   const long long B = P.B, rb = blockIdx.x, row0 = rb * RB;
   const int nrows = (int)min((long long)RB, B - row0), npairs = nrows * n;
@@ -721,43 +848,43 @@ __global__ void __launch_bounds__(PNT) lat_pair_fwd_kernel(const __grid_constant
       pair_eps_fwd<D, 2>(P, pm, row0 + prow, store, eps);
     }
   }
-  load_row_params<D, PNT>(P, S, row0, nrows);
-  __syncthreads();
-  for (int e = p; e < RB * (nb + 2); e += PNT) {
-    const int t = e / RB, r = e - t * RB;
-    float s = 0.0f;
-    if (t < nb) {
-      for (int i = 0; i < D::blk_size(P, t); ++i) s += logf(S.ROWPAR[(D::rp_L(P) + D::blk_loff(P, t) + i * (i + 1) / 2 + i) * RBMAX + r]);
-    } else {
-      const int k0 = t == nb ? 0 : D::cNC, k1 = t == nb ? D::cNC : nzd;
-      for (int k = k0; k < k1; ++k) s += logf(S.ROWPAR[(D::rp_psig(P) + k) * RBMAX + r]);
+  pair_stage_rows<D, 1>(P, S, row0, nrows);
+  if (p == PNT - 1) {   // per-dimension constants of the bijector log-det and of the uniform priors (utils/transforms.py:97-150, utils/priors.py:19-23)
+    float c_ld2 = 0.0f, c_lpx = 0.0f;
+#pragma unroll
+    for (int gi = 0; gi < NX; ++gi) {
+      c_ld2 += logf(fabsf(P.ub[gi] - P.lb[gi]));
+      if (P.prior_kind[gi] == 0) c_lpx += -logf(P.prior_b[gi] - P.prior_a[gi]);
     }
-    S.ROWLOG[t * RBMAX + r] = s;
+    CONSTS[0] = c_ld2;
+    CONSTS[1] = c_lpx;
   }
+  if (p >= PNT - 1 - nzin && p < PNT - 1) CONSTS[2 + (PNT - 2 - p)] = 1.0f / P.phys_in_std[PNT - 2 - p];
   __syncthreads();
 
   float z[Z], u[NX > 0 ? NX : 1];
-  float lq = 0.0f, ld1 = 0.0f, ld2 = 0.0f, lpx = 0.0f;
-  pair_sample_block<D, 0>(P, S.ROWPAR, S.ROWLOG, prow, eps, z, u, lq, ld1, ld2, lpx);
+  float lq = 0.0f, ld1 = 0.0f, lpx = CONSTS[1];
+  pair_sample_block<D, 0, true>(P, S.ROWPAR, S.ROWAUX, prow, eps, z, u, lq, ld1, lpx);
   if constexpr (nb > 1) {
-    pair_sample_block<D, 1>(P, S.ROWPAR, S.ROWLOG, prow, eps, z, u, lq, ld1, ld2, lpx);
-    pair_sample_block<D, 2>(P, S.ROWPAR, S.ROWLOG, prow, eps, z, u, lq, ld1, ld2, lpx);
+    pair_sample_block<D, 1, true>(P, S.ROWPAR, S.ROWAUX, prow, eps, z, u, lq, ld1, lpx);
+    pair_sample_block<D, 2, true>(P, S.ROWPAR, S.ROWAUX, prow, eps, z, u, lq, ld1, lpx);
   }
-  const float dens = lq - (ld1 + ld2);
+  const float dens = lq - (ld1 + CONSTS[0]);
   // conditional priors p(zc|c), p(zy|y): diagonal Gaussians (models/vae.py:200-207)
   float kl = dens - lpx;
 #pragma unroll
   for (int side = 0; side < 2; ++side) {
     const int a_nz = side ? D::cNY : D::cNC, a_j0 = side ? D::cNC : 0;
-    float mh = 0.0f;
+    float mh = 0.0f, sl = 0.0f;
 #pragma unroll
     for (int k = 0; k < (D::cNC > D::cNY ? D::cNC : D::cNY); ++k)
       if (k < a_nz) {
         const int kk = a_j0 + k;
-        const float t = (z[NX + kk] - S.ROWPAR[(D::rp_pmu(P) + kk) * RBMAX + prow]) / S.ROWPAR[(D::rp_psig(P) + kk) * RBMAX + prow];
+        const float t = (z[NX + kk] - S.ROWPAR[(rpM + kk) * RBMAX + prow]) * S.ROWAUX[(rpM + kk) * RBMAX + prow];
         mh = fmaf(t, t, mh);
+        sl += S.ROWAUX[(rpS + kk) * RBMAX + prow];   // log sigma
       }
-    kl -= -0.5f * ((float)a_nz * LOG_2PI + mh) - S.ROWLOG[(nb + side) * RBMAX + prow];
+    kl -= -0.5f * ((float)a_nz * LOG_2PI + mh) - sl;
   }
   // per-row KL = mean over the MC axis (models/vae.py:207): the n samples of a row are n consecutive lanes
   {
@@ -788,7 +915,7 @@ __global__ void __launch_bounds__(PNT) lat_pair_fwd_kernel(const __grid_constant
       else if (k >= cs0 && k < cs0 + nzin) {
         const int q = k - cs0;
         const float zz = q < NX ? z[q < NX ? q : 0] : S.ROWRAW[P.idx_c_phys[q - NX < 0 ? 0 : q - NX] * RBMAX + prow];
-        x = mlp ? (zz - P.phys_in_mean[q]) / P.phys_in_std[q] : zz;
+        x = mlp ? (zz - P.phys_in_mean[q]) * CONSTS[2 + q] : zz;
         if (!pvalid && mlp) x = 0.0f;
       }
       v[i] = x * 16.0f;
@@ -825,8 +952,8 @@ __device__ __forceinline__ int pair_src_feature(const DecParams& P, int o) {
 }
 
 template <class D, int b>
-__device__ __forceinline__ void pair_grad_block(const DecParams& P, const float* ROWPAR, int prow, int p, float bw, const float* eps,
-                                                const float* z, const float* u, const float* dz, float* FEAT) {
+__device__ __forceinline__ void pair_grad_block(const DecParams& P, const float* ROWPAR, const float* ROWAUX, int prow, int p, float bw,
+                                                const float* eps, const float* z, const float* u, const float* dz, float* FEAT) {
   constexpr int nz = Blk<D, b>::nz, s = Blk<D, b>::s, loff = Blk<D, b>::loff, NX = D::cNX, nzd = D::cnzd, Z = D::cZ;
   constexpr int f_L = Z, f_pmu = Z + D::cnL, f_psig = f_pmu + nzd;
 #pragma unroll
@@ -840,18 +967,19 @@ __device__ __forceinline__ void pair_grad_block(const DecParams& P, const float*
       gl = g * (P.ub[gi] - P.lb[gi]) * uu * (1.0f - uu) + bw * (2.0f * uu - 1.0f);
     } else {
       const int k = gi - NX;
-      const float sgm = ROWPAR[(f_psig + k) * RBMAX + prow];
-      const float t = (z[gi] - ROWPAR[(f_pmu + k) * RBMAX + prow]) / sgm;
-      gl = dz[k] + bw * t / sgm;
-      FEAT[(f_pmu + k) * PNT + p] = -bw * t / sgm;
-      FEAT[(f_psig + k) * PNT + p] = -bw * (t * t - 1.0f) / sgm;
+      const float inv = ROWAUX[(f_pmu + k) * RBMAX + prow];   // 1 / sigma of the conditional prior
+      const float t = (z[gi] - ROWPAR[(f_pmu + k) * RBMAX + prow]) * inv;
+      const float bti = bw * t * inv;
+      gl = dz[k] + bti;
+      FEAT[(f_pmu + k) * PNT + p] = -bti;
+      FEAT[(f_psig + k) * PNT + p] = -bw * (t * t - 1.0f) * inv;
     }
     FEAT[gi * PNT + p] = gl;
 #pragma unroll
     for (int j = 0; j <= i; ++j) {
       const int li = loff + i * (i + 1) / 2 + j;
       float v = gl * eps[s + j];
-      if (j == i) v -= bw / ROWPAR[(f_L + li) * RBMAX + prow];
+      if (j == i) v -= bw * ROWAUX[(f_L + li) * RBMAX + prow];   // 1 / L_ii
       FEAT[(f_L + li) * PNT + p] = v;
     }
   }
@@ -861,13 +989,14 @@ template <class D>
 __global__ void __launch_bounds__(PNT) lat_pair_bwd_kernel(const __grid_constant__ DecParams P) {
   extern __shared__ __align__(16) float lsm[];
   pdl_launch_dependents();   // the encoder backward kernel may stage its weights while these tiles are processed
-  constexpr int n = D::cn_mc, RB = TP / n, Z = D::cZ, NX = D::cNX, nzd = D::cnzd, nb = D::cnb, NF = D::cn_rowpar;
-  static_assert(n % 4 == 0, "MC reduction reads float4 groups");
+  constexpr int n = D::cn_mc, RB = TP / n, Z = D::cZ, NX = D::cNX, nb = D::cnb, NF = D::cn_rowpar, NQ = n >> 2;
+  static_assert(n % 4 == 0 && (NQ & (NQ - 1)) == 0, "MC reduction reads float4 groups in a rotated order");
   LatSmem S;
   S.ROWPAR = lsm;
   S.ROWMSK = S.ROWPAR + NF * RBMAX;
+  S.ROWAUX = S.ROWMSK + NF * RBMAX;
   S.ROWRAW = nullptr;
-  S.FEAT = S.ROWMSK + NF * RBMAX;
+  S.FEAT = S.ROWAUX + NF * RBMAX;
   int* SRC = reinterpret_cast<int*>(S.FEAT + NF * PNT);
   const int p = threadIdx.x;
   const long long B = P.B, rb = blockIdx.x, row0 = rb * RB;
@@ -890,25 +1019,27 @@ __global__ void __launch_bounds__(PNT) lat_pair_bwd_kernel(const __grid_constant
 #pragma unroll
     for (int k = 0; k < Z; ++k) dz[k] = pvalid ? __ldg(DZ + k * TP + p) : 0.0f;
   }
+  pair_stage_rows<D, 2>(P, S, row0, nrows);
   for (int o = p; o < P.O_tot; o += PNT) SRC[o] = pair_src_feature<D>(P, o);
-  load_row_params<D, PNT>(P, S, row0, nrows, true);
   __syncthreads();
 
   {
     float z[Z], u[NX > 0 ? NX : 1];
-    float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;
-    pair_sample_block<D, 0>(P, S.ROWPAR, nullptr, prow, eps, z, u, d0, d1, d2, d3);
-    pair_grad_block<D, 0>(P, S.ROWPAR, prow, p, bw, eps, z, u, dz, S.FEAT);
+    float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f;
+    pair_sample_block<D, 0, false>(P, S.ROWPAR, S.ROWAUX, prow, eps, z, u, d0, d1, d2);
+    pair_grad_block<D, 0>(P, S.ROWPAR, S.ROWAUX, prow, p, bw, eps, z, u, dz, S.FEAT);
     if constexpr (nb > 1) {
-      pair_sample_block<D, 1>(P, S.ROWPAR, nullptr, prow, eps, z, u, d0, d1, d2, d3);
-      pair_grad_block<D, 1>(P, S.ROWPAR, prow, p, bw, eps, z, u, dz, S.FEAT);
-      pair_sample_block<D, 2>(P, S.ROWPAR, nullptr, prow, eps, z, u, d0, d1, d2, d3);
-      pair_grad_block<D, 2>(P, S.ROWPAR, prow, p, bw, eps, z, u, dz, S.FEAT);
+      pair_sample_block<D, 1, false>(P, S.ROWPAR, S.ROWAUX, prow, eps, z, u, d0, d1, d2);
+      pair_grad_block<D, 1>(P, S.ROWPAR, S.ROWAUX, prow, p, bw, eps, z, u, dz, S.FEAT);
+      pair_sample_block<D, 2, false>(P, S.ROWPAR, S.ROWAUX, prow, eps, z, u, d0, d1, d2);
+      pair_grad_block<D, 2>(P, S.ROWPAR, S.ROWAUX, prow, p, bw, eps, z, u, dz, S.FEAT);
     }
   }
   __syncthreads();
   // head-output gradients: MC-axis sum of the feature (n consecutive pairs, fixed order) times the clamp / exp chain-rule
-  // factor of the head (models/encoders.py:35-43); consecutive threads write consecutive rows of one feature row of gpre
+  // factor of the head (models/encoders.py:35-43); consecutive threads write consecutive rows of one feature row of gpre.
+  // The float4 groups of a row are read in an order rotated by the row index: the 8 rows of a quarter-warp then hit
+  // 8 different bank groups (64-byte row stride: 4-way conflicts otherwise); the order is a function of the row only.
   float gmax = 0.0f;
   const int henc_end = D::hpri(P, 0);
   for (int e = p; e < P.O_tot * RB; e += PNT) {
@@ -918,10 +1049,11 @@ __global__ void __launch_bounds__(PNT) lat_pair_bwd_kernel(const __grid_constant
       float g = 0.0f;
       if (f >= 0) {
         const float4* s4 = reinterpret_cast<const float4*>(S.FEAT + f * PNT + r * n);
+        const int rot = r >> 1;
         float s = 0.0f;
 #pragma unroll
-        for (int m = 0; m < (n >> 2); ++m) {
-          const float4 t = s4[m];
+        for (int m = 0; m < NQ; ++m) {
+          const float4 t = s4[(m + rot) & (NQ - 1)];
           s += (t.x + t.y) + (t.z + t.w);
         }
         g = S.ROWMSK[f * RBMAX + r] * s;
@@ -964,8 +1096,8 @@ __global__ void __launch_bounds__(256) lat_noise_fill_kernel(const __grid_consta
 
 template <class D>
 static size_t pair_smem_bytes(const DecParams& p, bool bwd) {
-  if (bwd) return (size_t)(2 * D::cn_rowpar * RBMAX + D::cn_rowpar * PNT + p.O_tot) * sizeof(float);
-  return (size_t)(D::cn_rowpar * RBMAX + (D::cndc + D::cndy) * RBMAX + 5 * RBMAX) * sizeof(float);
+  if (bwd) return (size_t)(3 * D::cn_rowpar * RBMAX + D::cn_rowpar * PNT + p.O_tot) * sizeof(float);
+  return (size_t)(2 * D::cn_rowpar * RBMAX + (D::cndc + D::cndy) * RBMAX + 16) * sizeof(float);
 }
 
 }  // namespace
