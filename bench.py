@@ -37,7 +37,7 @@ WORKLOADS = {
 }
 MATH_DOC = {
     "tc_fp16x3": "decoder GEMMs on tcgen05: fp32 operands split into fp16 hi+lo planes, 3 MMAs per GEMM, fp32 TMEM accumulators "
-                 "(parity 1e-5 vs the fp64 oracle, tests/test_gpu_tc.py); encoders / ELBO / Adam fp32 FFMA",
+                 "(parity 1e-5 vs the fp64 oracle, tests/test_gpu_tc.py); P-model encoders on tcgen05 the same way, latent math / ELBO / Adam fp32 on the CUDA cores",
     "fp32": "all GEMMs fp32 FFMA on the CUDA cores",
     "tc_fp16": "decoder GEMMs on tcgen05 with plain fp16 operands, fp32 accumulate (tolerance 2e-3 loss / 2e-2 gradients)",
 }
