@@ -372,7 +372,7 @@ static int build_plan(dpivae_model* h) {
     b = 0;
     plane2(Q.Hc / 8, Q.Oc, Q.wb_1, Q.lb_1);
     Q.ab_h = b; b += (int)Q.hid_stride;
-    plane2(Q.Oc / 8, 128, Q.ab_g, Q.lb_g);
+    plane2((Q.Oc > 64 ? 64 : Q.Oc) / 8, 128, Q.ab_g, Q.lb_g);   // Oc > 64: two column passes through one 64-column buffer
     plane2(Q.KX / 8, 128, Q.ab_x, Q.lb_x);
     Q.fb_orow = b; b += Q.Oc * 4;
     Q.fb_red = b; b += 256;
@@ -383,10 +383,11 @@ static int build_plan(dpivae_model* h) {
       for (int u = 0; u < nu; ++u) raw += (long long)E.u[u].O * E.u[u].H;
       Q.fb_raw = -1;
       if (Q.total_b + raw * 4 <= 232448) { Q.fb_raw = Q.total_b; Q.total_b = (int)((Q.total_b + raw * 4 + 127) & ~127LL); }
+      else if (raw * 4 <= Q.hid_stride) Q.fb_raw = Q.ab_h;   // the hidden-record buffer is idle until the first tile's bulk copy
     }
     const int nchunk = Q.Hc > 128 ? 2 : 1;
-    h->enc_tc_bwd_ok = h->enc_tc_ok && Q.total_b <= 232448 && Q.Oc <= 64 && Q.Hc + nchunk * (Q.Oc + Q.KX) <= 512 &&
-                       256 * 32 * 4 <= (int)Q.hid_stride;
+    h->enc_tc_bwd_ok = h->enc_tc_ok && Q.total_b <= 232448 && Q.Oc <= 128 && Q.Hc + nchunk * (Q.Oc + Q.KX) <= 512 &&
+                       256 * (Q.Oc > 64 ? 64 : 32) * 4 <= (int)Q.hid_stride;
   }
 
   // ---- shared-memory plan of the tensor-core decoder kernel (byte offsets) ----

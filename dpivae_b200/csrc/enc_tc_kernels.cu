@@ -223,6 +223,12 @@ __global__ void __launch_bounds__(NW * 32, 1) enc_tc_fwd_kernel(const __grid_con
 //   wgrad layer0: D_W0[chunk][k][j] += sum_r GH[r][k] X[r][j]             (constant-one column of X -> bias gradient)
 // Weight gradients stay in tensor memory across all tiles of the CTA.
 // ------------------------------------------------------------------------------------------------------------
+// NPASS = 2 (head width Oc in (64, 128], the single-encoder S presets): the head-gradient operand G is staged and consumed in two
+// column passes of <= 64 columns through ONE 32 KB operand buffer -- head wgrad per pass into its own tensor-memory
+// columns, head dgrad accumulated over the passes (the contraction over the head outputs is split) -- because
+// W1 (64 KB) + hidden record (64 KB) + a full-width G (64 KB) + X (40 KB) do not fit in 227 KB.  Per-column constants
+// of the standardisation live in shared memory in that instantiation (the registers hold the second pass's prefetch).
+template <int NPASS>
 __global__ void __launch_bounds__(ENT, 1) enc_tc_bwd_kernel(const __grid_constant__ EncTcParams P) {
   extern __shared__ __align__(1024) unsigned char smb[];
   float* smf = reinterpret_cast<float*>(smb);
@@ -334,11 +340,17 @@ __global__ void __launch_bounds__(ENT, 1) enc_tc_bwd_kernel(const __grid_constan
   oG.base = tc::smem_u32(pG); oG.lo_off = P.lb_g; oG.R = TP;
   oH.base = tc::smem_u32(pH); oH.lo_off = P.hid_lo; oH.R = TP;
   oW1.base = tc::smem_u32(smb + P.wb_1); oW1.lo_off = P.lb_1; oW1.R = Oc;
-  const int hcols = Hc >> 1, ocols = Oc >> 1;
+  const int hcols = Hc >> 1, fcols = Oc >> 1;
+  // G passes: pass s covers head columns [64 s, 64 s + OW_s); thread (row p, half hh) owns OW_s / 2 of them
+  const int ow0 = NPASS == 2 ? 64 : Oc, ow1 = NPASS == 2 ? Oc - 64 : 0;
+  const int ocols = ow0 >> 1, ocols1 = ow1 >> 1;
   const long long ntiles = (B + TP - 1) / TP;
   float db1[32];
+  float db2[NPASS == 2 ? 32 : 1];
 #pragma unroll
   for (int i = 0; i < 32; ++i) db1[i] = 0.0f;
+#pragma unroll
+  for (int i = 0; i < (NPASS == 2 ? 32 : 1); ++i) db2[i] = 0.0f;
   uint32_t wacc = 0;
   const uint32_t hid_bytes = (uint32_t)P.hid_stride;
   if (tid == 0 && (long long)blockIdx.x < ntiles) {
@@ -351,15 +363,35 @@ __global__ void __launch_bounds__(ENT, 1) enc_tc_bwd_kernel(const __grid_constan
   const int nch = K0 >> 4;
   float4 xa[XC], xb[XC];
   float gq[32];
-  float mr[XC][8], sr[XC][8];
+  float gq2[NPASS == 2 ? 32 : 1];
+  float mr[NPASS == 2 ? 1 : XC][8], sr[NPASS == 2 ? 1 : XC][8];
+  if constexpr (NPASS == 1) {
 #pragma unroll
-  for (int c = 0; c < XC; ++c)
+    for (int c = 0; c < XC; ++c)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int k = hh * (K0 >> 1) + 8 * c + i;
-      mr[c][i] = (c < nch) ? P.mean_x[k] : 0.0f;
-      sr[c][i] = (c < nch) ? P.std_x[k] : 1.0f;
+      for (int i = 0; i < 8; ++i) {
+        const int k = hh * (K0 >> 1) + 8 * c + i;
+        mr[c][i] = (c < nch) ? P.mean_x[k] : 0.0f;
+        sr[c][i] = (c < nch) ? P.std_x[k] : 1.0f;
+      }
+  }
+  // second-pass head gradients (NPASS = 2): consumed late in a tile, so the next tile's are fetched only after that
+  auto fetch_g2 = [&](long long tile) {
+    if constexpr (NPASS == 2) {
+      const long long lr = tile * TP + p;
+      const bool ok = tile < ntiles && lr < B;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          gq2[c * 8 + i] = 0.0f;
+          if (ok && c < (ocols1 >> 3)) {
+            const int r = OROW[64 + hh * ocols1 + 8 * c + i];
+            if (r >= 0) gq2[c * 8 + i] = P.gpre[(long long)r * B + lr];
+          }
+        }
     }
+  };
   auto fetch_in = [&](long long tile) {
     const long long lr = tile * TP + p;
     const bool ok = tile < ntiles && lr < B;
@@ -399,6 +431,7 @@ __global__ void __launch_bounds__(ENT, 1) enc_tc_bwd_kernel(const __grid_constan
   }
   const float sgp = exp2f((float)e_g);
   fetch_in(blockIdx.x);
+  fetch_g2(blockIdx.x);
 
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long row0 = tile * TP;
@@ -429,7 +462,9 @@ __global__ void __launch_bounds__(ENT, 1) enc_tc_bwd_kernel(const __grid_constan
           const int k0 = hh * (K0 >> 1) + 8 * c;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float t = P.x_is_standardised ? v[i] : (v[i] - mr[c][i]) / sr[c][i];
+            float t;
+            if constexpr (NPASS == 1) t = P.x_is_standardised ? v[i] : (v[i] - mr[c][i]) / sr[c][i];
+            else t = P.x_is_standardised ? v[i] : (v[i] - P.mean_x[k0 + i]) / P.std_x[k0 + i];
             // |standardised input| > 3750 sigma would overflow the fp16 operand (inf -> NaN gradients): saturate instead
             v[i] = valid ? fminf(fmaxf(t * s_x, -60000.0f), 60000.0f) : 0.0f;
           }
@@ -457,9 +492,9 @@ __global__ void __launch_bounds__(ENT, 1) enc_tc_bwd_kernel(const __grid_constan
       for (int ck = 0; ck < nchunk; ++ck) {
         tc::Op a = oH;
         a.base += (uint32_t)(((ck ? ch1 : 0) >> 3) * TP) * 16u;
-        tc::issue_wgrad_w(el, C_W1 + (uint32_t)(ck * Oc), a, oG, Oc, wacc, 3);
+        tc::issue_wgrad_w(el, C_W1 + (uint32_t)(ck * Oc), a, oG, ow0, wacc, 3);
       }
-      tc::issue_dgrad_w(el, C_GH, oG, oW1, Oc, Hc, 0, 3);
+      tc::issue_dgrad_w(el, C_GH, oG, oW1, ow0, Hc, 0, 3);
       tc::commit_w(el, bar);
     }
     __syncwarp();
@@ -467,6 +502,42 @@ __global__ void __launch_bounds__(ENT, 1) enc_tc_bwd_kernel(const __grid_constan
     phase ^= 1u;
     __syncwarp();
     tc::fence_after_sync();
+    if constexpr (NPASS == 2) {
+      // second column pass: the MMAs that read the first pass's G planes are complete (waited above)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (c < (ocols1 >> 3)) {
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            v[i] = valid ? fminf(fmaxf(gq2[c * 8 + i] * sgp, -60000.0f), 60000.0f) : 0.0f;
+            db2[c * 8 + i] += v[i];
+          }
+          put8e(pG, P.lb_g, TP, (hh * ocols1 + 8 * c) >> 3, p, v);
+        }
+      }
+      fetch_g2(tile + gridDim.x);   // next tile's second-pass gradients: in flight under the rest of this tile
+      tc::fence_async_smem();
+      tc::fence_before_sync();
+      __syncthreads();
+      if (warp == 0) {
+        tc::fence_after_sync();
+        for (int ck = 0; ck < nchunk; ++ck) {
+          tc::Op a = oH;
+          a.base += (uint32_t)(((ck ? ch1 : 0) >> 3) * TP) * 16u;
+          tc::issue_wgrad_w(el, C_W1 + (uint32_t)(ck * Oc) + 64u, a, oG, ow1, wacc, 3);
+        }
+        tc::Op w2 = oW1;
+        w2.base += 64u * 16u;   // head rows 64.. of every hidden chunk
+        tc::issue_dgrad_w(el, C_GH, oG, w2, ow1, Hc, 1, 3);
+        tc::commit_w(el, bar);
+      }
+      __syncwarp();
+      tc::mbar_wait(bar, phase);
+      phase ^= 1u;
+      __syncwarp();
+      tc::fence_after_sync();
+    }
     // ---- ReLU mask (from the hidden record) on the dgrad result, written over the record in place ----
     for (int c = 0; c < (hcols >> 3); ++c) {
       const int k0 = hh * hcols + 8 * c;
@@ -518,8 +589,8 @@ __global__ void __launch_bounds__(ENT, 1) enc_tc_bwd_kernel(const __grid_constan
     int lk;
     const int uk = unit_of_h(k, lk);
     // heads: columns o of unit uk
-    for (int c = 0; c < (ocols >> 3); ++c) {
-      const int o0 = hh * ocols + 8 * c;
+    for (int c = 0; c < (fcols >> 3); ++c) {
+      const int o0 = hh * fcols + 8 * c;
       float v[8];
       tc::tmem_ld8(trow + C_W1 + (uint32_t)(ck * Oc) + o0, v);
       if (mine) {
@@ -547,16 +618,22 @@ __global__ void __launch_bounds__(ENT, 1) enc_tc_bwd_kernel(const __grid_constan
   // head-bias gradients: per-thread running sums -> fixed-order sum over the 128 row slots
   __syncthreads();
   float* R0 = reinterpret_cast<float*>(pH);
+  constexpr int RS = NPASS == 2 ? 64 : 32;   // scratch floats per thread: [pass][32]
 #pragma unroll
-  for (int i = 0; i < 32; ++i) R0[tid * 32 + i] = db1[i];
+  for (int i = 0; i < 32; ++i) R0[tid * RS + i] = db1[i];
+  if constexpr (NPASS == 2) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) R0[tid * RS + 32 + i] = db2[i];
+  }
   __syncthreads();
   if (tid < Oc) {
-    const int h2 = tid / ocols, i = tid - h2 * ocols;
+    const int ps = (NPASS == 2 && tid >= 64) ? 1 : 0, oc = tid - 64 * ps, oh = ps ? ocols1 : ocols;   // pass, column within it, columns per half
+    const int h2 = oc / oh, i = oc - h2 * oh;
     int l;
     const int u = unit_of_o(tid, l);
     if (u >= 0 && i < 32) {
       float s = 0.0f;
-      for (int j = 0; j < TP; ++j) s += R0[(h2 * TP + j) * 32 + i];
+      for (int j = 0; j < TP; ++j) s += R0[(h2 * TP + j) * RS + 32 * ps + i];
       part[P.g_b1[u] + l] = s * exp2f(-(float)e_g);
     }
   }
@@ -565,7 +642,10 @@ __global__ void __launch_bounds__(ENT, 1) enc_tc_bwd_kernel(const __grid_constan
   if (warp == 0) tc::tmem_dealloc(tb, 512);
 }
 
-void launch_enc_tc_bwd(const EncTcParams& p, int grid, cudaStream_t s) { launch_pdl(enc_tc_bwd_kernel, grid, ENT, (size_t)p.total_b, s, p); }
+void launch_enc_tc_bwd(const EncTcParams& p, int grid, cudaStream_t s) {
+  if (p.Oc > 64) launch_pdl(enc_tc_bwd_kernel<2>, grid, ENT, (size_t)p.total_b, s, p);
+  else launch_pdl(enc_tc_bwd_kernel<1>, grid, ENT, (size_t)p.total_b, s, p);
+}
 
 void launch_enc_tc_fwd(const EncTcParams& p, int grid, cudaStream_t s) {
   if (p.K0 == 64 && (p.Oc & 31) == 0 && (p.Hc & 31) == 0) enc_tc_fwd_kernel<16><<<grid, 512, p.total, s>>>(p);
@@ -574,7 +654,8 @@ void launch_enc_tc_fwd(const EncTcParams& p, int grid, cudaStream_t s) {
 int configure_enc_tc_kernels() {
   int e = (int)cudaFuncSetAttribute(enc_tc_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
   if (!e) e = (int)cudaFuncSetAttribute(enc_tc_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
-  if (!e) e = (int)cudaFuncSetAttribute(enc_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  if (!e) e = (int)cudaFuncSetAttribute(enc_tc_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  if (!e) e = (int)cudaFuncSetAttribute(enc_tc_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
   return e;
 }
 
