@@ -11,6 +11,7 @@
 // that still gives all 256 threads a tile, so the skinny layers (K or N of 2..8) do not leave
 // most of the CTA idle at the next barrier.
 #pragma once
+#include <cstdint>
 #include <cuda_runtime.h>
 #include <curand_kernel.h>
 #include <stdint.h>
@@ -61,11 +62,26 @@ __device__ __forceinline__ float philox_normal_elem(unsigned long long seed, uns
 }
 
 // Block-wide copy of n floats global -> shared with EIGHT independent loads in flight per thread (a rolled copy loop waits
-// a full memory latency, ~0.6 us, per trip: the kernels' set-up copies of 10-16 k weights took 15-20 us that way).
+// a full memory latency, ~0.6 us, per trip: the kernels' set-up copies of 10-16 k weights took 15-20 us that way); 16-byte
+// loads when both ends are 16-byte aligned (a quarter of the round trips), scalar loads for the rest.
 template <int NT>
 __device__ __forceinline__ void copy_g2s_batched(float* __restrict__ dst, const float* __restrict__ src, int n) {
   const int tid = threadIdx.x;
-  for (int e0 = 0; e0 < n; e0 += 8 * NT) {
+  int done = 0;
+  if (((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15u) == 0) {
+    const int n4 = n >> 2;
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (int e0 = 0; e0 < n4; e0 += 8 * NT) {
+      float4 t[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { const int e = e0 + k * NT + tid; t[k] = e < n4 ? __ldg(s4 + e) : make_float4(0.f, 0.f, 0.f, 0.f); }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { const int e = e0 + k * NT + tid; if (e < n4) d4[e] = t[k]; }
+    }
+    done = n4 << 2;
+  }
+  for (int e0 = done; e0 < n; e0 += 8 * NT) {
     float t[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) { const int e = e0 + k * NT + tid; t[k] = e < n ? __ldg(src + e) : 0.0f; }

@@ -187,6 +187,23 @@ __device__ void stage_weight(unsigned char* plane, uint32_t lo_off, int N, int K
   }
 }
 
+// Dense row-major [N][K] weights (already in shared memory, 16-byte aligned rows) -> X8 hi/lo plane pair.  Consecutive threads
+// take consecutive rows n (conflict-free 16-byte operand stores) and walk the K chunks in an order ROTATED by the row index,
+// so that the two 16-byte loads of a quarter-warp spread over the banks (2-way instead of the 32-way conflict of eight
+// scalar loads at a row stride that is a multiple of 32 words: ~10 us of the kernel's set-up).
+__device__ void stage_weight_dense(unsigned char* plane, uint32_t lo_off, int N, int K, int kexp, const float* W) {
+  const float s = exp2f((float)kexp);
+  const int nch = K >> 3;
+  for (int e = threadIdx.x; e < nch * N; e += NALL) {
+    const int c0 = e / N, n = e - c0 * N;
+    const int ch = (c0 + n) % nch;
+    const float4 a = *reinterpret_cast<const float4*>(W + (size_t)n * K + 8 * ch);
+    const float4 b = *reinterpret_cast<const float4*>(W + (size_t)n * K + 8 * ch + 4);
+    const float v[8] = {a.x * s, a.y * s, a.z * s, a.w * s, b.x * s, b.y * s, b.z * s, b.w * s};
+    put8(plane, lo_off, N, ch, n, v);
+  }
+}
+
 }  // namespace
 
 // One-time set-up of a CTA (all 512 threads): zero shared memory, barriers, tensor-memory allocation, operand staging of
@@ -306,13 +323,19 @@ static __device__ __noinline__ void dec_tc_setup(const TcParams& T, unsigned cha
       k_x = min(k_x, scale_exp(m[5]));  // fx1 and the last physics layer accumulate into the same TMEM columns
     }
   }
+  // dense matrices: vector loads when their rows are 16-byte aligned in the scratch (they are for every shipped case)
+  auto dense_ok = [&](const float* W, int K) { return ((reinterpret_cast<uintptr_t>(W) & 15u) == 0) && (K & 7) == 0; };
   stage_weight(smb + T.w_fx0, T.l_fx0, 128, KZ, k_fx0, g_fx0);
-  stage_weight(smb + T.w_fx1, T.l_fx1, ndx, 128, k_x, g_fx1);
+  if (dense_ok(FX + o_w1, 128)) stage_weight_dense(smb + T.w_fx1, T.l_fx1, ndx, 128, k_x, FX + o_w1);
+  else stage_weight(smb + T.w_fx1, T.l_fx1, ndx, 128, k_x, g_fx1);
   if constexpr (mlp) {
     stage_weight(smb + T.w_p[0], T.l_p[0], d1, KZ, k_p0, g_p0);
-    stage_weight(smb + T.w_p[1], T.l_p[1], d2, d1, k_p1, g_p1);
-    stage_weight(smb + T.w_p[2], T.l_p[2], d3, d2, k_p2, g_p2);
-    stage_weight(smb + T.w_p[3], T.l_p[3], ndx, d3, k_x, g_p3);
+    if (dense_ok(FR + P.pl[1].g_w, d1)) stage_weight_dense(smb + T.w_p[1], T.l_p[1], d2, d1, k_p1, FR + P.pl[1].g_w);
+    else stage_weight(smb + T.w_p[1], T.l_p[1], d2, d1, k_p1, g_p1);
+    if (dense_ok(FR + P.pl[2].g_w, d2)) stage_weight_dense(smb + T.w_p[2], T.l_p[2], d3, d2, k_p2, FR + P.pl[2].g_w);
+    else stage_weight(smb + T.w_p[2], T.l_p[2], d3, d2, k_p2, g_p2);
+    if (dense_ok(FR + P.pl[3].g_w, d3)) stage_weight_dense(smb + T.w_p[3], T.l_p[3], ndx, d3, k_x, FR + P.pl[3].g_w);
+    else stage_weight(smb + T.w_p[3], T.l_p[3], ndx, d3, k_x, g_p3);
   }
   for (int e = tid; e < ndx; e += NALL) BX[e] = FX[o_b1 + e] + bias_p3(e);
   if constexpr (mlp) {

@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(NW * 32, 1) enc_tc_fwd_kernel(const __grid_con
   uint64_t* bar = reinterpret_cast<uint64_t*>(smb + P.o_bar);
   uint32_t* tptr = reinterpret_cast<uint32_t*>(smb + P.o_bar + 8);
 
-  for (int e = tid; e < (P.total >> 2); e += ENTF) smf[e] = 0.0f;
+  for (int e = tid; e < (P.total >> 4); e += ENTF) reinterpret_cast<uint4*>(smb)[e] = make_uint4(0u, 0u, 0u, 0u);   // total is a multiple of 128
   __syncthreads();
   if (tid == 0) {
     tc::mbar_init(bar, 1);
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(ENT, 1) enc_tc_bwd_kernel(const __grid_constan
   uint32_t* tptr = reinterpret_cast<uint32_t*>(smb + P.ob_bar + 16);
   float* part = P.part + (long long)blockIdx.x * P.part_stride;
 
-  for (int e = tid; e < (P.total_b >> 2); e += ENT) smf[e] = 0.0f;
+  for (int e = tid; e < (P.total_b >> 4); e += ENT) reinterpret_cast<uint4*>(smb)[e] = make_uint4(0u, 0u, 0u, 0u);   // total_b is a multiple of 128
   __syncthreads();
   if (tid == 0) {
     tc::mbar_init(bar, 1);

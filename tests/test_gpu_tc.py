@@ -93,6 +93,36 @@ def test_tc_matches_fp32_kernel_with_philox_noise():
     assert torch.equal(rl, rl2)
 
 
+@pytest.mark.parametrize("case,mtype", [("bridge", "P"), ("bridge", "S"), ("simple_beam", "S"), ("damped_oscillator", "P")])
+def test_tc_shard_invariance_with_inkernel_philox(case, mtype):
+    """Thread-per-pair latent kernels (n_mc = 16), in-kernel Philox: an unsharded call draws its noise with the
+    pre-pass (one Philox evaluation per four elements, torch's mapping), row shards draw it per element inside the
+    forward; both must be the SAME stream -- per-row losses of the shards bitwise equal to the unsharded call's,
+    gradients and scalars summing to it."""
+    g, spec, sd, args, case_mod, vae, (x, c, y) = build_from_golden(case, mtype)
+    eng = vae.engine()
+    eng.set_math_mode("tc_fp16x3")
+    reps = 9   # 216 rows x 16 MC = 27 tiles; the shards end in ragged tiles
+    X, C_, Y = _tile(x, reps).cuda(), _tile(c, reps).cuda(), _tile(y, reps).cuda()
+    B = X.shape[0]
+    w = (1.0, 1.0, 1.0, 1.0)
+    torch.manual_seed(11)
+    rl, s = eng.loss(X, C_, Y, 16, w, True)
+    assert eng.used_tensor_cores()
+    g_full = eng.grads.clone()
+    cuts = [0, 67, 150, B]
+    rls, gsum, ssum = [], torch.zeros_like(g_full), torch.zeros_like(s)
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        torch.manual_seed(11)
+        rl_k, s_k = eng.loss(X[a:b], C_[a:b], Y[a:b], 16, w, True, B_global=B, row_offset=a)
+        rls.append(rl_k)
+        gsum += eng.grads
+        ssum += s_k
+    assert torch.equal(torch.cat(rls, dim=1), rl)
+    assert gu.rel_l2(gsum.cpu(), g_full.cpu()) < 2e-6
+    assert gu.rel_l2(ssum.cpu(), s.cpu()) < 2e-6
+
+
 # The K-step Adam trajectory of the tensor-core mode against the REFERENCE's own `train_model` run lives in
 # tests/test_gpu_ext.py::test_train_model_flagged_run_matches_reference[tc_fp16x3-*] (fixtures with n_mc = 8: the
 # first fixture set has n_mc = 4, below the tensor-core kernel's 8 <= n_mc <= 128 window).
