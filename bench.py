@@ -273,6 +273,7 @@ def workload_config(a, wl, n_gpus):
     rows = wl["rows"]
     return {"workload": a.workload, "math": MATH_DOC[a.math], "case": wl["case"], "preset": wl["preset"], "rows_per_gpu": rows,
             "global_batch": rows * n_gpus if a.scaling == "weak" else rows, "n_mc": wl["n_mc"], "parallelism": f"dp{n_gpus}",
+            "row_sharding": "cyclic (rank k of N owns global rows k, k + N, ...)" if n_gpus > 1 else "none",
             "minibatch_order": "identity (loss is a row sum; the reference's CPU multinomial draw is hoisted)",
             "data_generator": "on-device dpivae_sample_response (torch-stream Philox + surrogate MLP kernels)",
             "l2": "per-step working set (inputs + activations workspace) ~0.3 GB > 126 MB L2, no flush",
@@ -510,7 +511,7 @@ def rank_check(a, wl, case_mod, vae_factory, world, rank, dev, n, w):
         p0 = dp.eng.params.clone()
         torch.manual_seed(4242)
         off0 = gen.get_offset()
-        dp.step(mine[0], mine[1], mine[2], n, w, Bg, rank * rows, 1)
+        dp.step(mine[0], mine[1], mine[2], n, w, Bg, rank, 1, row_stride=world)   # cyclic shards, as in the timed run
         grads_n = dp.eng.gradbuf.clone()
         params_n = dp.eng.params.clone()
         # every rank must hold bitwise identical parameters (same allreduced gradient, same fused Adam)
@@ -529,7 +530,7 @@ def rank_check(a, wl, case_mod, vae_factory, world, rank, dev, n, w):
             eng1.set_math_mode(mode)
             torch.manual_seed(4242)   # (the model factory re-seeded the generator for its scaler sample)
             gen.set_offset(off0)
-            X, C_, Y = (torch.cat([sh[i] for sh in shards]) for i in range(3))
+            X, C_, Y = (torch.stack([sh[i] for sh in shards], dim=1).flatten(0, 1) for i in range(3))   # global row k + N t = rank k, local row t
             eng1.loss(X, C_, Y, n, w, True, B_global=Bg, row_offset=0, adam_step=1)
             g1, p1 = eng1.gradbuf, eng1.params
             gerr = float((grads_n.double() - g1.double()).norm() / g1.double().norm())
@@ -570,7 +571,9 @@ def run_train(a, wl, ctx, sub=False):
         rows = wl["rows"]
         B_global = rows * n_gpus
     wl = dict(wl, rows=rows)
-    row_off = rank * rows
+    # cyclic row shards: rank k of N owns the global rows k, k + N, ... (each rank then owns whole Philox evaluations of the
+    # noise stream); the global batch is the interleaved union of the shards
+    row_off, row_stride = (rank, world) if world > 1 else (0, 1)
     import contextlib, io
 
     def vae_factory():
@@ -595,7 +598,7 @@ def run_train(a, wl, ctx, sub=False):
             torch.cuda.synchronize()
 
     def step_resident(i):
-        dp.step(x, c, y, n, w, B_global, row_off, i)
+        dp.step(x, c, y, n, w, B_global, row_off, i, row_stride=row_stride)
 
     # End-to-end arm: every step's inputs come from pinned host memory and its 8 loss scalars go back to the host, where
     # the caller waits for them.  Two device input sets: while step i computes, a copy stream uploads the inputs of step
@@ -626,7 +629,7 @@ def run_train(a, wl, ctx, sub=False):
         main = torch.cuda.current_stream()
         main.wait_event(ready[k & 1])
         xd, cd, yd, idxd = dev_in[k & 1]
-        s = dp.step(xd, cd, yd, n, w, B_global, row_off, i, idx=idxd)
+        s = dp.step(xd, cd, yd, n, w, B_global, row_off, i, idx=idxd, row_stride=row_stride)
         upload((k + 1) & 1, k + 1)        # step k - 1, the last reader of that slot, was synchronised below
         scal_host.copy_(s, non_blocking=True)
         main.synchronize()         # the user reads the loss every step

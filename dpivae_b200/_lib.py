@@ -44,7 +44,7 @@ class ModelDesc(C.Structure):
 class Batch(C.Structure):
     _fields_ = [("x", C.c_void_p), ("c", C.c_void_p), ("y", C.c_void_p), ("idx", C.c_void_p),
                 ("B", C.c_int64), ("B_global", C.c_int64), ("row_offset", C.c_int64),
-                ("n_mc", C.c_int32), ("cond", C.c_int32)]
+                ("n_mc", C.c_int32), ("cond", C.c_int32), ("row_stride", C.c_int64)]
 
 
 class Rng(C.Structure):
@@ -83,7 +83,7 @@ EXPORTS = [
     "dpivae_step_graph_create", "dpivae_step_graph_reset", "dpivae_step_graph_launch", "dpivae_step_graph_destroy",
 ]
 MATH_FP32, MATH_TC_FP16X3, MATH_TC_FP16 = 0, 1, 2
-ABI_VERSION = 2   # include/dpivae_b200.h DPIVAE_ABI_VERSION
+ABI_VERSION = 3   # include/dpivae_b200.h DPIVAE_ABI_VERSION
 
 _lib = None
 

@@ -596,6 +596,8 @@ static int run_loss(dpivae_handle_t h, const dpivae_batch_t* bt, const dpivae_rn
   if (!h || !bt || !rng) return fail("null argument");
   if (!h->params) return fail("dpivae_bind has not been called");
   if (bt->B < 1 || bt->n_mc < 1 || bt->B_global < bt->B) return fail("bad batch sizes");
+  const long long row_stride = bt->row_stride > 1 ? bt->row_stride : 1;
+  if (bt->row_offset < 0 || bt->row_offset + (bt->B - 1) * row_stride >= bt->B_global) return fail("row_offset / row_stride leave the global batch");
   if (!bt->x || (!latent_only && !bt->c)) return fail("x / c must be given");
   if (with_grad && (!bt->y || !h->grads)) return fail("training needs y and a bound gradient buffer");
   if (h->d.phys_kind == DPIVAE_PHYS_MLP && !h->d_frozen && !latent_only) return fail("dpivae_set_physics_mlp has not been called");
@@ -656,7 +658,7 @@ static int run_loss(dpivae_handle_t h, const dpivae_batch_t* bt, const dpivae_rn
     F.q.x_is_standardised = x_std; F.q.terms = h->math_mode == DPIVAE_MATH_TC_FP16X3 ? 3 : 1;
     F.rng.ss = h->cur_ss; F.rng.mode = rng->mode; F.rng.seed = rng->seed;
     for (int k = 0; k < 4; ++k) { F.rng.eps[k] = rng->eps[k]; F.rng.offset[k] = rng->offset[k]; F.rng.grid_threads[k] = rng->grid_threads[k] ? rng->grid_threads[k] : 256; }
-    F.Bg = bt->B_global; F.row_off = bt->row_offset; F.n_mc = bt->n_mc;
+    F.Bg = bt->B_global; F.row_off = bt->row_offset; F.row_stride = row_stride; F.n_mc = bt->n_mc;
     F.phase = h->d_phase;
     F.dbg = (h->d_phase && getenv("DPIVAE_ENC_DBG")) ? atoi(getenv("DPIVAE_ENC_DBG")) : 0;
     F.trace = (h->d_phase && getenv("DPIVAE_ENCODE_TRACE")) ? h->d_phase + 32 : nullptr;   // the probe's buffer holds 32 + 6 * 402 counters
@@ -664,7 +666,7 @@ static int run_loss(dpivae_handle_t h, const dpivae_batch_t* bt, const dpivae_rn
     // in-kernel Philox noise: generated ahead by noise_fill_kernel (one evaluation per four elements, torch's own
     // mapping) into the hidden-activation region of the workspace, which this path does not use
     const long long Zt = h->d.nz_x + h->d.nz_c + h->d.nz_y;
-    if (rng->mode == 1 && (long long)bt->n_mc * Zt <= (long long)h->H_tot && !getenv("DPIVAE_NO_NOISE_PREPASS")) {
+    if (rng->mode == 1 && row_stride == 1 && (long long)bt->n_mc * Zt <= (long long)h->H_tot && !getenv("DPIVAE_NO_NOISE_PREPASS")) {
       float* e0 = hid;
       for (int b = 0; b < 3; ++b) { F.eps_local[b] = e0; e0 += ((size_t)bt->n_mc * bt->B * F.nz[b] + 3) & ~(size_t)3; }   // 16-byte aligned blocks (the few floats of rounding spill into headpre, equally unused here)
     }
@@ -702,7 +704,7 @@ static int run_loss(dpivae_handle_t h, const dpivae_batch_t* bt, const dpivae_rn
   DecParams D = h->dec;
   D.params = h->params; D.frozen = h->d_frozen;
   D.x = bt->x; D.c = bt->c; D.y = bt->y; D.idx = (const long long*)bt->idx;
-  D.B = bt->B; D.Bg = bt->B_global; D.row_off = bt->row_offset;
+  D.B = bt->B; D.Bg = bt->B_global; D.row_off = bt->row_offset; D.row_stride = row_stride;
   D.n_mc = bt->n_mc; D.cond = bt->cond; D.with_grad = with_grad;
   D.RB = L.RB; D.n_chunks = L.n_chunks; D.n_rowblocks = L.n_rowblocks;
   D.latent_only = latent_only;
@@ -739,8 +741,22 @@ static int run_loss(dpivae_handle_t h, const dpivae_batch_t* bt, const dpivae_rn
       if (!lat_v1 && lat_pair_supported(D)) {
         float* e0 = (float*)(base + L.epsbuf);
         for (int b = 0; b < D.n_blk; ++b) { D.eps_local[b] = e0; e0 += ((size_t)bt->n_mc * bt->B * D.blk_size[b] + 3) & ~(size_t)3; }
-        if (rng->mode == 1 && bt->B_global == bt->B && bt->row_offset == 0 && !no_prepass) {
-          launch_lat_noise_fill(D, st);
+        // noise ahead of the latent kernel, one Philox evaluation per four elements: unsharded calls, and CYCLIC row shards
+        // (rank k of S: rows k, k + S, ...) whenever S * nz divides torch's generator grid -- the four elements of an
+        // evaluation are grid_threads apart in the flattened (m, row, i) tensor, i.e. grid_threads / nz rows apart, so they
+        // then fall on the same rank.  Contiguous shards keep the per-element generator inside the forward.
+        int prepass = 0;
+        if (rng->mode == 1 && !no_prepass) {
+          if (bt->B_global == bt->B && bt->row_offset == 0) prepass = 1;
+          else if (row_stride > 1 && bt->B * row_stride == bt->B_global && bt->row_offset < row_stride &&
+                   (unsigned long long)bt->n_mc * (unsigned long long)bt->B_global < (1ull << 31)) {
+            prepass = 2;
+            for (int b = 0; b < D.n_blk; ++b)
+              if (D.rng.grid_threads[b] % (unsigned long long)(D.blk_size[b] * row_stride) != 0) prepass = 0;
+          }
+        }
+        if (prepass) {
+          launch_lat_noise_fill(D, prepass == 2, st);
           D.eps_ready = 1;
           ++launches;
         }
@@ -971,7 +987,7 @@ int dpivae_decode(dpivae_handle_t h, const float* zx_in, const float* zc, const 
   DecParams D = h->dec;
   D.params = h->params; D.frozen = h->d_frozen;
   D.x = zeros; D.c = zeros; D.y = zeros; D.idx = nullptr;
-  D.B = B; D.Bg = B; D.row_off = 0;
+  D.B = B; D.Bg = B; D.row_off = 0; D.row_stride = 1;
   D.n_mc = n_mc; D.cond = 0; D.with_grad = 0;
   D.RB = L.RB; D.n_chunks = L.n_chunks; D.n_rowblocks = L.n_rowblocks;
   D.latent_only = 0;

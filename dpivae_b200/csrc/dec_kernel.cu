@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(NT, 1) dec_kernel(const __grid_constant__ DecP
         float v = 0.0f;
         if (q < npairs) {
           const long long r = q / n, m = q - r * n;
-          const unsigned long long grow = (unsigned long long)(P.row_off + row0 + r);
+          const unsigned long long grow = (unsigned long long)(P.row_off + (row0 + r) * P.row_stride);
           const int b = block_of(P, i), il = i - P.blk_start[b], nzb = P.blk_size[b];
           const unsigned long long li = ((unsigned long long)m * (unsigned long long)P.Bg + grow) * nzb + il;
           v = P.rng.mode == 0 ? P.rng.eps[b][li] : philox_normal_elem(P.rng.seed, P.rng.ss ? P.rng.ss->philox_off[b] : P.rng.offset[b], P.rng.grid_threads[b], li);
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(NT, 1) dec_kernel(const __grid_constant__ DecP
           float v = 0.0f;
           if (q < npairs) {
             const long long r = q / n, m = q - r * n;
-            const unsigned long long grow = (unsigned long long)(P.row_off + row0 + r);
+            const unsigned long long grow = (unsigned long long)(P.row_off + (row0 + r) * P.row_stride);
             const unsigned long long li = ((unsigned long long)m * (unsigned long long)P.Bg + grow) * P.nz_c + i;
             v = P.rng.mode == 0 ? P.rng.eps[3][li] : philox_normal_elem(P.rng.seed, P.rng.ss ? P.rng.ss->philox_off[3] : P.rng.offset[3], P.rng.grid_threads[3], li);
           }

@@ -87,6 +87,7 @@ struct DecParams {
   const float *x, *c, *y;
   const long long* idx;
   long long B, Bg, row_off;
+  long long row_stride;         // global row of local row r = row_off + r * row_stride (>= 1)
   int n_mc, cond, with_grad, RB, n_chunks, latent_only;
   long long n_rowblocks;
   RngP rng;
@@ -111,6 +112,8 @@ struct DecParams {
   // per latent block; eps_ready = already filled by lat_noise_fill_kernel (else the forward fills it when a backward follows)
   float* eps_local[3];
   int eps_ready;
+  // cyclic noise pre-pass (lat_noise_fill_cyclic_kernel): per-block launch constants, computed once on the host
+  unsigned int cyc_nloc[3], cyc_gtn[3], cyc_step[3];   // GT / S generator threads of this rank, GT / nz, GT / (nz S)
 };
 
 // DPIVAE.prior_net post-processing and GaussianEncoder.sample on given (loc, scale_tril) (optim_kernels.cu)
@@ -138,7 +141,7 @@ size_t lat_smem_bytes(const DecParams& p, bool bwd);
 void launch_lat_fwd(const DecParams& p, long long n_tiles, cudaStream_t s);
 void launch_lat_bwd(const DecParams& p, long long n_tiles, cudaStream_t s);
 bool lat_pair_supported(const DecParams& p);
-void launch_lat_noise_fill(const DecParams& p, cudaStream_t s);
+void launch_lat_noise_fill(const DecParams& p, bool cyclic, cudaStream_t s);
 int configure_lat_kernels();
 void launch_lat_encode(const DecParams& p, cudaStream_t s);
 bool dec_tc_has_variant(int phys_kind, int nd_x);
@@ -207,7 +210,7 @@ struct EncFusedParams {
   int hn0[3], hN[3];           // head MMA of unit u: accumulator columns [hn0, hn0 + hN) (8-aligned start, multiple of 16 wide)
   float lb[4], ub[4];
   RngP rng;
-  long long Bg, row_off;
+  long long Bg, row_off, row_stride;
   int n_mc;
   int o_ms, o_bars;            // byte offsets: scaler statistics [2][64] floats, mbarrier block (both after the EncTcParams plan)
   float *zx, *zc, *zy, *dens;  // (n_mc, B, nz_*) latents and (n_mc, B) density, any may be null

@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(LNT) lat_fwd_kernel(const __grid_constant__ De
     float v = 0.0f;
     if (pp < npairs) {
       const int r = pp / n, m = pp - r * n;
-      const unsigned long long grow = (unsigned long long)(P.row_off + row0 + r);
+      const unsigned long long grow = (unsigned long long)(P.row_off + (row0 + r) * P.row_stride);
       const int b = block_of_l<D>(P, i), il = i - D::blk_start(P, b), nzb = D::blk_size(P, b);
       const unsigned long long li = ((unsigned long long)m * (unsigned long long)P.Bg + grow) * nzb + il;
       v = P.rng.mode == 0 ? P.rng.eps[b][li] : philox_normal_elem(P.rng.seed, P.rng.ss ? P.rng.ss->philox_off[b] : P.rng.offset[b], P.rng.grid_threads[b], li);
@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(LNT) lat_encode_kernel(const __grid_constant__
   const long long q = (long long)blockIdx.x * LNT + tid;
   if (q >= (long long)P.n_mc * B) return;
   const long long m = q / B, r = q - m * B;
-  const unsigned long long grow = (unsigned long long)(P.row_off + r);
+  const unsigned long long grow = (unsigned long long)(P.row_off + r * P.row_stride);
   // All head pre-activations of this row go to shared memory with 4-byte async copies (own column, read back by the
   // same thread in the same order): ~33 independent loads in flight under the Philox work, instead of loads that the
   // output stores (possible aliases for the compiler) keep in program order.
@@ -770,7 +770,7 @@ __device__ __forceinline__ void pair_eps_fwd(const DecParams& P, int m, long lon
   if (P.eps_ready) {
     ldg_vec<nz>(loc, eps + s);
   } else {
-    const unsigned long long li0 = ((unsigned long long)m * (unsigned long long)P.Bg + (unsigned long long)(P.row_off + lrow)) * nz;
+    const unsigned long long li0 = ((unsigned long long)m * (unsigned long long)P.Bg + (unsigned long long)(P.row_off + lrow * P.row_stride)) * nz;
     const unsigned long long off = P.rng.ss ? P.rng.ss->philox_off[b] : P.rng.offset[b];
 #pragma unroll
     for (int i = 0; i < nz; ++i)
@@ -1094,6 +1094,49 @@ __global__ void __launch_bounds__(256) lat_noise_fill_kernel(const __grid_consta
   if (li0 + 3ull * GT < numel) out[li0 + 3ull * GT] = g1.y;
 }
 
+// The same for a CYCLIC row shard (this rank owns the global rows row_off, row_off + S, ...; S = row_stride).  The four
+// elements of one evaluation are GT apart in the flattened (m, row, i) tensor = GT / nz rows apart; with S | GT / nz and
+// S | Bg they all belong to the rank that owns generator threads idx with (idx / nz) mod S == row_off, so every rank
+// evaluates exactly its own quarter-count of the stream (api.cu checks the divisibility; contiguous row blocks, at most
+// ~1.7 GT long per MC sample, would leave almost nothing to share).  Output in the rank's LOCAL (m, row, i) order.
+__global__ void __launch_bounds__(256) lat_noise_fill_cyclic_kernel(const __grid_constant__ DecParams P) {
+  const int b = blockIdx.z;
+  const unsigned int GT = P.rng.grid_threads[b], nz = (unsigned int)P.blk_size[b];
+  const unsigned int S = (unsigned int)P.row_stride, r0 = (unsigned int)P.row_off, Bg = (unsigned int)P.Bg;
+  const unsigned int t = blockIdx.x * 256u + threadIdx.x;   // this rank's t-th generator thread
+  if (t >= P.cyc_nloc[b]) return;
+  // (a run-time 32-bit division costs ~30 instructions: the per-launch quotients come from the host, and the two divisors
+  // that are powers of two in every shipped shape are shifts)
+  const bool nz_p2 = (nz & (nz - 1u)) == 0u, s_p2 = (S & (S - 1u)) == 0u;
+  const unsigned int u = nz_p2 ? t >> (__ffs((int)nz) - 1) : t / nz, il = t - u * nz;
+  const unsigned int idx = (u * S + r0) * nz + il;
+  const unsigned long long numel = (unsigned long long)P.n_mc * (unsigned long long)P.Bg * nz;
+  const unsigned long long j = blockIdx.y;
+  const unsigned long long li0 = (4ull * j) * GT + idx;
+  if (li0 >= numel) return;
+  const unsigned long long off = P.rng.ss ? P.rng.ss->philox_off[b] : P.rng.offset[b];
+  const unsigned long long nn = (off >> 2) + j;
+  const uint4 ctr = make_uint4((unsigned int)nn, (unsigned int)(nn >> 32), idx, 0u);
+  const uint2 key = make_uint2((unsigned int)P.rng.seed, (unsigned int)(P.rng.seed >> 32));
+  const uint4 r = curand_Philox4x32_10(ctr, key);
+  const float2 g0 = _curand_box_muller(r.x, r.y), g1 = _curand_box_muller(r.z, r.w);
+  const float vals[4] = {g0.x, g0.y, g1.x, g1.y};
+  // (m, local row) of element k = 0 -- one division -- then GT / (nz S) LOCAL rows further per element, wrapping into the
+  // next MC sample after B local rows (n_mc * Bg < 2^31: 32-bit arithmetic)
+  const unsigned int GTn = P.cyc_gtn[b], step = P.cyc_step[b], Bl = (unsigned int)P.B;
+  const unsigned int trow = 4u * (unsigned int)j * GTn + (u * S + r0);   // = li0 / nz (GT is a multiple of nz)
+  unsigned int m = trow / Bg;
+  const unsigned int gl = trow - m * Bg - r0;
+  unsigned int lrow = s_p2 ? gl >> (__ffs((int)S) - 1) : gl / S;
+  float* out = P.eps_local[b];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (li0 + (unsigned long long)k * GT < numel) out[((unsigned long long)m * Bl + lrow) * nz + il] = vals[k];
+    lrow += step;
+    while (lrow >= Bl) { lrow -= Bl; ++m; }
+  }
+}
+
 template <class D>
 static size_t pair_smem_bytes(const DecParams& p, bool bwd) {
   if (bwd) return (size_t)(3 * D::cn_rowpar * RBMAX + D::cn_rowpar * PNT + p.O_tot) * sizeof(float);
@@ -1178,7 +1221,13 @@ bool lat_pair_supported(const DecParams& p) {
   return shape_matches(p, ShBridgeP()) || shape_matches(p, ShBridgeS()) || shape_matches(p, ShOscP()) || shape_matches(p, ShOscS()) ||
          shape_matches(p, ShBeamP()) || shape_matches(p, ShBeamS());
 }
-void launch_lat_noise_fill(const DecParams& p, cudaStream_t s) {
+void launch_lat_noise_fill(const DecParams& p_in, bool cyclic, cudaStream_t s) {
+  DecParams p = p_in;
+  if (cyclic)
+    for (int b = 0; b < p.n_blk; ++b) {
+      const unsigned int GT = p.rng.grid_threads[b], nz = (unsigned int)p.blk_size[b], S = (unsigned int)p.row_stride;
+      p.cyc_nloc[b] = GT / S; p.cyc_gtn[b] = GT / nz; p.cyc_step[b] = GT / nz / S;
+    }
   unsigned long long gt = 0, iters = 0;
   for (int b = 0; b < p.n_blk; ++b) {
     const unsigned long long GT = p.rng.grid_threads[b], numel = (unsigned long long)p.n_mc * (unsigned long long)p.Bg * (unsigned long long)p.blk_size[b];
@@ -1186,7 +1235,12 @@ void launch_lat_noise_fill(const DecParams& p, cudaStream_t s) {
     gt = GT > gt ? GT : gt;
     iters = it > iters ? it : iters;
   }
-  lat_noise_fill_kernel<<<dim3((unsigned)((gt + 255) / 256), (unsigned)iters, (unsigned)p.n_blk), 256, 0, s>>>(p);
+  if (cyclic) {
+    const unsigned long long mine = gt / (unsigned long long)p.row_stride;   // generator threads of this rank
+    lat_noise_fill_cyclic_kernel<<<dim3((unsigned)((mine + 255) / 256), (unsigned)iters, (unsigned)p.n_blk), 256, 0, s>>>(p);
+  } else {
+    lat_noise_fill_kernel<<<dim3((unsigned)((gt + 255) / 256), (unsigned)iters, (unsigned)p.n_blk), 256, 0, s>>>(p);
+  }
 }
 void launch_lat_fwd(const DecParams& p, long long n_tiles, cudaStream_t s) { launch_lat(p, n_tiles, false, s); }
 void launch_lat_bwd(const DecParams& p, long long n_tiles, cudaStream_t s) { launch_lat(p, n_tiles, true, s); }

@@ -35,13 +35,16 @@ class DataParallelStep:
             # identical initial parameters everywhere
             dist.broadcast(self.eng.params, src=0, group=group)
 
-    def step(self, x, c, y, n_mc, weights, B_global, row_offset, step, idx=None, max_grad_norm=0.0):
+    def step(self, x, c, y, n_mc, weights, B_global, row_offset, step, idx=None, max_grad_norm=0.0, row_stride=1):
+        """`row_offset`, `row_stride`: global row of this rank's local row r is row_offset + r * row_stride.  Contiguous
+        shards: (rank * rows, 1).  CYCLIC shards -- (rank, world) -- are the faster choice with in-kernel noise: each rank
+        then owns whole Philox evaluations of torch's noise stream (include/dpivae_b200.h, dpivae_batch_t.row_stride)."""
         eng = self.eng
         if self.world == 1:
             eng.loss(x, c, y, n_mc, weights, True, idx=idx, B_global=B_global, row_offset=row_offset, adam_step=step,
-                     max_grad_norm=max_grad_norm)
+                     max_grad_norm=max_grad_norm, row_stride=row_stride)
         else:
-            eng.loss(x, c, y, n_mc, weights, True, idx=idx, B_global=B_global, row_offset=row_offset)
+            eng.loss(x, c, y, n_mc, weights, True, idx=idx, B_global=B_global, row_offset=row_offset, row_stride=row_stride)
             allreduce_flat(eng.gradbuf, self.group)
             eng.adam_step(step, max_grad_norm)
         return eng.scalars

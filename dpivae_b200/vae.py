@@ -239,7 +239,7 @@ class _Engine:
         gen.set_offset(new_off)
         return r
 
-    def _batch(self, x, c, y, n, cond=False, idx=None, B_global=None, row_offset=0):
+    def _batch(self, x, c, y, n, cond=False, idx=None, B_global=None, row_offset=0, row_stride=1):
         def prep(t):
             return None if t is None else t.to(self.dev, torch.float32).contiguous()
 
@@ -251,13 +251,14 @@ class _Engine:
         b.x, b.c, b.y, b.idx = _ptr(x), _ptr(c), _ptr(y), _ptr(idx)
         b.B, b.B_global, b.row_offset = B, int(B_global if B_global is not None else B), int(row_offset)
         b.n_mc, b.cond = int(n), int(bool(cond))
+        b.row_stride = int(row_stride)   # global row of local row r = row_offset + r * row_stride (cyclic shards: rank, world)
         return b, (x, c, y, idx), B
 
     def loss(self, x, c, y, n, weights, with_grad, outputs=None, eps=None, idx=None, B_global=None, row_offset=0,
-             adam_step=None, max_grad_norm=0.0):
+             adam_step=None, max_grad_norm=0.0, row_stride=1):
         """One dpivae_loss / dpivae_train_step call.  Returns (row_loss (6,B), scalars (8,))."""
         with torch.cuda.device(self.dev):
-            b, keep, B = self._batch(x, c, y, n, False, idx, B_global, row_offset)
+            b, keep, B = self._batch(x, c, y, n, False, idx, B_global, row_offset, row_stride)
             rng = self._rng(b.B_global, n, False, eps)
             w = _lib.LossWeights(*[float(v) for v in weights])
             out = _lib.Outputs()

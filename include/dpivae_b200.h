@@ -80,6 +80,9 @@ typedef struct {
   int64_t row_offset;    /* global index of this shard's first row */
   int32_t n_mc;          /* Monte-Carlo samples per row */
   int32_t cond;          /* forward(cond=True): zc drawn from the prior net (models/vae.py:165-167) */
+  int64_t row_stride;    /* global index of local row r = row_offset + r * row_stride; 0 or 1 = a contiguous block.
+                          * Cyclic shards (rank k of N: row_offset = k, row_stride = N) keep the four noise elements that
+                          * torch's normal_ kernel draws from ONE Philox evaluation on one rank */
 } dpivae_batch_t;
 
 /* Reparameterisation noise.  mode 0: injected buffers eps[k] of shape (n_mc, B_global, nz_k)
@@ -115,7 +118,7 @@ typedef struct {
 int dpivae_create(const dpivae_model_desc_t* desc, dpivae_handle_t* out);
 int dpivae_destroy(dpivae_handle_t h);
 const char* dpivae_last_error(void);
-#define DPIVAE_ABI_VERSION 2   /* 2: dpivae_regression_metrics returns per-output raw values; dpivae_sizeof_model_desc */
+#define DPIVAE_ABI_VERSION 3   /* 2: dpivae_regression_metrics returns per-output raw values; dpivae_sizeof_model_desc; 3: dpivae_batch_t.row_stride */
 int dpivae_abi_version(void);
 size_t dpivae_sizeof_model_desc(void);   /* sizeof(dpivae_model_desc_t) in the binary: bindings check their struct layout */
 

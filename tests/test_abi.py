@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, s), s
     # the ctypes binding lists the same set
     assert sorted(_lib.EXPORTS) == syms
-    assert lib.dpivae_abi_version() == 2
+    assert lib.dpivae_abi_version() == 3
 
 
 def test_struct_sizes_match_header():
@@ -31,7 +31,7 @@ def test_struct_sizes_match_header():
     from dpivae_b200 import _lib
 
     assert ctypes.sizeof(_lib.Mlp2) == 48
-    assert ctypes.sizeof(_lib.Batch) == 4 * 8 + 3 * 8 + 2 * 4
+    assert ctypes.sizeof(_lib.Batch) == 4 * 8 + 3 * 8 + 2 * 4 + 8   # ... + row_stride (ABI 3)
     assert ctypes.sizeof(_lib.Rng) == 8 + 4 * 8 + 8 + 4 * 8 + 4 * 4
     assert ctypes.sizeof(_lib.LossWeights) == 16
     assert ctypes.sizeof(_lib.Outputs) == 12 * 8
