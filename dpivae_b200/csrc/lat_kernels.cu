@@ -951,36 +951,47 @@ __device__ __forceinline__ int pair_src_feature(const DecParams& P, int o) {
   return f;
 }
 
+// Per-pair gradient features of latent block b, written to shared memory in TWO phases that share one buffer (the full
+// [feature][pair] plane -- 25 KB for P bridge, 41 KB for the S presets -- held the kernel at 35 % occupancy):
+//   phase A: d/d loc (slot = latent index), d/d prior mean, d/d prior sigma (slots Z.., Z + nzd..); gl[] stays in registers
+//   phase B: d/d L entries (slot = packed lower-triangular index)
 template <class D, int b>
-__device__ __forceinline__ void pair_grad_block(const DecParams& P, const float* ROWPAR, const float* ROWAUX, int prow, int p, float bw,
-                                                const float* eps, const float* z, const float* u, const float* dz, float* FEAT) {
-  constexpr int nz = Blk<D, b>::nz, s = Blk<D, b>::s, loff = Blk<D, b>::loff, NX = D::cNX, nzd = D::cnzd, Z = D::cZ;
-  constexpr int f_L = Z, f_pmu = Z + D::cnL, f_psig = f_pmu + nzd;
+__device__ __forceinline__ void pair_grad_block_a(const DecParams& P, const float* ROWPAR, const float* ROWAUX, int prow, int p, float bw,
+                                                  const float* z, const float* u, const float* dz, float* gl, float* FEAT) {
+  constexpr int nz = Blk<D, b>::nz, s = Blk<D, b>::s, NX = D::cNX, nzd = D::cnzd, Z = D::cZ;
+  constexpr int f_pmu = Z + D::cnL;
 #pragma unroll
   for (int i = 0; i < nz; ++i) {
     const int gi = s + i;
-    float gl;
     if (gi < NX) {
       float g = dz[nzd + gi];
       if (P.prior_kind[gi] == 1) g += bw * (z[gi] - P.prior_a[gi]) / (P.prior_b[gi] * P.prior_b[gi]);
       const float uu = u[gi < NX ? gi : 0];
-      gl = g * (P.ub[gi] - P.lb[gi]) * uu * (1.0f - uu) + bw * (2.0f * uu - 1.0f);
+      gl[gi] = g * (P.ub[gi] - P.lb[gi]) * uu * (1.0f - uu) + bw * (2.0f * uu - 1.0f);
     } else {
       const int k = gi - NX;
       const float inv = ROWAUX[(f_pmu + k) * RBMAX + prow];   // 1 / sigma of the conditional prior
       const float t = (z[gi] - ROWPAR[(f_pmu + k) * RBMAX + prow]) * inv;
       const float bti = bw * t * inv;
-      gl = dz[k] + bti;
-      FEAT[(f_pmu + k) * PNT + p] = -bti;
-      FEAT[(f_psig + k) * PNT + p] = -bw * (t * t - 1.0f) * inv;
+      gl[gi] = dz[k] + bti;
+      FEAT[(Z + k) * PNT + p] = -bti;
+      FEAT[(Z + nzd + k) * PNT + p] = -bw * (t * t - 1.0f) * inv;
     }
-    FEAT[gi * PNT + p] = gl;
+    FEAT[gi * PNT + p] = gl[gi];
+  }
+}
+template <class D, int b>
+__device__ __forceinline__ void pair_grad_block_b(const float* ROWAUX, int prow, int p, float bw, const float* eps, const float* gl,
+                                                  float* FEAT) {
+  constexpr int nz = Blk<D, b>::nz, s = Blk<D, b>::s, loff = Blk<D, b>::loff, Z = D::cZ;
+#pragma unroll
+  for (int i = 0; i < nz; ++i) {
 #pragma unroll
     for (int j = 0; j <= i; ++j) {
       const int li = loff + i * (i + 1) / 2 + j;
-      float v = gl * eps[s + j];
-      if (j == i) v -= bw * ROWAUX[(f_L + li) * RBMAX + prow];   // 1 / L_ii
-      FEAT[(f_L + li) * PNT + p] = v;
+      float v = gl[s + i] * eps[s + j];
+      if (j == i) v -= bw * ROWAUX[(Z + li) * RBMAX + prow];   // 1 / L_ii
+      FEAT[li * PNT + p] = v;
     }
   }
 }
@@ -990,6 +1001,7 @@ __global__ void __launch_bounds__(PNT) lat_pair_bwd_kernel(const __grid_constant
   extern __shared__ __align__(16) float lsm[];
   pdl_launch_dependents();   // the encoder backward kernel may stage its weights while these tiles are processed
   constexpr int n = D::cn_mc, RB = TP / n, Z = D::cZ, NX = D::cNX, nb = D::cnb, NF = D::cn_rowpar, NQ = n >> 2;
+  constexpr int nL = D::cnL, nzd = D::cnzd, NFA = Z + 2 * nzd, NFB = nL, NFM = NFA > NFB ? NFA : NFB;
   static_assert(n % 4 == 0 && (NQ & (NQ - 1)) == 0, "MC reduction reads float4 groups in a rotated order");
   LatSmem S;
   S.ROWPAR = lsm;
@@ -997,7 +1009,7 @@ __global__ void __launch_bounds__(PNT) lat_pair_bwd_kernel(const __grid_constant
   S.ROWAUX = S.ROWMSK + NF * RBMAX;
   S.ROWRAW = nullptr;
   S.FEAT = S.ROWAUX + NF * RBMAX;
-  int* SRC = reinterpret_cast<int*>(S.FEAT + NF * PNT);
+  int* SRC = reinterpret_cast<int*>(S.FEAT + NFM * PNT);
   const int p = threadIdx.x;
   const long long B = P.B, rb = blockIdx.x, row0 = rb * RB;
   const int nrows = (int)min((long long)RB, B - row0), npairs = nrows * n;
@@ -1023,45 +1035,59 @@ __global__ void __launch_bounds__(PNT) lat_pair_bwd_kernel(const __grid_constant
   for (int o = p; o < P.O_tot; o += PNT) SRC[o] = pair_src_feature<D>(P, o);
   __syncthreads();
 
-  {
-    float z[Z], u[NX > 0 ? NX : 1];
-    float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f;
-    pair_sample_block<D, 0, false>(P, S.ROWPAR, S.ROWAUX, prow, eps, z, u, d0, d1, d2);
-    pair_grad_block<D, 0>(P, S.ROWPAR, S.ROWAUX, prow, p, bw, eps, z, u, dz, S.FEAT);
-    if constexpr (nb > 1) {
-      pair_sample_block<D, 1, false>(P, S.ROWPAR, S.ROWAUX, prow, eps, z, u, d0, d1, d2);
-      pair_grad_block<D, 1>(P, S.ROWPAR, S.ROWAUX, prow, p, bw, eps, z, u, dz, S.FEAT);
-      pair_sample_block<D, 2, false>(P, S.ROWPAR, S.ROWAUX, prow, eps, z, u, d0, d1, d2);
-      pair_grad_block<D, 2>(P, S.ROWPAR, S.ROWAUX, prow, p, bw, eps, z, u, dz, S.FEAT);
-    }
-  }
-  __syncthreads();
   // head-output gradients: MC-axis sum of the feature (n consecutive pairs, fixed order) times the clamp / exp chain-rule
   // factor of the head (models/encoders.py:35-43); consecutive threads write consecutive rows of one feature row of gpre.
   // The float4 groups of a row are read in an order rotated by the row index: the 8 rows of a quarter-warp then hit
   // 8 different bank groups (64-byte row stride: 4-way conflicts otherwise); the order is a function of the row only.
   float gmax = 0.0f;
   const int henc_end = D::hpri(P, 0);
-  for (int e = p; e < P.O_tot * RB; e += PNT) {
-    const int o = e / RB, r = e - o * RB;
-    if (r < nrows) {
+  auto reduce_out = [&](bool phase_b) {
+    for (int e = p; e < P.O_tot * RB; e += PNT) {
+      const int o = e / RB, r = e - o * RB;
       const int f = SRC[o];
-      float g = 0.0f;
-      if (f >= 0) {
-        const float4* s4 = reinterpret_cast<const float4*>(S.FEAT + f * PNT + r * n);
-        const int rot = r >> 1;
-        float s = 0.0f;
+      const bool in_b = f >= Z && f < Z + nL;
+      if (r < nrows && in_b == phase_b) {
+        float g = 0.0f;
+        if (f >= 0) {
+          const int slot = phase_b ? f - Z : (f < Z ? f : f - nL);
+          const float4* s4 = reinterpret_cast<const float4*>(S.FEAT + slot * PNT + r * n);
+          const int rot = r >> 1;
+          float s = 0.0f;
 #pragma unroll
-        for (int m = 0; m < NQ; ++m) {
-          const float4 t = s4[(m + rot) & (NQ - 1)];
-          s += (t.x + t.y) + (t.z + t.w);
+          for (int m = 0; m < NQ; ++m) {
+            const float4 t = s4[(m + rot) & (NQ - 1)];
+            s += (t.x + t.y) + (t.z + t.w);
+          }
+          g = S.ROWMSK[f * RBMAX + r] * s;
         }
-        g = S.ROWMSK[f * RBMAX + r] * s;
+        P.gpre[(long long)o * B + row0 + r] = g;
+        if (o < henc_end) gmax = fmaxf(gmax, fabsf(g));
       }
-      P.gpre[(long long)o * B + row0 + r] = g;
-      if (o < henc_end) gmax = fmaxf(gmax, fabsf(g));
+    }
+  };
+  float gl[Z];
+  {
+    float z[Z], u[NX > 0 ? NX : 1];
+    float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f;
+    pair_sample_block<D, 0, false>(P, S.ROWPAR, S.ROWAUX, prow, eps, z, u, d0, d1, d2);
+    pair_grad_block_a<D, 0>(P, S.ROWPAR, S.ROWAUX, prow, p, bw, z, u, dz, gl, S.FEAT);
+    if constexpr (nb > 1) {
+      pair_sample_block<D, 1, false>(P, S.ROWPAR, S.ROWAUX, prow, eps, z, u, d0, d1, d2);
+      pair_grad_block_a<D, 1>(P, S.ROWPAR, S.ROWAUX, prow, p, bw, z, u, dz, gl, S.FEAT);
+      pair_sample_block<D, 2, false>(P, S.ROWPAR, S.ROWAUX, prow, eps, z, u, d0, d1, d2);
+      pair_grad_block_a<D, 2>(P, S.ROWPAR, S.ROWAUX, prow, p, bw, z, u, dz, gl, S.FEAT);
     }
   }
+  __syncthreads();
+  reduce_out(false);   // loc and prior heads (and the zero rows of the unused upper triangles)
+  __syncthreads();
+  pair_grad_block_b<D, 0>(S.ROWAUX, prow, p, bw, eps, gl, S.FEAT);
+  if constexpr (nb > 1) {
+    pair_grad_block_b<D, 1>(S.ROWAUX, prow, p, bw, eps, gl, S.FEAT);
+    pair_grad_block_b<D, 2>(S.ROWAUX, prow, p, bw, eps, gl, S.FEAT);
+  }
+  __syncthreads();
+  reduce_out(true);    // sigma and covariance heads
   if (P.gpre_max != nullptr) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, off));
@@ -1139,7 +1165,10 @@ __global__ void __launch_bounds__(256) lat_noise_fill_cyclic_kernel(const __grid
 
 template <class D>
 static size_t pair_smem_bytes(const DecParams& p, bool bwd) {
-  if (bwd) return (size_t)(3 * D::cn_rowpar * RBMAX + D::cn_rowpar * PNT + p.O_tot) * sizeof(float);
+  if (bwd) {
+    constexpr int nfa = D::cZ + 2 * D::cnzd, nfm = nfa > D::cnL ? nfa : D::cnL;   // feature plane of the larger phase
+    return (size_t)(3 * D::cn_rowpar * RBMAX + nfm * PNT + p.O_tot) * sizeof(float);
+  }
   return (size_t)(2 * D::cn_rowpar * RBMAX + (D::cndc + D::cndy) * RBMAX + 16) * sizeof(float);
 }
 
