@@ -138,6 +138,28 @@ def test_tc_shard_invariance_with_inkernel_philox(case, mtype):
         assert gu.rel_l2(ssum.cpu(), s.cpu()) < 2e-6
 
 
+@pytest.mark.parametrize("case,mtype", [("bridge", "P"), ("simple_beam", "S")])
+def test_tc_latent_outputs_match_fp32_kernel(case, mtype):
+    """Latent outputs of a loss call (zx / zc / zy / dens_z, models/vae.py:161-176) on the tensor-core path -- written by the
+    thread-per-pair latent kernel -- against the fp32 kernels on the same in-kernel Philox stream."""
+    g, spec, sd, args, case_mod, vae, (x, c, y) = build_from_golden(case, mtype)
+    eng = vae.engine()
+    reps, n = 7, 16
+    X, C_, Y = _tile(x, reps).cuda(), _tile(c, reps).cuda(), _tile(y, reps).cuda()
+    B = X.shape[0]
+    res = {}
+    for mode in ("fp32", "tc_fp16x3"):
+        eng.set_math_mode(mode)
+        out = {"zx": torch.zeros(n, B, vae.nz_x, device="cuda"), "zc": torch.zeros(n, B, vae.nz_c, device="cuda"),
+               "zy": torch.zeros(n, B, vae.nz_y, device="cuda"), "dens_z": torch.zeros(n, B, device="cuda")}
+        torch.manual_seed(3)
+        eng.loss(X, C_, Y, n, (1.0, 1.0, 1.0, 1.0), False, outputs=out)
+        assert eng.used_tensor_cores() == (mode != "fp32")
+        res[mode] = out
+    for k in ("zx", "zc", "zy", "dens_z"):
+        assert gu.rel_l2(res["tc_fp16x3"][k].cpu(), res["fp32"][k].cpu()) < 1e-5, k
+
+
 # The K-step Adam trajectory of the tensor-core mode against the REFERENCE's own `train_model` run lives in
 # tests/test_gpu_ext.py::test_train_model_flagged_run_matches_reference[tc_fp16x3-*] (fixtures with n_mc = 8: the
 # first fixture set has n_mc = 4, below the tensor-core kernel's 8 <= n_mc <= 128 window).

@@ -9,7 +9,7 @@ timeout 600 python -m pytest tests -m gpu -q 2>&1 | tail -15 > $O/${TAG}_pytest_
 timeout 280 python bench.py --steps 20 --warmup 5 > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err
 timeout 280 python bench.py --impl reference --steps 5 --warmup 1 > $O/${TAG}_bench_reference_arm.json 2> /dev/null
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches.csv python bench.py $S > /dev/null 2>&1
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:"dec_tc|lat_fwd|lat_bwd|enc_tc" -s 12 -c 5 -o $O/${TAG}_prof_train python bench.py $S > /dev/null 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:"dec_tc|lat_pair|lat_noise|enc_tc|prior_" -s 16 -c 8 -o $O/${TAG}_prof_train python bench.py $S > /dev/null 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:"enc_fused|noise_fill|enc_tc_fwd|lat_encode" -s 4 -c 4 -o $O/${TAG}_prof_encode python bench.py --workload bridge_encode --steps 2 --warmup 3 > /dev/null 2>&1
 timeout 100 python tools/phase_profile.py bridge_p 32768 tc_fp16x3 > $O/${TAG}_phase_bridge_p_tc.log 2>&1
 timeout 100 python tools/phase_profile.py beam_s 32768 tc_fp16x3 > $O/${TAG}_phase_beam_s_tc.log 2>&1
