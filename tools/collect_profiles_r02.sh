@@ -8,6 +8,8 @@ S="--steps 2 --warmup 3 --no-workloads --no-cpu-baseline --no-other-modes --sust
 timeout 600 python -m pytest tests -m gpu -q 2>&1 | tail -15 > $O/${TAG}_pytest_gpu.log
 timeout 280 python bench.py --steps 20 --warmup 5 > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err
 timeout 280 python bench.py --impl reference --steps 5 --warmup 1 > $O/${TAG}_bench_reference_arm.json 2> /dev/null
+timeout 200 python bench.py --scaling strong --steps 5 --warmup 3 --no-workloads --no-cpu-baseline --no-other-modes --sustain-s 0 > $O/${TAG}_bench_1gpu_strong.json 2> /dev/null
+timeout 200 python bench.py --workload bridge_s --steps 20 --warmup 5 --no-workloads --no-cpu-baseline --no-other-modes --sustain-s 0 > $O/${TAG}_bench_bridge_s.json 2> /dev/null
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches.csv python bench.py $S > /dev/null 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:"dec_tc|lat_pair|lat_noise|enc_tc|prior_" -s 16 -c 8 -o $O/${TAG}_prof_train python bench.py $S > /dev/null 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:"enc_fused|noise_fill|enc_tc_fwd|lat_encode" -s 4 -c 4 -o $O/${TAG}_prof_encode python bench.py --workload bridge_encode --steps 2 --warmup 3 > /dev/null 2>&1
