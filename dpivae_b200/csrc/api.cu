@@ -746,7 +746,8 @@ static int run_loss(dpivae_handle_t h, const dpivae_batch_t* bt, const dpivae_rn
         // evaluation are grid_threads apart in the flattened (m, row, i) tensor, i.e. grid_threads / nz rows apart, so they
         // then fall on the same rank.  Contiguous shards keep the per-element generator inside the forward.
         int prepass = 0;
-        if (rng->mode == 1 && !no_prepass) {
+        // (below 16 k pairs the per-element generator inside the forward is cheaper than one more launch: same stream)
+        if (rng->mode == 1 && !no_prepass && (long long)bt->B * bt->n_mc >= 16384) {
           if (bt->B_global == bt->B && bt->row_offset == 0) prepass = 1;
           else if (row_stride > 1 && bt->B * row_stride == bt->B_global && bt->row_offset < row_stride &&
                    (unsigned long long)bt->n_mc * (unsigned long long)bt->B_global < (1ull << 31)) {
