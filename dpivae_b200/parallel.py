@@ -1,8 +1,9 @@
 """Batch-sharded data parallelism for the fused step (the reference has no
-distributed code).  One process per GPU; rank r owns rows [r*B/G, (r+1)*B/G) of the global
-minibatch; noise is indexed by GLOBAL row and the loss normalised by the GLOBAL batch inside the
-kernels, so the only exchange is ONE allreduce(sum) of the flat [gradients | 8 loss scalars]
-buffer between the backward and the (replicated, identical) fused Adam update."""
+distributed code).  One process per GPU; rank r owns a shard of the rows of the global minibatch
+-- a contiguous block, or (preferred with in-kernel noise) the CYCLIC shard r, r + G, r + 2G, ... --;
+noise is indexed by GLOBAL row and the loss normalised by the GLOBAL batch inside the kernels, so
+the only exchange is ONE allreduce(sum) of the flat [gradients | 8 loss scalars] buffer between
+the backward and the (replicated, identical) fused Adam update."""
 import torch
 import torch.distributed as dist
 
@@ -12,6 +13,33 @@ def shard_bounds(n_rows, world_size, rank):
     base, rem = divmod(int(n_rows), int(world_size))
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
+
+
+def torch_normal_grid_threads(numel, sm_count=148, max_threads_per_sm=2048):
+    """Threads of the grid torch's CUDA `normal_` kernel launches for a tensor of `numel` elements
+    (ATen/native/cuda/DistributionTemplates.h; dpivae_philox_plan in csrc/api.cu computes the same): generator thread
+    idx draws the elements idx + grid_threads * (4 j + k), k = 0..3, of call j from ONE Philox evaluation."""
+    grid = min((int(numel) + 255) // 256, int(sm_count) * (int(max_threads_per_sm) // 256))
+    return 256 * max(grid, 1)
+
+
+def cyclic_shards_own_whole_evaluations(grid_threads, nz, world_size, rows_global):
+    """True when, with cyclic row shards (rank k owns global rows k, k + world, ...), the four elements of every Philox
+    evaluation of the (n_mc, rows_global, nz) noise tensor belong to ONE rank -- the condition under which every rank
+    can draw its noise with one evaluation per four elements (lat_noise_fill_cyclic_kernel; run_loss in csrc/api.cu
+    applies the same test).  The elements are grid_threads apart in the flattened tensor = grid_threads / nz rows."""
+    s, nz = int(world_size), int(nz)
+    return s >= 1 and int(grid_threads) % (nz * s) == 0 and int(rows_global) % s == 0
+
+
+def cyclic_local_slot(li, nz, world_size, rank, rows_global):
+    """(owner rank, local flat index) of element `li` of the flattened (n_mc, rows_global, nz) noise tensor under
+    cyclic row shards: the destination the cyclic noise pre-pass writes (local (m, row, i) order of the shard)."""
+    nz, s, bg = int(nz), int(world_size), int(rows_global)
+    il, trow = li % nz, li // nz
+    m, grow = divmod(trow, bg)
+    owner, lrow = grow % s, grow // s
+    return owner, (m * (bg // s) + lrow) * nz + il
 
 
 def allreduce_flat(buf, group=None):

@@ -180,3 +180,53 @@ def test_setup_model_builds_full_cov_prior_nets():
     names = dict(vae.named_parameters())
     assert tuple(names["prior_net_c.net.f_cov.weight"].shape) == (vae.nz_c * vae.nz_c, 64)
     assert tuple(names["prior_net_y.net.f_cov.bias"].shape) == (vae.nz_y * vae.nz_y,)
+
+
+def test_cyclic_shards_keep_philox_evaluations_on_one_rank():
+    """Host restatement of the cyclic noise pre-pass (lat_noise_fill_cyclic_kernel, csrc/lat_kernels.cu): when world * nz
+    divides torch's generator grid, the four elements a generator thread draws from one Philox evaluation land on ONE
+    rank, every rank's slots tile its local (m, row, i) buffer exactly once, and the kernel's incremental decoding
+    (one division, then + grid_threads / (nz world) local rows per element) agrees with the direct formula."""
+    from dpivae_b200.parallel import cyclic_local_slot, cyclic_shards_own_whole_evaluations, torch_normal_grid_threads
+
+    cases = [(16, 216, 4, 2), (16, 216, 2, 4), (16, 4104, 4, 8), (3, 40, 1, 2), (16, 131072 * 8, 4, 8), (16, 216, 10, 2)]
+    for n_mc, bg, nz, world in cases:
+        numel = n_mc * bg * nz
+        gt = torch_normal_grid_threads(numel)
+        assert gt % 256 == 0 and gt <= 148 * 8 * 256
+        ok = cyclic_shards_own_whole_evaluations(gt, nz, world, bg)
+        if numel > 2_000_000:      # the bench shape: eligible (2^13 * 37 generator threads), too large to enumerate here
+            assert ok and gt == 303104
+            continue
+        if not ok:
+            continue
+        b_local = bg // world
+        seen = [np.zeros(n_mc * b_local * nz, dtype=np.int32) for _ in range(world)]
+        iters = (numel + 4 * gt - 1) // (4 * gt)
+        for rank in range(world):
+            for t in range(gt // world):                 # this rank's generator threads (kernel: blockIdx.x * 256 + threadIdx.x)
+                u, il = divmod(t, nz)
+                idx = (u * world + rank) * nz + il
+                assert (idx // nz) % world == rank
+                for j in range(iters):
+                    li0 = 4 * j * gt + idx
+                    if li0 >= numel:
+                        break
+                    # kernel decode: one division for element 0, then incremental local rows
+                    gtn, step = gt // nz, gt // nz // world
+                    trow = 4 * j * gtn + (u * world + rank)
+                    m, lrow = trow // bg, (trow % bg - rank) // world
+                    for k in range(4):
+                        li = li0 + k * gt
+                        if li < numel:
+                            owner, dst = cyclic_local_slot(li, nz, world, rank, bg)
+                            assert owner == rank                      # the whole evaluation belongs to this rank
+                            assert dst == (m * b_local + lrow) * nz + il
+                            seen[rank][dst] += 1
+                        lrow += step
+                        while lrow >= b_local:
+                            lrow -= b_local
+                            m += 1
+        for rank in range(world):
+            assert (seen[rank] == 1).all()              # every local element drawn exactly once
+    assert not cyclic_shards_own_whole_evaluations(303104, 10, 2, 1 << 20)   # S presets of width 10: per-element fallback
