@@ -512,12 +512,6 @@ __global__ void __launch_bounds__(NALL, 1) dec_tc_kernel(const __grid_constant__
     // the top of the first tile and, when a backward follows, EARLY for every later tile: the x path signals as soon as
     // the previous tile's last reader of C_X is through, so these MMAs queue behind that tile's last weight gradients
     // and their results are ready when the next tile starts.
-    // static issue: the shapes of the shipped cases (latent operand of 16 columns, 3-term split, and for the MLP surrogate the
-    // bridge's 64 / 32 / 64 hidden widths) take fully unrolled, immediate-offset MMA series (tc.cuh issue_*_s); anything else
-    // keeps the run-time loops
-    // (closed-form physics cases: their tiles are bound by the auxiliary-decoder warps, whose own M = 64 MMAs then queue
-    // behind the burst of an unrolled series -- measured beam_s 0.48 -> 0.62 ms -- so they keep the paced run-time loops)
-    const bool stat = mlp && terms == 3 && KZ == 16 && d1 == 64 && d2 == 32 && d3 == 64;
     auto issue_s0 = [&](int it_) {
       const int buf_ = it_ & 1;
       const tc::Op oL = mkop(RECB + (size_t)buf_ * T.rec_buf, 0, 4096u, TP);
@@ -525,13 +519,8 @@ __global__ void __launch_bounds__(NALL, 1) dec_tc_kernel(const __grid_constant__
       __syncwarp();
       issuer_wait(sid++);   // S0
       ISSUER_MARK(iw);
-      if (stat) {
-        tc::issue_fwd_s<128, 16, 3, TP>(el, tbu + C_H, oL, oWFX0, 0);
-        if constexpr (mlp) tc::issue_fwd_s<64, 16, 3, TP>(el, tbu + C_X, oL, oWP0, 0);
-      } else {
-        tc::issue_fwd_w(el, tbu + C_H, oL, oWFX0, 128, KZ, 0, terms);
-        if constexpr (mlp) tc::issue_fwd_w(el, tbu + C_X, oL, oWP0, d1, KZ, 0, terms);
-      }
+      tc::issue_fwd_w(el, tbu + C_H, oL, oWFX0, 128, KZ, 0, terms);
+      if constexpr (mlp) tc::issue_fwd_w(el, tbu + C_X, oL, oWP0, d1, KZ, 0, terms);
       tc::commit_w(el, bar0);
       __syncwarp();
       ISSUER_MARK(ii);
@@ -545,31 +534,27 @@ __global__ void __launch_bounds__(NALL, 1) dec_tc_kernel(const __grid_constant__
       if constexpr (mlp) {
         issuer_wait(sid++);   // S2: physics layer 1
         ISSUER_MARK(iw);
-        if (stat) tc::issue_fwd_ts_s<32, 64, 3>(el, tbu + C_S, tbu + C_A0, oWP1, 0);
-        else tc::issue_fwd_ts_w(el, tbu + C_S, tbu + C_A0, oWP1, d2, d1, 0, terms);
+        tc::issue_fwd_ts_w(el, tbu + C_S, tbu + C_A0, oWP1, d2, d1, 0, terms);
         tc::commit_w(el, bar0);
         __syncwarp();
         ISSUER_MARK(ii);
       }
       issuer_wait(sid++);   // S5a: output layer of the data-driven decoder, as soon as its hidden activations are staged
       ISSUER_MARK(iw);
-      if (stat) tc::issue_fwd_s<ndx, 128, 3, TP>(el, tbu + C_X, oBIG, oWFX1, 0);
-      else tc::issue_fwd_w(el, tbu + C_X, oBIG, oWFX1, ndx, 128, 0, terms);
+      tc::issue_fwd_w(el, tbu + C_X, oBIG, oWFX1, ndx, 128, 0, terms);
       if constexpr (!mlp) tc::commit_w(el, bar0);   // (MLP physics: the commit of S5b covers these MMAs too)
       __syncwarp();
       ISSUER_MARK(ii);
       if constexpr (mlp) {
         issuer_wait(sid++);   // S4: physics layer 2 -> first half of C_H (the fx0 accumulator has been consumed)
         ISSUER_MARK(iw);
-        if (stat) tc::issue_fwd_ts_s<64, 32, 3>(el, tbu + C_H, tbu + C_A1, oWP2, 0);
-        else tc::issue_fwd_ts_w(el, tbu + C_H, tbu + C_A1, oWP2, d3, d2, 0, terms);
+        tc::issue_fwd_ts_w(el, tbu + C_H, tbu + C_A1, oWP2, d3, d2, 0, terms);
         tc::commit_w(el, bar0);
         __syncwarp();
         ISSUER_MARK(ii);
         issuer_wait(sid++);   // S5b: last physics layer on top of the data-driven decoder's output
         ISSUER_MARK(iw);
-        if (stat) tc::issue_fwd_ts_s<ndx, 64, 3>(el, tbu + C_X, tbu + C_A2, oWP3, 1);
-        else tc::issue_fwd_ts_w(el, tbu + C_X, tbu + C_A2, oWP3, ndx, d3, 1, terms);
+        tc::issue_fwd_ts_w(el, tbu + C_X, tbu + C_A2, oWP3, ndx, d3, 1, terms);
         tc::commit_w(el, bar0);
         __syncwarp();
         ISSUER_MARK(ii);
@@ -580,11 +565,9 @@ __global__ void __launch_bounds__(NALL, 1) dec_tc_kernel(const __grid_constant__
         {
           // MLP physics: the planes of W_p3 sit right behind those of W_fx1 (same row count), C_X right behind C_H: ONE
           // N = 192 dgrad per K step for both (96 cycles instead of 2 x 64: the A operand is fetched once)
-          if (stat) tc::issue_dgrad_s<ndx, mlp ? 192 : 128, 3, TP, ndx>(el, tbu + C_H, oG, oWFX1, 0);
-          else tc::issue_dgrad_w(el, tbu + C_H, oG, oWFX1, ndx, mlp ? 128 + d3 : 128, 0, terms);
+          tc::issue_dgrad_w(el, tbu + C_H, oG, oWFX1, ndx, mlp ? 128 + d3 : 128, 0, terms);
           tc::commit_w(el, bar0);
-          if (stat) tc::issue_wgrad_s<ndx, 3, TP, TP>(el, tbu + C_W1, oBIG, oG, wacc);
-          else tc::issue_wgrad_w(el, tbu + C_W1, oBIG, oG, ndx, wacc, terms);
+          tc::issue_wgrad_w(el, tbu + C_W1, oBIG, oG, ndx, wacc, terms);
           tc::commit_w(el, bar1);
         }
         __syncwarp();
@@ -593,8 +576,7 @@ __global__ void __launch_bounds__(NALL, 1) dec_tc_kernel(const __grid_constant__
           issuer_wait(sid++);   // S7
           ISSUER_MARK(iw);
           {
-            if (stat) tc::issue_dgrad_ts_s<64, 32, 3, 64>(el, tbu + C_S, tbu + C_A2, oWP2, 0);
-            else tc::issue_dgrad_ts_w(el, tbu + C_S, tbu + C_A2, oWP2, d3, d2, 0, terms);
+            tc::issue_dgrad_ts_w(el, tbu + C_S, tbu + C_A2, oWP2, d3, d2, 0, terms);
             tc::commit_w(el, bar0);
           }
           __syncwarp();
@@ -607,17 +589,11 @@ __global__ void __launch_bounds__(NALL, 1) dec_tc_kernel(const __grid_constant__
         if constexpr (mlp) {
           issuer_wait(sid++);   // S9
           ISSUER_MARK(iw);
-          if (stat) tc::issue_dgrad_ts_s<32, 64, 3, 32>(el, tbu + C_X, tbu + C_A1, oWP1, 0);
-          else tc::issue_dgrad_ts_w(el, tbu + C_X, tbu + C_A1, oWP1, d2, d1, 0, terms);
+          tc::issue_dgrad_ts_w(el, tbu + C_X, tbu + C_A1, oWP1, d2, d1, 0, terms);
           tc::commit_w(el, bar0);
         }
-        if (stat) {
-          tc::issue_dgrad_s<128, 16, 3, TP, 128>(el, tbu + C_T, oBIG, oWFX0, 0);
-          tc::issue_wgrad_s<16, 3, TP, TP>(el, tbu + C_W0, oBIG, oLAT, wacc);
-        } else {
-          tc::issue_dgrad_w(el, tbu + C_T, oBIG, oWFX0, 128, KZ, 0, terms);
-          tc::issue_wgrad_w(el, tbu + C_W0, oBIG, oLAT, KZ, wacc, terms);
-        }
+        tc::issue_dgrad_w(el, tbu + C_T, oBIG, oWFX0, 128, KZ, 0, terms);
+        tc::issue_wgrad_w(el, tbu + C_W0, oBIG, oLAT, KZ, wacc, terms);
         tc::commit_w(el, bar1);
         __syncwarp();
         ISSUER_MARK(ii);

@@ -459,55 +459,6 @@ __device__ __forceinline__ void issue_fwd_ts_s(uint32_t el, uint32_t d_tmem, uin
     }
   }
 }
-// compile-time shapes of the dgrad / wgrad forms (same operand conventions as the run-time versions below): every
-// descriptor is base + immediate and both loops unroll, so the single issuing warp spends its cycles on the MMAs
-// instead of on uniform-datapath address arithmetic
-//   dgrad : D[128][NIN] (+)= sum_o G[r][o] W[o][k]   G K-major (GR rows), W MN-major (WR rows); KOUT = contraction length
-template <int KOUT, int NIN, int TERMS, int GR, int WR>
-__device__ __forceinline__ void issue_dgrad_s(uint32_t el, uint32_t d_tmem, Op g, Op w, uint32_t accumulate) {
-  constexpr uint32_t idesc = make_idesc(128, NIN, 0, 1);
-  constexpr uint32_t ghi = 8u | DESC_VERSION_HI, whi = (uint32_t)WR | DESC_VERSION_HI;
-  const uint32_t g0 = ((g.base >> 4) & 0x3FFFu) | ((uint32_t)GR << 16), g1 = (((g.base + g.lo_off) >> 4) & 0x3FFFu) | ((uint32_t)GR << 16);
-  const uint32_t w0 = ((w.base >> 4) & 0x3FFFu) | (8u << 16), w1 = (((w.base + w.lo_off) >> 4) & 0x3FFFu) | (8u << 16);
-#pragma unroll
-  for (int t = 0; t < TERMS; ++t) {
-#pragma unroll
-    for (int k = 0; k < (KOUT >> 4); ++k) {
-      mma_f16_w(el, d_tmem, pack64((t == 1 ? g1 : g0) + (uint32_t)(k * 2 * GR), ghi), pack64((t == 2 ? w1 : w0) + (uint32_t)(k * 16), whi), idesc,
-                (t == 0 && k == 0) ? accumulate : 1u);
-    }
-  }
-}
-template <int KOUT, int NIN, int TERMS, int WR>
-__device__ __forceinline__ void issue_dgrad_ts_s(uint32_t el, uint32_t d_tmem, uint32_t g_tmem, Op w, uint32_t accumulate) {
-  constexpr uint32_t idesc = make_idesc(128, NIN, 0, 1);
-  constexpr uint32_t whi = (uint32_t)WR | DESC_VERSION_HI;
-  const uint32_t w0 = ((w.base >> 4) & 0x3FFFu) | (8u << 16), w1 = (((w.base + w.lo_off) >> 4) & 0x3FFFu) | (8u << 16);
-#pragma unroll
-  for (int t = 0; t < TERMS; ++t) {
-#pragma unroll
-    for (int k = 0; k < (KOUT >> 4); ++k) {
-      mma_f16_ts_w(el, d_tmem, g_tmem + (uint32_t)((t == 1 ? (KOUT >> 1) : 0) + 8 * k), pack64((t == 2 ? w1 : w0) + (uint32_t)(k * 16), whi), idesc,
-                   (t == 0 && k == 0) ? accumulate : 1u);
-    }
-  }
-}
-//   wgrad : D[128 units][N] (+)= sum_r H[r][unit] G[r][n]   both MN-major, HR = GR rows = contraction length
-template <int N, int TERMS, int HR, int GR>
-__device__ __forceinline__ void issue_wgrad_s(uint32_t el, uint32_t d_tmem, Op h, Op g, uint32_t accumulate) {
-  constexpr uint32_t idesc = make_idesc(128, N, 1, 1);
-  constexpr uint32_t hhi = (uint32_t)HR | DESC_VERSION_HI, ghi = (uint32_t)GR | DESC_VERSION_HI;
-  const uint32_t h0 = ((h.base >> 4) & 0x3FFFu) | (8u << 16), h1 = (((h.base + h.lo_off) >> 4) & 0x3FFFu) | (8u << 16);
-  const uint32_t g0 = ((g.base >> 4) & 0x3FFFu) | (8u << 16), g1 = (((g.base + g.lo_off) >> 4) & 0x3FFFu) | (8u << 16);
-#pragma unroll
-  for (int t = 0; t < TERMS; ++t) {
-#pragma unroll
-    for (int k = 0; k < (HR >> 4); ++k) {
-      mma_f16_w(el, d_tmem, pack64((t == 1 ? h1 : h0) + (uint32_t)(k * 16), hhi), pack64((t == 2 ? g1 : g0) + (uint32_t)(k * 16), ghi), idesc,
-                (t == 0 && k == 0) ? accumulate : 1u);
-    }
-  }
-}
 __device__ __forceinline__ void issue_dgrad_w(uint32_t el, uint32_t d_tmem, Op g, Op w, int Nout, int Kin, uint32_t accumulate, int terms) {
   const uint32_t idesc = make_idesc(128, Kin, 0, 1);
   const uint32_t ghi = 8u | DESC_VERSION_HI, whi = (uint32_t)w.R | DESC_VERSION_HI;
