@@ -16,11 +16,13 @@ namespace {
 
 constexpr int PNT = 256;    // forward: rows per CTA pass
 constexpr int PH = 64;      // hidden units per prior net (reference: FactorizedNN(nz, nd, [64]), dpivae.py:156-157)
-constexpr int PO = 16;      // head outputs per net, padded (2 nz <= 16)
+constexpr int PO_MAX = 16;  // head outputs per net, padded (2 nz <= 16); the kernels are instantiated for PO = 8 and 16: the bridge /
+                            // oscillator nets have 8 outputs, and zero-padded outputs cost a third of the backward's FMAs
 constexpr int PK = 4;       // inputs per net, padded (nd_c, nd_y <= 4)
 constexpr int PTILE = 128;  // backward: rows staged per pass
 constexpr int PRG = 4;      // backward: row groups per CTA (thread = (row group, net, hidden unit); rows r = rg mod PRG)
 
+template <int PO>
 struct PriorW {   // one net in shared memory
   float w0[PH][PK];
   float b0[PH];
@@ -28,7 +30,8 @@ struct PriorW {   // one net in shared memory
   float b1[PO];
 };
 
-__device__ __forceinline__ void stage_prior(const EncParams& P, const EncUnit& U, PriorW& W, int tid, int nthr) {
+template <int PO>
+__device__ __forceinline__ void stage_prior(const EncParams& P, const EncUnit& U, PriorW<PO>& W, int tid, int nthr) {
   for (int e = tid; e < PH * PK; e += nthr) {
     const int k = e / PK, j = e - k * PK;
     W.w0[k][j] = (k < U.H && j < U.K0) ? P.params[U.g_w0 + (long long)k * U.K0 + j] : 0.0f;
@@ -52,8 +55,9 @@ __device__ __forceinline__ void load_ct(const EncParams& P, const EncUnit& U, lo
 
 }  // namespace
 
+template <int PO>
 __global__ void __launch_bounds__(PNT) prior_fwd_kernel(const __grid_constant__ EncParams P) {
-  __shared__ PriorW W;
+  __shared__ PriorW<PO> W;
   for (int u = 0; u < P.n_units; ++u) {
     const EncUnit& U = P.u[u];
     if (U.src == 2 && P.y == nullptr) continue;
@@ -99,6 +103,7 @@ __global__ void __launch_bounds__(PNT) prior_fwd_kernel(const __grid_constant__ 
 }
 
 // blockDim = PRG * 64 * n_units: thread (row group rg, net u, hidden unit k)
+template <int PO>
 __global__ void __launch_bounds__(PRG * 2 * PH) prior_bwd_kernel(const __grid_constant__ EncParams P) {
   __shared__ __align__(16) float CT[2][PTILE][PK];
   __shared__ __align__(16) float G[2][PTILE][PO];
@@ -169,7 +174,10 @@ __global__ void __launch_bounds__(PRG * 2 * PH) prior_bwd_kernel(const __grid_co
         a_w1[4 * q4] = fmaf(g.x, h, a_w1[4 * q4]); a_w1[4 * q4 + 1] = fmaf(g.y, h, a_w1[4 * q4 + 1]);
         a_w1[4 * q4 + 2] = fmaf(g.z, h, a_w1[4 * q4 + 2]); a_w1[4 * q4 + 3] = fmaf(g.w, h, a_w1[4 * q4 + 3]);
       }
-      const float gh = pre > 0.0f ? (gq[0] + gq[1]) + (gq[2] + gq[3]) : 0.0f;
+      float gsum;
+      if constexpr (PO == 16) gsum = (gq[0] + gq[1]) + (gq[2] + gq[3]);
+      else gsum = gq[0] + gq[1];
+      const float gh = pre > 0.0f ? gsum : 0.0f;
       a_w0[0] = fmaf(gh, c4.x, a_w0[0]); a_w0[1] = fmaf(gh, c4.y, a_w0[1]); a_w0[2] = fmaf(gh, c4.z, a_w0[2]); a_w0[3] = fmaf(gh, c4.w, a_w0[3]);
       a_b0 += gh;
       if (k < PO) a_b1 += G[u][r][k];   // head-bias gradient of output k
@@ -219,20 +227,36 @@ __global__ void __launch_bounds__(PRG * 2 * PH) prior_bwd_kernel(const __grid_co
 bool prior_kernels_support(const EncParams& p) {
   if (p.n_units < 1 || p.n_units > 2) return false;
   for (int u = 0; u < p.n_units; ++u)
-    if (p.u[u].H > PH || p.u[u].O > PO || p.u[u].K0 > PK || p.u[u].src == 0) return false;
+    if (p.u[u].H > PH || p.u[u].O > PO_MAX || p.u[u].K0 > PK || p.u[u].src == 0) return false;
+  return true;
+}
+
+static bool prior_small_heads(const EncParams& p) {
+  for (int u = 0; u < p.n_units; ++u)
+    if (p.u[u].O > 8) return false;
   return true;
 }
 
 void launch_prior_fwd(const EncParams& p, int sm_count, cudaStream_t s, bool overlap) {
   long long g = (p.B + 2 * PNT - 1) / (2 * PNT);   // two rows per thread
   if (g > 4LL * sm_count) g = 4LL * sm_count;
-  if (overlap) launch_pdl(prior_fwd_kernel, (int)(g < 1 ? 1 : g), PNT, 0, s, p);
-  else prior_fwd_kernel<<<(unsigned)(g < 1 ? 1 : g), PNT, 0, s>>>(p);
+  if (prior_small_heads(p)) {
+    if (overlap) launch_pdl(prior_fwd_kernel<8>, (int)(g < 1 ? 1 : g), PNT, 0, s, p);
+    else prior_fwd_kernel<8><<<(unsigned)(g < 1 ? 1 : g), PNT, 0, s>>>(p);
+  } else {
+    if (overlap) launch_pdl(prior_fwd_kernel<16>, (int)(g < 1 ? 1 : g), PNT, 0, s, p);
+    else prior_fwd_kernel<16><<<(unsigned)(g < 1 ? 1 : g), PNT, 0, s>>>(p);
+  }
 }
 
 void launch_prior_bwd(const EncParams& p, int grid, cudaStream_t s, bool overlap) {
-  if (overlap) launch_pdl(prior_bwd_kernel, grid, PRG * PH * p.n_units, 0, s, p);
-  else prior_bwd_kernel<<<grid, PRG * PH * p.n_units, 0, s>>>(p);
+  if (prior_small_heads(p)) {
+    if (overlap) launch_pdl(prior_bwd_kernel<8>, grid, PRG * PH * p.n_units, 0, s, p);
+    else prior_bwd_kernel<8><<<grid, PRG * PH * p.n_units, 0, s>>>(p);
+  } else {
+    if (overlap) launch_pdl(prior_bwd_kernel<16>, grid, PRG * PH * p.n_units, 0, s, p);
+    else prior_bwd_kernel<16><<<grid, PRG * PH * p.n_units, 0, s>>>(p);
+  }
 }
 
 }  // namespace dpv
