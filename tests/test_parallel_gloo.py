@@ -12,7 +12,7 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, out_path):
+def _worker(rank, world, port, out_path, cyclic=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import golden_util as gu
@@ -29,9 +29,13 @@ def _worker(rank, world, port, out_path):
     x, c, y = (torch.from_numpy(g[k]).double() for k in "xcy")
     B = x.shape[0]
     eps = tuple(e.double() for e in gu.eps_of(g, spec))
-    lo, hi = shard_bounds(B, world, rank)
-    eps_s = tuple(e[:, lo:hi] for e in eps)
-    scal, _, _, grads = orc.loss_and_grads(sd, spec, x[lo:hi], c[lo:hi], y[lo:hi], eps_s, n_batch=B)
+    if cyclic:   # rank k owns the global rows k, k + world, ... (dpivae_batch_t.row_stride; DataParallelStep's default)
+        rows = slice(rank, None, world)
+    else:
+        lo, hi = shard_bounds(B, world, rank)
+        rows = slice(lo, hi)
+    eps_s = tuple(e[:, rows] for e in eps)
+    scal, _, _, grads = orc.loss_and_grads(sd, spec, x[rows], c[rows], y[rows], eps_s, n_batch=B)
     flat = torch.cat([grads[k].reshape(-1) for k in spec["trainable"]] + [torch.stack(scal)])
     allreduce_flat(flat)
     if rank == 0:
@@ -40,14 +44,18 @@ def _worker(rank, world, port, out_path):
     dist.destroy_process_group()
 
 
-def test_two_shards_allreduce_equals_full_batch(tmp_path):
+import pytest
+
+
+@pytest.mark.parametrize("cyclic", [False, True])
+def test_two_shards_allreduce_equals_full_batch(tmp_path, cyclic):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import golden_util as gu
     from oracle import dpivae_oracle as orc
 
     out = str(tmp_path / "flat.pt")
-    port = 29500 + (os.getpid() % 2000)
-    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    port = 29500 + (os.getpid() % 2000) + (7 if cyclic else 0)
+    mp.spawn(_worker, args=(2, port, out, cyclic), nprocs=2, join=True)
     flat = torch.load(out)
     g, spec, sd = gu.load("bridge", "P")
     spec = orc.cast_spec(spec, torch.float64)
