@@ -1,18 +1,25 @@
 // Per-pair latent kernels of the tensor-core path (sm_100a): everything between the encoder heads and the
 // decoders that is scalar work per (row, MC-sample) pair, kept OUT of the tensor-core decoder kernel so that it
-// runs at full occupancy instead of on the 8 latency-bound epilogue warps:
+// runs at full occupancy instead of on the latency-bound epilogue warps:
 //
-//   lat_fwd_kernel : head post-processing (clamp / exp / tril, models/encoders.py:35-43), reparameterised sample
-//                    z = loc + L eps (models/encoders.py:73-93), logistic + shift/scale bijector and its log-det
-//                    (utils/transforms.py:97-150), log q, log p(zx) (utils/priors.py:19-23), log p(zc|c), log p(zy|y)
-//                    (models/vae.py:200-207) -> per-row KL; writes, per 128-pair tile, the decoder kernel's input
-//                    RECORD: the latent operand [zd | 1 | physics input] already split into fp16 hi/lo planes in the
-//                    X8 layout of tc.cuh (the decoder kernel bulk-copies it straight into its operand buffer) plus
-//                    the raw c / y values per pair, and the noise (reused by the backward).
-//   lat_bwd_kernel : from the decoder kernel's per-pair dL/dz record: gradients w.r.t. loc / L / prior-net heads,
-//                    reduced over the MC axis, chain rule through clamp / exp -> gpre (input of enc_bwd_kernel).
+//   forward  : head post-processing (clamp / exp / tril, models/encoders.py:35-43), reparameterised sample
+//              z = loc + L eps (models/encoders.py:73-93), logistic + shift/scale bijector and its log-det
+//              (utils/transforms.py:97-150), log q, log p(zx) (utils/priors.py:19-23), log p(zc|c), log p(zy|y)
+//              (models/vae.py:200-207) -> per-row KL; writes, per 128-pair tile, the decoder kernel's input
+//              RECORD: the latent operand [zd | 1 | physics input] already split into fp16 hi/lo planes in the
+//              X8 layout of tc.cuh (the decoder kernel bulk-copies it straight into its operand buffer) plus
+//              the raw c / y values per pair.
+//   backward : from the decoder kernel's per-pair dL/dz record: gradients w.r.t. loc / L / prior-net heads,
+//              reduced over the MC axis, chain rule through clamp / exp -> gpre (input of the encoder backward).
 //
-// One CTA (256 threads) per tile of 128 pairs = RB rows x n_mc samples, same tiling as dec_tc_kernel.
+// Two implementations of each, same tiling as dec_tc_kernel (one tile = 128 pairs = RB rows x n_mc samples):
+//   lat_pair_fwd_kernel / lat_pair_bwd_kernel (second half of this file): thread-per-pair kernels for the compile-time
+//     shapes of the reference's six case x model presets at n_mc = 16, with the noise drawn ahead by
+//     lat_noise_fill_kernel / lat_noise_fill_cyclic_kernel (one Philox evaluation per four elements) -- the path of
+//     the benchmarked configurations;
+//   lat_fwd_kernel / lat_bwd_kernel (first half): run-time shapes (any case / preset / MC count), 256 threads per tile,
+//     intermediates in shared-memory planes, noise per element, tile-ordered noise record for the backward.
+//   lat_encode_kernel: encode-only inference of the fp32 mode (one thread per pair).
 #include <cuda_fp16.h>
 #include <curand_kernel.h>
 
