@@ -592,7 +592,7 @@ size_t dpivae_workspace_bytes(dpivae_handle_t h, int64_t B, int32_t n_mc) {
 
 static int run_loss(dpivae_handle_t h, const dpivae_batch_t* bt, const dpivae_rng_t* rng, const dpivae_loss_weights_t* w,
                     int with_grad, int latent_only, int x_std, const dpivae_outputs_t* out, void* ws, size_t ws_bytes,
-                    cudaStream_t st) {
+                    cudaStream_t st, const AdamParams* fuse_adam = nullptr) {
   if (!h || !bt || !rng) return fail("null argument");
   if (!h->params) return fail("dpivae_bind has not been called");
   if (bt->B < 1 || bt->n_mc < 1 || bt->B_global < bt->B) return fail("bad batch sizes");
@@ -818,6 +818,8 @@ static int run_loss(dpivae_handle_t h, const dpivae_batch_t* bt, const dpivae_rn
     R.scalars = (out && out->scalars) ? out->scalars : scal;
     R.inv_B = 1.0f / (float)bt->B_global;
     R.inv_BD = 1.0f / ((float)bt->B_global * (float)(h->d.nd_x + h->d.nd_c + h->d.nd_y));
+    R.fuse_adam = 0;
+    if (fuse_adam && with_grad) { R.fuse_adam = 1; R.adam = *fuse_adam; }
     { KTimer t(h, 3, st); launch_reduce(R, st); }
     ++launches;
   }
@@ -831,23 +833,15 @@ int dpivae_loss(dpivae_handle_t h, const dpivae_batch_t* batch, const dpivae_rng
   return run_loss(h, batch, rng, w, with_grad, 0, 0, out, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+static void fill_adam(dpivae_handle_t h, int64_t step, AdamParams& A);
+
 int dpivae_adam_step(dpivae_handle_t h, int64_t step, float max_grad_norm, void* stream) {
   if (!h || !h->params || !h->grads || !h->m || !h->v) return fail("Adam needs bound params / grads / exp_avg / exp_avg_sq");
   if (step < 1) return fail("step is 1-based");
   cudaStream_t st = (cudaStream_t)stream;
   int launches = 0;
   AdamParams A;
-  memset(&A, 0, sizeof(A));
-  A.params = h->params; A.grads = h->grads; A.m = h->m; A.v = h->v; A.group = h->d_group;
-  const double b1 = 0.9, b2 = 0.999;
-  const double bc1 = 1.0 - pow(b1, (double)step), bc2 = 1.0 - pow(b2, (double)step);
-  for (int g = 0; g < h->n_groups; ++g) { A.step_size[g] = (float)((double)h->lr[g] / bc1); A.wd[g] = h->wd[g]; }
-  A.bc2_sqrt = (float)sqrt(bc2);
-  A.beta1 = 0.9f; A.beta2 = 0.999f; A.eps = 1e-8f;
-  A.n_params = h->d.n_params;
-  A.clip_coef = nullptr;
-  A.ss = h->cur_ss; A.log = h->cur_log; A.log_cap = h->cur_log_cap; A.lsx_index = h->d.log_sigma_x;
-  A.scalars = h->grads + h->d.n_params;   // captured-step mode requires the [grads | 8 scalars] layout (checked there)
+  fill_adam(h, step, A);
   if (max_grad_norm > 0.0f) {
     launch_gradnorm(h->grads, h->d.n_params, max_grad_norm, h->d_clip, st);
     A.clip_coef = h->d_clip;
@@ -861,9 +855,31 @@ int dpivae_adam_step(dpivae_handle_t h, int64_t step, float max_grad_norm, void*
   return 0;
 }
 
+static void fill_adam(dpivae_handle_t h, int64_t step, AdamParams& A) {
+  memset(&A, 0, sizeof(A));
+  A.params = h->params; A.grads = h->grads; A.m = h->m; A.v = h->v; A.group = h->d_group;
+  const double b1 = 0.9, b2 = 0.999;
+  const double bc1 = 1.0 - pow(b1, (double)step), bc2 = 1.0 - pow(b2, (double)step);
+  for (int g = 0; g < h->n_groups; ++g) { A.step_size[g] = (float)((double)h->lr[g] / bc1); A.wd[g] = h->wd[g]; }
+  A.bc2_sqrt = (float)sqrt(bc2);
+  A.beta1 = 0.9f; A.beta2 = 0.999f; A.eps = 1e-8f;
+  A.n_params = h->d.n_params;
+  A.clip_coef = nullptr;
+  A.ss = h->cur_ss; A.log = h->cur_log; A.log_cap = h->cur_log_cap; A.lsx_index = h->d.log_sigma_x;
+  A.scalars = h->grads + h->d.n_params;   // captured-step mode requires the [grads | 8 scalars] layout (checked there)
+}
+
 int dpivae_train_step(dpivae_handle_t h, const dpivae_batch_t* batch, const dpivae_rng_t* rng, const dpivae_loss_weights_t* w,
                       int64_t step, float max_grad_norm, const dpivae_outputs_t* out, void* workspace,
                       size_t workspace_bytes, void* stream) {
+  // no gradient clipping: the Adam update rides on the gradient reduction (one launch, one pass over the gradients less)
+  static const bool no_fuse = getenv("DPIVAE_NO_FUSED_ADAM") != nullptr;
+  if (!(max_grad_norm > 0.0f) && !no_fuse && h && h->params && h->grads && h->m && h->v && step >= 1) {
+    AdamParams A;
+    fill_adam(h, step, A);
+    h->ev_used[4] = 0;
+    return run_loss(h, batch, rng, w, 1, 0, 0, out, workspace, workspace_bytes, (cudaStream_t)stream, &A);
+  }
   if (run_loss(h, batch, rng, w, 1, 0, 0, out, workspace, workspace_bytes, (cudaStream_t)stream)) return 1;
   const int l0 = h->last_launches;
   if (dpivae_adam_step(h, step, max_grad_norm, stream)) return 1;

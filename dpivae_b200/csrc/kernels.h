@@ -226,18 +226,6 @@ void launch_enc_tc_fwd(const EncTcParams& p, int grid, cudaStream_t s);
 int configure_enc_tc_kernels();
 
 // ---- reduce + Adam ------------------------------------------------------------------------------
-struct ReduceParams {
-  const float* part;
-  long long part_stride;
-  int n_cta[3];                 // number of CTA partials per owner class
-  long long base[3];            // first partial vector (in units of part_stride) of each owner class
-  long long n_params;
-  const unsigned char* owner;   // per param: 0 = decoder kernel, 1 = prior-net units, 2 = encoder units
-  float* grads;
-  float* scalars;               // 8 floats
-  float inv_B, inv_BD;
-};
-
 struct AdamParams {
   float* params;
   const float* grads;
@@ -255,6 +243,22 @@ struct AdamParams {
   float* log;                   // [log_cap][9] ring, or nullptr
   long long log_cap;
   long long lsx_index;
+};
+
+struct ReduceParams {
+  const float* part;
+  long long part_stride;
+  int n_cta[3];                 // number of CTA partials per owner class
+  long long base[3];            // first partial vector (in units of part_stride) of each owner class
+  long long n_params;
+  const unsigned char* owner;   // per param: 0 = decoder kernel, 1 = prior-net units, 2 = encoder units
+  float* grads;
+  float* scalars;               // 8 floats
+  float inv_B, inv_BD;
+  // single-shard train step without gradient clipping: the Adam update of a parameter is applied by the thread that just
+  // reduced its gradient (one launch and one pass over the gradients less); `adam` is ignored unless fuse_adam != 0
+  int fuse_adam;
+  AdamParams adam;
 };
 
 struct AdvanceParams {

@@ -11,6 +11,7 @@ namespace dpv {
 // Thread (parameter lane, row group): 32 consecutive parameters per block (coalesced partial rows), the CTA rows
 // split over 8 row groups with 4 independent accumulators each, combined through shared memory in a fixed order
 // (deterministic; the serial 148..296-load chain per parameter made this kernel latency-bound at 70 us).
+__device__ __forceinline__ void adam_update(const AdamParams& P, long long i, float g);
 constexpr int RED_P = 32, RED_G = 8;
 __global__ void __launch_bounds__(RED_P * RED_G) reduce_kernel(const ReduceParams P) {
   __shared__ float sm[RED_G][RED_P];
@@ -39,6 +40,7 @@ __global__ void __launch_bounds__(RED_P * RED_G) reduce_kernel(const ReduceParam
 #pragma unroll
     for (int g = 1; g < RED_G; ++g) t += sm[g][lane];
     P.grads[i] = t;
+    if (P.fuse_adam) adam_update(P.adam, i, t);
   }
   if (blockIdx.x == 0 && P.scalars != nullptr) {
     // the 6 loss sums: 32 row groups per scalar, then a fixed-order sum of the 32 partials
@@ -57,6 +59,12 @@ __global__ void __launch_bounds__(RED_P * RED_G) reduce_kernel(const ReduceParam
       if (kk == 0) P.scalars[0] = tot * P.inv_BD;
       else if (kk == 1) { P.scalars[1] = tot * P.inv_B; P.scalars[2] = 0.0f; P.scalars[3] = 0.0f; }
       else P.scalars[kk + 2] = tot * P.inv_B;
+      if (P.fuse_adam && P.adam.log != nullptr && P.adam.ss != nullptr) {   // captured-step log row (what adam_kernel copies otherwise)
+        float* row = P.adam.log + ((P.adam.ss->step - 1) % P.adam.log_cap) * 9;
+        if (kk == 0) row[0] = tot * P.inv_BD;
+        else if (kk == 1) { row[1] = tot * P.inv_B; row[2] = 0.0f; row[3] = 0.0f; }
+        else row[kk + 2] = tot * P.inv_B;
+      }
     }
   }
 }
@@ -79,15 +87,10 @@ __global__ void __launch_bounds__(1024) gradnorm_kernel(const float* __restrict_
   }
 }
 
-__global__ void __launch_bounds__(256) adam_kernel(const AdamParams P) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P.n_params) return;
+// torch.optim.Adam arithmetic for parameter i with gradient g (weight decay, exp_avg / exp_avg_sq, bias-corrected step);
+// in captured-step mode also the log_sigma_x entry of the step's log row
+__device__ __forceinline__ void adam_update(const AdamParams& P, long long i, float g) {
   const int gid = P.group[i];
-  float g = P.grads[i];
-  if (P.clip_coef != nullptr) {
-    g *= *P.clip_coef;
-    const_cast<float*>(P.grads)[i] = g;
-  }
   const float p = P.params[i];
   const float wd = P.wd[gid];
   if (wd != 0.0f) g = fmaf(wd, p, g);
@@ -101,12 +104,20 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamParams P) {
   P.params[i] = pn;
   P.m[i] = m;
   P.v[i] = v;
-  if (P.log != nullptr && P.ss != nullptr) {
-    // per-step log row of the device-resident loop (dpivae.py:439-451): 8 loss scalars + log_sigma_x after the update
-    float* row = P.log + ((P.ss->step - 1) % P.log_cap) * 9;
-    if (i < 8) row[i] = P.scalars[i];
-    if (i == P.lsx_index) row[8] = pn;
+  if (P.log != nullptr && P.ss != nullptr && i == P.lsx_index) P.log[((P.ss->step - 1) % P.log_cap) * 9 + 8] = pn;
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(const AdamParams P) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.n_params) return;
+  float g = P.grads[i];
+  if (P.clip_coef != nullptr) {
+    g *= *P.clip_coef;
+    const_cast<float*>(P.grads)[i] = g;
   }
+  adam_update(P, i, g);
+  // per-step log row of the device-resident loop (dpivae.py:439-451): 8 loss scalars (+ log_sigma_x after the update, above)
+  if (P.log != nullptr && P.ss != nullptr && i < 8) P.log[((P.ss->step - 1) % P.log_cap) * 9 + i] = P.scalars[i];
 }
 
 // Head of a captured step: advance the device-resident step state and stage the step's minibatch indices.
