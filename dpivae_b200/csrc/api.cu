@@ -638,7 +638,7 @@ static int run_loss(dpivae_handle_t h, const dpivae_batch_t* bt, const dpivae_rn
   const size_t enc_smem = enc_smem_bytes(h->enc, true);
   for (int k = 0; k < 4; ++k) h->ev_used[k] = 0;
   h->ev_used[5] = h->ev_used[6] = 0;
-  if (use_tc && with_grad) CUDA_OK(cudaMemsetAsync(base + L.gmax, 0, 4, st));   // max |gpre| of this batch (lat_bwd -> enc_tc_bwd)
+  // (max |gpre| of this batch, lat_bwd -> enc_tc_bwd: zeroed by the latent forward kernel, which precedes both)
   // encoder forward: tensor-core kernel for the encoder units (+ the FFMA kernel for the two prior nets) in the
   // tensor-core math modes when no backward follows; the FFMA kernel for everything otherwise
   const bool enc_tc = h->math_mode != DPIVAE_MATH_FP32 && h->enc_tc_ok && (!with_grad || h->enc_tc_bwd_ok);

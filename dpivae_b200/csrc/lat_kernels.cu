@@ -246,6 +246,7 @@ template <class D>
 __global__ void __launch_bounds__(LNT) lat_fwd_kernel(const __grid_constant__ DecParams P) {
   extern __shared__ __align__(16) float lsm[];
   pdl_launch_dependents();   // the decoder kernel may stage its weights while these tiles are processed
+  if (blockIdx.x == 0 && threadIdx.x == 0 && P.gpre_max != nullptr) *P.gpre_max = 0u;   // batch maximum of |gpre|: lat_bwd accumulates it
   const LatSmem S = lat_carve(lsm, P, false);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, hh = warp >> 2, p = 32 * q + lane;
@@ -832,6 +833,7 @@ __global__ void __launch_bounds__(PNT) lat_pair_fwd_kernel(const __grid_constant
   constexpr int n = D::cn_mc, RB = TP / n, Z = D::cZ, NX = D::cNX, nzd = D::cnzd, nb = D::cnb, ndc = D::cndc, ndy = D::cndy;
   constexpr int nzin = NX + D::cndp, c1 = nzd, cs0 = nzd + 1, NF = D::cn_rowpar, rpM = Z + D::cnL, rpS = rpM + nzd;
   static_assert((n & (n - 1)) == 0 && n <= 32 && RB <= RBMAX, "MC count must be a power of two that fills whole warps");
+  if (blockIdx.x == 0 && threadIdx.x == 0 && P.gpre_max != nullptr) *P.gpre_max = 0u;   // batch maximum of |gpre|: lat_bwd accumulates it
   LatSmem S;
   S.ROWPAR = lsm;
   S.ROWAUX = S.ROWPAR + NF * RBMAX;
